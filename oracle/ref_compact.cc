@@ -1,0 +1,357 @@
+// oracle/ref_compact.cc — drives the UNMODIFIED reference (oracle/_ref/libtoplingdb_ref.so) through
+// its public DB API so that the reference's own FlushJob / CompactionJob::Run ->
+// ProcessKeyValueCompaction (db/compaction/compaction_job.cc:642,1390) produce the input and output
+// SSTs that this repo's CUDA path is compared against byte for byte.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing in the product (toplingdb_b200/) links or executes this.
+//
+// usage: ref_compact <ops.bin> <workdir> [key=value ...]
+//   ops.bin  : write script (see oracle/ops_format.md): PUT/DEL/FLUSH/SNAPSHOT/COMPACT_ALL_TO records
+//   workdir  : receives inputs/NNNNNN.sst (the L0 files fed to the job, newest first),
+//              outputs/NNNNNN.sst, manifest.json (job parameters + CompactionJobStats)
+//   options  : output_level=1 target_file_size=67108864 block_size=4096 restart_interval=16
+//              checksum=xxh3|crc32c max_subcompactions=1 format_version=5 repeat=1 keep_db=0
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "rocksdb/db.h"
+#include "rocksdb/listener.h"
+#include "rocksdb/options.h"
+#include "rocksdb/table.h"
+#include "rocksdb/write_batch.h"
+
+using namespace ROCKSDB_NAMESPACE;
+
+namespace {
+
+struct Opts {
+  int output_level = 1;
+  uint64_t target_file_size = 64ull << 20;
+  uint64_t block_size = 4096;
+  int restart_interval = 16;
+  std::string checksum = "xxh3";
+  uint32_t max_subcompactions = 1;
+  uint32_t format_version = 5;
+  int keep_db = 0;
+  int paranoid = 0;
+};
+
+void Die(const char* what, const Status& s) {
+  fprintf(stderr, "ref_compact: %s: %s\n", what, s.ToString().c_str());
+  exit(2);
+}
+
+std::string Hex(const std::string& s) {
+  static const char* d = "0123456789abcdef";
+  std::string r;
+  for (unsigned char c : s) {
+    r.push_back(d[c >> 4]);
+    r.push_back(d[c & 15]);
+  }
+  return r;
+}
+
+void CopyFile(const std::string& from, const std::string& to) {
+  std::ifstream in(from, std::ios::binary);
+  std::ofstream out(to, std::ios::binary);
+  out << in.rdbuf();
+  if (!in.good() && !in.eof()) {
+    fprintf(stderr, "ref_compact: copy %s failed\n", from.c_str());
+    exit(2);
+  }
+}
+
+class StatsListener : public EventListener {
+ public:
+  CompactionJobInfo last;
+  int completed = 0;
+  void OnCompactionCompleted(DB*, const CompactionJobInfo& ci) override {
+    last = ci;
+    completed++;
+  }
+};
+
+struct Reader {
+  FILE* f;
+  bool u8(uint8_t* v) { return fread(v, 1, 1, f) == 1; }
+  uint32_t u32() {
+    uint32_t v = 0;
+    if (fread(&v, 4, 1, f) != 1) {
+      fprintf(stderr, "ref_compact: truncated ops file\n");
+      exit(2);
+    }
+    return v;
+  }
+  void bytes(std::string* s, size_t n) {
+    s->resize(n);
+    if (n && fread(&(*s)[0], 1, n, f) != n) {
+      fprintf(stderr, "ref_compact: truncated ops file\n");
+      exit(2);
+    }
+  }
+};
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 3) {
+    fprintf(stderr, "usage: ref_compact <ops.bin> <workdir> [key=value ...]\n");
+    return 1;
+  }
+  Opts o;
+  for (int i = 3; i < argc; i++) {
+    std::string a = argv[i];
+    size_t eq = a.find('=');
+    if (eq == std::string::npos) continue;
+    std::string k = a.substr(0, eq), v = a.substr(eq + 1);
+    if (k == "output_level") o.output_level = atoi(v.c_str());
+    else if (k == "target_file_size") o.target_file_size = strtoull(v.c_str(), nullptr, 0);
+    else if (k == "block_size") o.block_size = strtoull(v.c_str(), nullptr, 0);
+    else if (k == "restart_interval") o.restart_interval = atoi(v.c_str());
+    else if (k == "checksum") o.checksum = v;
+    else if (k == "max_subcompactions") o.max_subcompactions = (uint32_t)atoi(v.c_str());
+    else if (k == "format_version") o.format_version = (uint32_t)atoi(v.c_str());
+    else if (k == "keep_db") o.keep_db = atoi(v.c_str());
+    else if (k == "paranoid") o.paranoid = atoi(v.c_str());
+    else {
+      fprintf(stderr, "ref_compact: unknown option %s\n", k.c_str());
+      return 1;
+    }
+  }
+  const std::string work = argv[2];
+  const std::string dbdir = work + "/db";
+  mkdir(work.c_str(), 0755);
+  mkdir((work + "/inputs").c_str(), 0755);
+  mkdir((work + "/outputs").c_str(), 0755);
+
+  Options opt;
+  opt.create_if_missing = true;
+  opt.disable_auto_compactions = true;
+  opt.compression = kNoCompression;
+  opt.bottommost_compression = kDisableCompressionOption;
+  opt.compression_per_level.clear();
+  opt.num_levels = 7;
+  opt.write_buffer_size = size_t(8) << 30;  // flushes happen only where the script says FLUSH
+  opt.max_write_buffer_number = 4;
+  opt.level0_file_num_compaction_trigger = 1 << 20;
+  opt.level0_slowdown_writes_trigger = 1 << 20;
+  opt.level0_stop_writes_trigger = 1 << 20;
+  opt.target_file_size_base = o.target_file_size;
+  opt.max_subcompactions = o.max_subcompactions;
+  opt.max_background_jobs = 2;
+  opt.paranoid_file_checks = o.paranoid != 0;
+  opt.info_log_level = WARN_LEVEL;
+  opt.stats_dump_period_sec = 0;
+  opt.stats_persist_period_sec = 0;
+  BlockBasedTableOptions t;
+  t.block_size = o.block_size;
+  t.block_restart_interval = o.restart_interval;
+  t.format_version = o.format_version;
+  t.checksum = o.checksum == "crc32c" ? kCRC32c : kXXH3;
+  t.no_block_cache = true;
+  opt.table_factory.reset(NewBlockBasedTableFactory(t));
+  auto listener = std::make_shared<StatsListener>();
+  opt.listeners.push_back(listener);
+
+  DestroyDB(dbdir, opt).PermitUncheckedError();
+  DB* db = nullptr;
+  Status s = DB::Open(opt, dbdir, &db);
+  if (!s.ok()) Die("open", s);
+
+  FILE* f = fopen(argv[1], "rb");
+  if (!f) {
+    perror(argv[1]);
+    return 2;
+  }
+  char magic[8];
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "B2OPS\0\0\1", 8) != 0) {
+    fprintf(stderr, "ref_compact: bad ops magic\n");
+    return 2;
+  }
+  Reader rd{f};
+  std::vector<const Snapshot*> snaps;
+  WriteOptions wo;
+  wo.disableWAL = true;
+  WriteBatch batch;
+  size_t batch_n = 0;
+  auto flush_batch = [&]() {
+    if (batch_n) {
+      Status ws = db->Write(wo, &batch);
+      if (!ws.ok()) Die("write", ws);
+      batch.Clear();
+      batch_n = 0;
+    }
+  };
+  std::string key, val;
+  uint8_t op;
+  while (rd.u8(&op) && op != 0) {
+    switch (op) {
+      case 1: {
+        uint32_t kl = rd.u32(), vl = rd.u32();
+        rd.bytes(&key, kl);
+        rd.bytes(&val, vl);
+        batch.Put(key, val);
+        if (++batch_n >= 4096) flush_batch();
+        break;
+      }
+      case 2: {
+        uint32_t kl = rd.u32();
+        rd.bytes(&key, kl);
+        batch.Delete(key);
+        if (++batch_n >= 4096) flush_batch();
+        break;
+      }
+      case 3: {
+        flush_batch();
+        FlushOptions fo;
+        fo.wait = true;
+        s = db->Flush(fo);
+        if (!s.ok()) Die("flush", s);
+        break;
+      }
+      case 4:
+        flush_batch();
+        snaps.push_back(db->GetSnapshot());
+        break;
+      case 5: {
+        uint8_t lvl;
+        rd.u8(&lvl);
+        flush_batch();
+        std::vector<LiveFileMetaData> live;
+        db->GetLiveFilesMetaData(&live);
+        std::vector<std::string> names;
+        for (auto& m : live) names.push_back(m.name);
+        if (!names.empty()) {
+          CompactionOptions co;
+          co.compression = kNoCompression;
+          co.output_file_size_limit = UINT64_MAX;
+          s = db->CompactFiles(co, names, lvl);
+          if (!s.ok()) Die("setup compaction", s);
+        }
+        break;
+      }
+      default:
+        fprintf(stderr, "ref_compact: bad op %u\n", op);
+        return 2;
+    }
+  }
+  flush_batch();
+  fclose(f);
+
+  // The job: every L0 file -> output_level.  Input order = newest L0 file first, which is the
+  // order VersionSet::MakeInputIterator hands the children to the merging iterator
+  // (db/version_set.cc:7298-7320).
+  ColumnFamilyMetaData cfm;
+  db->GetColumnFamilyMetaData(&cfm);
+  std::vector<std::string> input_names;
+  std::vector<SstFileMetaData> inputs;
+  bool deeper_files = false;
+  for (auto& lvl : cfm.levels) {
+    if (lvl.level == 0) {
+      for (auto& fm : lvl.files) {
+        inputs.push_back(fm);
+        input_names.push_back(fm.name);
+      }
+    } else if (lvl.level > o.output_level && !lvl.files.empty()) {
+      deeper_files = true;
+    } else if (lvl.level > 0 && lvl.level <= o.output_level && !lvl.files.empty()) {
+      fprintf(stderr, "ref_compact: script left files at L%d (<= output level)\n", lvl.level);
+      return 2;
+    }
+  }
+  if (inputs.empty()) {
+    fprintf(stderr, "ref_compact: no L0 files to compact\n");
+    return 2;
+  }
+  for (auto& fm : inputs) CopyFile(dbdir + fm.name, work + "/inputs" + fm.name);
+
+  CompactionOptions co;
+  co.compression = kNoCompression;
+  co.output_file_size_limit = o.target_file_size;
+  co.max_subcompactions = o.max_subcompactions;
+  std::vector<std::string> out_names;
+  CompactionJobInfo ji;
+  auto t0 = std::chrono::steady_clock::now();
+  s = db->CompactFiles(co, input_names, o.output_level, -1, &out_names, &ji);
+  auto t1 = std::chrono::steady_clock::now();
+  if (!s.ok()) Die("compaction", s);
+  double wall_us = std::chrono::duration<double, std::micro>(t1 - t0).count();
+
+  std::string db_id, session_id;
+  db->GetDbIdentity(db_id).PermitUncheckedError();
+  db->GetDbSessionId(session_id).PermitUncheckedError();
+
+  FILE* m = fopen((work + "/manifest.json").c_str(), "w");
+  fprintf(m, "{\n  \"reference\": \"toplingdb (rocksdb %d.%d.%d)\",\n", ROCKSDB_MAJOR, ROCKSDB_MINOR,
+          ROCKSDB_PATCH);
+  fprintf(m, "  \"output_level\": %d,\n  \"target_file_size\": %" PRIu64 ",\n", o.output_level,
+          o.target_file_size);
+  fprintf(m, "  \"block_size\": %" PRIu64 ",\n  \"restart_interval\": %d,\n  \"format_version\": %u,\n",
+          o.block_size, o.restart_interval, o.format_version);
+  fprintf(m, "  \"checksum\": \"%s\",\n  \"max_subcompactions\": %u,\n", o.checksum.c_str(),
+          o.max_subcompactions);
+  fprintf(m, "  \"bottommost_level\": %s,\n", deeper_files ? "false" : "true");
+  fprintf(m, "  \"db_id\": \"%s\",\n  \"db_session_id\": \"%s\",\n", db_id.c_str(), session_id.c_str());
+  fprintf(m, "  \"snapshots\": [");
+  for (size_t i = 0; i < snaps.size(); i++)
+    fprintf(m, "%s%" PRIu64, i ? ", " : "", snaps[i]->GetSequenceNumber());
+  fprintf(m, "],\n  \"inputs\": [\n");
+  for (size_t i = 0; i < inputs.size(); i++) {
+    auto& fm = inputs[i];
+    fprintf(m,
+            "    {\"name\": \"%s\", \"level\": 0, \"size\": %" PRIu64 ", \"file_number\": %" PRIu64
+            ", \"smallest_seqno\": %" PRIu64 ", \"largest_seqno\": %" PRIu64 ", \"num_entries\": %" PRIu64
+            ", \"num_deletions\": %" PRIu64 "}%s\n",
+            fm.name.c_str(), fm.size, fm.file_number, fm.smallest_seqno, fm.largest_seqno, fm.num_entries,
+            fm.num_deletions, i + 1 < inputs.size() ? "," : "");
+  }
+  fprintf(m, "  ],\n  \"outputs\": [\n");
+  db->GetColumnFamilyMetaData(&cfm);
+  std::vector<SstFileMetaData> outs;
+  for (auto& lvl : cfm.levels)
+    if (lvl.level == o.output_level)
+      for (auto& fm : lvl.files) outs.push_back(fm);
+  for (size_t i = 0; i < outs.size(); i++) {
+    auto& fm = outs[i];
+    CopyFile(dbdir + fm.name, work + "/outputs" + fm.name);
+    fprintf(m,
+            "    {\"name\": \"%s\", \"size\": %" PRIu64 ", \"file_number\": %" PRIu64
+            ", \"smallest_seqno\": %" PRIu64 ", \"largest_seqno\": %" PRIu64 ", \"num_entries\": %" PRIu64
+            ", \"num_deletions\": %" PRIu64 ", \"smallestkey\": \"%s\", \"largestkey\": \"%s\"}%s\n",
+            fm.name.c_str(), fm.size, fm.file_number, fm.smallest_seqno, fm.largest_seqno, fm.num_entries,
+            fm.num_deletions, Hex(fm.smallestkey).c_str(), Hex(fm.largestkey).c_str(),
+            i + 1 < outs.size() ? "," : "");
+  }
+  const CompactionJobStats& st = ji.stats;
+  fprintf(m, "  ],\n  \"stats\": {\n");
+  fprintf(m, "    \"wall_micros\": %.0f,\n    \"elapsed_micros\": %" PRIu64 ",\n    \"cpu_micros\": %" PRIu64 ",\n",
+          wall_us, st.elapsed_micros, st.cpu_micros);
+  fprintf(m, "    \"num_input_records\": %" PRIu64 ",\n    \"num_output_records\": %" PRIu64 ",\n",
+          st.num_input_records, st.num_output_records);
+  fprintf(m, "    \"total_input_bytes\": %" PRIu64 ",\n    \"total_output_bytes\": %" PRIu64 ",\n",
+          st.total_input_bytes, st.total_output_bytes);
+  fprintf(m, "    \"num_records_replaced\": %" PRIu64 ",\n    \"total_input_raw_key_bytes\": %" PRIu64 ",\n",
+          st.num_records_replaced, st.total_input_raw_key_bytes);
+  fprintf(m, "    \"total_input_raw_value_bytes\": %" PRIu64 ",\n    \"num_input_deletion_records\": %" PRIu64 ",\n",
+          st.total_input_raw_value_bytes, st.num_input_deletion_records);
+  fprintf(m, "    \"num_expired_deletion_records\": %" PRIu64 ",\n    \"num_corrupt_keys\": %" PRIu64 "\n  }\n}\n",
+          st.num_expired_deletion_records, st.num_corrupt_keys);
+  fclose(m);
+
+  for (auto* sn : snaps) db->ReleaseSnapshot(sn);
+  s = db->Close();
+  delete db;
+  if (!o.keep_db) DestroyDB(dbdir, opt).PermitUncheckedError();
+  printf("ok inputs=%zu outputs=%zu elapsed_us=%" PRIu64 " cpu_us=%" PRIu64 " wall_us=%.0f\n", inputs.size(),
+         outs.size(), st.elapsed_micros, st.cpu_micros, wall_us);
+  return 0;
+}
