@@ -1,0 +1,113 @@
+/* oracle/compaction_oracle.h — CPU restatement of ToplingDB's compaction hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is the checker the CUDA path is compared against; nothing under
+ * toplingdb_b200/ may include, link or call it.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it.
+ *
+ * Parity status: PINNED.  The restatement is checked (tests/test_oracle_vs_reference.py and the
+ * committed fixtures under tests/golden/) against (a) the reference's own known-answer vectors
+ * (table/table_test.cc:2303-2389 block checksums, util/crc32c_test.cc:67, util/coding_test.cc,
+ * db/compaction/compaction_iterator_test.cc drop-rule vectors) and (b) byte-for-byte against SST files
+ * produced by the unmodified reference compiled into oracle/_ref (see oracle/Makefile, ref_compact.cc).
+ *
+ * Every function cites the reference file:line it restates (paths relative to /root/reference).
+ */
+#ifndef COMPACTION_ORACLE_H_
+#define COMPACTION_ORACLE_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_TYPE_DELETION = 0, ORC_TYPE_VALUE = 1, ORC_TYPE_MERGE = 2, ORC_TYPE_SINGLE_DELETION = 7 };
+enum { ORC_CKSUM_NONE = 0, ORC_CKSUM_CRC32C = 1, ORC_CKSUM_XXH3 = 4 };
+#define ORC_MAX_SEQ ((1ull << 56) - 1) /* kMaxSequenceNumber, db/dbformat.h:96 */
+#define ORC_VALUE_TYPE_FOR_SEEK 0x16ull  /* kValueTypeForSeek = kTypeWideColumnEntity, db/dbformat.cc:29 */
+
+/* Job description: the subset of CompactionParams (db/compaction/compaction_executor.h:33-118),
+ * BlockBasedTableOptions (include/rocksdb/table.h:237-564) and TableBuilderOptions
+ * (db/compaction/compaction_job.cc:2323-2331) that shapes the output bytes. */
+typedef struct orc_params {
+  int32_t output_level;
+  int32_t bottommost_level;        /* Compaction::bottommost_level() */
+  uint64_t max_output_file_size;   /* compaction.cc:291-295 */
+  uint32_t block_size;             /* 4096 */
+  uint32_t block_size_deviation;   /* 10 */
+  uint32_t block_restart_interval; /* 16 */
+  uint32_t index_block_restart_interval; /* 1 */
+  uint32_t format_version;         /* 5 */
+  uint32_t checksum_type;          /* ORC_CKSUM_* */
+  const uint64_t* snapshots;       /* ascending (existing_snapshots) */
+  uint32_t num_snapshots;
+  uint32_t column_family_id;
+  const char* column_family_name;
+  const char* db_id;
+  const char* db_session_id;
+  const char* db_host_id;
+  uint64_t creation_time;          /* rocksdb.creation.time (oldest ancestor time) */
+  uint64_t oldest_key_time;
+  const uint64_t* file_creation_times; /* one per output file; last repeats */
+  uint32_t num_file_creation_times;
+  uint64_t first_file_number;      /* outputs are numbered consecutively from here */
+} orc_params;
+
+typedef struct orc_file_meta { /* FileMinMeta, compaction_executor.h:120-131 + table properties */
+  uint64_t file_number, file_size;
+  uint64_t smallest_seqno, largest_seqno;
+  uint64_t num_entries, num_deletions, raw_key_size, raw_value_size, num_data_blocks;
+  uint32_t smallest_len, largest_len;
+  uint8_t smallest[256], largest[256]; /* internal keys (truncated copies if longer) */
+} orc_file_meta;
+
+typedef struct orc_stats { /* CompactionJobStats subset, include/rocksdb/compaction_job_stats.h */
+  uint64_t num_input_records, num_output_records;
+  uint64_t num_input_deletion_records;
+  uint64_t num_records_replaced;          /* num_record_drop_hidden */
+  uint64_t num_expired_deletion_records;  /* num_record_drop_obsolete */
+  uint64_t total_input_raw_key_bytes, total_input_raw_value_bytes;
+  uint64_t num_optimized_del_drop_obsolete;
+} orc_stats;
+
+typedef struct orc_result orc_result;
+
+/* leaf utilities */
+uint32_t orc_crc32c_value(const void* data, size_t n);                    /* util/crc32c.h:25-33 */
+uint32_t orc_crc32c_extend(uint32_t crc, const void* data, size_t n);
+uint32_t orc_crc32c_mask(uint32_t crc);                                   /* util/crc32c.h:37-42 */
+uint64_t orc_xxh3_64(const void* data, size_t n);                         /* util/xxhash.h XXH3_64bits */
+uint32_t orc_block_checksum(uint32_t type, const void* data, size_t n, uint8_t last_byte); /* table/format.cc:468-509 */
+uint32_t orc_checksum(uint32_t type, const void* data, size_t n);         /* table/format.cc:442-466 */
+int orc_put_varint64(uint8_t* dst, uint64_t v);                           /* util/coding.h */
+int orc_internal_key_less(const uint8_t* a, size_t an, const uint8_t* b, size_t bn); /* db/dbformat.h:1057-1097 */
+size_t orc_shortest_separator(uint8_t* start, size_t start_len, const uint8_t* limit, size_t limit_len); /* index_builder.cc:77-94 */
+
+/* "kv stream": repeated { u32 ikey_len, u32 value_len, ikey bytes, value bytes }, little endian. */
+
+/* Decode every entry of a BlockBasedTable file (verifying block checksums) into a kv stream.
+ * returns 0 or a negative error; *out is malloc'd. */
+int orc_sst_to_kvstream(const uint8_t* file, size_t len, uint8_t** out, size_t* out_len, uint64_t* num_entries);
+
+/* Build ONE BlockBasedTable file from a sorted kv stream (BlockBasedTableBuilder::Add/Finish). */
+int orc_build_sst(const orc_params* p, const uint8_t* kv, size_t kv_len, uint8_t** out, size_t* out_len);
+
+/* CompactionIterator over an already merged kv stream; emits the surviving kv stream. */
+int orc_compaction_iterator(const orc_params* p, const uint8_t* kv, size_t kv_len, uint8_t** out, size_t* out_len,
+                            orc_stats* stats);
+
+/* Whole job: decode inputs (inputs[0] = newest L0 run first), k-way merge, drop rules, encode. */
+int orc_compact(const orc_params* p, int n_inputs, const uint8_t* const* inputs, const uint64_t* input_lens,
+                orc_result** out);
+int orc_result_num_files(const orc_result* r);
+const uint8_t* orc_result_file(const orc_result* r, int i, uint64_t* len);
+void orc_result_meta(const orc_result* r, int i, orc_file_meta* m);
+void orc_result_stats(const orc_result* r, orc_stats* s);
+void orc_result_free(orc_result* r);
+void orc_free(void* p);
+const char* orc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,311 @@
+"""Test helpers: ctypes view of the CPU oracle (oracle/liboracle.so), the ops-script writer and the
+driver for the compiled reference (oracle/_ref/ref_compact).  Test infrastructure only."""
+import ctypes as C
+import json
+import os
+import shutil
+import struct
+import subprocess
+import tempfile
+
+import sstfmt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_compact")
+MAX_SEQ = (1 << 56) - 1
+CKSUM = {"none": 0, "crc32c": 1, "xxh3": 4}
+
+
+class OrcParams(C.Structure):
+    _fields_ = [
+        ("output_level", C.c_int32), ("bottommost_level", C.c_int32), ("max_output_file_size", C.c_uint64),
+        ("block_size", C.c_uint32), ("block_size_deviation", C.c_uint32), ("block_restart_interval", C.c_uint32),
+        ("index_block_restart_interval", C.c_uint32), ("format_version", C.c_uint32), ("checksum_type", C.c_uint32),
+        ("snapshots", C.POINTER(C.c_uint64)), ("num_snapshots", C.c_uint32), ("column_family_id", C.c_uint32),
+        ("column_family_name", C.c_char_p), ("db_id", C.c_char_p), ("db_session_id", C.c_char_p),
+        ("db_host_id", C.c_char_p), ("creation_time", C.c_uint64), ("oldest_key_time", C.c_uint64),
+        ("file_creation_times", C.POINTER(C.c_uint64)), ("num_file_creation_times", C.c_uint32),
+        ("first_file_number", C.c_uint64),
+    ]
+
+
+class OrcFileMeta(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("file_number", "file_size", "smallest_seqno", "largest_seqno", "num_entries",
+                                          "num_deletions", "raw_key_size", "raw_value_size", "num_data_blocks")] + [
+        ("smallest_len", C.c_uint32), ("largest_len", C.c_uint32), ("smallest", C.c_uint8 * 256),
+        ("largest", C.c_uint8 * 256)]
+
+
+class OrcStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("num_input_records", "num_output_records", "num_input_deletion_records",
+                                          "num_records_replaced", "num_expired_deletion_records",
+                                          "total_input_raw_key_bytes", "total_input_raw_value_bytes",
+                                          "num_optimized_del_drop_obsolete")]
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+        L = C.CDLL(ORACLE_SO)
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_xxh3_64.restype = C.c_uint64
+        L.orc_xxh3_64.argtypes = [C.c_char_p, C.c_size_t]
+        for f in ("orc_crc32c_value",):
+            getattr(L, f).restype = C.c_uint32
+            getattr(L, f).argtypes = [C.c_char_p, C.c_size_t]
+        L.orc_crc32c_mask.restype = C.c_uint32
+        L.orc_crc32c_mask.argtypes = [C.c_uint32]
+        L.orc_block_checksum.restype = C.c_uint32
+        L.orc_block_checksum.argtypes = [C.c_uint32, C.c_char_p, C.c_size_t, C.c_uint8]
+        L.orc_checksum.restype = C.c_uint32
+        L.orc_checksum.argtypes = [C.c_uint32, C.c_char_p, C.c_size_t]
+        L.orc_result_file.restype = C.POINTER(C.c_uint8)
+        L.orc_shortest_separator.restype = C.c_size_t
+        _oracle = L
+    return _oracle
+
+
+class Params:
+    """Python-side job description; .c() gives the ctypes struct (keeps referenced arrays alive)."""
+
+    def __init__(self, **kw):
+        self.output_level = 1
+        self.bottommost_level = True
+        self.max_output_file_size = 64 << 20
+        self.block_size = 4096
+        self.block_size_deviation = 10
+        self.block_restart_interval = 16
+        self.index_block_restart_interval = 1
+        self.format_version = 5
+        self.checksum = "xxh3"
+        self.snapshots = []
+        self.column_family_id = 0
+        self.column_family_name = "default"
+        self.db_id = "b200c-test-db"
+        self.db_session_id = "B200CSESSION00000000"
+        self.db_host_id = "b200"
+        self.creation_time = 1700000000
+        self.oldest_key_time = 0
+        self.file_creation_times = [1700000001]
+        self.first_file_number = 100
+        for k, v in kw.items():
+            assert hasattr(self, k), k
+            setattr(self, k, v)
+
+    def c(self):
+        p = OrcParams()
+        p.output_level = self.output_level
+        p.bottommost_level = int(self.bottommost_level)
+        p.max_output_file_size = self.max_output_file_size
+        p.block_size = self.block_size
+        p.block_size_deviation = self.block_size_deviation
+        p.block_restart_interval = self.block_restart_interval
+        p.index_block_restart_interval = self.index_block_restart_interval
+        p.format_version = self.format_version
+        p.checksum_type = CKSUM[self.checksum]
+        self._snaps = (C.c_uint64 * max(1, len(self.snapshots)))(*self.snapshots)
+        p.snapshots = C.cast(self._snaps, C.POINTER(C.c_uint64))
+        p.num_snapshots = len(self.snapshots)
+        p.column_family_id = self.column_family_id
+        p.column_family_name = self.column_family_name.encode()
+        p.db_id = self.db_id.encode()
+        p.db_session_id = self.db_session_id.encode()
+        p.db_host_id = self.db_host_id.encode()
+        p.creation_time = self.creation_time
+        p.oldest_key_time = self.oldest_key_time
+        self._fct = (C.c_uint64 * max(1, len(self.file_creation_times)))(*self.file_creation_times)
+        p.file_creation_times = C.cast(self._fct, C.POINTER(C.c_uint64))
+        p.num_file_creation_times = len(self.file_creation_times)
+        p.first_file_number = self.first_file_number
+        return p
+
+
+def ikey(user_key: bytes, seq: int, vtype: int = 1) -> bytes:
+    return user_key + struct.pack("<Q", (seq << 8) | vtype)
+
+
+def kvstream(entries):
+    """entries: iterable of (internal_key, value) -> kv stream bytes"""
+    out = bytearray()
+    for k, v in entries:
+        out += struct.pack("<II", len(k), len(v)) + k + v
+    return bytes(out)
+
+
+def parse_kvstream(b):
+    out = []
+    p = 0
+    while p + 8 <= len(b):
+        kl, vl = struct.unpack_from("<II", b, p)
+        p += 8
+        out.append((bytes(b[p:p + kl]), bytes(b[p + kl:p + kl + vl])))
+        p += kl + vl
+    return out
+
+
+def _take(ptr, n):
+    return C.string_at(ptr, n) if n else b""
+
+
+def oracle_sst_to_kv(data: bytes):
+    L = oracle()
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t()
+    cnt = C.c_uint64()
+    rc = L.orc_sst_to_kvstream(data, C.c_size_t(len(data)), C.byref(out), C.byref(n), C.byref(cnt))
+    assert rc == 0, (rc, L.orc_last_error())
+    b = _take(out, n.value)
+    L.orc_free(out)
+    return b, cnt.value
+
+
+def oracle_build_sst(params: Params, kv: bytes) -> bytes:
+    L = oracle()
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t()
+    cp = params.c()
+    rc = L.orc_build_sst(C.byref(cp), kv, C.c_size_t(len(kv)), C.byref(out), C.byref(n))
+    assert rc == 0, (rc, L.orc_last_error())
+    b = _take(out, n.value)
+    L.orc_free(out)
+    return b
+
+
+def oracle_citer(params: Params, kv: bytes):
+    L = oracle()
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t()
+    st = OrcStats()
+    cp = params.c()
+    rc = L.orc_compaction_iterator(C.byref(cp), kv, C.c_size_t(len(kv)), C.byref(out), C.byref(n), C.byref(st))
+    if rc != 0:
+        raise RuntimeError((rc, L.orc_last_error()))
+    b = _take(out, n.value)
+    L.orc_free(out)
+    return b, st
+
+
+def oracle_compact(params: Params, inputs):
+    """inputs: list of SST file bytes, newest L0 run first.  Returns (files, metas, stats)."""
+    L = oracle()
+    cp = params.c()
+    n = len(inputs)
+    bufs = [C.create_string_buffer(x, len(x)) for x in inputs]
+    ptrs = (C.c_void_p * max(1, n))(*[C.cast(b, C.c_void_p) for b in bufs])
+    lens = (C.c_uint64 * max(1, n))(*[len(x) for x in inputs])
+    res = C.c_void_p()
+    rc = L.orc_compact(C.byref(cp), n, ptrs, lens, C.byref(res))
+    if rc != 0:
+        raise RuntimeError((rc, L.orc_last_error()))
+    files, metas = [], []
+    for i in range(L.orc_result_num_files(res)):
+        ln = C.c_uint64()
+        ptr = L.orc_result_file(res, i, C.byref(ln))
+        files.append(_take(ptr, ln.value))
+        m = OrcFileMeta()
+        L.orc_result_meta(res, i, C.byref(m))
+        metas.append(m)
+    st = OrcStats()
+    L.orc_result_stats(res, C.byref(st))
+    L.orc_result_free(res)
+    return files, metas, st
+
+
+# ---------------------------------------------------------------- ops scripts + compiled reference
+class Ops:
+    """Write script for oracle/_ref/ref_compact (format: oracle/ops_format.md)."""
+
+    def __init__(self):
+        self.b = bytearray(b"B2OPS\0\0\1")
+
+    def put(self, k, v):
+        self.b += struct.pack("<BII", 1, len(k), len(v)) + k + v
+
+    def delete(self, k):
+        self.b += struct.pack("<BI", 2, len(k)) + k
+
+    def flush(self):
+        self.b += b"\x03"
+
+    def snapshot(self):
+        self.b += b"\x04"
+
+    def compact_all_to(self, level):
+        self.b += bytes([5, level])
+
+    def bytes(self):
+        return bytes(self.b) + b"\x00"
+
+
+def have_ref():
+    return os.path.exists(REF_BIN)
+
+
+def run_reference(ops: Ops, workdir=None, **opts):
+    """Run the compiled reference on an ops script.  Returns dict(manifest, inputs[bytes], outputs[bytes])."""
+    own = workdir is None
+    if own:
+        workdir = tempfile.mkdtemp(prefix="b200c_ref_")
+    try:
+        with open(os.path.join(workdir, "ops.bin"), "wb") as f:
+            f.write(ops.bytes())
+        args = [REF_BIN, os.path.join(workdir, "ops.bin"), os.path.join(workdir, "w")] + [f"{k}={v}" for k, v in opts.items()]
+        subprocess.check_call(args, stdout=subprocess.DEVNULL)
+        man = json.load(open(os.path.join(workdir, "w", "manifest.json")))
+        ins = [open(os.path.join(workdir, "w", "inputs" + m["name"]), "rb").read() for m in man["inputs"]]
+        outs = [open(os.path.join(workdir, "w", "outputs" + m["name"]), "rb").read() for m in man["outputs"]]
+        return dict(manifest=man, inputs=ins, outputs=outs)
+    finally:
+        if own:
+            shutil.rmtree(workdir, ignore_errors=True)
+
+
+def params_from_reference(ref) -> Params:
+    """Job parameters that reproduce a reference run: table options from the manifest, identity / clock /
+    file-number fields read back from the reference's own output files (they are inputs to the job:
+    TableBuilderOptions, db/compaction/compaction_job.cc:2258-2331)."""
+    man = ref["manifest"]
+    p = Params(output_level=man["output_level"], bottommost_level=man["bottommost_level"],
+               max_output_file_size=man["target_file_size"], block_size=man["block_size"],
+               block_restart_interval=man["restart_interval"], format_version=man["format_version"],
+               checksum=man["checksum"], snapshots=man["snapshots"])
+    if ref["outputs"]:
+        props = [sstfmt.parse_sst(o)["properties"] for o in ref["outputs"]]
+        p0 = props[0]
+        p.db_id = p0["rocksdb.creating.db.identity"].decode()
+        p.db_session_id = p0["rocksdb.creating.session.identity"].decode()
+        p.db_host_id = p0["rocksdb.creating.host.identity"].decode()
+        p.column_family_name = p0["rocksdb.column.family.name"].decode()
+        p.column_family_id = sstfmt.prop_u64(p0, "rocksdb.column.family.id")
+        p.creation_time = sstfmt.prop_u64(p0, "rocksdb.creation.time")
+        p.oldest_key_time = sstfmt.prop_u64(p0, "rocksdb.oldest.key.time")
+        p.file_creation_times = [sstfmt.prop_u64(q, "rocksdb.file.creation.time") for q in props]
+        p.first_file_number = sstfmt.prop_u64(p0, "rocksdb.original.file.number")
+        nums = [sstfmt.prop_u64(q, "rocksdb.original.file.number") for q in props]
+        assert nums == list(range(nums[0], nums[0] + len(nums))), nums
+    return p
+
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_cases():
+    return sorted(d for d in os.listdir(GOLDEN_DIR) if os.path.exists(os.path.join(GOLDEN_DIR, d, "manifest.json")))
+
+
+def load_golden(name):
+    d = os.path.join(GOLDEN_DIR, name)
+    man = json.load(open(os.path.join(d, "manifest.json")))
+    ins = [open(os.path.join(d, "inputs", m["name"].lstrip("/")), "rb").read() for m in man["inputs"]]
+    outs = [open(os.path.join(d, "outputs", m["name"].lstrip("/")), "rb").read() for m in man["outputs"]]
+    return dict(manifest=man, inputs=ins, outputs=outs)
+
+
+STAT_KEYS = ("num_input_records", "num_output_records", "num_records_replaced", "num_expired_deletion_records",
+             "num_input_deletion_records", "total_input_raw_key_bytes", "total_input_raw_value_bytes")
