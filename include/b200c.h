@@ -1,0 +1,157 @@
+/* include/b200c.h — C ABI of the B200 compaction engine (libb200c.so).
+ *
+ * This is the drop-in boundary for ToplingDB's compaction hot path.  The reference has no C ABI / FFI for
+ * this path (db/c.cc only exposes rocksdb_compact_range); the path sits behind two C++ virtual interfaces:
+ *   - CompactionExecutorFactory / CompactionExecutor   db/compaction/compaction_executor.h:160-178
+ *       SetParams(CompactionParams*, const Compaction*), Execute(const CompactionParams&, CompactionResults*)
+ *   - TableFactory / TableReader / TableBuilder         include/rocksdb/table.h:844-934
+ * The plugin classes registered with ROCKSDB_FACTORY_REG("B200Compact", ...) (see INTEGRATION.md and
+ * toplingdb_b200/plugin/) translate those objects into the calls below.  What each entry point replaces:
+ *
+ *   b200c_job_create        CompactionJob ctor + CompactionExecutor::SetParams   compaction_job.cc:921-963
+ *   b200c_job_add_input     VersionSet::MakeInputIterator: one child per L0 file / level   db/version_set.cc:7269-7352
+ *   b200c_job_run           CompactionExecutor::Execute -> CompactionJob::RunLocal ->
+ *                           ProcessKeyValueCompaction                          compaction_job.cc:659,971,1390-1780
+ *   b200c_job_output_*      CompactionResults::output_files[i] = FileMinMeta   compaction_executor.h:120-158
+ *   b200c_job_get_stats     CompactionResults::job_stats (CompactionJobStats)  include/rocksdb/compaction_job_stats.h
+ *
+ * Conventions: plain pointers and sizes only; integer status codes (0 = OK), never exceptions; the last
+ * error text of the calling thread is b200c_last_error().  One job handle may be used by one thread at a
+ * time; different handles are independent and the library is re-entrant across handles (the reference calls
+ * Execute() concurrently from several background compaction threads).  Input buffers are borrowed until
+ * b200c_job_destroy / b200c_job_run returns; output buffers are owned by the job.
+ * There is NO CPU fallback: every data-path call fails with B200C_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef B200C_H_
+#define B200C_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200C_ABI_VERSION 1
+#if defined(__GNUC__)
+#define B200C_API __attribute__((visibility("default")))
+#else
+#define B200C_API
+#endif
+
+enum b200c_status {
+  B200C_OK = 0,
+  B200C_ERR_INVALID_ARGUMENT = 1,
+  B200C_ERR_NO_DEVICE = 2,       /* no CUDA device / driver: the path has no CPU implementation */
+  B200C_ERR_CUDA = 3,            /* a CUDA runtime call failed (message has the call and error string) */
+  B200C_ERR_CORRUPTION = 4,      /* bad magic / handle / block checksum / key order in an input file */
+  B200C_ERR_NOT_SUPPORTED = 5,   /* input needs a rule outside the device rule set (merge operands, single
+                                    deletes, range tombstones, compressed blocks, user keys > 16 bytes, ...):
+                                    the executor must report ShouldRunLocal()==true / fall back (compaction_job.cc:649-652) */
+  B200C_ERR_OUT_OF_MEMORY = 6,
+  B200C_ERR_STATE = 7            /* call order violated (e.g. output queried before run) */
+};
+
+enum b200c_mem_kind { B200C_MEM_HOST = 0, B200C_MEM_DEVICE = 1 };
+enum b200c_checksum { B200C_CKSUM_NONE = 0, B200C_CKSUM_CRC32C = 1, B200C_CKSUM_XXH3 = 4 }; /* ChecksumType, table.h:54-60 */
+
+/* Job parameters: the fields of CompactionParams (compaction_executor.h:33-118), of the output
+ * BlockBasedTableOptions (include/rocksdb/table.h:237-564) and of TableBuilderOptions
+ * (compaction_job.cc:2258-2331) that decide the output bytes.  Zero-initialise, then b200c_params_init(). */
+typedef struct b200c_params {
+  uint32_t abi_version;            /* B200C_ABI_VERSION */
+  int32_t device;                  /* CUDA device ordinal for this job */
+  int32_t output_level;            /* CompactionParams::output_level; 0 => never cut files (compaction_outputs.cc:272) */
+  int32_t bottommost_level;        /* CompactionParams::bottommost_level */
+  uint64_t max_output_file_size;   /* Compaction::max_output_file_size() (compaction.cc:291-295) */
+  uint32_t block_size;             /* 4096 */
+  uint32_t block_size_deviation;   /* 10 */
+  uint32_t block_restart_interval; /* 16 */
+  uint32_t index_block_restart_interval; /* 1 (only value the device index builder accepts) */
+  uint32_t format_version;         /* 5 */
+  uint32_t checksum;               /* enum b200c_checksum of the OUTPUT files; inputs carry their own */
+  uint32_t verify_input_checksums; /* ReadOptions::verify_checksums of the compaction read (default 1) */
+  const uint64_t* snapshots;       /* CompactionParams::existing_snapshots, ascending; may be NULL */
+  uint32_t num_snapshots;
+  uint32_t column_family_id;
+  const char* column_family_name;  /* rocksdb.column.family.name */
+  const char* db_id;               /* rocksdb.creating.db.identity */
+  const char* db_session_id;       /* rocksdb.creating.session.identity */
+  const char* db_host_id;          /* rocksdb.creating.host.identity */
+  uint64_t creation_time;          /* rocksdb.creation.time = oldest ancestor time of the inputs */
+  uint64_t oldest_key_time;        /* rocksdb.oldest.key.time */
+  const uint64_t* file_creation_times; /* clock reading at each OpenCompactionOutputFile (compaction_job.cc:2258-2266);
+                                          entry i for output i, the last one repeats; NULL => 0 (property omitted) */
+  uint32_t num_file_creation_times;
+  uint64_t first_file_number;      /* outputs are numbered first_file_number, +1, ... (orig_file_number property) */
+  uint32_t output_mem;             /* enum b200c_mem_kind: where b200c_job_output_data() pointers live */
+  uint32_t reserved;
+} b200c_params;
+
+/* FileMinMeta (compaction_executor.h:120-131) + the TableProperties RunRemote re-reads (compaction_job.cc:1043-1061) */
+typedef struct b200c_file_meta {
+  uint64_t file_number, file_size;
+  uint64_t smallest_seqno, largest_seqno;
+  uint64_t num_entries, num_deletions, raw_key_size, raw_value_size, num_data_blocks, data_size, index_size;
+  uint32_t smallest_ikey_len, largest_ikey_len;
+  uint8_t smallest_ikey[64], largest_ikey[64];
+} b200c_file_meta;
+
+/* CompactionJobStats subset (include/rocksdb/compaction_job_stats.h) + device timings */
+typedef struct b200c_stats {
+  uint64_t num_input_records, num_output_records;
+  uint64_t num_input_deletion_records;
+  uint64_t num_records_replaced;         /* CompactionIterationStats::num_record_drop_hidden */
+  uint64_t num_expired_deletion_records; /* num_record_drop_obsolete */
+  uint64_t total_input_raw_key_bytes, total_input_raw_value_bytes;
+  uint64_t total_input_bytes, total_output_bytes;
+  uint64_t num_input_files, num_output_files;
+  /* device time of the last run, microseconds, CUDA events on the job stream */
+  double decode_us, merge_us, encode_us, total_us;
+  uint64_t kernel_launches; /* kernels of this library launched by the last run */
+} b200c_stats;
+
+typedef struct b200c_job b200c_job;
+
+B200C_API const char* b200c_last_error(void);
+B200C_API uint32_t b200c_abi_version(void);
+B200C_API int b200c_device_count(void); /* >= 0, or -B200C_ERR_NO_DEVICE */
+
+B200C_API void b200c_params_init(b200c_params* p); /* reference defaults (table.h:237-564, advanced_options.h:599) */
+
+B200C_API int b200c_job_create(const b200c_params* p, b200c_job** out);
+/* Append one sorted run (a whole BlockBasedTable file image).  Order matters exactly as in MakeInputIterator:
+ * L0 files newest first, then one run per deeper level.  `data` may be host or device memory (mem_kind). */
+B200C_API int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const void* data, uint64_t len, int mem_kind);
+/* decode -> k-way merge with the compaction-iterator rules -> encode, all on the device.  Synchronous. */
+B200C_API int b200c_job_run(b200c_job* j);
+B200C_API int b200c_job_output_count(const b200c_job* j);
+B200C_API int b200c_job_output_meta(const b200c_job* j, int i, b200c_file_meta* m);
+/* Pointer to the finished file image of output i (host or device memory according to params.output_mem). */
+B200C_API int b200c_job_output_data(b200c_job* j, int i, const void** data, uint64_t* len);
+/* Copy output i into caller memory (host). */
+B200C_API int b200c_job_output_read(b200c_job* j, int i, void* dst, uint64_t cap);
+B200C_API int b200c_job_get_stats(const b200c_job* j, b200c_stats* s);
+B200C_API void b200c_job_destroy(b200c_job* j);
+
+/* ---- stage-level entry points (used by the parity tests and by bench.py's per-kernel roofline) ---- */
+enum b200c_debug_array {
+  B200C_DBG_DECODED_KEYS = 1, /* run r: per entry { u64 hi, u64 lo, u64 trailer, u32 ulen, u32 vlen } (32 B) */
+  B200C_DBG_DECODED_VALUES = 2, /* run r: value bytes, concatenated in entry order */
+  B200C_DBG_MERGED_KEYS = 3,  /* surviving merged stream, same 32 B records */
+  B200C_DBG_MERGED_VALUES = 4,
+  B200C_DBG_BLOCK_LIST = 5    /* per output data block { u64 first_entry, u64 file_offset, u32 file_index, u32 n_entries } */
+};
+/* Run only up to a stage (1 = decode, 2 = merge, 3 = everything) keeping intermediates for b200c_job_debug_read. */
+B200C_API int b200c_job_run_until(b200c_job* j, int stage);
+/* Copies the array into dst (host) and returns the byte count needed in *len. run is ignored for merged arrays. */
+B200C_API int b200c_job_debug_read(b200c_job* j, int what, int run, void* dst, uint64_t cap, uint64_t* len);
+
+/* Block checksum of table/format.cc:468-509 computed on the device for n independent buffers laid out
+ * back to back (offsets[n+1]); results in out[n].  type = enum b200c_checksum. */
+B200C_API int b200c_block_checksums(int device, uint32_t type, const void* host_data, const uint64_t* offsets, uint32_t n,
+                          uint8_t last_byte, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200C_H_ */

@@ -1,0 +1,774 @@
+// toplingdb_b200/csrc/api.cu — the C ABI of include/b200c.h: job object + host orchestration of the three device stages.
+// Host work is O(files): parse the ~1 KB tail of every input, lay out the output images, build the ~1 KB tail of every
+// output.  Everything per entry / per block is a kernel launch (decode.cu, merge.cu, encode.cu).  No CPU data path exists.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200c.h"
+#include "kernels.h"
+#include "scan.cuh"
+#include "sst_host.h"
+
+using namespace b200c;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                                  \
+  do {                                                                                                            \
+    cudaError_t e_ = (call);                                                                                      \
+    if (e_ != cudaSuccess) {                                                                                      \
+      cudaGetLastError();                                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? B200C_ERR_OUT_OF_MEMORY : B200C_ERR_CUDA,                      \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                                            \
+    }                                                                                                             \
+  } while (0)
+
+struct DevBuf {  // grow-only device allocation, reused across runs of the same job
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + (n >> 4) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct Input {
+  int level;
+  uint64_t file_number;
+  const uint8_t* data;
+  uint64_t len;
+  int mem_kind;
+  DevBuf staged;  // device copy of a host input
+  const uint8_t* dev = nullptr;
+  InputTail tail;
+};
+struct Output {
+  b200c_file_meta meta;
+  uint64_t dev_off = 0;  // offset of the image inside out_buf
+  std::vector<uint8_t> host;  // when output_mem == HOST
+};
+
+}  // namespace
+
+struct b200c_job {
+  b200c_params p;
+  std::vector<uint64_t> snapshots, fct;
+  std::string cf_name, db_id, db_session_id, db_host_id;
+  std::vector<Input> inputs;
+  std::vector<Output> outputs;
+  b200c_stats stats;
+  bool ran = false;
+  int stage_done = 0;
+  int sms = 148;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // device state
+  DevBuf files_d, blk_off, blk_size, blk_cnt, blk_base, scan_tmp, run_start, small;  // small: err, totals, counters...
+  DevBuf dec[4], mrg[4], splits, tile_state, snaps_d;
+  DevBuf esz, eshared, nxt, disk, rows, tstate, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
+  uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
+  uint32_t nfiles_out = 0;
+  std::vector<uint64_t> run_start_h;
+};
+
+namespace {
+
+// layout of the `small` buffer (u64 slots)
+enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotCounters = 8 /* 7 */, kSmallSlots = 32 };
+
+int map_dev_err(uint32_t e) {
+  if (e == 0) return B200C_OK;
+  std::string m = "device reported:";
+  int code = B200C_ERR_CORRUPTION;
+  if (e & kErrCorruptBlock) m += " corrupt-block";
+  if (e & kErrChecksum) m += " block-checksum-mismatch";
+  if (e & kErrKeyOrder) m += " key-order/partition";
+  if (e & kErrCountMismatch) m += " entry-count-mismatch";
+  const uint32_t unsup = kErrKeyTooLong | kErrValueTooLong | kErrBadType | kErrCompressed | kErrBlockTooLong;
+  if (e & unsup) {
+    if (!(e & ~(unsup))) code = B200C_ERR_NOT_SUPPORTED;
+    if (e & kErrKeyTooLong) m += " user-key-longer-than-16-bytes";
+    if (e & kErrValueTooLong) m += " value>=128MiB";
+    if (e & kErrBadType) m += " value-type-outside-{Value,Deletion}";
+    if (e & kErrCompressed) m += " compressed-block";
+    if (e & kErrBlockTooLong) m += " output-block-with-too-many-entries";
+  }
+  if (e & kErrInternal) {
+    m += " internal";
+    code = B200C_ERR_CUDA;
+  }
+  return fail(code, m);
+}
+
+int fetch_tail(b200c_job* j, Input& in) {
+  // footer, metaindex, properties: three tiny reads (D2H when the image lives in device memory)
+  auto read = [&](uint64_t off, uint64_t n, std::vector<uint8_t>& buf) -> int {
+    buf.resize(n);
+    if (in.mem_kind == B200C_MEM_HOST) {
+      memcpy(buf.data(), in.data + off, n);
+    } else {
+      CU(cudaMemcpyAsync(buf.data(), in.data + off, n, cudaMemcpyDeviceToHost, j->st));
+      CU(cudaStreamSynchronize(j->st));
+    }
+    return B200C_OK;
+  };
+  if (in.len < 53) return fail(B200C_ERR_CORRUPTION, "input shorter than a footer");
+  const uint64_t tail_n = std::min<uint64_t>(in.len, 4096);
+  std::vector<uint8_t> tail, tmp;
+  int rc = read(in.len - tail_n, tail_n, tail);
+  if (rc) return rc;
+  std::string e = parse_footer(tail.data() + tail_n - 53, in.len, &in.tail);
+  if (!e.empty()) return fail(B200C_ERR_CORRUPTION, e);
+  auto view = [&](uint64_t off, uint64_t n, const uint8_t** p) -> int {
+    if (off >= in.len - tail_n && off + n <= in.len) {
+      *p = tail.data() + (off - (in.len - tail_n));
+      return B200C_OK;
+    }
+    int r = read(off, n, tmp);
+    *p = tmp.data();
+    return r;
+  };
+  const uint8_t* blk;
+  rc = view(in.tail.meta_off, in.tail.meta_size + 5, &blk);
+  if (rc) return rc;
+  if (in.tail.checksum_type &&
+      host_block_checksum(in.tail.checksum_type, blk, in.tail.meta_size, blk[in.tail.meta_size]) !=
+          ((uint32_t)blk[in.tail.meta_size + 1] | (uint32_t)blk[in.tail.meta_size + 2] << 8 |
+           (uint32_t)blk[in.tail.meta_size + 3] << 16 | (uint32_t)blk[in.tail.meta_size + 4] << 24))
+    return fail(B200C_ERR_CORRUPTION, "metaindex block checksum mismatch");
+  std::map<std::string, std::pair<uint64_t, uint64_t>> meta;
+  e = parse_metaindex(blk, in.tail.meta_size, &meta);
+  if (!e.empty()) return fail(B200C_ERR_CORRUPTION, e);
+  for (auto& kv : meta) {
+    if (kv.first == "rocksdb.range_del") in.tail.has_range_del = true;
+    if (kv.first.compare(0, 11, "fullfilter.") == 0 || kv.first.compare(0, 18, "partitionedfilter.") == 0) in.tail.has_filter = true;
+    if (kv.first == "rocksdb.compression_dict") in.tail.has_dict = true;
+  }
+  auto it = meta.find("rocksdb.properties");
+  if (it == meta.end()) return fail(B200C_ERR_CORRUPTION, "input has no properties block");
+  in.tail.props_off = it->second.first;
+  in.tail.props_size = it->second.second;
+  if (in.tail.props_off + in.tail.props_size + 5 > in.len) return fail(B200C_ERR_CORRUPTION, "properties handle out of range");
+  rc = view(in.tail.props_off, in.tail.props_size + 5, &blk);
+  if (rc) return rc;
+  e = parse_properties(blk, in.tail.props_size, &in.tail);
+  if (!e.empty()) return fail(B200C_ERR_CORRUPTION, e);
+  if (in.tail.has_range_del || in.tail.num_range_deletions)
+    return fail(B200C_ERR_NOT_SUPPORTED, "input holds range tombstones (CompactionRangeDelAggregator is not on the device path)");
+  if (in.tail.num_merge_operands) return fail(B200C_ERR_NOT_SUPPORTED, "input holds merge operands");
+  if (in.tail.has_dict) return fail(B200C_ERR_NOT_SUPPORTED, "input uses a compression dictionary");
+  if (!in.tail.comparator_name.empty() && in.tail.comparator_name != "leveldb.BytewiseComparator")
+    return fail(B200C_ERR_NOT_SUPPORTED, "comparator " + in.tail.comparator_name + " (only leveldb.BytewiseComparator runs on the device)");
+  if (in.tail.num_data_blocks > 0xffffffffull) return fail(B200C_ERR_NOT_SUPPORTED, "too many data blocks");
+  return B200C_OK;
+}
+
+void ikey_bytes(const KeyRec& k, uint8_t* out, uint32_t* len) {
+  uint32_t n = 0;
+  for (uint32_t t = 0; t < k.ulen && t < 16; t++) out[n++] = (uint8_t)((t < 8 ? k.hi >> (56 - 8 * t) : k.lo >> (56 - 8 * (t - 8))) & 0xff);
+  for (int t = 0; t < 8; t++) out[n++] = (uint8_t)(k.tr >> (8 * t));
+  *len = n;
+}
+
+int run_job(b200c_job* j, int until) {
+  const b200c_params& P = j->p;
+  CU(cudaSetDevice(P.device));
+  if (!j->st) {
+    CU(cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking));
+    for (auto& e : j->ev) CU(cudaEventCreate(&e));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, P.device));
+    j->sms = prop.multiProcessorCount;
+  }
+  cudaStream_t st = j->st;
+  uint64_t launches = 0;
+  j->outputs.clear();
+  j->ran = false;
+  j->stage_done = 0;
+  memset(&j->stats, 0, sizeof j->stats);
+  const int k = (int)j->inputs.size();
+  if (k == 0) return fail(B200C_ERR_INVALID_ARGUMENT, "job has no inputs");
+  if (k > kMaxRuns) return fail(B200C_ERR_NOT_SUPPORTED, "more than 64 input runs");
+
+  // ---------------- inputs: resident image + tail
+  CU(cudaEventRecord(j->ev[0], st));
+  uint64_t nblk = 0, n_props = 0, in_bytes = 0;
+  std::vector<FileDesc> fds(k);
+  for (int i = 0; i < k; i++) {
+    Input& in = j->inputs[i];
+    int rc = fetch_tail(j, in);
+    if (rc) return rc;
+    if (in.mem_kind == B200C_MEM_HOST) {
+      CU(in.staged.reserve(in.len + 64));
+      CU(cudaMemcpyAsync(in.staged.p, in.data, in.len, cudaMemcpyHostToDevice, st));
+      in.dev = in.staged.as<uint8_t>();
+    } else {
+      if ((uintptr_t)in.data & 15) return fail(B200C_ERR_INVALID_ARGUMENT, "device input images must be 16-byte aligned");
+      in.dev = in.data;
+    }
+    FileDesc& fd = fds[i];
+    fd.base = in.dev;
+    fd.len = in.len;
+    fd.index_off = in.tail.index_off;
+    fd.index_size = (uint32_t)in.tail.index_size;
+    fd.value_delta = in.tail.format_version >= 4;
+    fd.cksum = in.tail.checksum_type;
+    fd.gblk_first = (uint32_t)nblk;
+    fd.nblocks = (uint32_t)in.tail.num_data_blocks;
+    fd.pad = 0;
+    nblk += in.tail.num_data_blocks;
+    n_props += in.tail.num_entries;
+    in_bytes += in.len;
+    if (in.tail.index_size > 0xffffffffull) return fail(B200C_ERR_NOT_SUPPORTED, "index block >= 4 GiB");
+  }
+  if (nblk > 0xfffffff0ull) return fail(B200C_ERR_NOT_SUPPORTED, "too many data blocks");
+  j->nblk_in = nblk;
+  j->n_total = n_props;
+  j->stats.num_input_files = k;
+  j->stats.total_input_bytes = in_bytes;
+  j->stats.num_input_records = n_props;
+
+  CU(j->small.reserve(kSmallSlots * 8));
+  CU(cudaMemsetAsync(j->small.p, 0, kSmallSlots * 8, st));
+  uint64_t* small = j->small.as<uint64_t>();
+  uint32_t* err = reinterpret_cast<uint32_t*>(small + kSlotErr);
+  {
+    uint32_t ff = 0xffffffffu;
+    CU(cudaMemcpyAsync(small + kSlotMinS1, &ff, 4, cudaMemcpyHostToDevice, st));
+  }
+  CU(j->files_d.reserve(sizeof(FileDesc) * k));
+  CU(cudaMemcpyAsync(j->files_d.p, fds.data(), sizeof(FileDesc) * k, cudaMemcpyHostToDevice, st));
+  const uint64_t N = n_props;
+  CU(j->blk_off.reserve(8 * (nblk + 1)));
+  CU(j->blk_size.reserve(4 * (nblk + 1)));
+  CU(j->blk_cnt.reserve(4 * (nblk + 1)));
+  CU(j->blk_base.reserve(8 * (nblk + 1)));
+  CU(j->scan_tmp.reserve(8 * ((std::max<uint64_t>(nblk, N) / kScanTile) + 2)));
+  CU(j->run_start.reserve(8 * (k + 1)));
+  CU(j->dec[0].reserve(16 * (N + 1)));
+  CU(j->dec[1].reserve(8 * (N + 1)));
+  CU(j->dec[2].reserve(8 * (N + 1)));
+  CU(j->dec[3].reserve(4 * (N + 1)));
+  const FileDesc* files_d = j->files_d.as<FileDesc>();
+
+  // ---------------- decode
+  uint32_t maxb = 0;
+  for (auto& f : fds) maxb = std::max(maxb, f.nblocks);
+  if (nblk) {
+    launch_index_decode(files_d, k, maxb, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), err, st);
+    launch_block_count(files_d, k, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), (uint32_t)nblk, P.verify_input_checksums,
+                       j->blk_cnt.as<uint32_t>(), err, j->sms, st);
+    launches += 2;
+    exclusive_scan<uint32_t>(j->blk_cnt.as<uint32_t>(), j->blk_base.as<uint64_t>(), nblk, j->scan_tmp.as<uint64_t>(),
+                             small + kSlotTotalIn, st, &launches);
+  }
+  launch_run_starts(files_d, k, j->blk_base.as<uint64_t>(), small + kSlotTotalIn, (uint32_t)nblk, j->run_start.as<uint64_t>(), st);
+  launches++;
+  KeyColsMut dec{j->dec[0].as<ulonglong2>(), j->dec[1].as<uint64_t>(), j->dec[2].as<uint64_t>(), j->dec[3].as<uint32_t>()};
+  if (nblk) {
+    launch_block_decode(files_d, k, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), j->blk_base.as<uint64_t>(), (uint32_t)nblk,
+                        N, dec, err, j->sms, st);
+    launches++;
+  }
+  CU(cudaEventRecord(j->ev[1], st));
+  KeyCols decc{dec.pfx, dec.tr, dec.vref, dec.meta, N};
+  if (until == 1) {
+    uint64_t h[kSmallSlots];
+    CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
+    j->run_start_h.resize(k + 1);
+    CU(cudaMemcpyAsync(j->run_start_h.data(), j->run_start.p, 8 * (k + 1), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    int rc = map_dev_err((uint32_t)h[kSlotErr]);
+    if (rc) return rc;
+    if (h[kSlotTotalIn] != N) return fail(B200C_ERR_CORRUPTION, "decoded entry count differs from rocksdb.num.entries");
+    j->stage_done = 1;
+    j->stats.kernel_launches = launches;
+    return B200C_OK;
+  }
+
+  // ---------------- merge
+  const uint64_t mtiles = (N + kMergeTile - 1) / kMergeTile;
+  CU(j->splits.reserve(8 * (mtiles + 1) * k));
+  CU(j->tile_state.reserve(8 * (mtiles + 1)));
+  CU(cudaMemsetAsync(j->tile_state.p, 0, 8 * (mtiles + 1), st));
+  CU(j->snaps_d.reserve(8 * (P.num_snapshots + 1)));
+  if (P.num_snapshots) CU(cudaMemcpyAsync(j->snaps_d.p, j->snapshots.data(), 8 * P.num_snapshots, cudaMemcpyHostToDevice, st));
+  CU(j->mrg[0].reserve(16 * (N + 1)));
+  CU(j->mrg[1].reserve(8 * (N + 1)));
+  CU(j->mrg[2].reserve(8 * (N + 1)));
+  CU(j->mrg[3].reserve(4 * (N + 1)));
+  CU(j->esz.reserve(4 * (N + 1)));
+  CU(j->eshared.reserve(N + 1));
+  KeyColsMut mrg{j->mrg[0].as<ulonglong2>(), j->mrg[1].as<uint64_t>(), j->mrg[2].as<uint64_t>(), j->mrg[3].as<uint32_t>()};
+  MergeParams mp;
+  mp.nruns = (uint32_t)k;
+  mp.bottommost = P.bottommost_level != 0;
+  mp.nsnapshots = P.num_snapshots;
+  mp.snapshots = j->snaps_d.as<uint64_t>();
+  mp.earliest_snapshot = P.num_snapshots ? j->snapshots[0] : kMaxSeq;
+  MergeCounters* counters = reinterpret_cast<MergeCounters*>(small + kSlotCounters);
+  EncodeWork W;
+  memset(&W, 0, sizeof W);
+  W.esz = j->esz.as<uint32_t>();
+  W.eshared = j->eshared.as<uint8_t>();
+  W.min_s1 = reinterpret_cast<uint32_t*>(small + kSlotMinS1);
+  W.totals = small + kSlotTotals;
+  if (N) {
+    launch_merge_partition(decc, j->run_start.as<uint64_t>(), (uint32_t)k, N, mtiles, j->splits.as<uint64_t>(), err, st);
+    launch_merge_tiles(decc, j->run_start.as<uint64_t>(), mp, N, mtiles, j->splits.as<uint64_t>(),
+                       j->tile_state.as<unsigned long long>(), reinterpret_cast<uint32_t*>(small + kSlotTicket), mrg, counters, err, st);
+    launches += 2;
+  }
+  CU(cudaEventRecord(j->ev[2], st));
+  KeyCols mcols{mrg.pfx, mrg.tr, mrg.vref, mrg.meta, 0};
+  if (N) {
+    launch_encode_sizes(mcols, reinterpret_cast<const unsigned long long*>(&counters->n_out), W, N, st);
+    launches++;
+  }
+  uint64_t h[kSmallSlots];
+  CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));  // sync #1: survivors, smallest entry, error word
+  CU(cudaGetLastError());
+  {
+    int rc = map_dev_err((uint32_t)h[kSlotErr]);
+    if (rc) return rc;
+  }
+  if (h[kSlotTotalIn] != N) return fail(B200C_ERR_CORRUPTION, "decoded entry count differs from rocksdb.num.entries");
+  MergeCounters mc;
+  memcpy(&mc, h + kSlotCounters, sizeof mc);
+  const uint64_t n_out = mc.n_out;
+  j->n_out = n_out;
+  mcols.n = n_out;
+  j->stats.num_output_records = n_out;
+  j->stats.num_input_deletion_records = mc.n_input_deletions;
+  j->stats.num_records_replaced = mc.n_hidden;
+  j->stats.num_expired_deletion_records = mc.n_obsolete;
+  j->stats.total_input_raw_key_bytes = mc.raw_key_bytes;
+  j->stats.total_input_raw_value_bytes = mc.raw_value_bytes;
+  if (until == 2) {
+    j->stage_done = 2;
+    j->stats.kernel_launches = launches;
+    return B200C_OK;
+  }
+
+  // ---------------- encode
+  uint32_t nfiles = 0;
+  uint64_t nblocks = 0;
+  std::vector<FileRec> frs;
+  std::vector<uint64_t> base_off;
+  if (n_out) {
+    if (P.index_block_restart_interval != 1)
+      return fail(B200C_ERR_NOT_SUPPORTED, "index_block_restart_interval != 1 is not built on the device");
+    const uint32_t min_s1 = (uint32_t)h[kSlotMinS1];
+    EncodeParams ep;
+    ep.block_size = P.block_size;
+    ep.block_size_limit = P.block_size_deviation ? (uint32_t)(((uint64_t)P.block_size * (100 - P.block_size_deviation) + 99) / 100) : 0;
+    ep.restart_interval = P.block_restart_interval;
+    ep.checksum = P.checksum;
+    ep.format_version = P.format_version;
+    ep.output_level = (uint32_t)P.output_level;
+    ep.max_output_file_size = P.max_output_file_size;
+    uint64_t hop = (uint64_t)(P.block_size - 1) / std::max<uint32_t>(min_s1, 1) + 3;
+    if (hop > (uint64_t)kEncHalo) return fail(B200C_ERR_NOT_SUPPORTED, "block_size / smallest entry exceeds the encoder's 2048-entry block window");
+    const uint32_t hc = (uint32_t)hop;
+    const uint64_t etiles = (n_out + kEncTile - 1) / kEncTile;
+    CU(j->rows.reserve(sizeof(TileRow) * etiles * hc));
+    CU(j->tstate.reserve(sizeof(TileState) * etiles));
+    CU(j->nxt.reserve(2 * (n_out + 1)));
+    CU(j->disk.reserve(4 * (n_out + 1)));
+    CU(j->files_rec.reserve(sizeof(FileRec) * (kMaxOutFiles + 2)));
+    W.rows = j->rows.as<TileRow>();
+    W.tstate = j->tstate.as<TileState>();
+    W.nxt = j->nxt.as<uint16_t>();
+    W.disk = j->disk.as<uint32_t>();
+    W.files = j->files_rec.as<FileRec>();
+    W.scan_tmp = j->scan_tmp.as<uint64_t>();
+    launch_encode_tables(mcols, ep, W, etiles, hc, err, st);
+    launch_encode_stitch(mcols, ep, W, etiles, hc, err, st);
+    launches += 2;
+    CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // sync #2: number of blocks / files
+    CU(cudaGetLastError());
+    {
+      int rc = map_dev_err((uint32_t)h[kSlotErr]);
+      if (rc) return rc;
+    }
+    nblocks = h[kSlotTotals];
+    nfiles = (uint32_t)h[kSlotTotals + 1];
+    if (nfiles == 0 || nfiles > kMaxOutFiles) return fail(B200C_ERR_CUDA, "internal: bad output file count");
+    frs.resize(nfiles);
+    CU(cudaMemcpyAsync(frs.data(), W.files, sizeof(FileRec) * nfiles, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(j->blocks.reserve(sizeof(BlockRec) * (nblocks + 1)));
+    CU(j->idx_esz.reserve(4 * (nblocks + 1)));
+    CU(j->idx_eoff.reserve(8 * (nblocks + 1)));
+    CU(j->idx_sep.reserve(sizeof(KeyRec) * (nblocks + 1)));
+    W.blocks = j->blocks.as<BlockRec>();
+    W.idx_esz = j->idx_esz.as<uint32_t>();
+    W.idx_eoff = j->idx_eoff.as<uint64_t>();
+    W.idx_sep = j->idx_sep.as<KeyRec>();
+    // image layout: data blocks | index block (<= 45 B per data block + 9) | tail (properties, metaindex, footer)
+    base_off.resize(nfiles + 1);
+    uint64_t off = 0;
+    for (uint32_t f = 0; f < nfiles; f++) {
+      base_off[f] = off;
+      uint64_t cap = frs[f].data_size + frs[f].n_blocks * 48 + 64 + 4096;
+      off += (cap + 255) & ~255ull;
+    }
+    base_off[nfiles] = off;
+    CU(j->out_buf.reserve(off + 256));
+    std::vector<uint8_t*> bases(nfiles);
+    for (uint32_t f = 0; f < nfiles; f++) bases[f] = j->out_buf.as<uint8_t>() + base_off[f];
+    CU(j->out_base_d.reserve(8 * nfiles));
+    CU(cudaMemcpyAsync(j->out_base_d.p, bases.data(), 8 * nfiles, cudaMemcpyHostToDevice, st));
+    uint8_t* const* out_base_d = j->out_base_d.as<uint8_t*>();
+    launch_encode_blocklist(mcols, ep, W, etiles, nblocks, err, st);
+    launch_encode_filestats(mcols, W, nfiles, j->sms, st);
+    launch_encode_emit(mcols, ep, W, nblocks, out_base_d, err, j->sms, st);
+    launches += 3;
+    launch_encode_index(mcols, ep, W, nblocks, nfiles, out_base_d, err, st, &launches);
+    CU(cudaMemcpyAsync(frs.data(), W.files, sizeof(FileRec) * nfiles, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // sync #3: per-file records
+    CU(cudaGetLastError());
+    {
+      int rc = map_dev_err((uint32_t)h[kSlotErr]);
+      if (rc) return rc;
+    }
+    // tails
+    j->outputs.resize(nfiles);
+    for (uint32_t f = 0; f < nfiles; f++) {
+      const FileRec& fr = frs[f];
+      OutputTailInput ti;
+      ti.checksum_type = P.checksum;
+      ti.format_version = P.format_version;
+      ti.data_size = fr.data_size;
+      ti.index_size = fr.index_size;
+      ti.num_entries = fr.n_entries;
+      ti.num_deletions = fr.num_deletions;
+      ti.raw_key_size = fr.raw_key_size;
+      ti.raw_value_size = fr.raw_value_size;
+      ti.num_data_blocks = fr.n_blocks;
+      ti.index_key_is_user_key = !fr.index_has_seq && P.format_version > 2;
+      ti.column_family_id = P.column_family_id;
+      ti.column_family_name = j->cf_name;
+      ti.db_id = j->db_id;
+      ti.db_session_id = j->db_session_id;
+      ti.db_host_id = j->db_host_id;
+      ti.creation_time = P.creation_time;
+      ti.oldest_key_time = P.oldest_key_time;
+      ti.file_creation_time = j->fct.empty() ? 0 : j->fct[std::min<size_t>(f, j->fct.size() - 1)];
+      ti.orig_file_number = P.first_file_number + f;
+      std::vector<uint8_t> tail = build_output_tail(ti);
+      const uint64_t tail_off = fr.data_size + fr.index_size + 5;
+      if (tail_off + tail.size() > base_off[f + 1] - base_off[f]) return fail(B200C_ERR_CUDA, "internal: output image overflow");
+      CU(cudaMemcpyAsync(j->out_buf.as<uint8_t>() + base_off[f] + tail_off, tail.data(), tail.size(), cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));  // `tail` is a temporary
+      Output& o = j->outputs[f];
+      memset(&o.meta, 0, sizeof o.meta);
+      o.dev_off = base_off[f];
+      o.meta.file_number = ti.orig_file_number;
+      o.meta.file_size = tail_off + tail.size();
+      o.meta.smallest_seqno = fr.smallest_seq;
+      o.meta.largest_seqno = fr.largest_seq;
+      o.meta.num_entries = fr.n_entries;
+      o.meta.num_deletions = fr.num_deletions;
+      o.meta.raw_key_size = fr.raw_key_size;
+      o.meta.raw_value_size = fr.raw_value_size;
+      o.meta.num_data_blocks = fr.n_blocks;
+      o.meta.data_size = fr.data_size;
+      o.meta.index_size = fr.index_size;
+      ikey_bytes(fr.smallest, o.meta.smallest_ikey, &o.meta.smallest_ikey_len);
+      ikey_bytes(fr.largest, o.meta.largest_ikey, &o.meta.largest_ikey_len);
+      j->stats.total_output_bytes += o.meta.file_size;
+    }
+  }
+  j->nblocks_out = nblocks;
+  j->nfiles_out = nfiles;
+  CU(cudaEventRecord(j->ev[3], st));
+  if (P.output_mem == B200C_MEM_HOST) {
+    for (auto& o : j->outputs) {
+      o.host.resize(o.meta.file_size);
+      CU(cudaMemcpyAsync(o.host.data(), j->out_buf.as<uint8_t>() + o.dev_off, o.meta.file_size, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CU(cudaEventRecord(j->ev[4], st));
+  CU(cudaStreamSynchronize(st));
+  float ms;
+  cudaEventElapsedTime(&ms, j->ev[0], j->ev[1]);
+  j->stats.decode_us = ms * 1000.0;
+  cudaEventElapsedTime(&ms, j->ev[1], j->ev[2]);
+  j->stats.merge_us = ms * 1000.0;
+  cudaEventElapsedTime(&ms, j->ev[2], j->ev[3]);
+  j->stats.encode_us = ms * 1000.0;
+  cudaEventElapsedTime(&ms, j->ev[0], j->ev[4]);
+  j->stats.total_us = ms * 1000.0;
+  j->stats.num_output_files = nfiles;
+  j->stats.kernel_launches = launches;
+  j->ran = true;
+  j->stage_done = 3;
+  return B200C_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200c_last_error(void) { return g_err.c_str(); }
+uint32_t b200c_abi_version(void) { return B200C_ABI_VERSION; }
+int b200c_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+    return -B200C_ERR_NO_DEVICE;
+  }
+  return n;
+}
+
+void b200c_params_init(b200c_params* p) {
+  memset(p, 0, sizeof *p);
+  p->abi_version = B200C_ABI_VERSION;
+  p->device = 0;
+  p->output_level = 1;
+  p->bottommost_level = 0;
+  p->max_output_file_size = 64ull << 20;  // target_file_size_base, advanced_options.h:599
+  p->block_size = 4096;
+  p->block_size_deviation = 10;
+  p->block_restart_interval = 16;
+  p->index_block_restart_interval = 1;
+  p->format_version = 5;
+  p->checksum = B200C_CKSUM_XXH3;
+  p->verify_input_checksums = 1;
+  p->column_family_name = "default";
+  p->output_mem = B200C_MEM_HOST;
+}
+
+int b200c_job_create(const b200c_params* p, b200c_job** out) {
+  if (!p || !out) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  if (p->abi_version != B200C_ABI_VERSION) return fail(B200C_ERR_INVALID_ARGUMENT, "ABI version mismatch");
+  if (p->block_size < 64 || p->block_size > (1u << 20)) return fail(B200C_ERR_INVALID_ARGUMENT, "block_size out of range");
+  if (p->block_restart_interval < 1) return fail(B200C_ERR_INVALID_ARGUMENT, "block_restart_interval < 1");
+  if (p->block_size_deviation > 100) return fail(B200C_ERR_INVALID_ARGUMENT, "block_size_deviation > 100");
+  if (p->format_version < 3 || p->format_version > 5) return fail(B200C_ERR_NOT_SUPPORTED, "output format_version must be 3..5");
+  if (p->checksum != B200C_CKSUM_XXH3 && p->checksum != B200C_CKSUM_CRC32C && p->checksum != B200C_CKSUM_NONE)
+    return fail(B200C_ERR_NOT_SUPPORTED, "output checksum must be kNoChecksum, kCRC32c or kXXH3");
+  for (uint32_t i = 1; i < p->num_snapshots; i++)
+    if (p->snapshots[i] <= p->snapshots[i - 1]) return fail(B200C_ERR_INVALID_ARGUMENT, "snapshots must be strictly ascending");
+  int n = b200c_device_count();
+  if (n <= 0) return fail(B200C_ERR_NO_DEVICE, "no CUDA device: the compaction path has no CPU implementation in this library");
+  if (p->device < 0 || p->device >= n) return fail(B200C_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+  b200c_job* j = new b200c_job();
+  j->p = *p;
+  if (p->num_snapshots) j->snapshots.assign(p->snapshots, p->snapshots + p->num_snapshots);
+  if (p->num_file_creation_times) j->fct.assign(p->file_creation_times, p->file_creation_times + p->num_file_creation_times);
+  j->cf_name = p->column_family_name ? p->column_family_name : "";
+  j->db_id = p->db_id ? p->db_id : "";
+  j->db_session_id = p->db_session_id ? p->db_session_id : "";
+  j->db_host_id = p->db_host_id ? p->db_host_id : "";
+  j->p.snapshots = nullptr;
+  j->p.file_creation_times = nullptr;
+  memset(&j->stats, 0, sizeof j->stats);
+  *out = j;
+  return B200C_OK;
+}
+
+int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const void* data, uint64_t len, int mem_kind) {
+  if (!j || !data) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  if (mem_kind != B200C_MEM_HOST && mem_kind != B200C_MEM_DEVICE) return fail(B200C_ERR_INVALID_ARGUMENT, "bad mem_kind");
+  j->inputs.emplace_back();
+  Input& in = j->inputs.back();
+  in.level = level;
+  in.file_number = file_number;
+  in.data = static_cast<const uint8_t*>(data);
+  in.len = len;
+  in.mem_kind = mem_kind;
+  return B200C_OK;
+}
+
+int b200c_job_run(b200c_job* j) {
+  if (!j) return fail(B200C_ERR_INVALID_ARGUMENT, "null job");
+  return run_job(j, 3);
+}
+int b200c_job_run_until(b200c_job* j, int stage) {
+  if (!j || stage < 1 || stage > 3) return fail(B200C_ERR_INVALID_ARGUMENT, "bad stage");
+  return run_job(j, stage);
+}
+int b200c_job_output_count(const b200c_job* j) { return j && j->ran ? (int)j->outputs.size() : -B200C_ERR_STATE; }
+int b200c_job_output_meta(const b200c_job* j, int i, b200c_file_meta* m) {
+  if (!j || !j->ran || i < 0 || i >= (int)j->outputs.size() || !m) return fail(B200C_ERR_STATE, "no such output");
+  *m = j->outputs[i].meta;
+  return B200C_OK;
+}
+int b200c_job_output_data(b200c_job* j, int i, const void** data, uint64_t* len) {
+  if (!j || !j->ran || i < 0 || i >= (int)j->outputs.size()) return fail(B200C_ERR_STATE, "no such output");
+  Output& o = j->outputs[i];
+  *len = o.meta.file_size;
+  *data = j->p.output_mem == B200C_MEM_HOST ? (const void*)o.host.data() : (const void*)(j->out_buf.as<uint8_t>() + o.dev_off);
+  return B200C_OK;
+}
+int b200c_job_output_read(b200c_job* j, int i, void* dst, uint64_t cap) {
+  if (!j || !j->ran || i < 0 || i >= (int)j->outputs.size()) return fail(B200C_ERR_STATE, "no such output");
+  Output& o = j->outputs[i];
+  if (cap < o.meta.file_size) return fail(B200C_ERR_INVALID_ARGUMENT, "destination too small");
+  if (j->p.output_mem == B200C_MEM_HOST) {
+    memcpy(dst, o.host.data(), o.meta.file_size);
+    return B200C_OK;
+  }
+  CU(cudaSetDevice(j->p.device));
+  CU(cudaMemcpy(dst, j->out_buf.as<uint8_t>() + o.dev_off, o.meta.file_size, cudaMemcpyDeviceToHost));
+  return B200C_OK;
+}
+int b200c_job_get_stats(const b200c_job* j, b200c_stats* s) {
+  if (!j || !s) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  *s = j->stats;
+  return B200C_OK;
+}
+void b200c_job_destroy(b200c_job* j) {
+  if (!j) return;
+  cudaSetDevice(j->p.device);
+  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_cnt, &j->blk_base, &j->scan_tmp, &j->run_start, &j->small,
+                   &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
+                   &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->blocks,
+                   &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};
+  for (DevBuf* b : all) b->release();
+  for (auto& in : j->inputs) in.staged.release();
+  for (auto& e : j->ev)
+    if (e) cudaEventDestroy(e);
+  if (j->st) cudaStreamDestroy(j->st);
+  delete j;
+}
+
+int b200c_job_debug_read(b200c_job* j, int what, int run, void* dst, uint64_t cap, uint64_t* len) {
+  if (!j || !len) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(j->p.device));
+  cudaStream_t st = j->st;
+  struct Rec {
+    uint64_t hi, lo, tr;
+    uint32_t ulen, vlen;
+  };
+  auto read_keys = [&](const DevBuf* c, uint64_t first, uint64_t n) -> int {
+    *len = n * sizeof(Rec);
+    if (!dst || cap < *len) return B200C_OK;
+    std::vector<ulonglong2> pfx(n);
+    std::vector<uint64_t> tr(n);
+    std::vector<uint32_t> meta(n);
+    if (n) {
+      CU(cudaMemcpy(pfx.data(), c[0].as<ulonglong2>() + first, 16 * n, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(tr.data(), c[1].as<uint64_t>() + first, 8 * n, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(meta.data(), c[3].as<uint32_t>() + first, 4 * n, cudaMemcpyDeviceToHost));
+    }
+    Rec* r = static_cast<Rec*>(dst);
+    for (uint64_t i = 0; i < n; i++) r[i] = Rec{pfx[i].x, pfx[i].y, tr[i], meta_ulen(meta[i]), meta_vlen(meta[i])};
+    return B200C_OK;
+  };
+  auto read_values = [&](const DevBuf* c, uint64_t first, uint64_t n) -> int {
+    DevBuf vl, off, tmp, tot, bytes;
+    CU(vl.reserve(4 * (n + 1)));
+    CU(off.reserve(8 * (n + 1)));
+    CU(tmp.reserve(8 * (n / kScanTile + 2)));
+    CU(tot.reserve(8));
+    int rc = B200C_OK;
+    KeyCols kc{c[0].as<ulonglong2>() + first, c[1].as<uint64_t>() + first, c[2].as<uint64_t>() + first, c[3].as<uint32_t>() + first, n};
+    launch_meta_vlen(kc.meta, n, vl.as<uint32_t>(), st);
+    exclusive_scan<uint32_t>(vl.as<uint32_t>(), off.as<uint64_t>(), n, tmp.as<uint64_t>(), tot.as<uint64_t>(), st, nullptr);
+    uint64_t total = 0;
+    cudaMemcpyAsync(&total, tot.p, 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    *len = total;
+    if (dst && cap >= total && total) {
+      if (bytes.reserve(total) != cudaSuccess) rc = fail(B200C_ERR_OUT_OF_MEMORY, "debug value buffer");
+      else {
+        launch_gather_values(kc, off.as<uint64_t>(), bytes.as<uint8_t>(), st);
+        cudaMemcpyAsync(dst, bytes.p, total, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+      }
+    }
+    vl.release();
+    off.release();
+    tmp.release();
+    tot.release();
+    bytes.release();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B200C_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+  };
+  switch (what) {
+    case B200C_DBG_DECODED_KEYS:
+    case B200C_DBG_DECODED_VALUES: {
+      if (j->stage_done < 1) return fail(B200C_ERR_STATE, "decode stage has not run");
+      if (j->run_start_h.empty()) {
+        j->run_start_h.resize(j->inputs.size() + 1);
+        CU(cudaMemcpy(j->run_start_h.data(), j->run_start.p, 8 * (j->inputs.size() + 1), cudaMemcpyDeviceToHost));
+      }
+      if (run < 0 || run >= (int)j->inputs.size()) return fail(B200C_ERR_INVALID_ARGUMENT, "bad run index");
+      uint64_t first = j->run_start_h[run], n = j->run_start_h[run + 1] - first;
+      return what == B200C_DBG_DECODED_KEYS ? read_keys(j->dec, first, n) : read_values(j->dec, first, n);
+    }
+    case B200C_DBG_MERGED_KEYS:
+      if (j->stage_done < 2) return fail(B200C_ERR_STATE, "merge stage has not run");
+      return read_keys(j->mrg, 0, j->n_out);
+    case B200C_DBG_MERGED_VALUES:
+      if (j->stage_done < 2) return fail(B200C_ERR_STATE, "merge stage has not run");
+      return read_values(j->mrg, 0, j->n_out);
+    case B200C_DBG_BLOCK_LIST: {
+      if (j->stage_done < 3) return fail(B200C_ERR_STATE, "encode stage has not run");
+      *len = j->nblocks_out * sizeof(BlockRec);
+      if (dst && cap >= *len && *len) CU(cudaMemcpy(dst, j->blocks.p, *len, cudaMemcpyDeviceToHost));
+      return B200C_OK;
+    }
+  }
+  return fail(B200C_ERR_INVALID_ARGUMENT, "unknown debug array");
+}
+
+int b200c_block_checksums(int device, uint32_t type, const void* host_data, const uint64_t* offsets, uint32_t n, uint8_t last_byte,
+                          uint32_t* out) {
+  if (!host_data || !offsets || !out) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  int cnt = b200c_device_count();
+  if (cnt <= 0) return fail(B200C_ERR_NO_DEVICE, "no CUDA device");
+  CU(cudaSetDevice(device));
+  DevBuf d, o, r;
+  uint64_t total = offsets[n];
+  CU(d.reserve(total + 16));
+  CU(o.reserve(8 * (n + 1)));
+  CU(r.reserve(4 * (n + 1)));
+  CU(cudaMemcpy(d.p, host_data, total, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(o.p, offsets, 8 * (n + 1), cudaMemcpyHostToDevice));
+  launch_block_checksums(type, d.as<uint8_t>(), o.as<uint64_t>(), n, last_byte, r.as<uint32_t>(), 0);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out, r.p, 4 * n, cudaMemcpyDeviceToHost));
+  d.release();
+  o.release();
+  r.release();
+  return B200C_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,376 @@
+// toplingdb_b200/csrc/common.cuh — device-side building blocks shared by the decode / merge / encode kernels.
+// sm_100a only.  Formats follow the reference (paths relative to /root/reference):
+//   internal key   db/dbformat.h:99-178        varints util/coding.h       block layout table/block_based/block_builder.cc:21-32
+//   XXH3-64        util/xxhash.h:3644-5235     block checksum table/format.cc:436-509
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200c {
+
+// ---- error word (device) : first error wins per class, host maps to b200c_status ---------------------------
+enum DevErr : uint32_t {
+  kErrNone = 0,
+  kErrCorruptBlock = 1u << 0,    // malformed entry / restart array / handle out of range
+  kErrChecksum = 1u << 1,        // block checksum mismatch
+  kErrKeyTooLong = 1u << 2,      // user key > 16 bytes
+  kErrValueTooLong = 1u << 3,    // value >= 2^27 bytes
+  kErrBadType = 1u << 4,         // value type outside {kTypeDeletion, kTypeValue}
+  kErrCompressed = 1u << 5,      // block compression type != kNoCompression
+  kErrKeyOrder = 1u << 6,        // input run not strictly sorted / partition invariant broken
+  kErrBlockTooLong = 1u << 7,    // more entries in one output block than the encoder's window
+  kErrInternal = 1u << 8,
+  kErrCountMismatch = 1u << 9,   // entry count differs from rocksdb.num.entries
+};
+
+constexpr int kMaxUserKey = 16;
+constexpr uint32_t kMetaVlenBits = 27;
+constexpr uint32_t kMetaVlenMask = (1u << kMetaVlenBits) - 1;
+constexpr uint64_t kMaxSeq = (1ull << 56) - 1;
+constexpr uint8_t kTypeDeletion = 0, kTypeValue = 1;
+
+__host__ __device__ __forceinline__ uint32_t make_meta(uint32_t ulen, uint32_t vlen) { return (ulen << kMetaVlenBits) | vlen; }
+__host__ __device__ __forceinline__ uint32_t meta_ulen(uint32_t m) { return m >> kMetaVlenBits; }
+__host__ __device__ __forceinline__ uint32_t meta_vlen(uint32_t m) { return m & kMetaVlenMask; }
+
+// One sorted run / the merged stream, columnar in HBM.  hi/lo = first 16 user-key bytes as two big-endian
+// integers (zero padded) so that bytewise user-key order == (hi, lo, ulen) order; tr = (seq << 8) | type.
+struct KeyCols {
+  const ulonglong2* pfx;  // .x = hi, .y = lo
+  const uint64_t* tr;
+  const uint64_t* vref;   // device address of the value bytes (inside the input file image)
+  const uint32_t* meta;   // ulen << 27 | vlen
+  uint64_t n;
+};
+struct KeyColsMut {
+  ulonglong2* pfx;
+  uint64_t* tr;
+  uint64_t* vref;
+  uint32_t* meta;
+};
+
+// ---- unaligned little-endian loads from generic (global or shared) memory ---------------------------------
+__device__ __forceinline__ uint32_t ld_u32(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ uint64_t ld_u64(const uint8_t* p) { return (uint64_t)ld_u32(p) | ((uint64_t)ld_u32(p + 4) << 32); }
+
+// varint32/64 decode; returns bytes consumed or 0 on malformed / overrun
+__device__ __forceinline__ int get_varint(const uint8_t* p, const uint8_t* end, uint64_t* v) {
+  uint64_t r = 0;
+  int n = 0;
+#pragma unroll 1
+  for (int s = 0; s <= 63; s += 7) {
+    if (p + n >= end) return 0;
+    uint8_t c = p[n++];
+    r |= (uint64_t)(c & 127) << s;
+    if (c < 128) {
+      *v = r;
+      return n;
+    }
+  }
+  return 0;
+}
+__host__ __device__ __forceinline__ int varint_len(uint64_t v) {
+  int n = 1;
+  while (v >= 128) {
+    v >>= 7;
+    n++;
+  }
+  return n;
+}
+__host__ __device__ __forceinline__ int put_varint(uint8_t* p, uint64_t v) {
+  int n = 0;
+  while (v >= 128) {
+    p[n++] = (uint8_t)(v | 128);
+    v >>= 7;
+  }
+  p[n++] = (uint8_t)v;
+  return n;
+}
+
+// ---- key order (BytewiseCompareInternalKey, db/dbformat.h:1057-1097) ---------------------------------------
+struct Key {
+  uint64_t hi, lo, tr;
+  uint32_t ulen;
+};
+// user key compare: <0, 0, >0
+__device__ __forceinline__ int ukey_cmp(uint64_t ahi, uint64_t alo, uint32_t alen, uint64_t bhi, uint64_t blo, uint32_t blen) {
+  if (ahi != bhi) return ahi < bhi ? -1 : 1;
+  if (alo != blo) return alo < blo ? -1 : 1;
+  return (int)alen - (int)blen;  // equal zero-padded prefix: the shorter key is a proper prefix => smaller
+}
+__device__ __forceinline__ bool ikey_less(const Key& a, const Key& b) {
+  int c = ukey_cmp(a.hi, a.lo, a.ulen, b.hi, b.lo, b.ulen);
+  if (c) return c < 0;
+  return a.tr > b.tr;  // larger (seq,type) first
+}
+
+// ---- XXH3-64, seed 0, default secret ------------------------------------------------------------------------
+static __device__ __constant__ uint8_t kXxhSecret[192] = {
+    0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c, 0xde, 0xd4, 0x6d, 0xe9,
+    0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f, 0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78,
+    0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21, 0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6,
+    0x81, 0x3a, 0x26, 0x4c, 0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
+    0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8, 0xa8, 0xfa, 0x76, 0x3f,
+    0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d, 0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31,
+    0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64, 0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff,
+    0xfa, 0x13, 0x63, 0xeb, 0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
+    0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce, 0x45, 0xcb, 0x3a, 0x8f,
+    0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e};
+constexpr uint64_t kP32_1 = 0x9E3779B1ull, kP32_2 = 0x85EBCA77ull, kP32_3 = 0xC2B2AE3Dull;
+constexpr uint64_t kP64_1 = 0x9E3779B185EBCA87ull, kP64_2 = 0xC2B2AE3D27D4EB4Full, kP64_3 = 0x165667B19E3779F9ull,
+                   kP64_4 = 0x85EBCA77C2B2AE63ull, kP64_5 = 0x27D4EB2F165667C5ull;
+
+__device__ __forceinline__ uint64_t sec64(int off) {  // unaligned read of the constant secret
+  uint64_t v = 0;
+#pragma unroll
+  for (int i = 7; i >= 0; --i) v = (v << 8) | kXxhSecret[off + i];
+  return v;
+}
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t bswap64(uint64_t x) {
+  return ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(x >> 32), 0, 0x0123);
+}
+__device__ __forceinline__ uint64_t mul128_fold64(uint64_t a, uint64_t b) { return (a * b) ^ __umul64hi(a, b); }
+__device__ __forceinline__ uint64_t xxh64_avalanche(uint64_t h) {
+  h ^= h >> 33;
+  h *= kP64_2;
+  h ^= h >> 29;
+  h *= kP64_3;
+  h ^= h >> 32;
+  return h;
+}
+__device__ __forceinline__ uint64_t xxh3_avalanche(uint64_t h) {
+  h ^= h >> 37;
+  h *= 0x165667919E3779F9ull;
+  h ^= h >> 32;
+  return h;
+}
+__device__ __forceinline__ uint64_t xxh_mix16(const uint8_t* in, int soff) {
+  return mul128_fold64(ld_u64(in) ^ sec64(soff), ld_u64(in + 8) ^ sec64(soff + 8));
+}
+// inputs of at most 240 bytes: evaluated by a single thread (every lane of a warp may call it redundantly)
+__device__ inline uint64_t xxh3_64_short(const uint8_t* in, uint32_t len) {
+  if (len <= 16) {
+    if (len > 8) {
+      uint64_t lo = ld_u64(in) ^ (sec64(24) ^ sec64(32)), hi = ld_u64(in + len - 8) ^ (sec64(40) ^ sec64(48));
+      return xxh3_avalanche(len + bswap64(lo) + hi + mul128_fold64(lo, hi));
+    }
+    if (len >= 4) {
+      uint64_t i1 = ld_u32(in), i2 = ld_u32(in + len - 4);
+      uint64_t h = (i2 + (i1 << 32)) ^ (sec64(8) ^ sec64(16));
+      h ^= rotl64(h, 49) ^ rotl64(h, 24);
+      h *= 0x9FB21C651E98DF25ull;
+      h ^= (h >> 35) + len;
+      h *= 0x9FB21C651E98DF25ull;
+      return h ^ (h >> 28);
+    }
+    if (len) {
+      uint32_t c = ((uint32_t)in[0] << 16) | ((uint32_t)in[len >> 1] << 24) | in[len - 1] | (len << 8);
+      uint32_t s0 = (uint32_t)sec64(0), s1 = (uint32_t)(sec64(0) >> 32);
+      return xxh64_avalanche((uint64_t)c ^ (uint64_t)(s0 ^ s1));
+    }
+    return xxh64_avalanche(sec64(56) ^ sec64(64));
+  }
+  if (len <= 128) {
+    uint64_t acc = len * kP64_1, acc_end;
+    acc += xxh_mix16(in, 0);
+    acc_end = xxh_mix16(in + len - 16, 16);
+    if (len > 32) {
+      acc += xxh_mix16(in + 16, 32);
+      acc_end += xxh_mix16(in + len - 32, 48);
+      if (len > 64) {
+        acc += xxh_mix16(in + 32, 64);
+        acc_end += xxh_mix16(in + len - 48, 80);
+        if (len > 96) {
+          acc += xxh_mix16(in + 48, 96);
+          acc_end += xxh_mix16(in + len - 64, 112);
+        }
+      }
+    }
+    return xxh3_avalanche(acc + acc_end);
+  }
+  uint64_t acc = len * kP64_1, acc_end;
+  uint32_t rounds = len / 16;
+  for (uint32_t i = 0; i < 8; i++) acc += xxh_mix16(in + 16 * i, 16 * i);
+  acc_end = xxh_mix16(in + len - 16, 136 - 17);
+  acc = xxh3_avalanche(acc);
+  for (uint32_t i = 8; i < rounds; i++) acc_end += xxh_mix16(in + 16 * i, 16 * (i - 8) + 3);
+  return xxh3_avalanche(acc + acc_end);
+}
+
+// Warp-cooperative XXH3-64 of a buffer in generic memory (all 32 lanes call with identical arguments; every
+// lane returns the hash).  Long inputs: lane l owns accumulator lane (l & 7) of stripe group (l >> 3); the four
+// groups take stripes g, g+4, ... of each 1024-byte block, partial sums are folded with shuffles before the
+// scramble (additions commute inside a block; the scramble is the only sequential step).
+__device__ inline uint64_t xxh3_64_warp(const uint8_t* in, uint64_t len) {
+  const unsigned lane = threadIdx.x & 31;
+  if (len <= 240) return xxh3_64_short(in, (uint32_t)len);
+  const int a = lane & 7, g = lane >> 3;
+  const uint64_t init[8] = {kP32_3, kP64_1, kP64_2, kP64_3, kP64_4, kP32_2, kP64_5, kP32_1};
+  uint64_t acc = init[a];  // authoritative copy lives in lanes 0..7 (identical in the other groups after each fold)
+  const uint64_t nb_blocks = (len - 1) / 1024;
+  // per-lane secret words for stripes s = g, g+4, g+8, g+12 (secret offset 8*s + 8*a)
+  uint64_t ksec[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) ksec[i] = sec64(8 * (g + 4 * i) + 8 * a);
+  const uint64_t kscr = sec64(192 - 64 + 8 * a);
+  for (uint64_t n = 0; n <= nb_blocks; n++) {
+    const uint8_t* blk = in + n * 1024;
+    uint64_t nstripes = n < nb_blocks ? 16 : ((len - 1) - 1024 * nb_blocks) / 64;
+    uint64_t mul = 0, add = 0;  // contribution to acc[a] (product) and acc[a^1] (raw data)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint64_t s = g + 4 * i;
+      if (s < nstripes) {
+        uint64_t dv = ld_u64(blk + 64 * s + 8 * a), dk = dv ^ ksec[i];
+        mul += (dk & 0xffffffffull) * (dk >> 32);
+        add += dv;
+      }
+    }
+    uint64_t add_sw = __shfl_xor_sync(0xffffffffu, add, 1);  // raw data goes to the neighbouring accumulator lane
+    uint64_t part = mul + add_sw;
+    part += __shfl_xor_sync(0xffffffffu, part, 8);
+    part += __shfl_xor_sync(0xffffffffu, part, 16);
+    acc += part;
+    if (n < nb_blocks) {
+      acc ^= acc >> 47;
+      acc ^= kscr;
+      acc *= kP32_1;
+    }
+  }
+  // last stripe: input + len - 64 with secret offset 192 - 64 - 7
+  {
+    uint64_t dv = ld_u64(in + len - 64 + 8 * a), dk = dv ^ sec64(192 - 64 - 7 + 8 * a);
+    uint64_t mul = (dk & 0xffffffffull) * (dk >> 32);
+    uint64_t add_sw = __shfl_xor_sync(0xffffffffu, dv, 1);
+    acc += mul + add_sw;
+  }
+  // merge: result = len*P64_1 + sum_i fold(acc[2i] ^ sec(11+16i), acc[2i+1] ^ sec(11+16i+8))
+  uint64_t keyed = acc ^ sec64(11 + 8 * a);
+  uint64_t other = __shfl_xor_sync(0xffffffffu, keyed, 1);
+  uint64_t m = (a & 1) ? 0 : mul128_fold64(keyed, other);
+  m += __shfl_xor_sync(0xffffffffu, m, 2);
+  m += __shfl_xor_sync(0xffffffffu, m, 4);
+  uint64_t r = xxh3_avalanche(len * kP64_1 + m);
+  return __shfl_sync(0xffffffffu, r, 0);
+}
+
+// CRC32C (Castagnoli, reflected polynomial 0x82F63B78) — byte-wise table step used by the warp routine below.
+static __device__ __constant__ uint32_t kCrcTable[256] = {
+    0x00000000u, 0xf26b8303u, 0xe13b70f7u, 0x1350f3f4u, 0xc79a971fu, 0x35f1141cu, 0x26a1e7e8u, 0xd4ca64ebu,
+    0x8ad958cfu, 0x78b2dbccu, 0x6be22838u, 0x9989ab3bu, 0x4d43cfd0u, 0xbf284cd3u, 0xac78bf27u, 0x5e133c24u,
+    0x105ec76fu, 0xe235446cu, 0xf165b798u, 0x030e349bu, 0xd7c45070u, 0x25afd373u, 0x36ff2087u, 0xc494a384u,
+    0x9a879fa0u, 0x68ec1ca3u, 0x7bbcef57u, 0x89d76c54u, 0x5d1d08bfu, 0xaf768bbcu, 0xbc267848u, 0x4e4dfb4bu,
+    0x20bd8edeu, 0xd2d60dddu, 0xc186fe29u, 0x33ed7d2au, 0xe72719c1u, 0x154c9ac2u, 0x061c6936u, 0xf477ea35u,
+    0xaa64d611u, 0x580f5512u, 0x4b5fa6e6u, 0xb93425e5u, 0x6dfe410eu, 0x9f95c20du, 0x8cc531f9u, 0x7eaeb2fau,
+    0x30e349b1u, 0xc288cab2u, 0xd1d83946u, 0x23b3ba45u, 0xf779deaeu, 0x05125dadu, 0x1642ae59u, 0xe4292d5au,
+    0xba3a117eu, 0x4851927du, 0x5b016189u, 0xa96ae28au, 0x7da08661u, 0x8fcb0562u, 0x9c9bf696u, 0x6ef07595u,
+    0x417b1dbcu, 0xb3109ebfu, 0xa0406d4bu, 0x522bee48u, 0x86e18aa3u, 0x748a09a0u, 0x67dafa54u, 0x95b17957u,
+    0xcba24573u, 0x39c9c670u, 0x2a993584u, 0xd8f2b687u, 0x0c38d26cu, 0xfe53516fu, 0xed03a29bu, 0x1f682198u,
+    0x5125dad3u, 0xa34e59d0u, 0xb01eaa24u, 0x42752927u, 0x96bf4dccu, 0x64d4cecfu, 0x77843d3bu, 0x85efbe38u,
+    0xdbfc821cu, 0x2997011fu, 0x3ac7f2ebu, 0xc8ac71e8u, 0x1c661503u, 0xee0d9600u, 0xfd5d65f4u, 0x0f36e6f7u,
+    0x61c69362u, 0x93ad1061u, 0x80fde395u, 0x72966096u, 0xa65c047du, 0x5437877eu, 0x4767748au, 0xb50cf789u,
+    0xeb1fcbadu, 0x197448aeu, 0x0a24bb5au, 0xf84f3859u, 0x2c855cb2u, 0xdeeedfb1u, 0xcdbe2c45u, 0x3fd5af46u,
+    0x7198540du, 0x83f3d70eu, 0x90a324fau, 0x62c8a7f9u, 0xb602c312u, 0x44694011u, 0x5739b3e5u, 0xa55230e6u,
+    0xfb410cc2u, 0x092a8fc1u, 0x1a7a7c35u, 0xe811ff36u, 0x3cdb9bddu, 0xceb018deu, 0xdde0eb2au, 0x2f8b6829u,
+    0x82f63b78u, 0x709db87bu, 0x63cd4b8fu, 0x91a6c88cu, 0x456cac67u, 0xb7072f64u, 0xa457dc90u, 0x563c5f93u,
+    0x082f63b7u, 0xfa44e0b4u, 0xe9141340u, 0x1b7f9043u, 0xcfb5f4a8u, 0x3dde77abu, 0x2e8e845fu, 0xdce5075cu,
+    0x92a8fc17u, 0x60c37f14u, 0x73938ce0u, 0x81f80fe3u, 0x55326b08u, 0xa759e80bu, 0xb4091bffu, 0x466298fcu,
+    0x1871a4d8u, 0xea1a27dbu, 0xf94ad42fu, 0x0b21572cu, 0xdfeb33c7u, 0x2d80b0c4u, 0x3ed04330u, 0xccbbc033u,
+    0xa24bb5a6u, 0x502036a5u, 0x4370c551u, 0xb11b4652u, 0x65d122b9u, 0x97baa1bau, 0x84ea524eu, 0x7681d14du,
+    0x2892ed69u, 0xdaf96e6au, 0xc9a99d9eu, 0x3bc21e9du, 0xef087a76u, 0x1d63f975u, 0x0e330a81u, 0xfc588982u,
+    0xb21572c9u, 0x407ef1cau, 0x532e023eu, 0xa145813du, 0x758fe5d6u, 0x87e466d5u, 0x94b49521u, 0x66df1622u,
+    0x38cc2a06u, 0xcaa7a905u, 0xd9f75af1u, 0x2b9cd9f2u, 0xff56bd19u, 0x0d3d3e1au, 0x1e6dcdeeu, 0xec064eedu,
+    0xc38d26c4u, 0x31e6a5c7u, 0x22b65633u, 0xd0ddd530u, 0x0417b1dbu, 0xf67c32d8u, 0xe52cc12cu, 0x1747422fu,
+    0x49547e0bu, 0xbb3ffd08u, 0xa86f0efcu, 0x5a048dffu, 0x8ecee914u, 0x7ca56a17u, 0x6ff599e3u, 0x9d9e1ae0u,
+    0xd3d3e1abu, 0x21b862a8u, 0x32e8915cu, 0xc083125fu, 0x144976b4u, 0xe622f5b7u, 0xf5720643u, 0x07198540u,
+    0x590ab964u, 0xab613a67u, 0xb831c993u, 0x4a5a4a90u, 0x9e902e7bu, 0x6cfbad78u, 0x7fab5e8cu, 0x8dc0dd8fu,
+    0xe330a81au, 0x115b2b19u, 0x020bd8edu, 0xf0605beeu, 0x24aa3f05u, 0xd6c1bc06u, 0xc5914ff2u, 0x37faccf1u,
+    0x69e9f0d5u, 0x9b8273d6u, 0x88d28022u, 0x7ab90321u, 0xae7367cau, 0x5c18e4c9u, 0x4f48173du, 0xbd23943eu,
+    0xf36e6f75u, 0x0105ec76u, 0x12551f82u, 0xe03e9c81u, 0x34f4f86au, 0xc69f7b69u, 0xd5cf889du, 0x27a40b9eu,
+    0x79b737bau, 0x8bdcb4b9u, 0x988c474du, 0x6ae7c44eu, 0xbe2da0a5u, 0x4c4623a6u, 0x5f16d052u, 0xad7d5351u};
+__device__ __forceinline__ uint32_t crc32c_bytes(uint32_t c, const uint8_t* p, uint64_t n) {
+  for (uint64_t i = 0; i < n; i++) c = kCrcTable[(c ^ p[i]) & 0xff] ^ (c >> 8);
+  return c;
+}
+// multiply two polynomials mod the CRC32C polynomial (reflected representation)
+__device__ __forceinline__ uint32_t crc_gf_mul(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+#pragma unroll 1
+  for (int i = 0; i < 32; i++) {
+    p ^= (b & 0x80000000u) ? a : 0;
+    a = (a >> 1) ^ ((a & 1) ? 0x82F63B78u : 0);
+    b <<= 1;
+  }
+  return p;
+}
+// x^(8*nbytes) mod P, reflected
+__device__ inline uint32_t crc_xpow8n(uint64_t nbytes) {
+  uint32_t r = 0x80000000u;      // x^0
+  uint32_t base = 0x00800000u;   // x^8
+  while (nbytes) {
+    if (nbytes & 1) r = crc_gf_mul(r, base);
+    base = crc_gf_mul(base, base);
+    nbytes >>= 1;
+  }
+  return r;
+}
+// Warp-cooperative raw CRC state update over a buffer: returns crc32c::Extend(init=0) style *unfinalised* value
+// handling (internal state with pre/post inversion applied by caller).  Each lane CRCs a contiguous slice with a
+// zero initial state; slices are combined left to right: state = state * x^(8*len_slice) + crc_slice.
+__device__ inline uint32_t crc32c_value_warp(const uint8_t* in, uint64_t len) {
+  const unsigned lane = threadIdx.x & 31;
+  uint64_t per = (len + 31) / 32;
+  uint64_t b = per * lane < len ? per * lane : len, e = per * (lane + 1) < len ? per * (lane + 1) : len;
+  // raw polynomial remainder of the slice (no inversion): start state 0 except lane 0 which carries the 0xffffffff preset
+  uint32_t c = crc32c_bytes(lane == 0 ? 0xffffffffu : 0u, in + b, e - b);
+  uint64_t mylen = e - b;
+  // inclusive combine (left fold) via log-step scan: state over [0, end_of_lane)
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t pc = __shfl_up_sync(0xffffffffu, c, d);
+    uint64_t plen = __shfl_up_sync(0xffffffffu, mylen, d);
+    if ((int)lane >= d) {
+      c = crc_gf_mul(pc, crc_xpow8n(mylen)) ^ c;
+      mylen += plen;
+    }
+  }
+  uint32_t total = __shfl_sync(0xffffffffu, c, 31);
+  return total ^ 0xffffffffu;
+}
+__device__ __forceinline__ uint32_t crc32c_mask(uint32_t crc) { return ((crc >> 15) | (crc << 17)) + 0xa282ead8u; }
+
+// ComputeBuiltinChecksumWithLastByte (table/format.cc:468-509); warp-cooperative, all lanes get the value.
+__device__ inline uint32_t block_checksum_warp(uint32_t type, const uint8_t* data, uint64_t n, uint8_t last_byte) {
+  if (type == 4) return (uint32_t)xxh3_64_warp(data, n) ^ (uint32_t)last_byte * 0x6b9083d9u;
+  if (type == 1) {
+    uint32_t crc = crc32c_value_warp(data, n);
+    uint32_t c = crc ^ 0xffffffffu;
+    c = kCrcTable[(c ^ last_byte) & 0xff] ^ (c >> 8);
+    return crc32c_mask(c ^ 0xffffffffu);
+  }
+  return 0;
+}
+
+// ---- warp scans ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((int)lane >= d) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ uint64_t warp_incl_scan64(uint64_t v) {
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((int)lane >= d) v += t;
+  }
+  return v;
+}
+
+}  // namespace b200c

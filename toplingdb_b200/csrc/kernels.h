@@ -1,0 +1,129 @@
+// toplingdb_b200/csrc/kernels.h — host-visible declarations of the kernel launchers (decode.cu, merge.cu, encode.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace b200c {
+
+struct FileDesc {          // one input BlockBasedTable image resident in HBM
+  const uint8_t* base;
+  uint64_t len;
+  uint64_t index_off;
+  uint32_t index_size;
+  uint32_t value_delta;    // index values delta-encoded (format_version >= 4)
+  uint32_t cksum;          // footer checksum type
+  uint32_t gblk_first;     // first global data-block number of this file
+  uint32_t nblocks;        // rocksdb.num.data.blocks
+  uint32_t pad;
+};
+
+// ---- decode.cu
+void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blocks_per_file, uint64_t* blk_off,
+                         uint32_t* blk_size, uint32_t* err, cudaStream_t st);
+void launch_block_count(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
+                        uint32_t nblk, uint32_t verify, uint32_t* blk_cnt, uint32_t* err, int sms, cudaStream_t st);
+void launch_block_decode(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
+                         const uint64_t* blk_base, uint32_t nblk, uint64_t n_total, KeyColsMut out, uint32_t* err, int sms,
+                         cudaStream_t st);
+void launch_run_starts(const FileDesc* files_dev, int nfiles, const uint64_t* blk_base, const uint64_t* total, uint32_t nblk,
+                       uint64_t* run_start, cudaStream_t st);
+void launch_gather_values(KeyCols in, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st);
+void launch_meta_vlen(const uint32_t* meta, uint64_t n, uint32_t* vlen, cudaStream_t st);
+
+// ---- merge.cu
+constexpr int kMergeTile = 2048;     // merged entries per CTA tile
+constexpr int kMaxRuns = 64;
+struct MergeParams {
+  uint32_t nruns;
+  uint32_t bottommost;               // Compaction::bottommost_level()
+  uint32_t nsnapshots;
+  const uint64_t* snapshots;         // device, ascending
+  uint64_t earliest_snapshot;        // snapshots[0] or kMaxSeq
+};
+struct MergeCounters {               // device-side CompactionIterationStats
+  unsigned long long n_out, n_input_deletions, n_hidden, n_obsolete, raw_key_bytes, raw_value_bytes, n_silent;
+};
+// splits: (ntiles + 1) x nruns u64; tile_state: ntiles u64 (zeroed); ticket: u32 (zeroed)
+void launch_merge_partition(KeyCols in, const uint64_t* run_start, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
+                            uint64_t* splits, uint32_t* err, cudaStream_t st);
+void launch_merge_tiles(KeyCols in, const uint64_t* run_start, MergeParams mp, uint64_t n_total, uint64_t ntiles,
+                        const uint64_t* splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
+                        MergeCounters* counters, uint32_t* err, cudaStream_t st);
+
+// ---- encode.cu
+struct EncodeParams {
+  uint32_t block_size, block_size_limit /* ceil(block_size*(100-deviation)/100), 0 = disabled */, restart_interval;
+  uint32_t checksum, format_version, output_level;
+  uint64_t max_output_file_size;
+};
+struct BlockRec {            // one output data block
+  uint64_t first_entry;
+  uint64_t file_off;         // offset of the block payload inside its file
+  uint32_t file_idx;
+  uint32_t n_entries;
+};
+struct KeyRec {
+  uint64_t hi, lo, tr;
+  uint32_t ulen, pad;
+};
+struct FileRec {             // one output file (device-computed part)
+  uint64_t first_entry, n_entries;
+  uint64_t first_block, n_blocks;
+  uint64_t data_size;        // bytes of data blocks incl. trailers
+  uint64_t index_size;       // index block payload bytes (without trailer)
+  uint64_t raw_key_size, raw_value_size, num_deletions;
+  uint64_t smallest_seq, largest_seq;
+  KeyRec smallest, largest;
+  uint32_t index_has_seq;    // some adjacent blocks share a user key => index keys keep the 8-byte trailer
+  uint32_t index_cksum;      // checksum word of the index block trailer
+};
+struct TileRow {             // block-cut transfer function of one tile for one entry-point candidate
+  uint32_t exit;             // chain exit, entries past the tile end
+  uint32_t nblk;             // blocks started inside the tile
+  uint64_t bytes;            // on-disk bytes (payload + 5) of those blocks
+};
+struct TileState {           // resolved state when the chain enters a tile
+  uint64_t entry;            // absolute index of the first block start at/after the tile start
+  uint64_t blk;              // index of that block
+  uint64_t file_off;         // bytes already flushed to the current file
+  uint32_t file_idx;
+  uint32_t pad;
+};
+constexpr int kEncTile = 4096;       // entries per block-cut tile
+constexpr int kEncHalo = 2048;       // look-ahead window = the longest block (in entries) the encoder accepts
+constexpr uint32_t kMaxOutFiles = 4096;
+
+struct EncodeWork {                  // device scratch owned by the job
+  uint32_t* esz;        // n: encoded size of entry i as a non-restart entry (s1)
+  uint8_t* eshared;     // n: bytes shared with the previous internal key
+  uint32_t* min_s1;     // 1: global min of esz (bounds the entry-point candidate window)
+  TileRow* rows;        // ntiles x hc
+  TileState* tstate;    // ntiles
+  uint64_t* totals;     // [0] = number of blocks, [1] = number of files
+  BlockRec* blocks;     // capacity nblk_cap
+  FileRec* files;       // kMaxOutFiles
+  uint32_t* idx_esz;    // per block: encoded index entry size
+  uint64_t* idx_eoff;   // per block: exclusive scan of idx_esz (global; file-relative after subtracting the file's first)
+  KeyRec* idx_sep;      // per block: separator key (ulen excludes the trailer; pad=1 when the trailer was replaced)
+  uint64_t* scan_tmp;
+  uint16_t* nxt;        // n: tile-relative end of the block that would start at entry i
+  uint32_t* disk;       // n: on-disk bytes of that block
+};
+void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, uint64_t n_cap, cudaStream_t st);
+void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st);
+void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st);
+void launch_encode_blocklist(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint64_t nblk_cap, uint32_t* err,
+                             cudaStream_t st);
+void launch_encode_filestats(KeyCols m, EncodeWork w, uint32_t nfiles, int sms, cudaStream_t st);
+uint32_t encode_emit_slice(uint32_t block_size);
+// out_base[f] = device address where file f's image starts; slice = shared-memory bytes per warp
+void launch_encode_emit(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nblocks, uint8_t* const* out_base, uint32_t* err,
+                        int sms, cudaStream_t st);
+void launch_encode_index(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nblocks, uint32_t nfiles, uint8_t* const* out_base,
+                         uint32_t* err, cudaStream_t st, uint64_t* launches);
+void launch_block_checksums(uint32_t type, const uint8_t* data, const uint64_t* offsets, uint32_t n, uint8_t last_byte,
+                            uint32_t* out, cudaStream_t st);
+
+}  // namespace b200c

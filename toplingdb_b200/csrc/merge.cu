@@ -1,0 +1,576 @@
+// toplingdb_b200/csrc/merge.cu — the k-way merge with the compaction-iterator rules, on the device.
+//
+// Replaces CompactionMergingIterTmpl (table/compaction_merging_iterator.cc:10-402; heap of children, util/heap.h)
+// + BytewiseCompareInternalKey (db/dbformat.h:1057-1097) + CompactionIterator::NextFromInput / PrepareOutput
+// (db/compaction/compaction_iterator.cc:475-1087,1274-1341) for kTypeValue / kTypeDeletion entries.
+//
+// Two kernels:
+//   merge_partition_kernel  one warp per tile boundary: exact k-way merge-path split (multi-sequence selection;
+//                           lanes own runs and bisect them in parallel against a common pivot)
+//   merge_tiles_kernel      one CTA per tile of kMergeTile merged entries: coalesced load of the k segments into
+//                           shared memory, log2(k) rounds of pairwise merge-path merges (in place through
+//                           registers), drop rules against the in-tile predecessor, decoupled look-back for the
+//                           output offset, coalesced write of the surviving (key, value-ref) records.
+// HBM-bound: algorithmic bytes = 36 B read per input entry + 36 B written per surviving entry.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200c {
+
+constexpr int kMT = kMergeTile;
+constexpr int kMThreads = 256;
+constexpr int kMV = kMT / kMThreads;  // 8 merged entries per thread
+
+__device__ __forceinline__ Key load_key(const KeyCols& c, uint64_t i) {
+  Key k;
+  ulonglong2 p = c.pfx[i];
+  k.hi = p.x;
+  k.lo = p.y;
+  k.tr = c.tr[i];
+  k.ulen = meta_ulen(c.meta[i]);
+  return k;
+}
+
+// number of elements of run [base+lo, base+hi) that precede pivot X in the total order (key, run index):
+// before_equal == true counts elements <= X (runs with a smaller index than the pivot's run)
+__device__ __forceinline__ uint64_t count_before(const KeyCols& c, uint64_t base, uint64_t lo, uint64_t hi, const Key& x,
+                                                 bool before_equal) {
+  while (lo < hi) {
+    uint64_t mid = lo + ((hi - lo) >> 1);
+    Key e = load_key(c, base + mid);
+    bool precedes = before_equal ? !ikey_less(x, e) : ikey_less(e, x);
+    if (precedes) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128)
+merge_partition_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
+                       uint64_t* __restrict__ splits, uint32_t* __restrict__ err) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b > ntiles) return;
+  uint64_t d = b * (uint64_t)kMT;
+  if (d > n_total) d = n_total;
+  uint64_t base[2], lo[2], hi[2];
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    uint32_t r = lane + 32 * s;
+    base[s] = r < nruns ? run_start[r] : 0;
+    uint64_t n = r < nruns ? run_start[r + 1] - run_start[r] : 0;
+    lo[s] = (d == n_total) ? n : 0;
+    hi[s] = (d == 0) ? 0 : n;
+  }
+  for (int guard = 0; guard < 64 * 70; guard++) {
+    // widest bracket decides the pivot run
+    unsigned long long best = 0;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      unsigned long long wdt = hi[s] - lo[s];
+      unsigned long long enc = (wdt << 7) | (unsigned long long)(lane + 32 * s);
+      if (wdt && enc > best) best = enc;
+    }
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) {
+      unsigned long long o = __shfl_xor_sync(0xffffffffu, best, dd);
+      if (o > best) best = o;
+    }
+    if (best == 0) break;
+    const uint32_t p = (uint32_t)(best & 127);
+    const int ps = p >> 5, pl = p & 31;
+    uint64_t m = ps ? (lo[1] + ((hi[1] - lo[1]) >> 1)) : (lo[0] + ((hi[0] - lo[0]) >> 1));
+    m = __shfl_sync(0xffffffffu, m, pl);
+    uint64_t pbase = __shfl_sync(0xffffffffu, ps ? base[1] : base[0], pl);
+    const Key x = load_key(in, pbase + m);
+    uint64_t c[2], sum = 0;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      uint32_t r = lane + 32 * s;
+      if (r == p) c[s] = m;
+      else if (r < nruns) c[s] = count_before(in, base[s], lo[s], hi[s], x, r < p);
+      else c[s] = 0;
+      sum += c[s];
+    }
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
+    const bool x_before = sum < d;  // pivot is among the first d elements
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      uint32_t r = lane + 32 * s;
+      if (r >= nruns) continue;
+      if (x_before) lo[s] = (r == p) ? m + 1 : c[s];
+      else hi[s] = (r == p) ? m : c[s];
+    }
+  }
+  uint64_t tot = lo[0] + lo[1];
+#pragma unroll
+  for (int dd = 16; dd; dd >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, dd);
+  if (tot != d && lane == 0) atomicOr(err, kErrKeyOrder);
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    uint32_t r = lane + 32 * s;
+    if (r < nruns) splits[b * nruns + r] = lo[s];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ tile merge
+struct TileSmem {
+  uint64_t hi[kMT], lo[kMT], tr[kMT];
+  uint16_t m16[kMT];               // ulen << 11 | position in load order
+  uint32_t seg[kMaxRuns + 1];      // segment starts in load order
+  uint32_t lst[2][kMaxRuns + 2];   // list bounds per merge round (ping-pong)
+  uint64_t sbeg[kMaxRuns];         // absolute index of each segment's first element
+  uint64_t snaps[64];              // cached snapshots (first 64)
+  unsigned long long red[8];       // per-CTA counter staging
+  uint32_t wsum[40];
+  uint64_t base_out;
+  uint32_t tile_id, kept_total;
+  Key pred;
+  uint32_t has_pred;
+};
+
+__device__ __forceinline__ Key skey(const TileSmem& s, uint32_t i) {
+  Key k;
+  k.hi = s.hi[i];
+  k.lo = s.lo[i];
+  k.tr = s.tr[i];
+  k.ulen = s.m16[i] >> 11;
+  return k;
+}
+
+struct PairState {
+  uint32_t ai, a1, bi, b1, pend;  // cursors into A=[.., a1) and B=[.., b1); pend = end of this pair's output range
+  bool single;                    // unpaired list: copy through
+};
+// locate the pair containing output position o and run the merge-path search for its diagonal
+__device__ __noinline__ void init_pair(const TileSmem& s, const uint32_t* lst, uint32_t nlists, uint32_t o, PairState* ps) {
+  uint32_t pi = 0;
+  while (2 * pi + 2 <= nlists && lst[2 * pi + 2 <= nlists ? 2 * pi + 2 : nlists] <= o) pi++;
+  // pair pi covers lists 2pi and 2pi+1 (if present)
+  uint32_t a0 = lst[2 * pi];
+  uint32_t a1 = lst[2 * pi + 1];
+  bool single = 2 * pi + 1 >= nlists;
+  uint32_t b1 = single ? a1 : lst[2 * pi + 2];
+  ps->single = single;
+  ps->pend = b1;
+  ps->a1 = a1;
+  ps->b1 = b1;
+  if (single) {
+    ps->ai = o;
+    ps->bi = b1;
+    return;
+  }
+  uint32_t diag = o - a0, an = a1 - a0, bn = b1 - a1;
+  uint32_t lo = diag > bn ? diag - bn : 0, hi = diag < an ? diag : an;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    Key ka = skey(s, a0 + mid), kb = skey(s, a1 + diag - 1 - mid);
+    if (!ikey_less(kb, ka)) lo = mid + 1;  // a <= b: a goes first (stable, lower run index wins ties)
+    else hi = mid;
+  }
+  ps->ai = a0 + lo;
+  ps->bi = a1 + (diag - lo);
+}
+
+__device__ __forceinline__ uint64_t stripe_of(const uint64_t* snaps_s, const uint64_t* snaps_g, uint32_t ns, uint64_t seq,
+                                              uint64_t* prev) {
+  // findEarliestVisibleSnapshot (compaction_iterator.cc:1343-1396, no snapshot checker): lower_bound(seq)
+  uint32_t lo = 0, hi = ns;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    uint64_t v = mid < 64 ? snaps_s[mid] : snaps_g[mid];
+    if (v < seq) lo = mid + 1;
+    else hi = mid;
+  }
+  *prev = lo == 0 ? 0 : (lo - 1 < 64 ? snaps_s[lo - 1] : snaps_g[lo - 1]);
+  return lo < ns ? (lo < 64 ? snaps_s[lo] : snaps_g[lo]) : kMaxSeq;
+}
+
+// slow path helpers for groups that leave the tile (only with snapshots at the bottommost level)
+// oldest version of user key (hi,lo,ulen) over all runs has seq <= limit ?
+__device__ bool oldest_version_at_most(const KeyCols& in, const uint64_t* run_start, uint32_t nruns, uint64_t hi, uint64_t lo,
+                                       uint32_t ulen, uint64_t limit) {
+  Key x;
+  x.hi = hi;
+  x.lo = lo;
+  x.ulen = ulen;
+  x.tr = 0;  // (ukey, seq 0, type 0) sorts after every real version of ukey
+  for (uint32_t r = 0; r < nruns; r++) {
+    uint64_t base = run_start[r], n = run_start[r + 1] - base;
+    uint64_t c = count_before(in, base, 0, n, x, true);
+    if (c == 0) continue;
+    Key e = load_key(in, base + c - 1);
+    if (e.hi == hi && e.lo == lo && e.ulen == ulen && (e.tr >> 8) <= limit) return true;
+  }
+  return false;
+}
+// newest version of user key with seq <= stripe_hi: the head of that (user key, stripe) group
+__device__ bool group_head(const KeyCols& in, const uint64_t* run_start, uint32_t nruns, uint64_t hi, uint64_t lo, uint32_t ulen,
+                           uint64_t stripe_hi, uint64_t* head_tr) {
+  Key x;
+  x.hi = hi;
+  x.lo = lo;
+  x.ulen = ulen;
+  x.tr = (stripe_hi << 8) | 0xff;  // sorts before every version with seq <= stripe_hi
+  bool found = false;
+  uint64_t best = 0;
+  for (uint32_t r = 0; r < nruns; r++) {
+    uint64_t base = run_start[r], n = run_start[r + 1] - base;
+    uint64_t c = count_before(in, base, 0, n, x, false);
+    if (c >= n) continue;
+    Key e = load_key(in, base + c);
+    if (e.hi == hi && e.lo == lo && e.ulen == ulen && (!found || e.tr > best)) {
+      found = true;
+      best = e.tr;
+    }
+  }
+  *head_tr = best;
+  return found;
+}
+
+__global__ void __launch_bounds__(kMThreads)
+merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergeParams mp, uint64_t n_total, uint64_t ntiles,
+                   const uint64_t* __restrict__ splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
+                   MergeCounters* counters, uint32_t* __restrict__ err) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  TileSmem& s = *reinterpret_cast<TileSmem*>(smem_raw);
+  const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint32_t k = mp.nruns;
+  if (t == 0) s.tile_id = atomicAdd(ticket, 1u);
+  if (t < 8) s.red[t] = 0;
+  if (t < 64 && t < mp.nsnapshots) s.snaps[t] = mp.snapshots[t];
+  __syncthreads();
+  const uint64_t tile = s.tile_id;
+  if (tile >= ntiles) return;
+  // ---- segment table
+  if (t < k) {
+    uint64_t s0 = splits[tile * k + t], s1 = splits[(tile + 1) * k + t];
+    s.sbeg[t] = run_start[t] + s0;
+    s.lst[1][t] = (uint32_t)(s1 - s0);  // lengths, scanned below
+  }
+  __syncthreads();
+  if (t == 0) {
+    uint32_t acc = 0;
+    for (uint32_t r = 0; r < k; r++) {
+      s.seg[r] = acc;
+      s.lst[0][r] = acc;
+      acc += s.lst[1][r];
+    }
+    s.seg[k] = acc;
+    s.lst[0][k] = acc;
+    if (acc > kMT) {
+      atomicOr(err, kErrKeyOrder);
+      s.seg[k] = 0;
+    }
+    // predecessor of the tile in merged order = largest element before the split
+    s.has_pred = 0;
+    for (uint32_t r = 0; r < k; r++) {
+      uint64_t s0 = s.sbeg[r] - run_start[r];
+      if (s0 == 0) continue;
+      Key e = load_key(in, s.sbeg[r] - 1);
+      if (!s.has_pred || ikey_less(s.pred, e)) {
+        s.pred = e;
+        s.has_pred = 1;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t cnt = s.seg[k];
+  // ---- coalesced load of the k segments
+#pragma unroll
+  for (int j = 0; j < kMV; j++) {
+    uint32_t i = t + j * kMThreads;
+    if (i < cnt) {
+      uint32_t lo = 0, hi = k;  // run r with seg[r] <= i < seg[r+1]
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (s.seg[mid] <= i) lo = mid;
+        else hi = mid;
+      }
+      uint64_t src = s.sbeg[lo] + (i - s.seg[lo]);
+      ulonglong2 p = in.pfx[src];
+      s.hi[i] = p.x;
+      s.lo[i] = p.y;
+      s.tr[i] = in.tr[src];
+      s.m16[i] = (uint16_t)((meta_ulen(in.meta[src]) << 11) | i);
+    }
+  }
+  __syncthreads();
+  // ---- pairwise merge rounds, in place through registers
+  uint32_t nlists = k;
+  int cur = 0;
+  while (nlists > 1) {
+    const uint32_t* lst = s.lst[cur];
+    uint64_t rhi[kMV], rlo[kMV], rtr[kMV];
+    uint16_t rm[kMV];
+    const uint32_t o0 = t * kMV;
+    PairState ps;
+    ps.pend = 0;
+    ps.single = true;
+    ps.ai = ps.a1 = ps.bi = ps.b1 = 0;
+    Key ka, kb;
+    bool va = false, vb = false;
+#pragma unroll
+    for (int x = 0; x < kMV; x++) {
+      uint32_t o = o0 + x;
+      if (o < cnt) {
+        if (o >= ps.pend) {
+          init_pair(s, lst, nlists, o, &ps);
+          va = ps.ai < ps.a1;
+          vb = ps.bi < ps.b1;
+          if (va) ka = skey(s, ps.ai);
+          if (vb) kb = skey(s, ps.bi);
+        }
+        bool take_a = !vb || (va && !ikey_less(kb, ka));
+        uint32_t src = take_a ? ps.ai : ps.bi;
+        const Key& kk = take_a ? ka : kb;
+        rhi[x] = kk.hi;
+        rlo[x] = kk.lo;
+        rtr[x] = kk.tr;
+        rm[x] = s.m16[src];
+        if (take_a) {
+          ps.ai++;
+          va = ps.ai < ps.a1;
+          if (va) ka = skey(s, ps.ai);
+        } else {
+          ps.bi++;
+          vb = ps.bi < ps.b1;
+          if (vb) kb = skey(s, ps.bi);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int x = 0; x < kMV; x++) {
+      uint32_t o = o0 + x;
+      if (o < cnt) {
+        s.hi[o] = rhi[x];
+        s.lo[o] = rlo[x];
+        s.tr[o] = rtr[x];
+        s.m16[o] = rm[x];
+      }
+    }
+    // next round's list bounds
+    uint32_t nn = (nlists + 1) >> 1;
+    if (t <= nn) s.lst[cur ^ 1][t] = t == nn ? cnt : lst[2 * t];
+    __syncthreads();
+    nlists = nn;
+    cur ^= 1;
+  }
+  // ---- compaction-iterator rules per merged position
+  const bool cond_possible = mp.bottommost && mp.nsnapshots > 0;
+  uint32_t keep_mask = 0, nkeep = 0;
+  unsigned long long c_hidden = 0, c_obsolete = 0, c_indel = 0, c_kbytes = 0, c_vbytes = 0, c_silent = 0;
+  uint64_t otr[kMV];
+#pragma unroll
+  for (int x = 0; x < kMV; x++) {
+    uint32_t o = t * kMV + x;
+    otr[x] = 0;
+    if (o >= cnt) continue;
+    Key c = skey(s, o);
+    Key p;
+    bool has_prev = true;
+    if (o > 0) p = skey(s, o - 1);
+    else {
+      p = s.pred;
+      has_prev = s.has_pred != 0;
+    }
+    const bool same = has_prev && p.hi == c.hi && p.lo == c.lo && p.ulen == c.ulen;
+    const uint64_t seq = c.tr >> 8;
+    const uint32_t type = (uint32_t)(c.tr & 0xff);
+    uint64_t prev_snap = 0, dummy;
+    uint64_t st_c = mp.nsnapshots ? stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, seq, &prev_snap) : kMaxSeq;
+    bool hidden = same;
+    if (same && mp.nsnapshots) hidden = stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, p.tr >> 8, &dummy) == st_c;
+    bool keep = false, silent = false;
+    if (hidden) {
+      if (cond_possible && st_c != mp.earliest_snapshot) {
+        // did the head of this (user key, stripe) group take the bottommost-delete branch (:947-990)?  Its
+        // same-stripe followers are skipped there without touching any counter.
+        int q = (int)o - 1;
+        uint64_t head_tr = 0;
+        bool have = false;
+        while (q >= 0) {
+          Key h = skey(s, q);
+          uint64_t d2;
+          bool same_grp = h.hi == c.hi && h.lo == c.lo && h.ulen == c.ulen &&
+                          stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, h.tr >> 8, &d2) == st_c;
+          if (!same_grp) break;
+          head_tr = h.tr;
+          have = true;
+          q--;
+        }
+        if (q < 0 && s.has_pred) {  // group may start before the tile
+          uint64_t d2;
+          bool pred_same = s.pred.hi == c.hi && s.pred.lo == c.lo && s.pred.ulen == c.ulen &&
+                           stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, s.pred.tr >> 8, &d2) == st_c;
+          if (pred_same) have = group_head(in, run_start, k, c.hi, c.lo, c.ulen, st_c, &head_tr);
+        }
+        if (have && (head_tr & 0xff) == kTypeDeletion) silent = true;  // head seq > earliest snapshot since its stripe is not the first
+      }
+      if (!silent) c_hidden++;
+    } else if (type == kTypeDeletion && seq <= mp.earliest_snapshot && mp.bottommost) {
+      c_obsolete++;  // :912-946 (KeyNotExistsBeyondOutputLevel == bottommost on a worker, compaction.cc:555-556)
+    } else if (type == kTypeDeletion && mp.bottommost) {
+      // :947-990 keep the tombstone only if an older stripe still holds a version of this user key
+      bool resolved = false;
+      for (uint32_t q = o + 1; q < cnt; q++) {
+        Key nx = skey(s, q);
+        if (!(nx.hi == c.hi && nx.lo == c.lo && nx.ulen == c.ulen)) {
+          resolved = true;
+          break;
+        }
+        if ((nx.tr >> 8) <= prev_snap) {
+          keep = true;
+          resolved = true;
+          break;
+        }
+      }
+      if (!resolved) keep = oldest_version_at_most(in, run_start, k, c.hi, c.lo, c.ulen, prev_snap);
+    } else {
+      keep = true;
+    }
+    if (!silent) {
+      c_kbytes += c.ulen + 8;
+      if (type == kTypeDeletion) c_indel++;
+    }
+    if (silent) c_silent++;
+    if (keep) {
+      keep_mask |= 1u << x;
+      nkeep++;
+      // PrepareOutput :1299-1339 seqno zeroing
+      otr[x] = (mp.bottommost && seq <= mp.earliest_snapshot) ? (uint64_t)type : c.tr;
+    }
+    // stash "counted" flag for the value-byte statistic in bit 15.. not available: recomputed below from silent
+    if (silent) keep_mask |= 1u << (16 + x);
+  }
+  // ---- tile-local ranks
+  uint32_t inc = warp_incl_scan(nkeep);
+  if (lane == 31) s.wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t v = lane < (kMThreads / 32) ? s.wsum[lane] : 0;
+    uint32_t vi = warp_incl_scan(v);
+    s.wsum[lane] = vi - v;
+    if (lane == 31) s.kept_total = vi;
+  }
+  __syncthreads();
+  uint32_t rank = s.wsum[w] + inc - nkeep;
+  const uint32_t kept_total = s.kept_total;
+  // ---- decoupled look-back for the global output offset (tile ids are handed out in launch order)
+  if (w == 0) {
+    const unsigned long long kAgg = 1ull << 62, kPre = 2ull << 62, kVal = (1ull << 62) - 1;
+    uint64_t base_out = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(&tile_state[0], kPre | kept_total);
+    } else {
+      if (lane == 0) atomicExch(&tile_state[tile], kAgg | kept_total);
+      int64_t look = (int64_t)tile - 1;
+      while (true) {
+        int64_t idx = look - lane;
+        unsigned long long sv = kPre;  // virtual tiles before 0 contribute a zero prefix
+        if (idx >= 0) {
+          do {
+            sv = *((volatile unsigned long long*)&tile_state[idx]);
+          } while ((sv >> 62) == 0);
+        }
+        unsigned pre_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+        int first_pre = pre_mask ? __ffs(pre_mask) - 1 : 32;
+        uint64_t contrib = ((int)lane <= first_pre) ? (sv & kVal) : 0;
+#pragma unroll
+        for (int dd = 16; dd; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
+        base_out += contrib;
+        if (pre_mask) break;
+        look -= 32;
+      }
+      if (lane == 0) atomicExch(&tile_state[tile], kPre | (base_out + kept_total));
+    }
+    if (lane == 0) s.base_out = base_out;
+  }
+  // ---- compact survivors inside shared memory (reads are complete: everything needed is in registers)
+  uint64_t khi[kMV], klo[kMV];
+  uint16_t km[kMV];
+#pragma unroll
+  for (int x = 0; x < kMV; x++) {
+    uint32_t o = t * kMV + x;
+    if (o < cnt) {
+      khi[x] = s.hi[o];
+      klo[x] = s.lo[o];
+      km[x] = s.m16[o];
+    }
+  }
+  // value-byte statistic needs vlen of every counted entry: gather from the source columns by load position
+#pragma unroll
+  for (int x = 0; x < kMV; x++) {
+    uint32_t o = t * kMV + x;
+    if (o < cnt && !((keep_mask >> (16 + x)) & 1)) {
+      uint32_t pos = km[x] & 2047u, lo = 0, hi = k;
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (s.seg[mid] <= pos) lo = mid;
+        else hi = mid;
+      }
+      c_vbytes += meta_vlen(in.meta[s.sbeg[lo] + (pos - s.seg[lo])]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int x = 0; x < kMV; x++) {
+    if ((keep_mask >> x) & 1) {
+      s.hi[rank] = khi[x];
+      s.lo[rank] = klo[x];
+      s.tr[rank] = otr[x];
+      s.m16[rank] = km[x];
+      rank++;
+    }
+  }
+  __syncthreads();
+  const uint64_t base_out = s.base_out;
+  for (uint32_t i = t; i < kept_total; i += kMThreads) {
+    uint32_t pos = s.m16[i] & 2047u, lo = 0, hi = k;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (s.seg[mid] <= pos) lo = mid;
+      else hi = mid;
+    }
+    uint64_t src = s.sbeg[lo] + (pos - s.seg[lo]);
+    uint64_t dst = base_out + i;
+    out.pfx[dst] = make_ulonglong2(s.hi[i], s.lo[i]);
+    out.tr[dst] = s.tr[i];
+    out.vref[dst] = in.vref[src];
+    out.meta[dst] = in.meta[src];
+  }
+  // ---- counters: one atomic per CTA and counter
+  unsigned long long vals[7] = {(unsigned long long)nkeep, c_indel, c_hidden, c_obsolete, c_kbytes, c_vbytes, c_silent};
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    unsigned long long v = vals[i];
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) v += __shfl_xor_sync(0xffffffffu, v, dd);
+    if (lane == 0 && v) atomicAdd(&s.red[i], v);
+  }
+  __syncthreads();
+  if (t < 7 && s.red[t]) atomicAdd(((unsigned long long*)counters) + t, s.red[t]);
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+void launch_merge_partition(KeyCols in, const uint64_t* run_start, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
+                            uint64_t* splits, uint32_t* err, cudaStream_t st) {
+  unsigned warps = (unsigned)(ntiles + 1);
+  merge_partition_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, run_start, nruns, n_total, ntiles, splits, err);
+}
+void launch_merge_tiles(KeyCols in, const uint64_t* run_start, MergeParams mp, uint64_t n_total, uint64_t ntiles,
+                        const uint64_t* splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
+                        MergeCounters* counters, uint32_t* err, cudaStream_t st) {
+  if (ntiles == 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(merge_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    attr_set = true;
+  }
+  merge_tiles_kernel<<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, run_start, mp, n_total, ntiles, splits, tile_state,
+                                                                          ticket, out, counters, err);
+}
+
+}  // namespace b200c
