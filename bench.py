@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — compaction throughput of the B200 path (and of the reference's CPU path, --impl reference).
+
+One step = one whole compaction job: k pre-staged BlockBasedTable images (device resident) -> decode -> k-way merge
+with the compaction-iterator rules -> BlockBasedTable output images.  Workload at every N: per GPU, the configuration
+BASELINE.json's metric is quoted on (configs[1]: 8-way merge, 8 x 256 MiB synthetic sorted runs, 16 B keys / 32 B
+values); ranks hold disjoint key ranges = independent sub-compactions (weak scaling), and after every step all-gather
+the (smallest, largest) internal keys of their outputs over NCCL to stitch / assert the level's key order.
+
+metric  : compaction MB/s of input KV bytes (sum over input entries of internal-key + value bytes), MB = 1e6 bytes
+value   : device-resident inputs, CUDA-event time on the job stream, max over ranks
+e2e     : same job through the C ABI with HOST (pinned) input images and host outputs, H2D + D2H inside the timed region
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (k runs, raw KV bytes per run, value bytes, overlap, deletion fraction, bottommost)
+    "cfg2": dict(k=8, run_bytes=256 << 20, vlen=32, overlap=0.0, del_frac=0.0, bottommost=False,
+                 desc="8-way merge, 8x256MiB synthetic sorted runs, 16B keys / 32B values"),
+    "cfg3": dict(k=16, run_bytes=256 << 20, vlen=256, overlap=0.3, del_frac=0.1, bottommost=True,
+                 desc="16-way merge, 30% key overlap + 10% tombstones, 16B keys / 256B values"),
+    "cfg5": dict(k=4, run_bytes=64 << 20, vlen=128, overlap=0.0, del_frac=0.0, bottommost=False,
+                 desc="4-way x 64MiB sub-compaction, 16B keys / 128B values"),
+}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU ProcessKeyValueCompaction (oracle/_ref = the unmodified reference compiled here; else the
+    CPU oracle port), all host threads, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_baseline as CB
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    res = []
+    for _ in range(max(1, args.warmup > 0) + args.steps):
+        res.append(CB.run_sample(w, sample_bytes=args.sample_mb << 20, threads=cores))
+    res = res[1:] if len(res) > args.steps else res
+    mbps = statistics.mean(r["mbps"] for r in res)
+    line = {"impl": "reference", "metric": "compaction_input_kv_MB_per_s", "value": mbps, "unit": "MB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": statistics.mean(r["seconds"] for r in res) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": w["desc"], "sample": res[0]["sample"]},
+            "cpu_baseline": {"value": mbps, "unit": "MB/s", "cores": cores, "kind": res[0]["kind"], "sample": res[0]["sample"]},
+            "e2e": {"value": mbps, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the per-run size (debug only; invalidates the number)")
+    ap.add_argument("--sample-mb", type=int, default=192, help="raw KV MiB of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import toplingdb_b200 as T
+    from toplingdb_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the compaction path has no CPU implementation)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = WORKLOADS[args.workload]
+    entry = 24 + w["vlen"]
+    n_run = int(w["run_bytes"] * args.scale) // entry
+    n_total = n_run * w["k"]
+    key_base = rank * (n_total + 1024)  # disjoint, ordered key ranges per rank = independent sub-compactions
+    images, kv_bytes = synth.stage_runs(n_total, w["k"], w["vlen"], key_base=key_base, seed=2 + rank, overlap=w["overlap"],
+                                        del_frac=w["del_frac"], device_index=local)
+    in_bytes = sum(int(t.numel()) for t in images)
+    common = dict(device=local, output_level=1, bottommost_level=w["bottommost"], max_output_file_size=64 << 20,
+                  file_creation_times=[1700000000], first_file_number=1, db_id="bench", db_session_id="BENCH", db_host_id="b200")
+    job = T.CompactionJob(output_mem="device", profile=1, **common)
+    for i, img in enumerate(images):
+        job.add_input(img, level=0, file_number=100 + i)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def boundary_exchange():
+        """all-gather of each rank's (smallest, largest) output internal keys (2 x 24 B): the level's files span devices"""
+        if world == 1:
+            return
+        first, last = job.output_meta(0), job.output_meta(job.output_count() - 1)
+        mine = torch.tensor(list(bytes(first.smallest_ikey[:24])) + list(bytes(last.largest_ikey[:24])), dtype=torch.uint8, device="cuda")
+        allk = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        ks = [bytes(t.cpu().tolist()) for t in allk]
+        for a, b in zip(ks, ks[1:]):
+            assert a[24:40] < b[0:16], "sub-compaction outputs overlap"
+
+    for _ in range(args.warmup):
+        job.run()
+        boundary_exchange()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    dev_us, ktimes = [], {}
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        job.run()
+        boundary_exchange()
+        st = job.stats()
+        dev_us.append(st.total_us)
+        for name, us in job.kernel_times():
+            ktimes.setdefault(name, []).append(us)
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    st = job.stats()
+    nout = job.output_count()
+    out_bytes = sum(job.output_meta(i).file_size for i in range(nout))
+    out_data = sum(job.output_meta(i).data_size for i in range(nout))
+    launches = st.kernel_launches
+    # timing: device time per step, max over ranks
+    step_s = sum(dev_us) / 1e6 / args.steps
+    wall_s = wall / args.steps
+    if world > 1:
+        tt = torch.tensor([step_s, wall_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_s, wall_s = tt.tolist()
+    value = world * kv_bytes / step_s / 1e6
+
+    # size-independent checks at full size (untimed): entry conservation, ordered non-overlapping files
+    assert st.num_input_records == sum(1 for _ in [0]) * st.num_input_records
+    if w["overlap"] == 0 and w["del_frac"] == 0:
+        assert st.num_output_records == st.num_input_records, (st.num_output_records, st.num_input_records)
+    prev = None
+    for i in range(nout):
+        m = job.output_meta(i)
+        a, b = bytes(m.smallest_ikey[:16]), bytes(m.largest_ikey[:16])
+        assert a <= b and (prev is None or prev < a), "output files out of order"
+        prev = b
+
+    # per-kernel roofline on the dominant kernel group
+    pk, pk_src = peaks()
+    n_in, n_out = st.num_input_records, st.num_output_records
+    in_data = in_bytes  # data blocks dominate the image; index/tail < 1.5 %
+    val_out = st.total_input_raw_value_bytes if n_out == n_in else int(st.total_input_raw_value_bytes * n_out / max(1, n_in))
+    algo = {
+        "decode.block_count": in_data,
+        "decode.block_decode": in_data + 36 * n_in,
+        "merge.partition": 0,
+        "merge.tiles": 36 * n_in + 36 * n_out,
+        "encode.sizes": 28 * n_out + 5 * n_out,
+        "encode.tables": 9 * n_out + 6 * n_out,
+        "encode.emit": 36 * n_out + val_out + out_data,
+    }
+    kern = []
+    for name, xs in ktimes.items():
+        us = statistics.mean(xs)
+        ab = algo.get(name, 0)
+        kern.append({"name": name, "us": round(us, 1), "algo_bytes": ab, "gbs": round(ab / us / 1e3, 1) if us > 0 else None})
+    kern.sort(key=lambda x: -x["us"])
+    dom = kern[0] if kern else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if dom and os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom["name"])
+    roofline = None
+    if dom:
+        ach = dom["algo_bytes"] / dom["us"] / 1e3
+        roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(ach / pk["hbm_gbs"], 4), "traffic": traffic, "peak_source": pk_src,
+                    "algo_bytes_per_launch": dom["algo_bytes"], "avg_us": dom["us"]}
+
+    # e2e through the C ABI with host buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        host_imgs = [t.cpu().pin_memory() for t in images]
+        job.close()
+        del images
+        torch.cuda.empty_cache()
+        ej = T.CompactionJob(output_mem="host", **common)
+        for i, img in enumerate(host_imgs):
+            ej.add_input(img, level=0, file_number=100 + i)
+        for _ in range(2):
+            ej.run()
+        barrier()
+        t0 = time.perf_counter()
+        esteps = max(2, min(args.steps, 5))
+        for _ in range(esteps):
+            ej.run()
+            _ = ej.stats().num_output_records  # the result the caller reads
+        barrier()
+        es = (time.perf_counter() - t0) / esteps
+        if world > 1:
+            tt = torch.tensor([es], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            es = tt.item()
+        e2e = {"value": round(world * kv_bytes / es / 1e6, 1), "unit": "MB/s", "h2d_bytes_per_step": in_bytes,
+               "d2h_bytes_per_step": out_bytes, "ms_per_step": round(es * 1e3, 2)}
+        ej.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import cpu_baseline as CB
+        r = CB.run_sample(w, sample_bytes=min(args.sample_mb, 128) << 20, threads=1)
+        cpu = {"value": round(r["mbps"], 1), "unit": "MB/s", "cores": 1, "kind": r["kind"], "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": "compaction_input_kv_MB_per_s", "value": round(value, 1), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(step_s * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": w["desc"] + (f" (scale {args.scale})" if args.scale != 1.0 else ""), "k": w["k"],
+                           "entries_per_gpu": n_in, "input_kv_bytes_per_gpu": kv_bytes, "input_sst_bytes_per_gpu": in_bytes,
+                           "output_files_per_gpu": nout, "output_sst_bytes_per_gpu": out_bytes, "l2_policy": "inputs (2.2 GB) >> 126 MB L2",
+                           "parallelism": f"{world} independent sub-compactions, 1 per GPU" if world > 1 else "1 GPU"},
+                "wall_ms_per_step": round(wall_s * 1e3, 3), "e2e": e2e, "gpu_launches": int(launches) * args.steps, "roofline": roofline,
+                "kernels": kern, "cpu_baseline": cpu, "clocks": sampler.summary(),
+                "stage_us": {"decode": round(st.decode_us, 1), "merge": round(st.merge_us, 1), "encode": round(st.encode_us, 1)}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -84,7 +84,7 @@ typedef struct b200c_params {
   uint32_t num_file_creation_times;
   uint64_t first_file_number;      /* outputs are numbered first_file_number, +1, ... (orig_file_number property) */
   uint32_t output_mem;             /* enum b200c_mem_kind: where b200c_job_output_data() pointers live */
-  uint32_t reserved;
+  uint32_t profile;                /* != 0: bracket every kernel group with CUDA events (b200c_job_kernel_time) */
 } b200c_params;
 
 /* FileMinMeta (compaction_executor.h:120-131) + the TableProperties RunRemote re-reads (compaction_job.cc:1043-1061) */
@@ -128,7 +128,7 @@ B200C_API int b200c_job_output_count(const b200c_job* j);
 B200C_API int b200c_job_output_meta(const b200c_job* j, int i, b200c_file_meta* m);
 /* Pointer to the finished file image of output i (host or device memory according to params.output_mem). */
 B200C_API int b200c_job_output_data(b200c_job* j, int i, const void** data, uint64_t* len);
-/* Copy output i into caller memory (host). */
+/* Copy output i into caller memory (host; with output_mem == DEVICE the destination may also be device memory). */
 B200C_API int b200c_job_output_read(b200c_job* j, int i, void* dst, uint64_t cap);
 B200C_API int b200c_job_get_stats(const b200c_job* j, b200c_stats* s);
 B200C_API void b200c_job_destroy(b200c_job* j);
@@ -145,6 +145,19 @@ enum b200c_debug_array {
 B200C_API int b200c_job_run_until(b200c_job* j, int stage);
 /* Copies the array into dst (host) and returns the byte count needed in *len. run is ignored for merged arrays. */
 B200C_API int b200c_job_debug_read(b200c_job* j, int what, int run, void* dst, uint64_t cap, uint64_t* len);
+
+/* Per-kernel-group device times of the last run (params.profile != 0): name and microseconds. */
+B200C_API int b200c_job_kernel_time_count(const b200c_job* j);
+B200C_API int b200c_job_kernel_time(const b200c_job* j, int i, const char** name, double* us);
+
+/* TableBuilder side of the path alone (BlockBasedTableBuilder::Add/Finish, table/table_builder.h:168-235): encode one
+ * sorted run that already sits in device memory as columns into BlockBasedTable image(s), cut like compaction outputs.
+ * Columns, n entries each:  pfx  16 B  first 16 user-key bytes as two big-endian-decoded u64 (hi, lo), zero padded
+ *                           tr    8 B  (sequence << 8) | value type
+ *                           vref  8 B  device address of the value bytes
+ *                           meta  4 B  user_key_len << 27 | value_len
+ * Results are read with b200c_job_output_*.  Used by the table-factory plugin and to pre-stage synthetic inputs. */
+B200C_API int b200c_job_encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta);
 
 /* Block checksum of table/format.cc:468-509 computed on the device for n independent buffers laid out
  * back to back (offsets[n+1]); results in out[n].  type = enum b200c_checksum. */

@@ -68,10 +68,33 @@ struct Input {
   const uint8_t* dev = nullptr;
   InputTail tail;
 };
+struct HostBuf {  // grow-only pinned host allocation (D2H target of the finished images)
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost((void**)&p, n + (n >> 4) + 256);
+    if (e == cudaSuccess) cap = n + (n >> 4) + 256;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
 struct Output {
   b200c_file_meta meta;
-  uint64_t dev_off = 0;  // offset of the image inside out_buf
-  std::vector<uint8_t> host;  // when output_mem == HOST
+  uint64_t dev_off = 0;   // offset of the image inside out_buf
+  uint64_t host_off = 0;  // offset inside host_out when output_mem == HOST
+};
+struct KernelTime {
+  const char* name;
+  cudaEvent_t a, b;
+  float us;
 };
 
 }  // namespace
@@ -95,6 +118,27 @@ struct b200c_job {
   uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
   uint32_t nfiles_out = 0;
   std::vector<uint64_t> run_start_h;
+  HostBuf host_out;
+  std::vector<uint8_t> tails;  // staging of the per-file tails until the copy stream has consumed them
+  std::vector<KernelTime> ktimes;
+  size_t kt_used = 0;
+  // profiling: bracket a named group of launches with events (only when params.profile != 0)
+  void kt_begin(const char* name) {
+    if (!p.profile) return;
+    if (kt_used == ktimes.size()) {
+      KernelTime k{name, nullptr, nullptr, 0.f};
+      cudaEventCreate(&k.a);
+      cudaEventCreate(&k.b);
+      ktimes.push_back(k);
+    }
+    ktimes[kt_used].name = name;
+    cudaEventRecord(ktimes[kt_used].a, st);
+  }
+  void kt_end() {
+    if (!p.profile) return;
+    cudaEventRecord(ktimes[kt_used].b, st);
+    kt_used++;
+  }
 };
 
 namespace {
@@ -196,6 +240,200 @@ void ikey_bytes(const KeyRec& k, uint8_t* out, uint32_t* len) {
   *len = n;
 }
 
+// encode stage: merged columns (device) -> output file images + metas.  `h` holds the small-slot snapshot read at sync #1.
+int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, EncodeWork& W, uint32_t* err, uint64_t* small,
+                 uint64_t& launches, uint64_t& nblocks, uint32_t& nfiles) {
+  const b200c_params& P = j->p;
+  cudaStream_t st = j->st;
+  uint64_t h[kSmallSlots];
+  std::vector<FileRec> frs;
+  std::vector<uint64_t> base_off;
+  if (n_out) {
+    if (P.index_block_restart_interval != 1)
+      return fail(B200C_ERR_NOT_SUPPORTED, "index_block_restart_interval != 1 is not built on the device");
+    EncodeParams ep;
+    ep.block_size = P.block_size;
+    ep.block_size_limit = P.block_size_deviation ? (uint32_t)(((uint64_t)P.block_size * (100 - P.block_size_deviation) + 99) / 100) : 0;
+    ep.restart_interval = P.block_restart_interval;
+    ep.checksum = P.checksum;
+    ep.format_version = P.format_version;
+    ep.output_level = (uint32_t)P.output_level;
+    ep.max_output_file_size = P.max_output_file_size;
+    uint64_t hop = (uint64_t)(P.block_size - 1) / std::max<uint32_t>(min_s1, 1) + 3;
+    if (hop > (uint64_t)kEncHalo) return fail(B200C_ERR_NOT_SUPPORTED, "block_size / smallest entry exceeds the encoder's 2048-entry block window");
+    const uint32_t hc = (uint32_t)hop;
+    const uint64_t etiles = (n_out + kEncTile - 1) / kEncTile;
+    CU(j->rows.reserve(sizeof(TileRow) * etiles * hc));
+    CU(j->tstate.reserve(sizeof(TileState) * etiles));
+    CU(j->nxt.reserve(2 * (n_out + 1)));
+    CU(j->disk.reserve(4 * (n_out + 1)));
+    CU(j->files_rec.reserve(sizeof(FileRec) * (kMaxOutFiles + 2)));
+    W.rows = j->rows.as<TileRow>();
+    W.tstate = j->tstate.as<TileState>();
+    W.nxt = j->nxt.as<uint16_t>();
+    W.disk = j->disk.as<uint32_t>();
+    W.files = j->files_rec.as<FileRec>();
+    W.scan_tmp = j->scan_tmp.as<uint64_t>();
+    j->kt_begin("encode.tables");
+    launch_encode_tables(mcols, ep, W, etiles, hc, err, st);
+    j->kt_end();
+    j->kt_begin("encode.stitch");
+    launch_encode_stitch(mcols, ep, W, etiles, hc, err, st);
+    j->kt_end();
+    launches += 2;
+    CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // sync #2: number of blocks / files
+    CU(cudaGetLastError());
+    {
+      int rc = map_dev_err((uint32_t)h[kSlotErr]);
+      if (rc) return rc;
+    }
+    nblocks = h[kSlotTotals];
+    nfiles = (uint32_t)h[kSlotTotals + 1];
+    if (nfiles == 0 || nfiles > kMaxOutFiles) return fail(B200C_ERR_CUDA, "internal: bad output file count");
+    frs.resize(nfiles);
+    CU(cudaMemcpyAsync(frs.data(), W.files, sizeof(FileRec) * nfiles, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(j->blocks.reserve(sizeof(BlockRec) * (nblocks + 1)));
+    CU(j->idx_esz.reserve(4 * (nblocks + 1)));
+    CU(j->idx_eoff.reserve(8 * (nblocks + 1)));
+    CU(j->idx_sep.reserve(sizeof(KeyRec) * (nblocks + 1)));
+    W.blocks = j->blocks.as<BlockRec>();
+    W.idx_esz = j->idx_esz.as<uint32_t>();
+    W.idx_eoff = j->idx_eoff.as<uint64_t>();
+    W.idx_sep = j->idx_sep.as<KeyRec>();
+    // image layout: data blocks | index block (<= 45 B per data block + 9) | tail (properties, metaindex, footer)
+    base_off.resize(nfiles + 1);
+    uint64_t off = 0;
+    for (uint32_t f = 0; f < nfiles; f++) {
+      base_off[f] = off;
+      uint64_t cap = frs[f].data_size + frs[f].n_blocks * 48 + 64 + 4096;
+      off += (cap + 255) & ~255ull;
+    }
+    base_off[nfiles] = off;
+    CU(j->out_buf.reserve(off + 256));
+    std::vector<uint8_t*> bases(nfiles);
+    for (uint32_t f = 0; f < nfiles; f++) bases[f] = j->out_buf.as<uint8_t>() + base_off[f];
+    CU(j->out_base_d.reserve(8 * nfiles));
+    CU(cudaMemcpyAsync(j->out_base_d.p, bases.data(), 8 * nfiles, cudaMemcpyHostToDevice, st));
+    uint8_t* const* out_base_d = j->out_base_d.as<uint8_t*>();
+    j->kt_begin("encode.blocklist");
+    launch_encode_blocklist(mcols, ep, W, etiles, nblocks, err, st);
+    j->kt_end();
+    j->kt_begin("encode.filestats");
+    launch_encode_filestats(mcols, W, nfiles, j->sms, st);
+    j->kt_end();
+    j->kt_begin("encode.emit");
+    launch_encode_emit(mcols, ep, W, nblocks, out_base_d, err, j->sms, st);
+    j->kt_end();
+    launches += 3;
+    j->kt_begin("encode.index");
+    launch_encode_index(mcols, ep, W, nblocks, nfiles, out_base_d, err, st, &launches);
+    j->kt_end();
+    CU(cudaMemcpyAsync(frs.data(), W.files, sizeof(FileRec) * nfiles, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // sync #3: per-file records
+    CU(cudaGetLastError());
+    {
+      int rc = map_dev_err((uint32_t)h[kSlotErr]);
+      if (rc) return rc;
+    }
+    // tails
+    j->outputs.resize(nfiles);
+    j->tails.resize((size_t)nfiles * 4096);
+    for (uint32_t f = 0; f < nfiles; f++) {
+      const FileRec& fr = frs[f];
+      OutputTailInput ti;
+      ti.checksum_type = P.checksum;
+      ti.format_version = P.format_version;
+      ti.data_size = fr.data_size;
+      ti.index_size = fr.index_size;
+      ti.num_entries = fr.n_entries;
+      ti.num_deletions = fr.num_deletions;
+      ti.raw_key_size = fr.raw_key_size;
+      ti.raw_value_size = fr.raw_value_size;
+      ti.num_data_blocks = fr.n_blocks;
+      ti.index_key_is_user_key = !fr.index_has_seq && P.format_version > 2;
+      ti.column_family_id = P.column_family_id;
+      ti.column_family_name = j->cf_name;
+      ti.db_id = j->db_id;
+      ti.db_session_id = j->db_session_id;
+      ti.db_host_id = j->db_host_id;
+      ti.creation_time = P.creation_time;
+      ti.oldest_key_time = P.oldest_key_time;
+      ti.file_creation_time = j->fct.empty() ? 0 : j->fct[std::min<size_t>(f, j->fct.size() - 1)];
+      ti.orig_file_number = P.first_file_number + f;
+      std::vector<uint8_t> tail = build_output_tail(ti);
+      const uint64_t tail_off = fr.data_size + fr.index_size + 5;
+      if (tail_off + tail.size() > base_off[f + 1] - base_off[f]) return fail(B200C_ERR_CUDA, "internal: output image overflow");
+      const size_t so = (size_t)f * 4096;
+      if (tail.size() > 4096) return fail(B200C_ERR_CUDA, "internal: tail larger than its staging slot");
+      memcpy(j->tails.data() + so, tail.data(), tail.size());
+      CU(cudaMemcpyAsync(j->out_buf.as<uint8_t>() + base_off[f] + tail_off, j->tails.data() + so, tail.size(), cudaMemcpyHostToDevice, st));
+      Output& o = j->outputs[f];
+      memset(&o.meta, 0, sizeof o.meta);
+      o.dev_off = base_off[f];
+      o.meta.file_number = ti.orig_file_number;
+      o.meta.file_size = tail_off + tail.size();
+      o.meta.smallest_seqno = fr.smallest_seq;
+      o.meta.largest_seqno = fr.largest_seq;
+      o.meta.num_entries = fr.n_entries;
+      o.meta.num_deletions = fr.num_deletions;
+      o.meta.raw_key_size = fr.raw_key_size;
+      o.meta.raw_value_size = fr.raw_value_size;
+      o.meta.num_data_blocks = fr.n_blocks;
+      o.meta.data_size = fr.data_size;
+      o.meta.index_size = fr.index_size;
+      ikey_bytes(fr.smallest, o.meta.smallest_ikey, &o.meta.smallest_ikey_len);
+      ikey_bytes(fr.largest, o.meta.largest_ikey, &o.meta.largest_ikey_len);
+      j->stats.total_output_bytes += o.meta.file_size;
+    }
+  }
+  return B200C_OK;
+}
+
+// D2H of the finished images (host outputs), event times, bookkeeping
+int finish_run(b200c_job* j, uint64_t launches, uint64_t nblocks, uint32_t nfiles) {
+  const b200c_params& P = j->p;
+  cudaStream_t st = j->st;
+  j->nblocks_out = nblocks;
+  j->nfiles_out = nfiles;
+  CU(cudaEventRecord(j->ev[3], st));
+  if (P.output_mem == B200C_MEM_HOST) {
+    uint64_t tot = 0;
+    for (auto& o : j->outputs) {
+      o.host_off = tot;
+      tot += (o.meta.file_size + 63) & ~63ull;
+    }
+    CU(j->host_out.reserve(tot + 64));
+    for (auto& o : j->outputs)
+      CU(cudaMemcpyAsync(j->host_out.p + o.host_off, j->out_buf.as<uint8_t>() + o.dev_off, o.meta.file_size, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaEventRecord(j->ev[4], st));
+  CU(cudaStreamSynchronize(st));
+  float ms;
+  cudaEventElapsedTime(&ms, j->ev[0], j->ev[1]);
+  j->stats.decode_us = ms * 1000.0;
+  cudaEventElapsedTime(&ms, j->ev[1], j->ev[2]);
+  j->stats.merge_us = ms * 1000.0;
+  cudaEventElapsedTime(&ms, j->ev[2], j->ev[3]);
+  j->stats.encode_us = ms * 1000.0;
+  cudaEventElapsedTime(&ms, j->ev[0], j->ev[4]);
+  j->stats.total_us = ms * 1000.0;
+  for (size_t i = 0; i < j->kt_used; i++) {
+    float kms = 0;
+    cudaEventElapsedTime(&kms, j->ktimes[i].a, j->ktimes[i].b);
+    j->ktimes[i].us = kms * 1000.f;
+  }
+  j->stats.num_output_files = nfiles;
+  j->stats.kernel_launches = launches;
+  j->ran = true;
+  j->stage_done = 3;
+  return B200C_OK;
+}
+
+int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta);
+
 int run_job(b200c_job* j, int until) {
   const b200c_params& P = j->p;
   CU(cudaSetDevice(P.device));
@@ -211,6 +449,7 @@ int run_job(b200c_job* j, int until) {
   j->outputs.clear();
   j->ran = false;
   j->stage_done = 0;
+  j->kt_used = 0;
   memset(&j->stats, 0, sizeof j->stats);
   const int k = (int)j->inputs.size();
   if (k == 0) return fail(B200C_ERR_INVALID_ARGUMENT, "job has no inputs");
@@ -281,19 +520,27 @@ int run_job(b200c_job* j, int until) {
   uint32_t maxb = 0;
   for (auto& f : fds) maxb = std::max(maxb, f.nblocks);
   if (nblk) {
+    j->kt_begin("decode.index");
     launch_index_decode(files_d, k, maxb, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), err, st);
+    j->kt_end();
+    j->kt_begin("decode.block_count");
     launch_block_count(files_d, k, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), (uint32_t)nblk, P.verify_input_checksums,
                        j->blk_cnt.as<uint32_t>(), err, j->sms, st);
+    j->kt_end();
     launches += 2;
+    j->kt_begin("decode.scan");
     exclusive_scan<uint32_t>(j->blk_cnt.as<uint32_t>(), j->blk_base.as<uint64_t>(), nblk, j->scan_tmp.as<uint64_t>(),
                              small + kSlotTotalIn, st, &launches);
+    j->kt_end();
   }
   launch_run_starts(files_d, k, j->blk_base.as<uint64_t>(), small + kSlotTotalIn, (uint32_t)nblk, j->run_start.as<uint64_t>(), st);
   launches++;
   KeyColsMut dec{j->dec[0].as<ulonglong2>(), j->dec[1].as<uint64_t>(), j->dec[2].as<uint64_t>(), j->dec[3].as<uint32_t>()};
   if (nblk) {
+    j->kt_begin("decode.block_decode");
     launch_block_decode(files_d, k, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), j->blk_base.as<uint64_t>(), (uint32_t)nblk,
                         N, dec, err, j->sms, st);
+    j->kt_end();
     launches++;
   }
   CU(cudaEventRecord(j->ev[1], st));
@@ -341,15 +588,21 @@ int run_job(b200c_job* j, int until) {
   W.min_s1 = reinterpret_cast<uint32_t*>(small + kSlotMinS1);
   W.totals = small + kSlotTotals;
   if (N) {
+    j->kt_begin("merge.partition");
     launch_merge_partition(decc, j->run_start.as<uint64_t>(), (uint32_t)k, N, mtiles, j->splits.as<uint64_t>(), err, st);
+    j->kt_end();
+    j->kt_begin("merge.tiles");
     launch_merge_tiles(decc, j->run_start.as<uint64_t>(), mp, N, mtiles, j->splits.as<uint64_t>(),
                        j->tile_state.as<unsigned long long>(), reinterpret_cast<uint32_t*>(small + kSlotTicket), mrg, counters, err, st);
+    j->kt_end();
     launches += 2;
   }
   CU(cudaEventRecord(j->ev[2], st));
   KeyCols mcols{mrg.pfx, mrg.tr, mrg.vref, mrg.meta, 0};
   if (N) {
+    j->kt_begin("encode.sizes");
     launch_encode_sizes(mcols, reinterpret_cast<const unsigned long long*>(&counters->n_out), W, N, st);
+    j->kt_end();
     launches++;
   }
   uint64_t h[kSmallSlots];
@@ -381,160 +634,75 @@ int run_job(b200c_job* j, int until) {
   // ---------------- encode
   uint32_t nfiles = 0;
   uint64_t nblocks = 0;
-  std::vector<FileRec> frs;
-  std::vector<uint64_t> base_off;
-  if (n_out) {
-    if (P.index_block_restart_interval != 1)
-      return fail(B200C_ERR_NOT_SUPPORTED, "index_block_restart_interval != 1 is not built on the device");
-    const uint32_t min_s1 = (uint32_t)h[kSlotMinS1];
-    EncodeParams ep;
-    ep.block_size = P.block_size;
-    ep.block_size_limit = P.block_size_deviation ? (uint32_t)(((uint64_t)P.block_size * (100 - P.block_size_deviation) + 99) / 100) : 0;
-    ep.restart_interval = P.block_restart_interval;
-    ep.checksum = P.checksum;
-    ep.format_version = P.format_version;
-    ep.output_level = (uint32_t)P.output_level;
-    ep.max_output_file_size = P.max_output_file_size;
-    uint64_t hop = (uint64_t)(P.block_size - 1) / std::max<uint32_t>(min_s1, 1) + 3;
-    if (hop > (uint64_t)kEncHalo) return fail(B200C_ERR_NOT_SUPPORTED, "block_size / smallest entry exceeds the encoder's 2048-entry block window");
-    const uint32_t hc = (uint32_t)hop;
-    const uint64_t etiles = (n_out + kEncTile - 1) / kEncTile;
-    CU(j->rows.reserve(sizeof(TileRow) * etiles * hc));
-    CU(j->tstate.reserve(sizeof(TileState) * etiles));
-    CU(j->nxt.reserve(2 * (n_out + 1)));
-    CU(j->disk.reserve(4 * (n_out + 1)));
-    CU(j->files_rec.reserve(sizeof(FileRec) * (kMaxOutFiles + 2)));
-    W.rows = j->rows.as<TileRow>();
-    W.tstate = j->tstate.as<TileState>();
-    W.nxt = j->nxt.as<uint16_t>();
-    W.disk = j->disk.as<uint32_t>();
-    W.files = j->files_rec.as<FileRec>();
-    W.scan_tmp = j->scan_tmp.as<uint64_t>();
-    launch_encode_tables(mcols, ep, W, etiles, hc, err, st);
-    launch_encode_stitch(mcols, ep, W, etiles, hc, err, st);
-    launches += 2;
-    CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));  // sync #2: number of blocks / files
-    CU(cudaGetLastError());
-    {
-      int rc = map_dev_err((uint32_t)h[kSlotErr]);
-      if (rc) return rc;
-    }
-    nblocks = h[kSlotTotals];
-    nfiles = (uint32_t)h[kSlotTotals + 1];
-    if (nfiles == 0 || nfiles > kMaxOutFiles) return fail(B200C_ERR_CUDA, "internal: bad output file count");
-    frs.resize(nfiles);
-    CU(cudaMemcpyAsync(frs.data(), W.files, sizeof(FileRec) * nfiles, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    CU(j->blocks.reserve(sizeof(BlockRec) * (nblocks + 1)));
-    CU(j->idx_esz.reserve(4 * (nblocks + 1)));
-    CU(j->idx_eoff.reserve(8 * (nblocks + 1)));
-    CU(j->idx_sep.reserve(sizeof(KeyRec) * (nblocks + 1)));
-    W.blocks = j->blocks.as<BlockRec>();
-    W.idx_esz = j->idx_esz.as<uint32_t>();
-    W.idx_eoff = j->idx_eoff.as<uint64_t>();
-    W.idx_sep = j->idx_sep.as<KeyRec>();
-    // image layout: data blocks | index block (<= 45 B per data block + 9) | tail (properties, metaindex, footer)
-    base_off.resize(nfiles + 1);
-    uint64_t off = 0;
-    for (uint32_t f = 0; f < nfiles; f++) {
-      base_off[f] = off;
-      uint64_t cap = frs[f].data_size + frs[f].n_blocks * 48 + 64 + 4096;
-      off += (cap + 255) & ~255ull;
-    }
-    base_off[nfiles] = off;
-    CU(j->out_buf.reserve(off + 256));
-    std::vector<uint8_t*> bases(nfiles);
-    for (uint32_t f = 0; f < nfiles; f++) bases[f] = j->out_buf.as<uint8_t>() + base_off[f];
-    CU(j->out_base_d.reserve(8 * nfiles));
-    CU(cudaMemcpyAsync(j->out_base_d.p, bases.data(), 8 * nfiles, cudaMemcpyHostToDevice, st));
-    uint8_t* const* out_base_d = j->out_base_d.as<uint8_t*>();
-    launch_encode_blocklist(mcols, ep, W, etiles, nblocks, err, st);
-    launch_encode_filestats(mcols, W, nfiles, j->sms, st);
-    launch_encode_emit(mcols, ep, W, nblocks, out_base_d, err, j->sms, st);
-    launches += 3;
-    launch_encode_index(mcols, ep, W, nblocks, nfiles, out_base_d, err, st, &launches);
-    CU(cudaMemcpyAsync(frs.data(), W.files, sizeof(FileRec) * nfiles, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));  // sync #3: per-file records
-    CU(cudaGetLastError());
-    {
-      int rc = map_dev_err((uint32_t)h[kSlotErr]);
-      if (rc) return rc;
-    }
-    // tails
-    j->outputs.resize(nfiles);
-    for (uint32_t f = 0; f < nfiles; f++) {
-      const FileRec& fr = frs[f];
-      OutputTailInput ti;
-      ti.checksum_type = P.checksum;
-      ti.format_version = P.format_version;
-      ti.data_size = fr.data_size;
-      ti.index_size = fr.index_size;
-      ti.num_entries = fr.n_entries;
-      ti.num_deletions = fr.num_deletions;
-      ti.raw_key_size = fr.raw_key_size;
-      ti.raw_value_size = fr.raw_value_size;
-      ti.num_data_blocks = fr.n_blocks;
-      ti.index_key_is_user_key = !fr.index_has_seq && P.format_version > 2;
-      ti.column_family_id = P.column_family_id;
-      ti.column_family_name = j->cf_name;
-      ti.db_id = j->db_id;
-      ti.db_session_id = j->db_session_id;
-      ti.db_host_id = j->db_host_id;
-      ti.creation_time = P.creation_time;
-      ti.oldest_key_time = P.oldest_key_time;
-      ti.file_creation_time = j->fct.empty() ? 0 : j->fct[std::min<size_t>(f, j->fct.size() - 1)];
-      ti.orig_file_number = P.first_file_number + f;
-      std::vector<uint8_t> tail = build_output_tail(ti);
-      const uint64_t tail_off = fr.data_size + fr.index_size + 5;
-      if (tail_off + tail.size() > base_off[f + 1] - base_off[f]) return fail(B200C_ERR_CUDA, "internal: output image overflow");
-      CU(cudaMemcpyAsync(j->out_buf.as<uint8_t>() + base_off[f] + tail_off, tail.data(), tail.size(), cudaMemcpyHostToDevice, st));
-      CU(cudaStreamSynchronize(st));  // `tail` is a temporary
-      Output& o = j->outputs[f];
-      memset(&o.meta, 0, sizeof o.meta);
-      o.dev_off = base_off[f];
-      o.meta.file_number = ti.orig_file_number;
-      o.meta.file_size = tail_off + tail.size();
-      o.meta.smallest_seqno = fr.smallest_seq;
-      o.meta.largest_seqno = fr.largest_seq;
-      o.meta.num_entries = fr.n_entries;
-      o.meta.num_deletions = fr.num_deletions;
-      o.meta.raw_key_size = fr.raw_key_size;
-      o.meta.raw_value_size = fr.raw_value_size;
-      o.meta.num_data_blocks = fr.n_blocks;
-      o.meta.data_size = fr.data_size;
-      o.meta.index_size = fr.index_size;
-      ikey_bytes(fr.smallest, o.meta.smallest_ikey, &o.meta.smallest_ikey_len);
-      ikey_bytes(fr.largest, o.meta.largest_ikey, &o.meta.largest_ikey_len);
-      j->stats.total_output_bytes += o.meta.file_size;
-    }
+  {
+    int rc = encode_stage(j, mcols, n_out, (uint32_t)h[kSlotMinS1], W, err, small, launches, nblocks, nfiles);
+    if (rc) return rc;
   }
-  j->nblocks_out = nblocks;
-  j->nfiles_out = nfiles;
-  CU(cudaEventRecord(j->ev[3], st));
-  if (P.output_mem == B200C_MEM_HOST) {
-    for (auto& o : j->outputs) {
-      o.host.resize(o.meta.file_size);
-      CU(cudaMemcpyAsync(o.host.data(), j->out_buf.as<uint8_t>() + o.dev_off, o.meta.file_size, cudaMemcpyDeviceToHost, st));
-    }
+  return finish_run(j, launches, nblocks, nfiles);
+}
+
+int job_prepare(b200c_job* j) {
+  CU(cudaSetDevice(j->p.device));
+  if (!j->st) {
+    CU(cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking));
+    for (auto& e : j->ev) CU(cudaEventCreate(&e));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, j->p.device));
+    j->sms = prop.multiProcessorCount;
   }
-  CU(cudaEventRecord(j->ev[4], st));
-  CU(cudaStreamSynchronize(st));
-  float ms;
-  cudaEventElapsedTime(&ms, j->ev[0], j->ev[1]);
-  j->stats.decode_us = ms * 1000.0;
-  cudaEventElapsedTime(&ms, j->ev[1], j->ev[2]);
-  j->stats.merge_us = ms * 1000.0;
-  cudaEventElapsedTime(&ms, j->ev[2], j->ev[3]);
-  j->stats.encode_us = ms * 1000.0;
-  cudaEventElapsedTime(&ms, j->ev[0], j->ev[4]);
-  j->stats.total_us = ms * 1000.0;
-  j->stats.num_output_files = nfiles;
-  j->stats.kernel_launches = launches;
-  j->ran = true;
-  j->stage_done = 3;
+  j->outputs.clear();
+  j->ran = false;
+  j->stage_done = 0;
+  j->kt_used = 0;
+  memset(&j->stats, 0, sizeof j->stats);
   return B200C_OK;
+}
+
+// TableBuilder side only: one sorted run given as device columns -> BlockBasedTable image(s)
+int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta) {
+  int rc = job_prepare(j);
+  if (rc) return rc;
+  cudaStream_t st = j->st;
+  uint64_t launches = 0;
+  CU(cudaEventRecord(j->ev[0], st));
+  CU(cudaEventRecord(j->ev[1], st));
+  CU(cudaEventRecord(j->ev[2], st));
+  CU(j->small.reserve(kSmallSlots * 8));
+  CU(cudaMemsetAsync(j->small.p, 0, kSmallSlots * 8, st));
+  uint64_t* small = j->small.as<uint64_t>();
+  uint32_t* err = reinterpret_cast<uint32_t*>(small + kSlotErr);
+  uint32_t ff = 0xffffffffu;
+  CU(cudaMemcpyAsync(small + kSlotMinS1, &ff, 4, cudaMemcpyHostToDevice, st));
+  MergeCounters* counters = reinterpret_cast<MergeCounters*>(small + kSlotCounters);
+  CU(cudaMemcpyAsync(&counters->n_out, &n, 8, cudaMemcpyHostToDevice, st));
+  CU(j->esz.reserve(4 * (n + 1)));
+  CU(j->eshared.reserve(n + 1));
+  CU(j->scan_tmp.reserve(8 * ((n / kScanTile) + 2)));
+  EncodeWork W;
+  memset(&W, 0, sizeof W);
+  W.esz = j->esz.as<uint32_t>();
+  W.eshared = j->eshared.as<uint8_t>();
+  W.min_s1 = reinterpret_cast<uint32_t*>(small + kSlotMinS1);
+  W.totals = small + kSlotTotals;
+  KeyCols mcols{static_cast<const ulonglong2*>(pfx), static_cast<const uint64_t*>(tr), static_cast<const uint64_t*>(vref),
+                static_cast<const uint32_t*>(meta), n};
+  if (n) {
+    j->kt_begin("encode.sizes");
+    launch_encode_sizes(mcols, reinterpret_cast<const unsigned long long*>(&counters->n_out), W, n, st);
+    j->kt_end();
+    launches++;
+  }
+  uint64_t h[kSmallSlots];
+  CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  uint64_t nblocks = 0;
+  uint32_t nfiles = 0;
+  rc = encode_stage(j, mcols, n, (uint32_t)h[kSlotMinS1], W, err, small, launches, nblocks, nfiles);
+  if (rc) return rc;
+  j->n_out = n;
+  j->stats.num_output_records = n;
+  return finish_run(j, launches, nblocks, nfiles);
 }
 
 }  // namespace
@@ -632,7 +800,7 @@ int b200c_job_output_data(b200c_job* j, int i, const void** data, uint64_t* len)
   if (!j || !j->ran || i < 0 || i >= (int)j->outputs.size()) return fail(B200C_ERR_STATE, "no such output");
   Output& o = j->outputs[i];
   *len = o.meta.file_size;
-  *data = j->p.output_mem == B200C_MEM_HOST ? (const void*)o.host.data() : (const void*)(j->out_buf.as<uint8_t>() + o.dev_off);
+  *data = j->p.output_mem == B200C_MEM_HOST ? (const void*)(j->host_out.p + o.host_off) : (const void*)(j->out_buf.as<uint8_t>() + o.dev_off);
   return B200C_OK;
 }
 int b200c_job_output_read(b200c_job* j, int i, void* dst, uint64_t cap) {
@@ -640,11 +808,11 @@ int b200c_job_output_read(b200c_job* j, int i, void* dst, uint64_t cap) {
   Output& o = j->outputs[i];
   if (cap < o.meta.file_size) return fail(B200C_ERR_INVALID_ARGUMENT, "destination too small");
   if (j->p.output_mem == B200C_MEM_HOST) {
-    memcpy(dst, o.host.data(), o.meta.file_size);
+    memcpy(dst, j->host_out.p + o.host_off, o.meta.file_size);
     return B200C_OK;
   }
   CU(cudaSetDevice(j->p.device));
-  CU(cudaMemcpy(dst, j->out_buf.as<uint8_t>() + o.dev_off, o.meta.file_size, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(dst, j->out_buf.as<uint8_t>() + o.dev_off, o.meta.file_size, cudaMemcpyDefault));  // dst: host or device
   return B200C_OK;
 }
 int b200c_job_get_stats(const b200c_job* j, b200c_stats* s) {
@@ -661,10 +829,28 @@ void b200c_job_destroy(b200c_job* j) {
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};
   for (DevBuf* b : all) b->release();
   for (auto& in : j->inputs) in.staged.release();
+  j->host_out.release();
+  for (auto& kt : j->ktimes) {
+    cudaEventDestroy(kt.a);
+    cudaEventDestroy(kt.b);
+  }
   for (auto& e : j->ev)
     if (e) cudaEventDestroy(e);
   if (j->st) cudaStreamDestroy(j->st);
   delete j;
+}
+
+int b200c_job_kernel_time_count(const b200c_job* j) { return j ? (int)j->kt_used : 0; }
+int b200c_job_kernel_time(const b200c_job* j, int i, const char** name, double* us) {
+  if (!j || i < 0 || (size_t)i >= j->kt_used) return fail(B200C_ERR_INVALID_ARGUMENT, "no such kernel time");
+  *name = j->ktimes[i].name;
+  *us = j->ktimes[i].us;
+  return B200C_OK;
+}
+
+int b200c_job_encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta) {
+  if (!j || (n && (!pfx || !tr || !vref || !meta))) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  return encode_columns(j, n, pfx, tr, vref, meta);
 }
 
 int b200c_job_debug_read(b200c_job* j, int what, int run, void* dst, uint64_t cap, uint64_t* len) {

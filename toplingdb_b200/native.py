@@ -27,7 +27,7 @@ class Params(C.Structure):
         ("db_id", C.c_char_p), ("db_session_id", C.c_char_p), ("db_host_id", C.c_char_p), ("creation_time", C.c_uint64),
         ("oldest_key_time", C.c_uint64), ("file_creation_times", C.POINTER(C.c_uint64)),
         ("num_file_creation_times", C.c_uint32), ("first_file_number", C.c_uint64), ("output_mem", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("profile", C.c_uint32),
     ]
 
 
@@ -53,7 +53,8 @@ _lib = None
 EXPORTS = ["b200c_last_error", "b200c_abi_version", "b200c_device_count", "b200c_params_init", "b200c_job_create",
            "b200c_job_add_input", "b200c_job_run", "b200c_job_output_count", "b200c_job_output_meta",
            "b200c_job_output_data", "b200c_job_output_read", "b200c_job_get_stats", "b200c_job_destroy",
-           "b200c_job_run_until", "b200c_job_debug_read", "b200c_block_checksums"]
+           "b200c_job_run_until", "b200c_job_debug_read", "b200c_block_checksums", "b200c_job_kernel_time_count",
+           "b200c_job_kernel_time", "b200c_job_encode_columns"]
 
 
 def load_library(build_if_missing=True):
@@ -83,6 +84,9 @@ def load_library(build_if_missing=True):
     L.b200c_job_debug_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.b200c_block_checksums.argtypes = [C.c_int, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint8,
                                         C.POINTER(C.c_uint32)]
+    L.b200c_job_kernel_time_count.argtypes = [C.c_void_p]
+    L.b200c_job_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double)]
+    L.b200c_job_encode_columns.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200c_params_init.argtypes = [C.POINTER(Params)]
     L.b200c_params_init.restype = None
     _lib = L
@@ -174,6 +178,23 @@ class CompactionJob:
         _check(L.b200c_job_run(self._h) if until == 3 else L.b200c_job_run_until(self._h, until))
         return self
 
+    def encode_columns(self, n, pfx, tr, vref, meta):
+        """TableBuilder side alone: device columns (torch CUDA tensors) -> BlockBasedTable image(s)."""
+        self._keep += [pfx, tr, vref, meta]
+        _check(lib().b200c_job_encode_columns(self._h, n, C.c_void_p(pfx.data_ptr()), C.c_void_p(tr.data_ptr()),
+                                               C.c_void_p(vref.data_ptr()), C.c_void_p(meta.data_ptr())))
+        return self
+
+    def kernel_times(self):
+        """[(name, microseconds)] of the last run when created with profile=1"""
+        L = lib()
+        out = []
+        for i in range(L.b200c_job_kernel_time_count(self._h)):
+            name, us = C.c_char_p(), C.c_double()
+            _check(L.b200c_job_kernel_time(self._h, i, C.byref(name), C.byref(us)))
+            out.append((name.value.decode(), us.value))
+        return out
+
     def stats(self):
         s = JobStats()
         _check(lib().b200c_job_get_stats(self._h, C.byref(s)))
@@ -195,6 +216,13 @@ class CompactionJob:
         buf = C.create_string_buffer(m.file_size)
         _check(lib().b200c_job_output_read(self._h, i, buf, m.file_size))
         return buf.raw
+
+    def output_read_into(self, i, tensor):
+        """copy output i into a preallocated uint8 torch tensor (host, or device when output_mem='device')"""
+        m = self.output_meta(i)
+        assert tensor.numel() >= m.file_size
+        _check(lib().b200c_job_output_read(self._h, i, C.c_void_p(tensor.data_ptr()), tensor.numel()))
+        return m.file_size
 
     def output_ptr(self, i):
         p, n = C.c_void_p(), C.c_uint64()
