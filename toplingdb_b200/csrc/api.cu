@@ -114,7 +114,7 @@ struct b200c_job {
   // device state
   DevBuf files_d, blk_off, blk_size, blk_cnt, blk_base, scan_tmp, run_start, small;  // small: err, totals, counters...
   DevBuf dec[4], mrg[4], splits, tile_state, snaps_d;
-  DevBuf esz, eshared, nxt, disk, rows, tstate, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
+  DevBuf esz, eshared, nxt, disk, rows, tstate, grows, gstate, gflag, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
   uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
   uint32_t nfiles_out = 0;
   std::vector<uint64_t> run_start_h;
@@ -265,11 +265,18 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, E
     const uint64_t etiles = (n_out + kEncTile - 1) / kEncTile;
     CU(j->rows.reserve(sizeof(TileRow) * etiles * hc));
     CU(j->tstate.reserve(sizeof(TileState) * etiles));
+    const uint64_t egroups = (etiles + kEncGroupTiles - 1) / kEncGroupTiles;
+    CU(j->grows.reserve(sizeof(TileRow) * egroups * hc));
+    CU(j->gstate.reserve(sizeof(TileState) * egroups));
+    CU(j->gflag.reserve(4 * egroups));
     CU(j->nxt.reserve(2 * (n_out + 1)));
     CU(j->disk.reserve(4 * (n_out + 1)));
     CU(j->files_rec.reserve(sizeof(FileRec) * (kMaxOutFiles + 2)));
     W.rows = j->rows.as<TileRow>();
     W.tstate = j->tstate.as<TileState>();
+    W.grows = j->grows.as<TileRow>();
+    W.gstate = j->gstate.as<TileState>();
+    W.gflag = j->gflag.as<uint32_t>();
     W.nxt = j->nxt.as<uint16_t>();
     W.disk = j->disk.as<uint32_t>();
     W.files = j->files_rec.as<FileRec>();
@@ -278,9 +285,9 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, E
     launch_encode_tables(mcols, ep, W, etiles, hc, err, st);
     j->kt_end();
     j->kt_begin("encode.stitch");
-    launch_encode_stitch(mcols, ep, W, etiles, hc, err, st);
+    launch_encode_stitch(mcols, ep, W, etiles, hc, err, st, &launches);
     j->kt_end();
-    launches += 2;
+    launches += 1;
     CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));  // sync #2: number of blocks / files
     CU(cudaGetLastError());
@@ -825,7 +832,7 @@ void b200c_job_destroy(b200c_job* j) {
   cudaSetDevice(j->p.device);
   DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_cnt, &j->blk_base, &j->scan_tmp, &j->run_start, &j->small,
                    &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
-                   &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->blocks,
+                   &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};
   for (DevBuf* b : all) b->release();
   for (auto& in : j->inputs) in.staged.release();

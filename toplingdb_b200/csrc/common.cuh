@@ -55,6 +55,27 @@ __device__ __forceinline__ uint32_t ld_u32(const uint8_t* p) {
 }
 __device__ __forceinline__ uint64_t ld_u64(const uint8_t* p) { return (uint64_t)ld_u32(p) | ((uint64_t)ld_u32(p + 4) << 32); }
 
+__device__ __forceinline__ uint64_t ld_u64_aligned(const uint8_t* p) { return *reinterpret_cast<const uint64_t*>(p); }
+// bytes [s, s+16) of the 32-byte concatenation A|B (s in 0..15, warp-uniform): re-aligns 16-byte vectors on the fly
+__device__ __forceinline__ uint4 shift16(uint4 A, uint4 B, uint32_t s) {
+  const uint32_t bs = (s & 3) * 8;
+  uint4 r;
+  switch (s >> 2) {
+    case 0:
+      r.x = __funnelshift_r(A.x, A.y, bs), r.y = __funnelshift_r(A.y, A.z, bs), r.z = __funnelshift_r(A.z, A.w, bs), r.w = __funnelshift_r(A.w, B.x, bs);
+      break;
+    case 1:
+      r.x = __funnelshift_r(A.y, A.z, bs), r.y = __funnelshift_r(A.z, A.w, bs), r.z = __funnelshift_r(A.w, B.x, bs), r.w = __funnelshift_r(B.x, B.y, bs);
+      break;
+    case 2:
+      r.x = __funnelshift_r(A.z, A.w, bs), r.y = __funnelshift_r(A.w, B.x, bs), r.z = __funnelshift_r(B.x, B.y, bs), r.w = __funnelshift_r(B.y, B.z, bs);
+      break;
+    default:
+      r.x = __funnelshift_r(A.w, B.x, bs), r.y = __funnelshift_r(B.x, B.y, bs), r.z = __funnelshift_r(B.y, B.z, bs), r.w = __funnelshift_r(B.z, B.w, bs);
+  }
+  return r;
+}
+
 // varint32/64 decode; returns bytes consumed or 0 on malformed / overrun
 __device__ __forceinline__ int get_varint(const uint8_t* p, const uint8_t* end, uint64_t* v) {
   uint64_t r = 0;
@@ -204,7 +225,8 @@ __device__ inline uint64_t xxh3_64_short(const uint8_t* in, uint32_t len) {
 // lane returns the hash).  Long inputs: lane l owns accumulator lane (l & 7) of stripe group (l >> 3); the four
 // groups take stripes g, g+4, ... of each 1024-byte block, partial sums are folded with shuffles before the
 // scramble (additions commute inside a block; the scramble is the only sequential step).
-__device__ inline uint64_t xxh3_64_warp(const uint8_t* in, uint64_t len) {
+template <bool kAligned8>
+__device__ inline uint64_t xxh3_64_warp_t(const uint8_t* in, uint64_t len) {
   const unsigned lane = threadIdx.x & 31;
   if (len <= 240) return xxh3_64_short(in, (uint32_t)len);
   const int a = lane & 7, g = lane >> 3;
@@ -224,7 +246,7 @@ __device__ inline uint64_t xxh3_64_warp(const uint8_t* in, uint64_t len) {
     for (int i = 0; i < 4; i++) {
       uint64_t s = g + 4 * i;
       if (s < nstripes) {
-        uint64_t dv = ld_u64(blk + 64 * s + 8 * a), dk = dv ^ ksec[i];
+        uint64_t dv = kAligned8 ? ld_u64_aligned(blk + 64 * s + 8 * a) : ld_u64(blk + 64 * s + 8 * a), dk = dv ^ ksec[i];
         mul += (dk & 0xffffffffull) * (dk >> 32);
         add += dv;
       }
@@ -255,6 +277,10 @@ __device__ inline uint64_t xxh3_64_warp(const uint8_t* in, uint64_t len) {
   m += __shfl_xor_sync(0xffffffffu, m, 4);
   uint64_t r = xxh3_avalanche(len * kP64_1 + m);
   return __shfl_sync(0xffffffffu, r, 0);
+}
+
+__device__ inline uint64_t xxh3_64_warp(const uint8_t* in, uint64_t len) {
+  return (((uintptr_t)in & 7) == 0) ? xxh3_64_warp_t<true>(in, len) : xxh3_64_warp_t<false>(in, len);
 }
 
 // CRC32C (Castagnoli, reflected polynomial 0x82F63B78) — byte-wise table step used by the warp routine below.

@@ -125,18 +125,24 @@ __global__ void index_decode_kernel(const FileDesc* __restrict__ files, int nfil
 constexpr int kDecWarps = 8;
 constexpr int kDecSlice = 6144;  // bytes of shared memory per warp for one staged block (+trailer +align slack)
 
-// stage [src, src+total) into the warp's slice with aligned 16 B loads; returns the generic pointer to byte 0
+// stage [src, src+total) into the warp's slice, RE-ALIGNED so that byte 0 of the block sits at slice[0]: the
+// global side uses aligned 16 B loads, the funnel shift happens in registers, and everything that reads the staged
+// block afterwards (checksum stripes, restart array) can use naturally aligned shared-memory loads.
 __device__ __forceinline__ const uint8_t* stage_block(const uint8_t* src, uint32_t total, uint8_t* slice) {
   const unsigned lane = threadIdx.x & 31;
   if (total + 32 > (uint32_t)kDecSlice) return src;  // too big: parse straight from global memory
   uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15;
-  uint32_t shift = (uint32_t)((uintptr_t)src - a0);
-  uint32_t nvec = (shift + total + 15) >> 4;
+  const uint32_t shift = (uint32_t)((uintptr_t)src - a0);
+  const uint32_t nvec = (total + 15) >> 4;
   const uint4* g = (const uint4*)a0;
   uint4* s = (uint4*)slice;
-  for (uint32_t i = lane; i < nvec; i += 32) s[i] = __ldg(g + i);
+  if (shift == 0) {
+    for (uint32_t i = lane; i < nvec; i += 32) s[i] = __ldg(g + i);
+  } else {
+    for (uint32_t i = lane; i < nvec; i += 32) s[i] = shift16(__ldg(g + i), __ldg(g + i + 1), shift);
+  }
   __syncwarp();
-  return slice + shift;
+  return slice;
 }
 
 // number of entries in [p, end) (one restart interval); 0xffffffff on malformed data

@@ -144,34 +144,51 @@ __device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, c
 }
 
 struct CutParams {
-  uint32_t BS, LIM, R;
+  uint32_t BS, LIM, R, rshift;  // rshift = log2(R) when R is a power of two, else 32
 };
+__host__ __device__ __forceinline__ CutParams make_cut(uint32_t bs, uint32_t lim, uint32_t r) {
+  CutParams c{bs, lim, r, 32};
+  if ((r & (r - 1)) == 0) {
+    uint32_t sft = 0;
+    while ((1u << sft) < r) sft++;
+    c.rshift = sft;
+  }
+  return c;
+}
+__device__ __forceinline__ uint32_t div_r(uint32_t x, const CutParams& cp) { return cp.rshift < 32 ? x >> cp.rshift : x / cp.R; }
 // payload bytes of a block holding window entries [a, b)
-__device__ __forceinline__ uint64_t blk_payload(const Window& w, uint32_t a, uint32_t b, uint32_t R) {
-  uint32_t nrm1 = (b - 1 - a) / R;  // restarts - 1
-  uint32_t last = a + R * nrm1;
-  uint64_t q = (uint64_t)w.Q[last] - (a >= R ? (uint64_t)w.Q[a - R] : 0);
+__device__ __forceinline__ uint64_t blk_payload(const Window& w, uint32_t a, uint32_t b, const CutParams& cp) {
+  uint32_t nrm1 = div_r(b - 1 - a, cp);  // restarts - 1
+  uint32_t last = a + cp.R * nrm1;
+  uint64_t q = (uint64_t)w.Q[last] - (a >= cp.R ? (uint64_t)w.Q[a - cp.R] : 0);
   return w.P[b] - w.P[a] + q + 4ull * (nrm1 + 1) + 4;  // == BlockBuilder::CurrentSizeEstimate() (block_builder.cc:97,251)
 }
 // first b > a at which FlushBlockBySizePolicy::Update (flush_block_policy.cc:37-69) fires for a block started at a.
 // returns wlen at the end of the stream, 0xffffffff if the block does not end inside the window.
-__device__ __forceinline__ uint32_t next_block(const Window& w, uint32_t a, const CutParams& cp) {
+// hint: where the block of the previous start ended (0 = none); blocks of neighbouring starts end close to each other.
+__device__ __forceinline__ uint32_t next_block(const Window& w, uint32_t a, const CutParams& cp, uint32_t hint) {
   const uint32_t wlen = w.wlen;
   const uint64_t thr = cp.LIM ? cp.LIM : cp.BS - 1;
-  uint32_t lo = a + 1, hi = wlen + 1;
-  while (lo < hi) {  // first b with CurrentSizeEstimate > thr
+  uint32_t lo = a + 1, hi = wlen + 1;  // searching the first b in [lo, hi) with CurrentSizeEstimate(a, b) > thr; hi = none
+  if (hint > a + 1 && hint <= wlen) {
+    uint32_t l2 = hint > a + 4 ? hint - 3 : a + 1, h2 = hint + 5 < wlen ? hint + 5 : wlen;
+    if (l2 == a + 1 || blk_payload(w, a, l2 - 1, cp) <= thr) lo = l2;
+    if (blk_payload(w, a, h2, cp) > thr) hi = h2;
+  }
+  while (lo < hi) {
     uint32_t mid = (lo + hi) >> 1;
-    if (blk_payload(w, a, mid, cp.R) > thr) hi = mid;
+    if (blk_payload(w, a, mid, cp) > thr) hi = mid;
     else lo = mid + 1;
   }
   for (uint32_t b = lo; b < wlen; b++) {
-    uint64_t ec = blk_payload(w, a, b, cp.R);
+    uint64_t ec = blk_payload(w, a, b, cp);
     if (ec >= cp.BS) return b;
     if (cp.LIM) {  // BlockAlmostFull: EstimateSizeAfterKV (block_builder.cc:97-126) = ec + |k|+|v|+4+varints (+4 at a restart)
       uint64_t d = (uint64_t)w.Q[b] - (b >= cp.R ? (uint64_t)w.Q[b - cp.R] : 0);
       uint64_t s0 = (w.P[b + 1] - w.P[b]) + d;
-      uint64_t after = ec + s0 + 3 + (((b - a) % cp.R) == 0 ? 4 : 0);
-      if (after > cp.BS) return b;
+      uint32_t m = b - a;
+      bool at_restart = cp.rshift < 32 ? (m & (cp.R - 1)) == 0 : (m % cp.R) == 0;
+      if (ec + s0 + 3 + (at_restart ? 4 : 0) > cp.BS) return b;
     }
   }
   return w.at_end ? wlen : 0xffffffffu;
@@ -189,22 +206,32 @@ encode_tables_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TablesSmem& s = *reinterpret_cast<TablesSmem*>(smem_raw);
   const uint64_t tile = blockIdx.x, wstart = tile * (uint64_t)kTT;
-  const CutParams cp{ep.block_size, ep.block_size_limit, ep.restart_interval};
+  const CutParams cp = make_cut(ep.block_size, ep.block_size_limit, ep.restart_interval);
   build_window(s.w, m, wk.esz, wk.eshared, n, tile, cp.R);
   const uint32_t tl = s.w.wlen < (uint32_t)kTT ? s.w.wlen : (uint32_t)kTT;
-  for (uint32_t j = threadIdx.x; j < tl; j += kEncThreads) {
-    uint32_t b = next_block(s.w, j, cp);
-    uint16_t nx = 0xffff;
-    uint32_t dk = 0;
-    if (b != 0xffffffffu) {
-      nx = (uint16_t)b;
-      uint64_t pay = blk_payload(s.w, j, b, cp.R) + 5;
-      dk = pay > 0xffffffffull ? 0xffffffffu : (uint32_t)pay;
+  {
+    constexpr int kPer = kTT / kEncThreads;  // 16 consecutive block starts per thread: the previous answer is the hint
+    uint32_t hint = 0;
+    for (int i = 0; i < kPer; i++) {
+      const uint32_t j = threadIdx.x * kPer + i;
+      if (j >= tl) break;
+      uint32_t b = next_block(s.w, j, cp, hint);
+      hint = b == 0xffffffffu ? 0 : b;
+      uint16_t nx = 0xffff;
+      uint32_t dk = 0;
+      if (b != 0xffffffffu) {
+        nx = (uint16_t)b;
+        uint64_t pay = blk_payload(s.w, j, b, cp) + 5;
+        dk = pay > 0xffffffffull ? 0xffffffffu : (uint32_t)pay;
+      }
+      s.nxt[j] = nx;
+      s.disk[j] = dk;
     }
-    s.nxt[j] = nx;
-    s.disk[j] = dk;
-    g_nxt[wstart + j] = nx;
-    g_disk[wstart + j] = dk;
+  }
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < tl; j += kEncThreads) {  // coalesced copy for the block-list pass
+    g_nxt[wstart + j] = s.nxt[j];
+    g_disk[wstart + j] = s.disk[j];
   }
   __syncthreads();
   for (uint32_t c = threadIdx.x; c < hc; c += kEncThreads) {
@@ -231,6 +258,12 @@ encode_tables_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
 }
 
 // ------------------------------------------------------------------------------------------------ stitch
+// The chain of block starts is resolved hierarchically:
+//   encode_compose    composes the transfer functions of kEncGroup consecutive tiles per entry-point candidate
+//   encode_stitch     one CTA walks the group functions (a few hundred dependent steps); only groups in which an
+//                     output file ends are walked tile by tile, and only the tiles in which a file ends are walked
+//                     block by block (pointer chasing through nxt/disk staged in shared memory)
+//   encode_tilestate  per group: entry state of every tile, from the group's entry state
 struct WalkState {
   uint64_t a;         // absolute entry index where the open block starts
   uint64_t blk;       // blocks completed so far
@@ -257,18 +290,25 @@ __device__ __forceinline__ void close_file(FileRec* files, WalkState& st, uint64
   fr.index_has_seq = 0;
   fr.index_cksum = 0;
 }
-// walk the real chain through one tile with the window in shared memory (serial; only used for tiles in which an
-// output file ends).  emit != nullptr: also write BlockRecs.  Returns false on a block that leaves the window.
-__device__ bool walk_tile_serial(const Window& w, const CutParams& cp, const EncodeParams& ep, uint64_t wstart, uint64_t tile_end,
-                                 uint64_t n, WalkState& st, FileRec* files, BlockRec* emit, uint64_t emit_cap, uint32_t* err) {
-  while (st.a < tile_end && st.a < n) {
-    uint32_t ra = (uint32_t)(st.a - wstart);
-    uint32_t rb = next_block(w, ra, cp);
-    if (rb == 0xffffffffu) return false;
-    uint64_t y = wstart + rb;
-    uint64_t dsk = blk_payload(w, ra, rb, cp.R) + 5;
+// on-disk bytes of a data block that holds the single entry y
+__device__ __forceinline__ uint64_t single_entry_block_bytes(const KeyCols& m, const EncodeWork& wk, uint64_t y) {
+  uint32_t sh = wk.eshared[y], ks = meta_ulen(m.meta[y]) + 8;
+  uint64_t s0 = (uint64_t)wk.esz[y] + 1u + (uint32_t)varint_len(ks) + sh - (uint32_t)varint_len(sh) - (uint32_t)varint_len(ks - sh);
+  return s0 + 4 + 4 + 5;
+}
+// Follow the real chain through one tile whose nxt/disk sit in shared memory, applying the output-file cut rule
+// (compaction_outputs.cc:277: cut in front of the first entry added after the flushed size reached the maximum).
+// emit != nullptr: write BlockRecs.  files != nullptr: write FileRecs.
+__device__ bool chase_tile(const uint16_t* nxt, const uint32_t* disk, uint64_t tstart, uint32_t tl, uint64_t n, const EncodeParams& ep,
+                           const KeyCols& m, const EncodeWork& wk, WalkState& st, FileRec* files, BlockRec* emit, uint64_t emit_cap,
+                           uint32_t* err) {
+  while (st.a < tstart + tl) {
+    const uint32_t x = (uint32_t)(st.a - tstart);
+    const uint32_t yr = nxt[x];
+    if (yr == 0xffff || yr <= x) return false;
+    const uint64_t y = tstart + yr;
     if (emit && st.blk < emit_cap) emit[st.blk] = BlockRec{st.a, st.foff, st.f, (uint32_t)(y - st.a)};
-    st.foff += dsk;
+    st.foff += disk[x];
     st.blk++;
     if (y >= n) {  // Finish(): last block of the stream
       close_file(files, st, n, err);
@@ -277,9 +317,8 @@ __device__ bool walk_tile_serial(const Window& w, const CutParams& cp, const Enc
       return true;
     }
     if (ep.output_level != 0 && st.foff >= ep.max_output_file_size) {
-      // ShouldStopBefore fires in front of entry y+1: entry y (whose Add flushed the block) ends the file alone
-      if (rb + 1 > w.wlen) return false;
-      uint64_t d1 = blk_payload(w, rb, rb + 1, cp.R) + 5;
+      // entry y (whose Add flushed the block) still goes to this file and ends it as a single-entry block
+      const uint64_t d1 = single_entry_block_bytes(m, wk, y);
       if (emit && st.blk < emit_cap) emit[st.blk] = BlockRec{y, st.foff, st.f, 1u};
       st.foff += d1;
       st.blk++;
@@ -296,144 +335,219 @@ __device__ bool walk_tile_serial(const Window& w, const CutParams& cp, const Enc
   return true;
 }
 
+constexpr int kEncGroup = 64;  // tiles per group
+__global__ void encode_compose_kernel(EncodeWork wk, uint64_t n, uint64_t ntiles, uint32_t hc) {
+  const uint64_t g = blockIdx.x, t0 = g * kEncGroup, t1 = (t0 + kEncGroup) < ntiles ? (t0 + kEncGroup) : ntiles;
+  const uint64_t gstart = t0 * (uint64_t)kTT;
+  for (uint32_t c = threadIdx.x; c < hc; c += blockDim.x) {
+    uint64_t x = gstart + c, bytes = 0;
+    uint32_t nb = 0;
+    bool bad = false;
+    for (uint64_t t = t0; t < t1 && x < n; t++) {
+      const uint64_t tstart = t * (uint64_t)kTT, tend = (tstart + kTT) < n ? (tstart + kTT) : n;
+      if (x >= tend) continue;  // no block starts in this tile
+      const uint64_t cc = x - tstart;
+      if (cc >= hc) {
+        bad = true;
+        break;
+      }
+      const TileRow r = wk.rows[t * hc + cc];
+      if (r.exit == 0xffffffffu) {
+        bad = true;
+        break;
+      }
+      x = tstart + r.exit;
+      nb += r.nblk;
+      bytes += r.bytes;
+    }
+    TileRow o;
+    o.exit = bad ? 0xffffffffu : (uint32_t)(x - gstart);  // relative to the group start
+    o.nblk = nb;
+    o.bytes = bytes;
+    wk.grows[g * hc + c] = o;
+  }
+}
+
 struct StitchSmem {
-  Window w;
+  uint16_t nxt[kTT];
+  uint32_t disk[kTT];
   WalkState st;
-  uint64_t next_tile;
-  uint64_t filled;   // tiles whose TileState has been written
-  uint32_t need_window;
+  uint64_t tile;       // tile to chase next
+  uint32_t need_chase;
   uint32_t done;
 };
 __global__ void __launch_bounds__(kEncThreads)
-encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint64_t ntiles, uint32_t hc, uint32_t batch,
-                     uint32_t* __restrict__ err) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  StitchSmem& s = *reinterpret_cast<StitchSmem*>(smem_raw);
-  TileRow* rows = reinterpret_cast<TileRow*>(smem_raw + ((sizeof(StitchSmem) + 15) & ~(size_t)15));
-  const CutParams cp{ep.block_size, ep.block_size_limit, ep.restart_interval};
+encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint64_t ntiles, uint32_t hc, uint32_t* __restrict__ err) {
+  __shared__ StitchSmem s;
+  const uint64_t ngroups = (ntiles + kEncGroup - 1) / kEncGroup;
   if (threadIdx.x == 0) {
     s.st = WalkState{0, 0, 0, 0, 0, 0};
     s.done = (n == 0);
-    s.filled = 0;
-    s.need_window = 0;
-    s.next_tile = 0;
+    s.need_chase = 0;
+    s.tile = 0;
   }
   __syncthreads();
-  uint64_t t = 0;
-  while (t < ntiles && !s.done) {
-    const uint64_t tb = (ntiles - t) < batch ? (ntiles - t) : batch;
-    {  // prefetch the transfer functions of tiles [t, t + tb)
-      const uint4* src = reinterpret_cast<const uint4*>(wk.rows + t * hc);
-      uint4* dst = reinterpret_cast<uint4*>(rows);
-      for (uint64_t i = threadIdx.x; i < tb * hc; i += kEncThreads) dst[i] = src[i];
-    }
-    __syncthreads();
+  uint64_t g = 0;       // next group to enter (thread 0's view is authoritative; all threads keep it in step via smem)
+  __shared__ uint64_t s_g, s_t, s_tend;  // cursor: group, tile inside a detailed group (== s_tend when not detailed)
+  if (threadIdx.x == 0) {
+    s_g = 0;
+    s_t = 0;
+    s_tend = 0;
+  }
+  __syncthreads();
+  for (;;) {
     if (threadIdx.x == 0) {
       WalkState st = s.st;
-      uint64_t tt = t;
-      uint32_t need = 0;
-      for (; tt < t + tb; tt++) {
-        const uint64_t tstart = tt * (uint64_t)kTT;
-        const uint64_t tend = (tstart + kTT) < n ? (tstart + kTT) : n;
-        if (st.a >= n) break;
-        TileState ts;
-        ts.entry = st.a;
-        ts.blk = st.blk;
-        ts.file_off = st.foff;
-        ts.file_idx = st.f;
-        ts.pad = 0;
-        wk.tstate[tt] = ts;
-        s.filled = tt + 1;
-        if (st.a >= tend) continue;  // no block starts in this tile
-        uint64_t c = st.a - tstart;
-        if (c >= hc) {
-          atomicOr(err, kErrBlockTooLong);
+      s.need_chase = 0;
+      for (;;) {
+        if (st.a >= n) {
           s.done = 1;
           break;
         }
-        TileRow r = rows[(tt - t) * hc + c];
-        if (r.exit == 0xffffffffu) {
-          atomicOr(err, kErrBlockTooLong);
+        if (s_t < s_tend) {  // inside a detailed group: tile level
+          const uint64_t t = s_t, tstart = t * (uint64_t)kTT, tend = (tstart + kTT) < n ? (tstart + kTT) : n;
+          TileState ts{st.a, st.blk, st.foff, st.f, 0};
+          wk.tstate[t] = ts;
+          if (st.a >= tend) {
+            s_t++;
+            continue;
+          }
+          const uint64_t cc = st.a - tstart;
+          TileRow r;
+          r.exit = 0xffffffffu;
+          if (cc < hc) r = wk.rows[t * hc + cc];
+          const bool table_ok = cc < hc && r.exit != 0xffffffffu;
+          const bool cut = !table_ok || (ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size) || tstart + r.exit >= n;
+          if (cut) {  // a file ends in this tile (or the entry point is not tabulated): chase it block by block
+            s.tile = t;
+            s.need_chase = 1;
+            s_t++;
+            break;
+          }
+          st.a = tstart + r.exit;
+          st.blk += r.nblk;
+          st.foff += r.bytes;
+          s_t++;
+          continue;
+        }
+        // group level
+        if (s_g >= ngroups) {
           s.done = 1;
           break;
         }
-        const uint64_t exit_abs = tstart + r.exit;
-        const bool cut = ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size;
-        if (cut || exit_abs >= n) {  // a file ends inside this tile: walk it block by block
-          need = 1;
-          break;
+        const uint64_t gg = s_g, t0 = gg * kEncGroup, gstart = t0 * (uint64_t)kTT;
+        const uint64_t t1 = (t0 + kEncGroup) < ntiles ? (t0 + kEncGroup) : ntiles;
+        const uint64_t gend = (t1 * (uint64_t)kTT) < n ? (t1 * (uint64_t)kTT) : n;
+        TileState gs{st.a, st.blk, st.foff, st.f, 0};
+        wk.gstate[gg] = gs;
+        wk.gflag[gg] = 0;
+        s_g++;
+        if (st.a >= gend) continue;  // no block starts in this group
+        const uint64_t cc = st.a - gstart;
+        TileRow r;
+        r.exit = 0xffffffffu;
+        if (cc < hc) r = wk.grows[gg * hc + cc];
+        const bool table_ok = cc < hc && r.exit != 0xffffffffu;
+        const bool cut = !table_ok || (ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size) || gstart + r.exit >= n;
+        if (cut) {  // descend: tile by tile
+          wk.gflag[gg] = 1;
+          s_t = t0;
+          s_tend = t1;
+          continue;
         }
-        st.a = exit_abs;
+        st.a = gstart + r.exit;
         st.blk += r.nblk;
         st.foff += r.bytes;
       }
       s.st = st;
-      s.next_tile = tt;
-      s.need_window = need;
     }
     __syncthreads();
-    t = s.next_tile;
-    if (s.done) break;
-    if (s.need_window) {
-      build_window(s.w, m, wk.esz, wk.eshared, n, t, cp.R);
+    const uint32_t need = s.need_chase;  // stable: thread 0 writes these again only after the barrier that ends the iteration
+    uint32_t done = s.done;
+    if (need) {
+      const uint64_t t = s.tile, tstart = t * (uint64_t)kTT;
+      const uint32_t tl = (uint32_t)(((tstart + kTT) < n ? (tstart + kTT) : n) - tstart);
+      for (uint32_t j = threadIdx.x; j < tl; j += kEncThreads) {
+        s.nxt[j] = wk.nxt[tstart + j];
+        s.disk[j] = wk.disk[tstart + j];
+      }
       __syncthreads();
       if (threadIdx.x == 0) {
-        const uint64_t tstart = t * (uint64_t)kTT;
-        const uint64_t tend = (tstart + kTT) < n ? (tstart + kTT) : n;
         WalkState st = s.st;
-        if (!walk_tile_serial(s.w, cp, ep, tstart, tend, n, st, wk.files, nullptr, 0, err)) {
+        if (!chase_tile(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, wk.files, nullptr, 0, err)) {
           atomicOr(err, kErrBlockTooLong);
           s.done = 1;
         }
         s.st = st;
-        if (st.a >= n) s.done = 1;
       }
       __syncthreads();
-      t = t + 1;
+      done = s.done;
     }
-    if (threadIdx.x == 0 && s.st.a >= n) s.done = 1;
     __syncthreads();
+    if (done) break;
   }
   if (threadIdx.x == 0) {
-    // tiles never reached (stream ended earlier) get an entry point past the end
     wk.totals[0] = s.st.blk;
     wk.totals[1] = s.st.f;
-    for (uint64_t tt = s.filled; tt < ntiles; tt++) {
-      TileState ts;
-      ts.entry = n;
-      ts.blk = s.st.blk;
-      ts.file_off = 0;
-      ts.file_idx = s.st.f;
-      ts.pad = 0;
-      wk.tstate[tt] = ts;
+    // groups / tiles never entered (the stream ended before them) start past the end
+    TileState ts{n, s.st.blk, 0, s.st.f, 0};
+    for (uint64_t t = s_t; t < s_tend; t++) wk.tstate[t] = ts;
+    for (uint64_t gg = s_g; gg < ngroups; gg++) {
+      wk.gstate[gg] = ts;
+      wk.gflag[gg] = 0;
     }
+  }
+  (void)g;
+}
+
+// per group: entry state of each of its tiles (groups walked tile by tile by the stitch kernel already have them)
+__global__ void encode_tilestate_kernel(EncodeWork wk, uint64_t n, uint64_t ntiles, uint32_t hc, uint32_t* __restrict__ err) {
+  const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t ngroups = (ntiles + kEncGroup - 1) / kEncGroup;
+  if (g >= ngroups || wk.gflag[g]) return;
+  const TileState gs = wk.gstate[g];
+  uint64_t a = gs.entry, blk = gs.blk, foff = gs.file_off;
+  const uint64_t t0 = g * kEncGroup, t1 = (t0 + kEncGroup) < ntiles ? (t0 + kEncGroup) : ntiles;
+  for (uint64_t t = t0; t < t1; t++) {
+    const uint64_t tstart = t * (uint64_t)kTT, tend = (tstart + kTT) < n ? (tstart + kTT) : n;
+    TileState ts{a < n ? a : n, blk, foff, gs.file_idx, 0};
+    wk.tstate[t] = ts;
+    if (a >= n || a >= tend) continue;
+    const uint64_t cc = a - tstart;
+    if (cc >= hc) {
+      atomicOr(err, kErrBlockTooLong);
+      return;
+    }
+    const TileRow r = wk.rows[t * hc + cc];
+    if (r.exit == 0xffffffffu) {
+      atomicOr(err, kErrBlockTooLong);
+      return;
+    }
+    a = tstart + r.exit;
+    blk += r.nblk;
+    foff += r.bytes;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ block list
 struct BlistSmem {
-  Window w;              // only built on the serial path
   uint16_t nxt[kTT];
   uint32_t disk[kTT];
   uint8_t is_start[kTT];
   uint64_t ws[33];
   uint32_t serial;
-  WalkState st;
 };
 __global__ void __launch_bounds__(kEncThreads)
-encode_blocklist_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, const uint16_t* __restrict__ g_nxt,
-                        const uint32_t* __restrict__ g_disk, uint64_t nblk_cap, uint32_t* __restrict__ err) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  BlistSmem& s = *reinterpret_cast<BlistSmem*>(smem_raw);
+encode_blocklist_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint64_t nblk_cap, uint32_t* __restrict__ err) {
+  __shared__ BlistSmem s;
   const uint64_t tile = blockIdx.x, tstart = tile * (uint64_t)kTT;
   const uint64_t tend = (tstart + kTT) < n ? (tstart + kTT) : n;
   const uint32_t tl = (uint32_t)(tend - tstart);
   const TileState ts = wk.tstate[tile];
-  const CutParams cp{ep.block_size, ep.block_size_limit, ep.restart_interval};
   if (ts.entry >= tend) return;  // no block starts here
   for (uint32_t j = threadIdx.x; j < tl; j += kEncThreads) {
-    s.nxt[j] = g_nxt[tstart + j];
-    s.disk[j] = g_disk[tstart + j];
+    s.nxt[j] = wk.nxt[tstart + j];
+    s.disk[j] = wk.disk[tstart + j];
     s.is_start[j] = 0;
   }
   __syncthreads();
@@ -455,13 +569,7 @@ encode_blocklist_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, c
     }
     if (bad) atomicOr(err, kErrBlockTooLong);
     s.serial = bad ? 2 : ((ends || (ep.output_level != 0 && ts.file_off + bytes >= ep.max_output_file_size)) ? 1 : 0);
-  }
-  __syncthreads();
-  if (s.serial == 2) return;
-  if (s.serial == 1) {  // an output file ends inside this tile: replay the exact serial rule
-    build_window(s.w, m, wk.esz, wk.eshared, n, tile, cp.R);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (s.serial == 1) {  // an output file ends inside this tile: replay the exact serial rule
       WalkState st;
       st.a = ts.entry;
       st.blk = ts.blk;
@@ -469,10 +577,11 @@ encode_blocklist_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, c
       st.f = ts.file_idx;
       st.f_first_entry = 0;
       st.f_first_blk = 0;
-      if (!walk_tile_serial(s.w, cp, ep, tstart, tend, n, st, nullptr, wk.blocks, nblk_cap, err)) atomicOr(err, kErrBlockTooLong);
+      if (!chase_tile(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, nullptr, wk.blocks, nblk_cap, err)) atomicOr(err, kErrBlockTooLong);
     }
-    return;
   }
+  __syncthreads();
+  if (s.serial != 0) return;
   // parallel path: ranks and byte offsets of the block starts
   constexpr int kPer = kTT / kEncThreads;  // 16
   const uint32_t j0 = threadIdx.x * kPer;
@@ -564,6 +673,27 @@ constexpr int kEmitWarps = 8;
 __device__ __forceinline__ void lane_copy(uint8_t* dst, const uint8_t* src, uint32_t n) {
   for (uint32_t i = 0; i < n; i++) dst[i] = src[i];
 }
+// n <= 64 bytes from an arbitrarily aligned global address: all (aligned, independent) word loads are issued before
+// the first use, so the entry pays one memory latency instead of one per byte
+__device__ __forceinline__ void lane_copy_small(uint8_t* dst, const uint8_t* src, uint32_t n) {
+  const uint32_t a = (uint32_t)((uintptr_t)src & 3);
+  const uint32_t* ws = reinterpret_cast<const uint32_t*>((uintptr_t)src - a);
+  const uint32_t nw = (a + n + 3) >> 2;  // <= 17
+  uint32_t w[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) w[i] = (uint32_t)i < nw ? __ldg(ws + i) : 0u;
+  const uint32_t bs = a * 8;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    if ((uint32_t)(4 * i) < n) {
+      const uint32_t v = __funnelshift_r(w[i], w[i + 1], bs);
+      dst[4 * i] = (uint8_t)v;
+      if ((uint32_t)(4 * i + 1) < n) dst[4 * i + 1] = (uint8_t)(v >> 8);
+      if ((uint32_t)(4 * i + 2) < n) dst[4 * i + 2] = (uint8_t)(v >> 16);
+      if ((uint32_t)(4 * i + 3) < n) dst[4 * i + 3] = (uint8_t)(v >> 24);
+    }
+  }
+}
 __global__ void __launch_bounds__(kEmitWarps * 32)
 encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, uint8_t* const* __restrict__ out_base,
                    uint32_t slice_bytes, uint32_t* __restrict__ err) {
@@ -591,7 +721,7 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
     const uint64_t payload = body + 4ull * nrest + 4;
     const bool staged = payload + 5 + 16 <= slice_bytes;
     const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15);
-    uint8_t* img = staged ? slice + shift : gdst;
+    uint8_t* img = staged ? slice : gdst;  // image starts 16-byte aligned in shared memory: aligned checksum loads
     __syncwarp();
     // pass 2: encode entries, 32 at a time
     uint64_t off_base = 0;
@@ -622,7 +752,8 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
         p += put_varint(p, ks - sh);
         p += put_varint(p, vs);
         for (uint32_t t = sh; t < ks; t++) *p++ = (uint8_t)ikey_byte(hi, lo, ulen, tr, t);
-        if (vs < 128) lane_copy(p, (const uint8_t*)(uintptr_t)vref, vs);
+        if (vs <= 64) lane_copy_small(p, (const uint8_t*)(uintptr_t)vref, vs);
+        else if (vs < 128) lane_copy(p, (const uint8_t*)(uintptr_t)vref, vs);
         if (j % R == 0) {  // restart array slot (block_builder.cc:207-210,128-133)
           uint8_t* rp = img + body + 4ull * (j / R);
           uint32_t o32 = (uint32_t)off;
@@ -665,15 +796,19 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
       tp[4] = (uint8_t)(ck >> 24);
     }
     __syncwarp();
-    if (staged) {  // coalesced store of the image: head bytes, 16-byte body, tail bytes
+    if (staged) {  // coalesced store of the image: head bytes, 16-byte vectors re-aligned to the destination, tail bytes
       const uint32_t total = (uint32_t)payload + 5;
       uint32_t head = shift ? 16 - shift : 0;
       if (head > total) head = total;
       if (lane < head) gdst[lane] = img[lane];
       const uint32_t nvec = (total - head) >> 4;
-      const uint4* sv = reinterpret_cast<const uint4*>(img + head);
+      const uint4* sv = reinterpret_cast<const uint4*>(img);
       uint4* gv = reinterpret_cast<uint4*>(gdst + head);
-      for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
+      if (head == 0) {
+        for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
+      } else {
+        for (uint32_t i = lane; i < nvec; i += 32) gv[i] = shift16(sv[i], sv[i + 1], head);
+      }
       const uint32_t done = head + (nvec << 4);
       if (done + lane < total) gdst[done + lane] = img[done + lane];
       __syncwarp();
@@ -833,29 +968,20 @@ void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nti
   }
   encode_tables_kernel<<<(unsigned)ntiles, kEncThreads, sizeof(TablesSmem), st>>>(m, ep, w, m.n, hc, w.nxt, w.disk, err);
 }
-void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st) {
-  static bool attr = false;
-  const size_t base = (sizeof(StitchSmem) + 15) & ~(size_t)15;
-  size_t avail = 200 * 1024 - base;
-  uint32_t batch = (uint32_t)(avail / ((size_t)hc * sizeof(TileRow)));
-  if (batch > 512) batch = 512;
-  if (batch < 1) batch = 1;
-  size_t smem = base + (size_t)batch * hc * sizeof(TileRow);
-  if (!attr) {
-    cudaFuncSetAttribute(encode_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr = true;
-  }
-  encode_stitch_kernel<<<1, kEncThreads, smem, st>>>(m, ep, w, m.n, ntiles, hc, batch, err);
+void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st,
+                          uint64_t* launches) {
+  if (ntiles == 0) return;
+  const uint64_t ngroups = (ntiles + kEncGroup - 1) / kEncGroup;
+  unsigned ct = hc < 1024 ? ((hc + 31) & ~31u) : 1024;
+  encode_compose_kernel<<<(unsigned)ngroups, ct, 0, st>>>(w, m.n, ntiles, hc);
+  encode_stitch_kernel<<<1, kEncThreads, 0, st>>>(m, ep, w, m.n, ntiles, hc, err);
+  encode_tilestate_kernel<<<(unsigned)((ngroups + 63) / 64), 64, 0, st>>>(w, m.n, ntiles, hc, err);
+  if (launches) *launches += 3;
 }
 void launch_encode_blocklist(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint64_t nblk_cap, uint32_t* err,
                              cudaStream_t st) {
   if (ntiles == 0) return;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(encode_blocklist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlistSmem));
-    attr = true;
-  }
-  encode_blocklist_kernel<<<(unsigned)ntiles, kEncThreads, sizeof(BlistSmem), st>>>(m, ep, w, m.n, w.nxt, w.disk, nblk_cap, err);
+  encode_blocklist_kernel<<<(unsigned)ntiles, kEncThreads, 0, st>>>(m, ep, w, m.n, nblk_cap, err);
 }
 void launch_encode_filestats(KeyCols m, EncodeWork w, uint32_t nfiles, int sms, cudaStream_t st) {
   if (m.n == 0 || nfiles == 0) return;

@@ -92,7 +92,8 @@ struct TileState {           // resolved state when the chain enters a tile
   uint32_t pad;
 };
 constexpr int kEncTile = 4096;       // entries per block-cut tile
-constexpr int kEncHalo = 2048;       // look-ahead window = the longest block (in entries) the encoder accepts
+constexpr int kEncHalo = 2048;
+constexpr int kEncGroupTiles = 64;   // tiles per stitch group (encode.cu kEncGroup)       // look-ahead window = the longest block (in entries) the encoder accepts
 constexpr uint32_t kMaxOutFiles = 4096;
 
 struct EncodeWork {                  // device scratch owned by the job
@@ -100,6 +101,9 @@ struct EncodeWork {                  // device scratch owned by the job
   uint8_t* eshared;     // n: bytes shared with the previous internal key
   uint32_t* min_s1;     // 1: global min of esz (bounds the entry-point candidate window)
   TileRow* rows;        // ntiles x hc
+  TileRow* grows;       // ngroups x hc: composed transfer functions of kEncGroup tiles (exit relative to the group start)
+  TileState* gstate;    // ngroups: state at which the chain enters the group
+  uint32_t* gflag;      // ngroups: 1 = the stitch kernel walked this group tile by tile (a file ends inside)
   TileState* tstate;    // ntiles
   uint64_t* totals;     // [0] = number of blocks, [1] = number of files
   BlockRec* blocks;     // capacity nblk_cap
@@ -113,7 +117,8 @@ struct EncodeWork {                  // device scratch owned by the job
 };
 void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, uint64_t n_cap, cudaStream_t st);
 void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st);
-void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st);
+void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st,
+                          uint64_t* launches);
 void launch_encode_blocklist(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint64_t nblk_cap, uint32_t* err,
                              cudaStream_t st);
 void launch_encode_filestats(KeyCols m, EncodeWork w, uint32_t nfiles, int sms, cudaStream_t st);
