@@ -21,6 +21,7 @@ enum DevErr : uint32_t {
   kErrBlockTooLong = 1u << 7,    // more entries in one output block than the encoder's window
   kErrInternal = 1u << 8,
   kErrCountMismatch = 1u << 9,   // entry count differs from rocksdb.num.entries
+  kErrIrregularRestarts = 1u << 10,  // restart intervals of one block hold different numbers of entries
 };
 
 constexpr int kMaxUserKey = 16;

@@ -13,8 +13,8 @@
 //   index_decode_kernel   one thread per index restart point  -> data block handles
 //   block_count_kernel    one warp per data block: stage block in shared memory with 16 B loads, verify the
 //                         block checksum (warp-cooperative XXH3 / CRC32C), count entries per restart interval
-//   block_decode_kernel   one warp per data block: lanes own restart intervals (independent prefix-decode units),
-//                         rebuild keys, emit (hi, lo, trailer, vref, meta)
+//   block_decode_kernel   one THREAD per restart interval (the independent prefix-decode unit): aligned 8-byte loads
+//                         straight from the image, key rebuilt in registers, emits (hi, lo, trailer, vref, meta)
 #include "common.cuh"
 #include "kernels.h"
 
@@ -213,7 +213,7 @@ __device__ __forceinline__ BlockView open_block(const FileDesc& fd, uint64_t off
 __global__ void __launch_bounds__(kDecWarps * 32)
 block_count_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
                    const uint32_t* __restrict__ blk_size, uint32_t nblk, uint32_t verify, uint32_t* __restrict__ blk_cnt,
-                   uint32_t* __restrict__ err) {
+                   uint32_t* __restrict__ blk_nr, uint32_t* __restrict__ blk_r, uint32_t* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem[];
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint8_t* slice = smem + (size_t)w * kDecSlice;
@@ -222,104 +222,220 @@ block_count_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_
     const FileDesc fd = files[f];
     __syncwarp();
     BlockView v = open_block(fd, blk_off[b], blk_size[b], slice, verify, err);
-    uint32_t cnt = 0;
+    uint32_t cnt = 0, first = 0, irregular = 0;
     if (v.ok) {
-      for (uint32_t j = lane; j < v.nr; j += 32) {
-        uint32_t r0 = ld_u32(v.restarts + 4ull * j);
-        uint32_t r1 = j + 1 < v.nr ? ld_u32(v.restarts + 4ull * (j + 1)) : (uint32_t)(v.restarts - v.p);
-        uint32_t c = (r0 <= r1 && v.p + r1 <= v.restarts) ? count_interval(v.p + r0, v.p + r1) : 0xffffffffu;
-        if (c == 0xffffffffu) {
-          atomicOr(err, kErrCorruptBlock);
-          c = 0;
+      for (uint32_t j0 = 0; j0 < v.nr; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        uint32_t c = 0;
+        if (j < v.nr) {
+          uint32_t r0 = ld_u32(v.restarts + 4ull * j);
+          uint32_t r1 = j + 1 < v.nr ? ld_u32(v.restarts + 4ull * (j + 1)) : (uint32_t)(v.restarts - v.p);
+          c = (r0 <= r1 && v.p + r1 <= v.restarts) ? count_interval(v.p + r0, v.p + r1) : 0xffffffffu;
+          if (c == 0xffffffffu) {
+            atomicOr(err, kErrCorruptBlock);
+            c = 0;
+          }
         }
+        if (j0 == 0) first = __shfl_sync(0xffffffffu, c, 0);
+        // every restart interval but the last must hold the same number of entries (what BlockBuilder writes): the
+        // decoder derives an interval's output position from its index
+        if (j + 1 < v.nr && c != first) irregular = 1;
+        if (j + 1 == v.nr && c > first) irregular = 1;
         cnt += c;
       }
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if (__any_sync(0xffffffffu, irregular) && lane == 0) atomicOr(err, kErrIrregularRestarts);
+    if (lane == 0) {
+      blk_nr[b] = v.ok ? v.nr : 0;
+      blk_r[b] = first;
+    }
     if (lane == 0) blk_cnt[b] = cnt;
   }
 }
 
-__global__ void __launch_bounds__(kDecWarps * 32)
+// ---- thread-per-restart-interval decode -----------------------------------------------------------------------
+// A restart interval (16 entries by default) is the unit that can be prefix-decoded independently, so the decoder gives
+// every interval its own thread: ~N/16 threads in flight instead of one warp per 4 KB block with 5 busy lanes.
+// The thread streams through its ~1 KB of the file image with aligned 8-byte loads (L1 keeps the line for the next
+// entry); the current internal key lives in three registers (K0..K2 = its 24 bytes as little-endian words) and is
+// updated with mask / funnel-shift arithmetic instead of a byte buffer.
+
+struct Win {  // 40 bytes of the image starting at the 8-byte aligned address below p
+  uint64_t w0, w1, w2, w3, w4;
+};
+__device__ __forceinline__ Win load_win(const uint8_t* p) {
+  const uint64_t* a = reinterpret_cast<const uint64_t*>((uintptr_t)p & ~(uintptr_t)7);
+  Win w;
+  w.w0 = __ldg(a);
+  w.w1 = __ldg(a + 1);
+  w.w2 = __ldg(a + 2);
+  w.w3 = __ldg(a + 3);
+  w.w4 = __ldg(a + 4);
+  return w;
+}
+// 8 bytes of the window starting at byte k (0 <= k <= 32)
+__device__ __forceinline__ uint64_t win64(const Win& w, uint32_t k) {
+  const uint32_t i = k >> 3, sh = (k & 7) * 8;
+  uint64_t lo = i == 0 ? w.w0 : i == 1 ? w.w1 : i == 2 ? w.w2 : i == 3 ? w.w3 : w.w4;
+  uint64_t hi = i == 0 ? w.w1 : i == 1 ? w.w2 : i == 2 ? w.w3 : i == 3 ? w.w4 : 0;
+  return sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+}
+__device__ __forceinline__ uint64_t low_bytes_mask(uint32_t nbytes) {  // nbytes in 0..8
+  return nbytes >= 8 ? ~0ull : ((1ull << (8 * nbytes)) - 1);
+}
+
+__global__ void __launch_bounds__(256)
 block_decode_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
-                    const uint32_t* __restrict__ blk_size, const uint64_t* __restrict__ blk_base, uint32_t nblk,
-                    uint64_t n_total, KeyColsMut out, uint32_t* __restrict__ err) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint8_t* slice = smem + (size_t)w * kDecSlice;
-  for (uint32_t b = blockIdx.x * kDecWarps + w; b < nblk; b += gridDim.x * kDecWarps) {
+                    const uint32_t* __restrict__ blk_size, const uint64_t* __restrict__ blk_base, const uint32_t* __restrict__ blk_r,
+                    const uint64_t* __restrict__ rbase, const uint64_t* __restrict__ total_intervals, uint32_t nblk, uint64_t n_total,
+                    KeyColsMut out, uint32_t* __restrict__ err) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t total = *total_intervals;
+  const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  for (uint64_t ii0 = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; ii0 < total; ii0 += nwarps * 32) {
+    // block that holds interval ii0 (same search in every lane: uniform loads), then a short forward walk per lane
+    uint32_t lo = 0, hi = nblk;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (rbase[mid] <= ii0) lo = mid;
+      else hi = mid;
+    }
+    const uint64_t ii = ii0 + lane;
+    if (ii >= total) continue;
+    uint32_t b = lo;
+    while (b + 1 < nblk && rbase[b + 1] <= ii) b++;
+    const uint32_t j = (uint32_t)(ii - rbase[b]);
+    const uint32_t nr = (uint32_t)((b + 1 < nblk ? rbase[b + 1] : total) - rbase[b]);
     const int f = file_of_block(files, nfiles, b);
-    const FileDesc fd = files[f];
-    __syncwarp();
-    BlockView v = open_block(fd, blk_off[b], blk_size[b], slice, 0, err);
-    if (!v.ok) continue;
-    uint64_t base = blk_base[b];
-    for (uint32_t j0 = 0; j0 < v.nr; j0 += 32) {
-      uint32_t j = j0 + lane;
-      uint32_t r0 = 0, r1 = 0, c = 0;
-      if (j < v.nr) {
-        r0 = ld_u32(v.restarts + 4ull * j);
-        r1 = j + 1 < v.nr ? ld_u32(v.restarts + 4ull * (j + 1)) : (uint32_t)(v.restarts - v.p);
-        c = (r0 <= r1 && v.p + r1 <= v.restarts) ? count_interval(v.p + r0, v.p + r1) : 0;
-        if (c == 0xffffffffu) c = 0;
-      }
-      uint32_t inc = warp_incl_scan(c);
-      uint64_t e = base + (inc - c);
-      base += __shfl_sync(0xffffffffu, inc, 31);
-      if (c == 0) continue;
-      // prefix-decode this restart interval
-      uint8_t kb[kMaxUserKey + 8];
-      uint32_t klen = 0;
-      const uint8_t* p = v.p + r0;
-      const uint8_t* end = v.p + r1;
-      for (uint32_t i = 0; i < c; i++, e++) {
-        uint64_t shared, non_shared, vlen;
-        int cc;
-        if ((p[0] | p[1] | p[2]) < 128) {
-          shared = p[0];
-          non_shared = p[1];
-          vlen = p[2];
-          p += 3;
-        } else {
-          cc = get_varint(p, end, &shared);
-          p += cc;
-          cc = get_varint(p, end, &non_shared);
-          p += cc;
-          cc = get_varint(p, end, &vlen);
-          p += cc;
+    const uint8_t* blk = files[f].base + blk_off[b];
+    const uint32_t size = blk_size[b];
+    const uint8_t* restarts = blk + size - 4 - 4ull * nr;
+    const uint32_t r0 = ld_u32(restarts + 4ull * j);
+    const uint32_t r1 = j + 1 < nr ? ld_u32(restarts + 4ull * (j + 1)) : (uint32_t)(restarts - blk);
+    uint64_t e = blk_base[b] + (uint64_t)j * blk_r[b];
+    const uint8_t* p = blk + r0;
+    const uint8_t* end = blk + r1;
+    uint64_t K0 = 0, K1 = 0, K2 = 0;
+    uint32_t klen = 0;
+    while (p < end) {
+      const Win w = load_win(p);
+      const uint32_t o = (uint32_t)((uintptr_t)p & 7);
+      uint64_t h = win64(w, o);
+      uint32_t shared, non_shared, vlen, hdr;
+      if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {  // DecodeEntry fast path: three one-byte lengths
+        shared = (uint32_t)(h & 0xff);
+        non_shared = (uint32_t)((h >> 8) & 0xff);
+        vlen = (uint32_t)((h >> 16) & 0xff);
+        hdr = 3;
+      } else {  // varints from the 8 header bytes in the register (three varint32 of at most 8 bytes together)
+        uint64_t vals[3];
+        uint32_t k = 0;
+        bool ok = true;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          uint64_t v = 0;
+          uint32_t sft = 0;
+          for (;;) {
+            if (k >= 8) {
+              ok = false;
+              break;
+            }
+            uint32_t c = (uint32_t)((h >> (8 * k)) & 0xff);
+            k++;
+            v |= (uint64_t)(c & 127) << sft;
+            if (c < 128) break;
+            sft += 7;
+          }
+          vals[q] = v;
         }
-        if (shared > klen || shared + non_shared < 8) {
-          atomicOr(err, kErrCorruptBlock);
-          break;
+        if (!ok) {  // longer than 8 bytes: byte-wise from memory
+          const uint8_t* q = p;
+          int c1 = get_varint(q, end, &vals[0]);
+          q += c1;
+          int c2 = c1 ? get_varint(q, end, &vals[1]) : 0;
+          q += c2;
+          int c3 = c2 ? get_varint(q, end, &vals[2]) : 0;
+          if (!c3) {
+            atomicOr(err, kErrCorruptBlock);
+            break;
+          }
+          k = (uint32_t)(c1 + c2 + c3);
         }
-        if (shared + non_shared > (uint64_t)(kMaxUserKey + 8)) {
-          atomicOr(err, kErrKeyTooLong);
-          break;
-        }
-        if (vlen > kMetaVlenMask) {
+        if (vals[2] > kMetaVlenMask) {
           atomicOr(err, kErrValueTooLong);
           break;
         }
-        for (uint32_t t = 0; t < (uint32_t)non_shared; t++) kb[shared + t] = p[t];
-        klen = (uint32_t)(shared + non_shared);
-        p += non_shared;
-        const uint32_t ulen = klen - 8;
-        uint64_t hi = 0, lo = 0, tr = 0;
-        for (uint32_t t = 0; t < 8; t++) hi = (hi << 8) | (t < ulen ? kb[t] : 0);
-        for (uint32_t t = 8; t < 16; t++) lo = (lo << 8) | (t < ulen ? kb[t] : 0);
-        for (int t = 7; t >= 0; t--) tr = (tr << 8) | kb[ulen + t];
-        if ((tr & 0xff) > 1) atomicOr(err, kErrBadType);
-        if (e < n_total) {
-          out.pfx[e] = make_ulonglong2(hi, lo);
-          out.tr[e] = tr;
-          out.vref[e] = (uint64_t)(uintptr_t)(v.gsrc + (p - v.p));
-          out.meta[e] = make_meta(ulen, (uint32_t)vlen);
-        } else {
-          atomicOr(err, kErrCountMismatch);
+        if (vals[0] > 64 || vals[1] > 64 || k > 8) {  // keys longer than the device format / exotic header
+          atomicOr(err, vals[0] + vals[1] > (uint64_t)(kMaxUserKey + 8) ? kErrKeyTooLong : kErrCorruptBlock);
+          break;
         }
-        p += vlen;
+        shared = (uint32_t)vals[0];
+        non_shared = (uint32_t)vals[1];
+        vlen = (uint32_t)vals[2];
+        hdr = k;
       }
+      if (shared > klen || shared + non_shared < 8) {
+        atomicOr(err, kErrCorruptBlock);
+        break;
+      }
+      if (shared + non_shared > (uint32_t)(kMaxUserKey + 8)) {
+        atomicOr(err, kErrKeyTooLong);
+        break;
+      }
+      // key suffix: non_shared bytes that follow the header
+      const uint32_t so = o + hdr;
+      uint64_t S0 = win64(w, so), S1 = win64(w, so + 8), S2 = win64(w, so + 16);
+      S0 &= low_bytes_mask(non_shared);
+      S1 &= non_shared > 8 ? low_bytes_mask(non_shared - 8) : 0;
+      S2 &= non_shared > 16 ? low_bytes_mask(non_shared - 16) : 0;
+      // keep `shared` bytes of the previous key
+      K0 &= low_bytes_mask(shared);
+      K1 &= shared > 8 ? low_bytes_mask(shared - 8) : 0;
+      K2 &= shared > 16 ? low_bytes_mask(shared - 16) : 0;
+      // K |= S << (8 * shared)
+      {
+        const uint32_t ws = shared >> 3, bs = (shared & 7) * 8;
+        const uint64_t c0 = bs ? S0 >> (64 - bs) : 0, c1 = bs ? S1 >> (64 - bs) : 0;
+        const uint64_t T0 = S0 << bs, T1 = (S1 << bs) | c0, T2 = (S2 << bs) | c1;
+        if (ws == 0) {
+          K0 |= T0;
+          K1 |= T1;
+          K2 |= T2;
+        } else if (ws == 1) {
+          K1 |= T0;
+          K2 |= T1;
+        } else if (ws == 2) {
+          K2 |= T0;
+        }
+      }
+      klen = shared + non_shared;
+      const uint32_t ulen = klen - 8;
+      const uint64_t hi = bswap64(K0 & low_bytes_mask(ulen));
+      const uint64_t lo = bswap64(ulen > 8 ? K1 & low_bytes_mask(ulen - 8) : 0);
+      uint64_t tr;
+      {
+        const uint32_t ws = ulen >> 3, bs = (ulen & 7) * 8;
+        const uint64_t a = ws == 0 ? K0 : ws == 1 ? K1 : K2, c = ws == 0 ? K1 : ws == 1 ? K2 : 0;
+        tr = bs ? (a >> bs) | (c << (64 - bs)) : a;
+      }
+      if ((tr & 0xff) > 1) atomicOr(err, kErrBadType);
+      const uint8_t* val = p + hdr + non_shared;
+      if ((uint64_t)(end - val) < vlen) {
+        atomicOr(err, kErrCorruptBlock);
+        break;
+      }
+      if (e < n_total) {
+        out.pfx[e] = make_ulonglong2(hi, lo);
+        out.tr[e] = tr;
+        out.vref[e] = (uint64_t)(uintptr_t)val;
+        out.meta[e] = make_meta(ulen, vlen);
+      } else {
+        atomicOr(err, kErrCountMismatch);
+      }
+      e++;
+      p = val + vlen;
     }
   }
 }
@@ -359,15 +475,16 @@ static unsigned dec_grid(uint32_t nblk, int sms) {
   return want < cap ? (want ? want : 1) : cap;
 }
 void launch_block_count(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
-                        uint32_t nblk, uint32_t verify, uint32_t* blk_cnt, uint32_t* err, int sms, cudaStream_t st) {
+                        uint32_t nblk, uint32_t verify, uint32_t* blk_cnt, uint32_t* blk_nr, uint32_t* blk_r, uint32_t* err, int sms,
+                        cudaStream_t st) {
   block_count_kernel<<<dec_grid(nblk, sms), kDecWarps * 32, kDecWarps * kDecSlice, st>>>(files_dev, nfiles, blk_off, blk_size,
-                                                                                       nblk, verify, blk_cnt, err);
+                                                                                       nblk, verify, blk_cnt, blk_nr, blk_r, err);
 }
 void launch_block_decode(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
-                         const uint64_t* blk_base, uint32_t nblk, uint64_t n_total, KeyColsMut out, uint32_t* err, int sms,
-                         cudaStream_t st) {
-  block_decode_kernel<<<dec_grid(nblk, sms), kDecWarps * 32, kDecWarps * kDecSlice, st>>>(files_dev, nfiles, blk_off, blk_size,
-                                                                                        blk_base, nblk, n_total, out, err);
+                         const uint64_t* blk_base, const uint32_t* blk_r, const uint64_t* rbase, const uint64_t* total_intervals,
+                         uint32_t nblk, uint64_t n_total, KeyColsMut out, uint32_t* err, int sms, cudaStream_t st) {
+  block_decode_kernel<<<(unsigned)sms * 8, 256, 0, st>>>(files_dev, nfiles, blk_off, blk_size, blk_base, blk_r, rbase,
+                                                         total_intervals, nblk, n_total, out, err);
 }
 void launch_run_starts(const FileDesc* files_dev, int nfiles, const uint64_t* blk_base, const uint64_t* total, uint32_t nblk,
                        uint64_t* run_start, cudaStream_t st) {

@@ -210,13 +210,12 @@ encode_tables_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
   build_window(s.w, m, wk.esz, wk.eshared, n, tile, cp.R);
   const uint32_t tl = s.w.wlen < (uint32_t)kTT ? s.w.wlen : (uint32_t)kTT;
   {
-    constexpr int kPer = kTT / kEncThreads;  // 16 consecutive block starts per thread: the previous answer is the hint
-    uint32_t hint = 0;
-    for (int i = 0; i < kPer; i++) {
-      const uint32_t j = threadIdx.x * kPer + i;
-      if (j >= tl) break;
-      uint32_t b = next_block(s.w, j, cp, hint);
-      hint = b == 0xffffffffu ? 0 : b;
+    // thread t takes starts t, t+256, ...: neighbouring lanes touch neighbouring prefix-sum words (no bank conflicts);
+    // the length of the block found for the previous start is the hint for the next one
+    uint32_t prev_len = 0;
+    for (uint32_t j = threadIdx.x; j < tl; j += kEncThreads) {
+      uint32_t b = next_block(s.w, j, cp, prev_len ? j + prev_len : 0);
+      prev_len = b == 0xffffffffu ? 0 : b - j;
       uint16_t nx = 0xffff;
       uint32_t dk = 0;
       if (b != 0xffffffffu) {
@@ -372,87 +371,95 @@ struct StitchSmem {
   uint16_t nxt[kTT];
   uint32_t disk[kTT];
   WalkState st;
-  uint64_t tile;       // tile to chase next
-  uint32_t need_chase;
+  uint64_t g, t, tend;    // cursor: next group; next tile / end tile of the group being walked tile by tile
+  uint64_t ga, ta;        // first group / tile held by the row caches
+  uint32_t gn, tn;        // number of groups / tiles cached
+  uint64_t req_idx;       // argument of the request
+  uint32_t req;           // 0 none, 1 chase tile req_idx, 2 load group rows from req_idx, 3 load tile rows from req_idx
   uint32_t done;
 };
+constexpr uint32_t kStitchCacheBytes = 72 * 1024;  // per row cache
 __global__ void __launch_bounds__(kEncThreads)
 encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint64_t ntiles, uint32_t hc, uint32_t* __restrict__ err) {
-  __shared__ StitchSmem s;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  StitchSmem& s = *reinterpret_cast<StitchSmem*>(smem_raw);
+  TileRow* gcache = reinterpret_cast<TileRow*>(smem_raw + ((sizeof(StitchSmem) + 15) & ~(size_t)15));
+  TileRow* tcache = gcache + kStitchCacheBytes / sizeof(TileRow);
+  const uint32_t cache_rows = kStitchCacheBytes / sizeof(TileRow) / hc;  // groups / tiles per cache (>= 1: hc <= 2048)
   const uint64_t ngroups = (ntiles + kEncGroup - 1) / kEncGroup;
   if (threadIdx.x == 0) {
     s.st = WalkState{0, 0, 0, 0, 0, 0};
     s.done = (n == 0);
-    s.need_chase = 0;
-    s.tile = 0;
-  }
-  __syncthreads();
-  uint64_t g = 0;       // next group to enter (thread 0's view is authoritative; all threads keep it in step via smem)
-  __shared__ uint64_t s_g, s_t, s_tend;  // cursor: group, tile inside a detailed group (== s_tend when not detailed)
-  if (threadIdx.x == 0) {
-    s_g = 0;
-    s_t = 0;
-    s_tend = 0;
+    s.req = 0;
+    s.g = s.t = s.tend = 0;
+    s.ga = s.ta = 0;
+    s.gn = s.tn = 0;
   }
   __syncthreads();
   for (;;) {
     if (threadIdx.x == 0) {
       WalkState st = s.st;
-      s.need_chase = 0;
+      s.req = 0;
       for (;;) {
         if (st.a >= n) {
           s.done = 1;
           break;
         }
-        if (s_t < s_tend) {  // inside a detailed group: tile level
-          const uint64_t t = s_t, tstart = t * (uint64_t)kTT, tend = (tstart + kTT) < n ? (tstart + kTT) : n;
+        if (s.t < s.tend) {  // inside a group that is walked tile by tile
+          const uint64_t t = s.t, tstart = t * (uint64_t)kTT, tend = (tstart + kTT) < n ? (tstart + kTT) : n;
+          if (st.a < tend && !(t >= s.ta && t < s.ta + s.tn)) {
+            s.req = 3;
+            s.req_idx = t;
+            break;
+          }
           TileState ts{st.a, st.blk, st.foff, st.f, 0};
           wk.tstate[t] = ts;
-          if (st.a >= tend) {
-            s_t++;
-            continue;
-          }
+          s.t++;
+          if (st.a >= tend) continue;  // no block starts in this tile
           const uint64_t cc = st.a - tstart;
           TileRow r;
           r.exit = 0xffffffffu;
-          if (cc < hc) r = wk.rows[t * hc + cc];
+          if (cc < hc) r = tcache[(t - s.ta) * hc + cc];
           const bool table_ok = cc < hc && r.exit != 0xffffffffu;
           const bool cut = !table_ok || (ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size) || tstart + r.exit >= n;
           if (cut) {  // a file ends in this tile (or the entry point is not tabulated): chase it block by block
-            s.tile = t;
-            s.need_chase = 1;
-            s_t++;
+            s.req = 1;
+            s.req_idx = t;
             break;
           }
           st.a = tstart + r.exit;
           st.blk += r.nblk;
           st.foff += r.bytes;
-          s_t++;
           continue;
         }
         // group level
-        if (s_g >= ngroups) {
+        if (s.g >= ngroups) {
           s.done = 1;
           break;
         }
-        const uint64_t gg = s_g, t0 = gg * kEncGroup, gstart = t0 * (uint64_t)kTT;
+        const uint64_t gg = s.g, t0 = gg * kEncGroup, gstart = t0 * (uint64_t)kTT;
         const uint64_t t1 = (t0 + kEncGroup) < ntiles ? (t0 + kEncGroup) : ntiles;
         const uint64_t gend = (t1 * (uint64_t)kTT) < n ? (t1 * (uint64_t)kTT) : n;
+        if (st.a < gend && !(gg >= s.ga && gg < s.ga + s.gn)) {
+          s.req = 2;
+          s.req_idx = gg;
+          break;
+        }
         TileState gs{st.a, st.blk, st.foff, st.f, 0};
         wk.gstate[gg] = gs;
         wk.gflag[gg] = 0;
-        s_g++;
+        s.g++;
         if (st.a >= gend) continue;  // no block starts in this group
         const uint64_t cc = st.a - gstart;
         TileRow r;
         r.exit = 0xffffffffu;
-        if (cc < hc) r = wk.grows[gg * hc + cc];
+        if (cc < hc) r = gcache[(gg - s.ga) * hc + cc];
         const bool table_ok = cc < hc && r.exit != 0xffffffffu;
         const bool cut = !table_ok || (ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size) || gstart + r.exit >= n;
         if (cut) {  // descend: tile by tile
           wk.gflag[gg] = 1;
-          s_t = t0;
-          s_tend = t1;
+          s.t = t0;
+          s.tend = t1;
           continue;
         }
         st.a = gstart + r.exit;
@@ -462,10 +469,26 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
       s.st = st;
     }
     __syncthreads();
-    const uint32_t need = s.need_chase;  // stable: thread 0 writes these again only after the barrier that ends the iteration
+    const uint32_t req = s.req;  // stable: thread 0 writes these again only after the barrier that ends the iteration
+    const uint64_t ridx = s.req_idx;
     uint32_t done = s.done;
-    if (need) {
-      const uint64_t t = s.tile, tstart = t * (uint64_t)kTT;
+    if (req == 2 || req == 3) {  // refill a row cache
+      const uint64_t total = req == 2 ? ngroups : ntiles;
+      const uint32_t cnt = (uint32_t)((total - ridx) < cache_rows ? (total - ridx) : cache_rows);
+      const uint4* src = reinterpret_cast<const uint4*>((req == 2 ? wk.grows : wk.rows) + ridx * hc);
+      uint4* dst = reinterpret_cast<uint4*>(req == 2 ? gcache : tcache);
+      for (uint64_t i = threadIdx.x; i < (uint64_t)cnt * hc; i += kEncThreads) dst[i] = src[i];
+      if (threadIdx.x == 0) {
+        if (req == 2) {
+          s.ga = ridx;
+          s.gn = cnt;
+        } else {
+          s.ta = ridx;
+          s.tn = cnt;
+        }
+      }
+    } else if (req == 1) {
+      const uint64_t tstart = ridx * (uint64_t)kTT;
       const uint32_t tl = (uint32_t)(((tstart + kTT) < n ? (tstart + kTT) : n) - tstart);
       for (uint32_t j = threadIdx.x; j < tl; j += kEncThreads) {
         s.nxt[j] = wk.nxt[tstart + j];
@@ -491,13 +514,12 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
     wk.totals[1] = s.st.f;
     // groups / tiles never entered (the stream ended before them) start past the end
     TileState ts{n, s.st.blk, 0, s.st.f, 0};
-    for (uint64_t t = s_t; t < s_tend; t++) wk.tstate[t] = ts;
-    for (uint64_t gg = s_g; gg < ngroups; gg++) {
+    for (uint64_t t = s.t; t < s.tend; t++) wk.tstate[t] = ts;
+    for (uint64_t gg = s.g; gg < ngroups; gg++) {
       wk.gstate[gg] = ts;
       wk.gflag[gg] = 0;
     }
   }
-  (void)g;
 }
 
 // per group: entry state of each of its tiles (groups walked tile by tile by the stitch kernel already have them)
@@ -974,7 +996,13 @@ void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nti
   const uint64_t ngroups = (ntiles + kEncGroup - 1) / kEncGroup;
   unsigned ct = hc < 1024 ? ((hc + 31) & ~31u) : 1024;
   encode_compose_kernel<<<(unsigned)ngroups, ct, 0, st>>>(w, m.n, ntiles, hc);
-  encode_stitch_kernel<<<1, kEncThreads, 0, st>>>(m, ep, w, m.n, ntiles, hc, err);
+  static bool attr = false;
+  const size_t smem = ((sizeof(StitchSmem) + 15) & ~(size_t)15) + 2 * (size_t)kStitchCacheBytes;
+  if (!attr) {
+    cudaFuncSetAttribute(encode_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  encode_stitch_kernel<<<1, kEncThreads, smem, st>>>(m, ep, w, m.n, ntiles, hc, err);
   encode_tilestate_kernel<<<(unsigned)((ngroups + 63) / 64), 64, 0, st>>>(w, m.n, ntiles, hc, err);
   if (launches) *launches += 3;
 }

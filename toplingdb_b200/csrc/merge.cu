@@ -115,9 +115,12 @@ merge_partition_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint3
 }
 
 // ------------------------------------------------------------------------------------------------ tile merge
+// Keys stay where the coalesced load put them (structure of arrays in shared memory); the merge rounds permute a list
+// of 16-bit indices.  A comparison loads the high key word of both candidates and touches the other words only on a tie.
 struct TileSmem {
   uint64_t hi[kMT], lo[kMT], tr[kMT];
-  uint16_t m16[kMT];               // ulen << 11 | position in load order
+  uint16_t idx[kMT];               // merge order: idx[o] = load position of the o-th smallest key
+  uint8_t ulen[kMT];
   uint32_t seg[kMaxRuns + 1];      // segment starts in load order
   uint32_t lst[2][kMaxRuns + 2];   // list bounds per merge round (ping-pong)
   uint64_t sbeg[kMaxRuns];         // absolute index of each segment's first element
@@ -128,35 +131,47 @@ struct TileSmem {
   uint32_t tile_id, kept_total;
   Key pred;
   uint32_t has_pred;
+  Key cand[kMaxRuns];              // last element before the split, per run
+  uint32_t cand_ok[kMaxRuns];
 };
 
-__device__ __forceinline__ Key skey(const TileSmem& s, uint32_t i) {
+__device__ __forceinline__ Key skey(const TileSmem& s, uint32_t id) {
   Key k;
-  k.hi = s.hi[i];
-  k.lo = s.lo[i];
-  k.tr = s.tr[i];
-  k.ulen = s.m16[i] >> 11;
+  k.hi = s.hi[id];
+  k.lo = s.lo[id];
+  k.tr = s.tr[id];
+  k.ulen = s.ulen[id];
   return k;
+}
+// is key b (load position ib, high word hb) strictly before key a?
+__device__ __forceinline__ bool id_less(const TileSmem& s, uint32_t ib, uint64_t hb, uint32_t ia, uint64_t ha) {
+  if (hb != ha) return hb < ha;
+  const uint64_t lb = s.lo[ib], la = s.lo[ia];
+  if (lb != la) return lb < la;
+  const uint32_t ub = s.ulen[ib], ua = s.ulen[ia];
+  if (ub != ua) return ub < ua;
+  return s.tr[ib] > s.tr[ia];
 }
 
 struct PairState {
-  uint32_t ai, a1, bi, b1, pend;  // cursors into A=[.., a1) and B=[.., b1); pend = end of this pair's output range
-  bool single;                    // unpaired list: copy through
+  uint32_t ai, a1, bi, b1, pend;  // cursors into A=[.., a1) and B=[.., b1) of the index list; pend = end of the pair's output
 };
 // locate the pair containing output position o and run the merge-path search for its diagonal
 __device__ __noinline__ void init_pair(const TileSmem& s, const uint32_t* lst, uint32_t nlists, uint32_t o, PairState* ps) {
   uint32_t pi = 0;
-  while (2 * pi + 2 <= nlists && lst[2 * pi + 2 <= nlists ? 2 * pi + 2 : nlists] <= o) pi++;
-  // pair pi covers lists 2pi and 2pi+1 (if present)
+  for (;;) {  // pair pi merges lists 2pi and 2pi+1 into [lst[2pi], lst[2pi+2])
+    uint32_t e = 2 * pi + 2 <= nlists ? lst[2 * pi + 2] : lst[nlists];
+    if (o < e) break;
+    pi++;
+  }
   uint32_t a0 = lst[2 * pi];
   uint32_t a1 = lst[2 * pi + 1];
   bool single = 2 * pi + 1 >= nlists;
   uint32_t b1 = single ? a1 : lst[2 * pi + 2];
-  ps->single = single;
   ps->pend = b1;
   ps->a1 = a1;
   ps->b1 = b1;
-  if (single) {
+  if (single) {  // unpaired list: passes through
     ps->ai = o;
     ps->bi = b1;
     return;
@@ -165,8 +180,8 @@ __device__ __noinline__ void init_pair(const TileSmem& s, const uint32_t* lst, u
   uint32_t lo = diag > bn ? diag - bn : 0, hi = diag < an ? diag : an;
   while (lo < hi) {
     uint32_t mid = (lo + hi) >> 1;
-    Key ka = skey(s, a0 + mid), kb = skey(s, a1 + diag - 1 - mid);
-    if (!ikey_less(kb, ka)) lo = mid + 1;  // a <= b: a goes first (stable, lower run index wins ties)
+    const uint32_t ia = s.idx[a0 + mid], ib = s.idx[a1 + diag - 1 - mid];
+    if (!id_less(s, ib, s.hi[ib], ia, s.hi[ia])) lo = mid + 1;  // a <= b: a goes first (stable, lower run index wins ties)
     else hi = mid;
   }
   ps->ai = a0 + lo;
@@ -229,7 +244,7 @@ __device__ bool group_head(const KeyCols& in, const uint64_t* run_start, uint32_
   return found;
 }
 
-__global__ void __launch_bounds__(kMThreads)
+__global__ void __launch_bounds__(kMThreads, 3)
 merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                    const uint64_t* __restrict__ splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
                    MergeCounters* counters, uint32_t* __restrict__ err) {
@@ -293,50 +308,58 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       s.hi[i] = p.x;
       s.lo[i] = p.y;
       s.tr[i] = in.tr[src];
-      s.m16[i] = (uint16_t)((meta_ulen(in.meta[src]) << 11) | i);
+      s.ulen[i] = (uint8_t)meta_ulen(in.meta[src]);
+      s.idx[i] = (uint16_t)i;
     }
   }
   __syncthreads();
-  // ---- pairwise merge rounds, in place through registers
+  // ---- pairwise merge rounds over the index list, in place through registers
   uint32_t nlists = k;
   int cur = 0;
   while (nlists > 1) {
     const uint32_t* lst = s.lst[cur];
-    uint64_t rhi[kMV], rlo[kMV], rtr[kMV];
-    uint16_t rm[kMV];
+    uint16_t rid[kMV];
     const uint32_t o0 = t * kMV;
     PairState ps;
     ps.pend = 0;
-    ps.single = true;
     ps.ai = ps.a1 = ps.bi = ps.b1 = 0;
-    Key ka, kb;
+    uint32_t ia = 0, ib = 0;
+    uint64_t ha = 0, hb = 0;
     bool va = false, vb = false;
 #pragma unroll
     for (int x = 0; x < kMV; x++) {
       uint32_t o = o0 + x;
+      rid[x] = 0;
       if (o < cnt) {
         if (o >= ps.pend) {
           init_pair(s, lst, nlists, o, &ps);
           va = ps.ai < ps.a1;
           vb = ps.bi < ps.b1;
-          if (va) ka = skey(s, ps.ai);
-          if (vb) kb = skey(s, ps.bi);
+          if (va) {
+            ia = s.idx[ps.ai];
+            ha = s.hi[ia];
+          }
+          if (vb) {
+            ib = s.idx[ps.bi];
+            hb = s.hi[ib];
+          }
         }
-        bool take_a = !vb || (va && !ikey_less(kb, ka));
-        uint32_t src = take_a ? ps.ai : ps.bi;
-        const Key& kk = take_a ? ka : kb;
-        rhi[x] = kk.hi;
-        rlo[x] = kk.lo;
-        rtr[x] = kk.tr;
-        rm[x] = s.m16[src];
+        const bool take_a = !vb || (va && !id_less(s, ib, hb, ia, ha));
+        rid[x] = (uint16_t)(take_a ? ia : ib);
         if (take_a) {
           ps.ai++;
           va = ps.ai < ps.a1;
-          if (va) ka = skey(s, ps.ai);
+          if (va) {
+            ia = s.idx[ps.ai];
+            ha = s.hi[ia];
+          }
         } else {
           ps.bi++;
           vb = ps.bi < ps.b1;
-          if (vb) kb = skey(s, ps.bi);
+          if (vb) {
+            ib = s.idx[ps.bi];
+            hb = s.hi[ib];
+          }
         }
       }
     }
@@ -344,12 +367,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
 #pragma unroll
     for (int x = 0; x < kMV; x++) {
       uint32_t o = o0 + x;
-      if (o < cnt) {
-        s.hi[o] = rhi[x];
-        s.lo[o] = rlo[x];
-        s.tr[o] = rtr[x];
-        s.m16[o] = rm[x];
-      }
+      if (o < cnt) s.idx[o] = rid[x];
     }
     // next round's list bounds
     uint32_t nn = (nlists + 1) >> 1;
@@ -363,15 +381,19 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   uint32_t keep_mask = 0, nkeep = 0;
   unsigned long long c_hidden = 0, c_obsolete = 0, c_indel = 0, c_kbytes = 0, c_vbytes = 0, c_silent = 0;
   uint64_t otr[kMV];
+  uint16_t oid[kMV];
 #pragma unroll
   for (int x = 0; x < kMV; x++) {
     uint32_t o = t * kMV + x;
     otr[x] = 0;
+    oid[x] = 0;
     if (o >= cnt) continue;
-    Key c = skey(s, o);
+    const uint32_t id = s.idx[o];
+    oid[x] = (uint16_t)id;
+    Key c = skey(s, id);
     Key p;
     bool has_prev = true;
-    if (o > 0) p = skey(s, o - 1);
+    if (o > 0) p = skey(s, s.idx[o - 1]);
     else {
       p = s.pred;
       has_prev = s.has_pred != 0;
@@ -392,7 +414,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
         uint64_t head_tr = 0;
         bool have = false;
         while (q >= 0) {
-          Key h = skey(s, q);
+          Key h = skey(s, s.idx[q]);
           uint64_t d2;
           bool same_grp = h.hi == c.hi && h.lo == c.lo && h.ulen == c.ulen &&
                           stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, h.tr >> 8, &d2) == st_c;
@@ -416,7 +438,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       // :947-990 keep the tombstone only if an older stripe still holds a version of this user key
       bool resolved = false;
       for (uint32_t q = o + 1; q < cnt; q++) {
-        Key nx = skey(s, q);
+        Key nx = skey(s, s.idx[q]);
         if (!(nx.hi == c.hi && nx.lo == c.lo && nx.ulen == c.ulen)) {
           resolved = true;
           break;
@@ -442,7 +464,6 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       // PrepareOutput :1299-1339 seqno zeroing
       otr[x] = (mp.bottommost && seq <= mp.earliest_snapshot) ? (uint64_t)type : c.tr;
     }
-    // stash "counted" flag for the value-byte statistic in bit 15.. not available: recomputed below from silent
     if (silent) keep_mask |= 1u << (16 + x);
   }
   // ---- tile-local ranks
@@ -488,24 +509,12 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     }
     if (lane == 0) s.base_out = base_out;
   }
-  // ---- compact survivors inside shared memory (reads are complete: everything needed is in registers)
-  uint64_t khi[kMV], klo[kMV];
-  uint16_t km[kMV];
-#pragma unroll
-  for (int x = 0; x < kMV; x++) {
-    uint32_t o = t * kMV + x;
-    if (o < cnt) {
-      khi[x] = s.hi[o];
-      klo[x] = s.lo[o];
-      km[x] = s.m16[o];
-    }
-  }
   // value-byte statistic needs vlen of every counted entry: gather from the source columns by load position
 #pragma unroll
   for (int x = 0; x < kMV; x++) {
     uint32_t o = t * kMV + x;
     if (o < cnt && !((keep_mask >> (16 + x)) & 1)) {
-      uint32_t pos = km[x] & 2047u, lo = 0, hi = k;
+      uint32_t pos = oid[x], lo = 0, hi = k;
       while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
         if (s.seg[mid] <= pos) lo = mid;
@@ -514,21 +523,19 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       c_vbytes += meta_vlen(in.meta[s.sbeg[lo] + (pos - s.seg[lo])]);
     }
   }
-  __syncthreads();
+  __syncthreads();  // every read of idx[] / tr[] in merged order is done: compact in place
 #pragma unroll
   for (int x = 0; x < kMV; x++) {
     if ((keep_mask >> x) & 1) {
-      s.hi[rank] = khi[x];
-      s.lo[rank] = klo[x];
-      s.tr[rank] = otr[x];
-      s.m16[rank] = km[x];
+      s.idx[rank] = oid[x];
+      s.tr[oid[x]] = otr[x];  // each load position is owned by exactly one merged position
       rank++;
     }
   }
   __syncthreads();
   const uint64_t base_out = s.base_out;
   for (uint32_t i = t; i < kept_total; i += kMThreads) {
-    uint32_t pos = s.m16[i] & 2047u, lo = 0, hi = k;
+    uint32_t pos = s.idx[i], lo = 0, hi = k;
     while (hi - lo > 1) {
       uint32_t mid = (lo + hi) >> 1;
       if (s.seg[mid] <= pos) lo = mid;
@@ -536,8 +543,8 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     }
     uint64_t src = s.sbeg[lo] + (pos - s.seg[lo]);
     uint64_t dst = base_out + i;
-    out.pfx[dst] = make_ulonglong2(s.hi[i], s.lo[i]);
-    out.tr[dst] = s.tr[i];
+    out.pfx[dst] = make_ulonglong2(s.hi[pos], s.lo[pos]);
+    out.tr[dst] = s.tr[pos];
     out.vref[dst] = in.vref[src];
     out.meta[dst] = in.meta[src];
   }
