@@ -114,7 +114,7 @@ struct b200c_job {
   // device state
   DevBuf files_d, blk_off, blk_size, blk_cnt, blk_base, blk_nr, blk_r, rbase, scan_tmp, run_start, small;  // small: err, totals, counters...
   DevBuf dec[4], mrg[4], splits, tile_state, snaps_d;
-  DevBuf esz, eshared, nxt, disk, rows, tstate, grows, gstate, gflag, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
+  DevBuf esz, eshared, nxt, disk, rows, tstate, grows, gstate, gflag, idx_contrib, idx_contrib_off, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
   uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
   uint32_t nfiles_out = 0;
   std::vector<uint64_t> run_start_h;
@@ -320,6 +320,16 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, E
     }
     base_off[nfiles] = off;
     CU(j->out_buf.reserve(off + 256));
+    {  // scratch for the parallel part of the index-block checksum
+      std::vector<uint64_t> coff(nfiles + 1, 0);
+      for (uint32_t f = 0; f < nfiles; f++) coff[f + 1] = coff[f] + (frs[f].n_blocks * 48 + 64) / 1024 + 1;
+      CU(j->idx_contrib.reserve(64 * (coff[nfiles] + 1)));
+      CU(j->idx_contrib_off.reserve(8 * (nfiles + 1)));
+      CU(cudaMemcpyAsync(j->idx_contrib_off.p, coff.data(), 8 * (nfiles + 1), cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));  // coff is a temporary
+      W.idx_contrib = j->idx_contrib.as<uint64_t>();
+      W.idx_contrib_off = j->idx_contrib_off.as<uint64_t>();
+    }
     std::vector<uint8_t*> bases(nfiles);
     for (uint32_t f = 0; f < nfiles; f++) bases[f] = j->out_buf.as<uint8_t>() + base_off[f];
     CU(j->out_base_d.reserve(8 * nfiles));
@@ -838,7 +848,7 @@ void b200c_job_destroy(b200c_job* j) {
   cudaSetDevice(j->p.device);
   DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_cnt, &j->blk_base, &j->blk_nr, &j->blk_r, &j->rbase, &j->scan_tmp, &j->run_start, &j->small,
                    &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
-                   &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->blocks,
+                   &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};
   for (DevBuf* b : all) b->release();
   for (auto& in : j->inputs) in.staged.release();

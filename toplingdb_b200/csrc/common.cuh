@@ -57,6 +57,14 @@ __device__ __forceinline__ uint32_t ld_u32(const uint8_t* p) {
 __device__ __forceinline__ uint64_t ld_u64(const uint8_t* p) { return (uint64_t)ld_u32(p) | ((uint64_t)ld_u32(p + 4) << 32); }
 
 __device__ __forceinline__ uint64_t ld_u64_aligned(const uint8_t* p) { return *reinterpret_cast<const uint64_t*>(p); }
+// 8 bytes at ANY alignment from two naturally aligned 8-byte loads (global or shared).  May touch up to 7 bytes past p+8.
+__device__ __forceinline__ uint64_t ld_u64_funnel(const uint8_t* p) {
+  const uint32_t a = (uint32_t)((uintptr_t)p & 7);
+  const uint64_t* q = reinterpret_cast<const uint64_t*>((uintptr_t)p - a);
+  const uint64_t lo = q[0];
+  if (a == 0) return lo;
+  return (lo >> (8 * a)) | (q[1] << (64 - 8 * a));
+}
 // bytes [s, s+16) of the 32-byte concatenation A|B (s in 0..15, warp-uniform): re-aligns 16-byte vectors on the fly
 __device__ __forceinline__ uint4 shift16(uint4 A, uint4 B, uint32_t s) {
   const uint32_t bs = (s & 3) * 8;
@@ -226,37 +234,41 @@ __device__ inline uint64_t xxh3_64_short(const uint8_t* in, uint32_t len) {
 // lane returns the hash).  Long inputs: lane l owns accumulator lane (l & 7) of stripe group (l >> 3); the four
 // groups take stripes g, g+4, ... of each 1024-byte block, partial sums are folded with shuffles before the
 // scramble (additions commute inside a block; the scramble is the only sequential step).
+// accumulator contribution of `nstripes` (<= 16) 64-byte stripes starting at blk: every lane returns the total for its
+// accumulator lane a = lane & 7 (additions commute inside a 1024-byte block; raw data goes to lane a ^ 1)
 template <bool kAligned8>
-__device__ inline uint64_t xxh3_64_warp_t(const uint8_t* in, uint64_t len) {
+__device__ __forceinline__ uint64_t xxh3_block_contrib(const uint8_t* blk, uint64_t nstripes) {
+  const unsigned lane = threadIdx.x & 31;
+  const int a = lane & 7, g = lane >> 3;
+  uint64_t mul = 0, add = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint64_t s = g + 4 * i;
+    if (s < nstripes) {
+      const uint64_t dv = kAligned8 ? ld_u64_aligned(blk + 64 * s + 8 * a) : ld_u64_funnel(blk + 64 * s + 8 * a);
+      const uint64_t dk = dv ^ sec64(8 * (int)s + 8 * a);
+      mul += (dk & 0xffffffffull) * (dk >> 32);
+      add += dv;
+    }
+  }
+  uint64_t part = mul + __shfl_xor_sync(0xffffffffu, add, 1);
+  part += __shfl_xor_sync(0xffffffffu, part, 8);
+  part += __shfl_xor_sync(0xffffffffu, part, 16);
+  return part;
+}
+// pre != nullptr: contributions of the full 1024-byte blocks were computed elsewhere (pre[8 * n + a])
+template <bool kAligned8>
+__device__ inline uint64_t xxh3_64_warp_t(const uint8_t* in, uint64_t len, const uint64_t* pre = nullptr) {
   const unsigned lane = threadIdx.x & 31;
   if (len <= 240) return xxh3_64_short(in, (uint32_t)len);
-  const int a = lane & 7, g = lane >> 3;
+  const int a = lane & 7;
   const uint64_t init[8] = {kP32_3, kP64_1, kP64_2, kP64_3, kP64_4, kP32_2, kP64_5, kP32_1};
-  uint64_t acc = init[a];  // authoritative copy lives in lanes 0..7 (identical in the other groups after each fold)
+  uint64_t acc = init[a];  // identical in the four lane groups
   const uint64_t nb_blocks = (len - 1) / 1024;
-  // per-lane secret words for stripes s = g, g+4, g+8, g+12 (secret offset 8*s + 8*a)
-  uint64_t ksec[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) ksec[i] = sec64(8 * (g + 4 * i) + 8 * a);
   const uint64_t kscr = sec64(192 - 64 + 8 * a);
   for (uint64_t n = 0; n <= nb_blocks; n++) {
-    const uint8_t* blk = in + n * 1024;
-    uint64_t nstripes = n < nb_blocks ? 16 : ((len - 1) - 1024 * nb_blocks) / 64;
-    uint64_t mul = 0, add = 0;  // contribution to acc[a] (product) and acc[a^1] (raw data)
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      uint64_t s = g + 4 * i;
-      if (s < nstripes) {
-        uint64_t dv = kAligned8 ? ld_u64_aligned(blk + 64 * s + 8 * a) : ld_u64(blk + 64 * s + 8 * a), dk = dv ^ ksec[i];
-        mul += (dk & 0xffffffffull) * (dk >> 32);
-        add += dv;
-      }
-    }
-    uint64_t add_sw = __shfl_xor_sync(0xffffffffu, add, 1);  // raw data goes to the neighbouring accumulator lane
-    uint64_t part = mul + add_sw;
-    part += __shfl_xor_sync(0xffffffffu, part, 8);
-    part += __shfl_xor_sync(0xffffffffu, part, 16);
-    acc += part;
+    const uint64_t nstripes = n < nb_blocks ? 16 : ((len - 1) - 1024 * nb_blocks) / 64;
+    acc += (pre && n < nb_blocks) ? pre[8 * n + a] : xxh3_block_contrib<kAligned8>(in + n * 1024, nstripes);
     if (n < nb_blocks) {
       acc ^= acc >> 47;
       acc ^= kscr;
@@ -265,7 +277,7 @@ __device__ inline uint64_t xxh3_64_warp_t(const uint8_t* in, uint64_t len) {
   }
   // last stripe: input + len - 64 with secret offset 192 - 64 - 7
   {
-    uint64_t dv = ld_u64(in + len - 64 + 8 * a), dk = dv ^ sec64(192 - 64 - 7 + 8 * a);
+    uint64_t dv = ld_u64_funnel(in + len - 64 + 8 * a), dk = dv ^ sec64(192 - 64 - 7 + 8 * a);
     uint64_t mul = (dk & 0xffffffffull) * (dk >> 32);
     uint64_t add_sw = __shfl_xor_sync(0xffffffffu, dv, 1);
     acc += mul + add_sw;

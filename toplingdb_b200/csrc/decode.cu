@@ -122,146 +122,6 @@ __global__ void index_decode_kernel(const FileDesc* __restrict__ files, int nfil
 }
 
 // ---------------------------------------------------------------------------------------------- data blocks
-constexpr int kDecWarps = 8;
-constexpr int kDecSlice = 6144;  // bytes of shared memory per warp for one staged block (+trailer +align slack)
-
-// stage [src, src+total) into the warp's slice, RE-ALIGNED so that byte 0 of the block sits at slice[0]: the
-// global side uses aligned 16 B loads, the funnel shift happens in registers, and everything that reads the staged
-// block afterwards (checksum stripes, restart array) can use naturally aligned shared-memory loads.
-__device__ __forceinline__ const uint8_t* stage_block(const uint8_t* src, uint32_t total, uint8_t* slice) {
-  const unsigned lane = threadIdx.x & 31;
-  if (total + 32 > (uint32_t)kDecSlice) return src;  // too big: parse straight from global memory
-  uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15;
-  const uint32_t shift = (uint32_t)((uintptr_t)src - a0);
-  const uint32_t nvec = (total + 15) >> 4;
-  const uint4* g = (const uint4*)a0;
-  uint4* s = (uint4*)slice;
-  if (shift == 0) {
-    for (uint32_t i = lane; i < nvec; i += 32) s[i] = __ldg(g + i);
-  } else {
-    for (uint32_t i = lane; i < nvec; i += 32) s[i] = shift16(__ldg(g + i), __ldg(g + i + 1), shift);
-  }
-  __syncwarp();
-  return slice;
-}
-
-// number of entries in [p, end) (one restart interval); 0xffffffff on malformed data
-__device__ __forceinline__ uint32_t count_interval(const uint8_t* p, const uint8_t* end) {
-  uint32_t n = 0;
-  while (p < end) {
-    uint64_t shared, non_shared, vlen;
-    int c;
-    if (p + 3 <= end && (p[0] | p[1] | p[2]) < 128) {  // DecodeEntry fast path (block.cc:44-50)
-      non_shared = p[1];
-      vlen = p[2];
-      p += 3;
-    } else {
-      if (!(c = get_varint(p, end, &shared))) return 0xffffffffu;
-      p += c;
-      if (!(c = get_varint(p, end, &non_shared))) return 0xffffffffu;
-      p += c;
-      if (!(c = get_varint(p, end, &vlen))) return 0xffffffffu;
-      p += c;
-    }
-    if (non_shared + vlen > (uint64_t)(end - p)) return 0xffffffffu;
-    p += non_shared + vlen;
-    n++;
-  }
-  return n;
-}
-
-struct BlockView {
-  const uint8_t* p;      // staged (or global) payload
-  const uint8_t* gsrc;   // payload in the file image (global)
-  uint32_t size, nr;
-  const uint8_t* restarts;
-  bool ok;
-};
-
-__device__ __forceinline__ BlockView open_block(const FileDesc& fd, uint64_t off, uint32_t size, uint8_t* slice,
-                                                uint32_t verify, uint32_t* err) {
-  BlockView v;
-  v.ok = false;
-  v.gsrc = fd.base + off;
-  v.size = size;
-  v.p = stage_block(v.gsrc, size + 5, slice);
-  const unsigned lane = threadIdx.x & 31;
-  uint8_t ctype = v.p[size];
-  if (ctype != 0) {
-    if (lane == 0) atomicOr(err, kErrCompressed);
-    return v;
-  }
-  if (verify && fd.cksum != 0) {
-    uint32_t want = ld_u32(v.p + size + 1);
-    uint32_t got = block_checksum_warp(fd.cksum, v.p, size, ctype);
-    if (want != got) {
-      if (lane == 0) atomicOr(err, kErrChecksum);
-      return v;
-    }
-  }
-  uint32_t foot = ld_u32(v.p + size - 4);
-  v.nr = foot & 0x7fffffffu;
-  if ((foot >> 31) || v.nr == 0 || 4ull * v.nr + 4 > size) {  // hash-index blocks are not produced by the configs we accept
-    if (lane == 0) atomicOr(err, kErrCorruptBlock);
-    return v;
-  }
-  v.restarts = v.p + size - 4 - 4ull * v.nr;
-  v.ok = true;
-  return v;
-}
-
-__global__ void __launch_bounds__(kDecWarps * 32)
-block_count_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
-                   const uint32_t* __restrict__ blk_size, uint32_t nblk, uint32_t verify, uint32_t* __restrict__ blk_cnt,
-                   uint32_t* __restrict__ blk_nr, uint32_t* __restrict__ blk_r, uint32_t* __restrict__ err) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint8_t* slice = smem + (size_t)w * kDecSlice;
-  for (uint32_t b = blockIdx.x * kDecWarps + w; b < nblk; b += gridDim.x * kDecWarps) {
-    const int f = file_of_block(files, nfiles, b);
-    const FileDesc fd = files[f];
-    __syncwarp();
-    BlockView v = open_block(fd, blk_off[b], blk_size[b], slice, verify, err);
-    uint32_t cnt = 0, first = 0, irregular = 0;
-    if (v.ok) {
-      for (uint32_t j0 = 0; j0 < v.nr; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        uint32_t c = 0;
-        if (j < v.nr) {
-          uint32_t r0 = ld_u32(v.restarts + 4ull * j);
-          uint32_t r1 = j + 1 < v.nr ? ld_u32(v.restarts + 4ull * (j + 1)) : (uint32_t)(v.restarts - v.p);
-          c = (r0 <= r1 && v.p + r1 <= v.restarts) ? count_interval(v.p + r0, v.p + r1) : 0xffffffffu;
-          if (c == 0xffffffffu) {
-            atomicOr(err, kErrCorruptBlock);
-            c = 0;
-          }
-        }
-        if (j0 == 0) first = __shfl_sync(0xffffffffu, c, 0);
-        // every restart interval but the last must hold the same number of entries (what BlockBuilder writes): the
-        // decoder derives an interval's output position from its index
-        if (j + 1 < v.nr && c != first) irregular = 1;
-        if (j + 1 == v.nr && c > first) irregular = 1;
-        cnt += c;
-      }
-    }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-    if (__any_sync(0xffffffffu, irregular) && lane == 0) atomicOr(err, kErrIrregularRestarts);
-    if (lane == 0) {
-      blk_nr[b] = v.ok ? v.nr : 0;
-      blk_r[b] = first;
-    }
-    if (lane == 0) blk_cnt[b] = cnt;
-  }
-}
-
-// ---- thread-per-restart-interval decode -----------------------------------------------------------------------
-// A restart interval (16 entries by default) is the unit that can be prefix-decoded independently, so the decoder gives
-// every interval its own thread: ~N/16 threads in flight instead of one warp per 4 KB block with 5 busy lanes.
-// The thread streams through its ~1 KB of the file image with aligned 8-byte loads (L1 keeps the line for the next
-// entry); the current internal key lives in three registers (K0..K2 = its 24 bytes as little-endian words) and is
-// updated with mask / funnel-shift arithmetic instead of a byte buffer.
-
 struct Win {  // 40 bytes of the image starting at the 8-byte aligned address below p
   uint64_t w0, w1, w2, w3, w4;
 };
@@ -285,6 +145,116 @@ __device__ __forceinline__ uint64_t win64(const Win& w, uint32_t k) {
 __device__ __forceinline__ uint64_t low_bytes_mask(uint32_t nbytes) {  // nbytes in 0..8
   return nbytes >= 8 ? ~0ull : ((1ull << (8 * nbytes)) - 1);
 }
+
+
+// entries in one restart interval [p, end), parsed with aligned word loads; 0xffffffff on malformed data
+__device__ __forceinline__ uint32_t count_interval(const uint8_t* p, const uint8_t* end) {
+  uint32_t n = 0;
+  while (p < end) {
+    const uint64_t h = ld_u64_funnel(p);
+    uint32_t adv;
+    if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {  // DecodeEntry fast path (block.cc:44-50)
+      adv = 3 + (uint32_t)((h >> 8) & 0xff) + (uint32_t)((h >> 16) & 0xff);
+    } else {
+      uint64_t shared, non_shared, vlen;
+      const uint8_t* q = p;
+      int c;
+      if (!(c = get_varint(q, end, &shared))) return 0xffffffffu;
+      q += c;
+      if (!(c = get_varint(q, end, &non_shared))) return 0xffffffffu;
+      q += c;
+      if (!(c = get_varint(q, end, &vlen))) return 0xffffffffu;
+      q += c;
+      if (non_shared + vlen > (uint64_t)(end - q)) return 0xffffffffu;
+      adv = (uint32_t)(q - p) + (uint32_t)(non_shared + vlen);
+    }
+    if (adv > (uint64_t)(end - p)) return 0xffffffffu;
+    p += adv;
+    n++;
+  }
+  return n;
+}
+
+// One warp per group of 32 consecutive data blocks, no shared memory:
+//   phase A  the warp verifies each block's checksum straight from the image (aligned 8-byte loads + funnel shift,
+//            lanes own accumulator lanes / stripes)
+//   phase B  lane q counts block q: (restarts - 1) full intervals + the last one (the decode kernel re-checks every interval)
+constexpr int kCntWarps = 8;
+__global__ void __launch_bounds__(kCntWarps * 32)
+block_count_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
+                   const uint32_t* __restrict__ blk_size, uint32_t nblk, uint32_t verify, uint32_t* __restrict__ blk_cnt,
+                   uint32_t* __restrict__ blk_nr, uint32_t* __restrict__ blk_r, uint32_t* __restrict__ err) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t nwarps = (uint64_t)gridDim.x * kCntWarps;
+  for (uint64_t g = (uint64_t)blockIdx.x * kCntWarps + (threadIdx.x >> 5); g * 32 < nblk; g += nwarps) {
+    const uint32_t b0 = (uint32_t)(g * 32);
+    const uint32_t nb = nblk - b0 < 32 ? nblk - b0 : 32;
+    // phase A
+    uint32_t bad = 0;
+    for (uint32_t q = 0; q < nb; q++) {
+      const uint32_t b = b0 + q;
+      const FileDesc& fd = files[file_of_block(files, nfiles, b)];
+      const uint8_t* blk = fd.base + blk_off[b];
+      const uint32_t size = blk_size[b];
+      const uint8_t ctype = blk[size];
+      if (ctype != 0) {
+        if (lane == 0) atomicOr(err, kErrCompressed);
+        bad |= 1u << q;
+        continue;
+      }
+      if (verify && fd.cksum != 0) {
+        const uint32_t want = ld_u32(blk + size + 1);
+        const uint32_t got = block_checksum_warp(fd.cksum, blk, size, ctype);
+        if (want != got) {
+          if (lane == 0) atomicOr(err, kErrChecksum);
+          bad |= 1u << q;
+        }
+      }
+    }
+    // phase B
+    uint32_t cnt = 0, nr = 0, first = 0;
+    if (lane < nb && !((bad >> lane) & 1)) {
+      const uint32_t b = b0 + lane;
+      const FileDesc& fd = files[file_of_block(files, nfiles, b)];
+      const uint8_t* blk = fd.base + blk_off[b];
+      const uint32_t size = blk_size[b];
+      const uint32_t foot = ld_u32(blk + size - 4);
+      nr = foot & 0x7fffffffu;
+      if ((foot >> 31) || nr == 0 || 4ull * nr + 4 > size) {  // data-block hash index is not produced by accepted configs
+        atomicOr(err, kErrCorruptBlock);
+        nr = 0;
+      } else {
+        const uint8_t* restarts = blk + size - 4 - 4ull * nr;
+        const uint32_t rlast = ld_u32(restarts + 4ull * (nr - 1));
+        const uint32_t data_end = (uint32_t)(restarts - blk);
+        uint32_t last = rlast <= data_end ? count_interval(blk + rlast, restarts) : 0xffffffffu;
+        first = last;
+        if (nr > 1) {
+          const uint32_t r1 = ld_u32(restarts + 4);
+          first = (ld_u32(restarts) == 0 && r1 <= data_end) ? count_interval(blk, blk + r1) : 0xffffffffu;
+        }
+        if (last == 0xffffffffu || first == 0xffffffffu || last > first || ld_u32(restarts) != 0) {
+          atomicOr(err, last > first && last != 0xffffffffu && first != 0xffffffffu ? kErrIrregularRestarts : kErrCorruptBlock);
+          nr = 0;
+        } else {
+          cnt = (nr - 1) * first + last;
+        }
+      }
+    }
+    if (lane < nb) {
+      blk_cnt[b0 + lane] = cnt;
+      blk_nr[b0 + lane] = nr;
+      blk_r[b0 + lane] = first;
+    }
+  }
+}
+
+// ---- thread-per-restart-interval decode -----------------------------------------------------------------------
+// A restart interval (16 entries by default) is the unit that can be prefix-decoded independently, so the decoder gives
+// every interval its own thread: ~N/16 threads in flight instead of one warp per 4 KB block with 5 busy lanes.
+// The thread streams through its ~1 KB of the file image with aligned 8-byte loads (L1 keeps the line for the next
+// entry); the current internal key lives in three registers (K0..K2 = its 24 bytes as little-endian words) and is
+// updated with mask / funnel-shift arithmetic instead of a byte buffer.
 
 __global__ void __launch_bounds__(256)
 block_decode_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
@@ -319,6 +289,8 @@ block_decode_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64
     const uint8_t* end = blk + r1;
     uint64_t K0 = 0, K1 = 0, K2 = 0;
     uint32_t klen = 0;
+    const uint64_t e_begin = e;
+    const uint32_t want = j + 1 < nr ? blk_r[b] : 0xffffffffu;  // every interval but the last holds blk_r entries
     while (p < end) {
       const Win w = load_win(p);
       const uint32_t o = (uint32_t)((uintptr_t)p & 7);
@@ -437,6 +409,7 @@ block_decode_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64
       e++;
       p = val + vlen;
     }
+    if (want != 0xffffffffu ? (e - e_begin) != want : (e - e_begin) > blk_r[b]) atomicOr(err, kErrIrregularRestarts);
   }
 }
 
@@ -469,16 +442,12 @@ void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blo
   if (grid.x > 1024) grid.x = 1024;
   index_decode_kernel<<<grid, 256, 0, st>>>(files_dev, nfiles, blk_off, blk_size, err);
 }
-static unsigned dec_grid(uint32_t nblk, int sms) {
-  unsigned want = (nblk + kDecWarps - 1) / kDecWarps;
-  unsigned cap = (unsigned)sms * 4u;  // 4 CTAs of 8 warps per SM: 48 KB of staging each
-  return want < cap ? (want ? want : 1) : cap;
-}
 void launch_block_count(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
                         uint32_t nblk, uint32_t verify, uint32_t* blk_cnt, uint32_t* blk_nr, uint32_t* blk_r, uint32_t* err, int sms,
                         cudaStream_t st) {
-  block_count_kernel<<<dec_grid(nblk, sms), kDecWarps * 32, kDecWarps * kDecSlice, st>>>(files_dev, nfiles, blk_off, blk_size,
-                                                                                       nblk, verify, blk_cnt, blk_nr, blk_r, err);
+  unsigned want = (nblk + 32 * kCntWarps - 1) / (32 * kCntWarps), cap = (unsigned)sms * 8u;
+  block_count_kernel<<<want < cap ? (want ? want : 1) : cap, kCntWarps * 32, 0, st>>>(files_dev, nfiles, blk_off, blk_size, nblk, verify,
+                                                                                      blk_cnt, blk_nr, blk_r, err);
 }
 void launch_block_decode(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
                          const uint64_t* blk_base, const uint32_t* blk_r, const uint64_t* rbase, const uint64_t* total_intervals,

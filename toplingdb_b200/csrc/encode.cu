@@ -180,16 +180,21 @@ __device__ __forceinline__ uint32_t next_block(const Window& w, uint32_t a, cons
     if (blk_payload(w, a, mid, cp) > thr) hi = mid;
     else lo = mid + 1;
   }
+  if (lo >= wlen) return w.at_end ? wlen : 0xffffffffu;
+  uint64_t ec = blk_payload(w, a, lo, cp);  // CurrentSizeEstimate before adding entry b; updated incrementally
+  uint32_t m = lo - a;                     // entries already in the block
+  uint32_t mr = cp.rshift < 32 ? (m & (cp.R - 1)) : (m % cp.R);
   for (uint32_t b = lo; b < wlen; b++) {
-    uint64_t ec = blk_payload(w, a, b, cp);
     if (ec >= cp.BS) return b;
+    const uint64_t s1 = w.P[b + 1] - w.P[b];
+    const bool at_restart = mr == 0;  // entry b would open a new restart interval
+    const uint64_t d = at_restart ? (uint64_t)w.Q[b] - (b >= cp.R ? (uint64_t)w.Q[b - cp.R] : 0) : 0;
     if (cp.LIM) {  // BlockAlmostFull: EstimateSizeAfterKV (block_builder.cc:97-126) = ec + |k|+|v|+4+varints (+4 at a restart)
-      uint64_t d = (uint64_t)w.Q[b] - (b >= cp.R ? (uint64_t)w.Q[b - cp.R] : 0);
-      uint64_t s0 = (w.P[b + 1] - w.P[b]) + d;
-      uint32_t m = b - a;
-      bool at_restart = cp.rshift < 32 ? (m & (cp.R - 1)) == 0 : (m % cp.R) == 0;
-      if (ec + s0 + 3 + (at_restart ? 4 : 0) > cp.BS) return b;
+      const uint64_t dfull = at_restart ? d : (uint64_t)w.Q[b] - (b >= cp.R ? (uint64_t)w.Q[b - cp.R] : 0);
+      if (ec + s1 + dfull + 3 + (at_restart ? 4 : 0) > cp.BS) return b;
     }
+    ec += s1 + (at_restart ? d + 4 : 0);
+    mr = mr + 1 == cp.R ? 0 : mr + 1;
   }
   return w.at_end ? wlen : 0xffffffffu;
 }
@@ -334,7 +339,7 @@ __device__ bool chase_tile(const uint16_t* nxt, const uint32_t* disk, uint64_t t
   return true;
 }
 
-constexpr int kEncGroup = 64;  // tiles per group
+constexpr int kEncGroup = 16;  // tiles per group
 __global__ void encode_compose_kernel(EncodeWork wk, uint64_t n, uint64_t ntiles, uint32_t hc) {
   const uint64_t g = blockIdx.x, t0 = g * kEncGroup, t1 = (t0 + kEncGroup) < ntiles ? (t0 + kEncGroup) : ntiles;
   const uint64_t gstart = t0 * (uint64_t)kTT;
@@ -716,14 +721,13 @@ __device__ __forceinline__ void lane_copy_small(uint8_t* dst, const uint8_t* src
     }
   }
 }
-__global__ void __launch_bounds__(kEmitWarps * 32)
-encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, uint8_t* const* __restrict__ out_base,
-                   uint32_t slice_bytes, uint32_t* __restrict__ err) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint8_t* slice = smem + (size_t)w * slice_bytes;
+// one warp encodes one data block: entries 32 at a time into an image in shared memory (or straight into the file image
+// when the block does not fit `slice_bytes`), restart array, checksum, coalesced re-aligned store
+__device__ void emit_block_warp(const KeyCols& m, const EncodeParams& ep, const EncodeWork& wk, uint64_t b, uint8_t* const* out_base,
+                                uint8_t* slice, uint32_t slice_bytes) {
+  const unsigned lane = threadIdx.x & 31;
   const uint32_t R = ep.restart_interval;
-  for (uint64_t b = (uint64_t)blockIdx.x * kEmitWarps + w; b < nblocks; b += (uint64_t)gridDim.x * kEmitWarps) {
+  {
     const BlockRec br = wk.blocks[b];
     uint8_t* gdst = out_base[br.file_idx] + br.file_off;
     const uint32_t ne = br.n_entries, nrest = (ne + R - 1) / R;
@@ -834,6 +838,201 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
       const uint32_t done = head + (nvec << 4);
       if (done + lane < total) gdst[done + lane] = img[done + lane];
       __syncwarp();
+    }
+  }
+}
+
+// Batched emit: a CTA takes kEmitBatch consecutive data blocks.  Their entries are consecutive in the merged stream, so
+// every thread owns a few entries, loads their columns with coalesced accesses and their values with independent
+// aligned word loads (everything in flight at once: one memory latency per batch instead of one per 32 entries),
+// a CTA-wide scan turns entry sizes into byte offsets, threads write their entries into the block images in shared
+// memory, then one warp per block adds restart footer + checksum trailer and stores the image.
+constexpr int kEmitBatch = 8;
+constexpr int kEmitPerThread = 3;
+constexpr int kEmitMaxEntries = kEmitWarps * 32 * kEmitPerThread;  // 768
+struct EmitSmem {
+  uint64_t first_entry[kEmitBatch + 1];  // first entry of each block; [nb] = end
+  uint64_t cum0[kEmitBatch];             // scanned size at the first entry of each block
+  uint32_t body[kEmitBatch];             // bytes of all entries of the block
+  uint64_t ws[33];
+  uint64_t carry;
+  uint32_t nb, fits;
+};
+__global__ void __launch_bounds__(kEmitWarps * 32)
+encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, uint8_t* const* __restrict__ out_base,
+                   uint32_t slot_bytes, uint32_t* __restrict__ err) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  EmitSmem& s = *reinterpret_cast<EmitSmem*>(smem);
+  uint8_t* img0 = smem + ((sizeof(EmitSmem) + 15) & ~(size_t)15);
+  const unsigned t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint32_t R = ep.restart_interval;
+  const uint64_t nbatches = (nblocks + kEmitBatch - 1) / kEmitBatch;
+  for (uint64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
+    const uint64_t b0 = batch * kEmitBatch;
+    const uint32_t nb = (uint32_t)((nblocks - b0) < kEmitBatch ? (nblocks - b0) : kEmitBatch);
+    __syncthreads();  // previous batch fully stored
+    if (t < nb) {
+      const BlockRec br = wk.blocks[b0 + t];
+      s.first_entry[t] = br.first_entry;
+      if (t == nb - 1) s.first_entry[nb] = br.first_entry + br.n_entries;
+      s.body[t] = 0;
+    }
+    if (t == 0) s.carry = 0;
+    __syncthreads();
+    const uint64_t e0 = s.first_entry[0];
+    const uint32_t E = (uint32_t)(s.first_entry[nb] - e0);
+    // entries of consecutive blocks must be consecutive and few enough; otherwise warp-per-block fallback
+    bool fits = E <= (uint32_t)kEmitMaxEntries;
+    for (uint32_t q = 0; q + 1 < nb; q++) fits = fits && s.first_entry[q + 1] > s.first_entry[q];
+    uint32_t bi[kEmitPerThread], sz[kEmitPerThread], sh[kEmitPerThread], vs[kEmitPerThread], ul[kEmitPerThread];
+    uint64_t hi[kEmitPerThread], lo[kEmitPerThread], tr[kEmitPerThread], vr[kEmitPerThread], cum[kEmitPerThread];
+    if (fits) {
+#pragma unroll
+      for (int i = 0; i < kEmitPerThread; i++) {
+        const uint32_t x = t + i * (kEmitWarps * 32);
+        sz[i] = 0;
+        bi[i] = 0;
+        if (x < E) {
+          const uint64_t e = e0 + x;
+          uint32_t q = 0;
+          while (q + 1 < nb && s.first_entry[q + 1] <= e) q++;
+          bi[i] = q;
+          const uint32_t jj = (uint32_t)(e - s.first_entry[q]);
+          const uint32_t mt = m.meta[e];
+          ul[i] = meta_ulen(mt);
+          vs[i] = meta_vlen(mt);
+          sh[i] = (jj % R == 0) ? 0 : wk.eshared[e];
+          sz[i] = entry_size(sh[i], ul[i] + 8, vs[i]);
+          const ulonglong2 pp = m.pfx[e];
+          hi[i] = pp.x;
+          lo[i] = pp.y;
+          tr[i] = m.tr[e];
+          vr[i] = m.vref[e];
+        }
+      }
+      // scan of sizes in entry order (x = t + 256 i: one CTA scan per i)
+#pragma unroll
+      for (int i = 0; i < kEmitPerThread; i++) {
+        uint64_t tot;
+        const uint64_t ex = block_excl_scan64(sz[i], &tot, s.ws);
+        cum[i] = s.carry + ex;
+        __syncthreads();
+        if (t == 0) s.carry += tot;
+        __syncthreads();
+      }
+#pragma unroll
+      for (int i = 0; i < kEmitPerThread; i++) {
+        const uint32_t x = t + i * (kEmitWarps * 32);
+        if (x < E && e0 + x == s.first_entry[bi[i]]) s.cum0[bi[i]] = cum[i];
+        if (x < E) atomicAdd(&s.body[bi[i]], sz[i]);
+      }
+      __syncthreads();
+      for (uint32_t q = 0; q < nb; q++) {
+        const uint32_t nrest = ((uint32_t)(s.first_entry[q + 1] - s.first_entry[q]) + R - 1) / R;
+        fits = fits && (uint64_t)s.body[q] + 4ull * nrest + 4 + 5 + 32 <= slot_bytes;
+      }
+    }
+    if (!fits) {  // uniform decision: every thread evaluated the same shared values
+      __syncthreads();
+      if (w < nb) emit_block_warp(m, ep, wk, b0 + w, out_base, img0 + (size_t)w * slot_bytes, slot_bytes);
+      continue;
+    }
+    // write entries into the block images
+#pragma unroll
+    for (int i = 0; i < kEmitPerThread; i++) {
+      const uint32_t x = t + i * (kEmitWarps * 32);
+      if (x < E) {
+        const uint32_t q = bi[i];
+        uint8_t* img = img0 + (size_t)q * slot_bytes;
+        const uint32_t off = (uint32_t)(cum[i] - s.cum0[q]);
+        uint8_t* p = img + off;
+        const uint32_t ks = ul[i] + 8;
+        p += put_varint(p, sh[i]);
+        p += put_varint(p, ks - sh[i]);
+        p += put_varint(p, vs[i]);
+        for (uint32_t tt = sh[i]; tt < ks; tt++) *p++ = (uint8_t)ikey_byte(hi[i], lo[i], ul[i], tr[i], tt);
+        if (vs[i] <= 64) lane_copy_small(p, (const uint8_t*)(uintptr_t)vr[i], vs[i]);
+        const uint32_t jj = (uint32_t)(e0 + x - s.first_entry[q]);
+        if (jj % R == 0) {
+          uint8_t* rp = img + s.body[q] + 4ull * (jj / R);
+          rp[0] = (uint8_t)off;
+          rp[1] = (uint8_t)(off >> 8);
+          rp[2] = (uint8_t)(off >> 16);
+          rp[3] = (uint8_t)(off >> 24);
+        }
+      }
+    }
+    // values longer than 64 bytes: a warp copies each of its lanes' values with all lanes
+#pragma unroll
+    for (int i = 0; i < kEmitPerThread; i++) {
+      const uint32_t x = t + i * (kEmitWarps * 32);
+      unsigned big = __ballot_sync(0xffffffffu, x < E && vs[i] > 64);
+      while (big) {
+        const int sl = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t q = __shfl_sync(0xffffffffu, bi[i], sl);
+        const uint32_t vl = __shfl_sync(0xffffffffu, vs[i], sl);
+        const uint32_t voff = __shfl_sync(0xffffffffu, (uint32_t)(cum[i] - s.cum0[bi[i]]) + sz[i] - vs[i], sl);
+        const uint64_t vrr = __shfl_sync(0xffffffffu, vr[i], sl);
+        const uint8_t* sp = (const uint8_t*)(uintptr_t)vrr;
+        uint8_t* dp = img0 + (size_t)q * slot_bytes + voff;
+        // aligned 4-byte source words, funnel-shifted; byte stores into the image
+        const uint32_t a = (uint32_t)((uintptr_t)sp & 3);
+        const uint32_t* wsrc = reinterpret_cast<const uint32_t*>((uintptr_t)sp - a);
+        const uint32_t nwords = (vl + 3) >> 2;
+        for (uint32_t k = lane; k < nwords; k += 32) {
+          const uint32_t v = __funnelshift_r(__ldg(wsrc + k), __ldg(wsrc + k + 1), a * 8);
+          const uint32_t o = 4 * k;
+          dp[o] = (uint8_t)v;
+          if (o + 1 < vl) dp[o + 1] = (uint8_t)(v >> 8);
+          if (o + 2 < vl) dp[o + 2] = (uint8_t)(v >> 16);
+          if (o + 3 < vl) dp[o + 3] = (uint8_t)(v >> 24);
+        }
+      }
+    }
+    __syncthreads();
+    // per block: restart footer, checksum trailer, store
+    if (w < nb) {
+      const uint32_t q = w;
+      const BlockRec br = wk.blocks[b0 + q];
+      uint8_t* img = img0 + (size_t)q * slot_bytes;
+      uint8_t* gdst = out_base[br.file_idx] + br.file_off;
+      const uint32_t nrest = (br.n_entries + R - 1) / R;
+      const uint32_t body = s.body[q];
+      const uint32_t payload = body + 4 * nrest + 4;
+      if (lane == 0) {
+        uint8_t* fp = img + body + 4ull * nrest;
+        fp[0] = (uint8_t)nrest;
+        fp[1] = (uint8_t)(nrest >> 8);
+        fp[2] = (uint8_t)(nrest >> 16);
+        fp[3] = (uint8_t)(nrest >> 24);
+      }
+      __syncwarp();
+      const uint32_t ck = block_checksum_warp(ep.checksum, img, payload, 0);
+      if (lane == 0) {
+        uint8_t* tp = img + payload;
+        tp[0] = 0;
+        tp[1] = (uint8_t)ck;
+        tp[2] = (uint8_t)(ck >> 8);
+        tp[3] = (uint8_t)(ck >> 16);
+        tp[4] = (uint8_t)(ck >> 24);
+      }
+      __syncwarp();
+      const uint32_t total = payload + 5;
+      const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15);
+      uint32_t head = shift ? 16 - shift : 0;
+      if (head > total) head = total;
+      if (lane < head) gdst[lane] = img[lane];
+      const uint32_t nvec = (total - head) >> 4;
+      const uint4* sv = reinterpret_cast<const uint4*>(img);
+      uint4* gv = reinterpret_cast<uint4*>(gdst + head);
+      if (head == 0) {
+        for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
+      } else {
+        for (uint32_t i = lane; i < nvec; i += 32) gv[i] = shift16(sv[i], sv[i + 1], head);
+      }
+      const uint32_t done = head + (nvec << 4);
+      if (done + lane < total) gdst[done + lane] = img[done + lane];
     }
   }
   (void)err;
@@ -947,14 +1146,33 @@ __global__ void encode_index_write_kernel(EncodeWork wk, uint64_t nblocks, uint3
     }
   }
 }
+// XXH3 of a large index block: the per-1024-byte-block accumulator contributions are independent of the running state,
+// so one warp per block computes them in parallel; the per-file warp then only folds them (scramble chain).
+__global__ void encode_index_contrib_kernel(EncodeWork wk, uint32_t nfiles, uint8_t* const* __restrict__ out_base, uint64_t* __restrict__ contrib,
+                                            const uint64_t* __restrict__ contrib_off) {
+  const uint32_t f = blockIdx.y;
+  if (f >= nfiles) return;
+  const FileRec fr = wk.files[f];
+  if (fr.n_blocks == 0 || fr.index_size <= 240) return;
+  const uint8_t* ib = out_base[f] + fr.data_size;
+  const uint64_t nb_blocks = (fr.index_size - 1) / 1024;
+  const unsigned lane = threadIdx.x & 31;
+  for (uint64_t k = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nb_blocks; k += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+    const uint64_t part = xxh3_block_contrib<false>(ib + 1024 * k, 16);
+    if (lane < 8) contrib[(contrib_off[f] + k) * 8 + lane] = part;
+  }
+}
 // one warp per file: checksum of the index block, trailer written behind it
-__global__ void encode_index_cksum_kernel(EncodeWork wk, uint32_t nfiles, uint32_t cksum, uint8_t* const* __restrict__ out_base) {
+__global__ void encode_index_cksum_kernel(EncodeWork wk, uint32_t nfiles, uint32_t cksum, uint8_t* const* __restrict__ out_base,
+                                          const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ contrib_off) {
   const uint32_t f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (f >= nfiles) return;
   const FileRec fr = wk.files[f];
   if (fr.n_blocks == 0) return;
   uint8_t* ib = out_base[f] + fr.data_size;
-  uint32_t ck = block_checksum_warp(cksum, ib, fr.index_size, 0);
+  uint32_t ck;
+  if (cksum == 4) ck = (uint32_t)xxh3_64_warp_t<false>(ib, fr.index_size, contrib + contrib_off[f] * 8);  // last byte (type 0) adds nothing
+  else ck = block_checksum_warp(cksum, ib, fr.index_size, 0);
   if ((threadIdx.x & 31) == 0) {
     uint8_t* tp = ib + fr.index_size;
     tp[0] = 0;
@@ -1016,9 +1234,9 @@ void launch_encode_filestats(KeyCols m, EncodeWork w, uint32_t nfiles, int sms, 
   encode_filestats_kernel<<<sms * 4, 256, 0, st>>>(m, w, nfiles);
 }
 uint32_t encode_emit_slice(uint32_t block_size) {
-  uint32_t s = block_size + block_size / 2 + 1024;
-  s = (s + 1023) & ~1023u;
-  if (s < 8192) s = 8192;
+  uint32_t s = block_size + block_size / 4 + 512;
+  s = (s + 255) & ~255u;
+  if (s < 5632) s = 5632;
   if (s > 24 * 1024) s = 24 * 1024;
   return s;
 }
@@ -1030,14 +1248,14 @@ void launch_encode_emit(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nbloc
     cudaFuncSetAttribute(encode_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  uint32_t slice = encode_emit_slice(ep.block_size);
-  size_t smem = (size_t)slice * kEmitWarps;
-  unsigned per_sm = (unsigned)((220 * 1024) / smem);
+  const uint32_t slot = encode_emit_slice(ep.block_size);
+  const size_t smem = ((sizeof(EmitSmem) + 15) & ~(size_t)15) + (size_t)slot * kEmitBatch;
+  unsigned per_sm = (unsigned)((224 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
-  uint64_t want = (nblocks + kEmitWarps - 1) / kEmitWarps;
-  uint64_t cap = (uint64_t)sms * per_sm * 4;
-  encode_emit_kernel<<<(unsigned)(want < cap ? want : cap), kEmitWarps * 32, smem, st>>>(m, ep, w, nblocks, out_base, slice, err);
+  const uint64_t nbatches = (nblocks + kEmitBatch - 1) / kEmitBatch;
+  const uint64_t cap = (uint64_t)sms * per_sm * 2;
+  encode_emit_kernel<<<(unsigned)(nbatches < cap ? nbatches : cap), kEmitWarps * 32, smem, st>>>(m, ep, w, nblocks, out_base, slot, err);
 }
 void launch_encode_index(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nblocks, uint32_t nfiles, uint8_t* const* out_base,
                          uint32_t* err, cudaStream_t st, uint64_t* launches) {
@@ -1049,7 +1267,11 @@ void launch_encode_index(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nblo
   encode_index_size_kernel<<<g, 256, 0, st>>>(w, nblocks, ep.format_version);
   exclusive_scan<uint32_t>(w.idx_esz, w.idx_eoff, nblocks, w.scan_tmp, nullptr, st, launches);
   encode_index_write_kernel<<<g, 256, 0, st>>>(w, nblocks, ep.format_version, out_base);
-  encode_index_cksum_kernel<<<(nfiles + 3) / 4, 128, 0, st>>>(w, nfiles, ep.checksum, out_base);
+  if (ep.checksum == 4) {
+    encode_index_contrib_kernel<<<dim3(64, nfiles), 256, 0, st>>>(w, nfiles, out_base, w.idx_contrib, w.idx_contrib_off);
+    if (launches) *launches += 1;
+  }
+  encode_index_cksum_kernel<<<(nfiles + 3) / 4, 128, 0, st>>>(w, nfiles, ep.checksum, out_base, w.idx_contrib, w.idx_contrib_off);
   if (launches) *launches += 4;
 }
 void launch_block_checksums(uint32_t type, const uint8_t* data, const uint64_t* offsets, uint32_t n, uint8_t last_byte, uint32_t* out,

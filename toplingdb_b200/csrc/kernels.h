@@ -94,7 +94,7 @@ struct TileState {           // resolved state when the chain enters a tile
 };
 constexpr int kEncTile = 4096;       // entries per block-cut tile
 constexpr int kEncHalo = 2048;
-constexpr int kEncGroupTiles = 64;   // tiles per stitch group (encode.cu kEncGroup)       // look-ahead window = the longest block (in entries) the encoder accepts
+constexpr int kEncGroupTiles = 16;   // tiles per stitch group (encode.cu kEncGroup)       // look-ahead window = the longest block (in entries) the encoder accepts
 constexpr uint32_t kMaxOutFiles = 4096;
 
 struct EncodeWork {                  // device scratch owned by the job
@@ -113,6 +113,8 @@ struct EncodeWork {                  // device scratch owned by the job
   uint64_t* idx_eoff;   // per block: exclusive scan of idx_esz (global; file-relative after subtracting the file's first)
   KeyRec* idx_sep;      // per block: separator key (ulen excludes the trailer; pad=1 when the trailer was replaced)
   uint64_t* scan_tmp;
+  uint64_t* idx_contrib;      // XXH3 accumulator contributions of the 1024-byte blocks of every index block (8 u64 each)
+  uint64_t* idx_contrib_off;  // per file: first contribution slot
   uint16_t* nxt;        // n: tile-relative end of the block that would start at entry i
   uint32_t* disk;       // n: on-disk bytes of that block
 };
