@@ -175,76 +175,121 @@ __device__ __forceinline__ uint32_t count_interval(const uint8_t* p, const uint8
   return n;
 }
 
-// One warp per group of 32 consecutive data blocks, no shared memory:
-//   phase A  the warp verifies each block's checksum straight from the image (aligned 8-byte loads + funnel shift,
-//            lanes own accumulator lanes / stripes)
-//   phase B  lane q counts block q: (restarts - 1) full intervals + the last one (the decode kernel re-checks every interval)
+// One warp per data block, software-pipelined: while the warp checksums / counts block i out of shared memory, the 16-byte
+// vectors of block i+1 are already in flight into registers.  The staged copy keeps the file's 16-byte phase (no
+// re-alignment work); the checksum and the parser read it with aligned 8-byte loads + funnel shifts.
 constexpr int kCntWarps = 8;
+constexpr int kCntSlice = 4608;            // bytes staged per warp (block + trailer + phase); larger blocks are read in place
+constexpr int kCntVecs = kCntSlice / 16;   // 288
+constexpr int kCntPerLane = kCntVecs / 32;  // 9 vectors per lane
+
 __global__ void __launch_bounds__(kCntWarps * 32)
 block_count_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
                    const uint32_t* __restrict__ blk_size, uint32_t nblk, uint32_t verify, uint32_t* __restrict__ blk_cnt,
                    uint32_t* __restrict__ blk_nr, uint32_t* __restrict__ blk_r, uint32_t* __restrict__ err) {
-  const unsigned lane = threadIdx.x & 31;
-  const uint64_t nwarps = (uint64_t)gridDim.x * kCntWarps;
-  for (uint64_t g = (uint64_t)blockIdx.x * kCntWarps + (threadIdx.x >> 5); g * 32 < nblk; g += nwarps) {
-    const uint32_t b0 = (uint32_t)(g * 32);
-    const uint32_t nb = nblk - b0 < 32 ? nblk - b0 : 32;
-    // phase A
-    uint32_t bad = 0;
-    for (uint32_t q = 0; q < nb; q++) {
-      const uint32_t b = b0 + q;
-      const FileDesc& fd = files[file_of_block(files, nfiles, b)];
-      const uint8_t* blk = fd.base + blk_off[b];
-      const uint32_t size = blk_size[b];
-      const uint8_t ctype = blk[size];
-      if (ctype != 0) {
-        if (lane == 0) atomicOr(err, kErrCompressed);
-        bad |= 1u << q;
-        continue;
-      }
-      if (verify && fd.cksum != 0) {
-        const uint32_t want = ld_u32(blk + size + 1);
-        const uint32_t got = block_checksum_warp(fd.cksum, blk, size, ctype);
-        if (want != got) {
-          if (lane == 0) atomicOr(err, kErrChecksum);
-          bad |= 1u << q;
-        }
+  extern __shared__ __align__(16) uint8_t smem[];
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint4* slice = reinterpret_cast<uint4*>(smem + (size_t)w * kCntSlice);
+  const uint32_t stride = gridDim.x * kCntWarps;
+  uint32_t b = blockIdx.x * kCntWarps + w;
+  // prefetch state of the block about to be processed
+  uint4 pre[kCntPerLane];
+  const uint8_t* cur_src = nullptr;
+  uint32_t cur_size = 0, cur_shift = 0, cur_cksum = 0;
+  bool cur_staged = false;
+  auto prefetch = [&](uint32_t bb) {
+    const FileDesc& fd = files[file_of_block(files, nfiles, bb)];
+    cur_src = fd.base + blk_off[bb];
+    cur_size = blk_size[bb];
+    cur_cksum = fd.cksum;
+    const uintptr_t a0 = (uintptr_t)cur_src & ~(uintptr_t)15;
+    cur_shift = (uint32_t)((uintptr_t)cur_src - a0);
+    const uint32_t nvec = (cur_shift + cur_size + 5 + 15) >> 4;
+    cur_staged = nvec <= (uint32_t)kCntVecs - 1;
+    if (cur_staged) {
+      const uint4* g = reinterpret_cast<const uint4*>(a0);
+#pragma unroll
+      for (int i = 0; i < kCntPerLane; i++) {
+        const uint32_t v = lane + 32 * i;
+        if (v < nvec) pre[i] = __ldg(g + v);
       }
     }
-    // phase B
-    uint32_t cnt = 0, nr = 0, first = 0;
-    if (lane < nb && !((bad >> lane) & 1)) {
-      const uint32_t b = b0 + lane;
-      const FileDesc& fd = files[file_of_block(files, nfiles, b)];
-      const uint8_t* blk = fd.base + blk_off[b];
-      const uint32_t size = blk_size[b];
-      const uint32_t foot = ld_u32(blk + size - 4);
+  };
+  if (b < nblk) prefetch(b);
+  for (; b < nblk; b += stride) {
+    // commit the prefetched vectors of block b to shared memory
+    const uint8_t* src = cur_src;
+    const uint32_t size = cur_size, shift = cur_shift, cksum = cur_cksum;
+    const bool staged = cur_staged;
+    __syncwarp();
+    if (staged) {
+      const uint32_t nvec = (shift + size + 5 + 15) >> 4;
+#pragma unroll
+      for (int i = 0; i < kCntPerLane; i++) {
+        const uint32_t v = lane + 32 * i;
+        if (v < nvec) slice[v] = pre[i];
+      }
+    }
+    __syncwarp();
+    if (b + stride < nblk) prefetch(b + stride);  // next block's loads fly while this one is processed
+    const uint8_t* p = staged ? reinterpret_cast<const uint8_t*>(slice) + shift : src;
+    uint32_t cnt = 0, first = 0, nr = 0;
+    bool ok = true;
+    const uint8_t ctype = p[size];
+    if (ctype != 0) {
+      if (lane == 0) atomicOr(err, kErrCompressed);
+      ok = false;
+    }
+    if (ok && verify && cksum != 0) {
+      const uint32_t want = ld_u32(p + size + 1);
+      const uint32_t got = block_checksum_warp(cksum, p, size, ctype);
+      if (want != got) {
+        if (lane == 0) atomicOr(err, kErrChecksum);
+        ok = false;
+      }
+    }
+    if (ok) {
+      const uint32_t foot = ld_u32(p + size - 4);
       nr = foot & 0x7fffffffu;
-      if ((foot >> 31) || nr == 0 || 4ull * nr + 4 > size) {  // data-block hash index is not produced by accepted configs
-        atomicOr(err, kErrCorruptBlock);
+      if ((foot >> 31) || nr == 0 || 4ull * nr + 4 > size) {  // data-block hash index: not produced by accepted configs
+        if (lane == 0) atomicOr(err, kErrCorruptBlock);
+        ok = false;
         nr = 0;
-      } else {
-        const uint8_t* restarts = blk + size - 4 - 4ull * nr;
-        const uint32_t rlast = ld_u32(restarts + 4ull * (nr - 1));
-        const uint32_t data_end = (uint32_t)(restarts - blk);
-        uint32_t last = rlast <= data_end ? count_interval(blk + rlast, restarts) : 0xffffffffu;
-        first = last;
-        if (nr > 1) {
-          const uint32_t r1 = ld_u32(restarts + 4);
-          first = (ld_u32(restarts) == 0 && r1 <= data_end) ? count_interval(blk, blk + r1) : 0xffffffffu;
-        }
-        if (last == 0xffffffffu || first == 0xffffffffu || last > first || ld_u32(restarts) != 0) {
-          atomicOr(err, last > first && last != 0xffffffffu && first != 0xffffffffu ? kErrIrregularRestarts : kErrCorruptBlock);
-          nr = 0;
-        } else {
-          cnt = (nr - 1) * first + last;
-        }
       }
     }
-    if (lane < nb) {
-      blk_cnt[b0 + lane] = cnt;
-      blk_nr[b0 + lane] = nr;
-      blk_r[b0 + lane] = first;
+    if (ok) {
+      const uint8_t* restarts = p + size - 4 - 4ull * nr;
+      const uint32_t data_end = (uint32_t)(restarts - p);
+      uint32_t irregular = 0;
+      for (uint32_t j0 = 0; j0 < nr; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        uint32_t c = 0;
+        if (j < nr) {
+          const uint32_t r0 = ld_u32(restarts + 4ull * j);
+          const uint32_t r1 = j + 1 < nr ? ld_u32(restarts + 4ull * (j + 1)) : data_end;
+          c = (r0 <= r1 && r1 <= data_end && (j != 0 || r0 == 0)) ? count_interval(p + r0, p + r1) : 0xffffffffu;
+          if (c == 0xffffffffu) {
+            atomicOr(err, kErrCorruptBlock);
+            c = 0;
+          }
+        }
+        if (j0 == 0) first = __shfl_sync(0xffffffffu, c, 0);
+        // every restart interval but the last holds the same number of entries (what BlockBuilder writes): the decoder
+        // derives an interval's output position from its index
+        if (j + 1 < nr && c != first) irregular = 1;
+        if (j + 1 == nr && c > first) irregular = 1;
+        cnt += c;
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+      if (__any_sync(0xffffffffu, irregular)) {
+        if (lane == 0) atomicOr(err, kErrIrregularRestarts);
+      }
+    }
+    if (lane == 0) {
+      blk_cnt[b] = ok ? cnt : 0;
+      blk_nr[b] = ok ? nr : 0;
+      blk_r[b] = first;
     }
   }
 }
@@ -445,9 +490,9 @@ void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blo
 void launch_block_count(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
                         uint32_t nblk, uint32_t verify, uint32_t* blk_cnt, uint32_t* blk_nr, uint32_t* blk_r, uint32_t* err, int sms,
                         cudaStream_t st) {
-  unsigned want = (nblk + 32 * kCntWarps - 1) / (32 * kCntWarps), cap = (unsigned)sms * 8u;
-  block_count_kernel<<<want < cap ? (want ? want : 1) : cap, kCntWarps * 32, 0, st>>>(files_dev, nfiles, blk_off, blk_size, nblk, verify,
-                                                                                      blk_cnt, blk_nr, blk_r, err);
+  unsigned want = (nblk + kCntWarps - 1) / kCntWarps, cap = (unsigned)sms * 5u;
+  block_count_kernel<<<want < cap ? (want ? want : 1) : cap, kCntWarps * 32, kCntWarps * kCntSlice, st>>>(
+      files_dev, nfiles, blk_off, blk_size, nblk, verify, blk_cnt, blk_nr, blk_r, err);
 }
 void launch_block_decode(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
                          const uint64_t* blk_base, const uint32_t* blk_r, const uint64_t* rbase, const uint64_t* total_intervals,

@@ -858,7 +858,7 @@ struct EmitSmem {
   uint64_t carry;
   uint32_t nb, fits;
 };
-__global__ void __launch_bounds__(kEmitWarps * 32)
+__global__ void __launch_bounds__(kEmitWarps * 32, 2)
 encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, uint8_t* const* __restrict__ out_base,
                    uint32_t slot_bytes, uint32_t* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -887,9 +887,11 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
     uint32_t bi[kEmitPerThread], sz[kEmitPerThread], sh[kEmitPerThread], vs[kEmitPerThread], ul[kEmitPerThread];
     uint64_t hi[kEmitPerThread], lo[kEmitPerThread], tr[kEmitPerThread], vr[kEmitPerThread], cum[kEmitPerThread];
     if (fits) {
+      // thread t owns the consecutive entries [3t, 3t+3): one CTA-wide scan gives every entry its byte position
+      uint32_t tsum = 0;
 #pragma unroll
       for (int i = 0; i < kEmitPerThread; i++) {
-        const uint32_t x = t + i * (kEmitWarps * 32);
+        const uint32_t x = t * kEmitPerThread + i;
         sz[i] = 0;
         bi[i] = 0;
         if (x < E) {
@@ -908,24 +910,21 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
           lo[i] = pp.y;
           tr[i] = m.tr[e];
           vr[i] = m.vref[e];
+          tsum += sz[i];
         }
       }
-      // scan of sizes in entry order (x = t + 256 i: one CTA scan per i)
+      uint64_t tot;
+      uint64_t run = block_excl_scan64(tsum, &tot, s.ws);
 #pragma unroll
       for (int i = 0; i < kEmitPerThread; i++) {
-        uint64_t tot;
-        const uint64_t ex = block_excl_scan64(sz[i], &tot, s.ws);
-        cum[i] = s.carry + ex;
-        __syncthreads();
-        if (t == 0) s.carry += tot;
-        __syncthreads();
-      }
-#pragma unroll
-      for (int i = 0; i < kEmitPerThread; i++) {
-        const uint32_t x = t + i * (kEmitWarps * 32);
+        cum[i] = run;
+        run += sz[i];
+        const uint32_t x = t * kEmitPerThread + i;
         if (x < E && e0 + x == s.first_entry[bi[i]]) s.cum0[bi[i]] = cum[i];
-        if (x < E) atomicAdd(&s.body[bi[i]], sz[i]);
       }
+      if (t == 0) s.carry = tot;
+      __syncthreads();
+      if (t < nb) s.body[t] = (uint32_t)((t + 1 < nb ? s.cum0[t + 1] : s.carry) - s.cum0[t]);
       __syncthreads();
       for (uint32_t q = 0; q < nb; q++) {
         const uint32_t nrest = ((uint32_t)(s.first_entry[q + 1] - s.first_entry[q]) + R - 1) / R;
@@ -940,7 +939,7 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
     // write entries into the block images
 #pragma unroll
     for (int i = 0; i < kEmitPerThread; i++) {
-      const uint32_t x = t + i * (kEmitWarps * 32);
+      const uint32_t x = t * kEmitPerThread + i;
       if (x < E) {
         const uint32_t q = bi[i];
         uint8_t* img = img0 + (size_t)q * slot_bytes;
@@ -965,7 +964,7 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
     // values longer than 64 bytes: a warp copies each of its lanes' values with all lanes
 #pragma unroll
     for (int i = 0; i < kEmitPerThread; i++) {
-      const uint32_t x = t + i * (kEmitWarps * 32);
+      const uint32_t x = t * kEmitPerThread + i;
       unsigned big = __ballot_sync(0xffffffffu, x < E && vs[i] > 64);
       while (big) {
         const int sl = __ffs(big) - 1;
