@@ -148,6 +148,18 @@ static __device__ __constant__ uint8_t kXxhSecret[192] = {
     0xfa, 0x13, 0x63, 0xeb, 0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
     0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce, 0x45, 0xcb, 0x3a, 0x8f,
     0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e};
+// the same secret in global memory: lane-dependent offsets are served by the L1 instead of serialised constant-bank replays
+static __device__ const uint64_t kXxhSecretW[25] = {
+    0xbe4ba423396cfeb8ull, 0x1cad21f72c81017cull, 0xdb979083e96dd4deull, 0x1f67b3b7a4a44072ull, 0x78e5c0cc4ee679cbull,
+    0x2172ffcc7dd05a82ull, 0x8e2443f7744608b8ull, 0x4c263a81e69035e0ull, 0xcb00c391bb52283cull, 0xa32e531b8b65d088ull,
+    0x4ef90da297486471ull, 0xd8acdea946ef1938ull, 0x3f349ce33f76faa8ull, 0x1d4f0bc7c7bbdcf9ull, 0x3159b4cd4be0518aull,
+    0x647378d9c97e9fc8ull, 0xc3ebd33483acc5eaull, 0xeb6313faffa081c5ull, 0x49daf0b751dd0d17ull, 0x9e68d429265516d3ull,
+    0xfca1477d58be162bull, 0xce31d07ad1b8f88full, 0x280416958f3acb45ull, 0x7e404bbbcafbd7afull, 0ull};
+__device__ __forceinline__ uint64_t sec64g(int off) {  // unaligned 8 bytes of the secret, lane-divergent offsets welcome
+  const int wi = off >> 3, sh = (off & 7) * 8;
+  const uint64_t lo = kXxhSecretW[wi];
+  return sh ? (lo >> sh) | (kXxhSecretW[wi + 1] << (64 - sh)) : lo;
+}
 constexpr uint64_t kP32_1 = 0x9E3779B1ull, kP32_2 = 0x85EBCA77ull, kP32_3 = 0xC2B2AE3Dull;
 constexpr uint64_t kP64_1 = 0x9E3779B185EBCA87ull, kP64_2 = 0xC2B2AE3D27D4EB4Full, kP64_3 = 0x165667B19E3779F9ull,
                    kP64_4 = 0x85EBCA77C2B2AE63ull, kP64_5 = 0x27D4EB2F165667C5ull;
@@ -234,10 +246,22 @@ __device__ inline uint64_t xxh3_64_short(const uint8_t* in, uint32_t len) {
 // lane returns the hash).  Long inputs: lane l owns accumulator lane (l & 7) of stripe group (l >> 3); the four
 // groups take stripes g, g+4, ... of each 1024-byte block, partial sums are folded with shuffles before the
 // scramble (additions commute inside a block; the scramble is the only sequential step).
+// per-lane secret words of the four stripes a lane owns inside a 1024-byte block (stripe g + 4i, accumulator lane a)
+struct XxhLaneSecret {
+  uint64_t k[4];
+};
+__device__ __forceinline__ XxhLaneSecret xxh_lane_secret() {
+  const unsigned lane = threadIdx.x & 31;
+  const int a = lane & 7, g = lane >> 3;
+  XxhLaneSecret r;
+#pragma unroll
+  for (int i = 0; i < 4; i++) r.k[i] = sec64g(8 * (g + 4 * i) + 8 * a);
+  return r;
+}
 // accumulator contribution of `nstripes` (<= 16) 64-byte stripes starting at blk: every lane returns the total for its
 // accumulator lane a = lane & 7 (additions commute inside a 1024-byte block; raw data goes to lane a ^ 1)
 template <bool kAligned8>
-__device__ __forceinline__ uint64_t xxh3_block_contrib(const uint8_t* blk, uint64_t nstripes) {
+__device__ __forceinline__ uint64_t xxh3_block_contrib(const uint8_t* blk, uint64_t nstripes, const XxhLaneSecret& ks) {
   const unsigned lane = threadIdx.x & 31;
   const int a = lane & 7, g = lane >> 3;
   uint64_t mul = 0, add = 0;
@@ -246,7 +270,7 @@ __device__ __forceinline__ uint64_t xxh3_block_contrib(const uint8_t* blk, uint6
     const uint64_t s = g + 4 * i;
     if (s < nstripes) {
       const uint64_t dv = kAligned8 ? ld_u64_aligned(blk + 64 * s + 8 * a) : ld_u64_funnel(blk + 64 * s + 8 * a);
-      const uint64_t dk = dv ^ sec64(8 * (int)s + 8 * a);
+      const uint64_t dk = dv ^ ks.k[i];
       mul += (dk & 0xffffffffull) * (dk >> 32);
       add += dv;
     }
@@ -265,10 +289,11 @@ __device__ inline uint64_t xxh3_64_warp_t(const uint8_t* in, uint64_t len, const
   const uint64_t init[8] = {kP32_3, kP64_1, kP64_2, kP64_3, kP64_4, kP32_2, kP64_5, kP32_1};
   uint64_t acc = init[a];  // identical in the four lane groups
   const uint64_t nb_blocks = (len - 1) / 1024;
-  const uint64_t kscr = sec64(192 - 64 + 8 * a);
+  const uint64_t kscr = sec64g(192 - 64 + 8 * a);
+  const XxhLaneSecret ks = xxh_lane_secret();
   for (uint64_t n = 0; n <= nb_blocks; n++) {
     const uint64_t nstripes = n < nb_blocks ? 16 : ((len - 1) - 1024 * nb_blocks) / 64;
-    acc += (pre && n < nb_blocks) ? pre[8 * n + a] : xxh3_block_contrib<kAligned8>(in + n * 1024, nstripes);
+    acc += (pre && n < nb_blocks) ? pre[8 * n + a] : xxh3_block_contrib<kAligned8>(in + n * 1024, nstripes, ks);
     if (n < nb_blocks) {
       acc ^= acc >> 47;
       acc ^= kscr;
@@ -277,13 +302,13 @@ __device__ inline uint64_t xxh3_64_warp_t(const uint8_t* in, uint64_t len, const
   }
   // last stripe: input + len - 64 with secret offset 192 - 64 - 7
   {
-    uint64_t dv = ld_u64_funnel(in + len - 64 + 8 * a), dk = dv ^ sec64(192 - 64 - 7 + 8 * a);
+    uint64_t dv = ld_u64_funnel(in + len - 64 + 8 * a), dk = dv ^ sec64g(192 - 64 - 7 + 8 * a);
     uint64_t mul = (dk & 0xffffffffull) * (dk >> 32);
     uint64_t add_sw = __shfl_xor_sync(0xffffffffu, dv, 1);
     acc += mul + add_sw;
   }
   // merge: result = len*P64_1 + sum_i fold(acc[2i] ^ sec(11+16i), acc[2i+1] ^ sec(11+16i+8))
-  uint64_t keyed = acc ^ sec64(11 + 8 * a);
+  uint64_t keyed = acc ^ sec64g(11 + 8 * a);
   uint64_t other = __shfl_xor_sync(0xffffffffu, keyed, 1);
   uint64_t m = (a & 1) ? 0 : mul128_fold64(keyed, other);
   m += __shfl_xor_sync(0xffffffffu, m, 2);

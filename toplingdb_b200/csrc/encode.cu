@@ -1156,8 +1156,9 @@ __global__ void encode_index_contrib_kernel(EncodeWork wk, uint32_t nfiles, uint
   const uint8_t* ib = out_base[f] + fr.data_size;
   const uint64_t nb_blocks = (fr.index_size - 1) / 1024;
   const unsigned lane = threadIdx.x & 31;
+  const XxhLaneSecret ks = xxh_lane_secret();
   for (uint64_t k = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nb_blocks; k += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
-    const uint64_t part = xxh3_block_contrib<false>(ib + 1024 * k, 16);
+    const uint64_t part = xxh3_block_contrib<false>(ib + 1024 * k, 16, ks);
     if (lane < 8) contrib[(contrib_off[f] + k) * 8 + lane] = part;
   }
 }
