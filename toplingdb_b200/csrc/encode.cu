@@ -89,6 +89,7 @@ struct Window {
   uint64_t ws[33];
   uint32_t wlen;        // entries loaded
   uint32_t at_end;      // window reaches the end of the stream
+  uint32_t smax;        // largest restart-encoded entry (s0) in the window
 };
 
 // cooperative: load the window of tile `tile` and build P / Q
@@ -99,6 +100,8 @@ __device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, c
   constexpr int kPer = (kW + kEncThreads - 1) / kEncThreads;  // 24 consecutive entries per thread
   const uint32_t j0 = threadIdx.x * kPer;
   uint64_t loc[kPer], sum = 0;
+  uint32_t mx = 0;
+  if (threadIdx.x == 0) w.smax = 0;
 #pragma unroll
   for (int i = 0; i < kPer; i++) {
     uint32_t j = j0 + i;
@@ -107,12 +110,20 @@ __device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, c
       s1 = esz[wstart + j];
       uint32_t sh = eshared[wstart + j], ks = meta_ulen(m.meta[wstart + j]) + 8;
       // D = s0 - s1 with s0 = encoded size when shared == 0
-      w.Q[j] = 1u + (uint32_t)varint_len(ks) + sh - (uint32_t)varint_len(sh) - (uint32_t)varint_len(ks - sh);
+      const uint32_t d = 1u + (uint32_t)varint_len(ks) + sh - (uint32_t)varint_len(sh) - (uint32_t)varint_len(ks - sh);
+      w.Q[j] = d;
+      mx = s1 + d > mx ? s1 + d : mx;
     }
     loc[i] = s1;
     sum += s1;
   }
-  uint64_t ex = block_excl_scan64(sum, nullptr, w.ws);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    uint32_t o = __shfl_xor_sync(0xffffffffu, mx, d);
+    mx = o > mx ? o : mx;
+  }
+  uint64_t ex = block_excl_scan64(sum, nullptr, w.ws);  // (contains the barrier that orders the smax reset above)
+  if ((threadIdx.x & 31) == 0) atomicMax(&w.smax, mx);
 #pragma unroll
   for (int i = 0; i < kPer; i++) {
     uint32_t j = j0 + i;
@@ -168,7 +179,14 @@ __device__ __forceinline__ uint64_t blk_payload(const Window& w, uint32_t a, uin
 // hint: where the block of the previous start ended (0 = none); blocks of neighbouring starts end close to each other.
 __device__ __forceinline__ uint32_t next_block(const Window& w, uint32_t a, const CutParams& cp, uint32_t hint) {
   const uint32_t wlen = w.wlen;
-  const uint64_t thr = cp.LIM ? cp.LIM : cp.BS - 1;
+  // below `thr` neither flush condition can fire: condition 2 needs CurrentSizeEstimate > LIM and
+  // CurrentSizeEstimate + (size of the next entry, at most smax + 7) > BS
+  uint64_t thr = cp.BS - 1;
+  if (cp.LIM) {
+    thr = cp.LIM;
+    const uint64_t guard = (uint64_t)w.smax + 7;
+    if (cp.BS > guard && cp.BS - guard - 1 > thr) thr = cp.BS - guard - 1;
+  }
   uint32_t lo = a + 1, hi = wlen + 1;  // searching the first b in [lo, hi) with CurrentSizeEstimate(a, b) > thr; hi = none
   if (hint > a + 1 && hint <= wlen) {
     uint32_t l2 = hint > a + 4 ? hint - 3 : a + 1, h2 = hint + 5 < wlen ? hint + 5 : wlen;
@@ -215,12 +233,17 @@ encode_tables_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
   build_window(s.w, m, wk.esz, wk.eshared, n, tile, cp.R);
   const uint32_t tl = s.w.wlen < (uint32_t)kTT ? s.w.wlen : (uint32_t)kTT;
   {
-    // thread t takes starts t, t+256, ...: neighbouring lanes touch neighbouring prefix-sum words (no bank conflicts);
-    // the length of the block found for the previous start is the hint for the next one
-    uint32_t prev_len = 0;
-    for (uint32_t j = threadIdx.x; j < tl; j += kEncThreads) {
-      uint32_t b = next_block(s.w, j, cp, prev_len ? j + prev_len : 0);
-      prev_len = b == 0xffffffffu ? 0 : b - j;
+    // thread t owns the 16 consecutive starts [16t, 16t+16) so that the previous answer is a tight hint for the next
+    // start; it visits them in the rotated order (i + t) mod 16, which spreads the lanes of a warp over the
+    // shared-memory banks (plain blocked order would put all 32 lanes on the same bank pair)
+    constexpr int kPer = kTT / kEncThreads;
+    uint32_t prev_pos = 0xfffffff0u, prev_b = 0;
+    for (int i = 0; i < kPer; i++) {
+      const uint32_t j = threadIdx.x * kPer + ((i + threadIdx.x) & (kPer - 1));
+      if (j >= tl) continue;
+      uint32_t b = next_block(s.w, j, cp, prev_pos + 1 == j ? prev_b : 0);
+      prev_pos = j;
+      prev_b = b == 0xffffffffu ? 0 : b;
       uint16_t nx = 0xffff;
       uint32_t dk = 0;
       if (b != 0xffffffffu) {
@@ -847,11 +870,98 @@ __device__ void emit_block_warp(const KeyCols& m, const EncodeParams& ep, const 
 // aligned word loads (everything in flight at once: one memory latency per batch instead of one per 32 entries),
 // a CTA-wide scan turns entry sizes into byte offsets, threads write their entries into the block images in shared
 // memory, then one warp per block adds restart footer + checksum trailer and stores the image.
+// internal key bytes [sh, sh + n) (n <= 24) as three little-endian words, from the columnar (hi, lo, ulen, trailer) form
+__device__ __forceinline__ void key_suffix_words(uint64_t hi, uint64_t lo, uint32_t ulen, uint64_t tr, uint32_t sh, uint64_t* S0,
+                                                 uint64_t* S1, uint64_t* S2) {
+  const uint64_t U0 = bswap64(hi), U1 = bswap64(lo);  // user key bytes in memory order (zero padded beyond ulen)
+  uint64_t I0, I1, I2;
+  {
+    const uint32_t ws = ulen >> 3, bs = (ulen & 7) * 8;
+    const uint64_t T0 = tr << bs, T1 = bs ? tr >> (64 - bs) : 0;
+    if (ws == 0) {
+      I0 = U0 | T0;
+      I1 = T1;
+      I2 = 0;
+    } else if (ws == 1) {
+      I0 = U0;
+      I1 = U1 | T0;
+      I2 = T1;
+    } else {
+      I0 = U0;
+      I1 = U1;
+      I2 = tr;
+    }
+  }
+  const uint32_t ws = sh >> 3, bs = (sh & 7) * 8;
+  const uint64_t A = ws == 0 ? I0 : ws == 1 ? I1 : ws == 2 ? I2 : 0;
+  const uint64_t B = ws == 0 ? I1 : ws == 1 ? I2 : 0;
+  const uint64_t Cw = ws == 0 ? I2 : 0;
+  *S0 = bs ? (A >> bs) | (B << (64 - bs)) : A;
+  *S1 = bs ? (B >> bs) | (Cw << (64 - bs)) : B;
+  *S2 = Cw >> bs;
+}
+// n (<= 24) bytes of (S0, S1, S2) to an arbitrarily aligned (shared-memory) address
+__device__ __forceinline__ void store_bytes24(uint8_t* p, uint64_t S0, uint64_t S1, uint64_t S2, uint32_t n) {
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if ((uint32_t)k < n) p[k] = (uint8_t)(S0 >> (8 * k));
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if ((uint32_t)(8 + k) < n) p[8 + k] = (uint8_t)(S1 >> (8 * k));
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if ((uint32_t)(16 + k) < n) p[16 + k] = (uint8_t)(S2 >> (8 * k));
+}
+// n <= 64 value bytes: aligned word loads issued together, byte stores only for the unaligned head / tail of the
+// destination, 4-byte stores in between
+__device__ __forceinline__ void copy_value_small(uint8_t* dst, const uint8_t* src, uint32_t n) {
+  const uint32_t a = (uint32_t)((uintptr_t)src & 3);
+  const uint32_t* ws = reinterpret_cast<const uint32_t*>((uintptr_t)src - a);
+  const uint32_t nw = (a + n + 3) >> 2;  // <= 17
+  uint32_t w[18];
+#pragma unroll
+  for (int i = 0; i < 17; i++) w[i] = (uint32_t)i < nw ? __ldg(ws + i) : 0u;
+  w[17] = 0;
+  uint32_t head = (4 - (uint32_t)((uintptr_t)dst & 3)) & 3;
+  if (head > n) head = n;
+  {  // head bytes straight from the first words
+    const uint32_t v = __funnelshift_r(w[0], w[1], a * 8);
+    if (head > 0) dst[0] = (uint8_t)v;
+    if (head > 1) dst[1] = (uint8_t)(v >> 8);
+    if (head > 2) dst[2] = (uint8_t)(v >> 16);
+  }
+  const uint32_t t0 = a + head, bs = (t0 & 3) * 8;
+  const uint32_t nwords = (n - head) >> 2;
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + head);
+  uint32_t last;
+  if ((t0 >> 2) == 0) {
+#pragma unroll
+    for (int mI = 0; mI < 16; mI++)
+      if ((uint32_t)mI < nwords) d32[mI] = __funnelshift_r(w[mI], w[mI + 1], bs);
+    last = 0;
+  } else {
+#pragma unroll
+    for (int mI = 0; mI < 16; mI++)
+      if ((uint32_t)mI < nwords) d32[mI] = __funnelshift_r(w[mI + 1], w[mI + 2], bs);
+    last = 1;
+  }
+  const uint32_t done = head + 4 * nwords, rem = n - done;  // 0..3 tail bytes
+  if (rem) {
+    // tail word index = last + nwords (dynamic): fetch it again instead of indexing the register array dynamically
+    const uint32_t k = last + nwords;
+    const uint32_t lo = __ldg(ws + k), hi = (k + 1 < nw) ? __ldg(ws + k + 1) : 0u;
+    const uint32_t v = __funnelshift_r(lo, hi, bs);
+    dst[done] = (uint8_t)v;
+    if (rem > 1) dst[done + 1] = (uint8_t)(v >> 8);
+    if (rem > 2) dst[done + 2] = (uint8_t)(v >> 16);
+  }
+}
 constexpr int kEmitBatch = 8;
 constexpr int kEmitPerThread = 3;
 constexpr int kEmitMaxEntries = kEmitWarps * 32 * kEmitPerThread;  // 768
 struct EmitSmem {
   uint64_t first_entry[kEmitBatch + 1];  // first entry of each block; [nb] = end
+  uint32_t first_rel[kEmitBatch + 1];    // the same relative to the batch's first entry
   uint64_t cum0[kEmitBatch];             // scanned size at the first entry of each block
   uint32_t body[kEmitBatch];             // bytes of all entries of the block
   uint64_t ws[33];
@@ -880,30 +990,44 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
     if (t == 0) s.carry = 0;
     __syncthreads();
     const uint64_t e0 = s.first_entry[0];
-    const uint32_t E = (uint32_t)(s.first_entry[nb] - e0);
-    // entries of consecutive blocks must be consecutive and few enough; otherwise warp-per-block fallback
-    bool fits = E <= (uint32_t)kEmitMaxEntries;
-    for (uint32_t q = 0; q + 1 < nb; q++) fits = fits && s.first_entry[q + 1] > s.first_entry[q];
-    uint32_t bi[kEmitPerThread], sz[kEmitPerThread], sh[kEmitPerThread], vs[kEmitPerThread], ul[kEmitPerThread];
+    if (t == 0) {  // entries of consecutive blocks must be consecutive and few enough; otherwise warp-per-block fallback
+      bool f = s.first_entry[nb] - e0 <= (uint64_t)kEmitMaxEntries;
+      for (uint32_t q = 0; q < nb; q++) {
+        f = f && s.first_entry[q + 1] > s.first_entry[q];
+        s.first_rel[q] = (uint32_t)(s.first_entry[q] - e0);
+      }
+      s.first_rel[nb] = (uint32_t)(s.first_entry[nb] - e0);
+      s.fits = f;
+    }
+    __syncthreads();
+    bool fits = s.fits != 0;
+    const uint32_t E = s.first_rel[nb];
+    const uint32_t rmask = (R & (R - 1)) == 0 ? R - 1 : 0xffffffffu;  // power-of-two restart interval: mask instead of %
+    uint32_t bi[kEmitPerThread], sz[kEmitPerThread], sh[kEmitPerThread], vs[kEmitPerThread], ul[kEmitPerThread], jr[kEmitPerThread];
     uint64_t hi[kEmitPerThread], lo[kEmitPerThread], tr[kEmitPerThread], vr[kEmitPerThread], cum[kEmitPerThread];
     if (fits) {
       // thread t owns the consecutive entries [3t, 3t+3): one CTA-wide scan gives every entry its byte position
-      uint32_t tsum = 0;
+      uint32_t tsum = 0, q = 0;
+      {
+        const uint32_t x0 = t * kEmitPerThread;
+        while (q + 1 < nb && s.first_rel[q + 1] <= x0) q++;
+      }
 #pragma unroll
       for (int i = 0; i < kEmitPerThread; i++) {
         const uint32_t x = t * kEmitPerThread + i;
         sz[i] = 0;
         bi[i] = 0;
+        jr[i] = 1;
         if (x < E) {
           const uint64_t e = e0 + x;
-          uint32_t q = 0;
-          while (q + 1 < nb && s.first_entry[q + 1] <= e) q++;
+          while (q + 1 < nb && s.first_rel[q + 1] <= x) q++;
           bi[i] = q;
-          const uint32_t jj = (uint32_t)(e - s.first_entry[q]);
+          const uint32_t jj = x - s.first_rel[q];
+          jr[i] = rmask != 0xffffffffu ? (jj & rmask) : (jj % R);  // 0 = restart point
           const uint32_t mt = m.meta[e];
           ul[i] = meta_ulen(mt);
           vs[i] = meta_vlen(mt);
-          sh[i] = (jj % R == 0) ? 0 : wk.eshared[e];
+          sh[i] = jr[i] == 0 ? 0 : wk.eshared[e];
           sz[i] = entry_size(sh[i], ul[i] + 8, vs[i]);
           const ulonglong2 pp = m.pfx[e];
           hi[i] = pp.x;
@@ -920,18 +1044,24 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
         cum[i] = run;
         run += sz[i];
         const uint32_t x = t * kEmitPerThread + i;
-        if (x < E && e0 + x == s.first_entry[bi[i]]) s.cum0[bi[i]] = cum[i];
+        if (x < E && x == s.first_rel[bi[i]]) s.cum0[bi[i]] = cum[i];
       }
       if (t == 0) s.carry = tot;
       __syncthreads();
       if (t < nb) s.body[t] = (uint32_t)((t + 1 < nb ? s.cum0[t + 1] : s.carry) - s.cum0[t]);
       __syncthreads();
-      for (uint32_t q = 0; q < nb; q++) {
-        const uint32_t nrest = ((uint32_t)(s.first_entry[q + 1] - s.first_entry[q]) + R - 1) / R;
-        fits = fits && (uint64_t)s.body[q] + 4ull * nrest + 4 + 5 + 32 <= slot_bytes;
+      if (t == 0) {
+        bool f = true;
+        for (uint32_t qq = 0; qq < nb; qq++) {
+          const uint32_t nrest = (s.first_rel[qq + 1] - s.first_rel[qq] + R - 1) / R;
+          f = f && (uint64_t)s.body[qq] + 4ull * nrest + 4 + 5 + 32 <= slot_bytes;
+        }
+        s.fits = f;
       }
+      __syncthreads();
+      fits = s.fits != 0;
     }
-    if (!fits) {  // uniform decision: every thread evaluated the same shared values
+    if (!fits) {  // uniform decision
       __syncthreads();
       if (w < nb) emit_block_warp(m, ep, wk, b0 + w, out_base, img0 + (size_t)w * slot_bytes, slot_bytes);
       continue;
@@ -946,14 +1076,24 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
         const uint32_t off = (uint32_t)(cum[i] - s.cum0[q]);
         uint8_t* p = img + off;
         const uint32_t ks = ul[i] + 8;
-        p += put_varint(p, sh[i]);
-        p += put_varint(p, ks - sh[i]);
-        p += put_varint(p, vs[i]);
-        for (uint32_t tt = sh[i]; tt < ks; tt++) *p++ = (uint8_t)ikey_byte(hi[i], lo[i], ul[i], tr[i], tt);
-        if (vs[i] <= 64) lane_copy_small(p, (const uint8_t*)(uintptr_t)vr[i], vs[i]);
-        const uint32_t jj = (uint32_t)(e0 + x - s.first_entry[q]);
-        if (jj % R == 0) {
-          uint8_t* rp = img + s.body[q] + 4ull * (jj / R);
+        if ((sh[i] | (ks - sh[i]) | vs[i]) < 128) {
+          p[0] = (uint8_t)sh[i];
+          p[1] = (uint8_t)(ks - sh[i]);
+          p[2] = (uint8_t)vs[i];
+          p += 3;
+        } else {
+          p += put_varint(p, sh[i]);
+          p += put_varint(p, ks - sh[i]);
+          p += put_varint(p, vs[i]);
+        }
+        uint64_t S0, S1, S2;
+        key_suffix_words(hi[i], lo[i], ul[i], tr[i], sh[i], &S0, &S1, &S2);
+        store_bytes24(p, S0, S1, S2, ks - sh[i]);
+        p += ks - sh[i];
+        if (vs[i] <= 64) copy_value_small(p, (const uint8_t*)(uintptr_t)vr[i], vs[i]);
+        if (jr[i] == 0) {
+          const uint32_t jj = x - s.first_rel[q];
+          uint8_t* rp = img + s.body[q] + 4ull * (rmask != 0xffffffffu ? jj >> __popc(rmask) : jj / R);
           rp[0] = (uint8_t)off;
           rp[1] = (uint8_t)(off >> 8);
           rp[2] = (uint8_t)(off >> 16);
