@@ -109,6 +109,10 @@ __host__ __device__ __forceinline__ int varint_len(uint64_t v) {
   }
   return n;
 }
+// branch-free length of a varint32
+__host__ __device__ __forceinline__ uint32_t varint_len32(uint32_t v) {
+  return 1u + (v >= (1u << 7)) + (v >= (1u << 14)) + (v >= (1u << 21)) + (v >= (1u << 28));
+}
 __host__ __device__ __forceinline__ int put_varint(uint8_t* p, uint64_t v) {
   int n = 0;
   while (v >= 128) {

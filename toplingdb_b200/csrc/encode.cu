@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t shared_prefix(uint64_t ahi, uint64_t alo, ui
   return j;
 }
 __device__ __forceinline__ uint32_t entry_size(uint32_t shared, uint32_t ks, uint32_t vs) {
-  return (uint32_t)varint_len(shared) + (uint32_t)varint_len(ks - shared) + (uint32_t)varint_len(vs) + (ks - shared) + vs;
+  return varint_len32(shared) + varint_len32(ks - shared) + varint_len32(vs) + (ks - shared) + vs;
 }
 
 __global__ void encode_sizes_kernel(KeyCols m, const unsigned long long* __restrict__ n_dev, uint32_t* __restrict__ esz,
@@ -97,7 +97,9 @@ __device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, c
                              uint32_t R) {
   const uint64_t wstart = tile * (uint64_t)kTT;
   const uint32_t wlen = (uint32_t)((n - wstart) < (uint64_t)kW ? (n - wstart) : (uint64_t)kW);
-  constexpr int kPer = (kW + kEncThreads - 1) / kEncThreads;  // 24 consecutive entries per thread
+  // consecutive entries per thread; an ODD count keeps the blocked shared-memory accesses conflict-free (24 would put
+  // the lanes of a warp on only four banks)
+  constexpr int kPer = ((kW + kEncThreads - 1) / kEncThreads) | 1;  // 25
   const uint32_t j0 = threadIdx.x * kPer;
   uint64_t loc[kPer], sum = 0;
   uint32_t mx = 0;
@@ -110,7 +112,7 @@ __device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, c
       s1 = esz[wstart + j];
       uint32_t sh = eshared[wstart + j], ks = meta_ulen(m.meta[wstart + j]) + 8;
       // D = s0 - s1 with s0 = encoded size when shared == 0
-      const uint32_t d = 1u + (uint32_t)varint_len(ks) + sh - (uint32_t)varint_len(sh) - (uint32_t)varint_len(ks - sh);
+      const uint32_t d = 1u + varint_len32(ks) + sh - varint_len32(sh) - varint_len32(ks - sh);
       w.Q[j] = d;
       mx = s1 + d > mx ? s1 + d : mx;
     }
@@ -130,7 +132,6 @@ __device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, c
     if (j <= wlen && j <= (uint32_t)kW) w.P[j] = ex;
     ex += loc[i];
   }
-  if (threadIdx.x == kEncThreads - 1 && wlen == (uint32_t)kW) w.P[kW] = ex;
   if (threadIdx.x == 0) {
     w.wlen = wlen;
     w.at_end = (wstart + wlen == n);
@@ -320,7 +321,7 @@ __device__ __forceinline__ void close_file(FileRec* files, WalkState& st, uint64
 // on-disk bytes of a data block that holds the single entry y
 __device__ __forceinline__ uint64_t single_entry_block_bytes(const KeyCols& m, const EncodeWork& wk, uint64_t y) {
   uint32_t sh = wk.eshared[y], ks = meta_ulen(m.meta[y]) + 8;
-  uint64_t s0 = (uint64_t)wk.esz[y] + 1u + (uint32_t)varint_len(ks) + sh - (uint32_t)varint_len(sh) - (uint32_t)varint_len(ks - sh);
+  uint64_t s0 = (uint64_t)wk.esz[y] + 1u + varint_len32(ks) + sh - varint_len32(sh) - varint_len32(ks - sh);
   return s0 + 4 + 4 + 5;
 }
 // Follow the real chain through one tile whose nxt/disk sit in shared memory, applying the output-file cut rule
@@ -968,7 +969,7 @@ struct EmitSmem {
   uint64_t carry;
   uint32_t nb, fits;
 };
-__global__ void __launch_bounds__(kEmitWarps * 32, 2)
+__global__ void __launch_bounds__(kEmitWarps * 32, 3)
 encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, uint8_t* const* __restrict__ out_base,
                    uint32_t slot_bytes, uint32_t* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -1003,8 +1004,9 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
     bool fits = s.fits != 0;
     const uint32_t E = s.first_rel[nb];
     const uint32_t rmask = (R & (R - 1)) == 0 ? R - 1 : 0xffffffffu;  // power-of-two restart interval: mask instead of %
-    uint32_t bi[kEmitPerThread], sz[kEmitPerThread], sh[kEmitPerThread], vs[kEmitPerThread], ul[kEmitPerThread], jr[kEmitPerThread];
-    uint64_t hi[kEmitPerThread], lo[kEmitPerThread], tr[kEmitPerThread], vr[kEmitPerThread], cum[kEmitPerThread];
+    // pass 1 keeps only three words per entry alive across the scan; keys / value addresses are loaded in pass 2
+    uint32_t bi[kEmitPerThread], sz[kEmitPerThread], pk[kEmitPerThread], vs[kEmitPerThread];  // pk = shared | ulen << 8 | restart << 16
+    uint64_t cum[kEmitPerThread];
     if (fits) {
       // thread t owns the consecutive entries [3t, 3t+3): one CTA-wide scan gives every entry its byte position
       uint32_t tsum = 0, q = 0;
@@ -1017,23 +1019,20 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
         const uint32_t x = t * kEmitPerThread + i;
         sz[i] = 0;
         bi[i] = 0;
-        jr[i] = 1;
+        pk[i] = 0;
+        vs[i] = 0;
         if (x < E) {
           const uint64_t e = e0 + x;
           while (q + 1 < nb && s.first_rel[q + 1] <= x) q++;
           bi[i] = q;
           const uint32_t jj = x - s.first_rel[q];
-          jr[i] = rmask != 0xffffffffu ? (jj & rmask) : (jj % R);  // 0 = restart point
+          const bool restart = (rmask != 0xffffffffu ? (jj & rmask) : (jj % R)) == 0;
           const uint32_t mt = m.meta[e];
-          ul[i] = meta_ulen(mt);
+          const uint32_t ul = meta_ulen(mt);
           vs[i] = meta_vlen(mt);
-          sh[i] = jr[i] == 0 ? 0 : wk.eshared[e];
-          sz[i] = entry_size(sh[i], ul[i] + 8, vs[i]);
-          const ulonglong2 pp = m.pfx[e];
-          hi[i] = pp.x;
-          lo[i] = pp.y;
-          tr[i] = m.tr[e];
-          vr[i] = m.vref[e];
+          const uint32_t sh = restart ? 0 : wk.eshared[e];
+          pk[i] = sh | (ul << 8) | (restart ? 1u << 16 : 0);
+          sz[i] = entry_size(sh, ul + 8, vs[i]);
           tsum += sz[i];
         }
       }
@@ -1066,32 +1065,36 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
       if (w < nb) emit_block_warp(m, ep, wk, b0 + w, out_base, img0 + (size_t)w * slot_bytes, slot_bytes);
       continue;
     }
-    // write entries into the block images
+    // pass 2: write entries into the block images
 #pragma unroll
     for (int i = 0; i < kEmitPerThread; i++) {
       const uint32_t x = t * kEmitPerThread + i;
       if (x < E) {
-        const uint32_t q = bi[i];
+        const uint64_t e = e0 + x;
+        const uint32_t q = bi[i], sh = pk[i] & 0xff, ul = (pk[i] >> 8) & 0xff;
+        const ulonglong2 pp = m.pfx[e];
+        const uint64_t tr = m.tr[e];
+        const uint8_t* vsrc = (const uint8_t*)(uintptr_t)m.vref[e];
         uint8_t* img = img0 + (size_t)q * slot_bytes;
         const uint32_t off = (uint32_t)(cum[i] - s.cum0[q]);
         uint8_t* p = img + off;
-        const uint32_t ks = ul[i] + 8;
-        if ((sh[i] | (ks - sh[i]) | vs[i]) < 128) {
-          p[0] = (uint8_t)sh[i];
-          p[1] = (uint8_t)(ks - sh[i]);
+        const uint32_t ks = ul + 8;
+        if ((sh | (ks - sh) | vs[i]) < 128) {
+          p[0] = (uint8_t)sh;
+          p[1] = (uint8_t)(ks - sh);
           p[2] = (uint8_t)vs[i];
           p += 3;
         } else {
-          p += put_varint(p, sh[i]);
-          p += put_varint(p, ks - sh[i]);
+          p += put_varint(p, sh);
+          p += put_varint(p, ks - sh);
           p += put_varint(p, vs[i]);
         }
         uint64_t S0, S1, S2;
-        key_suffix_words(hi[i], lo[i], ul[i], tr[i], sh[i], &S0, &S1, &S2);
-        store_bytes24(p, S0, S1, S2, ks - sh[i]);
-        p += ks - sh[i];
-        if (vs[i] <= 64) copy_value_small(p, (const uint8_t*)(uintptr_t)vr[i], vs[i]);
-        if (jr[i] == 0) {
+        key_suffix_words(pp.x, pp.y, ul, tr, sh, &S0, &S1, &S2);
+        store_bytes24(p, S0, S1, S2, ks - sh);
+        p += ks - sh;
+        if (vs[i] <= 64) copy_value_small(p, vsrc, vs[i]);
+        if (pk[i] >> 16) {
           const uint32_t jj = x - s.first_rel[q];
           uint8_t* rp = img + s.body[q] + 4ull * (rmask != 0xffffffffu ? jj >> __popc(rmask) : jj / R);
           rp[0] = (uint8_t)off;
@@ -1112,7 +1115,7 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
         const uint32_t q = __shfl_sync(0xffffffffu, bi[i], sl);
         const uint32_t vl = __shfl_sync(0xffffffffu, vs[i], sl);
         const uint32_t voff = __shfl_sync(0xffffffffu, (uint32_t)(cum[i] - s.cum0[bi[i]]) + sz[i] - vs[i], sl);
-        const uint64_t vrr = __shfl_sync(0xffffffffu, vr[i], sl);
+        const uint64_t vrr = __shfl_sync(0xffffffffu, (x < E && vs[i] > 64) ? m.vref[e0 + x] : 0ull, sl);
         const uint8_t* sp = (const uint8_t*)(uintptr_t)vrr;
         uint8_t* dp = img0 + (size_t)q * slot_bytes + voff;
         // aligned 4-byte source words, funnel-shifted; byte stores into the image
