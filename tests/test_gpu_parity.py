@@ -6,6 +6,11 @@ import struct
 
 import pytest
 
+try:  # a fresh box can take minutes to page torch in: do it at collection time, outside any per-test timeout
+    import torch  # noqa: F401
+except Exception:  # pragma: no cover
+    torch = None
+
 import helpers as H
 import scenarios as S
 import sstfmt

@@ -647,7 +647,11 @@ int run_job(b200c_job* j, int until) {
   j->stats.num_records_replaced = mc.n_hidden;
   j->stats.num_expired_deletion_records = mc.n_obsolete;
   j->stats.total_input_raw_key_bytes = mc.raw_key_bytes;
-  j->stats.total_input_raw_value_bytes = mc.raw_value_bytes;
+  {  // every input value byte (rocksdb.raw.value.size of the inputs) minus the silently skipped entries
+    uint64_t all = 0;
+    for (auto& in : j->inputs) all += in.tail.raw_value_size;
+    j->stats.total_input_raw_value_bytes = all - mc.raw_value_bytes;
+  }
   if (until == 2) {
     j->stage_done = 2;
     j->stats.kernel_launches = launches;

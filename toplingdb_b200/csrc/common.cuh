@@ -85,6 +85,9 @@ __device__ __forceinline__ uint4 shift16(uint4 A, uint4 B, uint32_t s) {
   return r;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // varint32/64 decode; returns bytes consumed or 0 on malformed / overrun
 __device__ __forceinline__ int get_varint(const uint8_t* p, const uint8_t* end, uint64_t* v) {
   uint64_t r = 0;

@@ -247,7 +247,7 @@ __device__ bool group_head(const KeyCols& in, const uint64_t* run_start, uint32_
 __global__ void __launch_bounds__(kMThreads, 3)
 merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                    const uint64_t* __restrict__ splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
-                   MergeCounters* counters, uint32_t* __restrict__ err) {
+                   MergeCounters* counters, uint32_t* __restrict__ err, uint32_t prefetch_dist) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TileSmem& s = *reinterpret_cast<TileSmem*>(smem_raw);
   const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -292,6 +292,20 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   }
   __syncthreads();
   const uint32_t cnt = s.seg[k];
+  // ---- pull the segments of the tile one wave ahead into L2 (its CTA will find them there)
+  {
+    const uint64_t ahead = tile + prefetch_dist;
+    if (ahead < ntiles) {
+      const uint32_t part = t & 7;  // 8 threads per run
+      for (uint32_t r = t >> 3; r < k; r += kMThreads / 8) {
+        const uint64_t a0 = run_start[r] + splits[ahead * k + r], a1 = run_start[r] + splits[(ahead + 1) * k + r];
+        for (uint64_t e = a0 + part * 8; e < a1; e += 64) prefetch_l2(in.pfx + e);  // 8 entries per 128-byte line
+        for (uint64_t e = a0 + part * 16; e < a1; e += 128) prefetch_l2(in.tr + e);
+        for (uint64_t e = a0 + part * 16; e < a1; e += 128) prefetch_l2(in.vref + e);
+        for (uint64_t e = a0 + part * 32; e < a1; e += 256) prefetch_l2(in.meta + e);
+      }
+    }
+  }
   // ---- coalesced load of the k segments
 #pragma unroll
   for (int j = 0; j < kMV; j++) {
@@ -509,11 +523,12 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     }
     if (lane == 0) s.base_out = base_out;
   }
-  // value-byte statistic needs vlen of every counted entry: gather from the source columns by load position
+  // value-byte statistic: the inputs' raw.value.size property already sums every entry; only the (rare) silently
+  // skipped entries have to be subtracted, so only they pay a gather
 #pragma unroll
   for (int x = 0; x < kMV; x++) {
     uint32_t o = t * kMV + x;
-    if (o < cnt && !((keep_mask >> (16 + x)) & 1)) {
+    if (o < cnt && ((keep_mask >> (16 + x)) & 1)) {
       uint32_t pos = oid[x], lo = 0, hi = k;
       while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
@@ -577,7 +592,7 @@ void launch_merge_tiles(KeyCols in, const uint64_t* run_start, MergeParams mp, u
     attr_set = true;
   }
   merge_tiles_kernel<<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, run_start, mp, n_total, ntiles, splits, tile_state,
-                                                                          ticket, out, counters, err);
+                                                                          ticket, out, counters, err, 148u * 3u);
 }
 
 }  // namespace b200c
