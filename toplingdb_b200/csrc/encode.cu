@@ -502,7 +502,8 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
     const uint64_t ridx = s.req_idx;
     uint32_t done = s.done;
     if (req == 2 || req == 3) {  // refill a row cache
-      const uint64_t total = req == 2 ? ngroups : ntiles;
+      // group rows: as many as fit (the walk consumes them quickly); tile rows: only the rest of the group being walked
+      const uint64_t total = req == 2 ? ngroups : s.tend;
       const uint32_t cnt = (uint32_t)((total - ridx) < cache_rows ? (total - ridx) : cache_rows);
       const uint4* src = reinterpret_cast<const uint4*>((req == 2 ? wk.grows : wk.rows) + ridx * hc);
       uint4* dst = reinterpret_cast<uint4*>(req == 2 ? gcache : tcache);
