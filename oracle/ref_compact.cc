@@ -28,6 +28,10 @@
 #include "rocksdb/options.h"
 #include "rocksdb/table.h"
 #include "rocksdb/write_batch.h"
+#ifdef WITH_B200_PLUGIN
+#include "rocksdb/statistics.h"
+#include "toplingdb_b200/plugin/b200_compaction_executor.h"
+#endif
 
 using namespace ROCKSDB_NAMESPACE;
 
@@ -43,6 +47,7 @@ struct Opts {
   uint32_t format_version = 5;
   int keep_db = 0;
   int paranoid = 0;
+  std::string executor;  // "b200": route the job through the B200 CompactionExecutor plugin (ref_compact_b200 build only)
 };
 
 void Die(const char* what, const Status& s) {
@@ -122,6 +127,7 @@ int main(int argc, char** argv) {
     else if (k == "format_version") o.format_version = (uint32_t)atoi(v.c_str());
     else if (k == "keep_db") o.keep_db = atoi(v.c_str());
     else if (k == "paranoid") o.paranoid = atoi(v.c_str());
+    else if (k == "executor") o.executor = v;
     else {
       fprintf(stderr, "ref_compact: unknown option %s\n", k.c_str());
       return 1;
@@ -161,6 +167,22 @@ int main(int argc, char** argv) {
   opt.table_factory.reset(NewBlockBasedTableFactory(t));
   auto listener = std::make_shared<StatsListener>();
   opt.listeners.push_back(listener);
+  bool use_b200 = false;
+#ifdef WITH_B200_PLUGIN
+  if (o.executor == "b200" || o.executor == "b200+fallback") {
+    opt.statistics = CreateDBStatistics();
+    B200CompactOptions bo;
+    // "b200": a job the device path rejects fails the compaction (the tests want to see the device path, not a silent
+    // fallback); "b200+fallback": the reference re-runs such a job on its own CPU path (compaction_job.cc RunRemote -> RunLocal)
+    bo.allow_fallback_to_local = o.executor == "b200+fallback";
+    opt.compaction_executor_factory = NewB200CompactionExecutorFactory(bo);
+    use_b200 = true;
+  }
+#endif
+  if (!o.executor.empty() && !use_b200) {
+    fprintf(stderr, "ref_compact: executor=%s needs the ref_compact_b200 build\n", o.executor.c_str());
+    return 1;
+  }
 
   DestroyDB(dbdir, opt).PermitUncheckedError();
   DB* db = nullptr;
@@ -300,6 +322,33 @@ int main(int argc, char** argv) {
   fprintf(m, "  \"checksum\": \"%s\",\n  \"max_subcompactions\": %u,\n", o.checksum.c_str(),
           o.max_subcompactions);
   fprintf(m, "  \"bottommost_level\": %s,\n", deeper_files ? "false" : "true");
+  {
+    uint64_t remote_read = 0;
+#ifdef WITH_B200_PLUGIN
+    if (opt.statistics) remote_read = opt.statistics->getTickerCount(REMOTE_COMPACT_READ_BYTES);
+#endif
+    fprintf(m, "  \"executor\": \"%s\",\n  \"remote_compact_read_bytes\": %" PRIu64 ",\n", use_b200 ? "B200Compact" : "local", remote_read);
+  }
+  {
+    // Read the whole DB back through the reference's own table reader (block checksums verified): a digest of what a
+    // user sees after the job, identical whichever executor produced the files.
+    ReadOptions ro;
+    ro.verify_checksums = true;
+    ro.fill_cache = false;
+    std::unique_ptr<Iterator> it(db->NewIterator(ro));
+    uint64_t n = 0, h = 1469598103934665603ull;
+    auto mix = [&h](const Slice& x) {
+      for (size_t i = 0; i < x.size(); i++) h = (h ^ (unsigned char)x[i]) * 1099511628211ull;
+      h = (h ^ x.size()) * 1099511628211ull;
+    };
+    for (it->SeekToFirst(); it->Valid(); it->Next()) {
+      mix(it->key());
+      mix(it->value());
+      n++;
+    }
+    if (!it->status().ok()) Die("scan after compaction", it->status());
+    fprintf(m, "  \"scan_count\": %" PRIu64 ",\n  \"scan_digest\": \"%016" PRIx64 "\",\n", n, h);
+  }
   fprintf(m, "  \"db_id\": \"%s\",\n  \"db_session_id\": \"%s\",\n", db_id.c_str(), session_id.c_str());
   fprintf(m, "  \"snapshots\": [");
   for (size_t i = 0; i < snaps.size(); i++)

@@ -13,6 +13,7 @@ import sstfmt
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_compact")
+REF_B200_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_compact_b200")  # same driver + the product's CompactionExecutor plugin
 MAX_SEQ = (1 << 56) - 1
 CKSUM = {"none": 0, "crc32c": 1, "xxh3": 4}
 
@@ -247,15 +248,16 @@ def have_ref():
     return os.path.exists(REF_BIN)
 
 
-def run_reference(ops: Ops, workdir=None, **opts):
+def run_reference(ops: Ops, workdir=None, binary=None, **opts):
     """Run the compiled reference on an ops script.  Returns dict(manifest, inputs[bytes], outputs[bytes])."""
+    binary = binary or REF_BIN
     own = workdir is None
     if own:
         workdir = tempfile.mkdtemp(prefix="b200c_ref_")
     try:
         with open(os.path.join(workdir, "ops.bin"), "wb") as f:
             f.write(ops.bytes())
-        args = [REF_BIN, os.path.join(workdir, "ops.bin"), os.path.join(workdir, "w")] + [f"{k}={v}" for k, v in opts.items()]
+        args = [binary, os.path.join(workdir, "ops.bin"), os.path.join(workdir, "w")] + [f"{k}={v}" for k, v in opts.items()]
         subprocess.check_call(args, stdout=subprocess.DEVNULL)
         man = json.load(open(os.path.join(workdir, "w", "manifest.json")))
         ins = [open(os.path.join(workdir, "w", "inputs" + m["name"]), "rb").read() for m in man["inputs"]]

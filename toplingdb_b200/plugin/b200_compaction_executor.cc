@@ -1,0 +1,319 @@
+// toplingdb_b200/plugin/b200_compaction_executor.cc — see the header.  Host glue only: every byte of the data path goes
+// through libb200c.so (include/b200c.h).  Error behaviour mirrors RunRemote's contract (compaction_job.cc:921-1152):
+// Execute returns a Status, results->status carries the job status, no exception crosses the executor.
+#include "b200_compaction_executor.h"
+
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "b200c.h"
+#include "db/compaction/compaction.h"
+#include "db/version_edit.h"
+#include "file/filename.h"
+#include "rocksdb/comparator.h"
+#include "rocksdb/env.h"
+#include "rocksdb/table.h"
+
+namespace ROCKSDB_NAMESPACE {
+
+namespace {
+
+const BlockBasedTableOptions* BlockBasedOptionsOf(const Compaction* c) {
+  auto* tf = c->immutable_options()->table_factory.get();
+  if (tf == nullptr || strcmp(tf->Name(), TableFactory::kBlockBasedTableName()) != 0) return nullptr;
+  return tf->GetOptions<BlockBasedTableOptions>();
+}
+
+Status FromB200(int rc) {
+  const char* msg = b200c_last_error();
+  switch (rc) {
+    case B200C_OK: return Status::OK();
+    case B200C_ERR_NOT_SUPPORTED: return Status::NotSupported("b200c", msg);
+    case B200C_ERR_CORRUPTION: return Status::Corruption("b200c", msg);
+    case B200C_ERR_INVALID_ARGUMENT: return Status::InvalidArgument("b200c", msg);
+    case B200C_ERR_OUT_OF_MEMORY: return Status::MemoryLimit("b200c", msg);
+    default: return Status::Aborted("b200c", msg);
+  }
+}
+
+Status ReadWholeFile(const std::string& fname, std::string* out) {
+  FILE* f = fopen(fname.c_str(), "rb");
+  if (!f) return Status::IOError("open", fname);
+  struct stat st;
+  if (fstat(fileno(f), &st) != 0) {
+    fclose(f);
+    return Status::IOError("stat", fname);
+  }
+  out->resize((size_t)st.st_size);
+  size_t n = st.st_size ? fread(&(*out)[0], 1, (size_t)st.st_size, f) : 0;
+  fclose(f);
+  return n == (size_t)st.st_size ? Status::OK() : Status::IOError("short read", fname);
+}
+
+class B200CompactionExecutor : public CompactionExecutor {
+ public:
+  B200CompactionExecutor(const B200CompactOptions& o, const Compaction* c) : opt_(o), c_(c) {}
+
+  void SetParams(CompactionParams* p, const Compaction* c) override {
+    // the fields RunRemote leaves to the executor (compaction_job.cc:944-963 fills the rest)
+    auto* cfd = c->column_family_data();
+    p->num_levels = c->number_levels();
+    p->output_level = c->output_level();
+    p->cf_id = cfd->GetID();
+    p->cf_name = cfd->GetName();
+    p->inputs = c->inputs();
+    p->target_file_size = c->max_output_file_size();
+    p->max_compaction_bytes = c->max_compaction_bytes();
+    p->cf_paths = c->immutable_options()->cf_paths;
+    p->compression = c->output_compression();
+    p->compression_opts = c->output_compression_opts();
+    p->grandparents = &c->grandparents();
+    p->score = c->score();
+    p->manual_compaction = c->is_manual_compaction();
+    p->deletion_compaction = c->deletion_compaction();
+    p->compaction_reason = c->compaction_reason();
+    p->bottommost_level = c->bottommost_level();
+    p->smallest_user_key = c->GetSmallestUserKey().ToString();
+    p->largest_user_key = c->GetLargestUserKey().ToString();
+    p->level_compaction_dynamic_file_size = c->immutable_options()->level_compaction_dynamic_file_size;
+    p->compaction_style = c->immutable_options()->compaction_style;
+    p->compaction_pri = c->immutable_options()->compaction_pri;
+    p->is_deserialized = false;  // in-process: the struct borrows the DB's objects (compaction_executor.cc:12-38)
+  }
+
+  Status Execute(const CompactionParams& p, CompactionResults* r) override {
+    const auto t0 = std::chrono::steady_clock::now();
+    const BlockBasedTableOptions* bbt = BlockBasedOptionsOf(c_);
+    if (bbt == nullptr) return Fail(r, Status::NotSupported("B200Compact needs a BlockBasedTable output"));
+    if (!c_->grandparents().empty() && p.level_compaction_dynamic_file_size)
+      return Fail(r, Status::NotSupported("B200Compact: grandparent-aware file cutting is not on the device path"));
+    b200c_params bp;
+    b200c_params_init(&bp);
+    bp.device = opt_.device;
+    bp.output_level = p.output_level;
+    bp.bottommost_level = p.bottommost_level;
+    bp.max_output_file_size = c_->max_output_file_size();
+    bp.block_size = (uint32_t)bbt->block_size;
+    bp.block_size_deviation = (uint32_t)bbt->block_size_deviation;
+    bp.block_restart_interval = (uint32_t)bbt->block_restart_interval;
+    bp.index_block_restart_interval = (uint32_t)bbt->index_block_restart_interval;
+    bp.format_version = bbt->format_version;
+    bp.checksum = (uint32_t)bbt->checksum;
+    bp.verify_input_checksums = opt_.verify_input_checksums;
+    std::vector<uint64_t> snaps;
+    if (p.existing_snapshots) snaps.assign(p.existing_snapshots->begin(), p.existing_snapshots->end());
+    bp.snapshots = snaps.data();
+    bp.num_snapshots = (uint32_t)snaps.size();
+    bp.column_family_id = p.cf_id;
+    bp.column_family_name = p.cf_name.c_str();
+    bp.db_id = p.db_id.c_str();
+    bp.db_session_id = p.db_session_id.c_str();
+    std::string host = c_->immutable_options()->db_host_id;
+    if (host == kHostnameForDbHostId) {
+      host.clear();
+      c_->immutable_options()->env->GetHostNameString(&host).PermitUncheckedError();
+    }
+    bp.db_host_id = host.c_str();
+    int64_t now = 0;
+    c_->immutable_options()->clock->GetCurrentTime(&now).PermitUncheckedError();
+    uint64_t oldest = c_->MinInputFileOldestAncesterTime(nullptr, nullptr);
+    bp.creation_time = oldest == std::numeric_limits<uint64_t>::max() ? (uint64_t)now : oldest;  // compaction_job.cc:2258-2276
+    uint64_t fct = (uint64_t)now;
+    bp.file_creation_times = &fct;
+    bp.num_file_creation_times = 1;
+    bp.first_file_number = 1;  // numbers are local to output_dir; RunRemote renames every file (compaction_job.cc:1019-1033)
+    bp.output_mem = B200C_MEM_HOST;
+
+    b200c_job* job = nullptr;
+    Status s = FromB200(b200c_job_create(&bp, &job));
+    if (!s.ok()) return Fail(r, s);
+    // child order of VersionSet::MakeInputIterator (db/version_set.cc:7269-7352): L0 files as listed, then each level
+    std::vector<std::string> images;
+    uint64_t in_bytes = 0;
+    for (const auto& lvl : *p.inputs) images.reserve(images.size() + lvl.files.size());
+    for (const auto& lvl : *p.inputs) {
+      for (const FileMetaData* fm : lvl.files) {
+        if (fm->num_range_deletions) s = Status::NotSupported("B200Compact: range tombstones in input");
+        if (!s.ok()) break;
+        images.emplace_back();
+        s = ReadWholeFile(TableFileName(p.cf_paths, fm->fd.GetNumber(), fm->fd.GetPathId()), &images.back());
+        if (!s.ok()) break;
+        in_bytes += images.back().size();
+        s = FromB200(b200c_job_add_input(job, lvl.level, fm->fd.GetNumber(), images.back().data(), images.back().size(), B200C_MEM_HOST));
+        if (!s.ok()) break;
+      }
+      if (!s.ok()) break;
+    }
+    if (s.ok() && p.shutting_down && p.shutting_down->load(std::memory_order_acquire)) s = Status::ShutdownInProgress();
+    if (s.ok()) s = FromB200(b200c_job_run(job));
+    if (s.ok()) {
+      r->output_dir = opt_.scratch_dir.empty() ? p.dbname + "/b200c-tmp" : opt_.scratch_dir;
+      r->output_dir += "/job-" + std::to_string(p.job_id);
+      mkdir((opt_.scratch_dir.empty() ? p.dbname + "/b200c-tmp" : opt_.scratch_dir).c_str(), 0755);
+      mkdir(r->output_dir.c_str(), 0755);
+      r->output_files.resize(1);  // one sub-compaction: the device splits the job internally (merge-path tiles)
+      const int n = b200c_job_output_count(job);
+      for (int i = 0; i < n && s.ok(); i++) {
+        b200c_file_meta m;
+        const void* data;
+        uint64_t len;
+        s = FromB200(b200c_job_output_meta(job, i, &m));
+        if (s.ok()) s = FromB200(b200c_job_output_data(job, i, &data, &len));
+        if (!s.ok()) break;
+        const std::string fname = MakeTableFileName(r->output_dir, m.file_number);
+        FILE* f = fopen(fname.c_str(), "wb");
+        if (!f || fwrite(data, 1, len, f) != len) s = Status::IOError("write", fname);
+        if (f) fclose(f);
+        CompactionResults::FileMinMeta fm;
+        fm.file_number = m.file_number;
+        fm.file_size = m.file_size;
+        fm.smallest_seqno = m.smallest_seqno;
+        fm.largest_seqno = m.largest_seqno;
+        fm.smallest_ikey.DecodeFrom(Slice((const char*)m.smallest_ikey, m.smallest_ikey_len));
+        fm.largest_ikey.DecodeFrom(Slice((const char*)m.largest_ikey, m.largest_ikey_len));
+        fm.marked_for_compaction = false;
+        r->output_files[0].push_back(std::move(fm));
+      }
+    }
+    if (s.ok()) {
+      b200c_stats st;
+      b200c_job_get_stats(job, &st);
+      auto& js = r->job_stats;
+      js.Reset();
+      js.num_input_records = st.num_input_records;
+      js.num_output_records = st.num_output_records;
+      js.num_input_files = st.num_input_files;
+      js.num_output_files = st.num_output_files;
+      js.total_input_bytes = st.total_input_bytes;
+      js.total_output_bytes = st.total_output_bytes;
+      js.num_records_replaced = st.num_records_replaced;
+      js.num_expired_deletion_records = st.num_expired_deletion_records;
+      js.num_input_deletion_records = st.num_input_deletion_records;
+      js.total_input_raw_key_bytes = st.total_input_raw_key_bytes;
+      js.total_input_raw_value_bytes = st.total_input_raw_value_bytes;
+      js.is_manual_compaction = p.manual_compaction;
+      auto& cs = r->compaction_stats;
+      cs.num_input_records = st.num_input_records;
+      cs.num_output_records = st.num_output_records;
+      cs.bytes_written = st.total_output_bytes;
+      cs.num_output_files = (int)st.num_output_files;
+      cs.count = 1;
+      for (const auto& lvl : *p.inputs) {
+        uint64_t b = 0;
+        for (const FileMetaData* fm : lvl.files) b += fm->fd.GetFileSize();
+        if (lvl.level == p.output_level) {
+          cs.bytes_read_output_level += b;
+          cs.num_input_files_in_output_level += (int)lvl.files.size();
+        } else {
+          cs.bytes_read_non_output_levels += b;
+          cs.num_input_files_in_non_output_levels += (int)lvl.files.size();
+        }
+      }
+      cs.num_dropped_records = st.num_input_records - st.num_output_records;
+      r->statistics.tickers[COMPACT_READ_BYTES] = in_bytes;
+      r->statistics.tickers[COMPACT_WRITE_BYTES] = st.total_output_bytes;
+      r->statistics.tickers[LCOMPACT_WRITE_BYTES_RAW] = 0;
+      const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+      js.elapsed_micros = (uint64_t)us;
+      cs.micros = (uint64_t)us;
+      r->work_time_usec = (size_t)us;
+      r->curl_time_usec = r->mount_time_usec = r->prepare_time_usec = r->waiting_time_usec = 0;
+      r->status = Status::OK();
+    }
+    b200c_job_destroy(job);
+    return s.ok() ? s : Fail(r, s);
+  }
+
+  Status RenameFile(const std::string& src, const std::string& dst, off_t) override {
+    if (rename(src.c_str(), dst.c_str()) == 0) return Status::OK();
+    return CopyOneFile(src, dst, 0).ok() && unlink(src.c_str()) == 0 ? Status::OK() : Status::IOError("rename", src);
+  }
+  Status CopyOneFile(const std::string& src, const std::string& dst, off_t) override {
+    std::string data;
+    Status s = ReadWholeFile(src, &data);
+    if (!s.ok()) return s;
+    FILE* f = fopen(dst.c_str(), "wb");
+    if (!f || fwrite(data.data(), 1, data.size(), f) != data.size()) s = Status::IOError("write", dst);
+    if (f) fclose(f);
+    return s;
+  }
+  void CleanFiles(const CompactionParams&, const CompactionResults& r) override {
+    if (!r.output_dir.empty()) rmdir(r.output_dir.c_str());  // outputs were renamed away; the directory is empty
+  }
+
+ private:
+  static Status Fail(CompactionResults* r, const Status& s) {
+    r->status = s;
+    return s;
+  }
+  B200CompactOptions opt_;
+  const Compaction* c_;
+};
+
+}  // namespace
+
+B200CompactionExecutorFactory::B200CompactionExecutorFactory(const B200CompactOptions& o) : opt_(o) {
+  have_device_ = b200c_device_count() > opt_.device;
+}
+B200CompactionExecutorFactory::~B200CompactionExecutorFactory() = default;
+
+bool B200CompactionExecutorFactory::ShouldRunLocal(const Compaction* c) const {
+  if (!have_device_) return true;
+  const auto* io = c->immutable_options();
+  if (io->merge_operator != nullptr) return true;
+  if (io->compaction_filter != nullptr || io->compaction_filter_factory != nullptr) return true;
+  if (io->user_comparator != BytewiseComparator()) return true;
+  if (c->output_compression() != kNoCompression) return true;
+  if (io->sst_partitioner_factory != nullptr) return true;
+  if (BlockBasedOptionsOf(c) == nullptr) return true;
+  const BlockBasedTableOptions* t = BlockBasedOptionsOf(c);
+  if (t->filter_policy != nullptr || t->index_type != BlockBasedTableOptions::kBinarySearch ||
+      t->data_block_index_type != BlockBasedTableOptions::kDataBlockBinarySearch || t->index_block_restart_interval != 1 ||
+      t->block_align || t->format_version < 3 || t->format_version > 5 ||
+      (t->checksum != kXXH3 && t->checksum != kCRC32c && t->checksum != kNoChecksum))
+    return true;
+  size_t runs = 0;
+  for (const auto& lvl : *c->inputs()) {
+    runs += lvl.files.size();
+    for (const FileMetaData* fm : lvl.files)
+      if (fm->num_range_deletions) return true;
+  }
+  return runs == 0 || runs > 64;
+}
+bool B200CompactionExecutorFactory::AllowFallbackToLocal() const { return opt_.allow_fallback_to_local; }
+CompactionExecutor* B200CompactionExecutorFactory::NewExecutor(const Compaction* c) const {
+  return new B200CompactionExecutor(opt_, c);
+}
+const char* B200CompactionExecutorFactory::Name() const { return "B200Compact"; }
+std::string B200CompactionExecutorFactory::JobUrl(const std::string& dbname, int job_id, int attempt) const {
+  return "b200c://cuda:" + std::to_string(opt_.device) + "/" + dbname + "/job-" + std::to_string(job_id) + "/att-" +
+         std::to_string(attempt);
+}
+
+std::shared_ptr<CompactionExecutorFactory> NewB200CompactionExecutorFactory(const B200CompactOptions& o) {
+  return std::make_shared<B200CompactionExecutorFactory>(o);
+}
+
+#ifdef B200C_WITH_SIDEPLUGIN
+// rockside registration (sideplugin/rockside/src/topling/side_plugin_factory.h:290-293): selectable from JSON/YAML as
+//   "CompactionExecutorFactory": { "b200": { "class": "B200Compact", "params": { "device": 0 } } }
+}  // namespace ROCKSDB_NAMESPACE
+#include "topling/side_plugin_factory.h"
+namespace ROCKSDB_NAMESPACE {
+static std::shared_ptr<CompactionExecutorFactory> JS_NewB200Compact(const json& js, const SidePluginRepo&) {
+  B200CompactOptions o;
+  ROCKSDB_JSON_OPT_PROP(js, o.device);
+  ROCKSDB_JSON_OPT_PROP(js, o.allow_fallback_to_local);
+  ROCKSDB_JSON_OPT_PROP(js, o.verify_input_checksums);
+  ROCKSDB_JSON_OPT_PROP(js, o.scratch_dir);
+  return std::make_shared<B200CompactionExecutorFactory>(o);
+}
+ROCKSDB_FACTORY_REG("B200Compact", JS_NewB200Compact);
+#endif
+
+}  // namespace ROCKSDB_NAMESPACE
