@@ -113,7 +113,7 @@ def main():
     import torch
     import torch.distributed as dist
     import toplingdb_b200 as T
-    from toplingdb_b200 import synth
+    from toplingdb_b200 import sharding, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the compaction path has no CPU implementation)")
@@ -124,7 +124,7 @@ def main():
     entry = 24 + w["vlen"]
     n_run = int(w["run_bytes"] * args.scale) // entry
     n_total = n_run * w["k"]
-    key_base = rank * (n_total + 1024)  # disjoint, ordered key ranges per rank = independent sub-compactions
+    key_base = sharding.key_range_base(rank, n_total)  # disjoint, ordered key ranges per rank = independent sub-compactions
     images, kv_bytes = synth.stage_runs(n_total, w["k"], w["vlen"], key_base=key_base, seed=2 + rank, overlap=w["overlap"],
                                         del_frac=w["del_frac"], device_index=local)
     in_bytes = sum(int(t.numel()) for t in images)
@@ -141,16 +141,9 @@ def main():
             torch.cuda.synchronize()
 
     def boundary_exchange():
-        """all-gather of each rank's (smallest, largest) output internal keys (2 x 24 B): the level's files span devices"""
-        if world == 1:
-            return
-        first, last = job.output_meta(0), job.output_meta(job.output_count() - 1)
-        mine = torch.tensor(list(bytes(first.smallest_ikey[:24])) + list(bytes(last.largest_ikey[:24])), dtype=torch.uint8, device="cuda")
-        allk = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allk, mine)
-        ks = [bytes(t.cpu().tolist()) for t in allk]
-        for a, b in zip(ks, ks[1:]):
-            assert a[24:40] < b[0:16], "sub-compaction outputs overlap"
+        """the path's one collective: all-gather of each rank's 64-byte output boundary record + non-overlap check"""
+        if world > 1:
+            sharding.exchange_boundaries(sharding.job_boundary(job), device=torch.device("cuda", local))
 
     for _ in range(args.warmup):
         job.run()
