@@ -112,7 +112,7 @@ struct b200c_job {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // device state
-  DevBuf files_d, blk_off, blk_size, blk_cnt, blk_base, blk_nr, blk_r, rbase, scan_tmp, run_start, small;  // small: err, totals, counters...
+  DevBuf files_d, blk_off, blk_size, blk_state, scan_tmp, run_start, small;  // small: err, totals, counters...
   DevBuf dec[4], mrg[4], splits, tile_state, snaps_d;
   DevBuf esz, eshared, nxt, disk, rows, tstate, grows, gstate, gflag, idx_contrib, idx_contrib_off, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
   uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
@@ -144,7 +144,7 @@ struct b200c_job {
 namespace {
 
 // layout of the `small` buffer (u64 slots)
-enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotIntervals = 6, kSlotCounters = 8 /* 7 */, kSmallSlots = 32 };
+enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotDecTicket = 6, kSlotCounters = 8 /* 7 */, kSmallSlots = 32 };
 
 int map_dev_err(uint32_t e) {
   if (e == 0) return B200C_OK;
@@ -524,11 +524,7 @@ int run_job(b200c_job* j, int until) {
   const uint64_t N = n_props;
   CU(j->blk_off.reserve(8 * (nblk + 1)));
   CU(j->blk_size.reserve(4 * (nblk + 1)));
-  CU(j->blk_cnt.reserve(4 * (nblk + 1)));
-  CU(j->blk_base.reserve(8 * (nblk + 1)));
-  CU(j->blk_nr.reserve(4 * (nblk + 1)));
-  CU(j->blk_r.reserve(4 * (nblk + 1)));
-  CU(j->rbase.reserve(8 * (nblk + 1)));
+  CU(j->blk_state.reserve(8 * (nblk + 1)));
   CU(j->scan_tmp.reserve(8 * ((std::max<uint64_t>(nblk, N) / kScanTile) + 2)));
   CU(j->run_start.reserve(8 * (k + 1)));
   CU(j->dec[0].reserve(16 * (N + 1)));
@@ -544,25 +540,16 @@ int run_job(b200c_job* j, int until) {
     j->kt_begin("decode.index");
     launch_index_decode(files_d, k, maxb, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), err, st);
     j->kt_end();
-    j->kt_begin("decode.block_count");
-    launch_block_count(files_d, k, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), (uint32_t)nblk, P.verify_input_checksums,
-                       j->blk_cnt.as<uint32_t>(), j->blk_nr.as<uint32_t>(), j->blk_r.as<uint32_t>(), err, j->sms, st);
-    j->kt_end();
-    launches += 2;
-    j->kt_begin("decode.scan");
-    exclusive_scan<uint32_t>(j->blk_cnt.as<uint32_t>(), j->blk_base.as<uint64_t>(), nblk, j->scan_tmp.as<uint64_t>(),
-                             small + kSlotTotalIn, st, &launches);
-    exclusive_scan<uint32_t>(j->blk_nr.as<uint32_t>(), j->rbase.as<uint64_t>(), nblk, j->scan_tmp.as<uint64_t>(),
-                             small + kSlotIntervals, st, &launches);
-    j->kt_end();
+    launches++;
   }
-  launch_run_starts(files_d, k, j->blk_base.as<uint64_t>(), small + kSlotTotalIn, (uint32_t)nblk, j->run_start.as<uint64_t>(), st);
-  launches++;
   KeyColsMut dec{j->dec[0].as<ulonglong2>(), j->dec[1].as<uint64_t>(), j->dec[2].as<uint64_t>(), j->dec[3].as<uint32_t>()};
+  CU(cudaMemsetAsync(j->run_start.p, 0, 8 * (k + 1), st));  // stays zero when there is no data block at all
   if (nblk) {
-    j->kt_begin("decode.block_decode");
-    launch_block_decode(files_d, k, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), j->blk_base.as<uint64_t>(), j->blk_r.as<uint32_t>(),
-                        j->rbase.as<uint64_t>(), small + kSlotIntervals, (uint32_t)nblk, N, dec, err, j->sms, st);
+    CU(cudaMemsetAsync(j->blk_state.p, 0, 8 * (nblk + 1), st));
+    j->kt_begin("decode.blocks");
+    launch_block_decode_fused(files_d, k, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), (uint32_t)nblk, P.verify_input_checksums, N,
+                              dec, j->blk_state.as<unsigned long long>(), reinterpret_cast<uint32_t*>(small + kSlotDecTicket),
+                              j->run_start.as<uint64_t>(), small + kSlotTotalIn, err, j->sms, st);
     j->kt_end();
     launches++;
   }
@@ -850,7 +837,7 @@ int b200c_job_get_stats(const b200c_job* j, b200c_stats* s) {
 void b200c_job_destroy(b200c_job* j) {
   if (!j) return;
   cudaSetDevice(j->p.device);
-  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_cnt, &j->blk_base, &j->blk_nr, &j->blk_r, &j->rbase, &j->scan_tmp, &j->run_start, &j->small,
+  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->small,
                    &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
                    &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};

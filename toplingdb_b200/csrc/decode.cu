@@ -15,6 +15,8 @@
 //                         block checksum (warp-cooperative XXH3 / CRC32C), count entries per restart interval
 //   block_decode_kernel   one THREAD per restart interval (the independent prefix-decode unit): aligned 8-byte loads
 //                         straight from the image, key rebuilt in registers, emits (hi, lo, trailer, vref, meta)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -122,17 +124,17 @@ __global__ void index_decode_kernel(const FileDesc* __restrict__ files, int nfil
 }
 
 // ---------------------------------------------------------------------------------------------- data blocks
-struct Win {  // 40 bytes of the image starting at the 8-byte aligned address below p
+struct Win {  // 40 bytes starting at the 8-byte aligned address below p (generic loads: shared-memory staging or image)
   uint64_t w0, w1, w2, w3, w4;
 };
-__device__ __forceinline__ Win load_win(const uint8_t* p) {
+__device__ __forceinline__ Win load_win_any(const uint8_t* p) {
   const uint64_t* a = reinterpret_cast<const uint64_t*>((uintptr_t)p & ~(uintptr_t)7);
   Win w;
-  w.w0 = __ldg(a);
-  w.w1 = __ldg(a + 1);
-  w.w2 = __ldg(a + 2);
-  w.w3 = __ldg(a + 3);
-  w.w4 = __ldg(a + 4);
+  w.w0 = a[0];
+  w.w1 = a[1];
+  w.w2 = a[2];
+  w.w3 = a[3];
+  w.w4 = a[4];
   return w;
 }
 // 8 bytes of the window starting at byte k (0 <= k <= 32)
@@ -175,302 +177,448 @@ __device__ __forceinline__ uint32_t count_interval(const uint8_t* p, const uint8
   return n;
 }
 
-// One warp per data block, software-pipelined: while the warp checksums / counts block i out of shared memory, the 16-byte
-// vectors of block i+1 are already in flight into registers.  The staged copy keeps the file's 16-byte phase (no
-// re-alignment work); the checksum and the parser read it with aligned 8-byte loads + funnel shifts.
-constexpr int kCntWarps = 8;
-constexpr int kCntSlice = 4608;            // bytes staged per warp (block + trailer + phase); larger blocks are read in place
-constexpr int kCntVecs = kCntSlice / 16;   // 288
-constexpr int kCntPerLane = kCntVecs / 32;  // 9 vectors per lane
+// ---- fused checksum + count + decode: one warp per data block ----------------------------------------------------
+// The file image is read exactly once.  A warp
+//   1. stages its block in shared memory with 16-byte cp.async copies (the staged copy keeps the file's 16-byte phase,
+//      so there is no re-alignment work),
+//   2. verifies the block checksum out of shared memory (warp-cooperative XXH3 / CRC32C),
+//   3. walks the restart intervals, one lane per interval (the only inherently sequential part: an entry starts
+//      where the previous one ends), recording every entry's offset,
+//   4. gets its global output position with a decoupled look-back over per-block states (blocks are handed out in
+//      ticket order, so every predecessor is already running),
+//   5. decodes ONE ENTRY PER LANE: prefix decompression "key = first `shared` bytes of the previous key + suffix" is the
+//      map K -> (K & mask(shared)) | (suffix << shared); such maps compose associatively
+//      ((m1,D1) then (m2,D2) = (min(m1,m2), (D1 & mask(m2)) | D2)), so a warp inclusive scan rebuilds 32 keys at once,
+//   6. stores the columns coalesced (lane i -> entry base + i).
+// Blocks outside the fast path's limits (larger than the staging slice, more than 16 restart intervals, more than 16
+// entries in an interval) take a slower lane-per-interval path that needs regular intervals (what BlockBuilder writes).
+constexpr int kDecWarps = 8;
+constexpr int kDecPerTicket = 1;           // blocks per warp and ticket.  More would chain CTAs: a CTA's first round would wait
+                                           // (look-back) for the previous ticket holder's last round
+constexpr int kDecSlice = 4608;            // bytes staged per warp (block + trailer + phase); larger blocks are read in place
+constexpr int kDecVecs = kDecSlice / 16;   // 288
+constexpr int kDecPerLane = kDecVecs / 32;  // 9 vectors per lane
+constexpr int kDecRows = 16, kDecRowLen = 16;  // fast path: restart intervals per block, entries per interval
+struct DecWarpSmem {
+  uint4 slice[kDecVecs];
+  uint16_t tab[kDecRows * kDecRowLen];  // entry offsets, one row per restart interval
+  uint16_t ex[32];                      // entries before each interval
+};
 
-__global__ void __launch_bounds__(kCntWarps * 32)
-block_count_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
-                   const uint32_t* __restrict__ blk_size, uint32_t nblk, uint32_t verify, uint32_t* __restrict__ blk_cnt,
-                   uint32_t* __restrict__ blk_nr, uint32_t* __restrict__ blk_r, uint32_t* __restrict__ err) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint4* slice = reinterpret_cast<uint4*>(smem + (size_t)w * kCntSlice);
-  const uint32_t stride = gridDim.x * kCntWarps;
-  uint32_t b = blockIdx.x * kCntWarps + w;
-  // prefetch state of the block about to be processed
-  uint4 pre[kCntPerLane];
-  const uint8_t* cur_src = nullptr;
-  uint32_t cur_size = 0, cur_shift = 0, cur_cksum = 0;
-  bool cur_staged = false;
-  auto prefetch = [&](uint32_t bb) {
-    const FileDesc& fd = files[file_of_block(files, nfiles, bb)];
-    cur_src = fd.base + blk_off[bb];
-    cur_size = blk_size[bb];
-    cur_cksum = fd.cksum;
-    const uintptr_t a0 = (uintptr_t)cur_src & ~(uintptr_t)15;
-    cur_shift = (uint32_t)((uintptr_t)cur_src - a0);
-    const uint32_t nvec = (cur_shift + cur_size + 5 + 15) >> 4;
-    cur_staged = nvec <= (uint32_t)kCntVecs - 1;
-    if (cur_staged) {
-      const uint4* g = reinterpret_cast<const uint4*>(a0);
-#pragma unroll
-      for (int i = 0; i < kCntPerLane; i++) {
-        const uint32_t v = lane + 32 * i;
-        if (v < nvec) pre[i] = __ldg(g + v);
-      }
-    }
-  };
-  if (b < nblk) prefetch(b);
-  for (; b < nblk; b += stride) {
-    // commit the prefetched vectors of block b to shared memory
-    const uint8_t* src = cur_src;
-    const uint32_t size = cur_size, shift = cur_shift, cksum = cur_cksum;
-    const bool staged = cur_staged;
-    __syncwarp();
-    if (staged) {
-      const uint32_t nvec = (shift + size + 5 + 15) >> 4;
-#pragma unroll
-      for (int i = 0; i < kCntPerLane; i++) {
-        const uint32_t v = lane + 32 * i;
-        if (v < nvec) slice[v] = pre[i];
-      }
-    }
-    __syncwarp();
-    if (b + stride < nblk) prefetch(b + stride);  // next block's loads fly while this one is processed
-    const uint8_t* p = staged ? reinterpret_cast<const uint8_t*>(slice) + shift : src;
-    uint32_t cnt = 0, first = 0, nr = 0;
-    bool ok = true;
-    const uint8_t ctype = p[size];
-    if (ctype != 0) {
-      if (lane == 0) atomicOr(err, kErrCompressed);
-      ok = false;
-    }
-    if (ok && verify && cksum != 0) {
-      const uint32_t want = ld_u32(p + size + 1);
-      const uint32_t got = block_checksum_warp(cksum, p, size, ctype);
-      if (want != got) {
-        if (lane == 0) atomicOr(err, kErrChecksum);
-        ok = false;
-      }
-    }
-    if (ok) {
-      const uint32_t foot = ld_u32(p + size - 4);
-      nr = foot & 0x7fffffffu;
-      if ((foot >> 31) || nr == 0 || 4ull * nr + 4 > size) {  // data-block hash index: not produced by accepted configs
-        if (lane == 0) atomicOr(err, kErrCorruptBlock);
-        ok = false;
-        nr = 0;
-      }
-    }
-    if (ok) {
-      const uint8_t* restarts = p + size - 4 - 4ull * nr;
-      const uint32_t data_end = (uint32_t)(restarts - p);
-      uint32_t irregular = 0;
-      for (uint32_t j0 = 0; j0 < nr; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        uint32_t c = 0;
-        if (j < nr) {
-          const uint32_t r0 = ld_u32(restarts + 4ull * j);
-          const uint32_t r1 = j + 1 < nr ? ld_u32(restarts + 4ull * (j + 1)) : data_end;
-          c = (r0 <= r1 && r1 <= data_end && (j != 0 || r0 == 0)) ? count_interval(p + r0, p + r1) : 0xffffffffu;
-          if (c == 0xffffffffu) {
-            atomicOr(err, kErrCorruptBlock);
-            c = 0;
-          }
-        }
-        if (j0 == 0) first = __shfl_sync(0xffffffffu, c, 0);
-        // every restart interval but the last holds the same number of entries (what BlockBuilder writes): the decoder
-        // derives an interval's output position from its index
-        if (j + 1 < nr && c != first) irregular = 1;
-        if (j + 1 == nr && c > first) irregular = 1;
-        cnt += c;
-      }
-#pragma unroll
-      for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-      if (__any_sync(0xffffffffu, irregular)) {
-        if (lane == 0) atomicOr(err, kErrIrregularRestarts);
-      }
-    }
-    if (lane == 0) {
-      blk_cnt[b] = ok ? cnt : 0;
-      blk_nr[b] = ok ? nr : 0;
-      blk_r[b] = first;
-    }
+// entry header (three varint32: shared, non_shared, value length) from the 8 bytes h at p; false on malformed / unsupported
+__device__ __forceinline__ bool parse_header(uint64_t h, const uint8_t* p, const uint8_t* end, uint32_t* shared, uint32_t* non_shared,
+                                             uint32_t* vlen, uint32_t* hdr, uint32_t* __restrict__ err) {
+  if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {  // DecodeEntry fast path (block.cc:44-50): three one-byte lengths
+    *shared = (uint32_t)(h & 0xff);
+    *non_shared = (uint32_t)((h >> 8) & 0xff);
+    *vlen = (uint32_t)((h >> 16) & 0xff);
+    *hdr = 3;
+    return true;
   }
+  uint64_t v0 = 0, v1 = 0, v2 = 0;
+  uint32_t k = 0;
+  bool ok = true;
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    uint64_t v = 0;
+    uint32_t sft = 0;
+    for (;;) {
+      if (k >= 8) {
+        ok = false;
+        break;
+      }
+      uint32_t c = (uint32_t)((h >> (8 * k)) & 0xff);
+      k++;
+      v |= (uint64_t)(c & 127) << sft;
+      if (c < 128) break;
+      sft += 7;
+    }
+    if (q == 0) v0 = v;
+    else if (q == 1) v1 = v;
+    else v2 = v;
+  }
+  if (!ok) {  // longer than 8 bytes: byte-wise from memory
+    const uint8_t* q = p;
+    int c1 = get_varint(q, end, &v0);
+    q += c1;
+    int c2 = c1 ? get_varint(q, end, &v1) : 0;
+    q += c2;
+    int c3 = c2 ? get_varint(q, end, &v2) : 0;
+    if (!c3) {
+      atomicOr(err, kErrCorruptBlock);
+      return false;
+    }
+    k = (uint32_t)(c1 + c2 + c3);
+  }
+  if (v2 > kMetaVlenMask) {
+    atomicOr(err, kErrValueTooLong);
+    return false;
+  }
+  if (v0 > 64 || v1 > 64 || k > 8) {  // keys longer than the device format / exotic header
+    atomicOr(err, v0 + v1 > (uint64_t)(kMaxUserKey + 8) ? kErrKeyTooLong : kErrCorruptBlock);
+    return false;
+  }
+  *shared = (uint32_t)v0;
+  *non_shared = (uint32_t)v1;
+  *vlen = (uint32_t)v2;
+  *hdr = k;
+  return true;
+}
+// 24-byte key K as three little-endian words: masks of its first m bytes
+__device__ __forceinline__ void key_mask(uint32_t m, uint64_t* M0, uint64_t* M1, uint64_t* M2) {
+  *M0 = low_bytes_mask(m);
+  *M1 = m > 8 ? low_bytes_mask(m - 8) : 0;
+  *M2 = m > 16 ? low_bytes_mask(m - 16) : 0;
+}
+// D = S << (8 * shared) over three words
+__device__ __forceinline__ void key_shift(uint64_t S0, uint64_t S1, uint64_t S2, uint32_t shared, uint64_t* D0, uint64_t* D1, uint64_t* D2) {
+  const uint32_t wsh = shared >> 3, bs = (shared & 7) * 8;
+  const uint64_t c0 = bs ? S0 >> (64 - bs) : 0, c1 = bs ? S1 >> (64 - bs) : 0;
+  const uint64_t T0 = S0 << bs, T1 = (S1 << bs) | c0, T2 = (S2 << bs) | c1;
+  *D0 = wsh == 0 ? T0 : 0;
+  *D1 = wsh == 0 ? T1 : wsh == 1 ? T0 : 0;
+  *D2 = wsh == 0 ? T2 : wsh == 1 ? T1 : wsh == 2 ? T0 : 0;
+}
+// columns of one decoded entry from its 24-byte key image
+__device__ __forceinline__ void key_columns(uint64_t K0, uint64_t K1, uint64_t K2, uint32_t klen, uint64_t* hi, uint64_t* lo, uint64_t* tr) {
+  const uint32_t ulen = klen - 8;
+  *hi = bswap64(K0 & low_bytes_mask(ulen));
+  *lo = bswap64(ulen > 8 ? K1 & low_bytes_mask(ulen - 8) : 0);
+  const uint32_t wsh = ulen >> 3, bs = (ulen & 7) * 8;
+  const uint64_t a = wsh == 0 ? K0 : wsh == 1 ? K1 : K2, c = wsh == 0 ? K1 : wsh == 1 ? K2 : 0;
+  *tr = bs ? (a >> bs) | (c << (64 - bs)) : a;
 }
 
-// ---- thread-per-restart-interval decode -----------------------------------------------------------------------
-// A restart interval (16 entries by default) is the unit that can be prefix-decoded independently, so the decoder gives
-// every interval its own thread: ~N/16 threads in flight instead of one warp per 4 KB block with 5 busy lanes.
-// The thread streams through its ~1 KB of the file image with aligned 8-byte loads (L1 keeps the line for the next
-// entry); the current internal key lives in three registers (K0..K2 = its 24 bytes as little-endian words) and is
-// updated with mask / funnel-shift arithmetic instead of a byte buffer.
-
-__global__ void __launch_bounds__(256)
-block_decode_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
-                    const uint32_t* __restrict__ blk_size, const uint64_t* __restrict__ blk_base, const uint32_t* __restrict__ blk_r,
-                    const uint64_t* __restrict__ rbase, const uint64_t* __restrict__ total_intervals, uint32_t nblk, uint64_t n_total,
-                    KeyColsMut out, uint32_t* __restrict__ err) {
-  const unsigned lane = threadIdx.x & 31;
-  const uint64_t total = *total_intervals;
-  const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-  for (uint64_t ii0 = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; ii0 < total; ii0 += nwarps * 32) {
-    // block that holds interval ii0 (same search in every lane: uniform loads), then a short forward walk per lane
-    uint32_t lo = 0, hi = nblk;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (rbase[mid] <= ii0) lo = mid;
-      else hi = mid;
+// Slow path: decodes the restart interval [p, end) sequentially straight into the global columns at e0.
+__device__ __noinline__ uint32_t decode_interval_seq(const uint8_t* p, const uint8_t* end, const uint8_t* blk, const uint8_t* img,
+                                                     KeyColsMut out, uint64_t e0, uint64_t n_total, uint32_t* __restrict__ err) {
+  uint64_t K0 = 0, K1 = 0, K2 = 0;
+  uint32_t klen = 0, n = 0;
+  while (p < end) {
+    const Win w = load_win_any(p);
+    const uint32_t o = (uint32_t)((uintptr_t)p & 7);
+    uint32_t shared, non_shared, vlen, hdr;
+    if (!parse_header(win64(w, o), p, end, &shared, &non_shared, &vlen, &hdr, err)) break;
+    if (shared > klen || shared + non_shared < 8) {
+      atomicOr(err, kErrCorruptBlock);
+      break;
     }
-    const uint64_t ii = ii0 + lane;
-    if (ii >= total) continue;
-    uint32_t b = lo;
-    while (b + 1 < nblk && rbase[b + 1] <= ii) b++;
-    const uint32_t j = (uint32_t)(ii - rbase[b]);
-    const uint32_t nr = (uint32_t)((b + 1 < nblk ? rbase[b + 1] : total) - rbase[b]);
-    const int f = file_of_block(files, nfiles, b);
-    const uint8_t* blk = files[f].base + blk_off[b];
-    const uint32_t size = blk_size[b];
-    const uint8_t* restarts = blk + size - 4 - 4ull * nr;
-    const uint32_t r0 = ld_u32(restarts + 4ull * j);
-    const uint32_t r1 = j + 1 < nr ? ld_u32(restarts + 4ull * (j + 1)) : (uint32_t)(restarts - blk);
-    uint64_t e = blk_base[b] + (uint64_t)j * blk_r[b];
-    const uint8_t* p = blk + r0;
-    const uint8_t* end = blk + r1;
-    // the thread walks [p, end) front to back with dependent loads: pull its lines into L2 now so that every later miss
-    // pays L2 latency instead of a DRAM round trip
-    for (const uint8_t* q = p + 128; q < end; q += 128) prefetch_l2(q);
-    uint64_t K0 = 0, K1 = 0, K2 = 0;
-    uint32_t klen = 0;
-    const uint64_t e_begin = e;
-    const uint32_t want = j + 1 < nr ? blk_r[b] : 0xffffffffu;  // every interval but the last holds blk_r entries
-    while (p < end) {
-      const Win w = load_win(p);
-      const uint32_t o = (uint32_t)((uintptr_t)p & 7);
-      uint64_t h = win64(w, o);
-      uint32_t shared, non_shared, vlen, hdr;
-      if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {  // DecodeEntry fast path: three one-byte lengths
-        shared = (uint32_t)(h & 0xff);
-        non_shared = (uint32_t)((h >> 8) & 0xff);
-        vlen = (uint32_t)((h >> 16) & 0xff);
-        hdr = 3;
-      } else {  // varints from the 8 header bytes in the register (three varint32 of at most 8 bytes together)
-        uint64_t vals[3];
-        uint32_t k = 0;
-        bool ok = true;
+    if (shared + non_shared > (uint32_t)(kMaxUserKey + 8)) {
+      atomicOr(err, kErrKeyTooLong);
+      break;
+    }
+    const uint32_t so = o + hdr;
+    uint64_t S0 = win64(w, so), S1 = win64(w, so + 8), S2 = win64(w, so + 16), M0, M1, M2, D0, D1, D2;
+    key_mask(non_shared, &M0, &M1, &M2);
+    key_shift(S0 & M0, S1 & M1, S2 & M2, shared, &D0, &D1, &D2);
+    key_mask(shared, &M0, &M1, &M2);
+    K0 = (K0 & M0) | D0;
+    K1 = (K1 & M1) | D1;
+    K2 = (K2 & M2) | D2;
+    klen = shared + non_shared;
+    uint64_t hi, lo, tr;
+    key_columns(K0, K1, K2, klen, &hi, &lo, &tr);
+    if ((tr & 0xff) > 1) atomicOr(err, kErrBadType);
+    const uint8_t* val = p + hdr + non_shared;
+    if ((uint64_t)(end - val) < vlen) {
+      atomicOr(err, kErrCorruptBlock);
+      break;
+    }
+    const uint64_t e = e0 + n;
+    if (e < n_total) {
+      out.pfx[e] = make_ulonglong2(hi, lo);
+      out.tr[e] = tr;
+      out.vref[e] = (uint64_t)(uintptr_t)(img + (val - blk));
+      out.meta[e] = make_meta(klen - 8, vlen);
+    }
+    n++;
+    p = val + vlen;
+  }
+  return n;
+}
+
+template <int kMinCtas>
+__global__ void __launch_bounds__(kDecWarps * 32, kMinCtas)
+block_decode_fused_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
+                          const uint32_t* __restrict__ blk_size, uint32_t nblk, uint32_t verify, uint64_t n_total, KeyColsMut out,
+                          unsigned long long* blk_state, uint32_t* ticket, uint64_t* __restrict__ run_start,
+                          uint64_t* __restrict__ total_out, uint32_t* __restrict__ err) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ uint32_t s_tk[2];
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  DecWarpSmem& ws = reinterpret_cast<DecWarpSmem*>(smem)[w];
+  constexpr uint32_t kPerTicket = kDecWarps * kDecPerTicket;
+  for (int par = 0;; par ^= 1) {
+    if (threadIdx.x == 0) s_tk[par] = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint64_t b_first = (uint64_t)s_tk[par] * kPerTicket;
+    if (b_first >= nblk) break;  // uniform over the CTA
+#pragma unroll 1
+    for (int it = 0; it < kDecPerTicket; it++) {
+      const uint64_t b64 = b_first + (uint64_t)it * kDecWarps + w;
+      if (b64 >= nblk) break;
+      const uint32_t b = (uint32_t)b64;
+      const int f = file_of_block(files, nfiles, b);
+      const uint8_t* src = files[f].base + blk_off[b];
+      const uint32_t size = blk_size[b], cksum = files[f].cksum;
+      const uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15;
+      const uint32_t shift = (uint32_t)((uintptr_t)src - a0);
+      const uint32_t nvec = (shift + size + 5 + 15) >> 4;
+      const bool staged = nvec <= (uint32_t)kDecVecs - 3;  // 40-byte parse windows may run 32 bytes past the trailer
+      __syncwarp();  // the previous block's readers are done with the slice
+      if (staged) {
+        const uint4* g = reinterpret_cast<const uint4*>(a0);
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ws.slice);
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-          uint64_t v = 0;
-          uint32_t sft = 0;
-          for (;;) {
-            if (k >= 8) {
-              ok = false;
+        for (int i = 0; i < kDecPerLane; i++) {
+          const uint32_t v = lane + 32 * i;
+          if (v < nvec) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16 * v), "l"(g + v) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+      }
+      __syncwarp();
+      const uint8_t* p = staged ? reinterpret_cast<const uint8_t*>(ws.slice) + shift : src;
+      uint32_t cnt = 0, nr = 0;
+      bool ok = true;
+      const uint8_t ctype = p[size];
+      if (ctype != 0) {
+        if (lane == 0) atomicOr(err, kErrCompressed);
+        ok = false;
+      }
+      if (ok && verify && cksum != 0) {
+        const uint32_t want = ld_u32(p + size + 1);
+        const uint32_t got = block_checksum_warp(cksum, p, size, ctype);
+        if (want != got) {
+          if (lane == 0) atomicOr(err, kErrChecksum);
+          ok = false;
+        }
+      }
+      if (ok) {
+        const uint32_t foot = ld_u32(p + size - 4);
+        nr = foot & 0x7fffffffu;
+        if ((foot >> 31) || nr == 0 || 4ull * nr + 4 > size) {  // data-block hash index: not produced by accepted configs
+          if (lane == 0) atomicOr(err, kErrCorruptBlock);
+          ok = false;
+          nr = 0;
+        }
+      }
+      const uint8_t* restarts = p + size - 4 - 4ull * nr;
+      const uint32_t data_end = ok ? (uint32_t)(restarts - p) : 0;
+      // ---- walk the restart intervals
+      bool fast = ok && staged && nr <= (uint32_t)kDecRows;
+      uint32_t first = 0;  // slow path: entries per interval
+      if (fast) {
+        uint32_t c = 0;
+        bool bad = false;
+        if (lane < nr) {
+          const uint32_t r0 = ld_u32(restarts + 4ull * lane);
+          const uint32_t r1 = lane + 1 < nr ? ld_u32(restarts + 4ull * (lane + 1)) : data_end;
+          if (!(r0 <= r1 && r1 <= data_end && (lane != 0 || r0 == 0))) bad = true;
+          uint32_t q = r0;
+          while (!bad && q < r1) {
+            const uint64_t h = ld_u64_funnel(p + q);
+            uint32_t adv;
+            if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {
+              adv = 3 + (uint32_t)((h >> 8) & 0xff) + (uint32_t)((h >> 16) & 0xff);
+            } else {
+              uint64_t sh, ns, vl;
+              const uint8_t* x = p + q;
+              int c1 = get_varint(x, p + r1, &sh);
+              int c2 = c1 ? get_varint(x + c1, p + r1, &ns) : 0;
+              int c3 = c2 ? get_varint(x + c1 + c2, p + r1, &vl) : 0;
+              if (!c3 || ns + vl > (uint64_t)r1) {
+                bad = true;
+                break;
+              }
+              adv = (uint32_t)(c1 + c2 + c3) + (uint32_t)(ns + vl);
+            }
+            if (adv > r1 - q) {
+              bad = true;
               break;
             }
-            uint32_t c = (uint32_t)((h >> (8 * k)) & 0xff);
-            k++;
-            v |= (uint64_t)(c & 127) << sft;
-            if (c < 128) break;
-            sft += 7;
+            if (c < (uint32_t)kDecRowLen) ws.tab[lane * kDecRowLen + c] = (uint16_t)q;
+            q += adv;
+            c++;
           }
-          vals[q] = v;
         }
-        if (!ok) {  // longer than 8 bytes: byte-wise from memory
-          const uint8_t* q = p;
-          int c1 = get_varint(q, end, &vals[0]);
-          q += c1;
-          int c2 = c1 ? get_varint(q, end, &vals[1]) : 0;
-          q += c2;
-          int c3 = c2 ? get_varint(q, end, &vals[2]) : 0;
-          if (!c3) {
+        if (__ballot_sync(0xffffffffu, bad)) {
+          if (lane == 0) atomicOr(err, kErrCorruptBlock);
+          ok = false;
+          fast = false;
+        } else if (__ballot_sync(0xffffffffu, c > (uint32_t)kDecRowLen)) {
+          fast = false;  // unusually long intervals: slow path below recounts
+        } else {
+          const uint32_t inc = warp_incl_scan(c);
+          ws.ex[lane] = (uint16_t)(inc - c);
+          cnt = __shfl_sync(0xffffffffu, inc, 31);
+        }
+      }
+      if (ok && !fast) {
+        uint32_t irregular = 0;
+        for (uint32_t j0 = 0; j0 < nr; j0 += 32) {
+          const uint32_t j = j0 + lane;
+          uint32_t c = 0;
+          if (j < nr) {
+            const uint32_t r0 = ld_u32(restarts + 4ull * j);
+            const uint32_t r1 = j + 1 < nr ? ld_u32(restarts + 4ull * (j + 1)) : data_end;
+            c = (r0 <= r1 && r1 <= data_end && (j != 0 || r0 == 0)) ? count_interval(p + r0, p + r1) : 0xffffffffu;
+            if (c == 0xffffffffu) {
+              atomicOr(err, kErrCorruptBlock);
+              c = 0;
+              irregular = 1;
+            }
+          }
+          if (j0 == 0) first = __shfl_sync(0xffffffffu, c, 0);
+          if (j + 1 < nr && c != first) irregular = 1;
+          if (j + 1 == nr && c > first) irregular = 1;
+          cnt += c;
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (__ballot_sync(0xffffffffu, irregular != 0)) {
+          if (lane == 0) atomicOr(err, kErrIrregularRestarts);
+          ok = false;  // positions inside the block are not derivable
+        }
+      }
+      if (!ok) cnt = 0;  // a rejected block contributes no entries (the job fails anyway)
+      // ---- global position: decoupled look-back over block states
+      uint64_t base = 0;
+      {
+        const unsigned long long kAgg = 1ull << 62, kPre = 2ull << 62, kVal = (1ull << 62) - 1;
+        if (b == 0) {
+          if (lane == 0) atomicExch(&blk_state[0], kPre | cnt);
+        } else {
+          if (lane == 0) atomicExch(&blk_state[b], kAgg | cnt);
+          int64_t look = (int64_t)b - 1;
+          while (true) {
+            const int64_t idx = look - lane;
+            unsigned long long sv = kPre;  // virtual blocks before 0 contribute a zero prefix
+            if (idx >= 0) {
+              do {
+                sv = *((volatile unsigned long long*)&blk_state[idx]);
+              } while ((sv >> 62) == 0);
+            }
+            const unsigned pre_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+            const int first_pre = pre_mask ? __ffs(pre_mask) - 1 : 32;
+            uint64_t contrib = ((int)lane <= first_pre) ? (sv & kVal) : 0;
+#pragma unroll
+            for (int dd = 16; dd; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
+            base += contrib;
+            if (pre_mask) break;
+            look -= 32;
+          }
+          if (lane == 0) atomicExch(&blk_state[b], kPre | (base + cnt));
+        }
+      }
+      if (lane == 0) {
+        // runs start where their first block starts (runs without blocks start where the next one does)
+        for (int r = f; r >= 0 && files[r].gblk_first == b; r--) run_start[r] = base;
+        if (b + 1 == nblk) {
+          for (int r = nfiles; r > f && (r == nfiles || files[r].gblk_first >= nblk); r--) run_start[r] = base + cnt;
+          *total_out = base + cnt;
+        }
+      }
+      if (!ok || cnt == 0) continue;
+      if (base + cnt > n_total) {
+        if (lane == 0) atomicOr(err, kErrCountMismatch);
+        continue;
+      }
+      if (!fast) {  // lane per interval, sequential
+        for (uint32_t j0 = 0; j0 < nr; j0 += 32) {
+          const uint32_t j = j0 + lane;
+          if (j < nr) {
+            const uint32_t r0 = ld_u32(restarts + 4ull * j);
+            const uint32_t r1 = j + 1 < nr ? ld_u32(restarts + 4ull * (j + 1)) : data_end;
+            decode_interval_seq(p + r0, p + r1, p, src, out, base + (uint64_t)j * first, n_total, err);
+          }
+        }
+        continue;
+      }
+      // ---- one entry per lane; keys by a warp scan over the prefix-decompression maps
+      __syncwarp();
+      uint64_t C0 = 0, C1 = 0, C2 = 0;  // key of the entry before this round
+      uint32_t cklen = 0, cbad = 0;
+      for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+        const uint32_t idx = e0 + lane;
+        const bool valid = idx < cnt;
+        uint32_t m = 255, klen = 0, vlen = 0, voff = 0, shared = 0;
+        uint64_t D0 = 0, D1 = 0, D2 = 0;
+        bool bad = false;
+        if (valid) {
+          uint32_t j = 0;  // interval of entry idx: largest j < nr with ex[j] <= idx
+#pragma unroll
+          for (int st = kDecRows / 2; st; st >>= 1)
+            if (j + st < nr && ws.ex[j + st] <= idx) j += st;
+          const uint32_t q = ws.tab[j * kDecRowLen + (idx - ws.ex[j])];
+          const uint8_t* ep = p + q;
+          const Win wn = load_win_any(ep);
+          const uint32_t o = (uint32_t)((uintptr_t)ep & 7);
+          uint32_t non_shared, hdr;
+          if (!parse_header(win64(wn, o), ep, p + data_end, &shared, &non_shared, &vlen, &hdr, err)) {
+            bad = true;
+          } else if (shared + non_shared < 8) {
             atomicOr(err, kErrCorruptBlock);
-            break;
+            bad = true;
+          } else if (shared + non_shared > (uint32_t)(kMaxUserKey + 8)) {
+            atomicOr(err, kErrKeyTooLong);
+            bad = true;
+            klen = shared + non_shared;  // the successor's `shared` is still bounded by this length
+          } else {
+            const uint32_t so = o + hdr;
+            uint64_t S0 = win64(wn, so), S1 = win64(wn, so + 8), S2 = win64(wn, so + 16), M0, M1, M2;
+            key_mask(non_shared, &M0, &M1, &M2);
+            key_shift(S0 & M0, S1 & M1, S2 & M2, shared, &D0, &D1, &D2);
+            m = shared;
+            klen = shared + non_shared;
+            voff = q + hdr + non_shared;
           }
-          k = (uint32_t)(c1 + c2 + c3);
         }
-        if (vals[2] > kMetaVlenMask) {
-          atomicOr(err, kErrValueTooLong);
-          break;
+        // previous entry's key length bounds `shared`
+        uint32_t pk = __shfl_up_sync(0xffffffffu, klen, 1);
+        uint32_t pbad = __shfl_up_sync(0xffffffffu, (uint32_t)bad, 1);
+        if (lane == 0) pk = cklen, pbad = cbad;
+        if (valid && !bad && !pbad && shared > pk) {  // (after a rejected entry the bound is unknown: already an error)
+          atomicOr(err, kErrCorruptBlock);
+          bad = true;
         }
-        if (vals[0] > 64 || vals[1] > 64 || k > 8) {  // keys longer than the device format / exotic header
-          atomicOr(err, vals[0] + vals[1] > (uint64_t)(kMaxUserKey + 8) ? kErrKeyTooLong : kErrCorruptBlock);
-          break;
+        // inclusive scan of (m, D): left = earlier entries, right = own accumulated map
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t lm = __shfl_up_sync(0xffffffffu, m, d);
+          const uint64_t l0 = __shfl_up_sync(0xffffffffu, D0, d), l1 = __shfl_up_sync(0xffffffffu, D1, d),
+                         l2 = __shfl_up_sync(0xffffffffu, D2, d);
+          if (lane >= (unsigned)d) {
+            uint64_t M0, M1, M2;
+            key_mask(m, &M0, &M1, &M2);
+            D0 |= l0 & M0;
+            D1 |= l1 & M1;
+            D2 |= l2 & M2;
+            m = lm < m ? lm : m;
+          }
         }
-        shared = (uint32_t)vals[0];
-        non_shared = (uint32_t)vals[1];
-        vlen = (uint32_t)vals[2];
-        hdr = k;
-      }
-      if (shared > klen || shared + non_shared < 8) {
-        atomicOr(err, kErrCorruptBlock);
-        break;
-      }
-      if (shared + non_shared > (uint32_t)(kMaxUserKey + 8)) {
-        atomicOr(err, kErrKeyTooLong);
-        break;
-      }
-      // key suffix: non_shared bytes that follow the header
-      const uint32_t so = o + hdr;
-      uint64_t S0 = win64(w, so), S1 = win64(w, so + 8), S2 = win64(w, so + 16);
-      S0 &= low_bytes_mask(non_shared);
-      S1 &= non_shared > 8 ? low_bytes_mask(non_shared - 8) : 0;
-      S2 &= non_shared > 16 ? low_bytes_mask(non_shared - 16) : 0;
-      // keep `shared` bytes of the previous key
-      K0 &= low_bytes_mask(shared);
-      K1 &= shared > 8 ? low_bytes_mask(shared - 8) : 0;
-      K2 &= shared > 16 ? low_bytes_mask(shared - 16) : 0;
-      // K |= S << (8 * shared)
-      {
-        const uint32_t ws = shared >> 3, bs = (shared & 7) * 8;
-        const uint64_t c0 = bs ? S0 >> (64 - bs) : 0, c1 = bs ? S1 >> (64 - bs) : 0;
-        const uint64_t T0 = S0 << bs, T1 = (S1 << bs) | c0, T2 = (S2 << bs) | c1;
-        if (ws == 0) {
-          K0 |= T0;
-          K1 |= T1;
-          K2 |= T2;
-        } else if (ws == 1) {
-          K1 |= T0;
-          K2 |= T1;
-        } else if (ws == 2) {
-          K2 |= T0;
+        uint64_t M0, M1, M2;
+        key_mask(m, &M0, &M1, &M2);
+        const uint64_t K0 = (C0 & M0) | D0, K1 = (C1 & M1) | D1, K2 = (C2 & M2) | D2;
+        if (valid && !bad) {
+          uint64_t hi, lo, tr;
+          key_columns(K0, K1, K2, klen, &hi, &lo, &tr);
+          if ((tr & 0xff) > 1) atomicOr(err, kErrBadType);
+          const uint64_t e = base + idx;
+          out.pfx[e] = make_ulonglong2(hi, lo);
+          out.tr[e] = tr;
+          out.vref[e] = (uint64_t)(uintptr_t)(src + voff);
+          out.meta[e] = make_meta(klen - 8, vlen);
         }
+        C0 = __shfl_sync(0xffffffffu, K0, 31);
+        C1 = __shfl_sync(0xffffffffu, K1, 31);
+        C2 = __shfl_sync(0xffffffffu, K2, 31);
+        cklen = __shfl_sync(0xffffffffu, klen, 31);
+        cbad = __shfl_sync(0xffffffffu, (uint32_t)bad, 31);
       }
-      klen = shared + non_shared;
-      const uint32_t ulen = klen - 8;
-      const uint64_t hi = bswap64(K0 & low_bytes_mask(ulen));
-      const uint64_t lo = bswap64(ulen > 8 ? K1 & low_bytes_mask(ulen - 8) : 0);
-      uint64_t tr;
-      {
-        const uint32_t ws = ulen >> 3, bs = (ulen & 7) * 8;
-        const uint64_t a = ws == 0 ? K0 : ws == 1 ? K1 : K2, c = ws == 0 ? K1 : ws == 1 ? K2 : 0;
-        tr = bs ? (a >> bs) | (c << (64 - bs)) : a;
-      }
-      if ((tr & 0xff) > 1) atomicOr(err, kErrBadType);
-      const uint8_t* val = p + hdr + non_shared;
-      if ((uint64_t)(end - val) < vlen) {
-        atomicOr(err, kErrCorruptBlock);
-        break;
-      }
-      if (val + vlen < end) prefetch_l1(val + vlen);  // next entry's header while this key is assembled
-      if (e < n_total) {
-        out.pfx[e] = make_ulonglong2(hi, lo);
-        out.tr[e] = tr;
-        out.vref[e] = (uint64_t)(uintptr_t)val;
-        out.meta[e] = make_meta(ulen, vlen);
-      } else {
-        atomicOr(err, kErrCountMismatch);
-      }
-      e++;
-      p = val + vlen;
     }
-    if (want != 0xffffffffu ? (e - e_begin) != want : (e - e_begin) > blk_r[b]) atomicOr(err, kErrIrregularRestarts);
   }
 }
 
-// run_start[r] = number of entries before run r (blk_base at the run's first block); run_start[nfiles] = total
-__global__ void run_starts_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_base,
-                                  const uint64_t* __restrict__ total, uint32_t nblk, uint64_t* __restrict__ run_start) {
-  int r = threadIdx.x;
-  if (r < nfiles) run_start[r] = files[r].gblk_first < nblk ? blk_base[files[r].gblk_first] : *total;
-  if (r == nfiles) run_start[r] = *total;
-}
-
-// debug / test helper: gather value bytes through vref into a contiguous buffer (dst offsets from a scan of vlen)
 __global__ void gather_values_kernel(KeyCols in, const uint64_t* __restrict__ dst_off, uint8_t* __restrict__ dst) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < in.n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint8_t* s = (const uint8_t*)(uintptr_t)in.vref[i];
@@ -491,22 +639,28 @@ void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blo
   if (grid.x > 1024) grid.x = 1024;
   index_decode_kernel<<<grid, 256, 0, st>>>(files_dev, nfiles, blk_off, blk_size, err);
 }
-void launch_block_count(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
-                        uint32_t nblk, uint32_t verify, uint32_t* blk_cnt, uint32_t* blk_nr, uint32_t* blk_r, uint32_t* err, int sms,
-                        cudaStream_t st) {
-  unsigned want = (nblk + kCntWarps - 1) / kCntWarps, cap = (unsigned)sms * 5u;
-  block_count_kernel<<<want < cap ? (want ? want : 1) : cap, kCntWarps * 32, kCntWarps * kCntSlice, st>>>(
-      files_dev, nfiles, blk_off, blk_size, nblk, verify, blk_cnt, blk_nr, blk_r, err);
-}
-void launch_block_decode(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
-                         const uint64_t* blk_base, const uint32_t* blk_r, const uint64_t* rbase, const uint64_t* total_intervals,
-                         uint32_t nblk, uint64_t n_total, KeyColsMut out, uint32_t* err, int sms, cudaStream_t st) {
-  block_decode_kernel<<<(unsigned)sms * 8, 256, 0, st>>>(files_dev, nfiles, blk_off, blk_size, blk_base, blk_r, rbase,
-                                                         total_intervals, nblk, n_total, out, err);
-}
-void launch_run_starts(const FileDesc* files_dev, int nfiles, const uint64_t* blk_base, const uint64_t* total, uint32_t nblk,
-                       uint64_t* run_start, cudaStream_t st) {
-  run_starts_kernel<<<1, 128, 0, st>>>(files_dev, nfiles, blk_base, total, nblk, run_start);
+void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk,
+                               uint32_t verify, uint64_t n_total, KeyColsMut out, unsigned long long* blk_state, uint32_t* ticket,
+                               uint64_t* run_start, uint64_t* total_out, uint32_t* err, int sms, cudaStream_t st) {
+  static int occ = 0;
+  const int smem = kDecWarps * (int)sizeof(DecWarpSmem);
+  if (!occ) {
+    const char* e = getenv("B200C_DECODE_CTAS_PER_SM");  // tuning knob: 2 = no register spills, 3 / 4 = more warps
+    occ = e && atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;
+    cudaFuncSetAttribute(block_decode_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(block_decode_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(block_decode_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  }
+  const unsigned per = kDecWarps * kDecPerTicket;
+  unsigned want = (nblk + per - 1) / per, cap = (unsigned)sms * (unsigned)occ;
+  const unsigned grid = want < cap ? (want ? want : 1) : cap;
+#define B200C_LAUNCH_DEC(N)                                                                                                       \
+  block_decode_fused_kernel<N><<<grid, kDecWarps * 32, smem, st>>>(files_dev, nfiles, blk_off, blk_size, nblk, verify, n_total, out, \
+                                                                    blk_state, ticket, run_start, total_out, err)
+  if (occ == 2) B200C_LAUNCH_DEC(2);
+  else if (occ == 4) B200C_LAUNCH_DEC(4);
+  else B200C_LAUNCH_DEC(3);
+#undef B200C_LAUNCH_DEC
 }
 void launch_gather_values(KeyCols in, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st) {
   if (in.n == 0) return;

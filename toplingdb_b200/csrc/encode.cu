@@ -958,6 +958,45 @@ __device__ __forceinline__ void copy_value_small(uint8_t* dst, const uint8_t* sr
     if (rem > 2) dst[done + 2] = (uint8_t)(v >> 16);
   }
 }
+// the store half of copy_value_small for a value whose aligned source words w[0..NW) are already in registers
+// (w[NW] must be 0); a = source misalignment, n <= 4 * (NW - 1) bytes
+template <int NW>
+__device__ __forceinline__ void store_value_words(uint8_t* dst, const uint32_t* w, uint32_t a, uint32_t n) {
+  if (n == 0) return;
+  uint32_t head = (4 - (uint32_t)((uintptr_t)dst & 3)) & 3;
+  if (head > n) head = n;
+  {
+    const uint32_t v = __funnelshift_r(w[0], w[1], a * 8);
+    if (head > 0) dst[0] = (uint8_t)v;
+    if (head > 1) dst[1] = (uint8_t)(v >> 8);
+    if (head > 2) dst[2] = (uint8_t)(v >> 16);
+  }
+  const uint32_t t0 = a + head, bs = (t0 & 3) * 8;
+  const uint32_t nwords = (n - head) >> 2;
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + head);
+  const uint32_t done = head + 4 * nwords, rem = n - done;  // 0..3 tail bytes
+  uint32_t tailv = 0;
+  if ((t0 >> 2) == 0) {
+#pragma unroll
+    for (int mI = 0; mI < NW - 1; mI++) {
+      const uint32_t v = __funnelshift_r(w[mI], w[mI + 1], bs);
+      if ((uint32_t)mI < nwords) d32[mI] = v;
+      if ((uint32_t)mI == nwords) tailv = v;
+    }
+  } else {
+#pragma unroll
+    for (int mI = 0; mI < NW - 1; mI++) {
+      const uint32_t v = __funnelshift_r(w[mI + 1], mI + 2 <= NW ? w[mI + 2] : 0u, bs);
+      if ((uint32_t)mI < nwords) d32[mI] = v;
+      if ((uint32_t)mI == nwords) tailv = v;
+    }
+  }
+  if (rem) {
+    dst[done] = (uint8_t)tailv;
+    if (rem > 1) dst[done + 1] = (uint8_t)(tailv >> 8);
+    if (rem > 2) dst[done + 2] = (uint8_t)(tailv >> 16);
+  }
+}
 constexpr int kEmitBatch = 8;
 constexpr int kEmitPerThread = 3;
 constexpr int kEmitMaxEntries = kEmitWarps * 32 * kEmitPerThread;  // 768
@@ -1007,13 +1046,28 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
     const uint32_t rmask = (R & (R - 1)) == 0 ? R - 1 : 0xffffffffu;  // power-of-two restart interval: mask instead of %
     // pass 1 keeps only three words per entry alive across the scan; keys / value addresses are loaded in pass 2
     uint32_t bi[kEmitPerThread], sz[kEmitPerThread], pk[kEmitPerThread], vs[kEmitPerThread];  // pk = shared | ulen << 8 | restart << 16
-    uint64_t cum[kEmitPerThread];
+    uint64_t cum[kEmitPerThread], vrf[kEmitPerThread];
     if (fits) {
       // thread t owns the consecutive entries [3t, 3t+3): one CTA-wide scan gives every entry its byte position
       uint32_t tsum = 0, q = 0;
       {
         const uint32_t x0 = t * kEmitPerThread;
         while (q + 1 < nb && s.first_rel[q + 1] <= x0) q++;
+      }
+      // all column loads of the thread's entries are issued before the first use (one DRAM round trip, not three)
+      uint32_t mtv[kEmitPerThread], shv[kEmitPerThread];
+#pragma unroll
+      for (int i = 0; i < kEmitPerThread; i++) {
+        const uint32_t x = t * kEmitPerThread + i;
+        mtv[i] = 0;
+        shv[i] = 0;
+        vrf[i] = 0;
+        if (x < E) {
+          const uint64_t e = e0 + x;
+          mtv[i] = m.meta[e];
+          shv[i] = wk.eshared[e];
+          vrf[i] = m.vref[e];
+        }
       }
 #pragma unroll
       for (int i = 0; i < kEmitPerThread; i++) {
@@ -1023,15 +1077,13 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
         pk[i] = 0;
         vs[i] = 0;
         if (x < E) {
-          const uint64_t e = e0 + x;
           while (q + 1 < nb && s.first_rel[q + 1] <= x) q++;
           bi[i] = q;
           const uint32_t jj = x - s.first_rel[q];
           const bool restart = (rmask != 0xffffffffu ? (jj & rmask) : (jj % R)) == 0;
-          const uint32_t mt = m.meta[e];
-          const uint32_t ul = meta_ulen(mt);
-          vs[i] = meta_vlen(mt);
-          const uint32_t sh = restart ? 0 : wk.eshared[e];
+          const uint32_t ul = meta_ulen(mtv[i]);
+          vs[i] = meta_vlen(mtv[i]);
+          const uint32_t sh = restart ? 0 : shv[i];
           pk[i] = sh | (ul << 8) | (restart ? 1u << 16 : 0);
           sz[i] = entry_size(sh, ul + 8, vs[i]);
           tsum += sz[i];
@@ -1066,43 +1118,80 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
       if (w < nb) emit_block_warp(m, ep, wk, b0 + w, out_base, img0 + (size_t)w * slot_bytes, slot_bytes);
       continue;
     }
-    // pass 2: write entries into the block images
+    // pass 2: write entries into the block images.  Key columns for all of the thread's entries first, then (when every
+    // value is short) all value words, so that each group costs one DRAM round trip.
+    uint32_t voff[kEmitPerThread];  // image offset of the value bytes
+    {
+      ulonglong2 ppv[kEmitPerThread];
+      uint64_t trv[kEmitPerThread];
 #pragma unroll
-    for (int i = 0; i < kEmitPerThread; i++) {
-      const uint32_t x = t * kEmitPerThread + i;
-      if (x < E) {
-        const uint64_t e = e0 + x;
-        const uint32_t q = bi[i], sh = pk[i] & 0xff, ul = (pk[i] >> 8) & 0xff;
-        const ulonglong2 pp = m.pfx[e];
-        const uint64_t tr = m.tr[e];
-        const uint8_t* vsrc = (const uint8_t*)(uintptr_t)m.vref[e];
-        uint8_t* img = img0 + (size_t)q * slot_bytes;
-        const uint32_t off = (uint32_t)(cum[i] - s.cum0[q]);
-        uint8_t* p = img + off;
-        const uint32_t ks = ul + 8;
-        if ((sh | (ks - sh) | vs[i]) < 128) {
-          p[0] = (uint8_t)sh;
-          p[1] = (uint8_t)(ks - sh);
-          p[2] = (uint8_t)vs[i];
-          p += 3;
-        } else {
-          p += put_varint(p, sh);
-          p += put_varint(p, ks - sh);
-          p += put_varint(p, vs[i]);
+      for (int i = 0; i < kEmitPerThread; i++) {
+        const uint32_t x = t * kEmitPerThread + i;
+        ppv[i] = make_ulonglong2(0, 0);
+        trv[i] = 0;
+        if (x < E) {
+          ppv[i] = m.pfx[e0 + x];
+          trv[i] = m.tr[e0 + x];
         }
-        uint64_t S0, S1, S2;
-        key_suffix_words(pp.x, pp.y, ul, tr, sh, &S0, &S1, &S2);
-        store_bytes24(p, S0, S1, S2, ks - sh);
-        p += ks - sh;
-        if (vs[i] <= 64) copy_value_small(p, vsrc, vs[i]);
-        if (pk[i] >> 16) {
-          const uint32_t jj = x - s.first_rel[q];
-          uint8_t* rp = img + s.body[q] + 4ull * (rmask != 0xffffffffu ? jj >> __popc(rmask) : jj / R);
-          rp[0] = (uint8_t)off;
-          rp[1] = (uint8_t)(off >> 8);
-          rp[2] = (uint8_t)(off >> 16);
-          rp[3] = (uint8_t)(off >> 24);
+      }
+#pragma unroll
+      for (int i = 0; i < kEmitPerThread; i++) {
+        const uint32_t x = t * kEmitPerThread + i;
+        voff[i] = 0;
+        if (x < E) {
+          const uint32_t q = bi[i], sh = pk[i] & 0xff, ul = (pk[i] >> 8) & 0xff;
+          uint8_t* img = img0 + (size_t)q * slot_bytes;
+          const uint32_t off = (uint32_t)(cum[i] - s.cum0[q]);
+          uint8_t* p = img + off;
+          const uint32_t ks = ul + 8;
+          if ((sh | (ks - sh) | vs[i]) < 128) {
+            p[0] = (uint8_t)sh;
+            p[1] = (uint8_t)(ks - sh);
+            p[2] = (uint8_t)vs[i];
+            p += 3;
+          } else {
+            p += put_varint(p, sh);
+            p += put_varint(p, ks - sh);
+            p += put_varint(p, vs[i]);
+          }
+          uint64_t S0, S1, S2;
+          key_suffix_words(ppv[i].x, ppv[i].y, ul, trv[i], sh, &S0, &S1, &S2);
+          store_bytes24(p, S0, S1, S2, ks - sh);
+          p += ks - sh;
+          voff[i] = (uint32_t)(p - img0);
+          if (pk[i] >> 16) {
+            const uint32_t jj = x - s.first_rel[q];
+            uint8_t* rp = img + s.body[q] + 4ull * (rmask != 0xffffffffu ? jj >> __popc(rmask) : jj / R);
+            rp[0] = (uint8_t)off;
+            rp[1] = (uint8_t)(off >> 8);
+            rp[2] = (uint8_t)(off >> 16);
+            rp[3] = (uint8_t)(off >> 24);
+          }
         }
+      }
+    }
+    {
+      constexpr int kNW = 9;  // aligned words covering a value of <= 32 bytes at any alignment
+      bool all_short = true;
+#pragma unroll
+      for (int i = 0; i < kEmitPerThread; i++) all_short = all_short && vs[i] <= 32;
+      if (all_short) {
+        uint32_t vw[kEmitPerThread][kNW + 1];
+#pragma unroll
+        for (int i = 0; i < kEmitPerThread; i++) {
+          const uint32_t a = (uint32_t)(vrf[i] & 3);
+          const uint32_t* wsrc = reinterpret_cast<const uint32_t*>((uintptr_t)vrf[i] - a);
+          const uint32_t nw = vs[i] ? (a + vs[i] + 3) >> 2 : 0;
+#pragma unroll
+          for (int k = 0; k < kNW; k++) vw[i][k] = (uint32_t)k < nw ? __ldg(wsrc + k) : 0u;
+          vw[i][kNW] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < kEmitPerThread; i++) store_value_words<kNW>(img0 + voff[i], vw[i], (uint32_t)(vrf[i] & 3), vs[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kEmitPerThread; i++)
+          if (vs[i] && vs[i] <= 64) copy_value_small(img0 + voff[i], (const uint8_t*)(uintptr_t)vrf[i], vs[i]);
       }
     }
     // values longer than 64 bytes: a warp copies each of its lanes' values with all lanes
@@ -1115,10 +1204,10 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
         big &= big - 1;
         const uint32_t q = __shfl_sync(0xffffffffu, bi[i], sl);
         const uint32_t vl = __shfl_sync(0xffffffffu, vs[i], sl);
-        const uint32_t voff = __shfl_sync(0xffffffffu, (uint32_t)(cum[i] - s.cum0[bi[i]]) + sz[i] - vs[i], sl);
-        const uint64_t vrr = __shfl_sync(0xffffffffu, (x < E && vs[i] > 64) ? m.vref[e0 + x] : 0ull, sl);
+        const uint32_t vo = __shfl_sync(0xffffffffu, voff[i], sl);
+        const uint64_t vrr = __shfl_sync(0xffffffffu, vrf[i], sl);
         const uint8_t* sp = (const uint8_t*)(uintptr_t)vrr;
-        uint8_t* dp = img0 + (size_t)q * slot_bytes + voff;
+        uint8_t* dp = img0 + vo;
         // aligned 4-byte source words, funnel-shifted; byte stores into the image
         const uint32_t a = (uint32_t)((uintptr_t)sp & 3);
         const uint32_t* wsrc = reinterpret_cast<const uint32_t*>((uintptr_t)sp - a);

@@ -22,14 +22,9 @@ struct FileDesc {          // one input BlockBasedTable image resident in HBM
 // ---- decode.cu
 void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blocks_per_file, uint64_t* blk_off,
                          uint32_t* blk_size, uint32_t* err, cudaStream_t st);
-void launch_block_count(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
-                        uint32_t nblk, uint32_t verify, uint32_t* blk_cnt, uint32_t* blk_nr, uint32_t* blk_r, uint32_t* err, int sms,
-                        cudaStream_t st);
-void launch_block_decode(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size,
-                         const uint64_t* blk_base, const uint32_t* blk_r, const uint64_t* rbase, const uint64_t* total_intervals,
-                         uint32_t nblk, uint64_t n_total, KeyColsMut out, uint32_t* err, int sms, cudaStream_t st);
-void launch_run_starts(const FileDesc* files_dev, int nfiles, const uint64_t* blk_base, const uint64_t* total, uint32_t nblk,
-                       uint64_t* run_start, cudaStream_t st);
+void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk,
+                               uint32_t verify, uint64_t n_total, KeyColsMut out, unsigned long long* blk_state, uint32_t* ticket,
+                               uint64_t* run_start, uint64_t* total_out, uint32_t* err, int sms, cudaStream_t st);
 void launch_gather_values(KeyCols in, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st);
 void launch_meta_vlen(const uint32_t* meta, uint64_t n, uint32_t* vlen, cudaStream_t st);
 

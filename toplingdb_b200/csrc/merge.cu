@@ -258,11 +258,15 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   __syncthreads();
   const uint64_t tile = s.tile_id;
   if (tile >= ntiles) return;
-  // ---- segment table
+  // ---- segment table; the tile's predecessor in merged order (= largest element before the split) is fetched here
+  // too, one lane per run, so its DRAM round trip overlaps the split loads
   if (t < k) {
-    uint64_t s0 = splits[tile * k + t], s1 = splits[(tile + 1) * k + t];
-    s.sbeg[t] = run_start[t] + s0;
+    const uint64_t s0 = splits[tile * k + t], s1 = splits[(tile + 1) * k + t];
+    const uint64_t b0 = run_start[t] + s0;
+    s.sbeg[t] = b0;
     s.lst[1][t] = (uint32_t)(s1 - s0);  // lengths, scanned below
+    s.cand_ok[t] = s0 != 0;
+    if (s0 != 0) s.cand[t] = load_key(in, b0 - 1);
   }
   __syncthreads();
   if (t == 0) {
@@ -278,12 +282,10 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       atomicOr(err, kErrKeyOrder);
       s.seg[k] = 0;
     }
-    // predecessor of the tile in merged order = largest element before the split
     s.has_pred = 0;
     for (uint32_t r = 0; r < k; r++) {
-      uint64_t s0 = s.sbeg[r] - run_start[r];
-      if (s0 == 0) continue;
-      Key e = load_key(in, s.sbeg[r] - 1);
+      if (!s.cand_ok[r]) continue;
+      const Key e = s.cand[r];
       if (!s.has_pred || ikey_less(s.pred, e)) {
         s.pred = e;
         s.has_pred = 1;
@@ -306,24 +308,41 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       }
     }
   }
-  // ---- coalesced load of the k segments
+  // ---- coalesced load of the k segments.  All of a thread's loads are issued before the first one is consumed: a
+  // warp issues in order, so a load-then-store loop body would pay one DRAM round trip per iteration.
+  {
+    ulonglong2 lp[kMV];
+    uint64_t ltr[kMV];
+    uint32_t lmt[kMV];
 #pragma unroll
-  for (int j = 0; j < kMV; j++) {
-    uint32_t i = t + j * kMThreads;
-    if (i < cnt) {
-      uint32_t lo = 0, hi = k;  // run r with seg[r] <= i < seg[r+1]
-      while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (s.seg[mid] <= i) lo = mid;
-        else hi = mid;
+    for (int j = 0; j < kMV; j++) {
+      const uint32_t i = t + j * kMThreads;
+      lp[j] = make_ulonglong2(0, 0);
+      ltr[j] = 0;
+      lmt[j] = 0;
+      if (i < cnt) {
+        uint32_t lo = 0, hi = k;  // run r with seg[r] <= i < seg[r+1]
+        while (hi - lo > 1) {
+          uint32_t mid = (lo + hi) >> 1;
+          if (s.seg[mid] <= i) lo = mid;
+          else hi = mid;
+        }
+        const uint64_t src = s.sbeg[lo] + (i - s.seg[lo]);
+        lp[j] = in.pfx[src];
+        ltr[j] = in.tr[src];
+        lmt[j] = in.meta[src];
       }
-      uint64_t src = s.sbeg[lo] + (i - s.seg[lo]);
-      ulonglong2 p = in.pfx[src];
-      s.hi[i] = p.x;
-      s.lo[i] = p.y;
-      s.tr[i] = in.tr[src];
-      s.ulen[i] = (uint8_t)meta_ulen(in.meta[src]);
-      s.idx[i] = (uint16_t)i;
+    }
+#pragma unroll
+    for (int j = 0; j < kMV; j++) {
+      const uint32_t i = t + j * kMThreads;
+      if (i < cnt) {
+        s.hi[i] = lp[j].x;
+        s.lo[i] = lp[j].y;
+        s.tr[i] = ltr[j];
+        s.ulen[i] = (uint8_t)meta_ulen(lmt[j]);
+        s.idx[i] = (uint16_t)i;
+      }
     }
   }
   __syncthreads();
@@ -549,19 +568,43 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   }
   __syncthreads();
   const uint64_t base_out = s.base_out;
-  for (uint32_t i = t; i < kept_total; i += kMThreads) {
-    uint32_t pos = s.idx[i], lo = 0, hi = k;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (s.seg[mid] <= pos) lo = mid;
-      else hi = mid;
+  {
+    // gather the value references of the survivors (random within k contiguous segments) for all of the thread's
+    // output slots first, then write: again one round trip instead of kMV
+    uint64_t gv[kMV];
+    uint32_t gm[kMV];
+    uint16_t gp[kMV];
+#pragma unroll
+    for (int j = 0; j < kMV; j++) {
+      const uint32_t i = t + j * kMThreads;
+      gv[j] = 0;
+      gm[j] = 0;
+      gp[j] = 0;
+      if (i < kept_total) {
+        uint32_t pos = s.idx[i], lo = 0, hi = k;
+        while (hi - lo > 1) {
+          uint32_t mid = (lo + hi) >> 1;
+          if (s.seg[mid] <= pos) lo = mid;
+          else hi = mid;
+        }
+        const uint64_t src = s.sbeg[lo] + (pos - s.seg[lo]);
+        gp[j] = (uint16_t)pos;
+        gv[j] = in.vref[src];
+        gm[j] = in.meta[src];
+      }
     }
-    uint64_t src = s.sbeg[lo] + (pos - s.seg[lo]);
-    uint64_t dst = base_out + i;
-    out.pfx[dst] = make_ulonglong2(s.hi[pos], s.lo[pos]);
-    out.tr[dst] = s.tr[pos];
-    out.vref[dst] = in.vref[src];
-    out.meta[dst] = in.meta[src];
+#pragma unroll
+    for (int j = 0; j < kMV; j++) {
+      const uint32_t i = t + j * kMThreads;
+      if (i < kept_total) {
+        const uint32_t pos = gp[j];
+        const uint64_t dst = base_out + i;
+        out.pfx[dst] = make_ulonglong2(s.hi[pos], s.lo[pos]);
+        out.tr[dst] = s.tr[pos];
+        out.vref[dst] = gv[j];
+        out.meta[dst] = gm[j];
+      }
+    }
   }
   // ---- counters: one atomic per CTA and counter
   unsigned long long vals[7] = {(unsigned long long)nkeep, c_indel, c_hidden, c_obsolete, c_kbytes, c_vbytes, c_silent};
