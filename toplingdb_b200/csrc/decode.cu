@@ -193,8 +193,6 @@ __device__ __forceinline__ uint32_t count_interval(const uint8_t* p, const uint8
 // Blocks outside the fast path's limits (larger than the staging slice, more than 16 restart intervals, more than 16
 // entries in an interval) take a slower lane-per-interval path that needs regular intervals (what BlockBuilder writes).
 constexpr int kDecWarps = 8;
-constexpr int kDecPerTicket = 1;           // blocks per warp and ticket.  More would chain CTAs: a CTA's first round would wait
-                                           // (look-back) for the previous ticket holder's last round
 constexpr int kDecSlice = 4608;            // bytes staged per warp (block + trailer + phase); larger blocks are read in place
 constexpr int kDecVecs = kDecSlice / 16;   // 288
 constexpr int kDecPerLane = kDecVecs / 32;  // 9 vectors per lane
@@ -337,6 +335,274 @@ __device__ __noinline__ uint32_t decode_interval_seq(const uint8_t* p, const uin
   return n;
 }
 
+// global position of block b: decoupled look-back over the per-block states (flag in the two top bits: 1 = this block's
+// count, 2 = inclusive prefix).  The block's own count must already be published.
+__device__ __forceinline__ uint64_t block_lookback(unsigned long long* blk_state, uint32_t b, uint32_t cnt, unsigned lane) {
+  const unsigned long long kPre = 2ull << 62, kVal = (1ull << 62) - 1;
+  uint64_t base = 0;
+  if (b != 0) {
+    int64_t look = (int64_t)b - 1;
+    while (true) {
+      const int64_t idx = look - lane;
+      unsigned long long sv = kPre;  // virtual blocks before 0 contribute a zero prefix
+      if (idx >= 0) {
+        sv = *((volatile unsigned long long*)&blk_state[idx]);
+        while ((sv >> 62) == 0) {
+          __nanosleep(40);  // the predecessor is still walking its block: leave the issue slots to working warps
+          sv = *((volatile unsigned long long*)&blk_state[idx]);
+        }
+      }
+      const unsigned pre_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+      const int first_pre = pre_mask ? __ffs(pre_mask) - 1 : 32;
+      uint64_t contrib = ((int)lane <= first_pre) ? (sv & kVal) : 0;
+#pragma unroll
+      for (int dd = 16; dd; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
+      base += contrib;
+      if (pre_mask) break;
+      look -= 32;
+    }
+    if (lane == 0) atomicExch(&blk_state[b], kPre | (base + cnt));
+  }
+  return base;
+}
+__device__ __forceinline__ void publish_block_count(unsigned long long* blk_state, uint32_t b, uint32_t cnt, unsigned lane) {
+  if (lane == 0) atomicExch(&blk_state[b], ((b == 0 ? 2ull : 1ull) << 62) | cnt);
+}
+__device__ __forceinline__ void record_run_starts(const FileDesc* __restrict__ files, int nfiles, int f, uint32_t b, uint32_t nblk, uint64_t base,
+                                                  uint32_t cnt, uint64_t* __restrict__ run_start, uint64_t* __restrict__ total_out) {
+  // runs start where their first block starts (runs without blocks start where the next one does)
+  for (int r = f; r >= 0 && files[r].gblk_first == b; r--) run_start[r] = base;
+  if (b + 1 == nblk) {
+    for (int r = nfiles; r > f && (r == nfiles || files[r].gblk_first >= nblk); r--) run_start[r] = base + cnt;
+    *total_out = base + cnt;
+  }
+}
+
+// Fast path for a block staged in the warp's slice at byte `shift`.  Returns false (nothing published) when the block
+// is outside the fast path's limits and has to take decode_block_slow.
+__device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t shift, const uint8_t* src, uint32_t size, uint32_t cksum,
+                                                  uint32_t verify, uint32_t b, int f, const FileDesc* __restrict__ files, int nfiles,
+                                                  uint32_t nblk, uint64_t n_total, KeyColsMut out, unsigned long long* blk_state,
+                                                  uint64_t* __restrict__ run_start, uint64_t* __restrict__ total_out,
+                                                  uint32_t* __restrict__ err, unsigned lane) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(ws.slice) + shift;  // shared memory: 32-bit addressing throughout
+  const uint32_t foot = ld_u32(p + size - 4);
+  const uint32_t nr = foot & 0x7fffffffu;
+  if ((foot >> 31) || nr == 0 || nr > (uint32_t)kDecRows || 4 * nr + 4 > size) return false;
+  const uint8_t* restarts = p + size - 4 - 4 * nr;
+  const uint32_t data_end = size - 4 - 4 * nr;
+  // ---- walk the restart intervals, one lane each, recording entry offsets
+  uint32_t c = 0;
+  bool bad = false;
+  if (lane < nr) {
+    const uint32_t r0 = ld_u32(restarts + 4 * lane);
+    const uint32_t r1 = lane + 1 < nr ? ld_u32(restarts + 4 * (lane + 1)) : data_end;
+    if (!(r0 <= r1 && r1 <= data_end && (lane != 0 || r0 == 0))) bad = true;
+    uint32_t q = r0;
+    while (!bad && q < r1) {
+      const uint64_t h = ld_u64_funnel(p + q);
+      uint32_t adv;
+      if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {
+        adv = 3 + (uint32_t)((h >> 8) & 0xff) + (uint32_t)((h >> 16) & 0xff);
+      } else {
+        uint64_t sh, ns, vl;
+        const uint8_t* x = p + q;
+        int c1 = get_varint(x, p + r1, &sh);
+        int c2 = c1 ? get_varint(x + c1, p + r1, &ns) : 0;
+        int c3 = c2 ? get_varint(x + c1 + c2, p + r1, &vl) : 0;
+        if (!c3 || ns + vl > (uint64_t)r1) {
+          bad = true;
+          break;
+        }
+        adv = (uint32_t)(c1 + c2 + c3) + (uint32_t)(ns + vl);
+      }
+      if (adv > r1 - q) {
+        bad = true;
+        break;
+      }
+      if (c < (uint32_t)kDecRowLen) ws.tab[lane * kDecRowLen + c] = (uint16_t)q;
+      q += adv;
+      c++;
+    }
+  }
+  if (__ballot_sync(0xffffffffu, !bad && c > (uint32_t)kDecRowLen)) return false;  // unusually long intervals
+  bool ok = true;
+  if (__ballot_sync(0xffffffffu, bad)) {
+    if (lane == 0) atomicOr(err, kErrCorruptBlock);
+    ok = false;
+    c = 0;
+  }
+  const uint32_t inc = warp_incl_scan(c);
+  uint32_t cnt = __shfl_sync(0xffffffffu, inc, 31);
+  if (lane <= nr) ws.ex[lane] = (uint16_t)(inc - c);  // ex[nr] = cnt
+  publish_block_count(blk_state, b, cnt, lane);      // successors can look back while this warp checksums
+  const uint8_t ctype = p[size];
+  if (ctype != 0) {
+    if (lane == 0) atomicOr(err, kErrCompressed);
+    ok = false;
+  } else if (verify && cksum != 0) {
+    const uint32_t want = ld_u32(p + size + 1);
+    const uint32_t got = block_checksum_warp(cksum, p, size, ctype);
+    if (want != got) {
+      if (lane == 0) atomicOr(err, kErrChecksum);
+      ok = false;
+    }
+  }
+  const uint64_t base = block_lookback(blk_state, b, cnt, lane);
+  if (lane == 0) record_run_starts(files, nfiles, f, b, nblk, base, cnt, run_start, total_out);
+  if (!ok || cnt == 0) return true;
+  if (base + cnt > n_total) {
+    if (lane == 0) atomicOr(err, kErrCountMismatch);
+    return true;
+  }
+  __syncwarp();
+  // ---- one entry per lane, one restart interval per half-warp; keys by a segmented scan over the decompression maps
+  for (uint32_t row0 = 0; row0 < nr; row0 += 2) {
+    const uint32_t row = row0 + (lane >> 4), i = lane & 15;
+    const uint32_t ex0 = row < nr ? ws.ex[row] : 0, rc = row < nr ? ws.ex[row + 1] - ex0 : 0;
+    const bool valid = i < rc;
+    uint32_t m = 255, klen = 0, vlen = 0, voff = 0, shared = 0;
+    uint64_t D0 = 0, D1 = 0, D2 = 0;
+    bool ebad = false;
+    if (valid) {
+      const uint32_t q = ws.tab[row * kDecRowLen + i];
+      const uint8_t* ep = p + q;
+      const Win wn = load_win_any(ep);
+      const uint32_t o = (uint32_t)((shift + q) & 7);  // the slice is 16-byte aligned
+      uint32_t non_shared, hdr;
+      if (!parse_header(win64(wn, o), ep, p + data_end, &shared, &non_shared, &vlen, &hdr, err)) {
+        ebad = true;
+      } else if (shared + non_shared < 8) {
+        atomicOr(err, kErrCorruptBlock);
+        ebad = true;
+      } else if (shared + non_shared > (uint32_t)(kMaxUserKey + 8)) {
+        atomicOr(err, kErrKeyTooLong);
+        ebad = true;
+        klen = shared + non_shared;  // the successor's `shared` is still bounded by this length
+      } else {
+        const uint32_t so = o + hdr;
+        uint64_t S0 = win64(wn, so), S1 = win64(wn, so + 8), S2 = win64(wn, so + 16), M0, M1, M2;
+        key_mask(non_shared, &M0, &M1, &M2);
+        key_shift(S0 & M0, S1 & M1, S2 & M2, shared, &D0, &D1, &D2);
+        m = shared;
+        klen = shared + non_shared;
+        voff = q + hdr + non_shared;
+      }
+    }
+    // `shared` is bounded by the previous entry's key length (0 before a restart point)
+    uint32_t pk = __shfl_up_sync(0xffffffffu, klen, 1, 16);
+    uint32_t pbad = __shfl_up_sync(0xffffffffu, (uint32_t)ebad, 1, 16);
+    if (i == 0) pk = 0, pbad = 0;
+    if (valid && !ebad && !pbad && shared > pk) {  // (after a rejected entry the bound is unknown: already an error)
+      atomicOr(err, kErrCorruptBlock);
+      ebad = true;
+    }
+    // inclusive scan of (m, D) inside the half-warp: left = earlier entries, right = own accumulated map
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+      const uint32_t lm = __shfl_up_sync(0xffffffffu, m, d, 16);
+      const uint64_t l0 = __shfl_up_sync(0xffffffffu, D0, d, 16), l1 = __shfl_up_sync(0xffffffffu, D1, d, 16),
+                     l2 = __shfl_up_sync(0xffffffffu, D2, d, 16);
+      if (i >= (uint32_t)d) {
+        uint64_t M0, M1, M2;
+        key_mask(m, &M0, &M1, &M2);
+        D0 |= l0 & M0;
+        D1 |= l1 & M1;
+        D2 |= l2 & M2;
+        m = lm < m ? lm : m;
+      }
+    }
+    if (valid && !ebad) {  // the interval's first entry has shared == 0, so D is the whole key
+      uint64_t hi, lo, tr;
+      key_columns(D0, D1, D2, klen, &hi, &lo, &tr);
+      if ((tr & 0xff) > 1) atomicOr(err, kErrBadType);
+      const uint64_t e = base + ex0 + i;
+      out.pfx[e] = make_ulonglong2(hi, lo);
+      out.tr[e] = tr;
+      out.vref[e] = (uint64_t)(uintptr_t)(src + voff);
+      out.meta[e] = make_meta(klen - 8, vlen);
+    }
+  }
+  return true;
+}
+
+// Slow path straight from the image: lane per restart interval, sequential decode, regular intervals required.
+__device__ __noinline__ void decode_block_slow(const uint8_t* p, uint32_t size, uint32_t cksum, uint32_t verify, uint32_t b, int f,
+                                               const FileDesc* __restrict__ files, int nfiles, uint32_t nblk, uint64_t n_total,
+                                               KeyColsMut out, unsigned long long* blk_state, uint64_t* __restrict__ run_start,
+                                               uint64_t* __restrict__ total_out, uint32_t* __restrict__ err, unsigned lane) {
+  uint32_t cnt = 0, nr = 0, first = 0;
+  bool ok = true;
+  const uint8_t ctype = p[size];
+  if (ctype != 0) {
+    if (lane == 0) atomicOr(err, kErrCompressed);
+    ok = false;
+  }
+  if (ok && verify && cksum != 0) {
+    const uint32_t want = ld_u32(p + size + 1);
+    const uint32_t got = block_checksum_warp(cksum, p, size, ctype);
+    if (want != got) {
+      if (lane == 0) atomicOr(err, kErrChecksum);
+      ok = false;
+    }
+  }
+  if (ok) {
+    const uint32_t foot = ld_u32(p + size - 4);
+    nr = foot & 0x7fffffffu;
+    if ((foot >> 31) || nr == 0 || 4ull * nr + 4 > size) {  // data-block hash index: not produced by accepted configs
+      if (lane == 0) atomicOr(err, kErrCorruptBlock);
+      ok = false;
+      nr = 0;
+    }
+  }
+  const uint8_t* restarts = p + size - 4 - 4ull * nr;
+  const uint32_t data_end = ok ? (uint32_t)(restarts - p) : 0;
+  if (ok) {
+    uint32_t irregular = 0;
+    for (uint32_t j0 = 0; j0 < nr; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      uint32_t c = 0;
+      if (j < nr) {
+        const uint32_t r0 = ld_u32(restarts + 4ull * j);
+        const uint32_t r1 = j + 1 < nr ? ld_u32(restarts + 4ull * (j + 1)) : data_end;
+        c = (r0 <= r1 && r1 <= data_end && (j != 0 || r0 == 0)) ? count_interval(p + r0, p + r1) : 0xffffffffu;
+        if (c == 0xffffffffu) {
+          atomicOr(err, kErrCorruptBlock);
+          c = 0;
+          irregular = 1;
+        }
+      }
+      if (j0 == 0) first = __shfl_sync(0xffffffffu, c, 0);
+      if (j + 1 < nr && c != first) irregular = 1;
+      if (j + 1 == nr && c > first) irregular = 1;
+      cnt += c;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if (__ballot_sync(0xffffffffu, irregular != 0)) {
+      if (lane == 0) atomicOr(err, kErrIrregularRestarts);
+      ok = false;  // positions inside the block are not derivable
+    }
+  }
+  if (!ok) cnt = 0;  // a rejected block contributes no entries (the job fails anyway)
+  publish_block_count(blk_state, b, cnt, lane);
+  const uint64_t base = block_lookback(blk_state, b, cnt, lane);
+  if (lane == 0) record_run_starts(files, nfiles, f, b, nblk, base, cnt, run_start, total_out);
+  if (!ok || cnt == 0) return;
+  if (base + cnt > n_total) {
+    if (lane == 0) atomicOr(err, kErrCountMismatch);
+    return;
+  }
+  for (uint32_t j0 = 0; j0 < nr; j0 += 32) {
+    const uint32_t j = j0 + lane;
+    if (j < nr) {
+      const uint32_t r0 = ld_u32(restarts + 4ull * j);
+      const uint32_t r1 = j + 1 < nr ? ld_u32(restarts + 4ull * (j + 1)) : data_end;
+      decode_interval_seq(p + r0, p + r1, p, p, out, base + (uint64_t)j * first, n_total, err);
+    }
+  }
+}
+
 template <int kMinCtas>
 __global__ void __launch_bounds__(kDecWarps * 32, kMinCtas)
 block_decode_fused_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
@@ -347,275 +613,35 @@ block_decode_fused_kernel(const FileDesc* __restrict__ files, int nfiles, const 
   __shared__ uint32_t s_tk[2];
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   DecWarpSmem& ws = reinterpret_cast<DecWarpSmem*>(smem)[w];
-  constexpr uint32_t kPerTicket = kDecWarps * kDecPerTicket;
   for (int par = 0;; par ^= 1) {
     if (threadIdx.x == 0) s_tk[par] = atomicAdd(ticket, 1u);
     __syncthreads();
-    const uint64_t b_first = (uint64_t)s_tk[par] * kPerTicket;
-    if (b_first >= nblk) break;  // uniform over the CTA
-#pragma unroll 1
-    for (int it = 0; it < kDecPerTicket; it++) {
-      const uint64_t b64 = b_first + (uint64_t)it * kDecWarps + w;
-      if (b64 >= nblk) break;
-      const uint32_t b = (uint32_t)b64;
-      const int f = file_of_block(files, nfiles, b);
-      const uint8_t* src = files[f].base + blk_off[b];
-      const uint32_t size = blk_size[b], cksum = files[f].cksum;
-      const uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15;
-      const uint32_t shift = (uint32_t)((uintptr_t)src - a0);
-      const uint32_t nvec = (shift + size + 5 + 15) >> 4;
-      const bool staged = nvec <= (uint32_t)kDecVecs - 3;  // 40-byte parse windows may run 32 bytes past the trailer
-      __syncwarp();  // the previous block's readers are done with the slice
-      if (staged) {
-        const uint4* g = reinterpret_cast<const uint4*>(a0);
-        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ws.slice);
+    const uint64_t b64 = (uint64_t)s_tk[par] * kDecWarps + w;
+    if ((uint64_t)s_tk[par] * kDecWarps >= nblk) break;  // uniform over the CTA
+    if (b64 >= nblk) continue;
+    const uint32_t b = (uint32_t)b64;
+    const int f = file_of_block(files, nfiles, b);
+    const uint8_t* src = files[f].base + blk_off[b];
+    const uint32_t size = blk_size[b], cksum = files[f].cksum;
+    const uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15;
+    const uint32_t shift = (uint32_t)((uintptr_t)src - a0);
+    const uint32_t nvec = (shift + size + 5 + 15) >> 4;
+    bool done = false;
+    if (nvec <= (uint32_t)kDecVecs - 3 && size >= 8) {  // 40-byte parse windows may run 32 bytes past the trailer
+      const uint4* g = reinterpret_cast<const uint4*>(a0);
+      const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ws.slice);
 #pragma unroll
-        for (int i = 0; i < kDecPerLane; i++) {
-          const uint32_t v = lane + 32 * i;
-          if (v < nvec) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16 * v), "l"(g + v) : "memory");
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
+      for (int i = 0; i < kDecPerLane; i++) {
+        const uint32_t v = lane + 32 * i;
+        if (v < nvec) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16 * v), "l"(g + v) : "memory");
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");
       __syncwarp();
-      const uint8_t* p = staged ? reinterpret_cast<const uint8_t*>(ws.slice) + shift : src;
-      uint32_t cnt = 0, nr = 0;
-      bool ok = true;
-      const uint8_t ctype = p[size];
-      if (ctype != 0) {
-        if (lane == 0) atomicOr(err, kErrCompressed);
-        ok = false;
-      }
-      if (ok && verify && cksum != 0) {
-        const uint32_t want = ld_u32(p + size + 1);
-        const uint32_t got = block_checksum_warp(cksum, p, size, ctype);
-        if (want != got) {
-          if (lane == 0) atomicOr(err, kErrChecksum);
-          ok = false;
-        }
-      }
-      if (ok) {
-        const uint32_t foot = ld_u32(p + size - 4);
-        nr = foot & 0x7fffffffu;
-        if ((foot >> 31) || nr == 0 || 4ull * nr + 4 > size) {  // data-block hash index: not produced by accepted configs
-          if (lane == 0) atomicOr(err, kErrCorruptBlock);
-          ok = false;
-          nr = 0;
-        }
-      }
-      const uint8_t* restarts = p + size - 4 - 4ull * nr;
-      const uint32_t data_end = ok ? (uint32_t)(restarts - p) : 0;
-      // ---- walk the restart intervals
-      bool fast = ok && staged && nr <= (uint32_t)kDecRows;
-      uint32_t first = 0;  // slow path: entries per interval
-      if (fast) {
-        uint32_t c = 0;
-        bool bad = false;
-        if (lane < nr) {
-          const uint32_t r0 = ld_u32(restarts + 4ull * lane);
-          const uint32_t r1 = lane + 1 < nr ? ld_u32(restarts + 4ull * (lane + 1)) : data_end;
-          if (!(r0 <= r1 && r1 <= data_end && (lane != 0 || r0 == 0))) bad = true;
-          uint32_t q = r0;
-          while (!bad && q < r1) {
-            const uint64_t h = ld_u64_funnel(p + q);
-            uint32_t adv;
-            if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {
-              adv = 3 + (uint32_t)((h >> 8) & 0xff) + (uint32_t)((h >> 16) & 0xff);
-            } else {
-              uint64_t sh, ns, vl;
-              const uint8_t* x = p + q;
-              int c1 = get_varint(x, p + r1, &sh);
-              int c2 = c1 ? get_varint(x + c1, p + r1, &ns) : 0;
-              int c3 = c2 ? get_varint(x + c1 + c2, p + r1, &vl) : 0;
-              if (!c3 || ns + vl > (uint64_t)r1) {
-                bad = true;
-                break;
-              }
-              adv = (uint32_t)(c1 + c2 + c3) + (uint32_t)(ns + vl);
-            }
-            if (adv > r1 - q) {
-              bad = true;
-              break;
-            }
-            if (c < (uint32_t)kDecRowLen) ws.tab[lane * kDecRowLen + c] = (uint16_t)q;
-            q += adv;
-            c++;
-          }
-        }
-        if (__ballot_sync(0xffffffffu, bad)) {
-          if (lane == 0) atomicOr(err, kErrCorruptBlock);
-          ok = false;
-          fast = false;
-        } else if (__ballot_sync(0xffffffffu, c > (uint32_t)kDecRowLen)) {
-          fast = false;  // unusually long intervals: slow path below recounts
-        } else {
-          const uint32_t inc = warp_incl_scan(c);
-          ws.ex[lane] = (uint16_t)(inc - c);
-          cnt = __shfl_sync(0xffffffffu, inc, 31);
-        }
-      }
-      if (ok && !fast) {
-        uint32_t irregular = 0;
-        for (uint32_t j0 = 0; j0 < nr; j0 += 32) {
-          const uint32_t j = j0 + lane;
-          uint32_t c = 0;
-          if (j < nr) {
-            const uint32_t r0 = ld_u32(restarts + 4ull * j);
-            const uint32_t r1 = j + 1 < nr ? ld_u32(restarts + 4ull * (j + 1)) : data_end;
-            c = (r0 <= r1 && r1 <= data_end && (j != 0 || r0 == 0)) ? count_interval(p + r0, p + r1) : 0xffffffffu;
-            if (c == 0xffffffffu) {
-              atomicOr(err, kErrCorruptBlock);
-              c = 0;
-              irregular = 1;
-            }
-          }
-          if (j0 == 0) first = __shfl_sync(0xffffffffu, c, 0);
-          if (j + 1 < nr && c != first) irregular = 1;
-          if (j + 1 == nr && c > first) irregular = 1;
-          cnt += c;
-        }
-#pragma unroll
-        for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-        if (__ballot_sync(0xffffffffu, irregular != 0)) {
-          if (lane == 0) atomicOr(err, kErrIrregularRestarts);
-          ok = false;  // positions inside the block are not derivable
-        }
-      }
-      if (!ok) cnt = 0;  // a rejected block contributes no entries (the job fails anyway)
-      // ---- global position: decoupled look-back over block states
-      uint64_t base = 0;
-      {
-        const unsigned long long kAgg = 1ull << 62, kPre = 2ull << 62, kVal = (1ull << 62) - 1;
-        if (b == 0) {
-          if (lane == 0) atomicExch(&blk_state[0], kPre | cnt);
-        } else {
-          if (lane == 0) atomicExch(&blk_state[b], kAgg | cnt);
-          int64_t look = (int64_t)b - 1;
-          while (true) {
-            const int64_t idx = look - lane;
-            unsigned long long sv = kPre;  // virtual blocks before 0 contribute a zero prefix
-            if (idx >= 0) {
-              do {
-                sv = *((volatile unsigned long long*)&blk_state[idx]);
-              } while ((sv >> 62) == 0);
-            }
-            const unsigned pre_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
-            const int first_pre = pre_mask ? __ffs(pre_mask) - 1 : 32;
-            uint64_t contrib = ((int)lane <= first_pre) ? (sv & kVal) : 0;
-#pragma unroll
-            for (int dd = 16; dd; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
-            base += contrib;
-            if (pre_mask) break;
-            look -= 32;
-          }
-          if (lane == 0) atomicExch(&blk_state[b], kPre | (base + cnt));
-        }
-      }
-      if (lane == 0) {
-        // runs start where their first block starts (runs without blocks start where the next one does)
-        for (int r = f; r >= 0 && files[r].gblk_first == b; r--) run_start[r] = base;
-        if (b + 1 == nblk) {
-          for (int r = nfiles; r > f && (r == nfiles || files[r].gblk_first >= nblk); r--) run_start[r] = base + cnt;
-          *total_out = base + cnt;
-        }
-      }
-      if (!ok || cnt == 0) continue;
-      if (base + cnt > n_total) {
-        if (lane == 0) atomicOr(err, kErrCountMismatch);
-        continue;
-      }
-      if (!fast) {  // lane per interval, sequential
-        for (uint32_t j0 = 0; j0 < nr; j0 += 32) {
-          const uint32_t j = j0 + lane;
-          if (j < nr) {
-            const uint32_t r0 = ld_u32(restarts + 4ull * j);
-            const uint32_t r1 = j + 1 < nr ? ld_u32(restarts + 4ull * (j + 1)) : data_end;
-            decode_interval_seq(p + r0, p + r1, p, src, out, base + (uint64_t)j * first, n_total, err);
-          }
-        }
-        continue;
-      }
-      // ---- one entry per lane; keys by a warp scan over the prefix-decompression maps
-      __syncwarp();
-      uint64_t C0 = 0, C1 = 0, C2 = 0;  // key of the entry before this round
-      uint32_t cklen = 0, cbad = 0;
-      for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
-        const uint32_t idx = e0 + lane;
-        const bool valid = idx < cnt;
-        uint32_t m = 255, klen = 0, vlen = 0, voff = 0, shared = 0;
-        uint64_t D0 = 0, D1 = 0, D2 = 0;
-        bool bad = false;
-        if (valid) {
-          uint32_t j = 0;  // interval of entry idx: largest j < nr with ex[j] <= idx
-#pragma unroll
-          for (int st = kDecRows / 2; st; st >>= 1)
-            if (j + st < nr && ws.ex[j + st] <= idx) j += st;
-          const uint32_t q = ws.tab[j * kDecRowLen + (idx - ws.ex[j])];
-          const uint8_t* ep = p + q;
-          const Win wn = load_win_any(ep);
-          const uint32_t o = (uint32_t)((uintptr_t)ep & 7);
-          uint32_t non_shared, hdr;
-          if (!parse_header(win64(wn, o), ep, p + data_end, &shared, &non_shared, &vlen, &hdr, err)) {
-            bad = true;
-          } else if (shared + non_shared < 8) {
-            atomicOr(err, kErrCorruptBlock);
-            bad = true;
-          } else if (shared + non_shared > (uint32_t)(kMaxUserKey + 8)) {
-            atomicOr(err, kErrKeyTooLong);
-            bad = true;
-            klen = shared + non_shared;  // the successor's `shared` is still bounded by this length
-          } else {
-            const uint32_t so = o + hdr;
-            uint64_t S0 = win64(wn, so), S1 = win64(wn, so + 8), S2 = win64(wn, so + 16), M0, M1, M2;
-            key_mask(non_shared, &M0, &M1, &M2);
-            key_shift(S0 & M0, S1 & M1, S2 & M2, shared, &D0, &D1, &D2);
-            m = shared;
-            klen = shared + non_shared;
-            voff = q + hdr + non_shared;
-          }
-        }
-        // previous entry's key length bounds `shared`
-        uint32_t pk = __shfl_up_sync(0xffffffffu, klen, 1);
-        uint32_t pbad = __shfl_up_sync(0xffffffffu, (uint32_t)bad, 1);
-        if (lane == 0) pk = cklen, pbad = cbad;
-        if (valid && !bad && !pbad && shared > pk) {  // (after a rejected entry the bound is unknown: already an error)
-          atomicOr(err, kErrCorruptBlock);
-          bad = true;
-        }
-        // inclusive scan of (m, D): left = earlier entries, right = own accumulated map
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t lm = __shfl_up_sync(0xffffffffu, m, d);
-          const uint64_t l0 = __shfl_up_sync(0xffffffffu, D0, d), l1 = __shfl_up_sync(0xffffffffu, D1, d),
-                         l2 = __shfl_up_sync(0xffffffffu, D2, d);
-          if (lane >= (unsigned)d) {
-            uint64_t M0, M1, M2;
-            key_mask(m, &M0, &M1, &M2);
-            D0 |= l0 & M0;
-            D1 |= l1 & M1;
-            D2 |= l2 & M2;
-            m = lm < m ? lm : m;
-          }
-        }
-        uint64_t M0, M1, M2;
-        key_mask(m, &M0, &M1, &M2);
-        const uint64_t K0 = (C0 & M0) | D0, K1 = (C1 & M1) | D1, K2 = (C2 & M2) | D2;
-        if (valid && !bad) {
-          uint64_t hi, lo, tr;
-          key_columns(K0, K1, K2, klen, &hi, &lo, &tr);
-          if ((tr & 0xff) > 1) atomicOr(err, kErrBadType);
-          const uint64_t e = base + idx;
-          out.pfx[e] = make_ulonglong2(hi, lo);
-          out.tr[e] = tr;
-          out.vref[e] = (uint64_t)(uintptr_t)(src + voff);
-          out.meta[e] = make_meta(klen - 8, vlen);
-        }
-        C0 = __shfl_sync(0xffffffffu, K0, 31);
-        C1 = __shfl_sync(0xffffffffu, K1, 31);
-        C2 = __shfl_sync(0xffffffffu, K2, 31);
-        cklen = __shfl_sync(0xffffffffu, klen, 31);
-        cbad = __shfl_sync(0xffffffffu, (uint32_t)bad, 31);
-      }
+      done = decode_block_fast(ws, shift, src, size, cksum, verify, b, f, files, nfiles, nblk, n_total, out, blk_state, run_start,
+                               total_out, err, lane);
+      __syncwarp();  // all lanes are done with the slice before the next block overwrites it
     }
+    if (!done) decode_block_slow(src, size, cksum, verify, b, f, files, nfiles, nblk, n_total, out, blk_state, run_start, total_out, err, lane);
   }
 }
 
@@ -651,7 +677,7 @@ void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint
     cudaFuncSetAttribute(block_decode_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(block_decode_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   }
-  const unsigned per = kDecWarps * kDecPerTicket;
+  const unsigned per = kDecWarps;  // one block per warp and ticket: more would chain CTAs through the look-back
   unsigned want = (nblk + per - 1) / per, cap = (unsigned)sms * (unsigned)occ;
   const unsigned grid = want < cap ? (want ? want : 1) : cap;
 #define B200C_LAUNCH_DEC(N)                                                                                                       \
