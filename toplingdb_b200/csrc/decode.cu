@@ -378,54 +378,123 @@ __device__ __forceinline__ void record_run_starts(const FileDesc* __restrict__ f
   }
 }
 
+// ---- explicit shared-memory accesses by 32-bit shared address (keeps the hot loops free of generic 64-bit addressing)
+__device__ __forceinline__ uint64_t lds64(uint32_t a) {
+  uint64_t v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// 4 / 8 bytes at any alignment (reads up to 7 bytes past the value, inside the slice)
+__device__ __forceinline__ uint32_t lds32_any(uint32_t a) {
+  const uint32_t al = a & ~3u;
+  return __funnelshift_r(lds32(al), lds32(al + 4), (a & 3) * 8);
+}
+__device__ __forceinline__ uint64_t shr128(uint64_t lo, uint64_t hi, uint32_t s) {  // (hi:lo) >> s, s in {0, 8, .., 56}
+  return s ? (lo >> s) | (hi << (64 - s)) : lo;
+}
+__device__ __forceinline__ uint64_t lds64_any(uint32_t a) {
+  const uint32_t al = a & ~7u;
+  return shr128(lds64(al), lds64(al + 8), (a & 7) * 8);
+}
+// entry header from its first 8 bytes; false when the three varints need more than 8 bytes or exceed the device format
+__device__ __forceinline__ bool parse_header8(uint64_t h, uint32_t* shared, uint32_t* non_shared, uint32_t* vlen, uint32_t* hdr) {
+  if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {  // DecodeEntry fast path (block.cc:44-50): three one-byte lengths
+    *shared = (uint32_t)(h & 0xff);
+    *non_shared = (uint32_t)((h >> 8) & 0xff);
+    *vlen = (uint32_t)((h >> 16) & 0xff);
+    *hdr = 3;
+    return true;
+  }
+  uint32_t k = 0, v[3];
+  bool ok = true;
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    uint32_t x = 0, sft = 0;
+    for (;;) {
+      if (k >= 8 || sft > 28) {
+        ok = false;
+        break;
+      }
+      const uint32_t c = (uint32_t)((h >> (8 * k)) & 0xff);
+      k++;
+      x |= (c & 127) << sft;
+      if (c < 128) break;
+      sft += 7;
+    }
+    v[q] = x;
+  }
+  *shared = v[0];
+  *non_shared = v[1];
+  *vlen = v[2];
+  *hdr = k;
+  return ok && v[2] <= kMetaVlenMask;
+}
+// masks of the first m (0..24) key bytes, as a table in shared memory: [m][3]
+__device__ __forceinline__ void fill_key_mask_table(uint64_t* tab) {
+  for (uint32_t i = threadIdx.x; i < 25 * 3; i += blockDim.x) {
+    const uint32_t m = i / 3, wd = i % 3;
+    const uint32_t nb = m > 8 * wd ? (m - 8 * wd > 8 ? 8 : m - 8 * wd) : 0;
+    tab[i] = low_bytes_mask(nb);
+  }
+}
+
 // Fast path for a block staged in the warp's slice at byte `shift`.  Returns false (nothing published) when the block
-// is outside the fast path's limits and has to take decode_block_slow.
-__device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t shift, const uint8_t* src, uint32_t size, uint32_t cksum,
-                                                  uint32_t verify, uint32_t b, int f, const FileDesc* __restrict__ files, int nfiles,
-                                                  uint32_t nblk, uint64_t n_total, KeyColsMut out, unsigned long long* blk_state,
-                                                  uint64_t* __restrict__ run_start, uint64_t* __restrict__ total_out,
-                                                  uint32_t* __restrict__ err, unsigned lane) {
-  const uint8_t* p = reinterpret_cast<const uint8_t*>(ws.slice) + shift;  // shared memory: 32-bit addressing throughout
-  const uint32_t foot = ld_u32(p + size - 4);
+// is outside the fast path's limits (restart intervals / entries per interval / header length) and has to take
+// decode_block_slow.
+__device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t mask_tab, uint32_t shift, const uint8_t* src, uint32_t size,
+                                                  uint32_t cksum, uint32_t verify, uint32_t b, int f, const FileDesc* __restrict__ files,
+                                                  int nfiles, uint32_t nblk, uint64_t n_total, KeyColsMut out,
+                                                  unsigned long long* blk_state, uint64_t* __restrict__ run_start,
+                                                  uint64_t* __restrict__ total_out, uint32_t* __restrict__ err, unsigned lane) {
+  const uint32_t sp = (uint32_t)__cvta_generic_to_shared(ws.slice) + shift;  // shared address of the block's first byte
+  const uint32_t stab = (uint32_t)__cvta_generic_to_shared(ws.tab), sex = (uint32_t)__cvta_generic_to_shared(ws.ex);
+  const uint32_t foot = lds32_any(sp + size - 4);
   const uint32_t nr = foot & 0x7fffffffu;
   if ((foot >> 31) || nr == 0 || nr > (uint32_t)kDecRows || 4 * nr + 4 > size) return false;
-  const uint8_t* restarts = p + size - 4 - 4 * nr;
   const uint32_t data_end = size - 4 - 4 * nr;
+  const uint32_t srest = sp + data_end;
   // ---- walk the restart intervals, one lane each, recording entry offsets
   uint32_t c = 0;
-  bool bad = false;
+  bool bad = false, exotic = false;
   if (lane < nr) {
-    const uint32_t r0 = ld_u32(restarts + 4 * lane);
-    const uint32_t r1 = lane + 1 < nr ? ld_u32(restarts + 4 * (lane + 1)) : data_end;
+    const uint32_t r0 = lds32_any(srest + 4 * lane);
+    const uint32_t r1 = lane + 1 < nr ? lds32_any(srest + 4 * (lane + 1)) : data_end;
     if (!(r0 <= r1 && r1 <= data_end && (lane != 0 || r0 == 0))) bad = true;
     uint32_t q = r0;
     while (!bad && q < r1) {
-      const uint64_t h = ld_u64_funnel(p + q);
+      const uint64_t h = lds64_any(sp + q);
       uint32_t adv;
       if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {
         adv = 3 + (uint32_t)((h >> 8) & 0xff) + (uint32_t)((h >> 16) & 0xff);
       } else {
-        uint64_t sh, ns, vl;
-        const uint8_t* x = p + q;
-        int c1 = get_varint(x, p + r1, &sh);
-        int c2 = c1 ? get_varint(x + c1, p + r1, &ns) : 0;
-        int c3 = c2 ? get_varint(x + c1 + c2, p + r1, &vl) : 0;
-        if (!c3 || ns + vl > (uint64_t)r1) {
-          bad = true;
+        uint32_t sh, ns, vl, hd;
+        if (!parse_header8(h, &sh, &ns, &vl, &hd)) {
+          exotic = true;
           break;
         }
-        adv = (uint32_t)(c1 + c2 + c3) + (uint32_t)(ns + vl);
+        adv = hd + ns + vl;
       }
       if (adv > r1 - q) {
         bad = true;
         break;
       }
-      if (c < (uint32_t)kDecRowLen) ws.tab[lane * kDecRowLen + c] = (uint16_t)q;
+      if (c < (uint32_t)kDecRowLen) sts16(stab + 2 * (lane * kDecRowLen + c), q);
       q += adv;
       c++;
     }
   }
-  if (__ballot_sync(0xffffffffu, !bad && c > (uint32_t)kDecRowLen)) return false;  // unusually long intervals
+  if (__ballot_sync(0xffffffffu, exotic || (!bad && c > (uint32_t)kDecRowLen))) return false;  // unusual block: slow path
   bool ok = true;
   if (__ballot_sync(0xffffffffu, bad)) {
     if (lane == 0) atomicOr(err, kErrCorruptBlock);
@@ -433,19 +502,22 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t shif
     c = 0;
   }
   const uint32_t inc = warp_incl_scan(c);
-  uint32_t cnt = __shfl_sync(0xffffffffu, inc, 31);
-  if (lane <= nr) ws.ex[lane] = (uint16_t)(inc - c);  // ex[nr] = cnt
-  publish_block_count(blk_state, b, cnt, lane);      // successors can look back while this warp checksums
-  const uint8_t ctype = p[size];
-  if (ctype != 0) {
-    if (lane == 0) atomicOr(err, kErrCompressed);
-    ok = false;
-  } else if (verify && cksum != 0) {
-    const uint32_t want = ld_u32(p + size + 1);
-    const uint32_t got = block_checksum_warp(cksum, p, size, ctype);
-    if (want != got) {
-      if (lane == 0) atomicOr(err, kErrChecksum);
+  const uint32_t cnt = __shfl_sync(0xffffffffu, inc, 31);
+  if (lane <= nr) sts16(sex + 2 * lane, inc - c);  // ex[nr] = cnt
+  publish_block_count(blk_state, b, cnt, lane);    // successors can look back while this warp checksums
+  {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(ws.slice) + shift;
+    const uint8_t ctype = p[size];
+    if (ctype != 0) {
+      if (lane == 0) atomicOr(err, kErrCompressed);
       ok = false;
+    } else if (verify && cksum != 0) {
+      const uint32_t want = lds32_any(sp + size + 1);
+      const uint32_t got = block_checksum_warp(cksum, p, size, ctype);
+      if (want != got) {
+        if (lane == 0) atomicOr(err, kErrChecksum);
+        ok = false;
+      }
     }
   }
   const uint64_t base = block_lookback(blk_state, b, cnt, lane);
@@ -459,20 +531,20 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t shif
   // ---- one entry per lane, one restart interval per half-warp; keys by a segmented scan over the decompression maps
   for (uint32_t row0 = 0; row0 < nr; row0 += 2) {
     const uint32_t row = row0 + (lane >> 4), i = lane & 15;
-    const uint32_t ex0 = row < nr ? ws.ex[row] : 0, rc = row < nr ? ws.ex[row + 1] - ex0 : 0;
+    uint32_t ex0 = 0, rc = 0;
+    if (row < nr) {
+      ex0 = lds16(sex + 2 * row);
+      rc = lds16(sex + 2 * row + 2) - ex0;
+    }
     const bool valid = i < rc;
-    uint32_t m = 255, klen = 0, vlen = 0, voff = 0, shared = 0;
+    uint32_t m = 24, klen = 0, vlen = 0, voff = 0, shared = 0;
     uint64_t D0 = 0, D1 = 0, D2 = 0;
     bool ebad = false;
     if (valid) {
-      const uint32_t q = ws.tab[row * kDecRowLen + i];
-      const uint8_t* ep = p + q;
-      const Win wn = load_win_any(ep);
-      const uint32_t o = (uint32_t)((shift + q) & 7);  // the slice is 16-byte aligned
+      const uint32_t q = lds16(stab + 2 * (row * kDecRowLen + i));
       uint32_t non_shared, hdr;
-      if (!parse_header(win64(wn, o), ep, p + data_end, &shared, &non_shared, &vlen, &hdr, err)) {
-        ebad = true;
-      } else if (shared + non_shared < 8) {
+      parse_header8(lds64_any(sp + q), &shared, &non_shared, &vlen, &hdr);  // validated by the walk
+      if (shared + non_shared < 8) {
         atomicOr(err, kErrCorruptBlock);
         ebad = true;
       } else if (shared + non_shared > (uint32_t)(kMaxUserKey + 8)) {
@@ -480,10 +552,12 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t shif
         ebad = true;
         klen = shared + non_shared;  // the successor's `shared` is still bounded by this length
       } else {
-        const uint32_t so = o + hdr;
-        uint64_t S0 = win64(wn, so), S1 = win64(wn, so + 8), S2 = win64(wn, so + 16), M0, M1, M2;
-        key_mask(non_shared, &M0, &M1, &M2);
-        key_shift(S0 & M0, S1 & M1, S2 & M2, shared, &D0, &D1, &D2);
+        // key suffix: non_shared (<= 24) bytes after the header, from four aligned words
+        const uint32_t ks = sp + q + hdr, al = ks & ~7u, sft = (ks & 7) * 8;
+        const uint64_t A0 = lds64(al), A1 = lds64(al + 8), A2 = lds64(al + 16), A3 = lds64(al + 24);
+        const uint32_t mt = mask_tab + 24 * non_shared;
+        key_shift(shr128(A0, A1, sft) & lds64(mt), shr128(A1, A2, sft) & lds64(mt + 8), shr128(A2, A3, sft) & lds64(mt + 16), shared, &D0,
+                  &D1, &D2);
         m = shared;
         klen = shared + non_shared;
         voff = q + hdr + non_shared;
@@ -504,11 +578,10 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t shif
       const uint64_t l0 = __shfl_up_sync(0xffffffffu, D0, d, 16), l1 = __shfl_up_sync(0xffffffffu, D1, d, 16),
                      l2 = __shfl_up_sync(0xffffffffu, D2, d, 16);
       if (i >= (uint32_t)d) {
-        uint64_t M0, M1, M2;
-        key_mask(m, &M0, &M1, &M2);
-        D0 |= l0 & M0;
-        D1 |= l1 & M1;
-        D2 |= l2 & M2;
+        const uint32_t mt = mask_tab + 24 * m;
+        D0 |= l0 & lds64(mt);
+        D1 |= l1 & lds64(mt + 8);
+        D2 |= l2 & lds64(mt + 16);
         m = lm < m ? lm : m;
       }
     }
@@ -611,8 +684,11 @@ block_decode_fused_kernel(const FileDesc* __restrict__ files, int nfiles, const 
                           uint64_t* __restrict__ total_out, uint32_t* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_tk[2];
+  __shared__ uint64_t s_mask[25 * 3];
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   DecWarpSmem& ws = reinterpret_cast<DecWarpSmem*>(smem)[w];
+  fill_key_mask_table(s_mask);
+  const uint32_t mask_tab = (uint32_t)__cvta_generic_to_shared(s_mask);
   for (int par = 0;; par ^= 1) {
     if (threadIdx.x == 0) s_tk[par] = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -637,7 +713,7 @@ block_decode_fused_kernel(const FileDesc* __restrict__ files, int nfiles, const 
       }
       asm volatile("cp.async.wait_all;" ::: "memory");
       __syncwarp();
-      done = decode_block_fast(ws, shift, src, size, cksum, verify, b, f, files, nfiles, nblk, n_total, out, blk_state, run_start,
+      done = decode_block_fast(ws, mask_tab, shift, src, size, cksum, verify, b, f, files, nfiles, nblk, n_total, out, blk_state, run_start,
                                total_out, err, lane);
       __syncwarp();  // all lanes are done with the slice before the next block overwrites it
     }
