@@ -425,6 +425,26 @@ __device__ inline uint32_t block_checksum_warp(uint32_t type, const uint8_t* dat
 }
 
 // ---- warp scans ---------------------------------------------------------------------------------------------
+// Cooperative global -> shared copy with kDepth loads per thread in flight: a plain `dst[i] = src[i]` loop issues in
+// order, so each iteration would wait for its own DRAM round trip before the next load leaves.
+template <typename T, int kDepth = 8>
+__device__ __forceinline__ void coop_copy(T* __restrict__ dst, const T* __restrict__ src, uint32_t n) {
+  const uint32_t nt = blockDim.x;
+  for (uint32_t base = 0; base < n; base += kDepth * nt) {
+    T v[kDepth];
+#pragma unroll
+    for (int k = 0; k < kDepth; k++) {
+      const uint32_t i = base + k * nt + threadIdx.x;
+      if (i < n) v[k] = src[i];
+    }
+#pragma unroll
+    for (int k = 0; k < kDepth; k++) {
+      const uint32_t i = base + k * nt + threadIdx.x;
+      if (i < n) dst[i] = v[k];
+    }
+  }
+}
+
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
   const unsigned lane = threadIdx.x & 31;
 #pragma unroll

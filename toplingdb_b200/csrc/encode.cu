@@ -97,27 +97,47 @@ __device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, c
                              uint32_t R) {
   const uint64_t wstart = tile * (uint64_t)kTT;
   const uint32_t wlen = (uint32_t)((n - wstart) < (uint64_t)kW ? (n - wstart) : (uint64_t)kW);
-  // consecutive entries per thread; an ODD count keeps the blocked shared-memory accesses conflict-free (24 would put
-  // the lanes of a warp on only four banks)
+  // 1) coalesced load of the three size columns, eight entries per thread in flight at a time (a load-use loop body
+  //    would cost one DRAM round trip per iteration); s1 is parked in P[j + 1], the restart surcharge D goes to Q[j]
+  uint32_t mx = 0;
+  if (threadIdx.x == 0) w.smax = 0;
+  constexpr int kBatch = 8;
+  for (uint32_t jb = 0; jb < wlen; jb += kBatch * kEncThreads) {
+    uint32_t s1v[kBatch], shv[kBatch], mtv[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; i++) {
+      const uint32_t j = jb + i * kEncThreads + threadIdx.x;
+      s1v[i] = shv[i] = mtv[i] = 0;
+      if (j < wlen) {
+        s1v[i] = esz[wstart + j];
+        shv[i] = eshared[wstart + j];
+        mtv[i] = m.meta[wstart + j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; i++) {
+      const uint32_t j = jb + i * kEncThreads + threadIdx.x;
+      if (j < wlen) {
+        const uint32_t sh = shv[i], ks = meta_ulen(mtv[i]) + 8;
+        // D = s0 - s1 with s0 = encoded size when shared == 0
+        const uint32_t d = 1u + varint_len32(ks) + sh - varint_len32(sh) - varint_len32(ks - sh);
+        w.Q[j] = d;
+        w.P[j + 1] = s1v[i];
+        mx = s1v[i] + d > mx ? s1v[i] + d : mx;
+      }
+    }
+  }
+  __syncthreads();
+  // 2) blocked exclusive scan of s1: consecutive entries per thread; an ODD count keeps the blocked shared-memory
+  //    accesses conflict-free (24 would put the lanes of a warp on only four banks)
   constexpr int kPer = ((kW + kEncThreads - 1) / kEncThreads) | 1;  // 25
   const uint32_t j0 = threadIdx.x * kPer;
   uint64_t loc[kPer], sum = 0;
-  uint32_t mx = 0;
-  if (threadIdx.x == 0) w.smax = 0;
 #pragma unroll
   for (int i = 0; i < kPer; i++) {
-    uint32_t j = j0 + i;
-    uint32_t s1 = 0;
-    if (j < wlen) {
-      s1 = esz[wstart + j];
-      uint32_t sh = eshared[wstart + j], ks = meta_ulen(m.meta[wstart + j]) + 8;
-      // D = s0 - s1 with s0 = encoded size when shared == 0
-      const uint32_t d = 1u + varint_len32(ks) + sh - varint_len32(sh) - varint_len32(ks - sh);
-      w.Q[j] = d;
-      mx = s1 + d > mx ? s1 + d : mx;
-    }
-    loc[i] = s1;
-    sum += s1;
+    const uint32_t j = j0 + i;
+    loc[i] = j < wlen ? w.P[j + 1] : 0;
+    sum += loc[i];
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
@@ -507,7 +527,7 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
       const uint32_t cnt = (uint32_t)((total - ridx) < cache_rows ? (total - ridx) : cache_rows);
       const uint4* src = reinterpret_cast<const uint4*>((req == 2 ? wk.grows : wk.rows) + ridx * hc);
       uint4* dst = reinterpret_cast<uint4*>(req == 2 ? gcache : tcache);
-      for (uint64_t i = threadIdx.x; i < (uint64_t)cnt * hc; i += kEncThreads) dst[i] = src[i];
+      coop_copy<uint4, 8>(dst, src, cnt * hc);
       if (threadIdx.x == 0) {
         if (req == 2) {
           s.ga = ridx;
@@ -520,10 +540,8 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
     } else if (req == 1) {
       const uint64_t tstart = ridx * (uint64_t)kTT;
       const uint32_t tl = (uint32_t)(((tstart + kTT) < n ? (tstart + kTT) : n) - tstart);
-      for (uint32_t j = threadIdx.x; j < tl; j += kEncThreads) {
-        s.nxt[j] = wk.nxt[tstart + j];
-        s.disk[j] = wk.disk[tstart + j];
-      }
+      coop_copy<uint16_t, 16>(s.nxt, wk.nxt + tstart, tl);
+      coop_copy<uint32_t, 16>(s.disk, wk.disk + tstart, tl);
       __syncthreads();
       if (threadIdx.x == 0) {
         WalkState st = s.st;
