@@ -77,9 +77,11 @@ def reference_arm(args, rank, world):
     import cpu_baseline as CB
     w = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
+    # one process per host core, each compacting its own key range of >= 16 MiB raw KV (smaller jobs measure start-up)
+    sample = max(args.sample_mb << 20, cores * (16 << 20))
     res = []
     for _ in range(max(1, args.warmup > 0) + args.steps):
-        res.append(CB.run_sample(w, sample_bytes=args.sample_mb << 20, threads=cores))
+        res.append(CB.run_sample(w, sample_bytes=sample, threads=cores))
     res = res[1:] if len(res) > args.steps else res
     mbps = statistics.mean(r["mbps"] for r in res)
     line = {"impl": "reference", "metric": "compaction_input_kv_MB_per_s", "value": mbps, "unit": "MB/s", "n_gpus": args.gpus,
@@ -102,6 +104,7 @@ def main():
     ap.add_argument("--sample-mb", type=int, default=192, help="raw KV MiB of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="compaction jobs in flight in the end-to-end measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -227,11 +230,11 @@ def main():
         job.close()
         del images
         torch.cuda.empty_cache()
-        # Two jobs in flight (two host threads, each job on its own stream): the upload of one job overlaps the download
+        # Several jobs in flight (one host thread per job, each job on its own stream): the upload of one job overlaps the download
         # of the other, as concurrent background compactions do (max_background_compactions > 1).  Every step still does
         # its own H2D of the inputs and D2H of the outputs inside the timed region.
         import threading
-        depth = 2
+        depth = max(1, args.e2e_depth)
         ejs = [T.CompactionJob(output_mem="host", **common) for _ in range(depth)]
         for ej in ejs:
             for i, img in enumerate(host_imgs):
@@ -243,7 +246,7 @@ def main():
         _ = ejs[0].stats().num_output_records
         barrier()
         single_s = time.perf_counter() - t0
-        per_thread = max(2, (min(args.steps, 6) + depth - 1) // depth)
+        per_thread = max(2, (min(args.steps, 6) + depth - 1) // depth)  # every job runs at least twice in the timed region
         esteps = per_thread * depth
         errs = []
 

@@ -47,6 +47,7 @@ struct Opts {
   uint32_t format_version = 5;
   int keep_db = 0;
   int paranoid = 0;
+  int copy = 1;  // 0: leave inputs/ and outputs/ empty (timing runs only need the manifest)
   std::string executor;  // "b200": route the job through the B200 CompactionExecutor plugin (ref_compact_b200 build only)
 };
 
@@ -128,6 +129,7 @@ int main(int argc, char** argv) {
     else if (k == "keep_db") o.keep_db = atoi(v.c_str());
     else if (k == "paranoid") o.paranoid = atoi(v.c_str());
     else if (k == "executor") o.executor = v;
+    else if (k == "copy") o.copy = atoi(v.c_str());
     else {
       fprintf(stderr, "ref_compact: unknown option %s\n", k.c_str());
       return 1;
@@ -294,7 +296,8 @@ int main(int argc, char** argv) {
     fprintf(stderr, "ref_compact: no L0 files to compact\n");
     return 2;
   }
-  for (auto& fm : inputs) CopyFile(dbdir + fm.name, work + "/inputs" + fm.name);
+  if (o.copy)
+    for (auto& fm : inputs) CopyFile(dbdir + fm.name, work + "/inputs" + fm.name);
 
   CompactionOptions co;
   co.compression = kNoCompression;
@@ -371,7 +374,7 @@ int main(int argc, char** argv) {
       for (auto& fm : lvl.files) outs.push_back(fm);
   for (size_t i = 0; i < outs.size(); i++) {
     auto& fm = outs[i];
-    CopyFile(dbdir + fm.name, work + "/outputs" + fm.name);
+    if (o.copy) CopyFile(dbdir + fm.name, work + "/outputs" + fm.name);
     fprintf(m,
             "    {\"name\": \"%s\", \"size\": %" PRIu64 ", \"file_number\": %" PRIu64
             ", \"smallest_seqno\": %" PRIu64 ", \"largest_seqno\": %" PRIu64 ", \"num_entries\": %" PRIu64

@@ -68,7 +68,7 @@ def run_sample(w, sample_bytes, threads):
                 _ops_file(os.path.join(d, str(t), "ops.bin"), w, per, seed=2 + t)
             for t in range(threads):
                 procs.append(subprocess.Popen([REF_BIN, os.path.join(d, str(t), "ops.bin"), os.path.join(d, str(t), "w"),
-                                               "output_level=1", "max_subcompactions=1", "target_file_size=67108864"],
+                                               "output_level=1", "max_subcompactions=1", "target_file_size=67108864", "copy=0"],
                                               stdout=subprocess.DEVNULL))
             for pr in procs:
                 if pr.wait() != 0:

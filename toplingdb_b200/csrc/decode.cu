@@ -457,8 +457,11 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t mask
                                                   int nfiles, uint32_t nblk, uint64_t n_total, KeyColsMut out,
                                                   unsigned long long* blk_state, uint64_t* __restrict__ run_start,
                                                   uint64_t* __restrict__ total_out, uint32_t* __restrict__ err, unsigned lane) {
-  const uint32_t sp = (uint32_t)__cvta_generic_to_shared(ws.slice) + shift;  // shared address of the block's first byte
-  const uint32_t stab = (uint32_t)__cvta_generic_to_shared(ws.tab), sex = (uint32_t)__cvta_generic_to_shared(ws.ex);
+  // shared addresses of the block's first byte, the offset table and the interval prefix.  The empty asm makes them opaque:
+  // under register pressure the compiler otherwise re-derives them (S2R + address arithmetic) inside the hot loops
+  uint32_t sp = (uint32_t)__cvta_generic_to_shared(ws.slice) + shift;
+  uint32_t stab = (uint32_t)__cvta_generic_to_shared(ws.tab), sex = (uint32_t)__cvta_generic_to_shared(ws.ex);
+  asm volatile("" : "+r"(sp), "+r"(stab), "+r"(sex), "+r"(mask_tab));
   const uint32_t foot = lds32_any(sp + size - 4);
   const uint32_t nr = foot & 0x7fffffffu;
   if ((foot >> 31) || nr == 0 || nr > (uint32_t)kDecRows || 4 * nr + 4 > size) return false;
@@ -473,13 +476,13 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t mask
     if (!(r0 <= r1 && r1 <= data_end && (lane != 0 || r0 == 0))) bad = true;
     uint32_t q = r0;
     while (!bad && q < r1) {
-      const uint64_t h = lds64_any(sp + q);
+      const uint32_t h4 = lds32_any(sp + q);  // the common header is three one-byte lengths
       uint32_t adv;
-      if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {
-        adv = 3 + (uint32_t)((h >> 8) & 0xff) + (uint32_t)((h >> 16) & 0xff);
+      if ((h4 & 0x808080u) == 0) {
+        adv = 3 + ((h4 >> 8) & 0xff) + ((h4 >> 16) & 0xff);
       } else {
         uint32_t sh, ns, vl, hd;
-        if (!parse_header8(h, &sh, &ns, &vl, &hd)) {
+        if (!parse_header8(lds64_any(sp + q), &sh, &ns, &vl, &hd)) {
           exotic = true;
           break;
         }

@@ -920,6 +920,28 @@ __device__ __forceinline__ void key_suffix_words(uint64_t hi, uint64_t lo, uint3
   *S1 = bs ? (B >> bs) | (Cw << (64 - bs)) : B;
   *S2 = Cw >> bs;
 }
+// L (<= 27) bytes held in seven little-endian words w[0..7) (w[7] must be 0) to an arbitrarily aligned shared-memory
+// address: at most 3 head bytes, aligned 32-bit stores, at most 3 tail bytes -- instead of one store per byte
+__device__ __forceinline__ void store_stream28(uint8_t* p, const uint32_t* w, uint32_t L) {
+  uint32_t head = (4 - (uint32_t)((uintptr_t)p & 3)) & 3;
+  if (head > L) head = L;
+  if (head > 0) p[0] = (uint8_t)w[0];
+  if (head > 1) p[1] = (uint8_t)(w[0] >> 8);
+  if (head > 2) p[2] = (uint8_t)(w[0] >> 16);
+  const uint32_t bs = head * 8, nwords = (L - head) >> 2;
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(p + head);
+  uint32_t tailv = 0;
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    const uint32_t v = __funnelshift_r(w[k], w[k + 1], bs);
+    if ((uint32_t)k < nwords) d32[k] = v;
+    if ((uint32_t)k == nwords) tailv = v;
+  }
+  const uint32_t done = head + 4 * nwords, rem = L - done;
+  if (rem > 0) p[done] = (uint8_t)tailv;
+  if (rem > 1) p[done + 1] = (uint8_t)(tailv >> 8);
+  if (rem > 2) p[done + 2] = (uint8_t)(tailv >> 16);
+}
 // n (<= 24) bytes of (S0, S1, S2) to an arbitrarily aligned (shared-memory) address
 __device__ __forceinline__ void store_bytes24(uint8_t* p, uint64_t S0, uint64_t S1, uint64_t S2, uint32_t n) {
 #pragma unroll
@@ -1162,20 +1184,23 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
           const uint32_t off = (uint32_t)(cum[i] - s.cum0[q]);
           uint8_t* p = img + off;
           const uint32_t ks = ul + 8;
+          uint64_t S0, S1, S2;
+          key_suffix_words(ppv[i].x, ppv[i].y, ul, trv[i], sh, &S0, &S1, &S2);
           if ((sh | (ks - sh) | vs[i]) < 128) {
-            p[0] = (uint8_t)sh;
-            p[1] = (uint8_t)(ks - sh);
-            p[2] = (uint8_t)vs[i];
-            p += 3;
+            // three one-byte lengths + key suffix as one 27-byte stream
+            const uint64_t hdr = (uint64_t)sh | ((uint64_t)(ks - sh) << 8) | ((uint64_t)vs[i] << 16);
+            const uint64_t W0 = hdr | (S0 << 24), W1 = (S0 >> 40) | (S1 << 24), W2 = (S1 >> 40) | (S2 << 24), W3 = S2 >> 40;
+            const uint32_t wv[8] = {(uint32_t)W0, (uint32_t)(W0 >> 32), (uint32_t)W1, (uint32_t)(W1 >> 32),
+                                    (uint32_t)W2, (uint32_t)(W2 >> 32), (uint32_t)W3, 0u};
+            store_stream28(p, wv, 3 + ks - sh);
+            p += 3 + ks - sh;
           } else {
             p += put_varint(p, sh);
             p += put_varint(p, ks - sh);
             p += put_varint(p, vs[i]);
+            store_bytes24(p, S0, S1, S2, ks - sh);
+            p += ks - sh;
           }
-          uint64_t S0, S1, S2;
-          key_suffix_words(ppv[i].x, ppv[i].y, ul, trv[i], sh, &S0, &S1, &S2);
-          store_bytes24(p, S0, S1, S2, ks - sh);
-          p += ks - sh;
           voff[i] = (uint32_t)(p - img0);
           if (pk[i] >> 16) {
             const uint32_t jj = x - s.first_rel[q];

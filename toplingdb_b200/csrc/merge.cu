@@ -131,8 +131,6 @@ struct TileSmem {
   uint32_t tile_id, kept_total;
   Key pred;
   uint32_t has_pred;
-  Key cand[kMaxRuns];              // last element before the split, per run
-  uint32_t cand_ok[kMaxRuns];
 };
 
 __device__ __forceinline__ Key skey(const TileSmem& s, uint32_t id) {
@@ -143,14 +141,21 @@ __device__ __forceinline__ Key skey(const TileSmem& s, uint32_t id) {
   k.ulen = s.ulen[id];
   return k;
 }
-// is key b (load position ib, high word hb) strictly before key a?
-__device__ __forceinline__ bool id_less(const TileSmem& s, uint32_t ib, uint64_t hb, uint32_t ia, uint64_t ha) {
-  if (hb != ha) return hb < ha;
+// List positions are XOR-swizzled inside 16-element groups: a thread owns kMV = 8 consecutive list positions, and with
+// the plain layout the 32 lanes of one store to idx[] would fall on only eight banks (4-way conflict).
+__device__ __forceinline__ uint32_t PH(uint32_t e) { return e ^ ((e >> 4) & 15u); }
+// keys with equal high words: is the key at load position ib strictly before the one at ia?
+__device__ __forceinline__ bool tie_less(const TileSmem& s, uint32_t ib, uint32_t ia) {
   const uint64_t lb = s.lo[ib], la = s.lo[ia];
   if (lb != la) return lb < la;
   const uint32_t ub = s.ulen[ib], ua = s.ulen[ia];
   if (ub != ua) return ub < ua;
   return s.tr[ib] > s.tr[ia];
+}
+// is key b (load position ib, high word hb) strictly before key a?
+__device__ __forceinline__ bool id_less(const TileSmem& s, uint32_t ib, uint64_t hb, uint32_t ia, uint64_t ha) {
+  if (hb != ha) return hb < ha;
+  return tie_less(s, ib, ia);
 }
 
 struct PairState {
@@ -180,7 +185,7 @@ __device__ __noinline__ void init_pair(const TileSmem& s, const uint32_t* lst, u
   uint32_t lo = diag > bn ? diag - bn : 0, hi = diag < an ? diag : an;
   while (lo < hi) {
     uint32_t mid = (lo + hi) >> 1;
-    const uint32_t ia = s.idx[a0 + mid], ib = s.idx[a1 + diag - 1 - mid];
+    const uint32_t ia = s.idx[PH(a0 + mid)], ib = s.idx[PH(a1 + diag - 1 - mid)];
     if (!id_less(s, ib, s.hi[ib], ia, s.hi[ia])) lo = mid + 1;  // a <= b: a goes first (stable, lower run index wins ties)
     else hi = mid;
   }
@@ -258,6 +263,9 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   __syncthreads();
   const uint64_t tile = s.tile_id;
   if (tile >= ntiles) return;
+  // last element before the split, per run: staged in arrays the load phase overwrites later (keeps 3 CTAs per SM)
+  Key* cand = reinterpret_cast<Key*>(s.hi);
+  uint32_t* cand_ok = reinterpret_cast<uint32_t*>(s.idx);
   // ---- segment table; the tile's predecessor in merged order (= largest element before the split) is fetched here
   // too, one lane per run, so its DRAM round trip overlaps the split loads
   if (t < k) {
@@ -265,8 +273,8 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     const uint64_t b0 = run_start[t] + s0;
     s.sbeg[t] = b0;
     s.lst[1][t] = (uint32_t)(s1 - s0);  // lengths, scanned below
-    s.cand_ok[t] = s0 != 0;
-    if (s0 != 0) s.cand[t] = load_key(in, b0 - 1);
+    cand_ok[t] = s0 != 0;
+    if (s0 != 0) cand[t] = load_key(in, b0 - 1);
   }
   __syncthreads();
   if (t == 0) {
@@ -284,8 +292,8 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     }
     s.has_pred = 0;
     for (uint32_t r = 0; r < k; r++) {
-      if (!s.cand_ok[r]) continue;
-      const Key e = s.cand[r];
+      if (!cand_ok[r]) continue;
+      const Key e = cand[r];
       if (!s.has_pred || ikey_less(s.pred, e)) {
         s.pred = e;
         s.has_pred = 1;
@@ -314,6 +322,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     ulonglong2 lp[kMV];
     uint64_t ltr[kMV];
     uint32_t lmt[kMV];
+    uint32_t lr = 0;
 #pragma unroll
     for (int j = 0; j < kMV; j++) {
       const uint32_t i = t + j * kMThreads;
@@ -321,13 +330,8 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       ltr[j] = 0;
       lmt[j] = 0;
       if (i < cnt) {
-        uint32_t lo = 0, hi = k;  // run r with seg[r] <= i < seg[r+1]
-        while (hi - lo > 1) {
-          uint32_t mid = (lo + hi) >> 1;
-          if (s.seg[mid] <= i) lo = mid;
-          else hi = mid;
-        }
-        const uint64_t src = s.sbeg[lo] + (i - s.seg[lo]);
+        while (i >= s.seg[lr + 1]) lr++;  // run with seg[lr] <= i < seg[lr + 1]; i grows with j, so the walk only moves forward
+        const uint64_t src = s.sbeg[lr] + (i - s.seg[lr]);
         lp[j] = in.pfx[src];
         ltr[j] = in.tr[src];
         lmt[j] = in.meta[src];
@@ -341,7 +345,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
         s.lo[i] = lp[j].y;
         s.tr[i] = ltr[j];
         s.ulen[i] = (uint8_t)meta_ulen(lmt[j]);
-        s.idx[i] = (uint16_t)i;
+        s.idx[PH(i)] = (uint16_t)i;
       }
     }
   }
@@ -369,11 +373,11 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
           va = ps.ai < ps.a1;
           vb = ps.bi < ps.b1;
           if (va) {
-            ia = s.idx[ps.ai];
+            ia = s.idx[PH(ps.ai)];
             ha = s.hi[ia];
           }
           if (vb) {
-            ib = s.idx[ps.bi];
+            ib = s.idx[PH(ps.bi)];
             hb = s.hi[ib];
           }
         }
@@ -383,14 +387,14 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
           ps.ai++;
           va = ps.ai < ps.a1;
           if (va) {
-            ia = s.idx[ps.ai];
+            ia = s.idx[PH(ps.ai)];
             ha = s.hi[ia];
           }
         } else {
           ps.bi++;
           vb = ps.bi < ps.b1;
           if (vb) {
-            ib = s.idx[ps.bi];
+            ib = s.idx[PH(ps.bi)];
             hb = s.hi[ib];
           }
         }
@@ -400,7 +404,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
 #pragma unroll
     for (int x = 0; x < kMV; x++) {
       uint32_t o = o0 + x;
-      if (o < cnt) s.idx[o] = rid[x];
+      if (o < cnt) s.idx[PH(o)] = rid[x];
     }
     // next round's list bounds
     uint32_t nn = (nlists + 1) >> 1;
@@ -421,12 +425,12 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     otr[x] = 0;
     oid[x] = 0;
     if (o >= cnt) continue;
-    const uint32_t id = s.idx[o];
+    const uint32_t id = s.idx[PH(o)];
     oid[x] = (uint16_t)id;
     Key c = skey(s, id);
     Key p;
     bool has_prev = true;
-    if (o > 0) p = skey(s, s.idx[o - 1]);
+    if (o > 0) p = skey(s, s.idx[PH(o - 1)]);
     else {
       p = s.pred;
       has_prev = s.has_pred != 0;
@@ -447,7 +451,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
         uint64_t head_tr = 0;
         bool have = false;
         while (q >= 0) {
-          Key h = skey(s, s.idx[q]);
+          Key h = skey(s, s.idx[PH(q)]);
           uint64_t d2;
           bool same_grp = h.hi == c.hi && h.lo == c.lo && h.ulen == c.ulen &&
                           stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, h.tr >> 8, &d2) == st_c;
@@ -471,7 +475,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       // :947-990 keep the tombstone only if an older stripe still holds a version of this user key
       bool resolved = false;
       for (uint32_t q = o + 1; q < cnt; q++) {
-        Key nx = skey(s, s.idx[q]);
+        Key nx = skey(s, s.idx[PH(q)]);
         if (!(nx.hi == c.hi && nx.lo == c.lo && nx.ulen == c.ulen)) {
           resolved = true;
           break;
@@ -561,7 +565,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
 #pragma unroll
   for (int x = 0; x < kMV; x++) {
     if ((keep_mask >> x) & 1) {
-      s.idx[rank] = oid[x];
+      s.idx[PH(rank)] = oid[x];
       s.tr[oid[x]] = otr[x];  // each load position is owned by exactly one merged position
       rank++;
     }
@@ -581,7 +585,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       gm[j] = 0;
       gp[j] = 0;
       if (i < kept_total) {
-        uint32_t pos = s.idx[i], lo = 0, hi = k;
+        uint32_t pos = s.idx[PH(i)], lo = 0, hi = k;
         while (hi - lo > 1) {
           uint32_t mid = (lo + hi) >> 1;
           if (s.seg[mid] <= pos) lo = mid;
@@ -606,14 +610,22 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       }
     }
   }
-  // ---- counters: one atomic per CTA and counter
-  unsigned long long vals[7] = {(unsigned long long)nkeep, c_indel, c_hidden, c_obsolete, c_kbytes, c_vbytes, c_silent};
+  // ---- counters: one atomic per CTA and counter.  Per-thread partial counts are small (<= kMV entries), so the warp
+  // reduction is a single redux instruction per counter; only the (rare) value-byte correction needs 64 bits.
+  {
+    const unsigned vals[6] = {nkeep, (unsigned)c_indel, (unsigned)c_hidden, (unsigned)c_obsolete, (unsigned)c_kbytes, (unsigned)c_silent};
+    const int slot[6] = {0, 1, 2, 3, 4, 6};
 #pragma unroll
-  for (int i = 0; i < 7; i++) {
-    unsigned long long v = vals[i];
+    for (int i = 0; i < 6; i++) {
+      const unsigned v = __reduce_add_sync(0xffffffffu, vals[i]);
+      if (lane == 0 && v) atomicAdd(&s.red[slot[i]], (unsigned long long)v);
+    }
+    if (__any_sync(0xffffffffu, c_vbytes != 0)) {
+      unsigned long long v = c_vbytes;
 #pragma unroll
-    for (int dd = 16; dd; dd >>= 1) v += __shfl_xor_sync(0xffffffffu, v, dd);
-    if (lane == 0 && v) atomicAdd(&s.red[i], v);
+      for (int dd = 16; dd; dd >>= 1) v += __shfl_xor_sync(0xffffffffu, v, dd);
+      if (lane == 0) atomicAdd(&s.red[5], v);
+    }
   }
   __syncthreads();
   if (t < 7 && s.red[t]) atomicAdd(((unsigned long long*)counters) + t, s.red[t]);
@@ -625,6 +637,8 @@ void launch_merge_partition(KeyCols in, const uint64_t* run_start, uint32_t nrun
   unsigned warps = (unsigned)(ntiles + 1);
   merge_partition_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, run_start, nruns, n_total, ntiles, splits, err);
 }
+static_assert(sizeof(Key) * kMaxRuns <= sizeof(uint64_t) * kMT && 4 * kMaxRuns <= 2 * kMT, "candidate staging must fit");
+static_assert(3 * (sizeof(TileSmem) + 1024) <= 227 * 1024, "merge tile must fit three CTAs per SM");
 void launch_merge_tiles(KeyCols in, const uint64_t* run_start, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                         const uint64_t* splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
                         MergeCounters* counters, uint32_t* err, cudaStream_t st) {
