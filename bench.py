@@ -197,8 +197,7 @@ def main():
     in_data = in_bytes  # data blocks dominate the image; index/tail < 1.5 %
     val_out = st.total_input_raw_value_bytes if n_out == n_in else int(st.total_input_raw_value_bytes * n_out / max(1, n_in))
     algo = {
-        "decode.block_count": in_data,
-        "decode.block_decode": in_data + 36 * n_in,
+        "decode.blocks": in_data + 36 * n_in,
         "merge.partition": 0,
         "merge.tiles": 36 * n_in + 36 * n_out,
         "encode.sizes": 28 * n_out + 5 * n_out,
