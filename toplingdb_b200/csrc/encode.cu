@@ -1037,90 +1037,55 @@ __device__ __forceinline__ void store_value_words(uint8_t* dst, const uint32_t* 
     if (rem > 2) dst[done + 2] = (uint8_t)(tailv >> 16);
   }
 }
-constexpr int kEmitBatch = 8;
-constexpr int kEmitPerThread = 3;
-constexpr int kEmitMaxEntries = kEmitWarps * 32 * kEmitPerThread;  // 768
-struct EmitSmem {
-  uint64_t first_entry[kEmitBatch + 1];  // first entry of each block; [nb] = end
-  uint32_t first_rel[kEmitBatch + 1];    // the same relative to the batch's first entry
-  uint64_t cum0[kEmitBatch];             // scanned size at the first entry of each block
-  uint32_t body[kEmitBatch];             // bytes of all entries of the block
-  uint64_t ws[33];
-  uint64_t carry;
-  uint32_t nb, fits;
-};
+constexpr int kEmitPerLane = 3;
+constexpr int kEmitMaxEntries = 32 * kEmitPerLane;  // 96 entries per block on the fast path
+// One WARP per data block, no CTA-wide synchronisation: lane l owns the block's entries [3l, 3l + 3), a warp scan of the
+// entry sizes gives every entry its byte position, the lanes write header + key suffix + value into the warp's block
+// image in shared memory, then the warp appends restart array + footer, checksums the image and stores it re-aligned
+// to the file offset.  Global loads are issued in groups (size columns; key columns; value words) so that a block costs
+// three DRAM round trips.  Blocks with more than 96 entries or larger than the image slot take emit_block_warp.
 __global__ void __launch_bounds__(kEmitWarps * 32, 3)
 encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, uint8_t* const* __restrict__ out_base,
                    uint32_t slot_bytes, uint32_t* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem[];
-  EmitSmem& s = *reinterpret_cast<EmitSmem*>(smem);
-  uint8_t* img0 = smem + ((sizeof(EmitSmem) + 15) & ~(size_t)15);
-  const unsigned t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint8_t* img = smem + (size_t)w * slot_bytes;
   const uint32_t R = ep.restart_interval;
-  const uint64_t nbatches = (nblocks + kEmitBatch - 1) / kEmitBatch;
-  for (uint64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
-    const uint64_t b0 = batch * kEmitBatch;
-    const uint32_t nb = (uint32_t)((nblocks - b0) < kEmitBatch ? (nblocks - b0) : kEmitBatch);
-    __syncthreads();  // previous batch fully stored
-    if (t < nb) {
-      const BlockRec br = wk.blocks[b0 + t];
-      s.first_entry[t] = br.first_entry;
-      if (t == nb - 1) s.first_entry[nb] = br.first_entry + br.n_entries;
-      s.body[t] = 0;
+  const uint32_t rmask = (R & (R - 1)) == 0 ? R - 1 : 0xffffffffu;  // power-of-two restart interval: mask instead of %
+  const uint64_t stride = (uint64_t)gridDim.x * kEmitWarps;
+  for (uint64_t b = (uint64_t)blockIdx.x * kEmitWarps + w; b < nblocks; b += stride) {
+    const BlockRec br = wk.blocks[b];
+    const uint32_t E = br.n_entries;
+    const uint64_t e0 = br.first_entry;
+    __syncwarp();  // the previous block's image has been stored
+    if (E > (uint32_t)kEmitMaxEntries) {
+      emit_block_warp(m, ep, wk, b, out_base, img, slot_bytes);
+      continue;
     }
-    if (t == 0) s.carry = 0;
-    __syncthreads();
-    const uint64_t e0 = s.first_entry[0];
-    if (t == 0) {  // entries of consecutive blocks must be consecutive and few enough; otherwise warp-per-block fallback
-      bool f = s.first_entry[nb] - e0 <= (uint64_t)kEmitMaxEntries;
-      for (uint32_t q = 0; q < nb; q++) {
-        f = f && s.first_entry[q + 1] > s.first_entry[q];
-        s.first_rel[q] = (uint32_t)(s.first_entry[q] - e0);
-      }
-      s.first_rel[nb] = (uint32_t)(s.first_entry[nb] - e0);
-      s.fits = f;
-    }
-    __syncthreads();
-    bool fits = s.fits != 0;
-    const uint32_t E = s.first_rel[nb];
-    const uint32_t rmask = (R & (R - 1)) == 0 ? R - 1 : 0xffffffffu;  // power-of-two restart interval: mask instead of %
-    // pass 1 keeps only three words per entry alive across the scan; keys / value addresses are loaded in pass 2
-    uint32_t bi[kEmitPerThread], sz[kEmitPerThread], pk[kEmitPerThread], vs[kEmitPerThread];  // pk = shared | ulen << 8 | restart << 16
-    uint64_t cum[kEmitPerThread], vrf[kEmitPerThread];
-    if (fits) {
-      // thread t owns the consecutive entries [3t, 3t+3): one CTA-wide scan gives every entry its byte position
-      uint32_t tsum = 0, q = 0;
-      {
-        const uint32_t x0 = t * kEmitPerThread;
-        while (q + 1 < nb && s.first_rel[q + 1] <= x0) q++;
-      }
-      // all column loads of the thread's entries are issued before the first use (one DRAM round trip, not three)
-      uint32_t mtv[kEmitPerThread], shv[kEmitPerThread];
+    // ---- pass 1: sizes.  All column loads of the lane's entries are issued before the first use.
+    uint32_t sz[kEmitPerLane], pk[kEmitPerLane], vs[kEmitPerLane];  // pk = shared | ulen << 8 | restart << 16
+    uint64_t vrf[kEmitPerLane];
+    uint32_t tsum = 0;
+    {
+      uint32_t mtv[kEmitPerLane], shv[kEmitPerLane];
 #pragma unroll
-      for (int i = 0; i < kEmitPerThread; i++) {
-        const uint32_t x = t * kEmitPerThread + i;
+      for (int i = 0; i < kEmitPerLane; i++) {
+        const uint32_t x = lane * kEmitPerLane + i;
         mtv[i] = 0;
         shv[i] = 0;
         vrf[i] = 0;
         if (x < E) {
-          const uint64_t e = e0 + x;
-          mtv[i] = m.meta[e];
-          shv[i] = wk.eshared[e];
-          vrf[i] = m.vref[e];
+          mtv[i] = m.meta[e0 + x];
+          shv[i] = wk.eshared[e0 + x];
+          vrf[i] = m.vref[e0 + x];
         }
       }
 #pragma unroll
-      for (int i = 0; i < kEmitPerThread; i++) {
-        const uint32_t x = t * kEmitPerThread + i;
-        sz[i] = 0;
-        bi[i] = 0;
-        pk[i] = 0;
-        vs[i] = 0;
+      for (int i = 0; i < kEmitPerLane; i++) {
+        const uint32_t x = lane * kEmitPerLane + i;
+        sz[i] = pk[i] = vs[i] = 0;
         if (x < E) {
-          while (q + 1 < nb && s.first_rel[q + 1] <= x) q++;
-          bi[i] = q;
-          const uint32_t jj = x - s.first_rel[q];
-          const bool restart = (rmask != 0xffffffffu ? (jj & rmask) : (jj % R)) == 0;
+          const bool restart = (rmask != 0xffffffffu ? (x & rmask) : (x % R)) == 0;
           const uint32_t ul = meta_ulen(mtv[i]);
           vs[i] = meta_vlen(mtv[i]);
           const uint32_t sh = restart ? 0 : shv[i];
@@ -1129,44 +1094,32 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
           tsum += sz[i];
         }
       }
-      uint64_t tot;
-      uint64_t run = block_excl_scan64(tsum, &tot, s.ws);
-#pragma unroll
-      for (int i = 0; i < kEmitPerThread; i++) {
-        cum[i] = run;
-        run += sz[i];
-        const uint32_t x = t * kEmitPerThread + i;
-        if (x < E && x == s.first_rel[bi[i]]) s.cum0[bi[i]] = cum[i];
-      }
-      if (t == 0) s.carry = tot;
-      __syncthreads();
-      if (t < nb) s.body[t] = (uint32_t)((t + 1 < nb ? s.cum0[t + 1] : s.carry) - s.cum0[t]);
-      __syncthreads();
-      if (t == 0) {
-        bool f = true;
-        for (uint32_t qq = 0; qq < nb; qq++) {
-          const uint32_t nrest = (s.first_rel[qq + 1] - s.first_rel[qq] + R - 1) / R;
-          f = f && (uint64_t)s.body[qq] + 4ull * nrest + 4 + 5 + 32 <= slot_bytes;
-        }
-        s.fits = f;
-      }
-      __syncthreads();
-      fits = s.fits != 0;
     }
-    if (!fits) {  // uniform decision
-      __syncthreads();
-      if (w < nb) emit_block_warp(m, ep, wk, b0 + w, out_base, img0 + (size_t)w * slot_bytes, slot_bytes);
+    const uint64_t inc = warp_incl_scan64(tsum);
+    const uint64_t body64 = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t nrest = (E + R - 1) / R;
+    if (body64 + 4ull * nrest + 4 + 5 + 32 > slot_bytes) {  // uniform
+      emit_block_warp(m, ep, wk, b, out_base, img, slot_bytes);
       continue;
     }
-    // pass 2: write entries into the block images.  Key columns for all of the thread's entries first, then (when every
-    // value is short) all value words, so that each group costs one DRAM round trip.
-    uint32_t voff[kEmitPerThread];  // image offset of the value bytes
+    const uint32_t body = (uint32_t)body64;
+    uint32_t off[kEmitPerLane];
     {
-      ulonglong2 ppv[kEmitPerThread];
-      uint64_t trv[kEmitPerThread];
+      uint32_t run = (uint32_t)(inc - tsum);
 #pragma unroll
-      for (int i = 0; i < kEmitPerThread; i++) {
-        const uint32_t x = t * kEmitPerThread + i;
+      for (int i = 0; i < kEmitPerLane; i++) {
+        off[i] = run;
+        run += sz[i];
+      }
+    }
+    // ---- pass 2: key columns of all the lane's entries, then all value words (when every value is short)
+    uint32_t voff[kEmitPerLane];  // image offset of the value bytes
+    {
+      ulonglong2 ppv[kEmitPerLane];
+      uint64_t trv[kEmitPerLane];
+#pragma unroll
+      for (int i = 0; i < kEmitPerLane; i++) {
+        const uint32_t x = lane * kEmitPerLane + i;
         ppv[i] = make_ulonglong2(0, 0);
         trv[i] = 0;
         if (x < E) {
@@ -1175,14 +1128,12 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
         }
       }
 #pragma unroll
-      for (int i = 0; i < kEmitPerThread; i++) {
-        const uint32_t x = t * kEmitPerThread + i;
+      for (int i = 0; i < kEmitPerLane; i++) {
+        const uint32_t x = lane * kEmitPerLane + i;
         voff[i] = 0;
         if (x < E) {
-          const uint32_t q = bi[i], sh = pk[i] & 0xff, ul = (pk[i] >> 8) & 0xff;
-          uint8_t* img = img0 + (size_t)q * slot_bytes;
-          const uint32_t off = (uint32_t)(cum[i] - s.cum0[q]);
-          uint8_t* p = img + off;
+          const uint32_t sh = pk[i] & 0xff, ul = (pk[i] >> 8) & 0xff;
+          uint8_t* p = img + off[i];
           const uint32_t ks = ul + 8;
           uint64_t S0, S1, S2;
           key_suffix_words(ppv[i].x, ppv[i].y, ul, trv[i], sh, &S0, &S1, &S2);
@@ -1201,14 +1152,13 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
             store_bytes24(p, S0, S1, S2, ks - sh);
             p += ks - sh;
           }
-          voff[i] = (uint32_t)(p - img0);
+          voff[i] = (uint32_t)(p - img);
           if (pk[i] >> 16) {
-            const uint32_t jj = x - s.first_rel[q];
-            uint8_t* rp = img + s.body[q] + 4ull * (rmask != 0xffffffffu ? jj >> __popc(rmask) : jj / R);
-            rp[0] = (uint8_t)off;
-            rp[1] = (uint8_t)(off >> 8);
-            rp[2] = (uint8_t)(off >> 16);
-            rp[3] = (uint8_t)(off >> 24);
+            uint8_t* rp = img + body + 4u * (rmask != 0xffffffffu ? x >> __popc(rmask) : x / R);
+            rp[0] = (uint8_t)off[i];
+            rp[1] = (uint8_t)(off[i] >> 8);
+            rp[2] = (uint8_t)(off[i] >> 16);
+            rp[3] = (uint8_t)(off[i] >> 24);
           }
         }
       }
@@ -1217,11 +1167,11 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
       constexpr int kNW = 9;  // aligned words covering a value of <= 32 bytes at any alignment
       bool all_short = true;
 #pragma unroll
-      for (int i = 0; i < kEmitPerThread; i++) all_short = all_short && vs[i] <= 32;
+      for (int i = 0; i < kEmitPerLane; i++) all_short = all_short && vs[i] <= 32;
       if (all_short) {
-        uint32_t vw[kEmitPerThread][kNW + 1];
+        uint32_t vw[kEmitPerLane][kNW + 1];
 #pragma unroll
-        for (int i = 0; i < kEmitPerThread; i++) {
+        for (int i = 0; i < kEmitPerLane; i++) {
           const uint32_t a = (uint32_t)(vrf[i] & 3);
           const uint32_t* wsrc = reinterpret_cast<const uint32_t*>((uintptr_t)vrf[i] - a);
           const uint32_t nw = vs[i] ? (a + vs[i] + 3) >> 2 : 0;
@@ -1230,27 +1180,25 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
           vw[i][kNW] = 0;
         }
 #pragma unroll
-        for (int i = 0; i < kEmitPerThread; i++) store_value_words<kNW>(img0 + voff[i], vw[i], (uint32_t)(vrf[i] & 3), vs[i]);
+        for (int i = 0; i < kEmitPerLane; i++) store_value_words<kNW>(img + voff[i], vw[i], (uint32_t)(vrf[i] & 3), vs[i]);
       } else {
 #pragma unroll
-        for (int i = 0; i < kEmitPerThread; i++)
-          if (vs[i] && vs[i] <= 64) copy_value_small(img0 + voff[i], (const uint8_t*)(uintptr_t)vrf[i], vs[i]);
+        for (int i = 0; i < kEmitPerLane; i++)
+          if (vs[i] && vs[i] <= 64) copy_value_small(img + voff[i], (const uint8_t*)(uintptr_t)vrf[i], vs[i]);
       }
     }
-    // values longer than 64 bytes: a warp copies each of its lanes' values with all lanes
+    // values longer than 64 bytes: the warp copies each of them with all lanes
 #pragma unroll
-    for (int i = 0; i < kEmitPerThread; i++) {
-      const uint32_t x = t * kEmitPerThread + i;
-      unsigned big = __ballot_sync(0xffffffffu, x < E && vs[i] > 64);
+    for (int i = 0; i < kEmitPerLane; i++) {
+      unsigned big = __ballot_sync(0xffffffffu, vs[i] > 64);
       while (big) {
         const int sl = __ffs(big) - 1;
         big &= big - 1;
-        const uint32_t q = __shfl_sync(0xffffffffu, bi[i], sl);
         const uint32_t vl = __shfl_sync(0xffffffffu, vs[i], sl);
         const uint32_t vo = __shfl_sync(0xffffffffu, voff[i], sl);
         const uint64_t vrr = __shfl_sync(0xffffffffu, vrf[i], sl);
         const uint8_t* sp = (const uint8_t*)(uintptr_t)vrr;
-        uint8_t* dp = img0 + vo;
+        uint8_t* dp = img + vo;
         // aligned 4-byte source words, funnel-shifted; byte stores into the image
         const uint32_t a = (uint32_t)((uintptr_t)sp & 3);
         const uint32_t* wsrc = reinterpret_cast<const uint32_t*>((uintptr_t)sp - a);
@@ -1265,50 +1213,42 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
         }
       }
     }
-    __syncthreads();
-    // per block: restart footer, checksum trailer, store
-    if (w < nb) {
-      const uint32_t q = w;
-      const BlockRec br = wk.blocks[b0 + q];
-      uint8_t* img = img0 + (size_t)q * slot_bytes;
-      uint8_t* gdst = out_base[br.file_idx] + br.file_off;
-      const uint32_t nrest = (br.n_entries + R - 1) / R;
-      const uint32_t body = s.body[q];
-      const uint32_t payload = body + 4 * nrest + 4;
-      if (lane == 0) {
-        uint8_t* fp = img + body + 4ull * nrest;
-        fp[0] = (uint8_t)nrest;
-        fp[1] = (uint8_t)(nrest >> 8);
-        fp[2] = (uint8_t)(nrest >> 16);
-        fp[3] = (uint8_t)(nrest >> 24);
-      }
-      __syncwarp();
-      const uint32_t ck = block_checksum_warp(ep.checksum, img, payload, 0);
-      if (lane == 0) {
-        uint8_t* tp = img + payload;
-        tp[0] = 0;
-        tp[1] = (uint8_t)ck;
-        tp[2] = (uint8_t)(ck >> 8);
-        tp[3] = (uint8_t)(ck >> 16);
-        tp[4] = (uint8_t)(ck >> 24);
-      }
-      __syncwarp();
-      const uint32_t total = payload + 5;
-      const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15);
-      uint32_t head = shift ? 16 - shift : 0;
-      if (head > total) head = total;
-      if (lane < head) gdst[lane] = img[lane];
-      const uint32_t nvec = (total - head) >> 4;
-      const uint4* sv = reinterpret_cast<const uint4*>(img);
-      uint4* gv = reinterpret_cast<uint4*>(gdst + head);
-      if (head == 0) {
-        for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
-      } else {
-        for (uint32_t i = lane; i < nvec; i += 32) gv[i] = shift16(sv[i], sv[i + 1], head);
-      }
-      const uint32_t done = head + (nvec << 4);
-      if (done + lane < total) gdst[done + lane] = img[done + lane];
+    // ---- restart footer, checksum trailer, store
+    uint8_t* gdst = out_base[br.file_idx] + br.file_off;
+    const uint32_t payload = body + 4 * nrest + 4;
+    if (lane == 0) {
+      uint8_t* fp = img + body + 4u * nrest;
+      fp[0] = (uint8_t)nrest;
+      fp[1] = (uint8_t)(nrest >> 8);
+      fp[2] = (uint8_t)(nrest >> 16);
+      fp[3] = (uint8_t)(nrest >> 24);
     }
+    __syncwarp();
+    const uint32_t ck = block_checksum_warp(ep.checksum, img, payload, 0);
+    if (lane == 0) {
+      uint8_t* tp = img + payload;
+      tp[0] = 0;
+      tp[1] = (uint8_t)ck;
+      tp[2] = (uint8_t)(ck >> 8);
+      tp[3] = (uint8_t)(ck >> 16);
+      tp[4] = (uint8_t)(ck >> 24);
+    }
+    __syncwarp();
+    const uint32_t total = payload + 5;
+    const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15);
+    uint32_t head = shift ? 16 - shift : 0;
+    if (head > total) head = total;
+    if (lane < head) gdst[lane] = img[lane];
+    const uint32_t nvec = (total - head) >> 4;
+    const uint4* sv = reinterpret_cast<const uint4*>(img);
+    uint4* gv = reinterpret_cast<uint4*>(gdst + head);
+    if (head == 0) {
+      for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
+    } else {
+      for (uint32_t i = lane; i < nvec; i += 32) gv[i] = shift16(sv[i], sv[i + 1], head);
+    }
+    const uint32_t done = head + (nvec << 4);
+    if (done + lane < total) gdst[done + lane] = img[done + lane];
   }
   (void)err;
 }
@@ -1525,13 +1465,13 @@ void launch_encode_emit(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nbloc
     attr = true;
   }
   const uint32_t slot = encode_emit_slice(ep.block_size);
-  const size_t smem = ((sizeof(EmitSmem) + 15) & ~(size_t)15) + (size_t)slot * kEmitBatch;
+  const size_t smem = (size_t)slot * kEmitWarps;
   unsigned per_sm = (unsigned)((224 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
-  const uint64_t nbatches = (nblocks + kEmitBatch - 1) / kEmitBatch;
-  const uint64_t cap = (uint64_t)sms * per_sm * 2;
-  encode_emit_kernel<<<(unsigned)(nbatches < cap ? nbatches : cap), kEmitWarps * 32, smem, st>>>(m, ep, w, nblocks, out_base, slot, err);
+  if (per_sm > 3) per_sm = 3;
+  const uint64_t want = (nblocks + kEmitWarps - 1) / kEmitWarps;
+  const uint64_t cap = (uint64_t)sms * per_sm;
+  encode_emit_kernel<<<(unsigned)(want < cap ? want : cap), kEmitWarps * 32, smem, st>>>(m, ep, w, nblocks, out_base, slot, err);
 }
 void launch_encode_index(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nblocks, uint32_t nfiles, uint8_t* const* out_base,
                          uint32_t* err, cudaStream_t st, uint64_t* launches) {

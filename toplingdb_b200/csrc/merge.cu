@@ -302,20 +302,6 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   }
   __syncthreads();
   const uint32_t cnt = s.seg[k];
-  // ---- pull the segments of the tile one wave ahead into L2 (its CTA will find them there)
-  {
-    const uint64_t ahead = tile + prefetch_dist;
-    if (ahead < ntiles) {
-      const uint32_t part = t & 7;  // 8 threads per run
-      for (uint32_t r = t >> 3; r < k; r += kMThreads / 8) {
-        const uint64_t a0 = run_start[r] + splits[ahead * k + r], a1 = run_start[r] + splits[(ahead + 1) * k + r];
-        for (uint64_t e = a0 + part * 8; e < a1; e += 64) prefetch_l2(in.pfx + e);  // 8 entries per 128-byte line
-        for (uint64_t e = a0 + part * 16; e < a1; e += 128) prefetch_l2(in.tr + e);
-        for (uint64_t e = a0 + part * 16; e < a1; e += 128) prefetch_l2(in.vref + e);
-        for (uint64_t e = a0 + part * 32; e < a1; e += 256) prefetch_l2(in.meta + e);
-      }
-    }
-  }
   // ---- coalesced load of the k segments.  All of a thread's loads are issued before the first one is consumed: a
   // warp issues in order, so a load-then-store loop body would pay one DRAM round trip per iteration.
   {
@@ -516,36 +502,12 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   __syncthreads();
   uint32_t rank = s.wsum[w] + inc - nkeep;
   const uint32_t kept_total = s.kept_total;
-  // ---- decoupled look-back for the global output offset (tile ids are handed out in launch order)
-  if (w == 0) {
-    const unsigned long long kAgg = 1ull << 62, kPre = 2ull << 62, kVal = (1ull << 62) - 1;
-    uint64_t base_out = 0;
-    if (tile == 0) {
-      if (lane == 0) atomicExch(&tile_state[0], kPre | kept_total);
-    } else {
-      if (lane == 0) atomicExch(&tile_state[tile], kAgg | kept_total);
-      int64_t look = (int64_t)tile - 1;
-      while (true) {
-        int64_t idx = look - lane;
-        unsigned long long sv = kPre;  // virtual tiles before 0 contribute a zero prefix
-        if (idx >= 0) {
-          do {
-            sv = *((volatile unsigned long long*)&tile_state[idx]);
-          } while ((sv >> 62) == 0);
-        }
-        unsigned pre_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
-        int first_pre = pre_mask ? __ffs(pre_mask) - 1 : 32;
-        uint64_t contrib = ((int)lane <= first_pre) ? (sv & kVal) : 0;
-#pragma unroll
-        for (int dd = 16; dd; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
-        base_out += contrib;
-        if (pre_mask) break;
-        look -= 32;
-      }
-      if (lane == 0) atomicExch(&tile_state[tile], kPre | (base_out + kept_total));
-    }
-    if (lane == 0) s.base_out = base_out;
-  }
+  // ---- decoupled look-back for the global output offset (tile ids are handed out in launch order), in two halves:
+  // the tile's count is published now, the wait for the predecessors' counts comes after the compaction and the value
+  // reference gathers below -- a tile can only resolve its offset once EVERY earlier tile has published its count, so
+  // waiting here would idle the whole CTA for the spread of the predecessors' progress
+  const unsigned long long kAgg = 1ull << 62, kPre = 2ull << 62, kVal = (1ull << 62) - 1;
+  if (t == 0) atomicExch(&tile_state[tile], (tile == 0 ? kPre : kAgg) | kept_total);
   // value-byte statistic: the inputs' raw.value.size property already sums every entry; only the (rare) silently
   // skipped entries have to be subtracted, so only they pay a gather
 #pragma unroll
@@ -571,7 +533,6 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     }
   }
   __syncthreads();
-  const uint64_t base_out = s.base_out;
   {
     // gather the value references of the survivors (random within k contiguous segments) for all of the thread's
     // output slots first, then write: again one round trip instead of kMV
@@ -597,6 +558,35 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
         gm[j] = in.meta[src];
       }
     }
+    if (w == 0) {  // second half of the look-back
+      uint64_t base = 0;
+      if (tile != 0) {
+        int64_t look = (int64_t)tile - 1;
+        while (true) {
+          const int64_t idx = look - lane;
+          unsigned long long sv = kPre;  // virtual tiles before 0 contribute a zero prefix
+          if (idx >= 0) {
+            sv = *((volatile unsigned long long*)&tile_state[idx]);
+            while ((sv >> 62) == 0) {
+              __nanosleep(64);
+              sv = *((volatile unsigned long long*)&tile_state[idx]);
+            }
+          }
+          const unsigned pre_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+          const int first_pre = pre_mask ? __ffs(pre_mask) - 1 : 32;
+          uint64_t contrib = ((int)lane <= first_pre) ? (sv & kVal) : 0;
+#pragma unroll
+          for (int dd = 16; dd; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
+          base += contrib;
+          if (pre_mask) break;
+          look -= 32;
+        }
+        if (lane == 0) atomicExch(&tile_state[tile], kPre | (base + kept_total));
+      }
+      if (lane == 0) s.base_out = base;
+    }
+    __syncthreads();
+    const uint64_t base_out = s.base_out;
 #pragma unroll
     for (int j = 0; j < kMV; j++) {
       const uint32_t i = t + j * kMThreads;
