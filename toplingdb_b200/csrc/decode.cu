@@ -686,18 +686,19 @@ block_decode_fused_kernel(const FileDesc* __restrict__ files, int nfiles, const 
                           unsigned long long* blk_state, uint32_t* ticket, uint64_t* __restrict__ run_start,
                           uint64_t* __restrict__ total_out, uint32_t* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ uint32_t s_tk[2];
   __shared__ uint64_t s_mask[25 * 3];
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   DecWarpSmem& ws = reinterpret_cast<DecWarpSmem*>(smem)[w];
   fill_key_mask_table(s_mask);
   const uint32_t mask_tab = (uint32_t)__cvta_generic_to_shared(s_mask);
-  for (int par = 0;; par ^= 1) {
-    if (threadIdx.x == 0) s_tk[par] = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint64_t b64 = (uint64_t)s_tk[par] * kDecWarps + w;
-    if ((uint64_t)s_tk[par] * kDecWarps >= nblk) break;  // uniform over the CTA
-    if (b64 >= nblk) continue;
+  __syncthreads();  // mask table ready
+  for (;;) {
+    // one ticket per warp and block: blocks are started in ticket order (the look-back needs every predecessor running),
+    // and warps stay independent of each other -- no CTA-wide barrier couples a warp to its neighbours' look-back waits
+    uint32_t tk = 0;
+    if (lane == 0) tk = atomicAdd(ticket, 1u);
+    const uint64_t b64 = __shfl_sync(0xffffffffu, tk, 0);
+    if (b64 >= nblk) break;
     const uint32_t b = (uint32_t)b64;
     const int f = file_of_block(files, nfiles, b);
     const uint8_t* src = files[f].base + blk_off[b];
@@ -756,7 +757,7 @@ void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint
     cudaFuncSetAttribute(block_decode_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(block_decode_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   }
-  const unsigned per = kDecWarps;  // one block per warp and ticket: more would chain CTAs through the look-back
+  const unsigned per = kDecWarps;
   unsigned want = (nblk + per - 1) / per, cap = (unsigned)sms * (unsigned)occ;
   const unsigned grid = want < cap ? (want ? want : 1) : cap;
 #define B200C_LAUNCH_DEC(N)                                                                                                       \

@@ -157,21 +157,50 @@ __device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, c
     w.at_end = (wstart + wlen == n);
   }
   __syncthreads();
-  // strided inclusive scan of Q with stride R (Hillis-Steele doubling)
-  for (uint32_t off = R; off < wlen; off <<= 1) {
-    uint32_t add[kPer];
-#pragma unroll
-    for (int i = 0; i < kPer; i++) {
-      uint32_t j = j0 + i;
-      add[i] = (j < wlen && j >= off) ? w.Q[j - off] : 0;
+  // inclusive scan of Q with stride R, i.e. R independent prefix sums over the residue classes j mod R
+  if ((R & (R - 1)) == 0 && R <= 32 && kEncThreads % R == 0) {
+    // class c = t % R is shared by kEncThreads / R threads; each walks a contiguous range of its class (consecutive lanes
+    // touch consecutive words: no bank conflicts), the partial sums are scanned with shuffles inside the class's threads
+    const uint32_t c = threadIdx.x & (R - 1), part = threadIdx.x / R, nparts = kEncThreads / R;
+    const uint32_t per_class = (wlen + R - 1) / R;                   // elements of the longest class
+    const uint32_t chunk = (per_class + nparts - 1) / nparts;        // elements per thread
+    const uint32_t first = part * chunk;                             // first element (within the class) of this thread
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < chunk; i++) {
+      const uint32_t j = c + R * (first + i);
+      if (j < wlen) sum += w.Q[j];
+    }
+    // exclusive scan of `sum` over the parts of class c: the parts of a class sit R threads apart
+    __shared__ uint32_t part_sum[kEncThreads];
+    part_sum[threadIdx.x] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (uint32_t q = 0; q < part; q++) run += part_sum[c + R * q];
+    for (uint32_t i = 0; i < chunk; i++) {
+      const uint32_t j = c + R * (first + i);
+      if (j < wlen) {
+        run += w.Q[j];
+        w.Q[j] = run;
+      }
     }
     __syncthreads();
+  } else {
+    // generic restart interval: Hillis-Steele doubling
+    for (uint32_t off = R; off < wlen; off <<= 1) {
+      uint32_t add[kPer];
 #pragma unroll
-    for (int i = 0; i < kPer; i++) {
-      uint32_t j = j0 + i;
-      if (j < wlen) w.Q[j] += add[i];
+      for (int i = 0; i < kPer; i++) {
+        uint32_t j = j0 + i;
+        add[i] = (j < wlen && j >= off) ? w.Q[j - off] : 0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kPer; i++) {
+        uint32_t j = j0 + i;
+        if (j < wlen) w.Q[j] += add[i];
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
