@@ -76,8 +76,8 @@ def reference_arm(args, rank, world):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import cpu_baseline as CB
     w = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    # one process per host core, each compacting its own key range of >= 16 MiB raw KV (smaller jobs measure start-up)
+    cores = CB.usable_cores()
+    # one process per usable host core (affinity / cgroup quota), each compacting its own key range of >= 16 MiB raw KV (smaller jobs measure start-up)
     sample = max(args.sample_mb << 20, cores * (16 << 20))
     res = []
     for _ in range(max(1, args.warmup > 0) + args.steps):

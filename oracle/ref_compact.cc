@@ -11,7 +11,9 @@
 //              outputs/NNNNNN.sst, manifest.json (job parameters + CompactionJobStats)
 //   options  : output_level=1 target_file_size=67108864 block_size=4096 restart_interval=16
 //              checksum=xxh3|crc32c max_subcompactions=1 format_version=5 repeat=1 keep_db=0
+#include <dirent.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <cinttypes>
@@ -48,6 +50,8 @@ struct Opts {
   int keep_db = 0;
   int paranoid = 0;
   int copy = 1;  // 0: leave inputs/ and outputs/ empty (timing runs only need the manifest)
+  std::string barrier_dir;  // with barrier_n: wait until barrier_n processes have finished writing their inputs, so that
+  int barrier_n = 0;        // concurrent timing runs compact at the same time
   std::string executor;  // "b200": route the job through the B200 CompactionExecutor plugin (ref_compact_b200 build only)
 };
 
@@ -130,6 +134,8 @@ int main(int argc, char** argv) {
     else if (k == "paranoid") o.paranoid = atoi(v.c_str());
     else if (k == "executor") o.executor = v;
     else if (k == "copy") o.copy = atoi(v.c_str());
+    else if (k == "barrier_dir") o.barrier_dir = v;
+    else if (k == "barrier_n") o.barrier_n = atoi(v.c_str());
     else {
       fprintf(stderr, "ref_compact: unknown option %s\n", k.c_str());
       return 1;
@@ -299,6 +305,20 @@ int main(int argc, char** argv) {
   if (o.copy)
     for (auto& fm : inputs) CopyFile(dbdir + fm.name, work + "/inputs" + fm.name);
 
+  if (o.barrier_n > 1 && !o.barrier_dir.empty()) {
+    const std::string mine = o.barrier_dir + "/ready." + std::to_string((long)getpid());
+    fclose(fopen(mine.c_str(), "w"));
+    for (int spins = 0; spins < 600000; spins++) {  // <= 10 minutes
+      int n = 0;
+      if (DIR* d = opendir(o.barrier_dir.c_str())) {
+        while (dirent* e = readdir(d))
+          if (strncmp(e->d_name, "ready.", 6) == 0) n++;
+        closedir(d);
+      }
+      if (n >= o.barrier_n) break;
+      usleep(1000);
+    }
+  }
   CompactionOptions co;
   co.compression = kNoCompression;
   co.output_file_size_limit = o.target_file_size;

@@ -51,6 +51,29 @@ def _ops_file(path, w, n_total, seed=2):
         f.write(b"\x00")
 
 
+def usable_cores():
+    """host threads this process may really use: CPU affinity, capped by the cgroup CPU quota when there is one"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
+
+
 def run_sample(w, sample_bytes, threads):
     """threads > 1: that many concurrent reference processes, each compacting its own disjoint key range of the sample
     (the reference's own sub-compaction / dcompact parallelism is key-range partitioning); aggregate MB/s =
@@ -68,7 +91,8 @@ def run_sample(w, sample_bytes, threads):
                 _ops_file(os.path.join(d, str(t), "ops.bin"), w, per, seed=2 + t)
             for t in range(threads):
                 procs.append(subprocess.Popen([REF_BIN, os.path.join(d, str(t), "ops.bin"), os.path.join(d, str(t), "w"),
-                                               "output_level=1", "max_subcompactions=1", "target_file_size=67108864", "copy=0"],
+                                               "output_level=1", "max_subcompactions=1", "target_file_size=67108864", "copy=0",
+                                               f"barrier_dir={d}", f"barrier_n={threads}"],
                                               stdout=subprocess.DEVNULL))
             for pr in procs:
                 if pr.wait() != 0:
@@ -101,3 +125,12 @@ def run_sample(w, sample_bytes, threads):
     H.oracle_compact(p, runs)
     secs = time.perf_counter() - t0
     return {"mbps": n_total * entry / secs / 1e6, "seconds": secs, "kind": "port", "threads": 1, "sample": desc + "; CPU oracle port"}
+
+
+if __name__ == "__main__":  # scaling probe: python tests/cpu_baseline.py 1 8 32 128
+    import sys
+    W = dict(k=8, run_bytes=256 << 20, vlen=32, overlap=0.0, del_frac=0.0, bottommost=False, desc="cfg2")
+    print("usable cores:", usable_cores(), "cpu_count:", os.cpu_count())
+    for t in [int(a) for a in sys.argv[1:]] or [1, usable_cores()]:
+        r = run_sample(W, sample_bytes=t * (16 << 20), threads=t)
+        print(f"threads={t:4d}  {r['mbps']:9.1f} MB/s  slowest job {r['seconds']*1e3:8.1f} ms  ({r['mbps']/t:7.1f} MB/s per thread)")

@@ -114,6 +114,85 @@ merge_partition_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint3
   }
 }
 
+// The same split for up to 16 runs with ALL lanes busy: run r is owned by a group of g = 32 / pow2(nruns) lanes that
+// probe g points of its bracket per step (a (g+1)-ary search), which divides the depth of the dependent-load chain --
+// the whole cost of this kernel -- by log2(g + 1).
+__global__ void __launch_bounds__(128)
+merge_partition_grouped_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint32_t nruns, uint32_t gshift, uint64_t n_total,
+                               uint64_t ntiles, uint64_t* __restrict__ splits, uint32_t* __restrict__ err) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b > ntiles) return;
+  uint64_t d = b * (uint64_t)kMT;
+  if (d > n_total) d = n_total;
+  const uint32_t g = 1u << gshift, r = lane >> gshift, sub = lane & (g - 1), gbase = r << gshift;
+  const uint64_t base = r < nruns ? run_start[r] : 0;
+  const uint64_t nrun = r < nruns ? run_start[r + 1] - run_start[r] : 0;
+  uint64_t lo = (d == n_total) ? nrun : 0, hi = (d == 0) ? 0 : nrun;
+  for (int guard = 0; guard < 64 * 70; guard++) {
+    // widest bracket decides the pivot run
+    const unsigned long long wdt = hi - lo;
+    unsigned long long best = wdt ? ((wdt << 7) | (unsigned long long)r) : 0;
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, dd);
+      if (o > best) best = o;
+    }
+    if (best == 0) break;
+    const uint32_t p = (uint32_t)(best & 127);
+    const uint64_t m = __shfl_sync(0xffffffffu, lo + ((hi - lo) >> 1), (int)(p << gshift));
+    const uint64_t pbase = __shfl_sync(0xffffffffu, base, (int)(p << gshift));
+    const Key x = load_key(in, pbase + m);
+    // c = number of elements of run r that precede x in the total order (key, run index): (g+1)-ary search of [lo, hi)
+    const bool before_equal = r < p;
+    uint64_t clo = lo, chi = hi;
+    if (r == p) clo = chi = m;
+    while (__any_sync(0xffffffffu, chi > clo)) {
+      const uint64_t w = chi - clo;
+      uint64_t pos = clo;
+      bool valid = false;
+      if (w > 0) {
+        if (w <= g) {
+          pos = clo + sub;
+          valid = sub < w;
+        } else {
+          pos = clo + (w * (sub + 1)) / (g + 1);
+          valid = true;
+        }
+      }
+      bool prec = false;
+      if (valid) {
+        const Key e = load_key(in, base + pos);
+        prec = before_equal ? !ikey_less(x, e) : ikey_less(e, x);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, prec);
+      const uint32_t cp = __popc((bal >> gbase) & ((1u << g) - 1u));  // probes are increasing: the preceding ones form a prefix
+      const uint32_t nvalid = w == 0 ? 0 : (w <= g ? (uint32_t)w : g);
+      const uint64_t below = __shfl_sync(0xffffffffu, pos, (int)(gbase + (cp ? cp - 1 : 0)));
+      const uint64_t above = __shfl_sync(0xffffffffu, pos, (int)(gbase + (cp < g ? cp : g - 1)));
+      if (w > 0) {
+        if (cp) clo = below + 1;
+        if (cp < nvalid) chi = above;
+        else if (w <= g) chi = clo;  // every remaining element precedes
+      }
+    }
+    const uint64_t c = clo;
+    uint64_t sum = sub == 0 ? c : 0;
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
+    const bool x_before = sum < d;  // pivot is among the first d elements
+    if (r < nruns) {
+      if (x_before) lo = (r == p) ? m + 1 : c;
+      else hi = (r == p) ? m : c;
+    }
+  }
+  uint64_t tot = sub == 0 ? lo : 0;
+#pragma unroll
+  for (int dd = 16; dd; dd >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, dd);
+  if (tot != d && lane == 0) atomicOr(err, kErrKeyOrder);
+  if (r < nruns && sub == 0) splits[b * nruns + r] = lo;
+}
+
 // ------------------------------------------------------------------------------------------------ tile merge
 // Keys stay where the coalesced load put them (structure of arrays in shared memory); the merge rounds permute a list
 // of 16-bit indices.  A comparison loads the high key word of both candidates and touches the other words only on a tie.
@@ -625,6 +704,14 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
 void launch_merge_partition(KeyCols in, const uint64_t* run_start, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
                             uint64_t* splits, uint32_t* err, cudaStream_t st) {
   unsigned warps = (unsigned)(ntiles + 1);
+  if (nruns <= 16) {
+    uint32_t kp2 = 2;  // at most 16 lanes per run
+    while (kp2 < nruns) kp2 <<= 1;
+    uint32_t gshift = 0;
+    while ((kp2 << (gshift + 1)) <= 32) gshift++;  // lanes per run = 32 / pow2(nruns)
+    merge_partition_grouped_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, run_start, nruns, gshift, n_total, ntiles, splits, err);
+    return;
+  }
   merge_partition_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, run_start, nruns, n_total, ntiles, splits, err);
 }
 static_assert(sizeof(Key) * kMaxRuns <= sizeof(uint64_t) * kMT && 4 * kMaxRuns <= 2 * kMT, "candidate staging must fit");
