@@ -77,8 +77,9 @@ def reference_arm(args, rank, world):
     import cpu_baseline as CB
     w = WORKLOADS[args.workload]
     cores = CB.usable_cores()
-    # one process per usable host core (affinity / cgroup quota), each compacting its own key range of >= 16 MiB raw KV (smaller jobs measure start-up)
-    sample = max(args.sample_mb << 20, cores * (16 << 20))
+    # one process per usable host core (CPU affinity capped by the cgroup quota), each compacting its own key range of 64 MiB
+    # raw KV: long enough to span several scheduler quota periods, so that a burst above the quota does not flatter the number
+    sample = max(args.sample_mb << 20, cores * (64 << 20))
     res = []
     for _ in range(max(1, args.warmup > 0) + args.steps):
         res.append(CB.run_sample(w, sample_bytes=sample, threads=cores))
