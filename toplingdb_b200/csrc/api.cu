@@ -242,7 +242,7 @@ void ikey_bytes(const KeyRec& k, uint8_t* out, uint32_t* len) {
 }
 
 // encode stage: merged columns (device) -> output file images + metas.  `h` holds the small-slot snapshot read at sync #1.
-int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, EncodeWork& W, uint32_t* err, uint64_t* small,
+int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, uint32_t max_s1, EncodeWork& W, uint32_t* err, uint64_t* small,
                  uint64_t& launches, uint64_t& nblocks, uint32_t& nfiles) {
   const b200c_params& P = j->p;
   cudaStream_t st = j->st;
@@ -283,7 +283,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, E
     W.files = j->files_rec.as<FileRec>();
     W.scan_tmp = j->scan_tmp.as<uint64_t>();
     j->kt_begin("encode.tables");
-    launch_encode_tables(mcols, ep, W, etiles, hc, err, st);
+    launch_encode_tables(mcols, ep, W, etiles, hc, max_s1, err, st);
     j->kt_end();
     j->kt_begin("encode.stitch");
     launch_encode_stitch(mcols, ep, W, etiles, hc, err, st, &launches);
@@ -649,7 +649,7 @@ int run_job(b200c_job* j, int until) {
   uint32_t nfiles = 0;
   uint64_t nblocks = 0;
   {
-    int rc = encode_stage(j, mcols, n_out, (uint32_t)h[kSlotMinS1], W, err, small, launches, nblocks, nfiles);
+    int rc = encode_stage(j, mcols, n_out, (uint32_t)h[kSlotMinS1], (uint32_t)(h[kSlotMinS1] >> 32), W, err, small, launches, nblocks, nfiles);
     if (rc) return rc;
   }
   return finish_run(j, launches, nblocks, nfiles);
@@ -712,7 +712,7 @@ int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, co
   CU(cudaGetLastError());
   uint64_t nblocks = 0;
   uint32_t nfiles = 0;
-  rc = encode_stage(j, mcols, n, (uint32_t)h[kSlotMinS1], W, err, small, launches, nblocks, nfiles);
+  rc = encode_stage(j, mcols, n, (uint32_t)h[kSlotMinS1], (uint32_t)(h[kSlotMinS1] >> 32), W, err, small, launches, nblocks, nfiles);
   if (rc) return rc;
   j->n_out = n;
   j->stats.num_output_records = n;

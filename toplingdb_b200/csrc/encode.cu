@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t entry_size(uint32_t shared, uint32_t ks, uin
 __global__ void encode_sizes_kernel(KeyCols m, const unsigned long long* __restrict__ n_dev, uint32_t* __restrict__ esz,
                                     uint8_t* __restrict__ eshared, uint32_t* __restrict__ min_s1) {
   const uint64_t n = *n_dev;
-  uint32_t mn = 0xffffffffu;
+  uint32_t mn = 0xffffffffu, mxs = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     ulonglong2 c = m.pfx[i];
     uint64_t ctr = m.tr[i];
@@ -73,18 +73,22 @@ __global__ void encode_sizes_kernel(KeyCols m, const unsigned long long* __restr
     esz[i] = s1;
     eshared[i] = (uint8_t)sh;
     mn = s1 < mn ? s1 : mn;
+    mxs = s1 > mxs ? s1 : mxs;
   }
-#pragma unroll
-  for (int d = 16; d; d >>= 1) {
-    uint32_t o = __shfl_xor_sync(0xffffffffu, mn, d);
-    mn = o < mn ? o : mn;
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mxs = __reduce_max_sync(0xffffffffu, mxs);
+  if ((threadIdx.x & 31) == 0 && mn != 0xffffffffu) {
+    atomicMin(min_s1, mn);
+    atomicMax(min_s1 + 1, mxs);  // upper half of the slot: largest entry (selects the narrow block-cut window)
   }
-  if ((threadIdx.x & 31) == 0 && mn != 0xffffffffu) atomicMin(min_s1, mn);
 }
 
 // ------------------------------------------------------------------------------------------------ block-cut window
+// PT = uint32_t when the bytes of a whole window fit 32 bits (decided on the host from the largest entry): the narrow
+// window leaves room for three CTAs per SM instead of two
+template <typename PT>
 struct Window {
-  uint64_t P[kW + 1];   // P[j] = sum of s1 of window entries < j
+  PT P[kW + 1];         // P[j] = sum of s1 of window entries < j
   uint32_t Q[kW];       // Q[j] = D[j] + Q[j - R]: restart surcharge prefix per residue class (D = s0 - s1)
   uint64_t ws[33];
   uint32_t wlen;        // entries loaded
@@ -93,7 +97,8 @@ struct Window {
 };
 
 // cooperative: load the window of tile `tile` and build P / Q
-__device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, const uint8_t* eshared, uint64_t n, uint64_t tile,
+template <typename PT>
+__device__ void build_window(Window<PT>& w, const KeyCols& m, const uint32_t* esz, const uint8_t* eshared, uint64_t n, uint64_t tile,
                              uint32_t R) {
   const uint64_t wstart = tile * (uint64_t)kTT;
   const uint32_t wlen = (uint32_t)((n - wstart) < (uint64_t)kW ? (n - wstart) : (uint64_t)kW);
@@ -122,7 +127,7 @@ __device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, c
         // D = s0 - s1 with s0 = encoded size when shared == 0
         const uint32_t d = 1u + varint_len32(ks) + sh - varint_len32(sh) - varint_len32(ks - sh);
         w.Q[j] = d;
-        w.P[j + 1] = s1v[i];
+        w.P[j + 1] = (PT)s1v[i];
         mx = s1v[i] + d > mx ? s1v[i] + d : mx;
       }
     }
@@ -149,7 +154,7 @@ __device__ void build_window(Window& w, const KeyCols& m, const uint32_t* esz, c
 #pragma unroll
   for (int i = 0; i < kPer; i++) {
     uint32_t j = j0 + i;
-    if (j <= wlen && j <= (uint32_t)kW) w.P[j] = ex;
+    if (j <= wlen && j <= (uint32_t)kW) w.P[j] = (PT)ex;
     ex += loc[i];
   }
   if (threadIdx.x == 0) {
@@ -218,16 +223,18 @@ __host__ __device__ __forceinline__ CutParams make_cut(uint32_t bs, uint32_t lim
 }
 __device__ __forceinline__ uint32_t div_r(uint32_t x, const CutParams& cp) { return cp.rshift < 32 ? x >> cp.rshift : x / cp.R; }
 // payload bytes of a block holding window entries [a, b)
-__device__ __forceinline__ uint64_t blk_payload(const Window& w, uint32_t a, uint32_t b, const CutParams& cp) {
+template <typename PT>
+__device__ __forceinline__ uint64_t blk_payload(const Window<PT>& w, uint32_t a, uint32_t b, const CutParams& cp) {
   uint32_t nrm1 = div_r(b - 1 - a, cp);  // restarts - 1
   uint32_t last = a + cp.R * nrm1;
   uint64_t q = (uint64_t)w.Q[last] - (a >= cp.R ? (uint64_t)w.Q[a - cp.R] : 0);
-  return w.P[b] - w.P[a] + q + 4ull * (nrm1 + 1) + 4;  // == BlockBuilder::CurrentSizeEstimate() (block_builder.cc:97,251)
+  return (uint64_t)(PT)(w.P[b] - w.P[a]) + q + 4ull * (nrm1 + 1) + 4;  // == BlockBuilder::CurrentSizeEstimate() (block_builder.cc:97,251)
 }
 // first b > a at which FlushBlockBySizePolicy::Update (flush_block_policy.cc:37-69) fires for a block started at a.
 // returns wlen at the end of the stream, 0xffffffff if the block does not end inside the window.
 // hint: where the block of the previous start ended (0 = none); blocks of neighbouring starts end close to each other.
-__device__ __forceinline__ uint32_t next_block(const Window& w, uint32_t a, const CutParams& cp, uint32_t hint) {
+template <typename PT>
+__device__ __forceinline__ uint32_t next_block(const Window<PT>& w, uint32_t a, const CutParams& cp, uint32_t hint) {
   const uint32_t wlen = w.wlen;
   // below `thr` neither flush condition can fire: condition 2 needs CurrentSizeEstimate > LIM and
   // CurrentSizeEstimate + (size of the next entry, at most smax + 7) > BS
@@ -254,7 +261,7 @@ __device__ __forceinline__ uint32_t next_block(const Window& w, uint32_t a, cons
   uint32_t mr = cp.rshift < 32 ? (m & (cp.R - 1)) : (m % cp.R);
   for (uint32_t b = lo; b < wlen; b++) {
     if (ec >= cp.BS) return b;
-    const uint64_t s1 = w.P[b + 1] - w.P[b];
+    const uint64_t s1 = (uint64_t)(PT)(w.P[b + 1] - w.P[b]);
     const bool at_restart = mr == 0;  // entry b would open a new restart interval
     const uint64_t d = at_restart ? (uint64_t)w.Q[b] - (b >= cp.R ? (uint64_t)w.Q[b - cp.R] : 0) : 0;
     if (cp.LIM) {  // BlockAlmostFull: EstimateSizeAfterKV (block_builder.cc:97-126) = ec + |k|+|v|+4+varints (+4 at a restart)
@@ -268,16 +275,18 @@ __device__ __forceinline__ uint32_t next_block(const Window& w, uint32_t a, cons
 }
 
 // per tile: nxt / disk for every block start inside the tile, then the transfer function for hc entry points
+template <typename PT>
 struct TablesSmem {
-  Window w;
+  Window<PT> w;
   uint16_t nxt[kTT];   // window-relative end of the block that starts at j (0xffff = does not fit the window)
   uint32_t disk[kTT];  // on-disk bytes of that block (payload + 5-byte trailer)
 };
-__global__ void __launch_bounds__(kEncThreads)
+template <typename PT>
+__global__ void __launch_bounds__(kEncThreads, sizeof(PT) == 4 ? 3 : 2)
 encode_tables_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint32_t hc, uint16_t* __restrict__ g_nxt,
                      uint32_t* __restrict__ g_disk, uint32_t* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  TablesSmem& s = *reinterpret_cast<TablesSmem*>(smem_raw);
+  TablesSmem<PT>& s = *reinterpret_cast<TablesSmem<PT>*>(smem_raw);
   const uint64_t tile = blockIdx.x, wstart = tile * (uint64_t)kTT;
   const CutParams cp = make_cut(ep.block_size, ep.block_size_limit, ep.restart_interval);
   build_window(s.w, m, wk.esz, wk.eshared, n, tile, cp.R);
@@ -1444,14 +1453,20 @@ void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork 
   unsigned g = (unsigned)((n_cap + 255) / 256);
   encode_sizes_kernel<<<g > 148 * 16 ? 148 * 16 : g, 256, 0, st>>>(m, n_dev, w.esz, w.eshared, w.min_s1);
 }
-void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st) {
+void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t max_s1, uint32_t* err,
+                          cudaStream_t st) {
   if (ntiles == 0) return;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(encode_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TablesSmem));
+    cudaFuncSetAttribute(encode_tables_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TablesSmem<uint32_t>));
+    cudaFuncSetAttribute(encode_tables_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TablesSmem<uint64_t>));
     attr = true;
   }
-  encode_tables_kernel<<<(unsigned)ntiles, kEncThreads, sizeof(TablesSmem), st>>>(m, ep, w, m.n, hc, w.nxt, w.disk, err);
+  // all prefix sums of a window stay below 2^32 when (largest entry) x (window length) does
+  if (((uint64_t)max_s1 + 64) * (uint64_t)(kW + 1) < (1ull << 32))
+    encode_tables_kernel<uint32_t><<<(unsigned)ntiles, kEncThreads, sizeof(TablesSmem<uint32_t>), st>>>(m, ep, w, m.n, hc, w.nxt, w.disk, err);
+  else
+    encode_tables_kernel<uint64_t><<<(unsigned)ntiles, kEncThreads, sizeof(TablesSmem<uint64_t>), st>>>(m, ep, w, m.n, hc, w.nxt, w.disk, err);
 }
 void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st,
                           uint64_t* launches) {

@@ -95,7 +95,7 @@ constexpr uint32_t kMaxOutFiles = 4096;
 struct EncodeWork {                  // device scratch owned by the job
   uint32_t* esz;        // n: encoded size of entry i as a non-restart entry (s1)
   uint8_t* eshared;     // n: bytes shared with the previous internal key
-  uint32_t* min_s1;     // 1: global min of esz (bounds the entry-point candidate window)
+  uint32_t* min_s1;     // 2: [0] global min of esz (bounds the entry-point candidate window), [1] global max
   TileRow* rows;        // ntiles x hc
   TileRow* grows;       // ngroups x hc: composed transfer functions of kEncGroup tiles (exit relative to the group start)
   TileState* gstate;    // ngroups: state at which the chain enters the group
@@ -114,7 +114,8 @@ struct EncodeWork {                  // device scratch owned by the job
   uint32_t* disk;       // n: on-disk bytes of that block
 };
 void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, uint64_t n_cap, cudaStream_t st);
-void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st);
+void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t max_s1, uint32_t* err,
+                          cudaStream_t st);
 void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st,
                           uint64_t* launches);
 void launch_encode_blocklist(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint64_t nblk_cap, uint32_t* err,
