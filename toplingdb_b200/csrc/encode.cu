@@ -77,9 +77,21 @@ __global__ void encode_sizes_kernel(KeyCols m, const unsigned long long* __restr
   }
   mn = __reduce_min_sync(0xffffffffu, mn);
   mxs = __reduce_max_sync(0xffffffffu, mxs);
-  if ((threadIdx.x & 31) == 0 && mn != 0xffffffffu) {
-    atomicMin(min_s1, mn);
-    atomicMax(min_s1 + 1, mxs);  // upper half of the slot: largest entry (selects the narrow block-cut window)
+  // one pair of global atomics per CTA (same-address atomics serialise: one pair per warp costs ~60 us on a full grid)
+  __shared__ uint32_t s_mn, s_mx;
+  if (threadIdx.x == 0) {
+    s_mn = 0xffffffffu;
+    s_mx = 0;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&s_mn, mn);
+    atomicMax(&s_mx, mxs);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_mn != 0xffffffffu) {
+    atomicMin(min_s1, s_mn);
+    atomicMax(min_s1 + 1, s_mx);  // upper half of the slot: largest entry (selects the narrow block-cut window)
   }
 }
 
