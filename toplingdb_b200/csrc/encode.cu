@@ -1275,6 +1275,7 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
     }
     __syncwarp();
     const uint32_t ck = block_checksum_warp(ep.checksum, img, payload, 0);
+    __syncwarp();  // the checksum's 8-byte loads may touch the trailer bytes written next
     if (lane == 0) {
       uint8_t* tp = img + payload;
       tp[0] = 0;
