@@ -68,6 +68,7 @@ struct Input {
   const uint8_t* dev = nullptr;
   InputTail tail;
 };
+constexpr uint64_t kTailFetch = 4096;  // bytes read from the end of an input: footer + metaindex + properties live there
 struct HostBuf {  // grow-only pinned host allocation (D2H target of the finished images)
   uint8_t* p = nullptr;
   size_t cap = 0;
@@ -119,7 +120,8 @@ struct b200c_job {
   uint32_t nfiles_out = 0;
   std::vector<uint64_t> run_start_h;
   HostBuf host_out;
-  std::vector<uint8_t> tails;  // staging of the per-file tails until the copy stream has consumed them
+  HostBuf pin_small, pin_tails;  // pinned staging: input tails / tail-copy records, output tails
+  DevBuf dev_small, dev_tails;
   std::vector<KernelTime> ktimes;
   size_t kt_used = 0;
   // profiling: bracket a named group of launches with events (only when params.profile != 0)
@@ -171,7 +173,7 @@ int map_dev_err(uint32_t e) {
   return fail(code, m);
 }
 
-int fetch_tail(b200c_job* j, Input& in) {
+int fetch_tail(b200c_job* j, Input& in, const uint8_t* prefetched = nullptr) {
   // footer, metaindex, properties: three tiny reads (D2H when the image lives in device memory)
   auto read = [&](uint64_t off, uint64_t n, std::vector<uint8_t>& buf) -> int {
     buf.resize(n);
@@ -184,9 +186,11 @@ int fetch_tail(b200c_job* j, Input& in) {
     return B200C_OK;
   };
   if (in.len < 53) return fail(B200C_ERR_CORRUPTION, "input shorter than a footer");
-  const uint64_t tail_n = std::min<uint64_t>(in.len, 4096);
+  const uint64_t tail_n = std::min<uint64_t>(in.len, kTailFetch);
   std::vector<uint8_t> tail, tmp;
-  int rc = read(in.len - tail_n, tail_n, tail);
+  int rc = B200C_OK;
+  if (prefetched) tail.assign(prefetched, prefetched + tail_n);  // device image: fetched together with the other inputs' tails
+  else rc = read(in.len - tail_n, tail_n, tail);
   if (rc) return rc;
   std::string e = parse_footer(tail.data() + tail_n - 53, in.len, &in.tail);
   if (!e.empty()) return fail(B200C_ERR_CORRUPTION, e);
@@ -358,7 +362,9 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     }
     // tails
     j->outputs.resize(nfiles);
-    j->tails.resize((size_t)nfiles * 4096);
+    CU(j->pin_tails.reserve((size_t)nfiles * 4096 + 64));
+    CU(j->dev_tails.reserve((size_t)nfiles * 4096 + 64));
+    std::vector<TailCopy> tcs(nfiles);
     for (uint32_t f = 0; f < nfiles; f++) {
       const FileRec& fr = frs[f];
       OutputTailInput ti;
@@ -386,8 +392,8 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       if (tail_off + tail.size() > base_off[f + 1] - base_off[f]) return fail(B200C_ERR_CUDA, "internal: output image overflow");
       const size_t so = (size_t)f * 4096;
       if (tail.size() > 4096) return fail(B200C_ERR_CUDA, "internal: tail larger than its staging slot");
-      memcpy(j->tails.data() + so, tail.data(), tail.size());
-      CU(cudaMemcpyAsync(j->out_buf.as<uint8_t>() + base_off[f] + tail_off, j->tails.data() + so, tail.size(), cudaMemcpyHostToDevice, st));
+      memcpy(j->pin_tails.p + so, tail.data(), tail.size());
+      tcs[f] = TailCopy{base_off[f] + tail_off, (uint32_t)so, (uint32_t)tail.size()};
       Output& o = j->outputs[f];
       memset(&o.meta, 0, sizeof o.meta);
       o.dev_off = base_off[f];
@@ -406,6 +412,15 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       ikey_bytes(fr.largest, o.meta.largest_ikey, &o.meta.largest_ikey_len);
       j->stats.total_output_bytes += o.meta.file_size;
     }
+    // all tails with one H2D copy (records first, then the staged bytes) and one scatter launch
+    const size_t rec_bytes = sizeof(TailCopy) * nfiles;
+    CU(j->pin_small.reserve(rec_bytes));
+    memcpy(j->pin_small.p, tcs.data(), rec_bytes);
+    CU(j->dev_small.reserve(rec_bytes));
+    CU(cudaMemcpyAsync(j->dev_small.p, j->pin_small.p, rec_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(j->dev_tails.p, j->pin_tails.p, (size_t)nfiles * 4096, cudaMemcpyHostToDevice, st));
+    launch_scatter_tails(j->dev_small.as<TailCopy>(), nfiles, j->dev_tails.as<uint8_t>(), j->out_buf.as<uint8_t>(), st);
+    launches++;
   }
   return B200C_OK;
 }
@@ -477,9 +492,23 @@ int run_job(b200c_job* j, int until) {
   CU(cudaEventRecord(j->ev[0], st));
   uint64_t nblk = 0, n_props = 0, in_bytes = 0;
   std::vector<FileDesc> fds(k);
+  {  // tails of device-resident inputs: one batch of small D2H copies and a single synchronisation
+    bool any_dev = false;
+    for (int i = 0; i < k; i++) any_dev = any_dev || j->inputs[i].mem_kind != B200C_MEM_HOST;
+    if (any_dev) {
+      CU(j->pin_small.reserve((size_t)k * kTailFetch));
+      for (int i = 0; i < k; i++) {
+        const Input& in = j->inputs[i];
+        if (in.mem_kind == B200C_MEM_HOST || in.len < 53) continue;
+        const uint64_t tn = std::min<uint64_t>(in.len, kTailFetch);
+        CU(cudaMemcpyAsync(j->pin_small.p + (size_t)i * kTailFetch, in.data + in.len - tn, tn, cudaMemcpyDeviceToHost, st));
+      }
+      CU(cudaStreamSynchronize(st));
+    }
+  }
   for (int i = 0; i < k; i++) {
     Input& in = j->inputs[i];
-    int rc = fetch_tail(j, in);
+    int rc = fetch_tail(j, in, in.mem_kind != B200C_MEM_HOST && in.len >= 53 ? j->pin_small.p + (size_t)i * kTailFetch : nullptr);
     if (rc) return rc;
     if (in.mem_kind == B200C_MEM_HOST) {
       CU(in.staged.reserve(in.len + 64));
@@ -844,6 +873,10 @@ void b200c_job_destroy(b200c_job* j) {
   for (DevBuf* b : all) b->release();
   for (auto& in : j->inputs) in.staged.release();
   j->host_out.release();
+  j->pin_small.release();
+  j->pin_tails.release();
+  j->dev_small.release();
+  j->dev_tails.release();
   for (auto& kt : j->ktimes) {
     cudaEventDestroy(kt.a);
     cudaEventDestroy(kt.b);

@@ -1460,7 +1460,16 @@ __global__ void block_checksums_kernel(uint32_t type, const uint8_t* __restrict_
   if ((threadIdx.x & 31) == 0) out[i] = ck;
 }
 
+// file tails (properties | metaindex | footer, built on the host) from their staging buffer into the output images
+__global__ void scatter_tails_kernel(const TailCopy* __restrict__ recs, const uint8_t* __restrict__ staged, uint8_t* __restrict__ out) {
+  const TailCopy r = recs[blockIdx.x];
+  for (uint32_t i = threadIdx.x; i < r.len; i += blockDim.x) out[r.dst_off + i] = staged[r.src_off + i];
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
+void launch_scatter_tails(const TailCopy* recs, uint32_t n, const uint8_t* staged, uint8_t* out, cudaStream_t st) {
+  if (n) scatter_tails_kernel<<<n, 256, 0, st>>>(recs, staged, out);
+}
 void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, uint64_t n_cap, cudaStream_t st) {
   if (n_cap == 0) return;
   unsigned g = (unsigned)((n_cap + 255) / 256);

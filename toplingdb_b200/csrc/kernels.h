@@ -28,6 +28,12 @@ void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint
 void launch_gather_values(KeyCols in, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st);
 void launch_meta_vlen(const uint32_t* meta, uint64_t n, uint32_t* vlen, cudaStream_t st);
 
+struct TailCopy {  // one finished file tail: staged bytes [src_off, src_off + len) -> output buffer at dst_off
+  uint64_t dst_off;
+  uint32_t src_off, len;
+};
+void launch_scatter_tails(const TailCopy* recs, uint32_t n, const uint8_t* staged, uint8_t* out, cudaStream_t st);
+
 // ---- merge.cu
 constexpr int kMergeTile = 2048;     // merged entries per CTA tile
 constexpr int kMaxRuns = 64;
