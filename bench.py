@@ -47,6 +47,24 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        # NVML in-process (a sample every ~2 ms, so that even a 50 ms timed region is covered); nvidia-smi as a fallback
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [(0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6)]  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap -> row columns
+            while not self.stop_flag:
+                r = int(get_reasons(h))
+                row = [str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx), "0", "", "", "", ""]
+                for bit, col in bits:
+                    row[col] = "Active" if r & bit else "Not Active"
+                self.rows.append(row)
+                time.sleep(0.002)
+            return
+        except Exception:
+            pass
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
@@ -56,7 +74,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:
