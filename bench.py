@@ -123,7 +123,7 @@ def main():
     ap.add_argument("--sample-mb", type=int, default=192, help="raw KV MiB of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-depth", type=int, default=3, help="compaction jobs in flight in the end-to-end measurement")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="compaction jobs in flight in the end-to-end measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -77,7 +77,8 @@ struct HostBuf {  // grow-only pinned host allocation (D2H target of the finishe
     if (p) cudaFreeHost(p);
     p = nullptr;
     cap = 0;
-    cudaError_t e = cudaMallocHost((void**)&p, n + (n >> 4) + 256);
+    // mapped: kernels read / write it directly (same address under UVA), see read_small()
+    cudaError_t e = cudaHostAlloc((void**)&p, n + (n >> 4) + 256, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e == cudaSuccess) cap = n + (n >> 4) + 256;
     return e;
   }
@@ -120,8 +121,8 @@ struct b200c_job {
   uint32_t nfiles_out = 0;
   std::vector<uint64_t> run_start_h;
   HostBuf host_out;
-  HostBuf pin_small, pin_tails;  // pinned staging: input tails / tail-copy records, output tails
-  DevBuf dev_small, dev_tails;
+  HostBuf pin_small, pin_tails, pin_rd, pin_up;
+  size_t pin_up_used = 0;  // pinned staging: input tails / tail-copy records, output tails
   std::vector<KernelTime> ktimes;
   size_t kt_used = 0;
   // profiling: bracket a named group of launches with events (only when params.profile != 0)
@@ -246,6 +247,43 @@ void ikey_bytes(const KeyRec& k, uint8_t* out, uint32_t* len) {
 }
 
 // encode stage: merged columns (device) -> output file images + metas.  `h` holds the small-slot snapshot read at sync #1.
+// Small host -> device uploads (descriptors, offsets, snapshots): staged in mapped pinned memory and moved by a tiny kernel, for
+// the same reason as read_small(): a cudaMemcpy would wait on the copy engine behind other jobs' multi-GB input uploads.
+// The staging area is a bump allocator that is reset at the start of a run (the previous run has been synchronised).
+int upload_small(b200c_job* j, void* dev_dst, const void* host_src, size_t n) {
+  const size_t kCap = 256 * 1024;
+  CU(j->pin_up.reserve(kCap));
+  const size_t off = (j->pin_up_used + 15) & ~(size_t)15;
+  if (off + n > kCap) {  // unusually many files / snapshots: plain copy
+    CU(cudaMemcpyAsync(dev_dst, host_src, n, cudaMemcpyHostToDevice, j->st));
+    return B200C_OK;
+  }
+  memcpy(j->pin_up.p + off, host_src, n);
+  j->pin_up_used = off + n;
+  launch_copy_small(j->pin_up.p + off, dev_dst, (uint32_t)n, j->st);
+  return B200C_OK;
+}
+
+// Small device -> host reads (counters, per-file records) go through a tiny kernel that writes mapped pinned memory, not
+// through cudaMemcpy: a D2H copy would queue on the copy engine behind the multi-GB output downloads of OTHER jobs running
+// on the same device, and every host decision point of this job would wait for them.
+// Copies the `small` slots and (files != nullptr) the first *nfiles_dev file records, then synchronises the stream.
+constexpr size_t kRdSmall = kSmallSlots * 8;
+int read_small(b200c_job* j, const uint64_t* small, uint64_t* h, const FileRec* files, std::vector<FileRec>* frs) {
+  CU(j->pin_rd.reserve(kRdSmall + sizeof(FileRec) * (size_t)kMaxOutFiles));
+  launch_gather_small(small, (uint32_t)kRdSmall, files, files ? small + kSlotTotals + 1 : nullptr, j->pin_rd.p, j->st);
+  CU(cudaStreamSynchronize(j->st));
+  CU(cudaGetLastError());
+  memcpy(h, j->pin_rd.p, kRdSmall);
+  if (files && frs) {
+    uint64_t n = h[kSlotTotals + 1];
+    if (n > kMaxOutFiles) n = kMaxOutFiles;
+    frs->resize(n);
+    memcpy(frs->data(), j->pin_rd.p + kRdSmall, sizeof(FileRec) * n);
+  }
+  return B200C_OK;
+}
+
 int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, uint32_t max_s1, EncodeWork& W, uint32_t* err, uint64_t* small,
                  uint64_t& launches, uint64_t& nblocks, uint32_t& nfiles) {
   const b200c_params& P = j->p;
@@ -293,19 +331,15 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     launch_encode_stitch(mcols, ep, W, etiles, hc, err, st, &launches);
     j->kt_end();
     launches += 1;
-    CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));  // sync #2: number of blocks / files
-    CU(cudaGetLastError());
     {
-      int rc = map_dev_err((uint32_t)h[kSlotErr]);
+      int rc = read_small(j, small, h, W.files, &frs);  // sync #2: number of blocks / files, per-file records
+      if (rc) return rc;
+      rc = map_dev_err((uint32_t)h[kSlotErr]);
       if (rc) return rc;
     }
     nblocks = h[kSlotTotals];
     nfiles = (uint32_t)h[kSlotTotals + 1];
     if (nfiles == 0 || nfiles > kMaxOutFiles) return fail(B200C_ERR_CUDA, "internal: bad output file count");
-    frs.resize(nfiles);
-    CU(cudaMemcpyAsync(frs.data(), W.files, sizeof(FileRec) * nfiles, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
     CU(j->blocks.reserve(sizeof(BlockRec) * (nblocks + 1)));
     CU(j->idx_esz.reserve(4 * (nblocks + 1)));
     CU(j->idx_eoff.reserve(8 * (nblocks + 1)));
@@ -329,7 +363,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       for (uint32_t f = 0; f < nfiles; f++) coff[f + 1] = coff[f] + (frs[f].n_blocks * 48 + 64) / 1024 + 1;
       CU(j->idx_contrib.reserve(64 * (coff[nfiles] + 1)));
       CU(j->idx_contrib_off.reserve(8 * (nfiles + 1)));
-      CU(cudaMemcpyAsync(j->idx_contrib_off.p, coff.data(), 8 * (nfiles + 1), cudaMemcpyHostToDevice, st));
+      if (int rc = upload_small(j, j->idx_contrib_off.p, coff.data(), 8 * (nfiles + 1))) return rc;
       CU(cudaStreamSynchronize(st));  // coff is a temporary
       W.idx_contrib = j->idx_contrib.as<uint64_t>();
       W.idx_contrib_off = j->idx_contrib_off.as<uint64_t>();
@@ -337,7 +371,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     std::vector<uint8_t*> bases(nfiles);
     for (uint32_t f = 0; f < nfiles; f++) bases[f] = j->out_buf.as<uint8_t>() + base_off[f];
     CU(j->out_base_d.reserve(8 * nfiles));
-    CU(cudaMemcpyAsync(j->out_base_d.p, bases.data(), 8 * nfiles, cudaMemcpyHostToDevice, st));
+    if (int rc = upload_small(j, j->out_base_d.p, bases.data(), 8 * nfiles)) return rc;
     uint8_t* const* out_base_d = j->out_base_d.as<uint8_t*>();
     j->kt_begin("encode.blocklist");
     launch_encode_blocklist(mcols, ep, W, etiles, nblocks, err, st);
@@ -352,18 +386,16 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     j->kt_begin("encode.index");
     launch_encode_index(mcols, ep, W, nblocks, nfiles, out_base_d, err, st, &launches);
     j->kt_end();
-    CU(cudaMemcpyAsync(frs.data(), W.files, sizeof(FileRec) * nfiles, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));  // sync #3: per-file records
-    CU(cudaGetLastError());
     {
-      int rc = map_dev_err((uint32_t)h[kSlotErr]);
+      int rc = read_small(j, small, h, W.files, &frs);  // sync #3: per-file records
+      if (rc) return rc;
+      if (frs.size() != nfiles) return fail(B200C_ERR_CUDA, "internal: output file count changed");
+      rc = map_dev_err((uint32_t)h[kSlotErr]);
       if (rc) return rc;
     }
     // tails
     j->outputs.resize(nfiles);
     CU(j->pin_tails.reserve((size_t)nfiles * 4096 + 64));
-    CU(j->dev_tails.reserve((size_t)nfiles * 4096 + 64));
     std::vector<TailCopy> tcs(nfiles);
     for (uint32_t f = 0; f < nfiles; f++) {
       const FileRec& fr = frs[f];
@@ -412,14 +444,12 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       ikey_bytes(fr.largest, o.meta.largest_ikey, &o.meta.largest_ikey_len);
       j->stats.total_output_bytes += o.meta.file_size;
     }
-    // all tails with one H2D copy (records first, then the staged bytes) and one scatter launch
+    // all tails with one scatter launch
     const size_t rec_bytes = sizeof(TailCopy) * nfiles;
     CU(j->pin_small.reserve(rec_bytes));
     memcpy(j->pin_small.p, tcs.data(), rec_bytes);
-    CU(j->dev_small.reserve(rec_bytes));
-    CU(cudaMemcpyAsync(j->dev_small.p, j->pin_small.p, rec_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(j->dev_tails.p, j->pin_tails.p, (size_t)nfiles * 4096, cudaMemcpyHostToDevice, st));
-    launch_scatter_tails(j->dev_small.as<TailCopy>(), nfiles, j->dev_tails.as<uint8_t>(), j->out_buf.as<uint8_t>(), st);
+    // the scatter kernel reads records and bytes straight from mapped pinned memory: no copy-engine queue involved
+    launch_scatter_tails(reinterpret_cast<const TailCopy*>(j->pin_small.p), nfiles, j->pin_tails.p, j->out_buf.as<uint8_t>(), st);
     launches++;
   }
   return B200C_OK;
@@ -483,6 +513,7 @@ int run_job(b200c_job* j, int until) {
   j->ran = false;
   j->stage_done = 0;
   j->kt_used = 0;
+  j->pin_up_used = 0;
   memset(&j->stats, 0, sizeof j->stats);
   const int k = (int)j->inputs.size();
   if (k == 0) return fail(B200C_ERR_INVALID_ARGUMENT, "job has no inputs");
@@ -546,10 +577,10 @@ int run_job(b200c_job* j, int until) {
   uint32_t* err = reinterpret_cast<uint32_t*>(small + kSlotErr);
   {
     uint32_t ff = 0xffffffffu;
-    CU(cudaMemcpyAsync(small + kSlotMinS1, &ff, 4, cudaMemcpyHostToDevice, st));
+    if (int rc = upload_small(j, small + kSlotMinS1, &ff, 4)) return rc;
   }
   CU(j->files_d.reserve(sizeof(FileDesc) * k));
-  CU(cudaMemcpyAsync(j->files_d.p, fds.data(), sizeof(FileDesc) * k, cudaMemcpyHostToDevice, st));
+  if (int rc = upload_small(j, j->files_d.p, fds.data(), sizeof(FileDesc) * k)) return rc;
   const uint64_t N = n_props;
   CU(j->blk_off.reserve(8 * (nblk + 1)));
   CU(j->blk_size.reserve(4 * (nblk + 1)));
@@ -605,7 +636,8 @@ int run_job(b200c_job* j, int until) {
   CU(j->tile_state.reserve(8 * (mtiles + 1)));
   CU(cudaMemsetAsync(j->tile_state.p, 0, 8 * (mtiles + 1), st));
   CU(j->snaps_d.reserve(8 * (P.num_snapshots + 1)));
-  if (P.num_snapshots) CU(cudaMemcpyAsync(j->snaps_d.p, j->snapshots.data(), 8 * P.num_snapshots, cudaMemcpyHostToDevice, st));
+  if (P.num_snapshots)
+    if (int rc = upload_small(j, j->snaps_d.p, j->snapshots.data(), 8 * P.num_snapshots)) return rc;
   CU(j->mrg[0].reserve(16 * (N + 1)));
   CU(j->mrg[1].reserve(8 * (N + 1)));
   CU(j->mrg[2].reserve(8 * (N + 1)));
@@ -645,11 +677,10 @@ int run_job(b200c_job* j, int until) {
     launches++;
   }
   uint64_t h[kSmallSlots];
-  CU(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));  // sync #1: survivors, smallest entry, error word
-  CU(cudaGetLastError());
   {
-    int rc = map_dev_err((uint32_t)h[kSlotErr]);
+    int rc = read_small(j, small, h, nullptr, nullptr);  // sync #1: survivors, smallest entry, error word
+    if (rc) return rc;
+    rc = map_dev_err((uint32_t)h[kSlotErr]);
     if (rc) return rc;
   }
   if (h[kSlotTotalIn] != N) return fail(B200C_ERR_CORRUPTION, "decoded entry count differs from rocksdb.num.entries");
@@ -697,6 +728,7 @@ int job_prepare(b200c_job* j) {
   j->ran = false;
   j->stage_done = 0;
   j->kt_used = 0;
+  j->pin_up_used = 0;
   memset(&j->stats, 0, sizeof j->stats);
   return B200C_OK;
 }
@@ -874,9 +906,9 @@ void b200c_job_destroy(b200c_job* j) {
   for (auto& in : j->inputs) in.staged.release();
   j->host_out.release();
   j->pin_small.release();
+  j->pin_rd.release();
+  j->pin_up.release();
   j->pin_tails.release();
-  j->dev_small.release();
-  j->dev_tails.release();
   for (auto& kt : j->ktimes) {
     cudaEventDestroy(kt.a);
     cudaEventDestroy(kt.b);

@@ -1466,7 +1466,32 @@ __global__ void scatter_tails_kernel(const TailCopy* __restrict__ recs, const ui
   for (uint32_t i = threadIdx.x; i < r.len; i += blockDim.x) out[r.dst_off + i] = staged[r.src_off + i];
 }
 
+// `small` slots (+ the first *nfiles_dev file records behind them) into mapped pinned host memory
+__global__ void gather_small_kernel(const uint64_t* __restrict__ small, uint32_t small_words, const FileRec* __restrict__ files,
+                                    const uint64_t* __restrict__ nfiles_dev, uint64_t* __restrict__ dst) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (uint32_t i = t; i < small_words; i += nt) dst[i] = small[i];
+  if (files) {
+    uint64_t n = *nfiles_dev;
+    if (n > kMaxOutFiles) n = kMaxOutFiles;
+    const uint64_t words = n * (sizeof(FileRec) / 8);
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(files);
+    for (uint64_t i = t; i < words; i += nt) dst[small_words + i] = src[i];
+  }
+}
+static_assert(sizeof(FileRec) % 8 == 0, "FileRec is copied word-wise");
+
 // ------------------------------------------------------------------------------------------------ launchers
+void launch_gather_small(const uint64_t* small, uint32_t small_bytes, const FileRec* files, const uint64_t* nfiles_dev, uint8_t* dst,
+                         cudaStream_t st) {
+  gather_small_kernel<<<files ? 8 : 1, 256, 0, st>>>(small, small_bytes / 8, files, nfiles_dev, reinterpret_cast<uint64_t*>(dst));
+}
+__global__ void copy_small_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n) {
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+void launch_copy_small(const void* src, void* dst, uint32_t n, cudaStream_t st) {
+  if (n) copy_small_kernel<<<1, 256, 0, st>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n);
+}
 void launch_scatter_tails(const TailCopy* recs, uint32_t n, const uint8_t* staged, uint8_t* out, cudaStream_t st) {
   if (n) scatter_tails_kernel<<<n, 256, 0, st>>>(recs, staged, out);
 }

@@ -32,6 +32,10 @@ struct TailCopy {  // one finished file tail: staged bytes [src_off, src_off + l
   uint64_t dst_off;
   uint32_t src_off, len;
 };
+struct FileRec;
+void launch_gather_small(const uint64_t* small, uint32_t small_bytes, const FileRec* files, const uint64_t* nfiles_dev, uint8_t* dst,
+                         cudaStream_t st);
+void launch_copy_small(const void* src, void* dst, uint32_t n, cudaStream_t st);  // byte copy, either side may be mapped host memory
 void launch_scatter_tails(const TailCopy* recs, uint32_t n, const uint8_t* staged, uint8_t* out, cudaStream_t st);
 
 // ---- merge.cu
