@@ -752,10 +752,11 @@ void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint
   const int smem = kDecWarps * (int)sizeof(DecWarpSmem);
   if (!occ) {
     const char* e = getenv("B200C_DECODE_CTAS_PER_SM");  // tuning knob: 2 = no register spills, 3 / 4 = more warps
-    occ = e && atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;
+    occ = e && atoi(e) >= 2 && atoi(e) <= 5 ? atoi(e) : 4;  // 4: 64 registers with a small spill, but 32 independent warps per SM
     cudaFuncSetAttribute(block_decode_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(block_decode_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(block_decode_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(block_decode_fused_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   }
   const unsigned per = kDecWarps;
   unsigned want = (nblk + per - 1) / per, cap = (unsigned)sms * (unsigned)occ;
@@ -765,6 +766,7 @@ void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint
                                                                     blk_state, ticket, run_start, total_out, err)
   if (occ == 2) B200C_LAUNCH_DEC(2);
   else if (occ == 4) B200C_LAUNCH_DEC(4);
+  else if (occ == 5) B200C_LAUNCH_DEC(5);
   else B200C_LAUNCH_DEC(3);
 #undef B200C_LAUNCH_DEC
 }

@@ -18,6 +18,8 @@
 //                     into a shared-memory image, restart array, checksum, coalesced store into the file image
 //   encode_index_*    per block separator keys, per-file index block, its checksum
 // HBM-bound; algorithmic bytes of encode_emit = 36 B of columns + value bytes read + block bytes written per entry.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "scan.cuh"
@@ -1094,7 +1096,8 @@ constexpr int kEmitMaxEntries = 32 * kEmitPerLane;  // 96 entries per block on t
 // image in shared memory, then the warp appends restart array + footer, checksums the image and stores it re-aligned
 // to the file offset.  Global loads are issued in groups (size columns; key columns; value words) so that a block costs
 // three DRAM round trips.  Blocks with more than 96 entries or larger than the image slot take emit_block_warp.
-__global__ void __launch_bounds__(kEmitWarps * 32, 3)
+template <int kMinCtas>
+__global__ void __launch_bounds__(kEmitWarps * 32, kMinCtas)
 encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, uint8_t* const* __restrict__ out_base,
                    uint32_t slot_bytes, uint32_t* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -1550,19 +1553,25 @@ uint32_t encode_emit_slice(uint32_t block_size) {
 void launch_encode_emit(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nblocks, uint8_t* const* out_base, uint32_t* err, int sms,
                         cudaStream_t st) {
   if (nblocks == 0) return;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(encode_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr = true;
+  static int occ = 0;
+  if (!occ) {
+    const char* e = getenv("B200C_EMIT_CTAS_PER_SM");  // tuning knob
+    occ = e && atoi(e) >= 3 && atoi(e) <= 5 ? atoi(e) : 4;  // 4: 64 registers with a small spill, but 32 independent warps per SM
+    cudaFuncSetAttribute(encode_emit_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(encode_emit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(encode_emit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
   const uint32_t slot = encode_emit_slice(ep.block_size);
   const size_t smem = (size_t)slot * kEmitWarps;
-  unsigned per_sm = (unsigned)((224 * 1024) / (smem + 1024));
+  unsigned per_sm = (unsigned)((228 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 3) per_sm = 3;
+  if (per_sm > (unsigned)occ) per_sm = (unsigned)occ;
   const uint64_t want = (nblocks + kEmitWarps - 1) / kEmitWarps;
   const uint64_t cap = (uint64_t)sms * per_sm;
-  encode_emit_kernel<<<(unsigned)(want < cap ? want : cap), kEmitWarps * 32, smem, st>>>(m, ep, w, nblocks, out_base, slot, err);
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (occ == 4) encode_emit_kernel<4><<<grid, kEmitWarps * 32, smem, st>>>(m, ep, w, nblocks, out_base, slot, err);
+  else if (occ == 5) encode_emit_kernel<5><<<grid, kEmitWarps * 32, smem, st>>>(m, ep, w, nblocks, out_base, slot, err);
+  else encode_emit_kernel<3><<<grid, kEmitWarps * 32, smem, st>>>(m, ep, w, nblocks, out_base, slot, err);
 }
 void launch_encode_index(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nblocks, uint32_t nfiles, uint8_t* const* out_base,
                          uint32_t* err, cudaStream_t st, uint64_t* launches) {
