@@ -116,7 +116,7 @@ struct b200c_job {
   // device state
   DevBuf files_d, blk_off, blk_size, blk_state, scan_tmp, run_start, small;  // small: err, totals, counters...
   DevBuf dec[4], mrg[4], splits, tile_state, snaps_d;
-  DevBuf esz, eshared, nxt, disk, rows, tstate, grows, gstate, gflag, idx_contrib, idx_contrib_off, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
+  DevBuf esz, eshared, tstat, nxt, disk, rows, tstate, grows, gstate, gflag, idx_contrib, idx_contrib_off, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
   uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
   uint32_t nfiles_out = 0;
   std::vector<uint64_t> run_start_h;
@@ -644,6 +644,7 @@ int run_job(b200c_job* j, int until) {
   CU(j->mrg[3].reserve(4 * (N + 1)));
   CU(j->esz.reserve(4 * (N + 1)));
   CU(j->eshared.reserve(N + 1));
+  CU(j->tstat.reserve(sizeof(TileStat) * (N / kEncTile + 2)));
   KeyColsMut mrg{j->mrg[0].as<ulonglong2>(), j->mrg[1].as<uint64_t>(), j->mrg[2].as<uint64_t>(), j->mrg[3].as<uint32_t>()};
   MergeParams mp;
   mp.nruns = (uint32_t)k;
@@ -656,6 +657,7 @@ int run_job(b200c_job* j, int until) {
   memset(&W, 0, sizeof W);
   W.esz = j->esz.as<uint32_t>();
   W.eshared = j->eshared.as<uint8_t>();
+  W.tstat = j->tstat.as<TileStat>();
   W.min_s1 = reinterpret_cast<uint32_t*>(small + kSlotMinS1);
   W.totals = small + kSlotTotals;
   if (N) {
@@ -752,11 +754,13 @@ int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, co
   CU(cudaMemcpyAsync(&counters->n_out, &n, 8, cudaMemcpyHostToDevice, st));
   CU(j->esz.reserve(4 * (n + 1)));
   CU(j->eshared.reserve(n + 1));
+  CU(j->tstat.reserve(sizeof(TileStat) * (n / kEncTile + 2)));
   CU(j->scan_tmp.reserve(8 * ((n / kScanTile) + 2)));
   EncodeWork W;
   memset(&W, 0, sizeof W);
   W.esz = j->esz.as<uint32_t>();
   W.eshared = j->eshared.as<uint8_t>();
+  W.tstat = j->tstat.as<TileStat>();
   W.min_s1 = reinterpret_cast<uint32_t*>(small + kSlotMinS1);
   W.totals = small + kSlotTotals;
   KeyCols mcols{static_cast<const ulonglong2*>(pfx), static_cast<const uint64_t*>(tr), static_cast<const uint64_t*>(vref),
@@ -900,7 +904,7 @@ void b200c_job_destroy(b200c_job* j) {
   cudaSetDevice(j->p.device);
   DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->small,
                    &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
-                   &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
+                   &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->tstat, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};
   for (DevBuf* b : all) b->release();
   for (auto& in : j->inputs) in.staged.release();

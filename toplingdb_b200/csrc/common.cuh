@@ -298,7 +298,24 @@ __device__ inline uint64_t xxh3_64_warp_t(const uint8_t* in, uint64_t len, const
   const uint64_t nb_blocks = (len - 1) / 1024;
   const uint64_t kscr = sec64g(192 - 64 + 8 * a);
   const XxhLaneSecret ks = xxh_lane_secret();
-  for (uint64_t n = 0; n <= nb_blocks; n++) {
+  uint64_t n = 0;
+  if (pre) {
+    // precomputed block contributions: the scramble chain is sequential, the loads are not -- fetch eight blocks' values
+    // before the first is consumed (a load-use loop body costs one memory round trip per iteration)
+    for (; n + 8 <= nb_blocks; n += 8) {
+      uint64_t pv[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) pv[q] = pre[8 * (n + q) + a];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        acc += pv[q];
+        acc ^= acc >> 47;
+        acc ^= kscr;
+        acc *= kP32_1;
+      }
+    }
+  }
+  for (; n <= nb_blocks; n++) {
     const uint64_t nstripes = n < nb_blocks ? 16 : ((len - 1) - 1024 * nb_blocks) / 64;
     acc += (pre && n < nb_blocks) ? pre[8 * n + a] : xxh3_block_contrib<kAligned8>(in + n * 1024, nstripes, ks);
     if (n < nb_blocks) {

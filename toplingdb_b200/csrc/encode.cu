@@ -59,32 +59,71 @@ __device__ __forceinline__ uint32_t entry_size(uint32_t shared, uint32_t ks, uin
   return varint_len32(shared) + varint_len32(ks - shared) + varint_len32(vs) + (ks - shared) + vs;
 }
 
-__global__ void encode_sizes_kernel(KeyCols m, const unsigned long long* __restrict__ n_dev, uint32_t* __restrict__ esz,
-                                    uint8_t* __restrict__ eshared, uint32_t* __restrict__ min_s1) {
+// One CTA per tile of kEncTile merged entries (grid-stride over tiles): shared-prefix length + encoded size of every entry, the
+// global min / max entry size, and the tile's partial sums for the per-file statistics (so that the statistics pass reads
+// 40 bytes per tile instead of 12 bytes per entry).
+__global__ void __launch_bounds__(256)
+encode_sizes_kernel(KeyCols m, const unsigned long long* __restrict__ n_dev, uint32_t* __restrict__ esz, uint8_t* __restrict__ eshared,
+                    TileStat* __restrict__ tstat, uint32_t* __restrict__ min_s1) {
   const uint64_t n = *n_dev;
+  const uint64_t ntiles = (n + kEncTile - 1) / kEncTile;
   uint32_t mn = 0xffffffffu, mxs = 0;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    ulonglong2 c = m.pfx[i];
-    uint64_t ctr = m.tr[i];
-    uint32_t cm = m.meta[i], ulen = meta_ulen(cm), vs = meta_vlen(cm), ks = ulen + 8, sh = 0;
-    if (i > 0) {
-      ulonglong2 p = m.pfx[i - 1];
-      sh = shared_prefix(c.x, c.y, ulen, ctr, p.x, p.y, meta_ulen(m.meta[i - 1]), m.tr[i - 1]);
-    }
-    uint32_t s1 = entry_size(sh, ks, vs);
-    esz[i] = s1;
-    eshared[i] = (uint8_t)sh;
-    mn = s1 < mn ? s1 : mn;
-    mxs = s1 > mxs ? s1 : mxs;
-  }
-  mn = __reduce_min_sync(0xffffffffu, mn);
-  mxs = __reduce_max_sync(0xffffffffu, mxs);
-  // one pair of global atomics per CTA (same-address atomics serialise: one pair per warp costs ~60 us on a full grid)
+  __shared__ unsigned long long red[5];
   __shared__ uint32_t s_mn, s_mx;
   if (threadIdx.x == 0) {
     s_mn = 0xffffffffu;
     s_mx = 0;
   }
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (threadIdx.x < 5) red[threadIdx.x] = threadIdx.x == 3 ? ~0ull : 0ull;
+    __syncthreads();
+    const uint64_t t0 = tile * kEncTile, t1 = (t0 + kEncTile) < n ? (t0 + kEncTile) : n;
+    unsigned long long kb = 0, vb = 0, nd = 0, smin = ~0ull, smax = 0;
+#pragma unroll 4
+    for (uint64_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
+      const ulonglong2 c = m.pfx[i];
+      const uint64_t ctr = m.tr[i];
+      const uint32_t cm = m.meta[i], ulen = meta_ulen(cm), vs = meta_vlen(cm), ks = ulen + 8;
+      uint32_t sh = 0;
+      if (i > 0) {
+        const ulonglong2 p = m.pfx[i - 1];
+        sh = shared_prefix(c.x, c.y, ulen, ctr, p.x, p.y, meta_ulen(m.meta[i - 1]), m.tr[i - 1]);
+      }
+      const uint32_t s1 = entry_size(sh, ks, vs);
+      esz[i] = s1;
+      eshared[i] = (uint8_t)sh;
+      mn = s1 < mn ? s1 : mn;
+      mxs = s1 > mxs ? s1 : mxs;
+      kb += ks;
+      vb += vs;
+      nd += (ctr & 0xff) == kTypeDeletion;
+      const uint64_t sq = ctr >> 8;
+      smin = sq < smin ? sq : smin;
+      smax = sq > smax ? sq : smax;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      kb += __shfl_xor_sync(0xffffffffu, kb, d);
+      vb += __shfl_xor_sync(0xffffffffu, vb, d);
+      nd += __shfl_xor_sync(0xffffffffu, nd, d);
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, smin, d), b = __shfl_xor_sync(0xffffffffu, smax, d);
+      smin = a < smin ? a : smin;
+      smax = b > smax ? b : smax;
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&red[0], kb);
+      atomicAdd(&red[1], vb);
+      atomicAdd(&red[2], nd);
+      atomicMin(&red[3], smin);
+      atomicMax(&red[4], smax);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) tstat[tile] = TileStat{red[0], red[1], red[2], red[3], red[4]};
+    __syncthreads();
+  }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mxs = __reduce_max_sync(0xffffffffu, mxs);
+  // one pair of global atomics per CTA (same-address atomics serialise)
   __syncthreads();
   if ((threadIdx.x & 31) == 0) {
     atomicMin(&s_mn, mn);
@@ -399,13 +438,23 @@ __device__ __forceinline__ uint64_t single_entry_block_bytes(const KeyCols& m, c
 // Follow the real chain through one tile whose nxt/disk sit in shared memory, applying the output-file cut rule
 // (compaction_outputs.cc:277: cut in front of the first entry added after the flushed size reached the maximum).
 // emit != nullptr: write BlockRecs.  files != nullptr: write FileRecs.
-__device__ bool chase_tile(const uint16_t* nxt, const uint32_t* disk, uint64_t tstart, uint32_t tl, uint64_t n, const EncodeParams& ep,
-                           const KeyCols& m, const EncodeWork& wk, WalkState& st, FileRec* files, BlockRec* emit, uint64_t emit_cap,
-                           uint32_t* err) {
-  while (st.a < tstart + tl) {
+// The walk state is copied into registers for the loop (taking its address would put it in local memory and turn every
+// step of this single-thread pointer chase into a chain of dependent local loads and stores).
+__device__ __forceinline__ bool chase_tile(const uint16_t* nxt, const uint32_t* disk, uint64_t tstart, uint32_t tl, uint64_t n,
+                                           const EncodeParams& ep, const KeyCols& m, const EncodeWork& wk, WalkState& st_io, FileRec* files,
+                                           BlockRec* emit, uint64_t emit_cap, uint32_t* err) {
+  WalkState st = st_io;
+  const uint64_t tend = tstart + tl;
+  const bool cut_files = ep.output_level != 0;
+  const uint64_t fmax = ep.max_output_file_size;
+  bool ok = true;
+  while (st.a < tend) {
     const uint32_t x = (uint32_t)(st.a - tstart);
     const uint32_t yr = nxt[x];
-    if (yr == 0xffff || yr <= x) return false;
+    if (yr == 0xffff || yr <= x) {
+      ok = false;
+      break;
+    }
     const uint64_t y = tstart + yr;
     if (emit && st.blk < emit_cap) emit[st.blk] = BlockRec{st.a, st.foff, st.f, (uint32_t)(y - st.a)};
     st.foff += disk[x];
@@ -414,9 +463,9 @@ __device__ bool chase_tile(const uint16_t* nxt, const uint32_t* disk, uint64_t t
       close_file(files, st, n, err);
       st.a = n;
       st.f++;
-      return true;
+      break;
     }
-    if (ep.output_level != 0 && st.foff >= ep.max_output_file_size) {
+    if (cut_files && st.foff >= fmax) {
       // entry y (whose Add flushed the block) still goes to this file and ends it as a single-entry block
       const uint64_t d1 = single_entry_block_bytes(m, wk, y);
       if (emit && st.blk < emit_cap) emit[st.blk] = BlockRec{y, st.foff, st.f, 1u};
@@ -432,7 +481,8 @@ __device__ bool chase_tile(const uint16_t* nxt, const uint32_t* disk, uint64_t t
       st.a = y;
     }
   }
-  return true;
+  st_io = st;
+  return ok;
 }
 
 constexpr int kEncGroup = 16;  // tiles per group
@@ -499,33 +549,39 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
   __syncthreads();
   for (;;) {
     if (threadIdx.x == 0) {
+      // everything the serial walk touches per step lives in registers; shared memory is read / written once per section
       WalkState st = s.st;
-      s.req = 0;
+      uint64_t cg = s.g, ct = s.t;
+      const uint64_t ctend_in = s.tend, cga = s.ga, cta = s.ta;
+      uint64_t ctend = ctend_in;
+      const uint32_t cgn = s.gn, ctn = s.tn;
+      uint32_t req = 0, fin = 0;
+      uint64_t req_idx = 0;
       for (;;) {
         if (st.a >= n) {
-          s.done = 1;
+          fin = 1;
           break;
         }
-        if (s.t < s.tend) {  // inside a group that is walked tile by tile
-          const uint64_t t = s.t, tstart = t * (uint64_t)kTT, tend = (tstart + kTT) < n ? (tstart + kTT) : n;
-          if (st.a < tend && !(t >= s.ta && t < s.ta + s.tn)) {
-            s.req = 3;
-            s.req_idx = t;
+        if (ct < ctend) {  // inside a group that is walked tile by tile
+          const uint64_t t = ct, tstart = t * (uint64_t)kTT, tend = (tstart + kTT) < n ? (tstart + kTT) : n;
+          if (st.a < tend && !(t >= cta && t < cta + ctn)) {
+            req = 3;
+            req_idx = t;
             break;
           }
           TileState ts{st.a, st.blk, st.foff, st.f, 0};
           wk.tstate[t] = ts;
-          s.t++;
+          ct++;
           if (st.a >= tend) continue;  // no block starts in this tile
           const uint64_t cc = st.a - tstart;
           TileRow r;
           r.exit = 0xffffffffu;
-          if (cc < hc) r = tcache[(t - s.ta) * hc + cc];
+          if (cc < hc) r = tcache[(t - cta) * hc + cc];
           const bool table_ok = cc < hc && r.exit != 0xffffffffu;
           const bool cut = !table_ok || (ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size) || tstart + r.exit >= n;
           if (cut) {  // a file ends in this tile (or the entry point is not tabulated): chase it block by block
-            s.req = 1;
-            s.req_idx = t;
+            req = 1;
+            req_idx = t;
             break;
           }
           st.a = tstart + r.exit;
@@ -534,33 +590,33 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
           continue;
         }
         // group level
-        if (s.g >= ngroups) {
-          s.done = 1;
+        if (cg >= ngroups) {
+          fin = 1;
           break;
         }
-        const uint64_t gg = s.g, t0 = gg * kEncGroup, gstart = t0 * (uint64_t)kTT;
+        const uint64_t gg = cg, t0 = gg * kEncGroup, gstart = t0 * (uint64_t)kTT;
         const uint64_t t1 = (t0 + kEncGroup) < ntiles ? (t0 + kEncGroup) : ntiles;
         const uint64_t gend = (t1 * (uint64_t)kTT) < n ? (t1 * (uint64_t)kTT) : n;
-        if (st.a < gend && !(gg >= s.ga && gg < s.ga + s.gn)) {
-          s.req = 2;
-          s.req_idx = gg;
+        if (st.a < gend && !(gg >= cga && gg < cga + cgn)) {
+          req = 2;
+          req_idx = gg;
           break;
         }
         TileState gs{st.a, st.blk, st.foff, st.f, 0};
         wk.gstate[gg] = gs;
         wk.gflag[gg] = 0;
-        s.g++;
+        cg++;
         if (st.a >= gend) continue;  // no block starts in this group
         const uint64_t cc = st.a - gstart;
         TileRow r;
         r.exit = 0xffffffffu;
-        if (cc < hc) r = gcache[(gg - s.ga) * hc + cc];
+        if (cc < hc) r = gcache[(gg - cga) * hc + cc];
         const bool table_ok = cc < hc && r.exit != 0xffffffffu;
         const bool cut = !table_ok || (ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size) || gstart + r.exit >= n;
         if (cut) {  // descend: tile by tile
           wk.gflag[gg] = 1;
-          s.t = t0;
-          s.tend = t1;
+          ct = t0;
+          ctend = t1;
           continue;
         }
         st.a = gstart + r.exit;
@@ -568,6 +624,12 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
         st.foff += r.bytes;
       }
       s.st = st;
+      s.g = cg;
+      s.t = ct;
+      s.tend = ctend;
+      s.req = req;
+      s.req_idx = req_idx;
+      if (fin) s.done = 1;
     }
     __syncthreads();
     const uint32_t req = s.req;  // stable: thread 0 writes these again only after the barrier that ends the iteration
@@ -732,60 +794,75 @@ encode_blocklist_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, u
 }
 
 // ------------------------------------------------------------------------------------------------ per-file statistics
+// One CTA per output file: whole tiles inside the file come from the sizes kernel's partial sums, the (at most two) partly
+// covered tiles at its ends are read entry by entry; also the file's smallest / largest key.
 __global__ void encode_filestats_kernel(KeyCols m, EncodeWork wk, uint32_t nfiles) {
-  // each CTA owns a contiguous chunk of entries and adds its part to every file it overlaps
-  const uint64_t n = m.n;
-  const uint64_t chunk = (n + gridDim.x - 1) / gridDim.x;
-  const uint64_t c0 = (uint64_t)blockIdx.x * chunk, c1 = (c0 + chunk) < n ? (c0 + chunk) : n;
+  const uint32_t f = blockIdx.x;
+  if (f >= nfiles) return;
+  const uint64_t f0 = wk.files[f].first_entry, f1 = f0 + wk.files[f].n_entries;
   __shared__ unsigned long long red[5];
-  for (uint32_t f = 0; f < nfiles; f++) {
-    const uint64_t f0 = wk.files[f].first_entry, f1 = f0 + wk.files[f].n_entries;
-    const uint64_t lo = c0 > f0 ? c0 : f0, hi = c1 < f1 ? c1 : f1;
-    if (lo >= hi) continue;  // uniform per CTA
-    if (threadIdx.x < 5) red[threadIdx.x] = threadIdx.x == 3 ? ~0ull : 0ull;
-    __syncthreads();
-    unsigned long long kb = 0, vb = 0, nd = 0, smin = ~0ull, smax = 0;
-    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-      uint64_t tr = m.tr[i];
-      uint32_t mt = m.meta[i];
-      kb += meta_ulen(mt) + 8;
-      vb += meta_vlen(mt);
-      nd += (tr & 0xff) == kTypeDeletion;
-      uint64_t sq = tr >> 8;
-      smin = sq < smin ? sq : smin;
-      smax = sq > smax ? sq : smax;
-      if (i == f0 || i == f1 - 1) {
-        ulonglong2 p = m.pfx[i];
-        KeyRec kr{p.x, p.y, tr, meta_ulen(mt), 0};
-        if (i == f0) wk.files[f].smallest = kr;
-        if (i == f1 - 1) wk.files[f].largest = kr;
+  if (threadIdx.x < 5) red[threadIdx.x] = threadIdx.x == 3 ? ~0ull : 0ull;
+  __syncthreads();
+  unsigned long long kb = 0, vb = 0, nd = 0, smin = ~0ull, smax = 0;
+  if (f1 > f0) {
+    const uint64_t tfull0 = (f0 + kEncTile - 1) / kEncTile, tfull1 = f1 / kEncTile;  // tiles [tfull0, tfull1) lie inside the file
+    auto scan_entries = [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const uint64_t tr = m.tr[i];
+        const uint32_t mt = m.meta[i];
+        kb += meta_ulen(mt) + 8;
+        vb += meta_vlen(mt);
+        nd += (tr & 0xff) == kTypeDeletion;
+        const uint64_t sq = tr >> 8;
+        smin = sq < smin ? sq : smin;
+        smax = sq > smax ? sq : smax;
+      }
+    };
+    if (tfull0 >= tfull1) {
+      scan_entries(f0, f1);  // the file covers no whole tile
+    } else {
+      scan_entries(f0, tfull0 * kEncTile);
+      scan_entries(tfull1 * kEncTile, f1);
+      for (uint64_t t = tfull0 + threadIdx.x; t < tfull1; t += blockDim.x) {
+        const TileStat ts = wk.tstat[t];
+        kb += ts.raw_key;
+        vb += ts.raw_value;
+        nd += ts.deletions;
+        smin = ts.smallest_seq < smin ? ts.smallest_seq : smin;
+        smax = ts.largest_seq > smax ? ts.largest_seq : smax;
       }
     }
+    if (threadIdx.x < 2) {  // boundary keys
+      const uint64_t i = threadIdx.x == 0 ? f0 : f1 - 1;
+      const ulonglong2 p = m.pfx[i];
+      const KeyRec kr{p.x, p.y, m.tr[i], meta_ulen(m.meta[i]), 0};
+      if (threadIdx.x == 0) wk.files[f].smallest = kr;
+      else wk.files[f].largest = kr;
+    }
+  }
 #pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      kb += __shfl_xor_sync(0xffffffffu, kb, d);
-      vb += __shfl_xor_sync(0xffffffffu, vb, d);
-      nd += __shfl_xor_sync(0xffffffffu, nd, d);
-      unsigned long long a = __shfl_xor_sync(0xffffffffu, smin, d), b = __shfl_xor_sync(0xffffffffu, smax, d);
-      smin = a < smin ? a : smin;
-      smax = b > smax ? b : smax;
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&red[0], kb);
-      atomicAdd(&red[1], vb);
-      atomicAdd(&red[2], nd);
-      atomicMin(&red[3], smin);
-      atomicMax(&red[4], smax);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      atomicAdd((unsigned long long*)&wk.files[f].raw_key_size, red[0]);
-      atomicAdd((unsigned long long*)&wk.files[f].raw_value_size, red[1]);
-      atomicAdd((unsigned long long*)&wk.files[f].num_deletions, red[2]);
-      atomicMin((unsigned long long*)&wk.files[f].smallest_seq, red[3]);
-      atomicMax((unsigned long long*)&wk.files[f].largest_seq, red[4]);
-    }
-    __syncthreads();
+  for (int d = 16; d; d >>= 1) {
+    kb += __shfl_xor_sync(0xffffffffu, kb, d);
+    vb += __shfl_xor_sync(0xffffffffu, vb, d);
+    nd += __shfl_xor_sync(0xffffffffu, nd, d);
+    const unsigned long long a = __shfl_xor_sync(0xffffffffu, smin, d), b = __shfl_xor_sync(0xffffffffu, smax, d);
+    smin = a < smin ? a : smin;
+    smax = b > smax ? b : smax;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&red[0], kb);
+    atomicAdd(&red[1], vb);
+    atomicAdd(&red[2], nd);
+    atomicMin(&red[3], smin);
+    atomicMax(&red[4], smax);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    wk.files[f].raw_key_size = red[0];
+    wk.files[f].raw_value_size = red[1];
+    wk.files[f].num_deletions = red[2];
+    wk.files[f].smallest_seq = red[3];
+    wk.files[f].largest_seq = red[4];
   }
 }
 
@@ -1501,7 +1578,9 @@ void launch_scatter_tails(const TailCopy* recs, uint32_t n, const uint8_t* stage
 void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, uint64_t n_cap, cudaStream_t st) {
   if (n_cap == 0) return;
   unsigned g = (unsigned)((n_cap + 255) / 256);
-  encode_sizes_kernel<<<g > 148 * 16 ? 148 * 16 : g, 256, 0, st>>>(m, n_dev, w.esz, w.eshared, w.min_s1);
+  (void)g;
+  const uint64_t tiles = (n_cap + kEncTile - 1) / kEncTile;
+  encode_sizes_kernel<<<(unsigned)(tiles < 148 * 8 ? tiles : 148 * 8), 256, 0, st>>>(m, n_dev, w.esz, w.eshared, w.tstat, w.min_s1);
 }
 void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t max_s1, uint32_t* err,
                           cudaStream_t st) {
@@ -1541,7 +1620,8 @@ void launch_encode_blocklist(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t 
 }
 void launch_encode_filestats(KeyCols m, EncodeWork w, uint32_t nfiles, int sms, cudaStream_t st) {
   if (m.n == 0 || nfiles == 0) return;
-  encode_filestats_kernel<<<sms * 4, 256, 0, st>>>(m, w, nfiles);
+  (void)sms;
+  encode_filestats_kernel<<<nfiles, 256, 0, st>>>(m, w, nfiles);
 }
 uint32_t encode_emit_slice(uint32_t block_size) {
   uint32_t s = block_size + block_size / 4 + 512;

@@ -102,9 +102,13 @@ constexpr int kEncHalo = 2048;
 constexpr int kEncGroupTiles = 16;   // tiles per stitch group (encode.cu kEncGroup)       // look-ahead window = the longest block (in entries) the encoder accepts
 constexpr uint32_t kMaxOutFiles = 4096;
 
+struct TileStat {            // per kEncTile merged entries: partial sums for the per-file statistics
+  uint64_t raw_key, raw_value, deletions, smallest_seq, largest_seq;
+};
 struct EncodeWork {                  // device scratch owned by the job
   uint32_t* esz;        // n: encoded size of entry i as a non-restart entry (s1)
   uint8_t* eshared;     // n: bytes shared with the previous internal key
+  TileStat* tstat;      // ceil(n / kEncTile): written by the sizes kernel
   uint32_t* min_s1;     // 2: [0] global min of esz (bounds the entry-point candidate window), [1] global max
   TileRow* rows;        // ntiles x hc
   TileRow* grows;       // ngroups x hc: composed transfer functions of kEncGroup tiles (exit relative to the group start)
