@@ -79,27 +79,59 @@ encode_sizes_kernel(KeyCols m, const unsigned long long* __restrict__ n_dev, uin
     __syncthreads();
     const uint64_t t0 = tile * kEncTile, t1 = (t0 + kEncTile) < n ? (t0 + kEncTile) : n;
     unsigned long long kb = 0, vb = 0, nd = 0, smin = ~0ull, smax = 0;
-#pragma unroll 4
-    for (uint64_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
-      const ulonglong2 c = m.pfx[i];
-      const uint64_t ctr = m.tr[i];
-      const uint32_t cm = m.meta[i], ulen = meta_ulen(cm), vs = meta_vlen(cm), ks = ulen + 8;
-      uint32_t sh = 0;
-      if (i > 0) {
-        const ulonglong2 p = m.pfx[i - 1];
-        sh = shared_prefix(c.x, c.y, ulen, ctr, p.x, p.y, meta_ulen(m.meta[i - 1]), m.tr[i - 1]);
+    // four entries per thread in flight; the previous entry (for the shared-prefix length) comes from the neighbouring lane,
+    // only lane 0 of a warp fetches it from memory
+    constexpr int kB = 4;
+    for (uint64_t ib = t0; ib < t1; ib += (uint64_t)kB * blockDim.x) {
+      ulonglong2 c[kB], pc[kB];
+      uint64_t ctr[kB], ptr_[kB];
+      uint32_t cm[kB], pm[kB];
+      const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+      for (int q = 0; q < kB; q++) {
+        const uint64_t i = ib + (uint64_t)q * blockDim.x + threadIdx.x;
+        c[q] = make_ulonglong2(0, 0);
+        pc[q] = make_ulonglong2(0, 0);
+        ctr[q] = ptr_[q] = 0;
+        cm[q] = pm[q] = 0;
+        if (i < t1) {
+          c[q] = m.pfx[i];
+          ctr[q] = m.tr[i];
+          cm[q] = m.meta[i];
+          if (lane == 0 && i > 0) {
+            pc[q] = m.pfx[i - 1];
+            ptr_[q] = m.tr[i - 1];
+            pm[q] = m.meta[i - 1];
+          }
+        }
       }
-      const uint32_t s1 = entry_size(sh, ks, vs);
-      esz[i] = s1;
-      eshared[i] = (uint8_t)sh;
-      mn = s1 < mn ? s1 : mn;
-      mxs = s1 > mxs ? s1 : mxs;
-      kb += ks;
-      vb += vs;
-      nd += (ctr & 0xff) == kTypeDeletion;
-      const uint64_t sq = ctr >> 8;
-      smin = sq < smin ? sq : smin;
-      smax = sq > smax ? sq : smax;
+#pragma unroll
+      for (int q = 0; q < kB; q++) {
+        const uint64_t i = ib + (uint64_t)q * blockDim.x + threadIdx.x;
+        const uint64_t nx = __shfl_up_sync(0xffffffffu, c[q].x, 1), ny = __shfl_up_sync(0xffffffffu, c[q].y, 1);
+        const uint64_t nt = __shfl_up_sync(0xffffffffu, ctr[q], 1);
+        const uint32_t nm = __shfl_up_sync(0xffffffffu, cm[q], 1);
+        if (lane != 0) {
+          pc[q] = make_ulonglong2(nx, ny);
+          ptr_[q] = nt;
+          pm[q] = nm;
+        }
+        if (i < t1) {
+          const uint32_t ulen = meta_ulen(cm[q]), vs = meta_vlen(cm[q]), ks = ulen + 8;
+          const uint32_t sh = i > 0 ? shared_prefix(c[q].x, c[q].y, ulen, ctr[q], pc[q].x, pc[q].y, meta_ulen(pm[q]), ptr_[q]) : 0;
+          const uint32_t s1 = entry_size(sh, ks, vs);
+          esz[i] = s1;
+          eshared[i] = (uint8_t)sh;
+          mn = s1 < mn ? s1 : mn;
+          mxs = s1 > mxs ? s1 : mxs;
+          kb += ks;
+          vb += vs;
+          nd += (ctr[q] & 0xff) == kTypeDeletion;
+          const uint64_t sq = ctr[q] >> 8;
+          smin = sq < smin ? sq : smin;
+          smax = sq > smax ? sq : smax;
+        }
+      }
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
