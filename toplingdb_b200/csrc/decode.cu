@@ -9,12 +9,12 @@
 // owns [run_start[r], run_start[r+1]).  Values are NOT copied: vref[i] is the device address of the value bytes
 // inside the resident file image, so each value byte crosses HBM once more only (file image -> output block).
 //
-// Kernels (all HBM-bound; algorithmic bytes = file bytes read + 36 B of columns written per entry):
-//   index_decode_kernel   one thread per index restart point  -> data block handles
-//   block_count_kernel    one warp per data block: stage block in shared memory with 16 B loads, verify the
-//                         block checksum (warp-cooperative XXH3 / CRC32C), count entries per restart interval
-//   block_decode_kernel   one THREAD per restart interval (the independent prefix-decode unit): aligned 8-byte loads
-//                         straight from the image, key rebuilt in registers, emits (hi, lo, trailer, vref, meta)
+// Kernels (algorithmic bytes = file bytes read once + 36 B of columns written per entry):
+//   index_decode_kernel        one thread per index restart point -> data block handles
+//   block_decode_fused_kernel  one warp per data block: cp.async staging into shared memory, restart-interval walk (one lane
+//                              per interval), block checksum (warp-cooperative XXH3 / CRC32C), decoupled look-back for
+//                              the global entry position, one-entry-per-lane key reconstruction by a scan over the
+//                              prefix-decompression maps, coalesced column stores (details above the kernel)
 #include <cstdlib>
 
 #include "common.cuh"

@@ -7,7 +7,8 @@
 // CompactionOutputs::ShouldStopBefore (db/compaction/compaction_outputs.cc:231-354, max-file-size rule :277).
 //
 // The reference cuts blocks with a sequential greedy rule.  Here it is evaluated in parallel:
-//   encode_sizes      per entry: shared-prefix length with the previous internal key and encoded size
+//   encode_sizes      per entry: shared-prefix length with the previous internal key and encoded size; per tile: partial
+//                     sums for the per-file statistics
 //   encode_tables     per tile of kEncTile entries: next(a) = "where does a block that starts at entry a end" for every
 //                     a (prefix sums + bisection in shared memory), then the tile's transfer function
 //                     entry-point -> (exit point, bytes, #blocks) for every entry point a chain can arrive at

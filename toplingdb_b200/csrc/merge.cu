@@ -4,13 +4,15 @@
 // + BytewiseCompareInternalKey (db/dbformat.h:1057-1097) + CompactionIterator::NextFromInput / PrepareOutput
 // (db/compaction/compaction_iterator.cc:475-1087,1274-1341) for kTypeValue / kTypeDeletion entries.
 //
-// Two kernels:
-//   merge_partition_kernel  one warp per tile boundary: exact k-way merge-path split (multi-sequence selection;
-//                           lanes own runs and bisect them in parallel against a common pivot)
+// Kernels:
+//   merge_partition_grouped_kernel (<= 16 runs) / merge_partition_kernel (<= 64 runs)
+//                           one warp per tile boundary: exact k-way merge-path split (multi-sequence selection against
+//                           a common pivot); with few runs a group of lanes per run probes several points per step
 //   merge_tiles_kernel      one CTA per tile of kMergeTile merged entries: coalesced load of the k segments into
 //                           shared memory, log2(k) rounds of pairwise merge-path merges (in place through
 //                           registers), drop rules against the in-tile predecessor, decoupled look-back for the
-//                           output offset, coalesced write of the surviving (key, value-ref) records.
+//                           output offset (count published early, offset resolved after the value-reference gathers),
+//                           coalesced write of the surviving (key, value-ref) records.
 // HBM-bound: algorithmic bytes = 36 B read per input entry + 36 B written per surviving entry.
 #include "common.cuh"
 #include "kernels.h"
