@@ -141,6 +141,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the compaction path has no CPU implementation)")
     torch.cuda.set_device(local)
     if world > 1:
+        # the bench prints exactly one JSON line on stdout: keep NCCL's own banner / logs on stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOADS[args.workload]
     entry = 24 + w["vlen"]
