@@ -6,6 +6,8 @@ import re
 
 import pytest
 
+import helpers as H
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -51,3 +53,20 @@ def test_product_does_not_reference_the_oracle():
                 if "liboracle" in s or "compaction_oracle" in s or "oracle/" in s:
                     bad.append(f)
     assert not bad, bad
+
+
+@pytest.mark.skipif(not (os.path.exists(H.REF_BIN) and os.path.exists(H.REF_B200_BIN)), reason="oracle/_ref not built")
+def test_plugin_without_a_device_lets_the_reference_run_the_job_itself():
+    """No CUDA device: B200CompactionExecutorFactory::ShouldRunLocal() must answer true (compaction_executor.h:162), so the
+    reference's CompactionJob::Run takes RunLocal() (compaction_job.cc:645-647) -- the plugin never computes anything on
+    the CPU itself.  Same files as a run without the plugin, and no remote-compaction bytes accounted."""
+    import scenarios as S
+    if os.path.exists("/dev/nvidia0"):
+        pytest.skip("a CUDA device is present: covered by tests/test_gpu_plugin_integration.py")
+    ops, opts = S.ALL["cfg2_mini"](per_run=300)
+    want = H.run_reference(ops, **opts)
+    got = H.run_reference(ops, binary=H.REF_B200_BIN, executor="b200", **opts)
+    assert got["manifest"]["executor"] == "B200Compact"
+    assert got["manifest"]["remote_compact_read_bytes"] == 0
+    assert (got["manifest"]["scan_count"], got["manifest"]["scan_digest"]) == (want["manifest"]["scan_count"], want["manifest"]["scan_digest"])
+    assert [len(o) for o in got["outputs"]] == [len(o) for o in want["outputs"]]
