@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200C_ABI_VERSION 1
+#define B200C_ABI_VERSION 2
 #if defined(__GNUC__)
 #define B200C_API __attribute__((visibility("default")))
 #else
@@ -52,6 +52,12 @@ enum b200c_status {
 };
 
 enum b200c_mem_kind { B200C_MEM_HOST = 0, B200C_MEM_DEVICE = 1 };
+/* CompactionFilter applied inside the merge kernel (compaction_iterator.cc:231-473, :579-584): only built-in filters whose
+ * decision is a function of the entry itself can run on the device */
+enum b200c_compaction_filter {
+  B200C_FILTER_NONE = 0,
+  B200C_FILTER_REMOVE_EMPTY_VALUE = 1 /* RemoveEmptyValueCompactionFilter (utilities/compaction_filters/remove_emptyvalue_compactionfilter.cc:15-22) */
+};
 enum b200c_checksum { B200C_CKSUM_NONE = 0, B200C_CKSUM_CRC32C = 1, B200C_CKSUM_XXH3 = 4 }; /* ChecksumType, table.h:54-60 */
 
 /* Job parameters: the fields of CompactionParams (compaction_executor.h:33-118), of the output
@@ -85,6 +91,7 @@ typedef struct b200c_params {
   uint64_t first_file_number;      /* outputs are numbered first_file_number, +1, ... (orig_file_number property) */
   uint32_t output_mem;             /* enum b200c_mem_kind: where b200c_job_output_data() pointers live */
   uint32_t profile;                /* != 0: bracket every kernel group with CUDA events (b200c_job_kernel_time) */
+  uint32_t compaction_filter;      /* enum b200c_compaction_filter */
 } b200c_params;
 
 /* FileMinMeta (compaction_executor.h:120-131) + the TableProperties RunRemote re-reads (compaction_job.cc:1043-1061) */
@@ -108,6 +115,7 @@ typedef struct b200c_stats {
   /* device time of the last run, microseconds, CUDA events on the job stream */
   double decode_us, merge_us, encode_us, total_us;
   uint64_t kernel_launches; /* kernels of this library launched by the last run */
+  uint64_t num_record_drop_user; /* entries the compaction filter turned into tombstones (CompactionIterationStats) */
 } b200c_stats;
 
 typedef struct b200c_job b200c_job;

@@ -559,7 +559,8 @@ static void merge_next(input* in) {
 /* ------------------------------------------------------------------ CompactionIterator
  * db/compaction/compaction_iterator.cc: NextFromInput :475-1087, PrepareOutput :1274-1341,
  * findEarliestVisibleSnapshot :1343-1396, Next :…; restricted to kTypeValue / kTypeDeletion, no snapshot
- * checker, no merge operator, no range tombstones, no timestamps, no filter. */
+ * checker, no merge operator, no range tombstones, no timestamps; compaction filter: the built-in
+ * RemoveEmptyValueCompactionFilter only. */
 typedef struct citer {
   input* in;
   const orc_params* p;
@@ -623,6 +624,13 @@ static void citer_next_from_input(citer* c) {
       c->cur_seq = ORC_MAX_SEQ;
       c->cur_snap = 0;
       c->has_current_user_key = 1;
+      /* :579-584 the filter sees the first (newest) committed version of a user key, kTypeValue only (:236-239);
+       * Decision::kRemove turns it into a tombstone with no value (:385-391) */
+      if (c->p->compaction_filter == ORC_FILTER_REMOVE_EMPTY_VALUE && type == ORC_TYPE_VALUE && in->vlen == 0) {
+        type = ORC_TYPE_DELETION;
+        citer_set_trailer(c, seq, type);
+        c->st->num_record_drop_user++;
+      }
     } else { /* :589-611 */
       citer_set_trailer(c, seq, type);
     }

@@ -51,7 +51,10 @@ typedef struct orc_params {
   const uint64_t* file_creation_times; /* one per output file; last repeats */
   uint32_t num_file_creation_times;
   uint64_t first_file_number;      /* outputs are numbered consecutively from here */
+  uint32_t compaction_filter;      /* ORC_FILTER_*: built-in CompactionFilter applied by the iterator (compaction_iterator.cc:231-473) */
 } orc_params;
+#define ORC_FILTER_NONE 0
+#define ORC_FILTER_REMOVE_EMPTY_VALUE 1 /* utilities/compaction_filters/remove_emptyvalue_compactionfilter.cc:15-22 */
 
 typedef struct orc_file_meta { /* FileMinMeta, compaction_executor.h:120-131 + table properties */
   uint64_t file_number, file_size;
@@ -68,6 +71,7 @@ typedef struct orc_stats { /* CompactionJobStats subset, include/rocksdb/compact
   uint64_t num_expired_deletion_records;  /* num_record_drop_obsolete */
   uint64_t total_input_raw_key_bytes, total_input_raw_value_bytes;
   uint64_t num_optimized_del_drop_obsolete;
+  uint64_t num_record_drop_user;          /* entries the compaction filter turned into tombstones (:385-391) */
 } orc_stats;
 
 typedef struct orc_result orc_result;

@@ -29,7 +29,9 @@
 #include "rocksdb/listener.h"
 #include "rocksdb/options.h"
 #include "rocksdb/table.h"
+#include "rocksdb/compaction_filter.h"
 #include "rocksdb/write_batch.h"
+#include "utilities/compaction_filters/remove_emptyvalue_compactionfilter.h"
 #ifdef WITH_B200_PLUGIN
 #include "rocksdb/statistics.h"
 #include "toplingdb_b200/plugin/b200_compaction_executor.h"
@@ -50,6 +52,7 @@ struct Opts {
   int keep_db = 0;
   int paranoid = 0;
   int copy = 1;  // 0: leave inputs/ and outputs/ empty (timing runs only need the manifest)
+  std::string filter = "none";  // remove_empty_value: the reference's RemoveEmptyValueCompactionFilter through a factory
   std::string barrier_dir;  // with barrier_n: wait until barrier_n processes have finished writing their inputs, so that
   int barrier_n = 0;        // concurrent timing runs compact at the same time
   std::string executor;  // "b200": route the job through the B200 CompactionExecutor plugin (ref_compact_b200 build only)
@@ -88,6 +91,15 @@ class StatsListener : public EventListener {
     last = ci;
     completed++;
   }
+};
+
+// RunRemote only accepts filters that come from a factory (compaction_job.cc:942-943)
+class RemoveEmptyValueFactory : public CompactionFilterFactory {
+ public:
+  std::unique_ptr<CompactionFilter> CreateCompactionFilter(const CompactionFilter::Context&) override {
+    return std::unique_ptr<CompactionFilter>(new RemoveEmptyValueCompactionFilter());
+  }
+  const char* Name() const override { return "RemoveEmptyValueCompactionFilterFactory"; }
 };
 
 struct Reader {
@@ -134,6 +146,7 @@ int main(int argc, char** argv) {
     else if (k == "paranoid") o.paranoid = atoi(v.c_str());
     else if (k == "executor") o.executor = v;
     else if (k == "copy") o.copy = atoi(v.c_str());
+    else if (k == "filter") o.filter = v;
     else if (k == "barrier_dir") o.barrier_dir = v;
     else if (k == "barrier_n") o.barrier_n = atoi(v.c_str());
     else {
@@ -173,6 +186,11 @@ int main(int argc, char** argv) {
   t.checksum = o.checksum == "crc32c" ? kCRC32c : kXXH3;
   t.no_block_cache = true;
   opt.table_factory.reset(NewBlockBasedTableFactory(t));
+  if (o.filter == "remove_empty_value") opt.compaction_filter_factory = std::make_shared<RemoveEmptyValueFactory>();
+  else if (o.filter != "none") {
+    fprintf(stderr, "ref_compact: unknown filter %s\n", o.filter.c_str());
+    return 1;
+  }
   auto listener = std::make_shared<StatsListener>();
   opt.listeners.push_back(listener);
   bool use_b200 = false;
@@ -345,6 +363,7 @@ int main(int argc, char** argv) {
   fprintf(m, "  \"checksum\": \"%s\",\n  \"max_subcompactions\": %u,\n", o.checksum.c_str(),
           o.max_subcompactions);
   fprintf(m, "  \"bottommost_level\": %s,\n", deeper_files ? "false" : "true");
+  fprintf(m, "  \"compaction_filter\": \"%s\",\n", o.filter.c_str());
   {
     uint64_t remote_read = 0;
 #ifdef WITH_B200_PLUGIN

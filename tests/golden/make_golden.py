@@ -21,12 +21,15 @@ SMALL = dict(  # keep committed fixtures small (tens of KB each)
     basic_bottommost=dict(n=300, nruns=3), nonbottom_tombstones=dict(n=200), snapshots=dict(n=150),
     snapshots_nonbottom=dict(n=150), varlen_keys=dict(n=200), long_keys=dict(n=100), crc32c_small_blocks=dict(n=300),
     same_user_key_across_blocks={}, tiny={}, all_deleted={}, cfg2_mini=dict(per_run=250), cfg3_mini=dict(per_run=60),
-    output_level0={})
+    output_level0={}, filter_empty_value=dict(n=150), filter_empty_value_nonbottom=dict(n=150))
 
 
 def main():
     assert H.have_ref(), "oracle/_ref/ref_compact missing: run `make -C oracle ref` where /root/reference exists"
+    only = set(sys.argv[1:])  # optional: regenerate just the named cases (the others keep their committed bytes)
     for name, fn in S.ALL.items():
+        if only and name not in only:
+            continue
         ops, opts = fn(**SMALL[name])
         d = os.path.join(HERE, name)
         shutil.rmtree(d, ignore_errors=True)

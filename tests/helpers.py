@@ -16,6 +16,7 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_compact")
 REF_B200_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_compact_b200")  # same driver + the product's CompactionExecutor plugin
 MAX_SEQ = (1 << 56) - 1
 CKSUM = {"none": 0, "crc32c": 1, "xxh3": 4}
+FILTERS = {"none": 0, "remove_empty_value": 1}
 
 
 class OrcParams(C.Structure):
@@ -27,7 +28,7 @@ class OrcParams(C.Structure):
         ("column_family_name", C.c_char_p), ("db_id", C.c_char_p), ("db_session_id", C.c_char_p),
         ("db_host_id", C.c_char_p), ("creation_time", C.c_uint64), ("oldest_key_time", C.c_uint64),
         ("file_creation_times", C.POINTER(C.c_uint64)), ("num_file_creation_times", C.c_uint32),
-        ("first_file_number", C.c_uint64),
+        ("first_file_number", C.c_uint64), ("compaction_filter", C.c_uint32),
     ]
 
 
@@ -42,7 +43,7 @@ class OrcStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("num_input_records", "num_output_records", "num_input_deletion_records",
                                           "num_records_replaced", "num_expired_deletion_records",
                                           "total_input_raw_key_bytes", "total_input_raw_value_bytes",
-                                          "num_optimized_del_drop_obsolete")]
+                                          "num_optimized_del_drop_obsolete", "num_record_drop_user")]
 
 
 _oracle = None
@@ -95,6 +96,7 @@ class Params:
         self.oldest_key_time = 0
         self.file_creation_times = [1700000001]
         self.first_file_number = 100
+        self.compaction_filter = "none"  # or "remove_empty_value"
         for k, v in kw.items():
             assert hasattr(self, k), k
             setattr(self, k, v)
@@ -124,6 +126,7 @@ class Params:
         p.file_creation_times = C.cast(self._fct, C.POINTER(C.c_uint64))
         p.num_file_creation_times = len(self.file_creation_times)
         p.first_file_number = self.first_file_number
+        p.compaction_filter = FILTERS[self.compaction_filter]
         return p
 
 
@@ -276,7 +279,7 @@ def params_from_reference(ref) -> Params:
     p = Params(output_level=man["output_level"], bottommost_level=man["bottommost_level"],
                max_output_file_size=man["target_file_size"], block_size=man["block_size"],
                block_restart_interval=man["restart_interval"], format_version=man["format_version"],
-               checksum=man["checksum"], snapshots=man["snapshots"])
+               checksum=man["checksum"], snapshots=man["snapshots"], compaction_filter=man.get("compaction_filter", "none"))
     if ref["outputs"]:
         props = [sstfmt.parse_sst(o)["properties"] for o in ref["outputs"]]
         p0 = props[0]

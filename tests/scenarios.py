@@ -156,7 +156,45 @@ def output_level0(seed=13):
     return ops, dict(target_file_size=8 << 10, output_level=0)
 
 
+def _filter_runs(ops, rnd, n, nruns, snapshot_after=()):
+    """runs where ~30 % of the values are empty: RemoveEmptyValueCompactionFilter turns the NEWEST version of a user key into a
+    tombstone when its value is empty (older empty versions are left to the ordinary rules)"""
+    for r in range(nruns):
+        for k in sorted(rnd.sample(range(1, n * 2), n)):
+            x = rnd.random()
+            if x < 0.1:
+                ops.delete(key16(k))
+            elif x < 0.4:
+                ops.put(key16(k), b"")
+            else:
+                ops.put(key16(k), rnd.randbytes(rnd.randint(1, 60)))
+        ops.flush()
+        if r in snapshot_after:
+            ops.snapshot()
+
+
+def filter_empty_value(n=400, nruns=4, seed=14):
+    """bottommost: converted tombstones are dropped unless a snapshot pins them"""
+    rnd = random.Random(seed)
+    ops = Ops()
+    _filter_runs(ops, rnd, n, nruns, snapshot_after=(1,))
+    return ops, dict(target_file_size=24 << 10, filter="remove_empty_value")
+
+
+def filter_empty_value_nonbottom(n=400, nruns=3, seed=15):
+    """not bottommost: converted tombstones are written out as kTypeDeletion entries"""
+    rnd = random.Random(seed)
+    ops = Ops()
+    for k in [key16(0), key16(1 << 40)]:
+        ops.put(k, b"base")
+    ops.flush()
+    ops.compact_all_to(6)
+    _filter_runs(ops, rnd, n, nruns)
+    return ops, dict(target_file_size=24 << 10, filter="remove_empty_value")
+
+
 ALL = dict(basic_bottommost=basic_bottommost, nonbottom_tombstones=nonbottom_tombstones, snapshots=snapshots,
            snapshots_nonbottom=snapshots_nonbottom, varlen_keys=varlen_keys, long_keys=long_keys,
            crc32c_small_blocks=crc32c_small_blocks, same_user_key_across_blocks=same_user_key_across_blocks,
-           tiny=tiny, all_deleted=all_deleted, cfg2_mini=cfg2_mini, cfg3_mini=cfg3_mini, output_level0=output_level0)
+           tiny=tiny, all_deleted=all_deleted, cfg2_mini=cfg2_mini, cfg3_mini=cfg3_mini, output_level0=output_level0,
+           filter_empty_value=filter_empty_value, filter_empty_value_nonbottom=filter_empty_value_nonbottom)

@@ -182,3 +182,22 @@ def test_corrupt_input_is_detected():
     with pytest.raises(T.B200cError) as ei:
         run_product(p, [bytes(bad)] + g["inputs"][1:])
     assert ei.value.code == T.native.ERR_CORRUPTION
+
+
+@pytest.mark.parametrize("case", ["filter_empty_value", "filter_empty_value_nonbottom"])
+def test_in_kernel_compaction_filter_counts_like_the_oracle(case):
+    """RemoveEmptyValueCompactionFilter applied inside the merge kernel (compaction_iterator.cc:579-584, :385-391): output
+    bytes are covered by the fixture tests above; CompactionIterationStats::num_record_drop_user is not part of
+    CompactionJobStats, so it is checked against the oracle."""
+    from gpu_harness import run_product
+    g = H.load_golden(case)
+    p = H.params_from_reference(g)
+    assert p.compaction_filter == "remove_empty_value"
+    files, _, st = run_product(p, g["inputs"])
+    ofiles, _, ost = H.oracle_compact(p, g["inputs"])
+    assert files == ofiles == g["outputs"]
+    assert st.num_record_drop_user == ost.num_record_drop_user > 0
+    # the same inputs without the filter give different files: the rule really ran
+    p.compaction_filter = "none"
+    files2, _, st2 = run_product(p, g["inputs"])
+    assert st2.num_record_drop_user == 0 and files2 != files

@@ -652,6 +652,7 @@ int run_job(b200c_job* j, int until) {
   mp.nsnapshots = P.num_snapshots;
   mp.snapshots = j->snaps_d.as<uint64_t>();
   mp.earliest_snapshot = P.num_snapshots ? j->snapshots[0] : kMaxSeq;
+  mp.filter = P.compaction_filter;
   MergeCounters* counters = reinterpret_cast<MergeCounters*>(small + kSlotCounters);
   EncodeWork W;
   memset(&W, 0, sizeof W);
@@ -695,6 +696,7 @@ int run_job(b200c_job* j, int until) {
   j->stats.num_input_deletion_records = mc.n_input_deletions;
   j->stats.num_records_replaced = mc.n_hidden;
   j->stats.num_expired_deletion_records = mc.n_obsolete;
+  j->stats.num_record_drop_user = mc.n_user_drop;
   j->stats.total_input_raw_key_bytes = mc.raw_key_bytes;
   {  // every input value byte (rocksdb.raw.value.size of the inputs) minus the silently skipped entries
     uint64_t all = 0;
@@ -826,6 +828,8 @@ int b200c_job_create(const b200c_params* p, b200c_job** out) {
   if (p->block_restart_interval < 1) return fail(B200C_ERR_INVALID_ARGUMENT, "block_restart_interval < 1");
   if (p->block_size_deviation > 100) return fail(B200C_ERR_INVALID_ARGUMENT, "block_size_deviation > 100");
   if (p->format_version < 3 || p->format_version > 5) return fail(B200C_ERR_NOT_SUPPORTED, "output format_version must be 3..5");
+  if (p->compaction_filter != B200C_FILTER_NONE && p->compaction_filter != B200C_FILTER_REMOVE_EMPTY_VALUE)
+    return fail(B200C_ERR_NOT_SUPPORTED, "compaction filter is not one of the built-in device filters");
   if (p->checksum != B200C_CKSUM_XXH3 && p->checksum != B200C_CKSUM_CRC32C && p->checksum != B200C_CKSUM_NONE)
     return fail(B200C_ERR_NOT_SUPPORTED, "output checksum must be kNoChecksum, kCRC32c or kXXH3");
   for (uint32_t i = 1; i < p->num_snapshots; i++)

@@ -47,9 +47,10 @@ struct MergeParams {
   uint32_t nsnapshots;
   const uint64_t* snapshots;         // device, ascending
   uint64_t earliest_snapshot;        // snapshots[0] or kMaxSeq
+  uint32_t filter;                   // b200c_compaction_filter
 };
 struct MergeCounters {               // device-side CompactionIterationStats
-  unsigned long long n_out, n_input_deletions, n_hidden, n_obsolete, raw_key_bytes, raw_value_bytes, n_silent;
+  unsigned long long n_out, n_input_deletions, n_hidden, n_obsolete, raw_key_bytes, raw_value_bytes, n_silent, n_user_drop;
 };
 // splits: (ntiles + 1) x nruns u64; tile_state: ntiles u64 (zeroed); ticket: u32 (zeroed)
 void launch_merge_partition(KeyCols in, const uint64_t* run_start, uint32_t nruns, uint64_t n_total, uint64_t ntiles,

@@ -219,7 +219,7 @@ __device__ __forceinline__ Key skey(const TileSmem& s, uint32_t id) {
   k.hi = s.hi[id];
   k.lo = s.lo[id];
   k.tr = s.tr[id];
-  k.ulen = s.ulen[id];
+  k.ulen = s.ulen[id] & 0x7fu;
   return k;
 }
 // List positions are XOR-swizzled inside 16-element groups: a thread owns kMV = 8 consecutive list positions, and with
@@ -229,7 +229,7 @@ __device__ __forceinline__ uint32_t PH(uint32_t e) { return e ^ ((e >> 4) & 15u)
 __device__ __forceinline__ bool tie_less(const TileSmem& s, uint32_t ib, uint32_t ia) {
   const uint64_t lb = s.lo[ib], la = s.lo[ia];
   if (lb != la) return lb < la;
-  const uint32_t ub = s.ulen[ib], ua = s.ulen[ia];
+  const uint32_t ub = s.ulen[ib] & 0x7fu, ua = s.ulen[ia] & 0x7fu;
   if (ub != ua) return ub < ua;
   return s.tr[ib] > s.tr[ia];
 }
@@ -307,25 +307,34 @@ __device__ bool oldest_version_at_most(const KeyCols& in, const uint64_t* run_st
   return false;
 }
 // newest version of user key with seq <= stripe_hi: the head of that (user key, stripe) group
+// *head_tr carries the type the compaction iterator sees: with the remove-empty-value filter the NEWEST version of a user
+// key is turned into a tombstone when it is a kTypeValue with an empty value (compaction_iterator.cc:579-584, :385-391)
 __device__ bool group_head(const KeyCols& in, const uint64_t* run_start, uint32_t nruns, uint64_t hi, uint64_t lo, uint32_t ulen,
-                           uint64_t stripe_hi, uint64_t* head_tr) {
+                           uint64_t stripe_hi, uint32_t filter, uint64_t* head_tr) {
   Key x;
   x.hi = hi;
   x.lo = lo;
   x.ulen = ulen;
   x.tr = (stripe_hi << 8) | 0xff;  // sorts before every version with seq <= stripe_hi
-  bool found = false;
-  uint64_t best = 0;
+  bool found = false, newer_exists = false;
+  uint64_t best = 0, best_pos = 0;
   for (uint32_t r = 0; r < nruns; r++) {
     uint64_t base = run_start[r], n = run_start[r + 1] - base;
     uint64_t c = count_before(in, base, 0, n, x, false);
+    if (c > 0) {  // the element in front of the lower bound: a version of the same user key with seq > stripe_hi?
+      Key e = load_key(in, base + c - 1);
+      if (e.hi == hi && e.lo == lo && e.ulen == ulen) newer_exists = true;
+    }
     if (c >= n) continue;
     Key e = load_key(in, base + c);
     if (e.hi == hi && e.lo == lo && e.ulen == ulen && (!found || e.tr > best)) {
       found = true;
       best = e.tr;
+      best_pos = base + c;
     }
   }
+  if (found && filter == 1 && !newer_exists && (best & 0xff) == kTypeValue && meta_vlen(in.meta[best_pos]) == 0)
+    best = (best & ~0xffull) | kTypeDeletion;
   *head_tr = best;
   return found;
 }
@@ -411,7 +420,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
         s.hi[i] = lp[j].x;
         s.lo[i] = lp[j].y;
         s.tr[i] = ltr[j];
-        s.ulen[i] = (uint8_t)meta_ulen(lmt[j]);
+        s.ulen[i] = (uint8_t)(meta_ulen(lmt[j]) | (meta_vlen(lmt[j]) == 0 ? 0x80u : 0u));  // bit 7: empty value (compaction filter)
         s.idx[PH(i)] = (uint16_t)i;
       }
     }
@@ -483,7 +492,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   // ---- compaction-iterator rules per merged position
   const bool cond_possible = mp.bottommost && mp.nsnapshots > 0;
   uint32_t keep_mask = 0, nkeep = 0;
-  unsigned long long c_hidden = 0, c_obsolete = 0, c_indel = 0, c_kbytes = 0, c_vbytes = 0, c_silent = 0;
+  unsigned long long c_hidden = 0, c_obsolete = 0, c_indel = 0, c_kbytes = 0, c_vbytes = 0, c_silent = 0, c_userdrop = 0;
   uint64_t otr[kMV];
   uint16_t oid[kMV];
 #pragma unroll
@@ -504,7 +513,14 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     }
     const bool same = has_prev && p.hi == c.hi && p.lo == c.lo && p.ulen == c.ulen;
     const uint64_t seq = c.tr >> 8;
-    const uint32_t type = (uint32_t)(c.tr & 0xff);
+    const uint32_t type0 = (uint32_t)(c.tr & 0xff);  // as read; the input-side counters use it
+    uint32_t type = type0;
+    if (mp.filter == 1 && !same && type0 == kTypeValue && (s.ulen[id] & 0x80u)) {
+      // compaction filter on the first (newest) version of a user key: Decision::kRemove turns it into a tombstone
+      type = kTypeDeletion;
+      c.tr = (seq << 8) | kTypeDeletion;
+      c_userdrop++;
+    }
     uint64_t prev_snap = 0, dummy;
     uint64_t st_c = mp.nsnapshots ? stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, seq, &prev_snap) : kMaxSeq;
     bool hidden = same;
@@ -516,22 +532,36 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
         // same-stripe followers are skipped there without touching any counter.
         int q = (int)o - 1;
         uint64_t head_tr = 0;
+        uint32_t head_id = 0;
         bool have = false;
         while (q >= 0) {
-          Key h = skey(s, s.idx[PH(q)]);
+          const uint32_t hid = s.idx[PH(q)];
+          Key h = skey(s, hid);
           uint64_t d2;
           bool same_grp = h.hi == c.hi && h.lo == c.lo && h.ulen == c.ulen &&
                           stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, h.tr >> 8, &d2) == st_c;
           if (!same_grp) break;
           head_tr = h.tr;
+          head_id = hid;
           have = true;
           q--;
+        }
+        if (have && mp.filter == 1 && (head_tr & 0xff) == kTypeValue && (s.ulen[head_id] & 0x80u)) {
+          // the head is filtered if it is the first version of its user key: look at the entry in front of it
+          bool first_occ;
+          if (q >= 0) {
+            const Key b = skey(s, s.idx[PH(q)]);
+            first_occ = !(b.hi == c.hi && b.lo == c.lo && b.ulen == c.ulen);
+          } else {
+            first_occ = !(s.has_pred && s.pred.hi == c.hi && s.pred.lo == c.lo && s.pred.ulen == c.ulen);
+          }
+          if (first_occ) head_tr = (head_tr & ~0xffull) | kTypeDeletion;
         }
         if (q < 0 && s.has_pred) {  // group may start before the tile
           uint64_t d2;
           bool pred_same = s.pred.hi == c.hi && s.pred.lo == c.lo && s.pred.ulen == c.ulen &&
                            stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, s.pred.tr >> 8, &d2) == st_c;
-          if (pred_same) have = group_head(in, run_start, k, c.hi, c.lo, c.ulen, st_c, &head_tr);
+          if (pred_same) have = group_head(in, run_start, k, c.hi, c.lo, c.ulen, st_c, mp.filter, &head_tr);
         }
         if (have && (head_tr & 0xff) == kTypeDeletion) silent = true;  // head seq > earliest snapshot since its stripe is not the first
       }
@@ -559,7 +589,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     }
     if (!silent) {
       c_kbytes += c.ulen + 8;
-      if (type == kTypeDeletion) c_indel++;
+      if (type0 == kTypeDeletion) c_indel++;
     }
     if (silent) c_silent++;
     if (keep) {
@@ -684,10 +714,11 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   // ---- counters: one atomic per CTA and counter.  Per-thread partial counts are small (<= kMV entries), so the warp
   // reduction is a single redux instruction per counter; only the (rare) value-byte correction needs 64 bits.
   {
-    const unsigned vals[6] = {nkeep, (unsigned)c_indel, (unsigned)c_hidden, (unsigned)c_obsolete, (unsigned)c_kbytes, (unsigned)c_silent};
-    const int slot[6] = {0, 1, 2, 3, 4, 6};
+    const unsigned vals[7] = {nkeep, (unsigned)c_indel, (unsigned)c_hidden, (unsigned)c_obsolete, (unsigned)c_kbytes, (unsigned)c_silent,
+                              (unsigned)c_userdrop};
+    const int slot[7] = {0, 1, 2, 3, 4, 6, 7};
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
+    for (int i = 0; i < 7; i++) {
       const unsigned v = __reduce_add_sync(0xffffffffu, vals[i]);
       if (lane == 0 && v) atomicAdd(&s.red[slot[i]], (unsigned long long)v);
     }
@@ -699,7 +730,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     }
   }
   __syncthreads();
-  if (t < 7 && s.red[t]) atomicAdd(((unsigned long long*)counters) + t, s.red[t]);
+  if (t < 8 && s.red[t]) atomicAdd(((unsigned long long*)counters) + t, s.red[t]);
 }
 
 // ------------------------------------------------------------------------------------------------ launchers

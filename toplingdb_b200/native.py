@@ -27,7 +27,7 @@ class Params(C.Structure):
         ("db_id", C.c_char_p), ("db_session_id", C.c_char_p), ("db_host_id", C.c_char_p), ("creation_time", C.c_uint64),
         ("oldest_key_time", C.c_uint64), ("file_creation_times", C.POINTER(C.c_uint64)),
         ("num_file_creation_times", C.c_uint32), ("first_file_number", C.c_uint64), ("output_mem", C.c_uint32),
-        ("profile", C.c_uint32),
+        ("profile", C.c_uint32), ("compaction_filter", C.c_uint32),
     ]
 
 
@@ -45,7 +45,7 @@ class JobStats(C.Structure):
                                           "total_input_raw_key_bytes", "total_input_raw_value_bytes", "total_input_bytes",
                                           "total_output_bytes", "num_input_files", "num_output_files")] + [
         ("decode_us", C.c_double), ("merge_us", C.c_double), ("encode_us", C.c_double), ("total_us", C.c_double),
-        ("kernel_launches", C.c_uint64)]
+        ("kernel_launches", C.c_uint64), ("num_record_drop_user", C.c_uint64)]
 
 
 _lib = None
@@ -149,6 +149,8 @@ class CompactionJob:
                 p.output_mem = {"host": MEM_HOST, "device": MEM_DEVICE}.get(v, v)
             elif k == "bottommost_level":
                 p.bottommost_level = int(v)
+            elif k == "compaction_filter":
+                p.compaction_filter = {"none": 0, "remove_empty_value": 1}.get(v, v)
             else:
                 if not hasattr(p, k):
                     raise TypeError(f"unknown job parameter {k}")

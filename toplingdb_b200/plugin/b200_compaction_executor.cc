@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "b200c.h"
+#include "rocksdb/compaction_filter.h"
 #include "db/compaction/compaction.h"
 #include "db/version_edit.h"
 #include "file/filename.h"
@@ -22,6 +23,20 @@
 namespace ROCKSDB_NAMESPACE {
 
 namespace {
+
+// Which device filter (include/b200c.h b200c_compaction_filter) the column family's filter factory stands for; NONE when the
+// family has no factory or the filter is not one the merge kernel implements.  Filters are recognised by CompactionFilter::Name().
+uint32_t DeviceFilterOf(const Compaction* c) {
+  const auto& factory = c->immutable_options()->compaction_filter_factory;
+  if (!factory) return B200C_FILTER_NONE;
+  CompactionFilter::Context ctx;
+  ctx.is_full_compaction = c->is_full_compaction();
+  ctx.is_manual_compaction = c->is_manual_compaction();
+  ctx.column_family_id = c->column_family_data()->GetID();
+  std::unique_ptr<CompactionFilter> f = factory->CreateCompactionFilter(ctx);
+  if (f && std::string(f->Name()) == "RemoveEmptyValueCompactionFilter") return B200C_FILTER_REMOVE_EMPTY_VALUE;
+  return B200C_FILTER_NONE;
+}
 
 const BlockBasedTableOptions* BlockBasedOptionsOf(const Compaction* c) {
   auto* tf = c->immutable_options()->table_factory.get();
@@ -128,6 +143,7 @@ class B200CompactionExecutor : public CompactionExecutor {
     bp.num_file_creation_times = 1;
     bp.first_file_number = 1;  // numbers are local to output_dir; RunRemote renames every file (compaction_job.cc:1019-1033)
     bp.output_mem = B200C_MEM_HOST;
+    bp.compaction_filter = DeviceFilterOf(c_);
 
     b200c_job* job = nullptr;
     Status s = FromB200(b200c_job_create(&bp, &job));
@@ -266,7 +282,9 @@ bool B200CompactionExecutorFactory::ShouldRunLocal(const Compaction* c) const {
   if (!have_device_) return true;
   const auto* io = c->immutable_options();
   if (io->merge_operator != nullptr) return true;
-  if (io->compaction_filter != nullptr || io->compaction_filter_factory != nullptr) return true;
+  // RunRemote needs the filter to come from a factory (compaction_job.cc:942-943); only filters the merge kernel implements run remotely
+  if (io->compaction_filter != nullptr) return true;
+  if (io->compaction_filter_factory != nullptr && DeviceFilterOf(c) == B200C_FILTER_NONE) return true;
   if (io->user_comparator != BytewiseComparator()) return true;
   if (c->output_compression() != kNoCompression) return true;
   if (io->sst_partitioner_factory != nullptr) return true;
