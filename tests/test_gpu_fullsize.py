@@ -135,3 +135,36 @@ def test_cfg3_like_conservation_with_overlap_and_tombstones():
         n = _check_files(job)
         assert sum(job.output_meta(i).num_entries for i in range(n)) == st.num_output_records
         job.close()
+
+
+def test_cfg1_shape_against_the_reference_itself():
+    """configs[0] (the reference's own CPU-runnable case): 4 L0 BlockBasedTable SSTs from 1 M random 16-byte keys with
+    100-byte values (db_bench fillrandom shape: keys repeat within and across files), compacted to the bottommost level.
+    Full size, and the checker is the unmodified reference run right here (oracle/_ref travels to the GPU box): every output
+    file byte for byte, CompactionJobStats, FileMetaData."""
+    import os
+    import random
+    import struct
+    if not os.path.exists(H.REF_BIN):
+        pytest.fail("oracle/_ref/ref_compact missing: run __graft_entry__.build() where /root/reference exists")
+    from gpu_harness import run_product
+    rnd = random.Random(1)
+    n, files = 1_000_000, 4
+    ops = H.Ops()
+    per = n // files
+    for _ in range(files):
+        for _ in range(per):
+            ops.put(struct.pack(">QQ", 0, rnd.randrange(n)), rnd.randbytes(100))
+        ops.flush()
+    ref = H.run_reference(ops, target_file_size=64 << 20)
+    man = ref["manifest"]
+    assert len(ref["inputs"]) == files and man["stats"]["num_input_records"] > 0.9 * n * 0.8
+    p = H.params_from_reference(ref)
+    got, metas, st = run_product(p, ref["inputs"])
+    assert [len(f) for f in got] == [len(f) for f in ref["outputs"]]
+    for i, (a, b) in enumerate(zip(got, ref["outputs"])):
+        assert a == b, f"output {i} differs at byte {next(j for j in range(len(a)) if a[j] != b[j])}"
+    for k in H.STAT_KEYS:
+        assert getattr(st, k) == man["stats"][k], k
+    for m, want in zip(metas, man["outputs"]):
+        assert (m.file_size, m.num_entries, m.num_deletions) == (want["size"], want["num_entries"], want["num_deletions"])
