@@ -1018,6 +1018,7 @@ __device__ void emit_block_warp(const KeyCols& m, const EncodeParams& ep, const 
     __syncwarp();
     // trailer: compression type 0 + checksum (WriteMaybeCompressedBlock :1305-1329)
     uint32_t ck = block_checksum_warp(ep.checksum, img, payload, 0);
+    __syncwarp();  // the checksum's 8-byte loads may touch the trailer bytes written next
     if (lane == 0) {
       uint8_t* tp = img + payload;
       tp[0] = 0;
