@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200C_ABI_VERSION 2
+#define B200C_ABI_VERSION 3
 #if defined(__GNUC__)
 #define B200C_API __attribute__((visibility("default")))
 #else
@@ -56,7 +56,9 @@ enum b200c_mem_kind { B200C_MEM_HOST = 0, B200C_MEM_DEVICE = 1 };
  * decision is a function of the entry itself can run on the device */
 enum b200c_compaction_filter {
   B200C_FILTER_NONE = 0,
-  B200C_FILTER_REMOVE_EMPTY_VALUE = 1 /* RemoveEmptyValueCompactionFilter (utilities/compaction_filters/remove_emptyvalue_compactionfilter.cc:15-22) */
+  B200C_FILTER_REMOVE_EMPTY_VALUE = 1, /* RemoveEmptyValueCompactionFilter (utilities/compaction_filters/remove_emptyvalue_compactionfilter.cc:15-22) */
+  B200C_FILTER_TTL = 2                 /* TtlCompactionFilter of DBWithTTL without a user filter (utilities/ttl/db_ttl_impl.cc:200-206,
+                                          445-461): a value whose trailing fixed32 write time + ttl < ttl_now is removed */
 };
 enum b200c_checksum { B200C_CKSUM_NONE = 0, B200C_CKSUM_CRC32C = 1, B200C_CKSUM_XXH3 = 4 }; /* ChecksumType, table.h:54-60 */
 
@@ -92,6 +94,8 @@ typedef struct b200c_params {
   uint32_t output_mem;             /* enum b200c_mem_kind: where b200c_job_output_data() pointers live */
   uint32_t profile;                /* != 0: bracket every kernel group with CUDA events (b200c_job_kernel_time) */
   uint32_t compaction_filter;      /* enum b200c_compaction_filter */
+  int32_t ttl;                     /* B200C_FILTER_TTL: seconds; <= 0 keeps everything */
+  int64_t ttl_now;                 /* B200C_FILTER_TTL: clock reading (seconds) the write times are compared with */
 } b200c_params;
 
 /* FileMinMeta (compaction_executor.h:120-131) + the TableProperties RunRemote re-reads (compaction_job.cc:1043-1061) */

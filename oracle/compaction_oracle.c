@@ -616,6 +616,7 @@ static void citer_next_from_input(citer* c) {
       snprintf(g_err, sizeof g_err, "value type %u outside the restated rule set", type);
       return;
     }
+    int filtered = 0; /* the compaction filter removed this entry: tombstone without a value (:385-391) */
     int same = c->has_current_user_key && c->current_key.n - 8 == ulen &&
                memcmp(c->current_key.p, in->key, ulen) == 0;
     if (!same) { /* :538-588 first occurrence of this user key */
@@ -626,7 +627,18 @@ static void citer_next_from_input(citer* c) {
       c->has_current_user_key = 1;
       /* :579-584 the filter sees the first (newest) committed version of a user key, kTypeValue only (:236-239);
        * Decision::kRemove turns it into a tombstone with no value (:385-391) */
-      if (c->p->compaction_filter == ORC_FILTER_REMOVE_EMPTY_VALUE && type == ORC_TYPE_VALUE && in->vlen == 0) {
+      int remove = 0;
+      if (type == ORC_TYPE_VALUE) {
+        if (c->p->compaction_filter == ORC_FILTER_REMOVE_EMPTY_VALUE) remove = in->vlen == 0;
+        else if (c->p->compaction_filter == ORC_FILTER_TTL && c->p->ttl > 0 && in->vlen >= 4) {
+          /* DBWithTTLImpl::IsStale: the last four value bytes are the write time (fixed32), stale iff ts + ttl < now */
+          const uint8_t* t = in->val + in->vlen - 4;
+          int64_t ts = (int64_t)((uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24);
+          remove = ts + c->p->ttl < c->p->now;
+        }
+      }
+      if (remove) {
+        filtered = 1;
         type = ORC_TYPE_DELETION;
         citer_set_trailer(c, seq, type);
         c->st->num_record_drop_user++;
@@ -637,7 +649,7 @@ static void citer_next_from_input(citer* c) {
     c->out_seq = seq;
     c->out_type = type;
     c->out_val.n = 0;
-    buf_put(&c->out_val, in->val, in->vlen);
+    if (!filtered) buf_put(&c->out_val, in->val, in->vlen);
     /* :619-629 */
     uint64_t last_snapshot = c->cur_snap, prev_snapshot = 0;
     c->cur_seq = seq;

@@ -52,9 +52,12 @@ typedef struct orc_params {
   uint32_t num_file_creation_times;
   uint64_t first_file_number;      /* outputs are numbered consecutively from here */
   uint32_t compaction_filter;      /* ORC_FILTER_*: built-in CompactionFilter applied by the iterator (compaction_iterator.cc:231-473) */
+  int32_t ttl;                     /* ORC_FILTER_TTL: seconds (<= 0: nothing is stale, db_ttl_impl.cc:445-461) */
+  int64_t now;                     /* ORC_FILTER_TTL: the clock reading the filter compares against */
 } orc_params;
 #define ORC_FILTER_NONE 0
 #define ORC_FILTER_REMOVE_EMPTY_VALUE 1 /* utilities/compaction_filters/remove_emptyvalue_compactionfilter.cc:15-22 */
+#define ORC_FILTER_TTL 2                /* TtlCompactionFilter without a user filter, utilities/ttl/db_ttl_impl.cc:200-206,445-461 */
 
 typedef struct orc_file_meta { /* FileMinMeta, compaction_executor.h:120-131 + table properties */
   uint64_t file_number, file_size;

@@ -29,7 +29,10 @@
 #include "rocksdb/listener.h"
 #include "rocksdb/options.h"
 #include "rocksdb/table.h"
+#include "env/composite_env_wrapper.h"
 #include "rocksdb/compaction_filter.h"
+#include "rocksdb/system_clock.h"
+#include "rocksdb/utilities/db_ttl.h"
 #include "rocksdb/write_batch.h"
 #include "utilities/compaction_filters/remove_emptyvalue_compactionfilter.h"
 #ifdef WITH_B200_PLUGIN
@@ -52,6 +55,7 @@ struct Opts {
   int keep_db = 0;
   int paranoid = 0;
   int copy = 1;  // 0: leave inputs/ and outputs/ empty (timing runs only need the manifest)
+  int ttl = 0;  // > 0: open the DB as DBWithTTL (utilities/ttl): values carry a 4-byte timestamp, TtlCompactionFilter drops stale ones
   std::string filter = "none";  // remove_empty_value: the reference's RemoveEmptyValueCompactionFilter through a factory
   std::string barrier_dir;  // with barrier_n: wait until barrier_n processes have finished writing their inputs, so that
   int barrier_n = 0;        // concurrent timing runs compact at the same time
@@ -102,6 +106,18 @@ class RemoveEmptyValueFactory : public CompactionFilterFactory {
   const char* Name() const override { return "RemoveEmptyValueCompactionFilterFactory"; }
 };
 
+// wall clock under the script's control (op 6): DBWithTTL stamps values with it and TtlCompactionFilter compares against it
+class ScriptClock : public SystemClockWrapper {
+ public:
+  explicit ScriptClock(const std::shared_ptr<SystemClock>& base) : SystemClockWrapper(base) {}
+  const char* Name() const override { return "ScriptClock"; }
+  Status GetCurrentTime(int64_t* t) override {
+    *t = now;
+    return Status::OK();
+  }
+  int64_t now = 1700000000;
+};
+
 struct Reader {
   FILE* f;
   bool u8(uint8_t* v) { return fread(v, 1, 1, f) == 1; }
@@ -147,6 +163,7 @@ int main(int argc, char** argv) {
     else if (k == "executor") o.executor = v;
     else if (k == "copy") o.copy = atoi(v.c_str());
     else if (k == "filter") o.filter = v;
+    else if (k == "ttl") o.ttl = atoi(v.c_str());
     else if (k == "barrier_dir") o.barrier_dir = v;
     else if (k == "barrier_n") o.barrier_n = atoi(v.c_str());
     else {
@@ -210,9 +227,23 @@ int main(int argc, char** argv) {
     return 1;
   }
 
+  std::shared_ptr<ScriptClock> clock;
+  std::unique_ptr<Env> clock_env;
+  if (o.ttl > 0) {
+    clock = std::make_shared<ScriptClock>(SystemClock::Default());
+    clock_env.reset(new CompositeEnvWrapper(Env::Default(), clock));
+    opt.env = clock_env.get();
+  }
   DestroyDB(dbdir, opt).PermitUncheckedError();
   DB* db = nullptr;
-  Status s = DB::Open(opt, dbdir, &db);
+  Status s;
+  if (o.ttl > 0) {
+    DBWithTTL* tdb = nullptr;
+    s = DBWithTTL::Open(opt, dbdir, &tdb, o.ttl);
+    db = tdb;
+  } else {
+    s = DB::Open(opt, dbdir, &db);
+  }
   if (!s.ok()) Die("open", s);
 
   FILE* f = fopen(argv[1], "rb");
@@ -285,6 +316,12 @@ int main(int argc, char** argv) {
           s = db->CompactFiles(co, names, lvl);
           if (!s.ok()) Die("setup compaction", s);
         }
+        break;
+      }
+      case 6: {  // SET_TIME: seconds since the epoch seen by the DB from now on (ttl mode)
+        flush_batch();
+        uint32_t t = rd.u32();
+        if (clock) clock->now = t;
         break;
       }
       default:
@@ -363,7 +400,8 @@ int main(int argc, char** argv) {
   fprintf(m, "  \"checksum\": \"%s\",\n  \"max_subcompactions\": %u,\n", o.checksum.c_str(),
           o.max_subcompactions);
   fprintf(m, "  \"bottommost_level\": %s,\n", deeper_files ? "false" : "true");
-  fprintf(m, "  \"compaction_filter\": \"%s\",\n", o.filter.c_str());
+  fprintf(m, "  \"compaction_filter\": \"%s\",\n", o.ttl > 0 ? "ttl" : o.filter.c_str());
+  fprintf(m, "  \"ttl\": %d,\n  \"now\": %lld,\n", o.ttl, clock ? (long long)clock->now : 0ll);
   {
     uint64_t remote_read = 0;
 #ifdef WITH_B200_PLUGIN

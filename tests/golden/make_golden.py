@@ -21,7 +21,8 @@ SMALL = dict(  # keep committed fixtures small (tens of KB each)
     basic_bottommost=dict(n=300, nruns=3), nonbottom_tombstones=dict(n=200), snapshots=dict(n=150),
     snapshots_nonbottom=dict(n=150), varlen_keys=dict(n=200), long_keys=dict(n=100), crc32c_small_blocks=dict(n=300),
     same_user_key_across_blocks={}, tiny={}, all_deleted={}, cfg2_mini=dict(per_run=250), cfg3_mini=dict(per_run=60),
-    output_level0={}, filter_empty_value=dict(n=150), filter_empty_value_nonbottom=dict(n=150))
+    output_level0={}, filter_empty_value=dict(n=150), filter_empty_value_nonbottom=dict(n=150),
+    ttl_filter=dict(n=150), ttl_filter_nonbottom=dict(n=150))
 
 
 def main():

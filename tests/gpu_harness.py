@@ -12,7 +12,8 @@ def job_from_params(p, output_mem="host", **extra):
               column_family_id=p.column_family_id, column_family_name=p.column_family_name, db_id=p.db_id,
               db_session_id=p.db_session_id, db_host_id=p.db_host_id, creation_time=p.creation_time,
               oldest_key_time=p.oldest_key_time, file_creation_times=list(p.file_creation_times),
-              first_file_number=p.first_file_number, output_mem=output_mem, compaction_filter=p.compaction_filter)
+              first_file_number=p.first_file_number, output_mem=output_mem, compaction_filter=p.compaction_filter,
+              ttl=p.ttl, ttl_now=p.now)
     kw.update(extra)
     return T.CompactionJob(**kw)
 

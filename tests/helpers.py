@@ -16,7 +16,7 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_compact")
 REF_B200_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_compact_b200")  # same driver + the product's CompactionExecutor plugin
 MAX_SEQ = (1 << 56) - 1
 CKSUM = {"none": 0, "crc32c": 1, "xxh3": 4}
-FILTERS = {"none": 0, "remove_empty_value": 1}
+FILTERS = {"none": 0, "remove_empty_value": 1, "ttl": 2}
 
 
 class OrcParams(C.Structure):
@@ -28,7 +28,7 @@ class OrcParams(C.Structure):
         ("column_family_name", C.c_char_p), ("db_id", C.c_char_p), ("db_session_id", C.c_char_p),
         ("db_host_id", C.c_char_p), ("creation_time", C.c_uint64), ("oldest_key_time", C.c_uint64),
         ("file_creation_times", C.POINTER(C.c_uint64)), ("num_file_creation_times", C.c_uint32),
-        ("first_file_number", C.c_uint64), ("compaction_filter", C.c_uint32),
+        ("first_file_number", C.c_uint64), ("compaction_filter", C.c_uint32), ("ttl", C.c_int32), ("now", C.c_int64),
     ]
 
 
@@ -96,7 +96,9 @@ class Params:
         self.oldest_key_time = 0
         self.file_creation_times = [1700000001]
         self.first_file_number = 100
-        self.compaction_filter = "none"  # or "remove_empty_value"
+        self.compaction_filter = "none"  # or "remove_empty_value" / "ttl" (with ttl seconds and the clock reading `now`)
+        self.ttl = 0
+        self.now = 0
         for k, v in kw.items():
             assert hasattr(self, k), k
             setattr(self, k, v)
@@ -127,6 +129,8 @@ class Params:
         p.num_file_creation_times = len(self.file_creation_times)
         p.first_file_number = self.first_file_number
         p.compaction_filter = FILTERS[self.compaction_filter]
+        p.ttl = self.ttl
+        p.now = self.now
         return p
 
 
@@ -243,6 +247,9 @@ class Ops:
     def compact_all_to(self, level):
         self.b += bytes([5, level])
 
+    def set_time(self, seconds):
+        self.b += struct.pack("<BI", 6, seconds)
+
     def bytes(self):
         return bytes(self.b) + b"\x00"
 
@@ -279,7 +286,7 @@ def params_from_reference(ref) -> Params:
     p = Params(output_level=man["output_level"], bottommost_level=man["bottommost_level"],
                max_output_file_size=man["target_file_size"], block_size=man["block_size"],
                block_restart_interval=man["restart_interval"], format_version=man["format_version"],
-               checksum=man["checksum"], snapshots=man["snapshots"], compaction_filter=man.get("compaction_filter", "none"))
+               checksum=man["checksum"], snapshots=man["snapshots"], compaction_filter=man.get("compaction_filter", "none"), ttl=man.get("ttl", 0), now=man.get("now", 0))
     if ref["outputs"]:
         props = [sstfmt.parse_sst(o)["properties"] for o in ref["outputs"]]
         p0 = props[0]

@@ -193,8 +193,39 @@ def filter_empty_value_nonbottom(n=400, nruns=3, seed=15):
     return ops, dict(target_file_size=24 << 10, filter="remove_empty_value")
 
 
+def ttl_filter(n=400, nruns=4, seed=16, nonbottom=False):
+    """DBWithTTL (utilities/ttl): every value carries its write time; TtlCompactionFilter turns the newest version of a user key
+    into a tombstone when write time + ttl < now.  Runs written at different clock readings, compaction at a later one."""
+    rnd = random.Random(seed)
+    ops = Ops()
+    t0 = 1_700_000_000
+    if nonbottom:
+        ops.set_time(t0)
+        for k in [key16(0), key16(1 << 40)]:
+            ops.put(k, b"base")
+        ops.flush()
+        ops.compact_all_to(6)
+    for r in range(nruns):
+        ops.set_time(t0 + 400 * r)  # ttl 1000, compaction at t0 + 1500: runs 0 and 1 are stale, 2 and 3 are fresh
+        for k in sorted(rnd.sample(range(1, n * 2), n)):
+            if rnd.random() < 0.1:
+                ops.delete(key16(k))
+            else:
+                ops.put(key16(k), rnd.randbytes(rnd.randint(0, 50)))
+        ops.flush()
+        if r == 1:
+            ops.snapshot()
+    ops.set_time(t0 + 1500)
+    return ops, dict(target_file_size=24 << 10, ttl=1000)
+
+
+def ttl_filter_nonbottom(n=400, nruns=4, seed=17):
+    return ttl_filter(n, nruns, seed, nonbottom=True)
+
+
 ALL = dict(basic_bottommost=basic_bottommost, nonbottom_tombstones=nonbottom_tombstones, snapshots=snapshots,
            snapshots_nonbottom=snapshots_nonbottom, varlen_keys=varlen_keys, long_keys=long_keys,
            crc32c_small_blocks=crc32c_small_blocks, same_user_key_across_blocks=same_user_key_across_blocks,
            tiny=tiny, all_deleted=all_deleted, cfg2_mini=cfg2_mini, cfg3_mini=cfg3_mini, output_level0=output_level0,
-           filter_empty_value=filter_empty_value, filter_empty_value_nonbottom=filter_empty_value_nonbottom)
+           filter_empty_value=filter_empty_value, filter_empty_value_nonbottom=filter_empty_value_nonbottom,
+           ttl_filter=ttl_filter, ttl_filter_nonbottom=ttl_filter_nonbottom)

@@ -184,15 +184,15 @@ def test_corrupt_input_is_detected():
     assert ei.value.code == T.native.ERR_CORRUPTION
 
 
-@pytest.mark.parametrize("case", ["filter_empty_value", "filter_empty_value_nonbottom"])
+@pytest.mark.parametrize("case", ["filter_empty_value", "filter_empty_value_nonbottom", "ttl_filter", "ttl_filter_nonbottom"])
 def test_in_kernel_compaction_filter_counts_like_the_oracle(case):
-    """RemoveEmptyValueCompactionFilter applied inside the merge kernel (compaction_iterator.cc:579-584, :385-391): output
+    """RemoveEmptyValueCompactionFilter / TtlCompactionFilter (DBWithTTL) applied inside the merge kernel (compaction_iterator.cc:579-584, :385-391): output
     bytes are covered by the fixture tests above; CompactionIterationStats::num_record_drop_user is not part of
     CompactionJobStats, so it is checked against the oracle."""
     from gpu_harness import run_product
     g = H.load_golden(case)
     p = H.params_from_reference(g)
-    assert p.compaction_filter == "remove_empty_value"
+    assert p.compaction_filter in ("remove_empty_value", "ttl")
     files, _, st = run_product(p, g["inputs"])
     ofiles, _, ost = H.oracle_compact(p, g["inputs"])
     assert files == ofiles == g["outputs"]

@@ -653,6 +653,8 @@ int run_job(b200c_job* j, int until) {
   mp.snapshots = j->snaps_d.as<uint64_t>();
   mp.earliest_snapshot = P.num_snapshots ? j->snapshots[0] : kMaxSeq;
   mp.filter = P.compaction_filter;
+  mp.ttl = P.ttl;
+  mp.now = P.ttl_now;
   MergeCounters* counters = reinterpret_cast<MergeCounters*>(small + kSlotCounters);
   EncodeWork W;
   memset(&W, 0, sizeof W);
@@ -828,7 +830,8 @@ int b200c_job_create(const b200c_params* p, b200c_job** out) {
   if (p->block_restart_interval < 1) return fail(B200C_ERR_INVALID_ARGUMENT, "block_restart_interval < 1");
   if (p->block_size_deviation > 100) return fail(B200C_ERR_INVALID_ARGUMENT, "block_size_deviation > 100");
   if (p->format_version < 3 || p->format_version > 5) return fail(B200C_ERR_NOT_SUPPORTED, "output format_version must be 3..5");
-  if (p->compaction_filter != B200C_FILTER_NONE && p->compaction_filter != B200C_FILTER_REMOVE_EMPTY_VALUE)
+  if (p->compaction_filter != B200C_FILTER_NONE && p->compaction_filter != B200C_FILTER_REMOVE_EMPTY_VALUE &&
+      p->compaction_filter != B200C_FILTER_TTL)
     return fail(B200C_ERR_NOT_SUPPORTED, "compaction filter is not one of the built-in device filters");
   if (p->checksum != B200C_CKSUM_XXH3 && p->checksum != B200C_CKSUM_CRC32C && p->checksum != B200C_CKSUM_NONE)
     return fail(B200C_ERR_NOT_SUPPORTED, "output checksum must be kNoChecksum, kCRC32c or kXXH3");

@@ -48,6 +48,8 @@ struct MergeParams {
   const uint64_t* snapshots;         // device, ascending
   uint64_t earliest_snapshot;        // snapshots[0] or kMaxSeq
   uint32_t filter;                   // b200c_compaction_filter
+  int32_t ttl;                       // B200C_FILTER_TTL
+  int64_t now;
 };
 struct MergeCounters {               // device-side CompactionIterationStats
   unsigned long long n_out, n_input_deletions, n_hidden, n_obsolete, raw_key_bytes, raw_value_bytes, n_silent, n_user_drop;

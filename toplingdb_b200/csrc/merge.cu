@@ -219,7 +219,7 @@ __device__ __forceinline__ Key skey(const TileSmem& s, uint32_t id) {
   k.hi = s.hi[id];
   k.lo = s.lo[id];
   k.tr = s.tr[id];
-  k.ulen = s.ulen[id] & 0x7fu;
+  k.ulen = s.ulen[id] & 0x3fu;
   return k;
 }
 // List positions are XOR-swizzled inside 16-element groups: a thread owns kMV = 8 consecutive list positions, and with
@@ -229,7 +229,7 @@ __device__ __forceinline__ uint32_t PH(uint32_t e) { return e ^ ((e >> 4) & 15u)
 __device__ __forceinline__ bool tie_less(const TileSmem& s, uint32_t ib, uint32_t ia) {
   const uint64_t lb = s.lo[ib], la = s.lo[ia];
   if (lb != la) return lb < la;
-  const uint32_t ub = s.ulen[ib] & 0x7fu, ua = s.ulen[ia] & 0x7fu;
+  const uint32_t ub = s.ulen[ib] & 0x3fu, ua = s.ulen[ia] & 0x3fu;
   if (ub != ua) return ub < ua;
   return s.tr[ib] > s.tr[ia];
 }
@@ -307,10 +307,25 @@ __device__ bool oldest_version_at_most(const KeyCols& in, const uint64_t* run_st
   return false;
 }
 // newest version of user key with seq <= stripe_hi: the head of that (user key, stripe) group
+// Compaction filter decision (compaction_iterator.cc:231-473) for the kTypeValue entry at column position `src`: the built-in
+// filters only look at the entry itself.  REMOVE_EMPTY_VALUE: empty value; TTL: the value's trailing fixed32 write time + ttl < now
+// (DBWithTTLImpl::IsStale, utilities/ttl/db_ttl_impl.cc:445-461; values shorter than the 4-byte stamp are left alone).
+__device__ __forceinline__ bool filter_removes(const MergeParams& mp, const KeyCols& in, uint64_t src) {
+  const uint32_t vlen = meta_vlen(in.meta[src]);
+  if (mp.filter == 1) return vlen == 0;
+  if (mp.filter == 2) {
+    if (mp.ttl <= 0 || vlen < 4) return false;
+    const uint8_t* t = reinterpret_cast<const uint8_t*>((uintptr_t)in.vref[src]) + vlen - 4;
+    const int64_t ts = (int64_t)((uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24);
+    return ts + mp.ttl < mp.now;
+  }
+  return false;
+}
+
 // *head_tr carries the type the compaction iterator sees: with the remove-empty-value filter the NEWEST version of a user
 // key is turned into a tombstone when it is a kTypeValue with an empty value (compaction_iterator.cc:579-584, :385-391)
 __device__ bool group_head(const KeyCols& in, const uint64_t* run_start, uint32_t nruns, uint64_t hi, uint64_t lo, uint32_t ulen,
-                           uint64_t stripe_hi, uint32_t filter, uint64_t* head_tr) {
+                           uint64_t stripe_hi, const MergeParams& mp, uint64_t* head_tr) {
   Key x;
   x.hi = hi;
   x.lo = lo;
@@ -333,7 +348,7 @@ __device__ bool group_head(const KeyCols& in, const uint64_t* run_start, uint32_
       best_pos = base + c;
     }
   }
-  if (found && filter == 1 && !newer_exists && (best & 0xff) == kTypeValue && meta_vlen(in.meta[best_pos]) == 0)
+  if (found && mp.filter != 0 && !newer_exists && (best & 0xff) == kTypeValue && filter_removes(mp, in, best_pos))
     best = (best & ~0xffull) | kTypeDeletion;
   *head_tr = best;
   return found;
@@ -420,7 +435,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
         s.hi[i] = lp[j].x;
         s.lo[i] = lp[j].y;
         s.tr[i] = ltr[j];
-        s.ulen[i] = (uint8_t)(meta_ulen(lmt[j]) | (meta_vlen(lmt[j]) == 0 ? 0x80u : 0u));  // bit 7: empty value (compaction filter)
+        s.ulen[i] = (uint8_t)(meta_ulen(lmt[j]) | (meta_vlen(lmt[j]) == 0 ? 0x80u : 0u));  // bit 7: empty value (compaction filter); bit 6 is set later: value removed by the filter
         s.idx[PH(i)] = (uint16_t)i;
       }
     }
@@ -491,6 +506,15 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   }
   // ---- compaction-iterator rules per merged position
   const bool cond_possible = mp.bottommost && mp.nsnapshots > 0;
+  auto col_of = [&](uint32_t pos) -> uint64_t {  // column position of the entry at load position pos
+    uint32_t lo = 0, hi = k;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s.seg[mid] <= pos) lo = mid;
+      else hi = mid;
+    }
+    return s.sbeg[lo] + (pos - s.seg[lo]);
+  };
   uint32_t keep_mask = 0, nkeep = 0;
   unsigned long long c_hidden = 0, c_obsolete = 0, c_indel = 0, c_kbytes = 0, c_vbytes = 0, c_silent = 0, c_userdrop = 0;
   uint64_t otr[kMV];
@@ -515,7 +539,10 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     const uint64_t seq = c.tr >> 8;
     const uint32_t type0 = (uint32_t)(c.tr & 0xff);  // as read; the input-side counters use it
     uint32_t type = type0;
-    if (mp.filter == 1 && !same && type0 == kTypeValue && (s.ulen[id] & 0x80u)) {
+    bool removed = false;
+    if (mp.filter != 0 && !same && type0 == kTypeValue)
+      removed = mp.filter == 1 ? (s.ulen[id] & 0x80u) != 0 : filter_removes(mp, in, col_of(id));
+    if (removed) {
       // compaction filter on the first (newest) version of a user key: Decision::kRemove turns it into a tombstone
       type = kTypeDeletion;
       c.tr = (seq << 8) | kTypeDeletion;
@@ -546,7 +573,8 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
           have = true;
           q--;
         }
-        if (have && mp.filter == 1 && (head_tr & 0xff) == kTypeValue && (s.ulen[head_id] & 0x80u)) {
+        if (have && mp.filter != 0 && (head_tr & 0xff) == kTypeValue &&
+            (mp.filter == 1 ? (s.ulen[head_id] & 0x80u) != 0 : filter_removes(mp, in, col_of(head_id)))) {
           // the head is filtered if it is the first version of its user key: look at the entry in front of it
           bool first_occ;
           if (q >= 0) {
@@ -561,7 +589,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
           uint64_t d2;
           bool pred_same = s.pred.hi == c.hi && s.pred.lo == c.lo && s.pred.ulen == c.ulen &&
                            stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, s.pred.tr >> 8, &d2) == st_c;
-          if (pred_same) have = group_head(in, run_start, k, c.hi, c.lo, c.ulen, st_c, mp.filter, &head_tr);
+          if (pred_same) have = group_head(in, run_start, k, c.hi, c.lo, c.ulen, st_c, mp, &head_tr);
         }
         if (have && (head_tr & 0xff) == kTypeDeletion) silent = true;  // head seq > earliest snapshot since its stripe is not the first
       }
@@ -599,6 +627,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
       otr[x] = (mp.bottommost && seq <= mp.earliest_snapshot) ? (uint64_t)type : c.tr;
     }
     if (silent) keep_mask |= 1u << (16 + x);
+    if (removed && keep) keep_mask |= 1u << (24 + x);  // written out as a tombstone: its value must not follow it
   }
   // ---- tile-local ranks
   uint32_t inc = warp_incl_scan(nkeep);
@@ -640,6 +669,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
     if ((keep_mask >> x) & 1) {
       s.idx[PH(rank)] = oid[x];
       s.tr[oid[x]] = otr[x];  // each load position is owned by exactly one merged position
+      if ((keep_mask >> (24 + x)) & 1) s.ulen[oid[x]] |= 0x40u;
       rank++;
     }
   }
@@ -667,6 +697,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
         gp[j] = (uint16_t)pos;
         gv[j] = in.vref[src];
         gm[j] = in.meta[src];
+        if (s.ulen[pos] & 0x40u) gm[j] = make_meta(meta_ulen(gm[j]), 0);  // removed by the compaction filter: tombstone, no value
       }
     }
     if (w == 0) {  // second half of the look-back

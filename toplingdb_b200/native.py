@@ -27,7 +27,7 @@ class Params(C.Structure):
         ("db_id", C.c_char_p), ("db_session_id", C.c_char_p), ("db_host_id", C.c_char_p), ("creation_time", C.c_uint64),
         ("oldest_key_time", C.c_uint64), ("file_creation_times", C.POINTER(C.c_uint64)),
         ("num_file_creation_times", C.c_uint32), ("first_file_number", C.c_uint64), ("output_mem", C.c_uint32),
-        ("profile", C.c_uint32), ("compaction_filter", C.c_uint32),
+        ("profile", C.c_uint32), ("compaction_filter", C.c_uint32), ("ttl", C.c_int32), ("ttl_now", C.c_int64),
     ]
 
 
@@ -150,7 +150,7 @@ class CompactionJob:
             elif k == "bottommost_level":
                 p.bottommost_level = int(v)
             elif k == "compaction_filter":
-                p.compaction_filter = {"none": 0, "remove_empty_value": 1}.get(v, v)
+                p.compaction_filter = {"none": 0, "remove_empty_value": 1, "ttl": 2}.get(v, v)
             else:
                 if not hasattr(p, k):
                     raise TypeError(f"unknown job parameter {k}")

@@ -13,6 +13,7 @@
 
 #include "b200c.h"
 #include "rocksdb/compaction_filter.h"
+#include "rocksdb/convenience.h"
 #include "db/compaction/compaction.h"
 #include "db/version_edit.h"
 #include "file/filename.h"
@@ -26,9 +27,18 @@ namespace {
 
 // Which device filter (include/b200c.h b200c_compaction_filter) the column family's filter factory stands for; NONE when the
 // family has no factory or the filter is not one the merge kernel implements.  Filters are recognised by CompactionFilter::Name().
-uint32_t DeviceFilterOf(const Compaction* c) {
+uint32_t DeviceFilterOf(const Compaction* c, int32_t* ttl = nullptr) {
   const auto& factory = c->immutable_options()->compaction_filter_factory;
   if (!factory) return B200C_FILTER_NONE;
+  if (std::string(factory->Name()) == "TtlCompactionFilterFactory") {
+    // DBWithTTL (utilities/ttl/db_ttl_impl.h:183-206): only without a user filter stacked underneath; "ttl" is a registered option
+    if (factory->Inner() != nullptr) return B200C_FILTER_NONE;
+    std::string v;
+    ConfigOptions co;
+    if (!factory->GetOption(co, "ttl", &v).ok()) return B200C_FILTER_NONE;
+    if (ttl) *ttl = (int32_t)strtol(v.c_str(), nullptr, 10);
+    return B200C_FILTER_TTL;
+  }
   CompactionFilter::Context ctx;
   ctx.is_full_compaction = c->is_full_compaction();
   ctx.is_manual_compaction = c->is_manual_compaction();
@@ -143,7 +153,8 @@ class B200CompactionExecutor : public CompactionExecutor {
     bp.num_file_creation_times = 1;
     bp.first_file_number = 1;  // numbers are local to output_dir; RunRemote renames every file (compaction_job.cc:1019-1033)
     bp.output_mem = B200C_MEM_HOST;
-    bp.compaction_filter = DeviceFilterOf(c_);
+    bp.compaction_filter = DeviceFilterOf(c_, &bp.ttl);
+    bp.ttl_now = now;  // TtlCompactionFilter reads the clock per entry; one reading per job here
 
     b200c_job* job = nullptr;
     Status s = FromB200(b200c_job_create(&bp, &job));
