@@ -1096,6 +1096,78 @@ static uint64_t fct_for(const orc_params* p, int file_idx) {
   uint32_t i = (uint32_t)file_idx < p->num_file_creation_times ? (uint32_t)file_idx : p->num_file_creation_times - 1;
   return p->file_creation_times[i];
 }
+/* ------------------------------------------------------------------ grandparent-aware cutting
+ * CompactionOutputs::{UpdateGrandparentBoundaryInfo :133-187, GetCurrentKeyGrandparentOverlappedBytes :189-229,
+ * ShouldStopBefore :231-354}; sstableKeyCompare (compaction.cc:28-43) reduces to a user-key compare here (no range
+ * tombstone sentinels on the path). */
+typedef struct gp_state {
+  int being_gap, seen_key;
+  size_t index, switched;
+  uint64_t overlapped;
+} gp_state;
+static size_t gp_update(gp_state* g, const orc_params* p, const uint8_t* uk, size_t un) {
+  size_t crossed = 0;
+  const orc_grandparent* gp = p->grandparents;
+  const size_t n = p->num_grandparents;
+  while (g->index < n) {
+    if (g->being_gap) {
+      if (ukey_cmp(uk, un, gp[g->index].smallest, gp[g->index].smallest_len) < 0) break;
+      if (g->seen_key) {
+        crossed++;
+        g->overlapped += gp[g->index].file_size;
+        g->switched++;
+      }
+      g->being_gap = 0;
+    } else {
+      int c = ukey_cmp(uk, un, gp[g->index].largest, gp[g->index].largest_len);
+      if (c < 0 || (c == 0 && (g->index == n - 1 ||
+                               ukey_cmp(uk, un, gp[g->index + 1].smallest, gp[g->index + 1].smallest_len) < 0)))
+        break;
+      if (g->seen_key) {
+        crossed++;
+        g->switched++;
+      }
+      g->being_gap = 1;
+      g->index++;
+    }
+  }
+  if (!g->seen_key && !g->being_gap) { /* the first key sits inside a grandparent file */
+    g->overlapped = gp[g->index].file_size;
+    for (long i = (long)g->index - 1; i >= 0 && ukey_cmp(uk, un, gp[i].largest, gp[i].largest_len) == 0; i--)
+      g->overlapped += gp[i].file_size;
+  }
+  g->seen_key = 1;
+  return crossed;
+}
+static uint64_t gp_current_key_overlap(const gp_state* g, const orc_params* p, const uint8_t* uk, size_t un) {
+  if (g->being_gap) return 0;
+  const orc_grandparent* gp = p->grandparents;
+  uint64_t b = gp[g->index].file_size;
+  for (long i = (long)g->index - 1; i >= 0 && ukey_cmp(uk, un, gp[i].largest, gp[i].largest_len) == 0; i--) b += gp[i].file_size;
+  return b;
+}
+static int should_stop_before(gp_state* g, const orc_params* p, const uint8_t* uk, size_t un, int have_builder,
+                              uint64_t cur_file_size) {
+  const uint64_t prev_overlapped = g->overlapped;
+  size_t crossed = 0;
+  if (p->output_level > 0 && p->num_grandparents) crossed = gp_update(g, p, uk, un);
+  if (!have_builder) return 0;
+  if (p->output_level == 0) return 0; /* :272 */
+  if (cur_file_size >= p->max_output_file_size) return 1; /* :277 */
+  if (crossed > 0) {
+    if (g->overlapped + cur_file_size > p->max_compaction_bytes) return 1; /* :299 */
+    const size_t skippable = g->being_gap ? 2 : 3;
+    if (p->level_compaction_dynamic_file_size && crossed >= skippable &&
+        g->overlapped - prev_overlapped > p->target_output_file_size / 8) /* :325-331 */
+      return 1;
+    size_t pct = g->switched * 5 < 40 ? g->switched * 5 : 40;
+    if (p->level_compaction_dynamic_file_size &&
+        cur_file_size >= ((p->target_output_file_size + 99) / 100) * (50 + pct)) /* :343-349 */
+      return 1;
+  }
+  return 0;
+}
+
 int orc_compact(const orc_params* p, int n_inputs, const uint8_t* const* inputs, const uint64_t* input_lens,
                 orc_result** out) {
   merge_in m;
@@ -1121,13 +1193,16 @@ int orc_compact(const orc_params* p, int n_inputs, const uint8_t* const* inputs,
     int have_builder = 0, file_idx = 0;
     uint64_t cur_file_size = 0;
     orc_file_meta meta;
+    gp_state gps = {1, 0, 0, 0, 0}; /* compaction_outputs.h:331-372 initial values */
     while (c.valid && !c.err && !m.err) {
-      /* ShouldStopBefore :231-354 with no grandparents / partitioner / TTL */
-      if (have_builder && p->output_level != 0 && cur_file_size >= p->max_output_file_size) {
+      /* AddToOutput :356-384: ShouldStopBefore (no partitioner / TTL-file cut / round-robin), then the grandparent reset */
+      if (should_stop_before(&gps, p, c.current_key.p, c.current_key.n - 8, have_builder, cur_file_size) && have_builder) {
         tb_finish(&t);
         result_push(r, &t, &meta);
         tb_free(&t);
         have_builder = 0;
+        gps.switched = 0;
+        gps.overlapped = p->num_grandparents ? gp_current_key_overlap(&gps, p, c.current_key.p, c.current_key.n - 8) : 0;
       }
       if (!have_builder) {
         tb_init(&t, p, p->first_file_number + (uint64_t)file_idx, fct_for(p, file_idx));

@@ -29,6 +29,14 @@ enum { ORC_CKSUM_NONE = 0, ORC_CKSUM_CRC32C = 1, ORC_CKSUM_XXH3 = 4 };
 /* Job description: the subset of CompactionParams (db/compaction/compaction_executor.h:33-118),
  * BlockBasedTableOptions (include/rocksdb/table.h:237-564) and TableBuilderOptions
  * (db/compaction/compaction_job.cc:2323-2331) that shapes the output bytes. */
+typedef struct orc_grandparent { /* one file of the level below the output: FileMetaData::{smallest,largest}.user_key(), fd.GetFileSize() */
+  const uint8_t* smallest;
+  uint32_t smallest_len;
+  const uint8_t* largest;
+  uint32_t largest_len;
+  uint64_t file_size;
+} orc_grandparent;
+
 typedef struct orc_params {
   int32_t output_level;
   int32_t bottommost_level;        /* Compaction::bottommost_level() */
@@ -54,6 +62,12 @@ typedef struct orc_params {
   uint32_t compaction_filter;      /* ORC_FILTER_*: built-in CompactionFilter applied by the iterator (compaction_iterator.cc:231-473) */
   int32_t ttl;                     /* ORC_FILTER_TTL: seconds (<= 0: nothing is stale, db_ttl_impl.cc:445-461) */
   int64_t now;                     /* ORC_FILTER_TTL: the clock reading the filter compares against */
+  /* grandparent-aware output cutting, CompactionOutputs::ShouldStopBefore (compaction_outputs.cc:231-354) */
+  const orc_grandparent* grandparents; /* Compaction::grandparents(), sorted; NULL / 0 = none */
+  uint32_t num_grandparents;
+  uint32_t level_compaction_dynamic_file_size; /* ImmutableOptions (default true) */
+  uint64_t max_compaction_bytes;       /* Compaction::max_compaction_bytes() */
+  uint64_t target_output_file_size;    /* Compaction::target_output_file_size() (max_output_file_size is twice this with grandparents) */
 } orc_params;
 #define ORC_FILTER_NONE 0
 #define ORC_FILTER_REMOVE_EMPTY_VALUE 1 /* utilities/compaction_filters/remove_emptyvalue_compactionfilter.cc:15-22 */

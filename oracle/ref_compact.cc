@@ -15,6 +15,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cinttypes>
 #include <cstdio>
@@ -55,6 +56,9 @@ struct Opts {
   int keep_db = 0;
   int paranoid = 0;
   int copy = 1;  // 0: leave inputs/ and outputs/ empty (timing runs only need the manifest)
+  uint64_t setup_file_size = UINT64_MAX;  // output file size limit of the set-up compactions (op 5): several files below the job
+  std::string mode = "files";  // range: run the job through DB::CompactRange, the way the DB's own picker builds it -- the
+                               // compaction then carries its grandparents (files at output_level + 1); CompactFiles never does
   int ttl = 0;  // > 0: open the DB as DBWithTTL (utilities/ttl): values carry a 4-byte timestamp, TtlCompactionFilter drops stale ones
   std::string filter = "none";  // remove_empty_value: the reference's RemoveEmptyValueCompactionFilter through a factory
   std::string barrier_dir;  // with barrier_n: wait until barrier_n processes have finished writing their inputs, so that
@@ -91,9 +95,33 @@ class StatsListener : public EventListener {
  public:
   CompactionJobInfo last;
   int completed = 0;
-  void OnCompactionCompleted(DB*, const CompactionJobInfo& ci) override {
+  // range mode: DB::CompactRange goes on to push the result further down, so the L0 -> output_level job is captured here, right
+  // after it has been installed (its files are still in place)
+  int capture_level = -1;
+  bool captured = false;
+  bool copy = true;
+  std::string dbdir, outdir;
+  CompactionJobInfo job;
+  std::vector<SstFileMetaData> outs;
+  void OnCompactionCompleted(DB* db, const CompactionJobInfo& ci) override {
     last = ci;
     completed++;
+    if (getenv("REF_COMPACT_DEBUG"))
+      fprintf(stderr, "compaction #%d: L%d -> L%d, %zu inputs, %zu outputs, reason %d, in %llu out %llu records\n", completed,
+              ci.base_input_level, ci.output_level, ci.input_files.size(), ci.output_files.size(), (int)ci.compaction_reason,
+              (unsigned long long)ci.stats.num_input_records, (unsigned long long)ci.stats.num_output_records);
+    if (capture_level >= 0 && !captured && ci.base_input_level == 0 && ci.output_level == capture_level) {
+      captured = true;
+      job = ci;
+      ColumnFamilyMetaData cfm;
+      db->GetColumnFamilyMetaData(&cfm);
+      for (auto& lvl : cfm.levels)
+        if (lvl.level == capture_level)
+          for (auto& fm : lvl.files) {
+            outs.push_back(fm);
+            if (copy) CopyFile(dbdir + fm.name, outdir + fm.name);
+          }
+    }
   }
 };
 
@@ -163,6 +191,8 @@ int main(int argc, char** argv) {
     else if (k == "executor") o.executor = v;
     else if (k == "copy") o.copy = atoi(v.c_str());
     else if (k == "filter") o.filter = v;
+    else if (k == "mode") o.mode = v;
+    else if (k == "setup_file_size") o.setup_file_size = strtoull(v.c_str(), nullptr, 0);
     else if (k == "ttl") o.ttl = atoi(v.c_str());
     else if (k == "barrier_dir") o.barrier_dir = v;
     else if (k == "barrier_n") o.barrier_n = atoi(v.c_str());
@@ -193,6 +223,7 @@ int main(int argc, char** argv) {
   opt.max_subcompactions = o.max_subcompactions;
   opt.max_background_jobs = 2;
   opt.paranoid_file_checks = o.paranoid != 0;
+  if (o.mode == "range") opt.level_compaction_dynamic_level_bytes = false;  // CompactRange then goes L0 -> L1, not to a base level
   opt.info_log_level = WARN_LEVEL;
   opt.stats_dump_period_sec = 0;
   opt.stats_persist_period_sec = 0;
@@ -312,7 +343,7 @@ int main(int argc, char** argv) {
         if (!names.empty()) {
           CompactionOptions co;
           co.compression = kNoCompression;
-          co.output_file_size_limit = UINT64_MAX;
+          co.output_file_size_limit = o.setup_file_size;
           s = db->CompactFiles(co, names, lvl);
           if (!s.ok()) Die("setup compaction", s);
         }
@@ -374,6 +405,11 @@ int main(int argc, char** argv) {
       usleep(1000);
     }
   }
+  std::vector<SstFileMetaData> grandparents;  // what CompactionPicker::GetGrandparents would pick: files one level below the output
+  for (auto& lvl : cfm.levels)
+    if (lvl.level == o.output_level + 1)
+      for (auto& fm : lvl.files) grandparents.push_back(fm);
+  const bool range_mode = o.mode == "range";
   CompactionOptions co;
   co.compression = kNoCompression;
   co.output_file_size_limit = o.target_file_size;
@@ -381,7 +417,24 @@ int main(int argc, char** argv) {
   std::vector<std::string> out_names;
   CompactionJobInfo ji;
   auto t0 = std::chrono::steady_clock::now();
-  s = db->CompactFiles(co, input_names, o.output_level, -1, &out_names, &ji);
+  if (range_mode) {
+    listener->capture_level = o.output_level;
+    listener->copy = o.copy != 0;
+    listener->dbdir = dbdir;
+    listener->outdir = work + "/outputs";
+    CompactRangeOptions cro;
+    cro.exclusive_manual_compaction = true;
+    cro.bottommost_level_compaction = BottommostLevelCompaction::kSkip;
+    s = db->CompactRange(cro, nullptr, nullptr);
+    if (s.ok() && !listener->captured) {
+      fprintf(stderr, "ref_compact: CompactRange ran no L0 -> L%d compaction (trivial move?)\n", o.output_level);
+      return 2;
+    }
+    ji = listener->job;
+  } else {
+    grandparents.clear();  // DB::CompactFiles builds the compaction without grandparents (compaction_picker.cc CompactFiles)
+    s = db->CompactFiles(co, input_names, o.output_level, -1, &out_names, &ji);
+  }
   auto t1 = std::chrono::steady_clock::now();
   if (!s.ok()) Die("compaction", s);
   double wall_us = std::chrono::duration<double, std::micro>(t1 - t0).count();
@@ -400,6 +453,21 @@ int main(int argc, char** argv) {
   fprintf(m, "  \"checksum\": \"%s\",\n  \"max_subcompactions\": %u,\n", o.checksum.c_str(),
           o.max_subcompactions);
   fprintf(m, "  \"bottommost_level\": %s,\n", deeper_files ? "false" : "true");
+  {
+    // Compaction::max_output_file_size_ (compaction.cc:289-295): twice the target when the job has grandparents
+    // range mode takes the size from target_file_size_base, which the reference clamps to >= 512 KiB (options/cf_options.cc:1030-1033)
+    const uint64_t eff_target = range_mode ? std::max<uint64_t>(o.target_file_size, 512 << 10) : o.target_file_size;
+    const bool doubled = !grandparents.empty() && deeper_files && opt.level_compaction_dynamic_file_size;
+    fprintf(m, "  \"mode\": \"%s\",\n  \"max_output_file_size\": %" PRIu64 ",\n  \"max_compaction_bytes\": %" PRIu64 ",\n",
+            o.mode.c_str(), doubled ? 2 * eff_target : eff_target,
+            opt.max_compaction_bytes ? opt.max_compaction_bytes : eff_target * 25);
+    fprintf(m, "  \"target_output_file_size\": %" PRIu64 ",\n", eff_target);
+    fprintf(m, "  \"level_compaction_dynamic_file_size\": %s,\n  \"grandparents\": [", opt.level_compaction_dynamic_file_size ? "true" : "false");
+    for (size_t i = 0; i < grandparents.size(); i++)
+      fprintf(m, "%s\n    {\"smallestkey\": \"%s\", \"largestkey\": \"%s\", \"size\": %" PRIu64 "}", i ? "," : "",
+              Hex(grandparents[i].smallestkey).c_str(), Hex(grandparents[i].largestkey).c_str(), grandparents[i].size);
+    fprintf(m, "%s],\n", grandparents.empty() ? "" : "\n  ");
+  }
   fprintf(m, "  \"compaction_filter\": \"%s\",\n", o.ttl > 0 ? "ttl" : o.filter.c_str());
   fprintf(m, "  \"ttl\": %d,\n  \"now\": %lld,\n", o.ttl, clock ? (long long)clock->now : 0ll);
   {
@@ -446,12 +514,14 @@ int main(int argc, char** argv) {
   fprintf(m, "  ],\n  \"outputs\": [\n");
   db->GetColumnFamilyMetaData(&cfm);
   std::vector<SstFileMetaData> outs;
-  for (auto& lvl : cfm.levels)
-    if (lvl.level == o.output_level)
-      for (auto& fm : lvl.files) outs.push_back(fm);
+  if (range_mode) outs = listener->outs;  // captured (and copied) when the job completed
+  else
+    for (auto& lvl : cfm.levels)
+      if (lvl.level == o.output_level)
+        for (auto& fm : lvl.files) outs.push_back(fm);
   for (size_t i = 0; i < outs.size(); i++) {
     auto& fm = outs[i];
-    if (o.copy) CopyFile(dbdir + fm.name, work + "/outputs" + fm.name);
+    if (o.copy && !range_mode) CopyFile(dbdir + fm.name, work + "/outputs" + fm.name);
     fprintf(m,
             "    {\"name\": \"%s\", \"size\": %" PRIu64 ", \"file_number\": %" PRIu64
             ", \"smallest_seqno\": %" PRIu64 ", \"largest_seqno\": %" PRIu64 ", \"num_entries\": %" PRIu64

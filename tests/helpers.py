@@ -19,6 +19,11 @@ CKSUM = {"none": 0, "crc32c": 1, "xxh3": 4}
 FILTERS = {"none": 0, "remove_empty_value": 1, "ttl": 2}
 
 
+class OrcGrandparent(C.Structure):
+    _fields_ = [("smallest", C.c_char_p), ("smallest_len", C.c_uint32), ("largest", C.c_char_p), ("largest_len", C.c_uint32),
+                ("file_size", C.c_uint64)]
+
+
 class OrcParams(C.Structure):
     _fields_ = [
         ("output_level", C.c_int32), ("bottommost_level", C.c_int32), ("max_output_file_size", C.c_uint64),
@@ -29,6 +34,9 @@ class OrcParams(C.Structure):
         ("db_host_id", C.c_char_p), ("creation_time", C.c_uint64), ("oldest_key_time", C.c_uint64),
         ("file_creation_times", C.POINTER(C.c_uint64)), ("num_file_creation_times", C.c_uint32),
         ("first_file_number", C.c_uint64), ("compaction_filter", C.c_uint32), ("ttl", C.c_int32), ("now", C.c_int64),
+        ("grandparents", C.POINTER(OrcGrandparent)), ("num_grandparents", C.c_uint32),
+        ("level_compaction_dynamic_file_size", C.c_uint32), ("max_compaction_bytes", C.c_uint64),
+        ("target_output_file_size", C.c_uint64),
     ]
 
 
@@ -99,6 +107,10 @@ class Params:
         self.compaction_filter = "none"  # or "remove_empty_value" / "ttl" (with ttl seconds and the clock reading `now`)
         self.ttl = 0
         self.now = 0
+        self.grandparents = []  # [(smallest user key, largest user key, file size)]: files one level below the output
+        self.level_compaction_dynamic_file_size = True
+        self.max_compaction_bytes = 0  # 0: 25 x target
+        self.target_output_file_size = 0  # 0: max_output_file_size
         for k, v in kw.items():
             assert hasattr(self, k), k
             setattr(self, k, v)
@@ -131,6 +143,17 @@ class Params:
         p.compaction_filter = FILTERS[self.compaction_filter]
         p.ttl = self.ttl
         p.now = self.now
+        self._gp = (OrcGrandparent * max(1, len(self.grandparents)))()
+        for i, (a, b, sz) in enumerate(self.grandparents):
+            self._gp[i].smallest, self._gp[i].smallest_len = a, len(a)
+            self._gp[i].largest, self._gp[i].largest_len = b, len(b)
+            self._gp[i].file_size = sz
+        p.grandparents = C.cast(self._gp, C.POINTER(OrcGrandparent))
+        p.num_grandparents = len(self.grandparents)
+        p.level_compaction_dynamic_file_size = int(self.level_compaction_dynamic_file_size)
+        tgt = self.target_output_file_size or self.max_output_file_size
+        p.target_output_file_size = tgt
+        p.max_compaction_bytes = self.max_compaction_bytes or tgt * 25
         return p
 
 
@@ -284,9 +307,12 @@ def params_from_reference(ref) -> Params:
     TableBuilderOptions, db/compaction/compaction_job.cc:2258-2331)."""
     man = ref["manifest"]
     p = Params(output_level=man["output_level"], bottommost_level=man["bottommost_level"],
-               max_output_file_size=man["target_file_size"], block_size=man["block_size"],
+               max_output_file_size=man.get("max_output_file_size", man["target_file_size"]), block_size=man["block_size"],
                block_restart_interval=man["restart_interval"], format_version=man["format_version"],
-               checksum=man["checksum"], snapshots=man["snapshots"], compaction_filter=man.get("compaction_filter", "none"), ttl=man.get("ttl", 0), now=man.get("now", 0))
+               checksum=man["checksum"], snapshots=man["snapshots"], compaction_filter=man.get("compaction_filter", "none"), ttl=man.get("ttl", 0), now=man.get("now", 0),
+               grandparents=[(bytes.fromhex(g["smallestkey"]), bytes.fromhex(g["largestkey"]), g["size"]) for g in man.get("grandparents", [])],
+               level_compaction_dynamic_file_size=man.get("level_compaction_dynamic_file_size", True),
+               max_compaction_bytes=man.get("max_compaction_bytes", 0), target_output_file_size=man.get("target_output_file_size", 0))
     if ref["outputs"]:
         props = [sstfmt.parse_sst(o)["properties"] for o in ref["outputs"]]
         p0 = props[0]

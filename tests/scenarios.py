@@ -223,6 +223,26 @@ def ttl_filter_nonbottom(n=400, nruns=4, seed=17):
     return ttl_filter(n, nruns, seed, nonbottom=True)
 
 
+def grandparent_cuts(n=8000, seed=18, nruns=3):
+    """The job as the DB's own picker builds it (DB::CompactRange): L0 -> L1 with the overlapping L2 files as grandparents, so
+    CompactionOutputs::ShouldStopBefore also cuts output files at grandparent boundaries (compaction_outputs.cc:294-351).
+    Oracle-only: the device path does not implement these cut rules yet (the executor keeps such jobs on the CPU)."""
+    rnd = random.Random(seed)
+    ops = Ops()
+    for k in sorted(rnd.sample(range(1, n * 4), n)):
+        ops.put(key16(k), rnd.randbytes(60))
+    ops.flush()
+    ops.compact_all_to(2)
+    for _ in range(nruns):
+        for k in sorted(rnd.sample(range(1, n * 4), n // 2)):
+            ops.put(key16(k), rnd.randbytes(60))
+        ops.flush()
+    return ops, dict(mode="range", target_file_size=512 << 10, setup_file_size=128 << 10)
+
+
+# scenarios only the CPU oracle is checked on (rules the device path rejects)
+ORACLE_ONLY = dict(grandparent_cuts=grandparent_cuts)
+
 ALL = dict(basic_bottommost=basic_bottommost, nonbottom_tombstones=nonbottom_tombstones, snapshots=snapshots,
            snapshots_nonbottom=snapshots_nonbottom, varlen_keys=varlen_keys, long_keys=long_keys,
            crc32c_small_blocks=crc32c_small_blocks, same_user_key_across_blocks=same_user_key_across_blocks,
