@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200C_ABI_VERSION 3
+#define B200C_ABI_VERSION 4
 #if defined(__GNUC__)
 #define B200C_API __attribute__((visibility("default")))
 #else
@@ -61,6 +61,17 @@ enum b200c_compaction_filter {
                                           445-461): a value whose trailing fixed32 write time + ttl < ttl_now is removed */
 };
 enum b200c_checksum { B200C_CKSUM_NONE = 0, B200C_CKSUM_CRC32C = 1, B200C_CKSUM_XXH3 = 4 }; /* ChecksumType, table.h:54-60 */
+
+/* One file of the level below the output level (Compaction::grandparents(), compaction_executor.h:66-110 `grandparents`): user-key
+ * range and size.  With grandparents the output files are also cut at grandparent boundaries
+ * (CompactionOutputs::ShouldStopBefore, db/compaction/compaction_outputs.cc:294-351). */
+typedef struct b200c_grandparent {
+  const void* smallest_user_key;
+  uint32_t smallest_len;
+  const void* largest_user_key;
+  uint32_t largest_len;
+  uint64_t file_size;
+} b200c_grandparent;
 
 /* Job parameters: the fields of CompactionParams (compaction_executor.h:33-118), of the output
  * BlockBasedTableOptions (include/rocksdb/table.h:237-564) and of TableBuilderOptions
@@ -96,6 +107,11 @@ typedef struct b200c_params {
   uint32_t compaction_filter;      /* enum b200c_compaction_filter */
   int32_t ttl;                     /* B200C_FILTER_TTL: seconds; <= 0 keeps everything */
   int64_t ttl_now;                 /* B200C_FILTER_TTL: clock reading (seconds) the write times are compared with */
+  const b200c_grandparent* grandparents; /* sorted by key, as Compaction::grandparents(); NULL / 0: size rule only */
+  uint32_t num_grandparents;
+  uint32_t level_compaction_dynamic_file_size; /* ImmutableOptions::level_compaction_dynamic_file_size (default 1) */
+  uint64_t max_compaction_bytes;       /* Compaction::max_compaction_bytes(); 0 => 25 x target_output_file_size */
+  uint64_t target_output_file_size;    /* Compaction::target_output_file_size(); 0 => max_output_file_size */
 } b200c_params;
 
 /* FileMinMeta (compaction_executor.h:120-131) + the TableProperties RunRemote re-reads (compaction_job.cc:1043-1061) */

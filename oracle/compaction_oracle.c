@@ -556,6 +556,37 @@ static void merge_next(input* in) {
   merge_publish(in);
 }
 
+/* ClippingIterator (db/compaction/clipping_iterator.h:55-358) as ProcessKeyValueCompaction sets it up for a sub-compaction
+ * (compaction_job.cc:1495-1519): bounds are (user key, kMaxSequenceNumber, kValueTypeForSeek), i.e. start <= user key < end */
+typedef struct clip_in {
+  input* base;
+  const orc_params* p;
+  uint64_t delivered;
+} clip_in;
+static void clip_publish(input* in) {
+  clip_in* c = (clip_in*)in->impl;
+  input* b = c->base;
+  in->valid = b->valid;
+  if (b->valid && c->p->has_range_end && ukey_cmp(b->key, b->klen - 8, c->p->range_end, c->p->range_end_len) >= 0) in->valid = 0;
+  if (!in->valid) return;
+  in->key = b->key;
+  in->klen = b->klen;
+  in->val = b->val;
+  in->vlen = b->vlen;
+  c->delivered++;
+}
+static void clip_next(input* in) {
+  clip_in* c = (clip_in*)in->impl;
+  c->base->next(c->base);
+  clip_publish(in);
+}
+static void clip_seek_to_first(input* in) {
+  clip_in* c = (clip_in*)in->impl;
+  input* b = c->base;
+  while (b->valid && c->p->has_range_start && ukey_cmp(b->key, b->klen - 8, c->p->range_start, c->p->range_start_len) < 0) b->next(b);
+  clip_publish(in);
+}
+
 /* ------------------------------------------------------------------ CompactionIterator
  * db/compaction/compaction_iterator.cc: NextFromInput :475-1087, PrepareOutput :1274-1341,
  * findEarliestVisibleSnapshot :1343-1396, Next :…; restricted to kTypeValue / kTypeDeletion, no snapshot
@@ -1187,8 +1218,14 @@ int orc_compact(const orc_params* p, int n_inputs, const uint8_t* const* inputs,
     in.impl = &m;
     in.next = merge_next;
     merge_publish(&in);
+    const int clipped = p->has_range_start || p->has_range_end;
+    clip_in clip = {&in, p, 0};
+    input cin = {0};
+    cin.impl = &clip;
+    cin.next = clip_next;
+    if (clipped) clip_seek_to_first(&cin);
     citer c;
-    citer_init(&c, &in, p, &r->stats);
+    citer_init(&c, clipped ? &cin : &in, p, &r->stats);
     tbuilder t;
     int have_builder = 0, file_idx = 0;
     uint64_t cur_file_size = 0;
@@ -1231,6 +1268,8 @@ int orc_compact(const orc_params* p, int n_inputs, const uint8_t* const* inputs,
      * (UpdateCompactionInputStatsHelper, compaction_job.cc:2383-2396), not the iterator's own count */
     r->stats.num_input_records = 0;
     for (int i = 0; i < n_inputs; i++) r->stats.num_input_records += m.its[i].yielded;
+    /* a sub-compaction's own count is what its CompactionIterator consumed (compaction_job.cc:1676-1683) */
+    if (clipped) r->stats.num_input_records = clip.delivered;
     if (have_builder) {
       if (!rc) {
         tb_finish(&t);

@@ -68,6 +68,12 @@ typedef struct orc_params {
   uint32_t level_compaction_dynamic_file_size; /* ImmutableOptions (default true) */
   uint64_t max_compaction_bytes;       /* Compaction::max_compaction_bytes() */
   uint64_t target_output_file_size;    /* Compaction::target_output_file_size() (max_output_file_size is twice this with grandparents) */
+  /* sub-compaction key range (SubcompactionState::start / end, compaction_job.cc:1433-1519): the merged input is clipped to
+   * start <= user key < end by a ClippingIterator before CompactionIterator sees it; has_* == 0: unbounded on that side */
+  const uint8_t* range_start;
+  uint32_t range_start_len, has_range_start;
+  const uint8_t* range_end;
+  uint32_t range_end_len, has_range_end;
 } orc_params;
 #define ORC_FILTER_NONE 0
 #define ORC_FILTER_REMOVE_EMPTY_VALUE 1 /* utilities/compaction_filters/remove_emptyvalue_compactionfilter.cc:15-22 */

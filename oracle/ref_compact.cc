@@ -23,6 +23,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -103,6 +104,18 @@ class StatsListener : public EventListener {
   std::string dbdir, outdir;
   CompactionJobInfo job;
   std::vector<SstFileMetaData> outs;
+  // per sub-compaction statistics (CompactionJob::ProcessKeyValueCompaction fills them, compaction_job.cc:1676-1700): which output
+  // files belong to which key range is not reported anywhere else
+  struct Sub {
+    int job_id, sub_id;
+    CompactionJobStats st;
+  };
+  std::vector<Sub> subs;
+  std::mutex subs_mu;
+  void OnSubcompactionCompleted(const SubcompactionJobInfo& si) override {
+    std::lock_guard<std::mutex> g(subs_mu);
+    subs.push_back(Sub{si.job_id, si.subcompaction_job_id, si.stats});
+  }
   void OnCompactionCompleted(DB* db, const CompactionJobInfo& ci) override {
     last = ci;
     completed++;
@@ -530,8 +543,27 @@ int main(int argc, char** argv) {
             fm.num_deletions, Hex(fm.smallestkey).c_str(), Hex(fm.largestkey).c_str(),
             i + 1 < outs.size() ? "," : "");
   }
+  fprintf(m, "  ],\n  \"subcompactions\": [");
+  {
+    std::vector<StatsListener::Sub> subs;
+    for (auto& sb : listener->subs)
+      if (sb.job_id == ji.job_id && sb.sub_id >= 0) subs.push_back(sb);
+    std::sort(subs.begin(), subs.end(), [](const StatsListener::Sub& a, const StatsListener::Sub& b) { return a.sub_id < b.sub_id; });
+    for (size_t i = 0; i < subs.size(); i++) {
+      const CompactionJobStats& ss = subs[i].st;
+      fprintf(m,
+              "%s\n    {\"id\": %d, \"num_input_records\": %" PRIu64 ", \"num_output_records\": %" PRIu64 ", \"num_output_files\": %" PRIu64
+              ", \"num_input_deletion_records\": %" PRIu64 ", \"num_expired_deletion_records\": %" PRIu64
+              ", \"num_records_replaced\": %" PRIu64 ", \"total_input_raw_key_bytes\": %" PRIu64
+              ", \"total_input_raw_value_bytes\": %" PRIu64 "}",
+              i ? "," : "", subs[i].sub_id, ss.num_input_records, ss.num_output_records, (uint64_t)ss.num_output_files,
+              ss.num_input_deletion_records, ss.num_expired_deletion_records, ss.num_records_replaced, ss.total_input_raw_key_bytes,
+              ss.total_input_raw_value_bytes);
+    }
+    fprintf(m, "%s],\n", subs.empty() ? "" : "\n  ");
+  }
   const CompactionJobStats& st = ji.stats;
-  fprintf(m, "  ],\n  \"stats\": {\n");
+  fprintf(m, "  \"stats\": {\n");
   fprintf(m, "    \"wall_micros\": %.0f,\n    \"elapsed_micros\": %" PRIu64 ",\n    \"cpu_micros\": %" PRIu64 ",\n",
           wall_us, st.elapsed_micros, st.cpu_micros);
   fprintf(m, "    \"num_input_records\": %" PRIu64 ",\n    \"num_output_records\": %" PRIu64 ",\n",

@@ -13,7 +13,9 @@ def job_from_params(p, output_mem="host", **extra):
               db_session_id=p.db_session_id, db_host_id=p.db_host_id, creation_time=p.creation_time,
               oldest_key_time=p.oldest_key_time, file_creation_times=list(p.file_creation_times),
               first_file_number=p.first_file_number, output_mem=output_mem, compaction_filter=p.compaction_filter,
-              ttl=p.ttl, ttl_now=p.now)
+              ttl=p.ttl, ttl_now=p.now, grandparents=list(p.grandparents),
+              level_compaction_dynamic_file_size=int(p.level_compaction_dynamic_file_size),
+              max_compaction_bytes=p.max_compaction_bytes, target_output_file_size=p.target_output_file_size)
     kw.update(extra)
     return T.CompactionJob(**kw)
 

@@ -37,6 +37,8 @@ class OrcParams(C.Structure):
         ("grandparents", C.POINTER(OrcGrandparent)), ("num_grandparents", C.c_uint32),
         ("level_compaction_dynamic_file_size", C.c_uint32), ("max_compaction_bytes", C.c_uint64),
         ("target_output_file_size", C.c_uint64),
+        ("range_start", C.c_char_p), ("range_start_len", C.c_uint32), ("has_range_start", C.c_uint32),
+        ("range_end", C.c_char_p), ("range_end_len", C.c_uint32), ("has_range_end", C.c_uint32),
     ]
 
 
@@ -111,6 +113,8 @@ class Params:
         self.level_compaction_dynamic_file_size = True
         self.max_compaction_bytes = 0  # 0: 25 x target
         self.target_output_file_size = 0  # 0: max_output_file_size
+        self.range_start = None  # sub-compaction key range: start <= user key < end (None: unbounded)
+        self.range_end = None
         for k, v in kw.items():
             assert hasattr(self, k), k
             setattr(self, k, v)
@@ -153,6 +157,10 @@ class Params:
         p.level_compaction_dynamic_file_size = int(self.level_compaction_dynamic_file_size)
         tgt = self.target_output_file_size or self.max_output_file_size
         p.target_output_file_size = tgt
+        if self.range_start is not None:
+            p.range_start, p.range_start_len, p.has_range_start = self.range_start, len(self.range_start), 1
+        if self.range_end is not None:
+            p.range_end, p.range_end_len, p.has_range_end = self.range_end, len(self.range_end), 1
         p.max_compaction_bytes = self.max_compaction_bytes or tgt * 25
         return p
 
@@ -326,8 +334,32 @@ def params_from_reference(ref) -> Params:
         p.file_creation_times = [sstfmt.prop_u64(q, "rocksdb.file.creation.time") for q in props]
         p.first_file_number = sstfmt.prop_u64(p0, "rocksdb.original.file.number")
         nums = [sstfmt.prop_u64(q, "rocksdb.original.file.number") for q in props]
-        assert nums == list(range(nums[0], nums[0] + len(nums))), nums
+        # concurrent sub-compactions draw their file numbers from one counter, so only a single-range job numbers consecutively
+        assert len(man.get("subcompactions", [])) > 1 or nums == list(range(nums[0], nums[0] + len(nums))), nums
     return p
+
+
+def subcompaction_ranges(ref):
+    """Key ranges [start, end) of the sub-compactions of a reference run (max_subcompactions > 1).  The reference reports per
+    sub-compaction only statistics (SubcompactionJobInfo); `total_input_raw_key_bytes` of sub-compaction i is the key bytes of the
+    merged input entries its ClippingIterator let through (compaction_job.cc:1495-1519,1676-1700), which pins where in the merged
+    input stream each range ends.  Returns [(start or None, end or None, stats dict)]."""
+    subs = ref["manifest"]["subcompactions"]
+    ents = []
+    for data in ref["inputs"]:
+        ents += [(ik[:-8], -struct.unpack("<Q", ik[-8:])[0], len(ik)) for ik, _ in sstfmt.parse_sst(data)["entries"]]
+    ents.sort()
+    bounds, i, acc = [], 0, 0
+    for sb in subs[:-1]:
+        want = acc + sb["total_input_raw_key_bytes"]
+        while acc < want:
+            acc += ents[i][2]
+            i += 1
+        assert acc == want and ents[i][0] != ents[i - 1][0], "sub-compaction boundary inside a user key"
+        bounds.append(ents[i][0])
+    assert sum(e[2] for e in ents[i:]) == subs[-1]["total_input_raw_key_bytes"]
+    starts, ends = [None] + bounds, bounds + [None]
+    return [(a, b, sb) for a, b, sb in zip(starts, ends, subs)]
 
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")

@@ -1,8 +1,7 @@
 """Grandparent-aware output cutting (CompactionOutputs::ShouldStopBefore, db/compaction/compaction_outputs.cc:231-354:
 max_compaction_bytes overlap, skippable-file and pre-cut rules) restated in the CPU oracle and pinned against the compiled
 reference.  The job is built by the DB's own picker (DB::CompactRange) because DB::CompactFiles never attaches grandparents.
-The device path does not implement these rules yet: the executor plugin keeps jobs with grandparents on the CPU
-(toplingdb_b200/plugin/b200_compaction_executor.cc, Execute), so this file has no GPU counterpart."""
+GPU counterpart: tests/test_gpu_grandparents.py; host-compiled rank rules: tests/test_gp_rules_host.py."""
 import pytest
 
 import helpers as H

@@ -121,6 +121,10 @@ struct b200c_job {
   uint32_t nfiles_out = 0;
   std::vector<uint64_t> run_start_h;
   HostBuf host_out;
+  std::vector<GpKey> gp_small, gp_large;  // grandparent boundaries in column form (packed at job creation)
+  std::vector<uint64_t> gp_size;
+  std::vector<uint8_t> gp_same;
+  DevBuf gp_keys_d, gp_ranks_d, gp_size_d, gp_same_d, gp_cuts_d;
   HostBuf pin_small, pin_tails, pin_rd, pin_up;
   size_t pin_up_used = 0;  // pinned staging: input tails / tail-copy records, output tails
   std::vector<KernelTime> ktimes;
@@ -147,7 +151,7 @@ struct b200c_job {
 namespace {
 
 // layout of the `small` buffer (u64 slots)
-enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotDecTicket = 6, kSlotCounters = 8 /* 7 */, kSmallSlots = 32 };
+enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotDecTicket = 6, kSlotGpCuts = 7, kSlotCounters = 8 /* 8 */, kSmallSlots = 32 };
 
 int map_dev_err(uint32_t e) {
   if (e == 0) return B200C_OK;
@@ -294,7 +298,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
   if (n_out) {
     if (P.index_block_restart_interval != 1)
       return fail(B200C_ERR_NOT_SUPPORTED, "index_block_restart_interval != 1 is not built on the device");
-    EncodeParams ep;
+    EncodeParams ep{};
     ep.block_size = P.block_size;
     ep.block_size_limit = P.block_size_deviation ? (uint32_t)(((uint64_t)P.block_size * (100 - P.block_size_deviation) + 99) / 100) : 0;
     ep.restart_interval = P.block_restart_interval;
@@ -302,6 +306,34 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     ep.format_version = P.format_version;
     ep.output_level = (uint32_t)P.output_level;
     ep.max_output_file_size = P.max_output_file_size;
+    if (!j->gp_small.empty() && P.output_level > 0) {
+      // grandparent boundaries -> ranks in the merged stream; the cut rules themselves run inside the stitch kernel
+      const uint32_t G = (uint32_t)j->gp_small.size();
+      CU(j->gp_keys_d.reserve(sizeof(GpKey) * 2 * G));
+      CU(j->gp_ranks_d.reserve(8 * 3 * (size_t)G));
+      CU(j->gp_size_d.reserve(8 * (size_t)G));
+      CU(j->gp_same_d.reserve(G + 16));
+      CU(j->gp_cuts_d.reserve(sizeof(GpCut) * (2 * (size_t)G + 2)));
+      GpKey* keys = j->gp_keys_d.as<GpKey>();
+      if (int rc = upload_small(j, keys, j->gp_small.data(), sizeof(GpKey) * G)) return rc;
+      if (int rc = upload_small(j, keys + G, j->gp_large.data(), sizeof(GpKey) * G)) return rc;
+      if (int rc = upload_small(j, j->gp_size_d.p, j->gp_size.data(), 8 * (size_t)G)) return rc;
+      if (int rc = upload_small(j, j->gp_same_d.p, j->gp_same.data(), G)) return rc;
+      uint64_t* ranks = j->gp_ranks_d.as<uint64_t>();
+      launch_gp_ranks(mcols, keys, keys + G, G, ranks, ranks + G, ranks + 2 * G, st);
+      launches += 1;
+      ep.gp.n = G;
+      ep.gp.dynamic_file_size = P.level_compaction_dynamic_file_size;
+      ep.gp.lo = ranks;
+      ep.gp.eq = ranks + G;
+      ep.gp.hi = ranks + 2 * G;
+      ep.gp.size = j->gp_size_d.as<uint64_t>();
+      ep.gp.next_same = j->gp_same_d.as<uint8_t>();
+      ep.gp.target_output_file_size = P.target_output_file_size ? P.target_output_file_size : P.max_output_file_size;
+      ep.gp.max_compaction_bytes = P.max_compaction_bytes ? P.max_compaction_bytes : ep.gp.target_output_file_size * 25;
+      ep.gp_cuts = j->gp_cuts_d.as<GpCut>();
+      ep.gp_ncuts = reinterpret_cast<uint32_t*>(small + kSlotGpCuts);
+    }
     uint64_t hop = (uint64_t)(P.block_size - 1) / std::max<uint32_t>(min_s1, 1) + 3;
     if (hop > (uint64_t)kEncHalo) return fail(B200C_ERR_NOT_SUPPORTED, "block_size / smallest entry exceeds the encoder's 2048-entry block window");
     const uint32_t hc = (uint32_t)hop;
@@ -819,6 +851,7 @@ void b200c_params_init(b200c_params* p) {
   p->format_version = 5;
   p->checksum = B200C_CKSUM_XXH3;
   p->verify_input_checksums = 1;
+  p->level_compaction_dynamic_file_size = 1;  // advanced_options.h (default true)
   p->column_family_name = "default";
   p->output_mem = B200C_MEM_HOST;
 }
@@ -850,6 +883,40 @@ int b200c_job_create(const b200c_params* p, b200c_job** out) {
   j->db_host_id = p->db_host_id ? p->db_host_id : "";
   j->p.snapshots = nullptr;
   j->p.file_creation_times = nullptr;
+  // grandparents: user keys packed like the key columns (two big-endian words + length)
+  auto pack = [](const void* key, uint32_t len, GpKey* k) {
+    uint8_t b[16] = {0};
+    memcpy(b, key, len);
+    k->hi = k->lo = 0;
+    for (int i = 0; i < 8; i++) k->hi = (k->hi << 8) | b[i], k->lo = (k->lo << 8) | b[8 + i];
+    k->ulen = len;
+    k->pad = 0;
+  };
+  for (uint32_t i = 0; i < p->num_grandparents; i++) {
+    const b200c_grandparent& g = p->grandparents[i];
+    if (g.smallest_len > kMaxUserKey || g.largest_len > kMaxUserKey || (!g.smallest_user_key && g.smallest_len) ||
+        (!g.largest_user_key && g.largest_len)) {
+      delete j;
+      return fail(B200C_ERR_NOT_SUPPORTED, "grandparent boundary key longer than 16 bytes");
+    }
+    GpKey a, b;
+    pack(g.smallest_user_key, g.smallest_len, &a);
+    pack(g.largest_user_key, g.largest_len, &b);
+    if (i && (j->gp_large[i - 1].hi > a.hi || (j->gp_large[i - 1].hi == a.hi && (j->gp_large[i - 1].lo > a.lo ||
+              (j->gp_large[i - 1].lo == a.lo && j->gp_large[i - 1].ulen > a.ulen))))) {
+      delete j;
+      return fail(B200C_ERR_INVALID_ARGUMENT, "grandparents must be sorted and non-overlapping");
+    }
+    j->gp_small.push_back(a);
+    j->gp_large.push_back(b);
+    j->gp_size.push_back(g.file_size);
+  }
+  for (uint32_t i = 0; i < p->num_grandparents; i++) {
+    const bool same = i + 1 < p->num_grandparents && j->gp_small[i + 1].hi == j->gp_large[i].hi &&
+                      j->gp_small[i + 1].lo == j->gp_large[i].lo && j->gp_small[i + 1].ulen == j->gp_large[i].ulen;
+    j->gp_same.push_back(same ? 1 : 0);
+  }
+  j->p.grandparents = nullptr;
   memset(&j->stats, 0, sizeof j->stats);
   *out = j;
   return B200C_OK;
@@ -914,6 +981,11 @@ void b200c_job_destroy(b200c_job* j) {
                    &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->tstat, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};
   for (DevBuf* b : all) b->release();
+  j->gp_keys_d.release();
+  j->gp_ranks_d.release();
+  j->gp_size_d.release();
+  j->gp_same_d.release();
+  j->gp_cuts_d.release();
   for (auto& in : j->inputs) in.staged.release();
   j->host_out.release();
   j->pin_small.release();

@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "gp_rules.h"
 #include "kernels.h"
 #include "scan.cuh"
 
@@ -468,15 +469,64 @@ __device__ __forceinline__ uint64_t single_entry_block_bytes(const KeyCols& m, c
   uint64_t s0 = (uint64_t)wk.esz[y] + 1u + varint_len32(ks) + sh - varint_len32(sh) - varint_len32(ks - sh);
   return s0 + 4 + 4 + 5;
 }
-// Follow the real chain through one tile whose nxt/disk sit in shared memory, applying the output-file cut rule
-// (compaction_outputs.cc:277: cut in front of the first entry added after the flushed size reached the maximum).
-// emit != nullptr: write BlockRecs.  files != nullptr: write FileRecs.
+// ---- grandparent boundaries on entry ranks: the state machine itself is gp_rules.h (host + device)
+// on-disk bytes (payload + trailer) of a block holding the entries [a, e): what BlockBuilder would have written had the block
+// been flushed there (every restart entry is stored with shared == 0)
+__device__ uint64_t truncated_block_bytes(const KeyCols& m, const EncodeWork& wk, uint32_t R, uint64_t a, uint64_t e) {
+  uint64_t sum = 0;
+  for (uint64_t j0 = a; j0 < e; j0 += 8) {
+    uint32_t s1[8], sh[8], mt[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const uint64_t j = j0 + q;
+      s1[q] = sh[q] = mt[q] = 0;
+      if (j < e) {
+        s1[q] = wk.esz[j];
+        sh[q] = wk.eshared[j];
+        mt[q] = m.meta[j];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const uint64_t j = j0 + q;
+      if (j < e) {
+        sum += s1[q];
+        if ((j - a) % R == 0) {
+          const uint32_t ks = meta_ulen(mt[q]) + 8;
+          sum += 1u + varint_len32(ks) + sh[q] - varint_len32(sh[q]) - varint_len32(ks - sh[q]);
+        }
+      }
+    }
+  }
+  const uint64_t nrest = (e - a + R - 1) / R;
+  return sum + 4 * nrest + 4 + 5;
+}
+
+// Follow the real chain through one tile whose nxt/disk sit in shared memory, applying the output-file cut rules
+// (compaction_outputs.cc:277: cut in front of the first entry added after the flushed size reached the maximum; :294-351 the
+// grandparent rules).  emit != nullptr: write BlockRecs.  files != nullptr: write FileRecs.
+// kGp: 0 = no grandparents; 1 = evaluate the grandparent rules (stitch; records the cuts); 2 = replay recorded cuts (block list).
 // The walk state is copied into registers for the loop (taking its address would put it in local memory and turn every
 // step of this single-thread pointer chase into a chain of dependent local loads and stores).
+template <int kGp>
 __device__ __forceinline__ bool chase_tile(const uint16_t* nxt, const uint32_t* disk, uint64_t tstart, uint32_t tl, uint64_t n,
                                            const EncodeParams& ep, const KeyCols& m, const EncodeWork& wk, WalkState& st_io, FileRec* files,
-                                           BlockRec* emit, uint64_t emit_cap, uint32_t* err) {
+                                           BlockRec* emit, uint64_t emit_cap, uint32_t* err, GpState* gp_io = nullptr) {
   WalkState st = st_io;
+  GpState g{};
+  if (kGp == 1) g = *gp_io;
+  uint32_t ncuts = 0, cut_i = 0;
+  if (kGp == 2) {
+    ncuts = *ep.gp_ncuts;
+    // first recorded cut behind the current position
+    uint32_t lo = 0, hi = ncuts;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (ep.gp_cuts[mid].entry <= st.a) lo = mid + 1;
+      else hi = mid;
+    }
+    cut_i = lo;
+  }
   const uint64_t tend = tstart + tl;
   const bool cut_files = ep.output_level != 0;
   const uint64_t fmax = ep.max_output_file_size;
@@ -489,6 +539,42 @@ __device__ __forceinline__ bool chase_tile(const uint16_t* nxt, const uint32_t* 
       break;
     }
     const uint64_t y = tstart + yr;
+    if (kGp != 0 && cut_files) {
+      // entries a < e <= y are added while the block [a, y) is open: the flushed size they see is st.foff
+      uint64_t cut_at = ~0ull, cut_bytes = 0;
+      if (kGp == 1) {
+        uint64_t ev;
+        while ((ev = gp_next_event(g, ep.gp)) <= y && ev < n) {
+          const uint64_t prev_overlapped = g.overlapped;
+          const uint32_t crossed = gp_advance(g, ep.gp, ev);
+          if (ev > st.f_first_entry && gp_should_stop(g, ep.gp, crossed, prev_overlapped, st.foff)) {
+            cut_at = ev;
+            cut_bytes = ev == y ? (uint64_t)disk[x] : truncated_block_bytes(m, wk, ep.restart_interval, st.a, ev);
+            const uint32_t ci = *ep.gp_ncuts;
+            ep.gp_cuts[ci] = GpCut{cut_at, cut_bytes};
+            *ep.gp_ncuts = ci + 1;
+            break;
+          }
+        }
+      } else if (cut_i < ncuts && ep.gp_cuts[cut_i].entry <= y) {
+        cut_at = ep.gp_cuts[cut_i].entry;
+        cut_bytes = ep.gp_cuts[cut_i].block_bytes;
+        cut_i++;
+      }
+      if (cut_at != ~0ull) {  // the file ends in front of entry cut_at: the open block is flushed with the entries [a, cut_at)
+        if (emit && st.blk < emit_cap) emit[st.blk] = BlockRec{st.a, st.foff, st.f, (uint32_t)(cut_at - st.a)};
+        st.foff += cut_bytes;
+        st.blk++;
+        close_file(files, st, cut_at, err);
+        st.f++;
+        st.foff = 0;
+        st.f_first_entry = cut_at;
+        st.f_first_blk = st.blk;
+        st.a = cut_at;
+        if (kGp == 1) gp_file_started(g, ep.gp, cut_at);
+        continue;
+      }
+    }
     if (emit && st.blk < emit_cap) emit[st.blk] = BlockRec{st.a, st.foff, st.f, (uint32_t)(y - st.a)};
     st.foff += disk[x];
     st.blk++;
@@ -510,11 +596,16 @@ __device__ __forceinline__ bool chase_tile(const uint16_t* nxt, const uint32_t* 
       st.f_first_entry = y + 1;
       st.f_first_blk = st.blk;
       st.a = y + 1;
+      if (kGp == 1 && y + 1 < n) {  // ShouldStopBefore(y + 1) updated the boundary state before the size rule fired
+        gp_advance(g, ep.gp, y + 1);
+        gp_file_started(g, ep.gp, y + 1);
+      }
     } else {
       st.a = y;
     }
   }
   st_io = st;
+  if (kGp == 1) *gp_io = g;
   return ok;
 }
 
@@ -555,6 +646,7 @@ struct StitchSmem {
   uint16_t nxt[kTT];
   uint32_t disk[kTT];
   WalkState st;
+  GpState gp;             // grandparent boundary state of the reference's CompactionOutputs (rules off: untouched)
   uint64_t g, t, tend;    // cursor: next group; next tile / end tile of the group being walked tile by tile
   uint64_t ga, ta;        // first group / tile held by the row caches
   uint32_t gn, tn;        // number of groups / tiles cached
@@ -573,6 +665,11 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
   const uint64_t ngroups = (ntiles + kEncGroup - 1) / kEncGroup;
   if (threadIdx.x == 0) {
     s.st = WalkState{0, 0, 0, 0, 0, 0};
+    s.gp = gp_initial_state();
+    if (ep.gp.n) {
+      *ep.gp_ncuts = 0;
+      if (n) gp_advance(s.gp, ep.gp, 0);  // ShouldStopBefore of the first key: no builder yet, but the boundary state moves
+    }
     s.done = (n == 0);
     s.req = 0;
     s.g = s.t = s.tend = 0;
@@ -584,6 +681,8 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
     if (threadIdx.x == 0) {
       // everything the serial walk touches per step lives in registers; shared memory is read / written once per section
       WalkState st = s.st;
+      const GpState gps = s.gp;  // only read here: boundaries are crossed (and the state changes) inside chase_tile
+      const uint64_t next_ev = ep.gp.n ? gp_next_event(gps, ep.gp) : ~0ull;
       uint64_t cg = s.g, ct = s.t;
       const uint64_t ctend_in = s.tend, cga = s.ga, cta = s.ta;
       uint64_t ctend = ctend_in;
@@ -611,7 +710,8 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
           r.exit = 0xffffffffu;
           if (cc < hc) r = tcache[(t - cta) * hc + cc];
           const bool table_ok = cc < hc && r.exit != 0xffffffffu;
-          const bool cut = !table_ok || (ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size) || tstart + r.exit >= n;
+          const bool cut = !table_ok || (ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size) || tstart + r.exit >= n ||
+                           next_ev <= tstart + r.exit;  // a grandparent boundary is crossed inside: the rules need the block-level state
           if (cut) {  // a file ends in this tile (or the entry point is not tabulated): chase it block by block
             req = 1;
             req_idx = t;
@@ -645,7 +745,8 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
         r.exit = 0xffffffffu;
         if (cc < hc) r = gcache[(gg - cga) * hc + cc];
         const bool table_ok = cc < hc && r.exit != 0xffffffffu;
-        const bool cut = !table_ok || (ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size) || gstart + r.exit >= n;
+        const bool cut = !table_ok || (ep.output_level != 0 && st.foff + r.bytes >= ep.max_output_file_size) || gstart + r.exit >= n ||
+                         next_ev <= gstart + r.exit;
         if (cut) {  // descend: tile by tile
           wk.gflag[gg] = 1;
           ct = t0;
@@ -692,7 +793,11 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
       __syncthreads();
       if (threadIdx.x == 0) {
         WalkState st = s.st;
-        if (!chase_tile(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, wk.files, nullptr, 0, err)) {
+        GpState g = s.gp;
+        const bool chased = ep.gp.n ? chase_tile<1>(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, wk.files, nullptr, 0, err, &g)
+                                    : chase_tile<0>(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, wk.files, nullptr, 0, err);
+        s.gp = g;
+        if (!chased) {
           atomicOr(err, kErrBlockTooLong);
           s.done = 1;
         }
@@ -785,7 +890,18 @@ encode_blocklist_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, u
       x = y;
     }
     if (bad) atomicOr(err, kErrBlockTooLong);
-    s.serial = bad ? 2 : ((ends || (ep.output_level != 0 && ts.file_off + bytes >= ep.max_output_file_size)) ? 1 : 0);
+    bool gp_cut = false;  // a recorded grandparent cut inside this tile's chain (ts.entry, x]
+    if (ep.gp.n && !bad) {
+      const uint32_t nc = *ep.gp_ncuts;
+      uint32_t lo = 0, hi = nc;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (ep.gp_cuts[mid].entry <= ts.entry) lo = mid + 1;
+        else hi = mid;
+      }
+      gp_cut = lo < nc && ep.gp_cuts[lo].entry <= tstart + x;
+    }
+    s.serial = bad ? 2 : ((ends || gp_cut || (ep.output_level != 0 && ts.file_off + bytes >= ep.max_output_file_size)) ? 1 : 0);
     if (s.serial == 1) {  // an output file ends inside this tile: replay the exact serial rule
       WalkState st;
       st.a = ts.entry;
@@ -794,7 +910,9 @@ encode_blocklist_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, u
       st.f = ts.file_idx;
       st.f_first_entry = 0;
       st.f_first_blk = 0;
-      if (!chase_tile(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, nullptr, wk.blocks, nblk_cap, err)) atomicOr(err, kErrBlockTooLong);
+      const bool chased = ep.gp.n ? chase_tile<2>(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, nullptr, wk.blocks, nblk_cap, err)
+                                  : chase_tile<0>(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, nullptr, wk.blocks, nblk_cap, err);
+      if (!chased) atomicOr(err, kErrBlockTooLong);
     }
   }
   __syncthreads();
@@ -1574,6 +1692,31 @@ __global__ void block_checksums_kernel(uint32_t type, const uint8_t* __restrict_
   if ((threadIdx.x & 31) == 0) out[i] = ck;
 }
 
+// ranks of the grandparent boundary keys in the merged stream (one thread per grandparent file)
+__global__ void gp_rank_kernel(KeyCols m, const GpKey* __restrict__ smallest, const GpKey* __restrict__ largest, uint32_t n,
+                               uint64_t* __restrict__ lo, uint64_t* __restrict__ eq, uint64_t* __restrict__ hi) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto bound = [&](const GpKey& k, bool upper) -> uint64_t {  // first entry with user key >= k (upper: > k)
+    uint64_t a = 0, b = m.n;
+    while (a < b) {
+      const uint64_t mid = a + ((b - a) >> 1);
+      const ulonglong2 p = m.pfx[mid];
+      const int c = ukey_cmp(p.x, p.y, meta_ulen(m.meta[mid]), k.hi, k.lo, k.ulen);
+      if (c < 0 || (upper && c == 0)) a = mid + 1;
+      else b = mid;
+    }
+    return a;
+  };
+  lo[i] = bound(smallest[i], false);
+  eq[i] = bound(largest[i], false);
+  hi[i] = bound(largest[i], true);
+}
+void launch_gp_ranks(KeyCols m, const GpKey* smallest, const GpKey* largest, uint32_t n, uint64_t* lo, uint64_t* eq, uint64_t* hi,
+                     cudaStream_t st) {
+  if (n) gp_rank_kernel<<<(n + 63) / 64, 64, 0, st>>>(m, smallest, largest, n, lo, eq, hi);
+}
+
 // file tails (properties | metaindex | footer, built on the host) from their staging buffer into the output images
 __global__ void scatter_tails_kernel(const TailCopy* __restrict__ recs, const uint8_t* __restrict__ staged, uint8_t* __restrict__ out) {
   const TailCopy r = recs[blockIdx.x];
@@ -1611,8 +1754,6 @@ void launch_scatter_tails(const TailCopy* recs, uint32_t n, const uint8_t* stage
 }
 void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, uint64_t n_cap, cudaStream_t st) {
   if (n_cap == 0) return;
-  unsigned g = (unsigned)((n_cap + 255) / 256);
-  (void)g;
   const uint64_t tiles = (n_cap + kEncTile - 1) / kEncTile;
   encode_sizes_kernel<<<(unsigned)(tiles < 148 * 8 ? tiles : 148 * 8), 256, 0, st>>>(m, n_dev, w.esz, w.eshared, w.tstat, w.min_s1);
 }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "common.cuh"
+#include "gp_rules.h"
 
 namespace b200c {
 
@@ -62,11 +63,27 @@ void launch_merge_tiles(KeyCols in, const uint64_t* run_start, MergeParams mp, u
                         MergeCounters* counters, uint32_t* err, cudaStream_t st);
 
 // ---- encode.cu
+// Grandparent-aware output cutting (CompactionOutputs::ShouldStopBefore, compaction_outputs.cc:231-354).  The walk over the block
+// chain only needs to know at which merged ENTRY each boundary of a grandparent file is crossed, so the boundaries are turned
+// into entry ranks once (gp_rank_kernel) and the reference's key-driven state machine runs on ranks.
+struct GpCut {                 // an output file that was cut in front of `entry` by a grandparent rule
+  uint64_t entry;
+  uint64_t block_bytes;        // on-disk bytes of the (truncated) block that ends in front of it
+};
 struct EncodeParams {
   uint32_t block_size, block_size_limit /* ceil(block_size*(100-deviation)/100), 0 = disabled */, restart_interval;
   uint32_t checksum, format_version, output_level;
   uint64_t max_output_file_size;
+  GpCtx gp;
+  GpCut* gp_cuts;              // written by the stitch kernel (capacity 2 * gp.n + 2), replayed by the block-list kernel
+  uint32_t* gp_ncuts;
 };
+struct GpKey {                 // grandparent boundary key in column form
+  uint64_t hi, lo;
+  uint32_t ulen, pad;
+};
+void launch_gp_ranks(KeyCols m, const GpKey* smallest, const GpKey* largest, uint32_t n, uint64_t* lo, uint64_t* eq, uint64_t* hi,
+                     cudaStream_t st);
 struct BlockRec {            // one output data block
   uint64_t first_entry;
   uint64_t file_off;         // offset of the block payload inside its file

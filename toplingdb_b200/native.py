@@ -17,6 +17,11 @@ class B200cError(RuntimeError):
         self.code = code
 
 
+class Grandparent(C.Structure):
+    _fields_ = [("smallest_user_key", C.c_char_p), ("smallest_len", C.c_uint32), ("largest_user_key", C.c_char_p),
+                ("largest_len", C.c_uint32), ("file_size", C.c_uint64)]
+
+
 class Params(C.Structure):
     _fields_ = [
         ("abi_version", C.c_uint32), ("device", C.c_int32), ("output_level", C.c_int32), ("bottommost_level", C.c_int32),
@@ -28,6 +33,9 @@ class Params(C.Structure):
         ("oldest_key_time", C.c_uint64), ("file_creation_times", C.POINTER(C.c_uint64)),
         ("num_file_creation_times", C.c_uint32), ("first_file_number", C.c_uint64), ("output_mem", C.c_uint32),
         ("profile", C.c_uint32), ("compaction_filter", C.c_uint32), ("ttl", C.c_int32), ("ttl_now", C.c_int64),
+        ("grandparents", C.POINTER(Grandparent)), ("num_grandparents", C.c_uint32),
+        ("level_compaction_dynamic_file_size", C.c_uint32), ("max_compaction_bytes", C.c_uint64),
+        ("target_output_file_size", C.c_uint64),
     ]
 
 
@@ -149,6 +157,16 @@ class CompactionJob:
                 p.output_mem = {"host": MEM_HOST, "device": MEM_DEVICE}.get(v, v)
             elif k == "bottommost_level":
                 p.bottommost_level = int(v)
+            elif k == "grandparents":  # [(smallest user key, largest user key, file size)]
+                arr = (Grandparent * max(1, len(v)))()
+                for i, (a, b, sz) in enumerate(v):
+                    arr[i].smallest_user_key, arr[i].smallest_len = a, len(a)
+                    arr[i].largest_user_key, arr[i].largest_len = b, len(b)
+                    arr[i].file_size = sz
+                    self._keep += [a, b]
+                self._keep.append(arr)
+                p.grandparents = C.cast(arr, C.POINTER(Grandparent))
+                p.num_grandparents = len(v)
             elif k == "compaction_filter":
                 p.compaction_filter = {"none": 0, "remove_empty_value": 1, "ttl": 2}.get(v, v)
             else:

@@ -115,8 +115,6 @@ class B200CompactionExecutor : public CompactionExecutor {
     const auto t0 = std::chrono::steady_clock::now();
     const BlockBasedTableOptions* bbt = BlockBasedOptionsOf(c_);
     if (bbt == nullptr) return Fail(r, Status::NotSupported("B200Compact needs a BlockBasedTable output"));
-    if (!c_->grandparents().empty() && p.level_compaction_dynamic_file_size)
-      return Fail(r, Status::NotSupported("B200Compact: grandparent-aware file cutting is not on the device path"));
     b200c_params bp;
     b200c_params_init(&bp);
     bp.device = opt_.device;
@@ -153,6 +151,28 @@ class B200CompactionExecutor : public CompactionExecutor {
     bp.num_file_creation_times = 1;
     bp.first_file_number = 1;  // numbers are local to output_dir; RunRemote renames every file (compaction_job.cc:1019-1033)
     bp.output_mem = B200C_MEM_HOST;
+    // grandparents: CompactionOutputs::ShouldStopBefore cuts output files at their boundaries (compaction_outputs.cc:294-351)
+    std::vector<b200c_grandparent> gps;
+    std::vector<std::string> gp_keys;  // owns the user-key bytes
+    gp_keys.reserve(2 * c_->grandparents().size());
+    for (const FileMetaData* fm : c_->grandparents()) {
+      gp_keys.push_back(fm->smallest.user_key().ToString());
+      gp_keys.push_back(fm->largest.user_key().ToString());
+    }
+    for (size_t i = 0; i < c_->grandparents().size(); i++) {
+      b200c_grandparent g;
+      g.smallest_user_key = gp_keys[2 * i].data();
+      g.smallest_len = (uint32_t)gp_keys[2 * i].size();
+      g.largest_user_key = gp_keys[2 * i + 1].data();
+      g.largest_len = (uint32_t)gp_keys[2 * i + 1].size();
+      g.file_size = c_->grandparents()[i]->fd.GetFileSize();
+      gps.push_back(g);
+    }
+    bp.grandparents = gps.data();
+    bp.num_grandparents = (uint32_t)gps.size();
+    bp.level_compaction_dynamic_file_size = p.level_compaction_dynamic_file_size;
+    bp.max_compaction_bytes = c_->max_compaction_bytes();
+    bp.target_output_file_size = c_->target_output_file_size();
     bp.compaction_filter = DeviceFilterOf(c_, &bp.ttl);
     bp.ttl_now = now;  // TtlCompactionFilter reads the clock per entry; one reading per job here
 
