@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200C_ABI_VERSION 4
+#define B200C_ABI_VERSION 5
 #if defined(__GNUC__)
 #define B200C_API __attribute__((visibility("default")))
 #else
@@ -112,6 +112,21 @@ typedef struct b200c_params {
   uint32_t level_compaction_dynamic_file_size; /* ImmutableOptions::level_compaction_dynamic_file_size (default 1) */
   uint64_t max_compaction_bytes;       /* Compaction::max_compaction_bytes(); 0 => 25 x target_output_file_size */
   uint64_t target_output_file_size;    /* Compaction::target_output_file_size(); 0 => max_output_file_size */
+  /* Sub-compaction key range (SubcompactionState::start / end, db/compaction/subcompaction_state.h; ProcessKeyValueCompaction clips
+   * the merged input with a ClippingIterator, compaction_job.cc:1433-1519, db/compaction/clipping_iterator.h:55-358): only entries
+   * with range_start <= user key < range_end are compacted; the job's statistics count those entries only.  has_* == 0: unbounded
+   * on that side.  Jobs over disjoint ranges of the same inputs are independent (one per GPU / stream). */
+  const void* range_start_user_key;
+  uint32_t range_start_len;
+  uint32_t has_range_start;
+  const void* range_end_user_key;
+  uint32_t range_end_len;
+  uint32_t has_range_end;
+  /* CompactionParams::paranoid_file_checks (compaction_executor.h:71; CompactionJob::Run, compaction_job.cc:829-853, re-reads every
+   * output file and compares an OutputValidator hash of its keys and values with the one taken while writing).  != 0: after the
+   * output images are complete they are decoded again on the device (block checksums verified) and every key and value is compared
+   * with what the encoder was given; a difference fails the job with B200C_ERR_CORRUPTION "Paranoid checksums do not match". */
+  uint32_t paranoid_file_checks;
 } b200c_params;
 
 /* FileMinMeta (compaction_executor.h:120-131) + the TableProperties RunRemote re-reads (compaction_job.cc:1043-1061) */

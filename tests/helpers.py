@@ -341,25 +341,34 @@ def params_from_reference(ref) -> Params:
 
 def subcompaction_ranges(ref):
     """Key ranges [start, end) of the sub-compactions of a reference run (max_subcompactions > 1).  The reference reports per
-    sub-compaction only statistics (SubcompactionJobInfo); `total_input_raw_key_bytes` of sub-compaction i is the key bytes of the
-    merged input entries its ClippingIterator let through (compaction_job.cc:1495-1519,1676-1700), which pins where in the merged
-    input stream each range ends.  Returns [(start or None, end or None, stats dict)]."""
+    sub-compaction only statistics (SubcompactionJobInfo).  `total_input_raw_key_bytes` of sub-compaction i counts the keys its
+    CompactionIterator consumed behind the ClippingIterator (compaction_job.cc:1495-1519,1676-1700) and grows with the range end, so
+    the end of each range is found by bisection over the user keys of the input with the oracle's own accounting; the caller then
+    checks files and the other statistics of every range.  Returns [(start or None, end or None, stats dict)]."""
     subs = ref["manifest"]["subcompactions"]
-    ents = []
-    for data in ref["inputs"]:
-        ents += [(ik[:-8], -struct.unpack("<Q", ik[-8:])[0], len(ik)) for ik, _ in sstfmt.parse_sst(data)["entries"]]
-    ents.sort()
-    bounds, i, acc = [], 0, 0
+    if len(subs) < 2:
+        return [(None, None, sb) for sb in subs]
+    ukeys = sorted({ik[:-8] for data in ref["inputs"] for ik, _ in sstfmt.parse_sst(data)["entries"]})
+    p = params_from_reference(ref)
+    bounds, start = [], None
     for sb in subs[:-1]:
-        want = acc + sb["total_input_raw_key_bytes"]
-        while acc < want:
-            acc += ents[i][2]
-            i += 1
-        assert acc == want and ents[i][0] != ents[i - 1][0], "sub-compaction boundary inside a user key"
-        bounds.append(ents[i][0])
-    assert sum(e[2] for e in ents[i:]) == subs[-1]["total_input_raw_key_bytes"]
-    starts, ends = [None] + bounds, bounds + [None]
-    return [(a, b, sb) for a, b, sb in zip(starts, ends, subs)]
+        want = sb["total_input_raw_key_bytes"]
+
+        def consumed(end):
+            p.range_start, p.range_end = start, end
+            return oracle_compact(p, ref["inputs"])[2].total_input_raw_key_bytes
+
+        lo, hi = 0, len(ukeys) - 1  # smallest end key whose range consumes at least `want`
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if consumed(ukeys[mid]) >= want:
+                hi = mid
+            else:
+                lo = mid + 1
+        assert consumed(ukeys[lo]) == want, "no user-key boundary reproduces the sub-compaction's input"
+        bounds.append(ukeys[lo])
+        start = ukeys[lo]
+    return list(zip([None] + bounds, bounds + [None], subs))
 
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")

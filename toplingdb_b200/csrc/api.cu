@@ -125,6 +125,9 @@ struct b200c_job {
   std::vector<uint64_t> gp_size;
   std::vector<uint8_t> gp_same;
   DevBuf gp_keys_d, gp_ranks_d, gp_size_d, gp_same_d, gp_cuts_d;
+  BoundKey range_lo{}, range_hi{};  // sub-compaction key range in column form (has_range_start / has_range_end in p)
+  DevBuf clip_d;                    // clipped run bounds: begin[k] | end[k]
+  DevBuf vfiles_d, vrun_start;      // paranoid_file_checks: descriptors / run table of the outputs being read back
   HostBuf pin_small, pin_tails, pin_rd, pin_up;
   size_t pin_up_used = 0;  // pinned staging: input tails / tail-copy records, output tails
   std::vector<KernelTime> ktimes;
@@ -151,7 +154,7 @@ struct b200c_job {
 namespace {
 
 // layout of the `small` buffer (u64 slots)
-enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotDecTicket = 6, kSlotGpCuts = 7, kSlotCounters = 8 /* 8 */, kSmallSlots = 32 };
+enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotDecTicket = 6, kSlotGpCuts = 7, kSlotCounters = 8 /* 8 */, kSlotClip = 16 /* 2: entries, value bytes in range */, kSmallSlots = 32 };
 
 int map_dev_err(uint32_t e) {
   if (e == 0) return B200C_OK;
@@ -161,6 +164,7 @@ int map_dev_err(uint32_t e) {
   if (e & kErrChecksum) m += " block-checksum-mismatch";
   if (e & kErrKeyOrder) m += " key-order/partition";
   if (e & kErrCountMismatch) m += " entry-count-mismatch";
+  if (e & kErrParanoid) m += " Paranoid checksums do not match (an output file does not read back as written)";
   const uint32_t unsup = kErrKeyTooLong | kErrValueTooLong | kErrBadType | kErrCompressed | kErrBlockTooLong | kErrIrregularRestarts;
   if (e & unsup) {
     if (!(e & ~(unsup))) code = B200C_ERR_NOT_SUPPORTED;
@@ -483,6 +487,68 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     // the scatter kernel reads records and bytes straight from mapped pinned memory: no copy-engine queue involved
     launch_scatter_tails(reinterpret_cast<const TailCopy*>(j->pin_small.p), nfiles, j->pin_tails.p, j->out_buf.as<uint8_t>(), st);
     launches++;
+    if (P.paranoid_file_checks) {
+      // CompactionParams::paranoid_file_checks (compaction_job.cc:829-853): read every finished output back -- the decoder verifies each
+      // block checksum -- and compare the entries with what the encoder was given.  The input columns of the merge are free by now and
+      // hold the re-read entries.
+      std::vector<FileDesc> ofd(nfiles);
+      uint32_t g = 0, maxb = 0;
+      for (uint32_t f = 0; f < nfiles; f++) {
+        const FileRec& fr = frs[f];
+        FileDesc d;
+        memset(&d, 0, sizeof d);
+        d.base = j->out_buf.as<uint8_t>() + base_off[f];
+        d.len = j->outputs[f].meta.file_size;
+        d.index_off = fr.data_size;
+        d.index_size = (uint32_t)fr.index_size;
+        d.value_delta = P.format_version >= 4;
+        d.cksum = P.checksum;
+        d.gblk_first = g;
+        d.nblocks = (uint32_t)fr.n_blocks;
+        g += d.nblocks;
+        maxb = std::max(maxb, d.nblocks);
+        ofd[f] = d;
+      }
+      if (g != nblocks) return fail(B200C_ERR_CUDA, "internal: block count of the outputs changed");
+      CU(j->vfiles_d.reserve(sizeof(FileDesc) * nfiles));
+      if (int rc = upload_small(j, j->vfiles_d.p, ofd.data(), sizeof(FileDesc) * nfiles)) return rc;
+      CU(cudaStreamSynchronize(st));  // ofd is a temporary
+      CU(j->blk_off.reserve(8 * (nblocks + 1)));
+      CU(j->blk_size.reserve(4 * (nblocks + 1)));
+      CU(j->blk_state.reserve(8 * (nblocks + 1)));
+      CU(j->vrun_start.reserve(8 * ((size_t)nfiles + 1)));
+      CU(j->dec[0].reserve(16 * (n_out + 1)));
+      CU(j->dec[1].reserve(8 * (n_out + 1)));
+      CU(j->dec[2].reserve(8 * (n_out + 1)));
+      CU(j->dec[3].reserve(4 * (n_out + 1)));
+      if (const char* flip = getenv("B200C_TEST_FLIP_OUTPUT_BYTE")) {  // test hook: damage file 0 before it is read back
+        const uint64_t at = strtoull(flip, nullptr, 10);
+        if (at < j->outputs[0].meta.file_size) launch_flip_byte(j->out_buf.as<uint8_t>() + base_off[0] + at, st);
+      }
+      CU(cudaMemsetAsync(small + kSlotDecTicket, 0, 8, st));
+      CU(cudaMemsetAsync(small + kSlotTotalIn, 0, 8, st));
+      CU(cudaMemsetAsync(j->vrun_start.p, 0, 8 * ((size_t)nfiles + 1), st));
+      CU(cudaMemsetAsync(j->blk_state.p, 0, 8 * (nblocks + 1), st));
+      const FileDesc* vf = j->vfiles_d.as<FileDesc>();
+      KeyColsMut re{j->dec[0].as<ulonglong2>(), j->dec[1].as<uint64_t>(), j->dec[2].as<uint64_t>(), j->dec[3].as<uint32_t>()};
+      j->kt_begin("verify.reread");
+      launch_index_decode(vf, (int)nfiles, maxb, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), err, st);
+      launch_block_decode_fused(vf, (int)nfiles, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), (uint32_t)nblocks, 1, n_out, re,
+                                j->blk_state.as<unsigned long long>(), reinterpret_cast<uint32_t*>(small + kSlotDecTicket),
+                                j->vrun_start.as<uint64_t>(), small + kSlotTotalIn, err, j->sms, st);
+      launch_compare_columns(mcols, KeyCols{re.pfx, re.tr, re.vref, re.meta, n_out}, n_out, err, st);
+      j->kt_end();
+      launches += 3;
+      uint64_t hv[kSmallSlots];
+      int rc = read_small(j, small, hv, nullptr, nullptr);
+      if (rc) return rc;
+      if ((uint32_t)hv[kSlotErr]) {  // whatever the reader tripped over, the file is not what was written
+        map_dev_err((uint32_t)hv[kSlotErr]);
+        const std::string detail = g_err;
+        return fail(B200C_ERR_CORRUPTION, "Paranoid checksums do not match: " + detail);
+      }
+      if (hv[kSlotTotalIn] != n_out) return fail(B200C_ERR_CORRUPTION, "Paranoid checksums do not match (entry count of the outputs)");
+    }
   }
   return B200C_OK;
 }
@@ -528,6 +594,9 @@ int finish_run(b200c_job* j, uint64_t launches, uint64_t nblocks, uint32_t nfile
 }
 
 int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta);
+
+int run_merge_encode(b200c_job* j, int until, KeyCols decc, RunBounds runs, uint64_t n_decoded, uint64_t N, bool clipped,
+                     uint64_t range_value_bytes, uint64_t* small, uint32_t* err, uint64_t launches);
 
 int run_job(b200c_job* j, int until) {
   const b200c_params& P = j->p;
@@ -662,6 +731,38 @@ int run_job(b200c_job* j, int until) {
     return B200C_OK;
   }
 
+  // ---------------- sub-compaction key range: clip every run, the merge and everything behind it only see [start, end)
+  RunBounds runs{j->run_start.as<uint64_t>(), j->run_start.as<uint64_t>() + 1};
+  const bool clipped = P.has_range_start || P.has_range_end;
+  const uint64_t n_decoded = N;
+  uint64_t N_in = N, range_value_bytes = 0;
+  if (clipped) {
+    CU(j->clip_d.reserve(16 * (k + 1)));
+    j->kt_begin("merge.clip");
+    launch_clip_runs(decc, j->run_start.as<uint64_t>(), (uint32_t)k, j->range_lo, P.has_range_start, j->range_hi, P.has_range_end,
+                     j->clip_d.as<uint64_t>(), reinterpret_cast<unsigned long long*>(small + kSlotClip), st);
+    j->kt_end();
+    launches++;
+    uint64_t hc[kSmallSlots];
+    int rc = read_small(j, small, hc, nullptr, nullptr);  // sync: the merge grid depends on the number of entries in range
+    if (rc) return rc;
+    rc = map_dev_err((uint32_t)hc[kSlotErr]);
+    if (rc) return rc;
+    N_in = hc[kSlotClip];
+    range_value_bytes = hc[kSlotClip + 1];
+    if (N_in > n_decoded) return fail(B200C_ERR_CUDA, "internal: clipped entry count exceeds the input");
+    runs = RunBounds{j->clip_d.as<uint64_t>(), j->clip_d.as<uint64_t>() + k};
+    j->stats.num_input_records = N_in;
+  }
+  return run_merge_encode(j, until, decc, runs, n_decoded, N_in, clipped, range_value_bytes, small, err, launches);
+}
+
+// merge + encode over the (possibly clipped) runs; N = entries the merge consumes
+int run_merge_encode(b200c_job* j, int until, KeyCols decc, RunBounds runs, uint64_t n_decoded, uint64_t N, bool clipped,
+                     uint64_t range_value_bytes, uint64_t* small, uint32_t* err, uint64_t launches) {
+  const b200c_params& P = j->p;
+  cudaStream_t st = j->st;
+  const size_t k = j->inputs.size();
   // ---------------- merge
   const uint64_t mtiles = (N + kMergeTile - 1) / kMergeTile;
   CU(j->splits.reserve(8 * (mtiles + 1) * k));
@@ -697,10 +798,10 @@ int run_job(b200c_job* j, int until) {
   W.totals = small + kSlotTotals;
   if (N) {
     j->kt_begin("merge.partition");
-    launch_merge_partition(decc, j->run_start.as<uint64_t>(), (uint32_t)k, N, mtiles, j->splits.as<uint64_t>(), err, st);
+    launch_merge_partition(decc, runs, (uint32_t)k, N, mtiles, j->splits.as<uint64_t>(), err, st);
     j->kt_end();
     j->kt_begin("merge.tiles");
-    launch_merge_tiles(decc, j->run_start.as<uint64_t>(), mp, N, mtiles, j->splits.as<uint64_t>(),
+    launch_merge_tiles(decc, runs, mp, N, mtiles, j->splits.as<uint64_t>(),
                        j->tile_state.as<unsigned long long>(), reinterpret_cast<uint32_t*>(small + kSlotTicket), mrg, counters, err, st);
     j->kt_end();
     launches += 2;
@@ -720,7 +821,7 @@ int run_job(b200c_job* j, int until) {
     rc = map_dev_err((uint32_t)h[kSlotErr]);
     if (rc) return rc;
   }
-  if (h[kSlotTotalIn] != N) return fail(B200C_ERR_CORRUPTION, "decoded entry count differs from rocksdb.num.entries");
+  if (h[kSlotTotalIn] != n_decoded) return fail(B200C_ERR_CORRUPTION, "decoded entry count differs from rocksdb.num.entries");
   MergeCounters mc;
   memcpy(&mc, h + kSlotCounters, sizeof mc);
   const uint64_t n_out = mc.n_out;
@@ -735,6 +836,7 @@ int run_job(b200c_job* j, int until) {
   {  // every input value byte (rocksdb.raw.value.size of the inputs) minus the silently skipped entries
     uint64_t all = 0;
     for (auto& in : j->inputs) all += in.tail.raw_value_size;
+    if (clipped) all = range_value_bytes;  // a sub-compaction counts what its clipped iterator consumed
     j->stats.total_input_raw_value_bytes = all - mc.raw_value_bytes;
   }
   if (until == 2) {
@@ -886,7 +988,7 @@ int b200c_job_create(const b200c_params* p, b200c_job** out) {
   // grandparents: user keys packed like the key columns (two big-endian words + length)
   auto pack = [](const void* key, uint32_t len, GpKey* k) {
     uint8_t b[16] = {0};
-    memcpy(b, key, len);
+    if (len) memcpy(b, key, len);
     k->hi = k->lo = 0;
     for (int i = 0; i < 8; i++) k->hi = (k->hi << 8) | b[i], k->lo = (k->lo << 8) | b[8 + i];
     k->ulen = len;
@@ -917,6 +1019,15 @@ int b200c_job_create(const b200c_params* p, b200c_job** out) {
     j->gp_same.push_back(same ? 1 : 0);
   }
   j->p.grandparents = nullptr;
+  // sub-compaction key range
+  if ((p->has_range_start && (p->range_start_len > kMaxUserKey || (!p->range_start_user_key && p->range_start_len))) ||
+      (p->has_range_end && (p->range_end_len > kMaxUserKey || (!p->range_end_user_key && p->range_end_len)))) {
+    delete j;
+    return fail(B200C_ERR_NOT_SUPPORTED, "sub-compaction range bound longer than 16 bytes");
+  }
+  if (p->has_range_start) pack(p->range_start_user_key, p->range_start_len, &j->range_lo);
+  if (p->has_range_end) pack(p->range_end_user_key, p->range_end_len, &j->range_hi);
+  j->p.range_start_user_key = j->p.range_end_user_key = nullptr;
   memset(&j->stats, 0, sizeof j->stats);
   *out = j;
   return B200C_OK;
@@ -986,6 +1097,9 @@ void b200c_job_destroy(b200c_job* j) {
   j->gp_size_d.release();
   j->gp_same_d.release();
   j->gp_cuts_d.release();
+  j->clip_d.release();
+  j->vfiles_d.release();
+  j->vrun_start.release();
   for (auto& in : j->inputs) in.staged.release();
   j->host_out.release();
   j->pin_small.release();

@@ -22,6 +22,7 @@ enum DevErr : uint32_t {
   kErrInternal = 1u << 8,
   kErrCountMismatch = 1u << 9,   // entry count differs from rocksdb.num.entries
   kErrIrregularRestarts = 1u << 10,  // restart intervals of one block hold different numbers of entries
+  kErrParanoid = 1u << 11,       // paranoid_file_checks: an output file does not read back as what was written
 };
 
 constexpr int kMaxUserKey = 16;

@@ -781,4 +781,33 @@ void launch_meta_vlen(const uint32_t* meta, uint64_t n, uint32_t* vlen, cudaStre
   meta_vlen_kernel<<<g > 4096 ? 4096 : g, 256, 0, st>>>(meta, n, vlen);
 }
 
+// ---- paranoid_file_checks (OutputValidator, db/output_validator.cc:31-69 + compaction_job.cc:829-853): the reference hashes every key
+// and value while writing and again while re-reading the finished file; here the re-read columns are compared with the written ones
+// directly (equal sequences have equal rolling hashes, and a difference is found even where two hashes would collide).
+__global__ void compare_columns_kernel(KeyCols a, KeyCols b, uint64_t n, uint32_t* __restrict__ err) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 pa = a.pfx[i], pb = b.pfx[i];
+    const uint32_t ma = a.meta[i];
+    bool bad = pa.x != pb.x || pa.y != pb.y || a.tr[i] != b.tr[i] || ma != b.meta[i];
+    if (!bad) {
+      const uint32_t vlen = meta_vlen(ma);
+      const uint8_t* x = reinterpret_cast<const uint8_t*>((uintptr_t)a.vref[i]);
+      const uint8_t* y = reinterpret_cast<const uint8_t*>((uintptr_t)b.vref[i]);
+      for (uint32_t t = 0; t < vlen; t++)
+        if (x[t] != y[t]) {
+          bad = true;
+          break;
+        }
+    }
+    if (bad) atomicOr(err, (uint32_t)kErrParanoid);
+  }
+}
+__global__ void flip_byte_kernel(uint8_t* p) { *p ^= 0x40; }
+void launch_flip_byte(uint8_t* p, cudaStream_t st) { flip_byte_kernel<<<1, 1, 0, st>>>(p); }
+void launch_compare_columns(KeyCols written, KeyCols reread, uint64_t n, uint32_t* err, cudaStream_t st) {
+  if (n == 0) return;
+  const uint64_t blocks = (n + 255) / 256;
+  compare_columns_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(written, reread, n, err);
+}
+
 }  // namespace b200c

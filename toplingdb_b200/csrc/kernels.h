@@ -26,6 +26,10 @@ void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blo
 void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk,
                                uint32_t verify, uint64_t n_total, KeyColsMut out, unsigned long long* blk_state, uint32_t* ticket,
                                uint64_t* run_start, uint64_t* total_out, uint32_t* err, int sms, cudaStream_t st);
+// paranoid_file_checks: entry i of `written` (what the encoder consumed) and of `reread` (the output images decoded again) must be
+// the same key, the same trailer and the same value bytes; a difference sets kErrParanoid
+void launch_flip_byte(uint8_t* p, cudaStream_t st);  // test hook of paranoid_file_checks
+void launch_compare_columns(KeyCols written, KeyCols reread, uint64_t n, uint32_t* err, cudaStream_t st);
 void launch_gather_values(KeyCols in, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st);
 void launch_meta_vlen(const uint32_t* meta, uint64_t n, uint32_t* vlen, cudaStream_t st);
 
@@ -56,9 +60,24 @@ struct MergeCounters {               // device-side CompactionIterationStats
   unsigned long long n_out, n_input_deletions, n_hidden, n_obsolete, raw_key_bytes, raw_value_bytes, n_silent, n_user_drop;
 };
 // splits: (ntiles + 1) x nruns u64; tile_state: ntiles u64 (zeroed); ticket: u32 (zeroed)
-void launch_merge_partition(KeyCols in, const uint64_t* run_start, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
+// run r of the merge = entries [begin[r], end[r]) of the decoded columns.  Whole input files: end = begin + 1 over the run_start
+// array the decoder fills; a sub-compaction's key range: the clipped bounds from launch_clip_runs.
+struct RunBounds {
+  const uint64_t* begin;
+  const uint64_t* end;
+};
+struct BoundKey {              // a user key in column form (grandparent boundary, sub-compaction range bound)
+  uint64_t hi, lo;
+  uint32_t ulen, pad;
+};
+// Sub-compaction key range (ClippingIterator, db/compaction/clipping_iterator.h:55-358): per run the entries with
+// start <= user key < end.  clip[r] / clip[nruns + r] = first / one-past-last entry of run r in range; totals[0] += entries in
+// range, totals[1] += their value bytes.
+void launch_clip_runs(KeyCols in, const uint64_t* run_start, uint32_t nruns, BoundKey start, uint32_t has_start, BoundKey end,
+                      uint32_t has_end, uint64_t* clip, unsigned long long* totals, cudaStream_t st);
+void launch_merge_partition(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
                             uint64_t* splits, uint32_t* err, cudaStream_t st);
-void launch_merge_tiles(KeyCols in, const uint64_t* run_start, MergeParams mp, uint64_t n_total, uint64_t ntiles,
+void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                         const uint64_t* splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
                         MergeCounters* counters, uint32_t* err, cudaStream_t st);
 
@@ -78,10 +97,7 @@ struct EncodeParams {
   GpCut* gp_cuts;              // written by the stitch kernel (capacity 2 * gp.n + 2), replayed by the block-list kernel
   uint32_t* gp_ncuts;
 };
-struct GpKey {                 // grandparent boundary key in column form
-  uint64_t hi, lo;
-  uint32_t ulen, pad;
-};
+using GpKey = BoundKey;       // grandparent boundary key in column form
 void launch_gp_ranks(KeyCols m, const GpKey* smallest, const GpKey* largest, uint32_t n, uint64_t* lo, uint64_t* eq, uint64_t* hi,
                      cudaStream_t st);
 struct BlockRec {            // one output data block

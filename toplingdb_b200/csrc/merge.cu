@@ -48,7 +48,7 @@ __device__ __forceinline__ uint64_t count_before(const KeyCols& c, uint64_t base
 }
 
 __global__ void __launch_bounds__(128)
-merge_partition_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
+merge_partition_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
                        uint64_t* __restrict__ splits, uint32_t* __restrict__ err) {
   const unsigned lane = threadIdx.x & 31;
   const uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -59,8 +59,8 @@ merge_partition_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint3
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     uint32_t r = lane + 32 * s;
-    base[s] = r < nruns ? run_start[r] : 0;
-    uint64_t n = r < nruns ? run_start[r + 1] - run_start[r] : 0;
+    base[s] = r < nruns ? runs.begin[r] : 0;
+    uint64_t n = r < nruns ? runs.end[r] - runs.begin[r] : 0;
     lo[s] = (d == n_total) ? n : 0;
     hi[s] = (d == 0) ? 0 : n;
   }
@@ -120,7 +120,7 @@ merge_partition_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint3
 // probe g points of its bracket per step (a (g+1)-ary search), which divides the depth of the dependent-load chain --
 // the whole cost of this kernel -- by log2(g + 1).
 __global__ void __launch_bounds__(128)
-merge_partition_grouped_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint32_t nruns, uint32_t gshift, uint64_t n_total,
+merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint32_t gshift, uint64_t n_total,
                                uint64_t ntiles, uint64_t* __restrict__ splits, uint32_t* __restrict__ err) {
   const unsigned lane = threadIdx.x & 31;
   const uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -128,8 +128,8 @@ merge_partition_grouped_kernel(KeyCols in, const uint64_t* __restrict__ run_star
   uint64_t d = b * (uint64_t)kMT;
   if (d > n_total) d = n_total;
   const uint32_t g = 1u << gshift, r = lane >> gshift, sub = lane & (g - 1), gbase = r << gshift;
-  const uint64_t base = r < nruns ? run_start[r] : 0;
-  const uint64_t nrun = r < nruns ? run_start[r + 1] - run_start[r] : 0;
+  const uint64_t base = r < nruns ? runs.begin[r] : 0;
+  const uint64_t nrun = r < nruns ? runs.end[r] - runs.begin[r] : 0;
   uint64_t lo = (d == n_total) ? nrun : 0, hi = (d == 0) ? 0 : nrun;
   for (int guard = 0; guard < 64 * 70; guard++) {
     // widest bracket decides the pivot run
@@ -290,7 +290,7 @@ __device__ __forceinline__ uint64_t stripe_of(const uint64_t* snaps_s, const uin
 
 // slow path helpers for groups that leave the tile (only with snapshots at the bottommost level)
 // oldest version of user key (hi,lo,ulen) over all runs has seq <= limit ?
-__device__ bool oldest_version_at_most(const KeyCols& in, const uint64_t* run_start, uint32_t nruns, uint64_t hi, uint64_t lo,
+__device__ bool oldest_version_at_most(const KeyCols& in, RunBounds runs, uint32_t nruns, uint64_t hi, uint64_t lo,
                                        uint32_t ulen, uint64_t limit) {
   Key x;
   x.hi = hi;
@@ -298,7 +298,7 @@ __device__ bool oldest_version_at_most(const KeyCols& in, const uint64_t* run_st
   x.ulen = ulen;
   x.tr = 0;  // (ukey, seq 0, type 0) sorts after every real version of ukey
   for (uint32_t r = 0; r < nruns; r++) {
-    uint64_t base = run_start[r], n = run_start[r + 1] - base;
+    uint64_t base = runs.begin[r], n = runs.end[r] - base;
     uint64_t c = count_before(in, base, 0, n, x, true);
     if (c == 0) continue;
     Key e = load_key(in, base + c - 1);
@@ -324,7 +324,7 @@ __device__ __forceinline__ bool filter_removes(const MergeParams& mp, const KeyC
 
 // *head_tr carries the type the compaction iterator sees: with the remove-empty-value filter the NEWEST version of a user
 // key is turned into a tombstone when it is a kTypeValue with an empty value (compaction_iterator.cc:579-584, :385-391)
-__device__ bool group_head(const KeyCols& in, const uint64_t* run_start, uint32_t nruns, uint64_t hi, uint64_t lo, uint32_t ulen,
+__device__ bool group_head(const KeyCols& in, RunBounds runs, uint32_t nruns, uint64_t hi, uint64_t lo, uint32_t ulen,
                            uint64_t stripe_hi, const MergeParams& mp, uint64_t* head_tr) {
   Key x;
   x.hi = hi;
@@ -334,7 +334,7 @@ __device__ bool group_head(const KeyCols& in, const uint64_t* run_start, uint32_
   bool found = false, newer_exists = false;
   uint64_t best = 0, best_pos = 0;
   for (uint32_t r = 0; r < nruns; r++) {
-    uint64_t base = run_start[r], n = run_start[r + 1] - base;
+    uint64_t base = runs.begin[r], n = runs.end[r] - base;
     uint64_t c = count_before(in, base, 0, n, x, false);
     if (c > 0) {  // the element in front of the lower bound: a version of the same user key with seq > stripe_hi?
       Key e = load_key(in, base + c - 1);
@@ -355,7 +355,7 @@ __device__ bool group_head(const KeyCols& in, const uint64_t* run_start, uint32_
 }
 
 __global__ void __launch_bounds__(kMThreads, 3)
-merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergeParams mp, uint64_t n_total, uint64_t ntiles,
+merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                    const uint64_t* __restrict__ splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
                    MergeCounters* counters, uint32_t* __restrict__ err, uint32_t prefetch_dist) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -375,7 +375,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   // too, one lane per run, so its DRAM round trip overlaps the split loads
   if (t < k) {
     const uint64_t s0 = splits[tile * k + t], s1 = splits[(tile + 1) * k + t];
-    const uint64_t b0 = run_start[t] + s0;
+    const uint64_t b0 = runs.begin[t] + s0;
     s.sbeg[t] = b0;
     s.lst[1][t] = (uint32_t)(s1 - s0);  // lengths, scanned below
     cand_ok[t] = s0 != 0;
@@ -589,7 +589,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
           uint64_t d2;
           bool pred_same = s.pred.hi == c.hi && s.pred.lo == c.lo && s.pred.ulen == c.ulen &&
                            stripe_of(s.snaps, mp.snapshots, mp.nsnapshots, s.pred.tr >> 8, &d2) == st_c;
-          if (pred_same) have = group_head(in, run_start, k, c.hi, c.lo, c.ulen, st_c, mp, &head_tr);
+          if (pred_same) have = group_head(in, runs, k, c.hi, c.lo, c.ulen, st_c, mp, &head_tr);
         }
         if (have && (head_tr & 0xff) == kTypeDeletion) silent = true;  // head seq > earliest snapshot since its stripe is not the first
       }
@@ -611,7 +611,7 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
           break;
         }
       }
-      if (!resolved) keep = oldest_version_at_most(in, run_start, k, c.hi, c.lo, c.ulen, prev_snap);
+      if (!resolved) keep = oldest_version_at_most(in, runs, k, c.hi, c.lo, c.ulen, prev_snap);
     } else {
       keep = true;
     }
@@ -764,8 +764,57 @@ merge_tiles_kernel(KeyCols in, const uint64_t* __restrict__ run_start, MergePara
   if (t < 8 && s.red[t]) atomicAdd(((unsigned long long*)counters) + t, s.red[t]);
 }
 
+// ------------------------------------------------------------------------------------------------ sub-compaction key range
+// ProcessKeyValueCompaction clips the merged input of a sub-compaction to [start, end) with a ClippingIterator whose bounds are
+// (user key, kMaxSequenceNumber, kValueTypeForSeek) (compaction_job.cc:1495-1519), i.e. start <= user key < end.  Every run is
+// sorted, so the clip is a sub-range per run: two binary searches; the merge then runs over the clipped runs and never sees the
+// rest.  grid = (slices, runs): every CTA repeats its run's two searches (lanes 0 / 1), then the slices add up the value bytes of
+// the run's entries in range (CompactionJobStats::total_input_raw_value_bytes counts what the iterator consumed).
+constexpr int kClipSlices = 64;
+__global__ void __launch_bounds__(256)
+clip_runs_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint32_t nruns, BoundKey start, uint32_t has_start, BoundKey end,
+                 uint32_t has_end, uint64_t* __restrict__ clip, unsigned long long* __restrict__ totals) {
+  __shared__ uint64_t sb[2];
+  const uint32_t r = blockIdx.y;
+  if (threadIdx.x < 2) {
+    const bool is_end = threadIdx.x == 1;
+    const uint64_t a0 = run_start[r], b0 = run_start[r + 1];
+    uint64_t pos = is_end ? b0 : a0;
+    if (is_end ? has_end : has_start) {  // first entry of the run with user key >= bound
+      const BoundKey k = is_end ? end : start;
+      uint64_t a = a0, b = b0;
+      while (a < b) {
+        const uint64_t mid = a + ((b - a) >> 1);
+        const ulonglong2 p = in.pfx[mid];
+        if (ukey_cmp(p.x, p.y, meta_ulen(in.meta[mid]), k.hi, k.lo, k.ulen) < 0) a = mid + 1;
+        else b = mid;
+      }
+      pos = a;
+    }
+    sb[threadIdx.x] = pos;
+  }
+  __syncthreads();
+  const uint64_t b = sb[0];
+  const uint64_t e = sb[1] > b ? sb[1] : b;  // end <= start: empty range
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    clip[r] = b;
+    clip[nruns + r] = e;
+    atomicAdd(&totals[0], (unsigned long long)(e - b));
+  }
+  unsigned long long sum = 0;
+  for (uint64_t i = b + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (uint64_t)gridDim.x * blockDim.x)
+    sum += meta_vlen(in.meta[i]);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&totals[1], sum);
+}
+void launch_clip_runs(KeyCols in, const uint64_t* run_start, uint32_t nruns, BoundKey start, uint32_t has_start, BoundKey end,
+                      uint32_t has_end, uint64_t* clip, unsigned long long* totals, cudaStream_t st) {
+  if (nruns) clip_runs_kernel<<<dim3(kClipSlices, nruns), 256, 0, st>>>(in, run_start, nruns, start, has_start, end, has_end, clip, totals);
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
-void launch_merge_partition(KeyCols in, const uint64_t* run_start, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
+void launch_merge_partition(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
                             uint64_t* splits, uint32_t* err, cudaStream_t st) {
   unsigned warps = (unsigned)(ntiles + 1);
   if (nruns <= 16) {
@@ -773,14 +822,14 @@ void launch_merge_partition(KeyCols in, const uint64_t* run_start, uint32_t nrun
     while (kp2 < nruns) kp2 <<= 1;
     uint32_t gshift = 0;
     while ((kp2 << (gshift + 1)) <= 32) gshift++;  // lanes per run = 32 / pow2(nruns)
-    merge_partition_grouped_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, run_start, nruns, gshift, n_total, ntiles, splits, err);
+    merge_partition_grouped_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, runs, nruns, gshift, n_total, ntiles, splits, err);
     return;
   }
-  merge_partition_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, run_start, nruns, n_total, ntiles, splits, err);
+  merge_partition_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, runs, nruns, n_total, ntiles, splits, err);
 }
 static_assert(sizeof(Key) * kMaxRuns <= sizeof(uint64_t) * kMT && 4 * kMaxRuns <= 2 * kMT, "candidate staging must fit");
 static_assert(3 * (sizeof(TileSmem) + 1024) <= 227 * 1024, "merge tile must fit three CTAs per SM");
-void launch_merge_tiles(KeyCols in, const uint64_t* run_start, MergeParams mp, uint64_t n_total, uint64_t ntiles,
+void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                         const uint64_t* splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
                         MergeCounters* counters, uint32_t* err, cudaStream_t st) {
   if (ntiles == 0) return;
@@ -789,7 +838,7 @@ void launch_merge_tiles(KeyCols in, const uint64_t* run_start, MergeParams mp, u
     cudaFuncSetAttribute(merge_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
     attr_set = true;
   }
-  merge_tiles_kernel<<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, run_start, mp, n_total, ntiles, splits, tile_state,
+  merge_tiles_kernel<<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state,
                                                                           ticket, out, counters, err, 148u * 3u);
 }
 

@@ -36,6 +36,9 @@ class Params(C.Structure):
         ("grandparents", C.POINTER(Grandparent)), ("num_grandparents", C.c_uint32),
         ("level_compaction_dynamic_file_size", C.c_uint32), ("max_compaction_bytes", C.c_uint64),
         ("target_output_file_size", C.c_uint64),
+        ("range_start_user_key", C.c_char_p), ("range_start_len", C.c_uint32), ("has_range_start", C.c_uint32),
+        ("range_end_user_key", C.c_char_p), ("range_end_len", C.c_uint32), ("has_range_end", C.c_uint32),
+        ("paranoid_file_checks", C.c_uint32),
     ]
 
 
@@ -167,6 +170,13 @@ class CompactionJob:
                 self._keep.append(arr)
                 p.grandparents = C.cast(arr, C.POINTER(Grandparent))
                 p.num_grandparents = len(v)
+            elif k in ("range_start", "range_end"):  # sub-compaction key range: start <= user key < end; None = unbounded
+                if v is not None:
+                    v = bytes(v)
+                    self._keep.append(v)
+                    setattr(p, k + "_user_key", v)
+                    setattr(p, k + "_len", len(v))
+                    setattr(p, "has_" + k, 1)
             elif k == "compaction_filter":
                 p.compaction_filter = {"none": 0, "remove_empty_value": 1, "ttl": 2}.get(v, v)
             else:

@@ -128,6 +128,7 @@ class B200CompactionExecutor : public CompactionExecutor {
     bp.format_version = bbt->format_version;
     bp.checksum = (uint32_t)bbt->checksum;
     bp.verify_input_checksums = opt_.verify_input_checksums;
+    bp.paranoid_file_checks = p.paranoid_file_checks;  // RunRemote cannot hash what it did not write (compaction_job.cc:1065-1068)
     std::vector<uint64_t> snaps;
     if (p.existing_snapshots) snaps.assign(p.existing_snapshots->begin(), p.existing_snapshots->end());
     bp.snapshots = snaps.data();

@@ -114,3 +114,16 @@ def job_boundary(job) -> Boundary:
     first, last = job.output_meta(0), job.output_meta(n - 1)
     ents = sum(job.output_meta(i).num_entries for i in range(n))
     return Boundary(bytes(first.smallest_ikey[:first.smallest_ikey_len]), bytes(last.largest_ikey[:last.largest_ikey_len]), n, ents)
+
+
+def subcompaction_ranges(boundaries: Sequence[bytes]) -> List[Tuple[Optional[bytes], Optional[bytes]]]:
+    """n sorted boundary user keys -> the n + 1 key ranges [start, end) of one job's sub-compactions, first and last one
+    unbounded, exactly how CompactionJob::Prepare turns `boundaries_` into SubcompactionStates (compaction_job.cc:264-281).
+    Each range is one `CompactionJob(range_start=..., range_end=...)` over the SAME input files; ranges are independent, so
+    `assign_jobs` spreads them over the ranks and `exchange_boundaries` checks the stitched level afterwards."""
+    bs = list(boundaries)
+    if any(bs[i] >= bs[i + 1] for i in range(len(bs) - 1)):
+        raise ValueError("sub-compaction boundaries must be strictly ascending")
+    starts: List[Optional[bytes]] = [None] + bs
+    ends: List[Optional[bytes]] = bs + [None]
+    return list(zip(starts, ends))
