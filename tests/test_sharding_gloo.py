@@ -51,6 +51,40 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
+def _split_worker(rank, world, port, q):
+    """one job, its sub-compaction ranges spread over the ranks; the CPU oracle stands in for the device (the host logic around it is
+    what runs on every rank of the real thing)"""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+    import sstfmt
+    from toplingdb_b200 import sharding as sh
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = H.load_golden("cfg3_mini")
+        p = H.params_from_reference(g)
+        keys = sorted({ik[:-8] for d in g["inputs"] for ik, _ in sstfmt.parse_sst(d)["entries"]})
+        bounds = [keys[len(keys) * i // 5] for i in range(1, 5)]
+        ranges = sh.subcompaction_ranges(bounds)
+        entries, nfiles, first, last = [], 0, b"", b""
+        for i in sh.ranges_of_rank(len(ranges), world, rank):
+            p.range_start, p.range_end = ranges[i]
+            files, metas, st = H.oracle_compact(p, g["inputs"])
+            for f in files:
+                es = sstfmt.parse_sst(f)["entries"]
+                entries += es
+            nfiles += len(files)
+        if entries:
+            first, last = entries[0][0], entries[-1][0]
+        table = sh.exchange_boundaries(sh.Boundary(first, last, nfiles, len(entries)))
+        q.put((rank, "ok", ([(b.smallest, b.largest, b.n_files, b.n_entries) for b in table], entries)))
+    except ValueError as e:
+        q.put((rank, "err", str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
 def _run(mode, world=2):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -87,6 +121,41 @@ def test_rank_with_no_output_is_skipped():
     res = _run("empty_rank")
     assert [r[1] for r in res] == ["ok", "ok"]
     assert res[0][2][0] == (b"", b"", 0, 0)
+
+
+@pytest.mark.timeout(300)
+def test_one_job_split_into_key_ranges_over_two_ranks():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+    import sstfmt
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_split_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == ["ok", "ok"]
+    assert res[0][2][0] == res[1][2][0]  # same boundary table on both ranks
+    g = H.load_golden("cfg3_mini")
+    whole = [e for f in g["outputs"] for e in sstfmt.parse_sst(f)["entries"]]
+    assert res[0][2][1] + res[1][2][1] == whole  # rank order = key order; nothing lost, nothing twice
+    assert sum(b[3] for b in res[0][2][0]) == len(whole)
+
+
+def test_range_planning_helpers():
+    from toplingdb_b200 import sharding as sh
+    assert sh.subcompaction_ranges([]) == [(None, None)]
+    assert sh.subcompaction_ranges([b"b", b"d"]) == [(None, b"b"), (b"b", b"d"), (b"d", None)]
+    with pytest.raises(ValueError):
+        sh.subcompaction_ranges([b"d", b"b"])
+    for n, w in [(5, 2), (8, 8), (3, 4), (0, 2), (7, 3)]:
+        got = [list(sh.ranges_of_rank(n, w, r)) for r in range(w)]
+        assert [i for g in got for i in g] == list(range(n))
+        assert max(len(g) for g in got) - min(len(g) for g in got) <= 1
 
 
 def test_boundary_record_roundtrip_and_limits():

@@ -127,3 +127,11 @@ def subcompaction_ranges(boundaries: Sequence[bytes]) -> List[Tuple[Optional[byt
     starts: List[Optional[bytes]] = [None] + bs
     ends: List[Optional[bytes]] = bs + [None]
     return list(zip(starts, ends))
+
+
+def ranges_of_rank(n_ranges: int, world: int, rank: int) -> range:
+    """Contiguous block of one job's sub-compaction ranges for `rank`: rank order = key order, which is what `check_disjoint`
+    verifies after the boundary exchange and what lets rank r's output files be installed between those of r - 1 and r + 1."""
+    per, extra = divmod(n_ranges, world)
+    lo = rank * per + min(rank, extra)
+    return range(lo, lo + per + (1 if rank < extra else 0))
