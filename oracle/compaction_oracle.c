@@ -875,7 +875,89 @@ size_t orc_shortest_separator(uint8_t* start, size_t start_len, const uint8_t* l
  * table/block_based/block_based_table_builder.cc: Add :961-1071, Flush/WriteBlock :1073-1133,
  * WriteMaybeCompressedBlock :1277-1378, Finish :1921-1977; flush policy flush_block_policy.cc:37-69;
  * index builder index_builder.h:130-274; properties meta_blocks.cc:54-175; footer format.cc:211-259 */
+/* ------------------------------------------------------------------ full Bloom filter block
+ * Hash64 = XXPH3_64bits (util/hash.cc:81-88; util/xxph3.h is the frozen PREVIEW of XXH3: its short-input paths :1083-1138 and
+ * 17..128-byte path :1640-1677 differ from the final XXH3 used for block checksums); seed 0, default secret (same 192 bytes). */
+static uint64_t xxph_mul_fold(uint64_t a, uint64_t b) {
+  __uint128_t m = (__uint128_t)a * b;
+  return (uint64_t)m ^ (uint64_t)(m >> 64);
+}
+static uint64_t xxph_avalanche(uint64_t h) {
+  h ^= h >> 37;
+  h *= 0x165667B19E3779F9ull;
+  h ^= h >> 32;
+  return h;
+}
+static uint64_t xxph_mix16(const uint8_t* in, const uint8_t* sec) { return xxph_mul_fold(rd64(in) ^ rd64(sec), rd64(in + 8) ^ rd64(sec + 8)); }
+int orc_xxph3_64(const uint8_t* in, size_t len, uint64_t* out) {
+  if (len > 128) return -1; /* longer inputs take the striped long-hash loop: not restated (user keys here are short) */
+  if (len > 16) {
+    uint64_t acc = (uint64_t)len * 0x9E3779B185EBCA87ull;
+    if (len > 32) {
+      if (len > 64) {
+        if (len > 96) {
+          acc += xxph_mix16(in + 48, kSecret + 96);
+          acc += xxph_mix16(in + len - 64, kSecret + 112);
+        }
+        acc += xxph_mix16(in + 32, kSecret + 64);
+        acc += xxph_mix16(in + len - 48, kSecret + 80);
+      }
+      acc += xxph_mix16(in + 16, kSecret + 32);
+      acc += xxph_mix16(in + len - 32, kSecret + 48);
+    }
+    acc += xxph_mix16(in, kSecret);
+    acc += xxph_mix16(in + len - 16, kSecret + 16);
+    *out = xxph_avalanche(acc);
+  } else if (len > 8) {
+    uint64_t lo = rd64(in) ^ rd64(kSecret), hi = rd64(in + len - 8) ^ rd64(kSecret + 8);
+    *out = xxph_avalanche((uint64_t)len + (lo + hi) + xxph_mul_fold(lo, hi));
+  } else if (len >= 4) {
+    uint64_t in64 = (uint64_t)rd32(in) | ((uint64_t)rd32(in + len - 4) << 32);
+    uint64_t keyed = in64 ^ rd64(kSecret);
+    uint64_t mix = (uint64_t)len + ((keyed ^ (keyed >> 51)) * 0x9E3779B1ull);
+    *out = xxph_avalanche((mix ^ (mix >> 47)) * 0xC2B2AE3D27D4EB4Full);
+  } else if (len) {
+    uint32_t comb = (uint32_t)in[0] | ((uint32_t)in[len >> 1] << 8) | ((uint32_t)in[len - 1] << 16) | ((uint32_t)len << 24);
+    *out = xxph_avalanche(((uint64_t)comb ^ (uint64_t)rd32(kSecret)) * 0x9E3779B185EBCA87ull);
+  } else {
+    *out = xxph_mul_fold(rd64(kSecret), 0xC2B2AE3D27D4EB4Full); /* RocksDB's change to the preview: hash of the seed */
+  }
+  return 0;
+}
+/* FastLocalBloomImpl::ChooseNumProbes (util/bloom_impl.h:156-198) */
+static int bloom_num_probes(int mb) {
+  static const int lim[] = {2080, 3580, 5100, 6640, 8300, 10070, 11720, 14001, 16050, 18300, 22001, 25501};
+  for (int i = 0; i < 12; i++)
+    if (mb <= lim[i]) return i + 1;
+  if (mb > 50000) return 24;
+  return (mb - 1) / 2000 - 1;
+}
+/* FastLocalBloomBitsBuilder::Finish / CalculateSpace / AddAllEntries (filter_policy.cc:326-424,462-506) +
+ * FastLocalBloomImpl::AddHash (bloom_impl.h:200-214): filter bytes incl. the 5 metadata bytes; caller frees */
+uint8_t* orc_bloom_build(const uint64_t* hashes, size_t n, uint32_t millibits, size_t* out_len) {
+  uint64_t raw = ((uint64_t)n * millibits + 7999) / 8000;
+  if (raw >= 0xffffffc0ull) raw = 0xffffffc0ull;
+  uint32_t len = (uint32_t)((raw + 63) & ~63ull);
+  uint8_t* d = (uint8_t*)calloc((size_t)len + 5, 1);
+  int probes = bloom_num_probes((int)millibits);
+  for (size_t i = 0; i < n && len; i++) {
+    uint32_t h1 = (uint32_t)hashes[i], h = (uint32_t)(hashes[i] >> 32);
+    uint8_t* line = d + ((size_t)(((uint64_t)h1 * (len >> 6)) >> 32) << 6); /* FastRange32 */
+    for (int k = 0; k < probes; k++, h *= 0x9e3779b9u) {
+      uint32_t bit = h >> (32 - 9);
+      line[bit >> 3] |= (uint8_t)(1u << (bit & 7));
+    }
+  }
+  d[len] = 0xff; /* marker: newer Bloom implementations */
+  d[len + 1] = 0; /* sub-implementation: FastLocalBloom */
+  d[len + 2] = (uint8_t)probes;
+  *out_len = (size_t)len + 5;
+  return d;
+}
+
 typedef struct tbuilder {
+  uint64_t* fhash; /* XXPH3FilterBitsBuilder::hash_entries_ (filter_policy.cc:73-92): consecutive duplicates are dropped */
+  size_t fhash_n, fhash_cap;
   const orc_params* p;
   buf file;
   bbuilder data, idx_seq, idx_noseq;
@@ -887,6 +969,7 @@ typedef struct tbuilder {
   int have_last_handle;
   uint64_t num_entries, num_deletions, raw_key_size, raw_value_size, num_data_blocks, data_size;
   uint64_t file_number, file_creation_time;
+  int filter_err;
 } tbuilder;
 static void tb_write_raw_block(tbuilder* t, const uint8_t* d, size_t n, uint64_t* off, uint64_t* size) {
   *off = t->file.n;
@@ -908,6 +991,7 @@ static void tb_init(tbuilder* t, const orc_params* p, uint64_t file_number, uint
   t->file_creation_time = file_creation_time;
 }
 static void tb_free(tbuilder* t) {
+  free(t->fhash);
   buf_free(&t->file);
   buf_free(&t->last_key);
   bb_free(&t->data);
@@ -958,6 +1042,17 @@ static void tb_add(tbuilder* t, const uint8_t* key, size_t klen, const uint8_t* 
   bb_add(&t->data, key, klen, val, vlen, NULL, 0);
   t->last_key.n = 0;
   buf_put(&t->last_key, key, klen);
+  if (t->p->bloom_millibits_per_key) { /* BlockBasedTableBuilder::Add :1010-1014 -> FullFilterBlockBuilder::Add(user key) */
+    uint64_t h = 0;
+    if (orc_xxph3_64(key, klen - 8, &h)) t->filter_err = 1;
+    if (t->fhash_n == 0 || t->fhash[t->fhash_n - 1] != h) {
+      if (t->fhash_n == t->fhash_cap) {
+        t->fhash_cap = t->fhash_cap ? 2 * t->fhash_cap : 1024;
+        t->fhash = (uint64_t*)realloc(t->fhash, 8 * t->fhash_cap);
+      }
+      t->fhash[t->fhash_n++] = h;
+    }
+  }
   t->num_entries++;
   t->raw_key_size += klen;
   t->raw_value_size += vlen;
@@ -986,6 +1081,14 @@ static void tb_finish(tbuilder* t) {
   tb_flush(t);
   if (!empty) tb_add_index_entry(t, NULL, 0);
   uint64_t tail_start = t->file.n;
+  /* filter block first (Finish :1958 WriteFilterBlock :1488-1538): uncompressed, ordinary trailer */
+  uint64_t foff = 0, fsize = 0, filter_entries = t->fhash_n;
+  if (t->fhash_n) {
+    size_t flen = 0;
+    uint8_t* fd = orc_bloom_build(t->fhash, t->fhash_n, t->p->bloom_millibits_per_key, &flen);
+    tb_write_raw_block(t, fd, flen, &foff, &fsize);
+    free(fd);
+  }
   /* index block (WriteIndexBlock :1540-1603; goes through WriteBlock, uncompressed here) */
   bbuilder* ib = t->sep_is_key_plus_seq ? &t->idx_seq : &t->idx_noseq;
   bb_finish(ib);
@@ -1018,7 +1121,8 @@ static void tb_finish(tbuilder* t) {
   prop_u64(ps, &n, "rocksdb.data.size", t->data_size);
   prop_u64(ps, &n, "rocksdb.deleted.keys", t->num_deletions);
   if (t->file_creation_time > 0) prop_u64(ps, &n, "rocksdb.file.creation.time", t->file_creation_time);
-  prop_u64(ps, &n, "rocksdb.filter.size", 0);
+  if (p->bloom_millibits_per_key) prop_str(ps, &n, "rocksdb.filter.policy", "bloomfilter", 11); /* props.filter_policy_name :1610 */
+  prop_u64(ps, &n, "rocksdb.filter.size", fsize);
   prop_u64(ps, &n, "rocksdb.fixed.key.length", 0);
   prop_u64(ps, &n, "rocksdb.format.version", 0);
   prop_u64(ps, &n, "rocksdb.index.key.is.user.key", !t->sep_is_key_plus_seq);
@@ -1028,7 +1132,7 @@ static void tb_finish(tbuilder* t) {
   prop_str(ps, &n, "rocksdb.merge.operator", "nullptr", 7);
   prop_u64(ps, &n, "rocksdb.num.data.blocks", t->num_data_blocks);
   prop_u64(ps, &n, "rocksdb.num.entries", t->num_entries);
-  prop_u64(ps, &n, "rocksdb.num.filter_entries", 0);
+  prop_u64(ps, &n, "rocksdb.num.filter_entries", filter_entries);
   prop_u64(ps, &n, "rocksdb.num.range-deletions", 0);
   prop_u64(ps, &n, "rocksdb.oldest.key.time", p->oldest_key_time);
   prop_u64(ps, &n, "rocksdb.original.file.number", t->file_number);
@@ -1051,7 +1155,13 @@ static void tb_finish(tbuilder* t) {
   bbuilder mb;
   bb_init(&mb, 1, 0);
   uint8_t h[20];
-  int hn = orc_put_varint64(h, poff);
+  int hn;
+  if (fsize) { /* "fullfilter." + filter_policy->CompatibilityName() :1532-1536; metaindex keys are sorted */
+    hn = orc_put_varint64(h, foff);
+    hn += orc_put_varint64(h + hn, fsize);
+    bb_add(&mb, (const uint8_t*)"fullfilter.rocksdb.BuiltinBloomFilter", 37, h, (size_t)hn, NULL, 0);
+  }
+  hn = orc_put_varint64(h, poff);
   hn += orc_put_varint64(h + hn, psize);
   bb_add(&mb, (const uint8_t*)"rocksdb.properties", 18, h, (size_t)hn, NULL, 0);
   bb_finish(&mb);
@@ -1250,6 +1360,10 @@ int orc_compact(const orc_params* p, int n_inputs, const uint8_t* const* inputs,
         have_builder = 1;
       }
       tb_add(&t, c.current_key.p, c.current_key.n, c.out_val.p, c.out_val.n);
+      if (t.filter_err) {
+        c.err = -8; /* filter key longer than the restated XXPH3 paths */
+        break;
+      }
       r->stats.num_output_records++;
       cur_file_size = t.file.n; /* EstimatedFileSize() == offset, builder :1997-2010 */
       size_t kl = c.current_key.n < 256 ? c.current_key.n : 256;

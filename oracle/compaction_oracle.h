@@ -74,6 +74,10 @@ typedef struct orc_params {
   uint32_t range_start_len, has_range_start;
   const uint8_t* range_end;
   uint32_t range_end_len, has_range_end;
+  /* BlockBasedTableOptions::filter_policy = NewBloomFilterPolicy(bits): BloomLikeFilterPolicy::millibits_per_key_
+   * (table/block_based/filter_policy.cc:1327-1343); 0 = no filter block.  Full filter over whole user keys, format_version >= 5
+   * (FastLocalBloom). */
+  uint32_t bloom_millibits_per_key;
 } orc_params;
 #define ORC_FILTER_NONE 0
 #define ORC_FILTER_REMOVE_EMPTY_VALUE 1 /* utilities/compaction_filters/remove_emptyvalue_compactionfilter.cc:15-22 */

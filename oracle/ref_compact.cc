@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "rocksdb/db.h"
+#include "rocksdb/filter_policy.h"
 #include "rocksdb/listener.h"
 #include "rocksdb/options.h"
 #include "rocksdb/table.h"
@@ -56,6 +57,7 @@ struct Opts {
   uint32_t format_version = 5;
   int keep_db = 0;
   int paranoid = 0;
+  double bloom_bits = 0;  // > 0: BlockBasedTableOptions::filter_policy = NewBloomFilterPolicy(bloom_bits) (full filter, whole keys)
   int copy = 1;  // 0: leave inputs/ and outputs/ empty (timing runs only need the manifest)
   uint64_t setup_file_size = UINT64_MAX;  // output file size limit of the set-up compactions (op 5): several files below the job
   std::string mode = "files";  // range: run the job through DB::CompactRange, the way the DB's own picker builds it -- the
@@ -201,6 +203,7 @@ int main(int argc, char** argv) {
     else if (k == "format_version") o.format_version = (uint32_t)atoi(v.c_str());
     else if (k == "keep_db") o.keep_db = atoi(v.c_str());
     else if (k == "paranoid") o.paranoid = atoi(v.c_str());
+    else if (k == "bloom_bits") o.bloom_bits = atof(v.c_str());
     else if (k == "executor") o.executor = v;
     else if (k == "copy") o.copy = atoi(v.c_str());
     else if (k == "filter") o.filter = v;
@@ -246,6 +249,7 @@ int main(int argc, char** argv) {
   t.format_version = o.format_version;
   t.checksum = o.checksum == "crc32c" ? kCRC32c : kXXH3;
   t.no_block_cache = true;
+  if (o.bloom_bits > 0) t.filter_policy.reset(NewBloomFilterPolicy(o.bloom_bits, false));
   opt.table_factory.reset(NewBlockBasedTableFactory(t));
   if (o.filter == "remove_empty_value") opt.compaction_filter_factory = std::make_shared<RemoveEmptyValueFactory>();
   else if (o.filter != "none") {
@@ -465,6 +469,8 @@ int main(int argc, char** argv) {
           o.block_size, o.restart_interval, o.format_version);
   fprintf(m, "  \"checksum\": \"%s\",\n  \"max_subcompactions\": %u,\n", o.checksum.c_str(),
           o.max_subcompactions);
+  // BloomFilterPolicy keeps bits_per_key as millibits (filter_policy.cc: round(bits_per_key * 1000), at least 1000)
+  fprintf(m, "  \"bloom_millibits_per_key\": %d,\n", o.bloom_bits > 0 ? std::max(1000, (int)(o.bloom_bits * 1000.0 + 0.500001)) : 0);
   fprintf(m, "  \"bottommost_level\": %s,\n", deeper_files ? "false" : "true");
   {
     // Compaction::max_output_file_size_ (compaction.cc:289-295): twice the target when the job has grandparents

@@ -39,6 +39,7 @@ class OrcParams(C.Structure):
         ("target_output_file_size", C.c_uint64),
         ("range_start", C.c_char_p), ("range_start_len", C.c_uint32), ("has_range_start", C.c_uint32),
         ("range_end", C.c_char_p), ("range_end_len", C.c_uint32), ("has_range_end", C.c_uint32),
+        ("bloom_millibits_per_key", C.c_uint32),
     ]
 
 
@@ -115,6 +116,7 @@ class Params:
         self.target_output_file_size = 0  # 0: max_output_file_size
         self.range_start = None  # sub-compaction key range: start <= user key < end (None: unbounded)
         self.range_end = None
+        self.bloom_millibits_per_key = 0  # NewBloomFilterPolicy(bits) * 1000; 0 = no filter block
         for k, v in kw.items():
             assert hasattr(self, k), k
             setattr(self, k, v)
@@ -157,6 +159,7 @@ class Params:
         p.level_compaction_dynamic_file_size = int(self.level_compaction_dynamic_file_size)
         tgt = self.target_output_file_size or self.max_output_file_size
         p.target_output_file_size = tgt
+        p.bloom_millibits_per_key = self.bloom_millibits_per_key
         if self.range_start is not None:
             p.range_start, p.range_start_len, p.has_range_start = self.range_start, len(self.range_start), 1
         if self.range_end is not None:
@@ -320,7 +323,8 @@ def params_from_reference(ref) -> Params:
                checksum=man["checksum"], snapshots=man["snapshots"], compaction_filter=man.get("compaction_filter", "none"), ttl=man.get("ttl", 0), now=man.get("now", 0),
                grandparents=[(bytes.fromhex(g["smallestkey"]), bytes.fromhex(g["largestkey"]), g["size"]) for g in man.get("grandparents", [])],
                level_compaction_dynamic_file_size=man.get("level_compaction_dynamic_file_size", True),
-               max_compaction_bytes=man.get("max_compaction_bytes", 0), target_output_file_size=man.get("target_output_file_size", 0))
+               max_compaction_bytes=man.get("max_compaction_bytes", 0), target_output_file_size=man.get("target_output_file_size", 0),
+               bloom_millibits_per_key=man.get("bloom_millibits_per_key", 0))
     if ref["outputs"]:
         props = [sstfmt.parse_sst(o)["properties"] for o in ref["outputs"]]
         p0 = props[0]
