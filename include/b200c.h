@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200C_ABI_VERSION 5
+#define B200C_ABI_VERSION 6
 #if defined(__GNUC__)
 #define B200C_API __attribute__((visibility("default")))
 #else
@@ -127,6 +127,13 @@ typedef struct b200c_params {
    * output images are complete they are decoded again on the device (block checksums verified) and every key and value is compared
    * with what the encoder was given; a difference fails the job with B200C_ERR_CORRUPTION "Paranoid checksums do not match". */
   uint32_t paranoid_file_checks;
+  /* BlockBasedTableOptions::filter_policy = NewBloomFilterPolicy(bits_per_key): BloomLikeFilterPolicy::millibits_per_key_
+   * (= int(bits_per_key * 1000 + 0.500001), table/block_based/filter_policy.cc:1327-1343).  != 0: every output file gets a full
+   * (non-partitioned) FastLocalBloom filter block over its whole user keys, between the data blocks and the index block
+   * (BlockBasedTableBuilder::WriteFilterBlock, block_based_table_builder.cc:1488-1538), the metaindex entry
+   * "fullfilter.rocksdb.BuiltinBloomFilter" and the filter properties.  Needs format_version >= 5 (older versions build the legacy
+   * Bloom filter), whole_key_filtering, no prefix extractor, optimize_filters_for_memory = false (the defaults). */
+  uint32_t bloom_millibits_per_key;
 } b200c_params;
 
 /* FileMinMeta (compaction_executor.h:120-131) + the TableProperties RunRemote re-reads (compaction_job.cc:1043-1061) */

@@ -508,13 +508,23 @@ int main(int argc, char** argv) {
       for (size_t i = 0; i < x.size(); i++) h = (h ^ (unsigned char)x[i]) * 1099511628211ull;
       h = (h ^ x.size()) * 1099511628211ull;
     };
+    // with a filter policy: every key the scan shows is also looked up with Get(), which consults the files' Bloom filters first -- a
+    // filter with a missing bit turns into NotFound here (the reference counts useful / positive filter probes in its tickers)
+    uint64_t get_found = 0, get_missing = 0;
+    std::string got;
     for (it->SeekToFirst(); it->Valid(); it->Next()) {
       mix(it->key());
       mix(it->value());
       n++;
+      if (o.bloom_bits > 0) {
+        Status gs = db->Get(ro, it->key(), &got);
+        if (gs.ok() && Slice(got) == it->value()) get_found++;
+        else get_missing++;
+      }
     }
     if (!it->status().ok()) Die("scan after compaction", it->status());
     fprintf(m, "  \"scan_count\": %" PRIu64 ",\n  \"scan_digest\": \"%016" PRIx64 "\",\n", n, h);
+    fprintf(m, "  \"get_found\": %" PRIu64 ",\n  \"get_missing\": %" PRIu64 ",\n", get_found, get_missing);
   }
   fprintf(m, "  \"db_id\": \"%s\",\n  \"db_session_id\": \"%s\",\n", db_id.c_str(), session_id.c_str());
   fprintf(m, "  \"snapshots\": [");

@@ -16,7 +16,7 @@ def job_from_params(p, output_mem="host", **extra):
               ttl=p.ttl, ttl_now=p.now, grandparents=list(p.grandparents),
               level_compaction_dynamic_file_size=int(p.level_compaction_dynamic_file_size),
               max_compaction_bytes=p.max_compaction_bytes, target_output_file_size=p.target_output_file_size,
-              range_start=p.range_start, range_end=p.range_end)
+              range_start=p.range_start, range_end=p.range_end, bloom_millibits_per_key=p.bloom_millibits_per_key)
     kw.update(extra)
     return T.CompactionJob(**kw)
 

@@ -367,6 +367,12 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     launch_encode_stitch(mcols, ep, W, etiles, hc, err, st, &launches);
     j->kt_end();
     launches += 1;
+    if (P.bloom_millibits_per_key) {  // filter entries per file decide where each file's index block starts
+      j->kt_begin("encode.bloom_count");
+      launch_bloom_count(mcols, n_out, W.files, small + kSlotTotals + 1, P.bloom_millibits_per_key, st);
+      j->kt_end();
+      launches += 2;
+    }
     {
       int rc = read_small(j, small, h, W.files, &frs);  // sync #2: number of blocks / files, per-file records
       if (rc) return rc;
@@ -389,7 +395,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     uint64_t off = 0;
     for (uint32_t f = 0; f < nfiles; f++) {
       base_off[f] = off;
-      uint64_t cap = frs[f].data_size + frs[f].n_blocks * 48 + 64 + 4096;
+      uint64_t cap = frs[f].data_size + frs[f].filter_bytes + frs[f].n_blocks * 48 + 64 + 4096;
       off += (cap + 255) & ~255ull;
     }
     base_off[nfiles] = off;
@@ -419,6 +425,14 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     launch_encode_emit(mcols, ep, W, nblocks, out_base_d, err, j->sms, st);
     j->kt_end();
     launches += 3;
+    if (P.bloom_millibits_per_key) {
+      j->kt_begin("encode.bloom_build");
+      for (uint32_t f = 0; f < nfiles; f++)
+        if (frs[f].filter_bytes) CU(cudaMemsetAsync(bases[f] + frs[f].data_size, 0, frs[f].filter_bytes, st));
+      launch_bloom_build(mcols, n_out, W.files, nfiles, P.bloom_millibits_per_key, P.checksum, out_base_d, st);
+      j->kt_end();
+      launches += 2;
+    }
     j->kt_begin("encode.index");
     launch_encode_index(mcols, ep, W, nblocks, nfiles, out_base_d, err, st, &launches);
     j->kt_end();
@@ -440,6 +454,8 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       ti.format_version = P.format_version;
       ti.data_size = fr.data_size;
       ti.index_size = fr.index_size;
+      ti.filter_size = fr.filter_bytes ? fr.filter_bytes - 5 : 0;
+      ti.filter_entries = fr.filter_entries;
       ti.num_entries = fr.n_entries;
       ti.num_deletions = fr.num_deletions;
       ti.raw_key_size = fr.raw_key_size;
@@ -456,7 +472,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       ti.file_creation_time = j->fct.empty() ? 0 : j->fct[std::min<size_t>(f, j->fct.size() - 1)];
       ti.orig_file_number = P.first_file_number + f;
       std::vector<uint8_t> tail = build_output_tail(ti);
-      const uint64_t tail_off = fr.data_size + fr.index_size + 5;
+      const uint64_t tail_off = fr.data_size + fr.filter_bytes + fr.index_size + 5;
       if (tail_off + tail.size() > base_off[f + 1] - base_off[f]) return fail(B200C_ERR_CUDA, "internal: output image overflow");
       const size_t so = (size_t)f * 4096;
       if (tail.size() > 4096) return fail(B200C_ERR_CUDA, "internal: tail larger than its staging slot");
@@ -499,7 +515,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
         memset(&d, 0, sizeof d);
         d.base = j->out_buf.as<uint8_t>() + base_off[f];
         d.len = j->outputs[f].meta.file_size;
-        d.index_off = fr.data_size;
+        d.index_off = fr.data_size + fr.filter_bytes;
         d.index_size = (uint32_t)fr.index_size;
         d.value_delta = P.format_version >= 4;
         d.cksum = P.checksum;
@@ -1019,6 +1035,10 @@ int b200c_job_create(const b200c_params* p, b200c_job** out) {
     j->gp_same.push_back(same ? 1 : 0);
   }
   j->p.grandparents = nullptr;
+  if (p->bloom_millibits_per_key && (p->format_version < 5 || p->bloom_millibits_per_key < 1000)) {
+    delete j;
+    return fail(B200C_ERR_NOT_SUPPORTED, "Bloom filter block needs format_version >= 5 (FastLocalBloom) and >= 1000 millibits per key");
+  }
   // sub-compaction key range
   if ((p->has_range_start && (p->range_start_len > kMaxUserKey || (!p->range_start_user_key && p->range_start_len))) ||
       (p->has_range_end && (p->range_end_len > kMaxUserKey || (!p->range_end_user_key && p->range_end_len)))) {

@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "bloom_rules.h"
 #include "gp_rules.h"
 #include "kernels.h"
 #include "scan.cuh"
@@ -462,6 +463,7 @@ __device__ __forceinline__ void close_file(FileRec* files, WalkState& st, uint64
   fr.largest_seq = 0;
   fr.index_has_seq = 0;
   fr.index_cksum = 0;
+  fr.filter_entries = fr.filter_bytes = 0;
 }
 // on-disk bytes of a data block that holds the single entry y
 __device__ __forceinline__ uint64_t single_entry_block_bytes(const KeyCols& m, const EncodeWork& wk, uint64_t y) {
@@ -1615,7 +1617,7 @@ __global__ void encode_index_write_kernel(EncodeWork wk, uint64_t nblocks, uint3
     const uint64_t eoff = wk.idx_eoff[b] - wk.idx_eoff[fr.first_block];
     const uint64_t entries_bytes =
         wk.idx_eoff[fr.first_block + fr.n_blocks - 1] + wk.idx_esz[fr.first_block + fr.n_blocks - 1] - wk.idx_eoff[fr.first_block];
-    uint8_t* ib = out_base[br.file_idx] + fr.data_size;  // index block follows the last data block
+    uint8_t* ib = out_base[br.file_idx] + fr.data_size + fr.filter_bytes;  // index block follows the last data block
     uint8_t* p = ib + eoff;
     uint8_t h[20];
     uint32_t hn = (uint32_t)put_varint(h, br.file_off);
@@ -1652,7 +1654,7 @@ __global__ void encode_index_contrib_kernel(EncodeWork wk, uint32_t nfiles, uint
   if (f >= nfiles) return;
   const FileRec fr = wk.files[f];
   if (fr.n_blocks == 0 || fr.index_size <= 240) return;
-  const uint8_t* ib = out_base[f] + fr.data_size;
+  const uint8_t* ib = out_base[f] + fr.data_size + fr.filter_bytes;
   const uint64_t nb_blocks = (fr.index_size - 1) / 1024;
   const unsigned lane = threadIdx.x & 31;
   const XxhLaneSecret ks = xxh_lane_secret();
@@ -1668,7 +1670,7 @@ __global__ void encode_index_cksum_kernel(EncodeWork wk, uint32_t nfiles, uint32
   if (f >= nfiles) return;
   const FileRec fr = wk.files[f];
   if (fr.n_blocks == 0) return;
-  uint8_t* ib = out_base[f] + fr.data_size;
+  uint8_t* ib = out_base[f] + fr.data_size + fr.filter_bytes;
   uint32_t ck;
   if (cksum == 4) ck = (uint32_t)xxh3_64_warp_t<false>(ib, fr.index_size, contrib + contrib_off[f] * 8);  // last byte (type 0) adds nothing
   else ck = block_checksum_warp(cksum, ib, fr.index_size, 0);
@@ -1690,6 +1692,127 @@ __global__ void block_checksums_kernel(uint32_t type, const uint8_t* __restrict_
   if (i >= n) return;
   uint32_t ck = block_checksum_warp(type, data + offsets[i], offsets[i + 1] - offsets[i], last_byte);
   if ((threadIdx.x & 31) == 0) out[i] = ck;
+}
+
+// ------------------------------------------------------------------------------------------------ Bloom filter block
+// One FastLocalBloom filter per output file over the XXPH3 hashes of its user keys (bloom_rules.h).  The hash is recomputed from the
+// key columns wherever it is needed (a few integer ops) instead of being stored: 8 B per entry of extra traffic would cost more.
+__device__ __forceinline__ uint64_t entry_key_hash(const KeyCols& m, uint64_t e) {
+  const ulonglong2 p = m.pfx[e];
+  return xxph3_of_key(p.x, p.y, meta_ulen(m.meta[e]));
+}
+__device__ __forceinline__ uint32_t file_of_entry(const FileRec* __restrict__ files, uint32_t nfiles, uint64_t e) {
+  uint32_t lo = 0, hi = nfiles;  // last file with first_entry <= e
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (files[mid].first_entry <= e) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+// does entry e add a hash to the filter of its file?  (XXPH3FilterBitsBuilder::AddKey, filter_policy.cc:73-92: not if the previous
+// key ADDED TO THIS FILTER hashed the same; every entry of a file is offered to it, so that is the previous entry of the file)
+__device__ __forceinline__ bool entry_adds_hash(const KeyCols& m, uint64_t e, uint64_t file_first, uint64_t* h_out) {
+  const uint64_t h = entry_key_hash(m, e);
+  *h_out = h;
+  return e == file_first || entry_key_hash(m, e - 1) != h;
+}
+__global__ void __launch_bounds__(256)
+bloom_count_kernel(KeyCols m, uint64_t n, FileRec* __restrict__ files, const uint64_t* __restrict__ nfiles_dev) {
+  const uint32_t nfiles = (uint32_t)*nfiles_dev;
+  if (nfiles == 0 || nfiles > kMaxOutFiles) return;
+  const unsigned lane = threadIdx.x & 31;
+  for (uint64_t e0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; e0 < n; e0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t e = e0 + lane;
+    uint32_t f = 0xffffffffu;
+    bool add = false;
+    if (e < n) {
+      f = file_of_entry(files, nfiles, e);
+      uint64_t h;
+      add = entry_adds_hash(m, e, files[f].first_entry, &h);
+    }
+    // a warp's 32 consecutive entries almost always belong to one file: one atomic per warp then
+    const uint32_t f0 = __shfl_sync(0xffffffffu, f, 0);
+    const bool uniform = __all_sync(0xffffffffu, f == f0 || f == 0xffffffffu);
+    if (uniform) {
+      const unsigned cnt = __popc(__ballot_sync(0xffffffffu, add));
+      if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&files[f0].filter_entries), (unsigned long long)cnt);
+    } else if (add) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&files[f].filter_entries), 1ull);
+    }
+  }
+}
+__global__ void bloom_layout_kernel(FileRec* __restrict__ files, const uint64_t* __restrict__ nfiles_dev, uint32_t millibits) {
+  const uint32_t nfiles = (uint32_t)*nfiles_dev;
+  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nfiles && f < kMaxOutFiles; f += gridDim.x * blockDim.x) {
+    const uint64_t cnt = files[f].filter_entries;
+    files[f].filter_bytes = cnt ? (uint64_t)bloom_bits_bytes(cnt, millibits) + kBloomMetadataLen + 5 : 0;
+  }
+}
+void launch_bloom_count(KeyCols m, uint64_t n, FileRec* files, const uint64_t* nfiles_dev, uint32_t millibits, cudaStream_t st) {
+  if (n == 0) return;
+  const uint64_t blocks = (n + 255) / 256;
+  bloom_count_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(m, n, files, nfiles_dev);
+  bloom_layout_kernel<<<(kMaxOutFiles + 255) / 256, 256, 0, st>>>(files, nfiles_dev, millibits);
+}
+// the filter bytes were zeroed by the host (cudaMemsetAsync per file); bits are OR-ed in through the aligned 32-bit word that holds
+// the byte (the block starts wherever the data blocks ended, so its bytes are not word aligned; OR-ing zeros into the neighbouring
+// bytes of a word leaves them as they are)
+__global__ void __launch_bounds__(256)
+bloom_bits_kernel(KeyCols m, uint64_t n, const FileRec* __restrict__ files, uint32_t nfiles, int probes, uint8_t* const* __restrict__ out_base) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t f = file_of_entry(files, nfiles, e);
+    const FileRec& fr = files[f];
+    uint64_t h;
+    if (!entry_adds_hash(m, e, fr.first_entry, &h)) continue;
+    if (fr.filter_bytes <= kBloomMetadataLen + 5) continue;  // zero-length bit array (cannot happen with >= 1 entry)
+    const uint32_t bits_bytes = (uint32_t)(fr.filter_bytes - kBloomMetadataLen - 5);
+    uint8_t* line = out_base[f] + fr.data_size + bloom_line_offset(h, bits_bytes);
+    uint32_t p = bloom_first_probe(h);
+    for (int k = 0; k < probes; k++, p = bloom_next_probe(p)) {
+      const uint32_t bit = bloom_probe_bit(p);
+      const uintptr_t addr = (uintptr_t)(line + (bit >> 3));
+      atomicOr(reinterpret_cast<unsigned int*>(addr & ~(uintptr_t)3), 1u << (8 * (uint32_t)(addr & 3) + (bit & 7)));
+    }
+  }
+}
+// one warp per file: metadata bytes, then the block trailer (WriteMaybeCompressedBlock: type kNoCompression + checksum)
+__global__ void bloom_finish_kernel(const FileRec* __restrict__ files, uint32_t nfiles, int probes, uint32_t cksum,
+                                    uint8_t* const* __restrict__ out_base) {
+  const uint32_t f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= nfiles) return;
+  const FileRec fr = files[f];
+  if (fr.filter_bytes == 0) return;
+  uint8_t* fb = out_base[f] + fr.data_size;
+  const uint64_t content = fr.filter_bytes - 5;  // bits + metadata
+  if ((threadIdx.x & 31) == 0) {
+    uint8_t* md = fb + content - kBloomMetadataLen;
+    md[0] = 0xff;  // marker: newer Bloom implementations (filter_policy.cc:378-385)
+    md[1] = 0;     // sub-implementation: FastLocalBloom
+    md[2] = (uint8_t)probes;
+    md[3] = 0;
+    md[4] = 0;
+  }
+  __threadfence();
+  __syncwarp();
+  const uint32_t ck = block_checksum_warp(cksum, fb, content, 0);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    uint8_t* tp = fb + content;
+    tp[0] = 0;
+    tp[1] = (uint8_t)ck;
+    tp[2] = (uint8_t)(ck >> 8);
+    tp[3] = (uint8_t)(ck >> 16);
+    tp[4] = (uint8_t)(ck >> 24);
+  }
+}
+void launch_bloom_build(KeyCols m, uint64_t n, const FileRec* files, uint32_t nfiles, uint32_t millibits, uint32_t cksum,
+                        uint8_t* const* out_base, cudaStream_t st) {
+  if (n == 0 || nfiles == 0) return;
+  const int probes = bloom_num_probes((int)millibits);
+  const uint64_t blocks = (n + 255) / 256;
+  bloom_bits_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(m, n, files, nfiles, probes, out_base);
+  bloom_finish_kernel<<<(nfiles + 3) / 4, 128, 0, st>>>(files, nfiles, probes, cksum, out_base);
 }
 
 // ranks of the grandparent boundary keys in the merged stream (one thread per grandparent file)

@@ -98,6 +98,11 @@ struct EncodeParams {
   uint32_t* gp_ncuts;
 };
 using GpKey = BoundKey;       // grandparent boundary key in column form
+// ---- full Bloom filter block (bloom_rules.h).  count: per file the number of entries whose key hash differs from the predecessor's
+// (XXPH3FilterBitsBuilder::AddKey drops consecutive duplicates) and from it the block size; build: set the bits, metadata, trailer.
+void launch_bloom_count(KeyCols m, uint64_t n, FileRec* files, const uint64_t* nfiles_dev, uint32_t millibits, cudaStream_t st);
+void launch_bloom_build(KeyCols m, uint64_t n, const FileRec* files, uint32_t nfiles, uint32_t millibits, uint32_t cksum,
+                        uint8_t* const* out_base, cudaStream_t st);
 void launch_gp_ranks(KeyCols m, const GpKey* smallest, const GpKey* largest, uint32_t n, uint64_t* lo, uint64_t* eq, uint64_t* hi,
                      cudaStream_t st);
 struct BlockRec {            // one output data block
@@ -120,6 +125,8 @@ struct FileRec {             // one output file (device-computed part)
   KeyRec smallest, largest;
   uint32_t index_has_seq;    // some adjacent blocks share a user key => index keys keep the 8-byte trailer
   uint32_t index_cksum;      // checksum word of the index block trailer
+  uint64_t filter_entries;   // hashes in the Bloom filter (rocksdb.num.filter_entries); 0 without a filter policy
+  uint64_t filter_bytes;     // filter block on disk: bits + 5 metadata bytes + 5 trailer bytes; sits between data and index blocks
 };
 struct TileRow {             // block-cut transfer function of one tile for one entry-point candidate
   uint32_t exit;             // chain exit, entries past the tile end

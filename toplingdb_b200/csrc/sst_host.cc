@@ -287,7 +287,8 @@ std::vector<uint8_t> build_output_tail(const OutputTailInput& in) {
   props["rocksdb.data.size"] = vu64(in.data_size);
   props["rocksdb.deleted.keys"] = vu64(in.num_deletions);
   if (in.file_creation_time > 0) props["rocksdb.file.creation.time"] = vu64(in.file_creation_time);
-  props["rocksdb.filter.size"] = vu64(0);
+  if (in.filter_size) props["rocksdb.filter.policy"] = vstr("bloomfilter");  // props.filter_policy_name (builder :1610)
+  props["rocksdb.filter.size"] = vu64(in.filter_size);
   props["rocksdb.fixed.key.length"] = vu64(0);
   props["rocksdb.format.version"] = vu64(0);
   props["rocksdb.index.key.is.user.key"] = vu64(in.index_key_is_user_key ? 1 : 0);
@@ -297,7 +298,7 @@ std::vector<uint8_t> build_output_tail(const OutputTailInput& in) {
   props["rocksdb.merge.operator"] = vstr("nullptr");
   props["rocksdb.num.data.blocks"] = vu64(in.num_data_blocks);
   props["rocksdb.num.entries"] = vu64(in.num_entries);
-  props["rocksdb.num.filter_entries"] = vu64(0);
+  props["rocksdb.num.filter_entries"] = vu64(in.filter_entries);
   props["rocksdb.num.range-deletions"] = vu64(0);
   props["rocksdb.oldest.key.time"] = vu64(in.oldest_key_time);
   props["rocksdb.original.file.number"] = vu64(in.orig_file_number);
@@ -316,12 +317,20 @@ std::vector<uint8_t> build_output_tail(const OutputTailInput& in) {
     out.push_back(0);
     put_u32(out, host_block_checksum(in.checksum_type, blk.data(), blk.size(), 0));
   };
-  const uint64_t index_off = in.data_size;
+  // file := data blocks | [filter block] | index block | properties | metaindex | footer (Finish :1948-1970)
+  const uint64_t filter_off = in.data_size;
+  const uint64_t index_off = in.data_size + (in.filter_size ? in.filter_size + 5 : 0);
   const uint64_t props_off = index_off + in.index_size + 5;
   append_block(pb.b);
   const uint64_t meta_off = props_off + pb.b.size() + 5;
   HostBlock mb(1);
   std::vector<uint8_t> h;
+  if (in.filter_size) {  // "fullfilter." + FilterPolicy::CompatibilityName() (WriteFilterBlock :1532-1536); keys in sorted order
+    put_varint(h, filter_off);
+    put_varint(h, in.filter_size);
+    mb.add("fullfilter.rocksdb.BuiltinBloomFilter", h);
+    h.clear();
+  }
   put_varint(h, props_off);
   put_varint(h, pb.b.size());
   mb.add("rocksdb.properties", h);

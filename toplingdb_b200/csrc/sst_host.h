@@ -36,6 +36,7 @@ uint64_t host_xxh3_64(const uint8_t* data, uint64_t n);
 struct OutputTailInput {      // per output file
   uint32_t checksum_type, format_version;
   uint64_t data_size, index_size /* payload, no trailer */;
+  uint64_t filter_size = 0 /* filter block content (bits + metadata, no trailer); 0 = no filter block */, filter_entries = 0;
   uint64_t num_entries, num_deletions, raw_key_size, raw_value_size, num_data_blocks;
   bool index_key_is_user_key;
   uint32_t column_family_id;

@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -20,6 +21,7 @@
 #include "rocksdb/comparator.h"
 #include "rocksdb/env.h"
 #include "rocksdb/table.h"
+#include "table/block_based/filter_policy_internal.h"
 
 namespace ROCKSDB_NAMESPACE {
 
@@ -46,6 +48,18 @@ uint32_t DeviceFilterOf(const Compaction* c, int32_t* ttl = nullptr) {
   std::unique_ptr<CompactionFilter> f = factory->CreateCompactionFilter(ctx);
   if (f && std::string(f->Name()) == "RemoveEmptyValueCompactionFilter") return B200C_FILTER_REMOVE_EMPTY_VALUE;
   return B200C_FILTER_NONE;
+}
+
+// Filter block of the output files: 0 = none; > 0 = millibits per key of a BloomFilterPolicy (NewBloomFilterPolicy) in the one shape the
+// device builds -- full filter over whole keys, format_version >= 5 (FastLocalBloom), no prefix extractor, no malloc-size dependent
+// rounding; < 0 = any other filter (Ribbon, partitioned, prefixes, user policies): the job stays on the CPU.
+int DeviceBloomMillibits(const Compaction* c, const BlockBasedTableOptions* t) {
+  const FilterPolicy* fp = t->filter_policy.get();
+  if (fp == nullptr) return 0;
+  if (strcmp(fp->Name(), "bloomfilter") != 0) return -1;
+  if (t->partition_filters || !t->whole_key_filtering || t->optimize_filters_for_memory || t->format_version < 5) return -1;
+  if (c->mutable_cf_options()->prefix_extractor != nullptr) return -1;
+  return static_cast<const BloomLikeFilterPolicy*>(fp)->GetMillibitsPerKey();
 }
 
 const BlockBasedTableOptions* BlockBasedOptionsOf(const Compaction* c) {
@@ -128,7 +142,8 @@ class B200CompactionExecutor : public CompactionExecutor {
     bp.format_version = bbt->format_version;
     bp.checksum = (uint32_t)bbt->checksum;
     bp.verify_input_checksums = opt_.verify_input_checksums;
-    bp.paranoid_file_checks = p.paranoid_file_checks;  // RunRemote cannot hash what it did not write (compaction_job.cc:1065-1068)
+    bp.paranoid_file_checks = p.paranoid_file_checks;
+    bp.bloom_millibits_per_key = (uint32_t)std::max(0, DeviceBloomMillibits(c_, bbt));  // RunRemote cannot hash what it did not write (compaction_job.cc:1065-1068)
     std::vector<uint64_t> snaps;
     if (p.existing_snapshots) snaps.assign(p.existing_snapshots->begin(), p.existing_snapshots->end());
     bp.snapshots = snaps.data();
@@ -322,7 +337,7 @@ bool B200CompactionExecutorFactory::ShouldRunLocal(const Compaction* c) const {
   if (io->sst_partitioner_factory != nullptr) return true;
   if (BlockBasedOptionsOf(c) == nullptr) return true;
   const BlockBasedTableOptions* t = BlockBasedOptionsOf(c);
-  if (t->filter_policy != nullptr || t->index_type != BlockBasedTableOptions::kBinarySearch ||
+  if (DeviceBloomMillibits(c, t) < 0 || t->index_type != BlockBasedTableOptions::kBinarySearch ||
       t->data_block_index_type != BlockBasedTableOptions::kDataBlockBinarySearch || t->index_block_restart_interval != 1 ||
       t->block_align || t->format_version < 3 || t->format_version > 5 ||
       (t->checksum != kXXH3 && t->checksum != kCRC32c && t->checksum != kNoChecksum))
