@@ -70,3 +70,33 @@ def test_plugin_without_a_device_lets_the_reference_run_the_job_itself():
     assert got["manifest"]["remote_compact_read_bytes"] == 0
     assert (got["manifest"]["scan_count"], got["manifest"]["scan_digest"]) == (want["manifest"]["scan_count"], want["manifest"]["scan_digest"])
     assert [len(o) for o in got["outputs"]] == [len(o) for o in want["outputs"]]
+
+
+def test_ctypes_mirror_has_the_layout_of_the_header(tmp_path):
+    """toplingdb_b200/native.py restates the structs of include/b200c.h by hand; a C program compiled against the header prints
+    sizeof / offsetof of every field the mirror names, and they must agree (a drifted mirror would hand the library garbage)."""
+    import subprocess
+    import toplingdb_b200 as T
+    pairs = [("b200c_grandparent", T.native.Grandparent), ("b200c_params", T.native.Params), ("b200c_file_meta", T.native.FileMeta),
+             ("b200c_stats", T.native.JobStats)]
+    src = ['#include <stddef.h>', '#include <stdio.h>', '#include "b200c.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        src.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            src.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src += ["  return 0;", "}"]
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I" + os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    want = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    hdr = open(os.path.join(ROOT, "include", "b200c.h")).read()
+    for cname, cls in pairs:
+        assert C.sizeof(cls) == int(want[cname]), cname
+        for fname, _ in cls._fields_:
+            assert getattr(cls, fname).offset == int(want[f"{cname}.{fname}"]), (cname, fname)
+        # and the mirror names every field of the C struct (same count of declarators)
+        body = hdr[hdr.index("typedef struct " + cname + " {"):hdr.index("} " + cname + ";")]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        decls = [d for stmt in body.split("{", 1)[1].split(";") for d in stmt.split(",") if d.strip()]
+        assert len(decls) == len(cls._fields_), (cname, len(decls), len(cls._fields_))

@@ -753,10 +753,15 @@ void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint
   if (!occ) {
     const char* e = getenv("B200C_DECODE_CTAS_PER_SM");  // tuning knob: 2 = no register spills, 3 / 4 = more warps
     occ = e && atoi(e) >= 2 && atoi(e) <= 5 ? atoi(e) : 4;  // 4: 64 registers with a small spill, but 32 independent warps per SM
+  }
+  static PerDeviceFlag attr;
+  const uint64_t dev_bit = attr.bit_of_current_device();
+  if (!attr.is_set(dev_bit)) {
     cudaFuncSetAttribute(block_decode_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(block_decode_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(block_decode_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(block_decode_fused_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr.set(dev_bit);
   }
   const unsigned per = kDecWarps;
   unsigned want = (nblk + per - 1) / per, cap = (unsigned)sms * (unsigned)occ;

@@ -1883,11 +1883,12 @@ void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork 
 void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t max_s1, uint32_t* err,
                           cudaStream_t st) {
   if (ntiles == 0) return;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceFlag attr;
+  const uint64_t dev_bit = attr.bit_of_current_device();
+  if (!attr.is_set(dev_bit)) {
     cudaFuncSetAttribute(encode_tables_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TablesSmem<uint32_t>));
     cudaFuncSetAttribute(encode_tables_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TablesSmem<uint64_t>));
-    attr = true;
+    attr.set(dev_bit);
   }
   // all prefix sums of a window stay below 2^32 when (largest entry) x (window length) does
   if (((uint64_t)max_s1 + 64) * (uint64_t)(kW + 1) < (1ull << 32))
@@ -1901,11 +1902,12 @@ void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nti
   const uint64_t ngroups = (ntiles + kEncGroup - 1) / kEncGroup;
   unsigned ct = hc < 1024 ? ((hc + 31) & ~31u) : 1024;
   encode_compose_kernel<<<(unsigned)ngroups, ct, 0, st>>>(w, m.n, ntiles, hc);
-  static bool attr = false;
+  static PerDeviceFlag attr;
+  const uint64_t dev_bit = attr.bit_of_current_device();
   const size_t smem = ((sizeof(StitchSmem) + 15) & ~(size_t)15) + 2 * (size_t)kStitchCacheBytes;
-  if (!attr) {
+  if (!attr.is_set(dev_bit)) {
     cudaFuncSetAttribute(encode_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
+    attr.set(dev_bit);
   }
   encode_stitch_kernel<<<1, kEncThreads, smem, st>>>(m, ep, w, m.n, ntiles, hc, err);
   encode_tilestate_kernel<<<(unsigned)((ngroups + 63) / 64), 64, 0, st>>>(w, m.n, ntiles, hc, err);
@@ -1935,9 +1937,14 @@ void launch_encode_emit(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nbloc
   if (!occ) {
     const char* e = getenv("B200C_EMIT_CTAS_PER_SM");  // tuning knob
     occ = e && atoi(e) >= 3 && atoi(e) <= 5 ? atoi(e) : 4;  // 4: 64 registers with a small spill, but 32 independent warps per SM
+  }
+  static PerDeviceFlag attr;
+  const uint64_t dev_bit = attr.bit_of_current_device();
+  if (!attr.is_set(dev_bit)) {
     cudaFuncSetAttribute(encode_emit_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(encode_emit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(encode_emit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr.set(dev_bit);
   }
   const uint32_t slot = encode_emit_slice(ep.block_size);
   const size_t smem = (size_t)slot * kEmitWarps;

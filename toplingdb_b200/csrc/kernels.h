@@ -3,10 +3,25 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "gp_rules.h"
 
 namespace b200c {
+
+// cudaFuncSetAttribute acts on the current device only, and one process may drive several devices (one executor factory per GPU):
+// remember per device ordinal which kernels already carry their dynamic shared memory limit.  Racing threads just set it twice.
+struct PerDeviceFlag {
+  std::atomic<uint64_t> mask{0};
+  uint64_t bit_of_current_device() const {
+    int d = 0;
+    cudaGetDevice(&d);
+    return 1ull << (d & 63);
+  }
+  bool is_set(uint64_t bit) const { return (mask.load(std::memory_order_acquire) & bit) != 0; }
+  void set(uint64_t bit) { mask.fetch_or(bit, std::memory_order_release); }
+};
 
 struct FileDesc {          // one input BlockBasedTable image resident in HBM
   const uint8_t* base;

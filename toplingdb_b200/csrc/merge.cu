@@ -833,10 +833,11 @@ void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_t
                         const uint64_t* splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
                         MergeCounters* counters, uint32_t* err, cudaStream_t st) {
   if (ntiles == 0) return;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr;
+  const uint64_t dev_bit = attr.bit_of_current_device();
+  if (!attr.is_set(dev_bit)) {
     cudaFuncSetAttribute(merge_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
-    attr_set = true;
+    attr.set(dev_bit);
   }
   merge_tiles_kernel<<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state,
                                                                           ticket, out, counters, err, 148u * 3u);
