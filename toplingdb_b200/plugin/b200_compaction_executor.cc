@@ -62,6 +62,25 @@ int DeviceBloomMillibits(const Compaction* c, const BlockBasedTableOptions* t) {
   return static_cast<const BloomLikeFilterPolicy*>(fp)->GetMillibitsPerKey();
 }
 
+// Output-file cut rules of CompactionOutputs::ShouldStopBefore (compaction_outputs.cc:231-354) that the device does NOT evaluate: the
+// TTL cut at old files of the output level (FillFilesToCutForTtl :737-777, same conditions restated here) and the round-robin cursor
+// split (:282-291).  When one of them could fire, the reference must cut the files itself.
+bool HasHostOnlyFileCutRule(const Compaction* c) {
+  if (c->output_level() == 0) return false;
+  if (c->GetOutputSplitKey() != nullptr) return true;
+  const auto* io = c->immutable_options();
+  const auto* mo = c->mutable_cf_options();
+  if (io->compaction_style != kCompactionStyleLevel || io->compaction_pri != kMinOverlappingRatio || mo->ttl == 0 ||
+      c->num_input_levels() < 2 || c->bottommost_level())
+    return false;
+  int64_t now = 0;
+  if (!io->clock->GetCurrentTime(&now).ok() || (uint64_t)now < mo->ttl) return false;
+  const uint64_t old_age_thres = (uint64_t)now - mo->ttl / 2;
+  for (FileMetaData* f : *c->inputs(c->num_input_levels() - 1))
+    if (f->TryGetOldestAncesterTime() < old_age_thres && f->fd.GetFileSize() > mo->target_file_size_base / 2) return true;
+  return false;
+}
+
 const BlockBasedTableOptions* BlockBasedOptionsOf(const Compaction* c) {
   auto* tf = c->immutable_options()->table_factory.get();
   if (tf == nullptr || strcmp(tf->Name(), TableFactory::kBlockBasedTableName()) != 0) return nullptr;
@@ -172,6 +191,11 @@ class B200CompactionExecutor : public CompactionExecutor {
     std::vector<std::string> gp_keys;  // owns the user-key bytes
     gp_keys.reserve(2 * c_->grandparents().size());
     for (const FileMetaData* fm : c_->grandparents()) {
+      // a boundary that is a range-tombstone sentinel compares as an EXCLUSIVE bound (sstableKeyCompare, compaction.cc:28-43); the
+      // device rules treat boundaries as plain user keys, so such a job keeps the reference's own file cuts by running locally
+      const uint64_t sentinel = PackSequenceAndType(kMaxSequenceNumber, kTypeRangeDeletion);
+      if (ExtractInternalKeyFooter(fm->smallest.Encode()) == sentinel || ExtractInternalKeyFooter(fm->largest.Encode()) == sentinel)
+        return Fail(r, Status::NotSupported("B200Compact: grandparent file bounded by a range tombstone"));
       gp_keys.push_back(fm->smallest.user_key().ToString());
       gp_keys.push_back(fm->largest.user_key().ToString());
     }
@@ -335,6 +359,7 @@ bool B200CompactionExecutorFactory::ShouldRunLocal(const Compaction* c) const {
   if (io->user_comparator != BytewiseComparator()) return true;
   if (c->output_compression() != kNoCompression) return true;
   if (io->sst_partitioner_factory != nullptr) return true;
+  if (HasHostOnlyFileCutRule(c)) return true;
   if (BlockBasedOptionsOf(c) == nullptr) return true;
   const BlockBasedTableOptions* t = BlockBasedOptionsOf(c);
   if (DeviceBloomMillibits(c, t) < 0 || t->index_type != BlockBasedTableOptions::kBinarySearch ||
