@@ -75,3 +75,35 @@ def test_empty_and_unbounded_ranges():
     assert got == [ik for f in whole for ik, _ in sstfmt.parse_sst(f)["entries"]]
     assert sa.num_input_records + sb.num_input_records == st.num_input_records
     assert sa.num_output_records + sb.num_output_records == st.num_output_records
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,n", [(5, 40000), (6, 30000)])
+def test_subcompactions_of_a_picker_built_job_with_grandparents_and_filters(seed, n):
+    """everything at once, as a live DB does it: DB::CompactRange picks L0 -> L1 with the L2 files as grandparents, the job is split
+    into 4 sub-compactions, the table has a Bloom filter policy.  Every sub-compaction starts its own grandparent walk at its first
+    key (CompactionOutputs is per sub-compaction), which is what a clipped oracle job does."""
+    ops, opts = S.grandparent_cuts(n=n, seed=seed)
+    ref = H.run_reference(ops, max_subcompactions=4, bloom_bits=10, **opts)
+    assert len(ref["manifest"]["grandparents"]) >= 2
+    ranges = H.subcompaction_ranges(ref)
+    assert len(ranges) >= 2
+    props = [sstfmt.parse_sst(o)["properties"] for o in ref["outputs"]]
+    k = 0
+    for start, end, rstats in ranges:
+        p = H.params_from_reference(ref)
+        p.range_start, p.range_end = start, end
+        nfiles = len(H.oracle_compact(p, ref["inputs"])[0])
+        p.file_creation_times = [sstfmt.prop_u64(q, "rocksdb.file.creation.time") for q in props[k:k + nfiles]] or [0]
+        files, _, st = H.oracle_compact(p, ref["inputs"])
+        want = ref["outputs"][k:k + nfiles]
+        assert [len(f) for f in files] == [len(f) for f in want]
+        for got, exp in zip(files, want):
+            assert file_parts(got) == file_parts(exp)
+            t = sstfmt.parse_sst(got)
+            fo, fs = t["metaindex"]["fullfilter.rocksdb.BuiltinBloomFilter"]
+            assert got[fo:fo + fs + 5] == exp[fo:fo + fs + 5]
+        for key in SUB_STATS:
+            assert getattr(st, key) == rstats[key], key
+        k += nfiles
+    assert k == len(ref["outputs"])
