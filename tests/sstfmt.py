@@ -87,7 +87,12 @@ def parse_sst(data):
     iblock, _, _ = read_block(data, ft["index"])
     index = []
     prev = None
-    for k, p, shared in block_entries(iblock, value_delta=True):
+    if ft["format_version"] < 4:  # index values are plain block handles (no delta encoding, IndexValue::EncodeTo format.cc:102-118)
+        for k, v, _ in block_entries(iblock):
+            o, q = varint(v, 0)
+            s, q = varint(v, q)
+            index.append((k, (o, s)))
+    for k, p, shared in (block_entries(iblock, value_delta=True) if ft["format_version"] >= 4 else []):
         if shared == 0:
             o, p = varint(iblock, p)
             s, p = varint(iblock, p)
