@@ -1309,6 +1309,32 @@ static int should_stop_before(gp_state* g, const orc_params* p, const uint8_t* u
   return 0;
 }
 
+/* Test hook: the output-file cut rules alone, over a key list and a caller-supplied size model.  The reference's own known-answer
+ * tests for these rules (db/compaction/compaction_job_test.cc:1755-2150, CompactionJobDynamicFileSizeTest) run on mock tables whose
+ * FileSize() is entries x constant (table/mock_table.cc:180), which a BlockBasedTable job cannot reproduce; this runs the same
+ * should_stop_before / reset sequence as orc_compact with that size model.  cut_before[i] = 1: a new output file starts at key i. */
+int orc_file_cut_sim(const orc_params* p, int n, const uint8_t* const* ukeys, const uint32_t* ulens, uint64_t bytes_per_entry,
+                     uint8_t* cut_before) {
+  gp_state gps = {1, 0, 0, 0, 0};
+  int have_builder = 0;
+  uint64_t in_file = 0;
+  for (int i = 0; i < n; i++) {
+    cut_before[i] = 0;
+    if (should_stop_before(&gps, p, ukeys[i], ulens[i], have_builder, in_file * bytes_per_entry) && have_builder) {
+      have_builder = 0;
+      gps.switched = 0;
+      gps.overlapped = p->num_grandparents ? gp_current_key_overlap(&gps, p, ukeys[i], ulens[i]) : 0;
+    }
+    if (!have_builder) {
+      cut_before[i] = 1;
+      have_builder = 1;
+      in_file = 0;
+    }
+    in_file++;
+  }
+  return 0;
+}
+
 int orc_compact(const orc_params* p, int n_inputs, const uint8_t* const* inputs, const uint64_t* input_lens,
                 orc_result** out) {
   merge_in m;

@@ -128,6 +128,8 @@ int orc_compaction_iterator(const orc_params* p, const uint8_t* kv, size_t kv_le
                             orc_stats* stats);
 
 /* Whole job: decode inputs (inputs[0] = newest L0 run first), k-way merge, drop rules, encode. */
+int orc_file_cut_sim(const orc_params* p, int n, const uint8_t* const* ukeys, const uint32_t* ulens, uint64_t bytes_per_entry,
+                     uint8_t* cut_before);
 int orc_compact(const orc_params* p, int n_inputs, const uint8_t* const* inputs, const uint64_t* input_lens,
                 orc_result** out);
 int orc_result_num_files(const orc_result* r);
