@@ -605,6 +605,11 @@ typedef struct citer {
   uint64_t out_seq;
   uint8_t out_type;
   buf out_val;
+  /* SingleDelete bookkeeping (compaction_iterator.h): */
+  int has_outputted_key;          /* a record of the current user key went out (set in Next() :223-226, not in SeekToFirst) */
+  int last_key_seq_zeroed;        /* PrepareOutput zeroed the sequence number of the last output (:1323-1324) */
+  int clear_and_output_next_key;  /* the SingleDelete was kept for write-conflict checking: its Put follows with an empty value */
+  uint64_t earliest_write_conflict_snapshot;
 } citer;
 static uint64_t find_earliest_visible_snapshot(const orc_params* p, uint64_t in, uint64_t* prev) {
   uint32_t lo = 0, hi = p->num_snapshots; /* lower_bound */
@@ -617,9 +622,18 @@ static uint64_t find_earliest_visible_snapshot(const orc_params* p, uint64_t in,
   return lo < p->num_snapshots ? p->snapshots[lo] : ORC_MAX_SEQ;
 }
 static int key_not_exists_beyond_output_level(const citer* c) {
-  /* Compaction::KeyNotExistsBeyondOutputLevel (db/compaction/compaction.cc:548-586): true at the bottommost
-   * level, false on a compaction worker otherwise (:555-556) — the deployment this repo targets. */
-  return c->p->bottommost_level != 0;
+  /* Compaction::KeyNotExistsBeyondOutputLevel (db/compaction/compaction.cc:548-586): true at the bottommost level; on a compaction
+   * worker false otherwise (:555-556) -- the deployment this repo targets; for a job the DB runs itself the deeper levels' file ranges
+   * decide (key_not_exists_mode 1, used to replay the reference's own CompactionJob tests). */
+  if (c->p->bottommost_level) return 1;
+  if (c->p->key_not_exists_mode != 1) return 0;
+  const uint8_t* uk = c->current_key.p;
+  size_t un = c->current_key.n - 8;
+  for (uint32_t i = 0; i < c->p->num_deeper_files; i++) {
+    const orc_grandparent* f = &c->p->deeper_files[i];
+    if (ukey_cmp(uk, un, f->largest, f->largest_len) <= 0 && ukey_cmp(uk, un, f->smallest, f->smallest_len) >= 0) return 0;
+  }
+  return 1;
 }
 static void citer_set_trailer(citer* c, uint64_t seq, uint8_t type) {
   uint64_t t = (seq << 8) | type;
@@ -642,7 +656,7 @@ static void citer_next_from_input(citer* c) {
     if (type == ORC_TYPE_DELETION || type == ORC_TYPE_SINGLE_DELETION) c->st->num_input_deletion_records++;
     c->st->total_input_raw_key_bytes += in->klen;
     c->st->total_input_raw_value_bytes += in->vlen;
-    if (type != ORC_TYPE_VALUE && type != ORC_TYPE_DELETION) {
+    if (type != ORC_TYPE_VALUE && type != ORC_TYPE_DELETION && type != ORC_TYPE_SINGLE_DELETION) {
       c->err = -7;
       snprintf(g_err, sizeof g_err, "value type %u outside the restated rule set", type);
       return;
@@ -656,6 +670,8 @@ static void citer_next_from_input(citer* c) {
       c->cur_seq = ORC_MAX_SEQ;
       c->cur_snap = 0;
       c->has_current_user_key = 1;
+      c->has_outputted_key = 0; /* :578-580 */
+      c->last_key_seq_zeroed = 0;
       /* :579-584 the filter sees the first (newest) committed version of a user key, kTypeValue only (:236-239);
        * Decision::kRemove turns it into a tombstone with no value (:385-391) */
       int remove = 0;
@@ -685,7 +701,59 @@ static void citer_next_from_input(citer* c) {
     uint64_t last_snapshot = c->cur_snap, prev_snapshot = 0;
     c->cur_seq = seq;
     c->cur_snap = c->visible_at_tip ? c->earliest_snapshot : find_earliest_visible_snapshot(c->p, seq, &prev_snapshot);
-    if (last_snapshot == c->cur_snap || (last_snapshot > 0 && last_snapshot < c->cur_snap)) {
+    if (c->clear_and_output_next_key) { /* :635-661 the Put behind a SingleDelete that had to stay: keep it, without its value */
+      if (type != ORC_TYPE_VALUE) {
+        c->err = -9;
+        snprintf(g_err, sizeof g_err, "unexpected type %u behind a kept SingleDelete", type);
+        return;
+      }
+      c->out_val.n = 0;
+      c->valid = 1;
+      c->clear_and_output_next_key = 0;
+    } else if (type == ORC_TYPE_SINGLE_DELETION) { /* :662-887 */
+      in->next(in);
+      int next_same = in->valid && in->klen >= 8 && in->klen - 8 == ulen && memcmp(in->key, c->current_key.p, ulen) == 0;
+      if (next_same) {
+        uint64_t ntr = trailer_of(in->key, in->klen), nseq = ntr >> 8;
+        uint8_t ntype = (uint8_t)(ntr & 0xff);
+        if (c->last_key_seq_zeroed) { /* :753-757 */
+          c->st->num_records_replaced++;
+          c->st->num_expired_deletion_records++;
+          in->next(in);
+        } else if (prev_snapshot == 0 || nseq > prev_snapshot) { /* the next key is in the SingleDelete's snapshot stripe */
+          if (ntype == ORC_TYPE_SINGLE_DELETION) { /* :765-778 two in a row: drop the first */
+            c->st->num_expired_deletion_records++;
+          } else if (ntype == ORC_TYPE_DELETION) { /* :779-800 contract violation; enforce_single_del_contracts defaults to true */
+            c->st->num_expired_deletion_records++;
+            c->err = -10;
+            snprintf(g_err, sizeof g_err, "SingleDelete and Delete on the same key");
+            return;
+          } else if (c->has_outputted_key || seq <= c->earliest_write_conflict_snapshot ||
+                     (c->earliest_snapshot < c->earliest_write_conflict_snapshot && seq <= c->earliest_snapshot)) {
+            c->st->num_records_replaced++; /* :803-829 the pair cancels out */
+            c->st->num_expired_deletion_records++;
+            in->next(in);
+          } else { /* :830-846 keep the SingleDelete for write-conflict checking, its Put follows without a value */
+            c->valid = 1;
+            c->clear_and_output_next_key = 1;
+          }
+        } else { /* :847-853 the next version belongs to an older snapshot */
+          c->valid = 1;
+        }
+      } else { /* :854-884 last version of this user key in the input */
+        c->has_current_user_key = 0;
+        if (seq <= c->earliest_snapshot && key_not_exists_beyond_output_level(c)) {
+          c->st->num_expired_deletion_records++;
+          if (!c->p->bottommost_level) c->st->num_optimized_del_drop_obsolete++;
+        } else if (c->last_key_seq_zeroed) {
+          c->st->num_records_replaced++;
+          c->st->num_expired_deletion_records++;
+        } else {
+          c->valid = 1;
+        }
+      }
+      if (c->valid) c->at_next = 1;
+    } else if (last_snapshot == c->cur_snap || (last_snapshot > 0 && last_snapshot < c->cur_snap)) {
       c->st->num_records_replaced++; /* rule (A) :890-911 */
       in->next(in);
     } else if (type == ORC_TYPE_DELETION && seq <= c->earliest_snapshot && key_not_exists_beyond_output_level(c)) {
@@ -709,6 +777,7 @@ static void citer_next_from_input(citer* c) {
 static void citer_prepare_output(citer* c) { /* :1274-1341 */
   if (c->valid && c->p->bottommost_level && c->out_seq <= c->earliest_snapshot && c->out_type != ORC_TYPE_MERGE) {
     c->out_seq = 0;
+    c->last_key_seq_zeroed = 1;
     citer_set_trailer(c, 0, c->out_type);
   }
 }
@@ -719,12 +788,14 @@ static void citer_init(citer* c, input* in, const orc_params* p, orc_stats* st) 
   c->st = st;
   c->visible_at_tip = p->num_snapshots == 0;
   c->earliest_snapshot = p->num_snapshots ? p->snapshots[0] : ORC_MAX_SEQ;
+  c->earliest_write_conflict_snapshot = p->earliest_write_conflict_snapshot ? p->earliest_write_conflict_snapshot : ORC_MAX_SEQ;
   citer_next_from_input(c); /* SeekToFirst :199-203 */
   citer_prepare_output(c);
 }
 static void citer_next(citer* c) {
   if (!c->at_next) c->in->next(c->in);
   citer_next_from_input(c);
+  if (c->valid) c->has_outputted_key = 1; /* Next() :223-226 */
   citer_prepare_output(c);
 }
 static void citer_free(citer* c) {

@@ -78,6 +78,16 @@ typedef struct orc_params {
    * (table/block_based/filter_policy.cc:1327-1343); 0 = no filter block.  Full filter over whole user keys, format_version >= 5
    * (FastLocalBloom). */
   uint32_t bloom_millibits_per_key;
+  /* CompactionIterator's earliest_write_conflict_snapshot (kMaxSequenceNumber unless a transaction DB holds write-conflict snapshots);
+   * 0 = kMaxSequenceNumber.  Only the SingleDelete rule reads it (compaction_iterator.cc:803-808). */
+  uint64_t earliest_write_conflict_snapshot;
+  /* Compaction::KeyNotExistsBeyondOutputLevel (db/compaction/compaction.cc:548-586).  0 (default): a compaction worker's answer --
+   * true only at the bottommost level (:553-556), which is what the executor plugin's jobs get.  1: the answer of a job the DB runs
+   * itself: at a non-bottommost level the key may exist beyond the output level iff it falls into the user-key range of one of the
+   * files of the deeper levels, listed in deeper_files (orc_grandparent: smallest / largest user key; file_size unused). */
+  uint32_t key_not_exists_mode;
+  const orc_grandparent* deeper_files;
+  uint32_t num_deeper_files;
 } orc_params;
 #define ORC_FILTER_NONE 0
 #define ORC_FILTER_REMOVE_EMPTY_VALUE 1 /* utilities/compaction_filters/remove_emptyvalue_compactionfilter.cc:15-22 */

@@ -337,6 +337,13 @@ int main(int argc, char** argv) {
         if (++batch_n >= 4096) flush_batch();
         break;
       }
+      case 7: {  // WriteBatch::SingleDelete
+        uint32_t kl = rd.u32();
+        rd.bytes(&key, kl);
+        batch.SingleDelete(key);
+        if (++batch_n >= 4096) flush_batch();
+        break;
+      }
       case 3: {
         flush_batch();
         FlushOptions fo;

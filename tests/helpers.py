@@ -39,7 +39,8 @@ class OrcParams(C.Structure):
         ("target_output_file_size", C.c_uint64),
         ("range_start", C.c_char_p), ("range_start_len", C.c_uint32), ("has_range_start", C.c_uint32),
         ("range_end", C.c_char_p), ("range_end_len", C.c_uint32), ("has_range_end", C.c_uint32),
-        ("bloom_millibits_per_key", C.c_uint32),
+        ("bloom_millibits_per_key", C.c_uint32), ("earliest_write_conflict_snapshot", C.c_uint64),
+        ("key_not_exists_mode", C.c_uint32), ("deeper_files", C.POINTER(OrcGrandparent)), ("num_deeper_files", C.c_uint32),
     ]
 
 
@@ -117,6 +118,9 @@ class Params:
         self.range_start = None  # sub-compaction key range: start <= user key < end (None: unbounded)
         self.range_end = None
         self.bloom_millibits_per_key = 0  # NewBloomFilterPolicy(bits) * 1000; 0 = no filter block
+        self.earliest_write_conflict_snapshot = 0  # 0 = kMaxSequenceNumber
+        self.deeper_files = None  # [(smallest user key, largest user key)] of the levels below the output level: the DB's own (non-worker)
+        #                           KeyNotExistsBeyondOutputLevel; None = worker semantics (true only at the bottommost level)
         for k, v in kw.items():
             assert hasattr(self, k), k
             setattr(self, k, v)
@@ -160,6 +164,15 @@ class Params:
         tgt = self.target_output_file_size or self.max_output_file_size
         p.target_output_file_size = tgt
         p.bloom_millibits_per_key = self.bloom_millibits_per_key
+        p.earliest_write_conflict_snapshot = self.earliest_write_conflict_snapshot
+        if self.deeper_files is not None:
+            self._deeper = (OrcGrandparent * max(1, len(self.deeper_files)))()
+            for i, (a, b) in enumerate(self.deeper_files):
+                self._deeper[i].smallest, self._deeper[i].smallest_len = a, len(a)
+                self._deeper[i].largest, self._deeper[i].largest_len = b, len(b)
+            p.key_not_exists_mode = 1
+            p.deeper_files = C.cast(self._deeper, C.POINTER(OrcGrandparent))
+            p.num_deeper_files = len(self.deeper_files)
         if self.range_start is not None:
             p.range_start, p.range_start_len, p.has_range_start = self.range_start, len(self.range_start), 1
         if self.range_end is not None:
@@ -271,6 +284,9 @@ class Ops:
 
     def delete(self, k):
         self.b += struct.pack("<BI", 2, len(k)) + k
+
+    def single_delete(self, k):
+        self.b += struct.pack("<BI", 7, len(k)) + k
 
     def flush(self):
         self.b += b"\x03"

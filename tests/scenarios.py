@@ -249,3 +249,45 @@ ALL = dict(basic_bottommost=basic_bottommost, nonbottom_tombstones=nonbottom_tom
            tiny=tiny, all_deleted=all_deleted, cfg2_mini=cfg2_mini, cfg3_mini=cfg3_mini, output_level0=output_level0,
            filter_empty_value=filter_empty_value, filter_empty_value_nonbottom=filter_empty_value_nonbottom,
            ttl_filter=ttl_filter, ttl_filter_nonbottom=ttl_filter_nonbottom)
+
+
+def single_deletes(n=400, nruns=5, seed=19, nonbottom=False, with_snapshots=True):
+    """SingleDelete (compaction_iterator.cc:662-887): Put / SingleDelete pairs across runs, repeated pairs on one key, SingleDeletes
+    whose Put lives in an older snapshot stripe or below the output level, dangling SingleDeletes.  Delete is never mixed with
+    SingleDelete on one key (that breaks the SingleDelete contract and fails the job).  Outside the device rule set: oracle-side only."""
+    rnd = random.Random(seed)
+    ops = Ops()
+    if nonbottom:
+        for k in [key16(0), key16(1 << 40)]:
+            ops.put(k, b"base")
+        ops.flush()
+        ops.compact_all_to(6)
+    sd_keys = set(rnd.sample(range(1, n * 2), n // 2))  # keys that only ever see Put / SingleDelete
+    live = set()
+    for r in range(nruns):
+        for k in sorted(rnd.sample(range(1, n * 2), n)):
+            if k in sd_keys:
+                if k in live and rnd.random() < 0.6:
+                    ops.single_delete(key16(k))
+                    live.discard(k)
+                    if rnd.random() < 0.3:  # written again in the same run: Put SD Put
+                        ops.put(key16(k), rnd.randbytes(rnd.randint(0, 30)))
+                        live.add(k)
+                elif k not in live:
+                    if rnd.random() < 0.1:
+                        ops.single_delete(key16(k))  # nothing to delete: a dangling SingleDelete
+                    else:
+                        ops.put(key16(k), rnd.randbytes(rnd.randint(0, 30)))
+                        live.add(k)
+            elif rnd.random() < 0.15:
+                ops.delete(key16(k))
+            else:
+                ops.put(key16(k), rnd.randbytes(rnd.randint(0, 30)))
+        ops.flush()
+        if with_snapshots and r in (1, 3):
+            ops.snapshot()
+    return ops, dict(target_file_size=48 << 10)
+
+
+ORACLE_ONLY["single_deletes"] = single_deletes
+ORACLE_ONLY["single_deletes_nonbottom"] = lambda **kw: single_deletes(nonbottom=True, **kw)

@@ -62,3 +62,36 @@ def test_simple_non_last_level():  # :848-878: level 2 holds older versions, so 
     file2 = [(ik("a", 3), b"val"), (ik("b", 4), b"val")]     # L1
     got, _ = run([file1, file2], bottommost=False)
     assert got == [(ik("a", 5), b"val2"), (ik("b", 6), b"val3")]
+
+
+# ---- SingleDelete: the reference's CompactionJob tests, extracted by tests/golden/make_compaction_job_kat.py ---------------------------
+import json
+import os
+
+import pytest
+
+SD_KAT = json.load(open(os.path.join(H.GOLDEN_DIR, "compaction_job_kat.json")))["cases"]
+
+
+@pytest.mark.parametrize("c", SD_KAT, ids=[c["name"] for c in SD_KAT])
+def test_single_delete_known_answers(c):
+    """SimpleSingleDelete, SingleDeleteSnapshots, EarliestWriteConflictSnapshot, SingleDeleteZeroSeq, MultiSingleDelete
+    (compaction_job_test.cc:1032-1388): SingleDelete/Put pairs cancel only inside one snapshot stripe, a SingleDelete kept for
+    write-conflict checking is followed by its Put with the value cleared, leftovers are dropped where the key cannot exist beyond the
+    output level.  The tests run a job of the DB itself, so KeyNotExistsBeyondOutputLevel looks at the deeper levels' files."""
+    def ent(e):
+        return ik(e[0], e[1], e[2]), e[3].encode()
+    files = [[ent(e) for e in f["entries"]] for f in c["inputs"]]
+    deeper = [(min(e[0] for e in f["entries"]).encode(), max(e[0] for e in f["entries"]).encode()) for f in c["deeper_levels"]]
+    inputs = [H.oracle_build_sst(H.Params(), H.kvstream(f)) for f in reversed(files)]  # later AddMockFile = newer level-0 file
+    p = H.Params(output_level=1, bottommost_level=not deeper, snapshots=c["snapshots"], deeper_files=deeper,
+                 earliest_write_conflict_snapshot=c["earliest_write_conflict_snapshot"] or 0)
+    out, _, st = H.oracle_compact(p, inputs)
+    got = [e for f in out for e in sstfmt.parse_sst(f)["entries"]]
+    assert got == [ent(e) for e in c["expected"]]
+
+
+def test_remove_single_deletion_at_bottom_level():  # db/compaction/compaction_iterator_test.cc:749-756
+    kv = H.kvstream([(ik("a", 1, 7), b""), (ik("b", 2, 7), b"")])
+    out, _ = H.oracle_citer(H.Params(bottommost_level=True, snapshots=[1]), kv)
+    assert H.parse_kvstream(out) == [(ik("b", 2, 7), b"")]
