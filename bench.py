@@ -103,12 +103,17 @@ def reference_arm(args, rank, world):
         res.append(CB.run_sample(w, sample_bytes=sample, threads=cores))
     res = res[1:] if len(res) > args.steps else res
     mbps = statistics.mean(r["mbps"] for r in res)
+    # the same cores used the other way the reference can: ONE job split by max_subcompactions (threads inside one CompactionJob)
+    sub = CB.run_subcompactions(w, sample_bytes=sample, threads=cores)
     line = {"impl": "reference", "metric": "compaction_input_kv_MB_per_s", "value": mbps, "unit": "MB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": statistics.mean(r["seconds"] for r in res) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": w["desc"], "sample": res[0]["sample"]},
             "cpu_baseline": {"value": mbps, "unit": "MB/s", "cores": cores, "kind": res[0]["kind"], "sample": res[0]["sample"]},
             "e2e": {"value": mbps, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if sub:
+        line["one_job_max_subcompactions"] = {"value": round(sub["mbps"], 1), "unit": "MB/s", "max_subcompactions": sub["max_subcompactions"],
+                                              "sub_compactions_formed": sub["sub_compactions_formed"], "sample": sub["sample"]}
     print(json.dumps(line))
 
 

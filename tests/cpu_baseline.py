@@ -127,6 +127,30 @@ def run_sample(w, sample_bytes, threads):
     return {"mbps": n_total * entry / secs / 1e6, "seconds": secs, "kind": "port", "threads": 1, "sample": desc + "; CPU oracle port"}
 
 
+def run_subcompactions(w, sample_bytes, threads):
+    """SURVEY 8(d)(ii): ONE reference job with max_subcompactions = threads (CompactionJob::GenSubcompactionBoundaries splits the key
+    space at the input files' anchors, one thread per range).  Returns MB/s over CompactionJobStats.elapsed_micros and how many
+    sub-compactions the reference really formed."""
+    if not os.path.exists(REF_BIN):
+        return None
+    entry = 24 + w["vlen"]
+    n_total = max(w["k"] * 1000, sample_bytes // entry)
+    d = tempfile.mkdtemp(prefix="b200c_cpu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        _ops_file(os.path.join(d, "ops.bin"), w, n_total, seed=2)
+        subprocess.check_call([REF_BIN, os.path.join(d, "ops.bin"), os.path.join(d, "w"), "output_level=1",
+                               f"max_subcompactions={threads}", "target_file_size=67108864", "copy=0"], stdout=subprocess.DEVNULL)
+        man = json.load(open(os.path.join(d, "w", "manifest.json")))
+        stt = man["stats"]
+        kv = stt["total_input_raw_key_bytes"] + stt["total_input_raw_value_bytes"]
+        secs = stt["elapsed_micros"] / 1e6
+        return {"mbps": kv / secs / 1e6, "seconds": secs, "max_subcompactions": threads,
+                "sub_compactions_formed": max(1, len(man.get("subcompactions", []))),
+                "sample": f"one job, {w['k']} runs x {n_total // w['k']} entries = {n_total * entry / 2**20:.0f} MiB raw KV"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 if __name__ == "__main__":  # scaling probe: python tests/cpu_baseline.py 1 8 32 128
     import sys
     W = dict(k=8, run_bytes=256 << 20, vlen=32, overlap=0.0, del_frac=0.0, bottommost=False, desc="cfg2")
