@@ -1,7 +1,10 @@
 """Random cross-check of the CPU oracle against the compiled reference (oracle/_ref): scenarios of tests/scenarios.py re-seeded at random,
 with random table options (block size, restart interval, format_version 3-5, checksum), a Bloom filter policy at random bits per key,
 random target file sizes, SingleDelete scenarios included.  Every run compares all output files byte for byte and the job statistics.
-`python tools/fuzz_oracle_vs_reference.py [seconds] [seed]`; the run recorded in DESIGN.md: 1500 s, seed 777 -> 16 244 jobs, 0 mismatches."""
+`python tools/fuzz_oracle_vs_reference.py [seconds] [seed]`; the run recorded in DESIGN.md: 1500 s, seed 777 -> 16 244 jobs, 0 mismatches.
+`python tools/fuzz_oracle_vs_reference.py [seconds] [seed] picker`: jobs the DB's own picker builds (DB::CompactRange: grandparents
+attached) with 1-8 sub-compactions and a random filter policy, every sub-compaction range checked on its own (files + statistics);
+recorded run: 800 s, seed 99 -> 1 105 jobs, 0 mismatches."""
 import os
 import random
 import sys
@@ -13,9 +16,44 @@ import helpers as H  # noqa: E402
 import scenarios as S  # noqa: E402
 
 
+def picker_jobs(budget, rnd):
+    import sstfmt
+    from test_oracle_subcompactions import SUB_STATS, file_parts
+    runs = bad = 0
+    t0 = time.time()
+    while time.time() - t0 < budget:
+        seed, n = rnd.randrange(1, 10 ** 6), rnd.choice([6000, 15000, 30000, 50000])
+        ops, opts = S.grandparent_cuts(n=n, seed=seed)
+        extra = dict(max_subcompactions=rnd.choice([1, 1, 2, 4, 8]))
+        if rnd.random() < 0.4:
+            extra["bloom_bits"] = rnd.choice([5, 10, 15.5])
+        ref = H.run_reference(ops, **dict(opts, **extra))
+        ranges = H.subcompaction_ranges(ref)
+        props = [sstfmt.parse_sst(o)["properties"] for o in ref["outputs"]]
+        k, ok = 0, True
+        for start, end, rs in ranges:
+            p = H.params_from_reference(ref)
+            p.range_start, p.range_end = start, end
+            nf = len(H.oracle_compact(p, ref["inputs"])[0])
+            p.file_creation_times = [sstfmt.prop_u64(q, "rocksdb.file.creation.time") for q in props[k:k + nf]] or [0]
+            files, _, st = H.oracle_compact(p, ref["inputs"])
+            want = ref["outputs"][k:k + nf]
+            ok = ok and len(want) == len(files) and all(file_parts(a) == file_parts(b) for a, b in zip(files, want))
+            ok = ok and (len(ranges) == 1 or all(getattr(st, key) == rs[key] for key in SUB_STATS))
+            k += nf
+        runs += 1
+        if not ok or k != len(ref["outputs"]):
+            bad += 1
+            print("MISMATCH", seed, n, extra, flush=True)
+    print("runs", runs, "mismatches", bad)
+    return 1 if bad else 0
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rnd = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 777)
+    if len(sys.argv) > 3 and sys.argv[3] == "picker":
+        return picker_jobs(budget, rnd)
     names = [n for n in S.ALL if n != "long_keys"] + ["single_deletes", "single_deletes_nonbottom"]
     runs = bad = 0
     t0 = time.time()
