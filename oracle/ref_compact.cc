@@ -57,6 +57,7 @@ struct Opts {
   uint32_t format_version = 5;
   int keep_db = 0;
   int paranoid = 0;
+  int blob = 0, ingest_behind = 0, ribbon = 0, partition_filters = 0;  // option shapes the B200 executor must leave to the CPU path
   double bloom_bits = 0;  // > 0: BlockBasedTableOptions::filter_policy = NewBloomFilterPolicy(bloom_bits) (full filter, whole keys)
   int copy = 1;  // 0: leave inputs/ and outputs/ empty (timing runs only need the manifest)
   uint64_t setup_file_size = UINT64_MAX;  // output file size limit of the set-up compactions (op 5): several files below the job
@@ -204,6 +205,10 @@ int main(int argc, char** argv) {
     else if (k == "keep_db") o.keep_db = atoi(v.c_str());
     else if (k == "paranoid") o.paranoid = atoi(v.c_str());
     else if (k == "bloom_bits") o.bloom_bits = atof(v.c_str());
+    else if (k == "blob") o.blob = atoi(v.c_str());
+    else if (k == "ingest_behind") o.ingest_behind = atoi(v.c_str());
+    else if (k == "ribbon") o.ribbon = atoi(v.c_str());
+    else if (k == "partition_filters") o.partition_filters = atoi(v.c_str());
     else if (k == "executor") o.executor = v;
     else if (k == "copy") o.copy = atoi(v.c_str());
     else if (k == "filter") o.filter = v;
@@ -239,6 +244,9 @@ int main(int argc, char** argv) {
   opt.max_subcompactions = o.max_subcompactions;
   opt.max_background_jobs = 2;
   opt.paranoid_file_checks = o.paranoid != 0;
+  opt.enable_blob_files = o.blob != 0;
+  opt.min_blob_size = 16;
+  opt.allow_ingest_behind = o.ingest_behind != 0;
   if (o.mode == "range") opt.level_compaction_dynamic_level_bytes = false;  // CompactRange then goes L0 -> L1, not to a base level
   opt.info_log_level = WARN_LEVEL;
   opt.stats_dump_period_sec = 0;
@@ -250,6 +258,11 @@ int main(int argc, char** argv) {
   t.checksum = o.checksum == "crc32c" ? kCRC32c : kXXH3;
   t.no_block_cache = true;
   if (o.bloom_bits > 0) t.filter_policy.reset(NewBloomFilterPolicy(o.bloom_bits, false));
+  if (o.ribbon) t.filter_policy.reset(NewRibbonFilterPolicy(10));
+  if (o.partition_filters) {
+    t.partition_filters = true;
+    t.index_type = BlockBasedTableOptions::kTwoLevelIndexSearch;
+  }
   opt.table_factory.reset(NewBlockBasedTableFactory(t));
   if (o.filter == "remove_empty_value") opt.compaction_filter_factory = std::make_shared<RemoveEmptyValueFactory>();
   else if (o.filter != "none") {

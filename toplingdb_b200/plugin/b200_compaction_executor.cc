@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -349,31 +350,52 @@ B200CompactionExecutorFactory::B200CompactionExecutorFactory(const B200CompactOp
 }
 B200CompactionExecutorFactory::~B200CompactionExecutorFactory() = default;
 
-bool B200CompactionExecutorFactory::ShouldRunLocal(const Compaction* c) const {
-  if (!have_device_) return true;
+// Why a job has to stay on the reference's own CPU path (nullptr: the device takes it).  Everything here is decided from the job's
+// OPTIONS and metadata; data-dependent reasons (a Merge / SingleDelete record, a long key) surface later as Status::NotSupported from
+// Execute().  The list errs on the side of running locally: an option that changes what CompactionIterator, CompactionOutputs or the
+// table builder do and that the device does not implement must keep the reference's own behaviour.
+static const char* WhyLocal(const Compaction* c) {
   const auto* io = c->immutable_options();
-  if (io->merge_operator != nullptr) return true;
+  const auto* mo = c->mutable_cf_options();
+  if (io->merge_operator != nullptr) return "merge operator";
   // RunRemote needs the filter to come from a factory (compaction_job.cc:942-943); only filters the merge kernel implements run remotely
-  if (io->compaction_filter != nullptr) return true;
-  if (io->compaction_filter_factory != nullptr && DeviceFilterOf(c) == B200C_FILTER_NONE) return true;
-  if (io->user_comparator != BytewiseComparator()) return true;
-  if (c->output_compression() != kNoCompression) return true;
-  if (io->sst_partitioner_factory != nullptr) return true;
-  if (HasHostOnlyFileCutRule(c)) return true;
-  if (BlockBasedOptionsOf(c) == nullptr) return true;
+  if (io->compaction_filter != nullptr) return "compaction filter object (not a factory)";
+  if (io->compaction_filter_factory != nullptr && DeviceFilterOf(c) == B200C_FILTER_NONE) return "compaction filter the device does not implement";
+  if (io->user_comparator != BytewiseComparator()) return "comparator other than the bytewise one (incl. user-defined timestamps)";
+  if (c->output_compression() != kNoCompression) return "block compression";
+  if (io->sst_partitioner_factory != nullptr) return "sst partitioner";
+  if (io->allow_ingest_behind) return "allow_ingest_behind (no sequence-number zeroing, compaction_iterator.cc:1299-1304)";
+  if (io->preclude_last_level_data_seconds > 0 || io->preserve_internal_time_seconds > 0)
+    return "seqno-to-time preservation (preserve_time_min_seqno_, per-key placement)";
+  if (c->SupportsPerKeyPlacement()) return "per-key placement (penultimate level output)";
+  if (mo->enable_blob_files) return "blob files (large values are extracted while compacting)";
+  if (!io->table_properties_collector_factories.empty()) return "user table-properties collectors";
+  if (mo->sample_for_compression > 0) return "sample_for_compression (adds table properties)";
+  if (HasHostOnlyFileCutRule(c)) return "an output-file cut rule the device does not evaluate (TTL cut / round-robin split)";
   const BlockBasedTableOptions* t = BlockBasedOptionsOf(c);
-  if (DeviceBloomMillibits(c, t) < 0 || t->index_type != BlockBasedTableOptions::kBinarySearch ||
-      t->data_block_index_type != BlockBasedTableOptions::kDataBlockBinarySearch || t->index_block_restart_interval != 1 ||
-      t->block_align || t->format_version < 3 || t->format_version > 5 ||
+  if (t == nullptr) return "table factory other than BlockBasedTable";
+  if (DeviceBloomMillibits(c, t) < 0) return "filter policy other than a full Bloom filter over whole keys (format_version >= 5)";
+  if (t->index_type != BlockBasedTableOptions::kBinarySearch || t->data_block_index_type != BlockBasedTableOptions::kDataBlockBinarySearch ||
+      t->index_block_restart_interval != 1 || t->block_align || t->format_version < 3 || t->format_version > 5 ||
       (t->checksum != kXXH3 && t->checksum != kCRC32c && t->checksum != kNoChecksum))
-    return true;
+    return "BlockBasedTableOptions outside the device's format subset";
   size_t runs = 0;
   for (const auto& lvl : *c->inputs()) {
     runs += lvl.files.size();
     for (const FileMetaData* fm : lvl.files)
-      if (fm->num_range_deletions) return true;
+      if (fm->num_range_deletions) return "range tombstones in an input file";
   }
-  return runs == 0 || runs > 64;
+  if (runs == 0) return "no input files";
+  if (runs > 64) return "more than 64 input files";
+  return nullptr;
+}
+
+bool B200CompactionExecutorFactory::ShouldRunLocal(const Compaction* c) const {
+  const char* why = WhyLocal(c);
+  if (getenv("B200C_PLUGIN_TRACE") != nullptr)  // one line per job: where it runs and why
+    fprintf(stderr, "B200Compact: job L%d -> L%d: %s%s\n", c->start_level(), c->output_level(), why ? why : "device-eligible",
+            have_device_ ? "" : " [no CUDA device: runs locally]");
+  return !have_device_ || why != nullptr;
 }
 bool B200CompactionExecutorFactory::AllowFallbackToLocal() const { return opt_.allow_fallback_to_local; }
 CompactionExecutor* B200CompactionExecutorFactory::NewExecutor(const Compaction* c) const {
