@@ -1,0 +1,128 @@
+/* tests/native/mock_b200c.c -- test double of libb200c.so for the executor plugin (test infrastructure).  It claims one device, records
+ * the b200c_params the plugin hands to b200c_job_create and the inputs it adds as one JSON object per job (file named by the environment
+ * variable B200C_MOCK_DUMP, appended), and then refuses to run with B200C_ERR_NOT_SUPPORTED -- so a DB opened with
+ * `executor=b200+fallback` goes on to compact locally.  tests/test_plugin_params.py compares what the plugin translated
+ * (CompactionParams + BlockBasedTableOptions -> b200c_params) with what the reference itself reports about the same job. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b200c.h"
+
+struct b200c_job {
+  FILE* f;
+  int n_inputs;
+};
+static const char* g_err = "";
+
+static void hex(FILE* f, const void* p, uint32_t n) {
+  const unsigned char* b = (const unsigned char*)p;
+  fputc('"', f);
+  for (uint32_t i = 0; i < n; i++) fprintf(f, "%02x", b[i]);
+  fputc('"', f);
+}
+static void str(FILE* f, const char* s) {
+  fputc('"', f);
+  for (; s && *s; s++) {
+    if (*s == '"' || *s == '\\') fputc('\\', f);
+    fputc(*s, f);
+  }
+  fputc('"', f);
+}
+
+const char* b200c_last_error(void) { return g_err; }
+uint32_t b200c_abi_version(void) { return B200C_ABI_VERSION; }
+int b200c_device_count(void) { return 1; }
+void b200c_params_init(b200c_params* p) { /* the defaults of the real library (api.cu) */
+  memset(p, 0, sizeof *p);
+  p->abi_version = B200C_ABI_VERSION;
+  p->output_level = 1;
+  p->max_output_file_size = 64ull << 20;
+  p->block_size = 4096;
+  p->block_size_deviation = 10;
+  p->block_restart_interval = 16;
+  p->index_block_restart_interval = 1;
+  p->format_version = 5;
+  p->checksum = B200C_CKSUM_XXH3;
+  p->verify_input_checksums = 1;
+  p->level_compaction_dynamic_file_size = 1;
+  p->column_family_name = "default";
+  p->output_mem = B200C_MEM_HOST;
+}
+int b200c_job_create(const b200c_params* p, b200c_job** out) {
+  const char* path = getenv("B200C_MOCK_DUMP");
+  b200c_job* j = (b200c_job*)calloc(1, sizeof *j);
+  j->f = path ? fopen(path, "a") : NULL;
+  if (j->f) {
+    FILE* f = j->f;
+    fprintf(f, "{\"abi_version\": %u, \"device\": %d, \"output_level\": %d, \"bottommost_level\": %d, \"max_output_file_size\": %llu, ",
+            p->abi_version, p->device, p->output_level, p->bottommost_level, (unsigned long long)p->max_output_file_size);
+    fprintf(f, "\"block_size\": %u, \"block_size_deviation\": %u, \"block_restart_interval\": %u, \"index_block_restart_interval\": %u, "
+               "\"format_version\": %u, \"checksum\": %u, \"verify_input_checksums\": %u, ",
+            p->block_size, p->block_size_deviation, p->block_restart_interval, p->index_block_restart_interval, p->format_version,
+            p->checksum, p->verify_input_checksums);
+    fprintf(f, "\"snapshots\": [");
+    for (uint32_t i = 0; i < p->num_snapshots; i++) fprintf(f, "%s%llu", i ? ", " : "", (unsigned long long)p->snapshots[i]);
+    fprintf(f, "], \"column_family_id\": %u, \"column_family_name\": ", p->column_family_id);
+    str(f, p->column_family_name);
+    fprintf(f, ", \"db_id\": ");
+    str(f, p->db_id);
+    fprintf(f, ", \"db_session_id\": ");
+    str(f, p->db_session_id);
+    fprintf(f, ", \"db_host_id\": ");
+    str(f, p->db_host_id);
+    fprintf(f, ", \"creation_time\": %llu, \"oldest_key_time\": %llu, \"file_creation_times\": [", (unsigned long long)p->creation_time,
+            (unsigned long long)p->oldest_key_time);
+    for (uint32_t i = 0; i < p->num_file_creation_times; i++)
+      fprintf(f, "%s%llu", i ? ", " : "", (unsigned long long)p->file_creation_times[i]);
+    fprintf(f, "], \"first_file_number\": %llu, \"output_mem\": %u, \"compaction_filter\": %u, \"ttl\": %d, \"ttl_now\": %lld, ",
+            (unsigned long long)p->first_file_number, p->output_mem, p->compaction_filter, p->ttl, (long long)p->ttl_now);
+    fprintf(f, "\"grandparents\": [");
+    for (uint32_t i = 0; i < p->num_grandparents; i++) {
+      fprintf(f, "%s{\"smallestkey\": ", i ? ", " : "");
+      hex(f, p->grandparents[i].smallest_user_key, p->grandparents[i].smallest_len);
+      fprintf(f, ", \"largestkey\": ");
+      hex(f, p->grandparents[i].largest_user_key, p->grandparents[i].largest_len);
+      fprintf(f, ", \"size\": %llu}", (unsigned long long)p->grandparents[i].file_size);
+    }
+    fprintf(f, "], \"level_compaction_dynamic_file_size\": %u, \"max_compaction_bytes\": %llu, \"target_output_file_size\": %llu, ",
+            p->level_compaction_dynamic_file_size, (unsigned long long)p->max_compaction_bytes,
+            (unsigned long long)p->target_output_file_size);
+    fprintf(f, "\"has_range_start\": %u, \"has_range_end\": %u, \"paranoid_file_checks\": %u, \"bloom_millibits_per_key\": %u, \"inputs\": [",
+            p->has_range_start, p->has_range_end, p->paranoid_file_checks, p->bloom_millibits_per_key);
+  }
+  *out = j;
+  return B200C_OK;
+}
+int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const void* data, uint64_t len, int mem_kind) {
+  (void)data;
+  if (j->f)
+    fprintf(j->f, "%s{\"level\": %d, \"file_number\": %llu, \"len\": %llu, \"mem_kind\": %d}", j->n_inputs ? ", " : "", level,
+            (unsigned long long)file_number, (unsigned long long)len, mem_kind);
+  j->n_inputs++;
+  return B200C_OK;
+}
+int b200c_job_run(b200c_job* j) {
+  (void)j;
+  g_err = "mock library: records the job and leaves it to the reference";
+  return B200C_ERR_NOT_SUPPORTED;
+}
+int b200c_job_output_count(const b200c_job* j) { (void)j; return 0; }
+int b200c_job_output_meta(const b200c_job* j, int i, b200c_file_meta* m) { (void)j; (void)i; (void)m; return B200C_ERR_STATE; }
+int b200c_job_output_data(b200c_job* j, int i, const void** d, uint64_t* l) { (void)j; (void)i; (void)d; (void)l; return B200C_ERR_STATE; }
+int b200c_job_output_read(b200c_job* j, int i, void* d, uint64_t c) { (void)j; (void)i; (void)d; (void)c; return B200C_ERR_STATE; }
+int b200c_job_get_stats(const b200c_job* j, b200c_stats* s) { (void)j; memset(s, 0, sizeof *s); return B200C_OK; }
+void b200c_job_destroy(b200c_job* j) {
+  if (!j) return;
+  if (j->f) {
+    fprintf(j->f, "]}\n");
+    fclose(j->f);
+  }
+  free(j);
+}
+int b200c_job_run_until(b200c_job* j, int stage) { (void)stage; return b200c_job_run(j); }
+int b200c_job_debug_read(b200c_job* j, int w, int r, void* d, uint64_t c, uint64_t* l) { (void)j; (void)w; (void)r; (void)d; (void)c; (void)l; return B200C_ERR_STATE; }
+int b200c_job_kernel_time_count(const b200c_job* j) { (void)j; return 0; }
+int b200c_job_kernel_time(const b200c_job* j, int i, const char** n, double* us) { (void)j; (void)i; (void)n; (void)us; return B200C_ERR_STATE; }
+int b200c_job_encode_columns(b200c_job* j, uint64_t n, const void* a, const void* b, const void* c, const void* d) { (void)j; (void)n; (void)a; (void)b; (void)c; (void)d; return B200C_ERR_NOT_SUPPORTED; }
+int b200c_block_checksums(int dev, uint32_t t, const void* h, const uint64_t* o, uint32_t n, uint8_t lb, uint32_t* out) { (void)dev; (void)t; (void)h; (void)o; (void)n; (void)lb; (void)out; return B200C_ERR_NO_DEVICE; }

@@ -162,8 +162,8 @@ class B200CompactionExecutor : public CompactionExecutor {
     bp.format_version = bbt->format_version;
     bp.checksum = (uint32_t)bbt->checksum;
     bp.verify_input_checksums = opt_.verify_input_checksums;
-    bp.paranoid_file_checks = p.paranoid_file_checks;
-    bp.bloom_millibits_per_key = (uint32_t)std::max(0, DeviceBloomMillibits(c_, bbt));  // RunRemote cannot hash what it did not write (compaction_job.cc:1065-1068)
+    bp.paranoid_file_checks = p.paranoid_file_checks;  // RunRemote cannot hash what it did not write (compaction_job.cc:1065-1068)
+    bp.bloom_millibits_per_key = (uint32_t)std::max(0, DeviceBloomMillibits(c_, bbt));
     std::vector<uint64_t> snaps;
     if (p.existing_snapshots) snaps.assign(p.existing_snapshots->begin(), p.existing_snapshots->end());
     bp.snapshots = snaps.data();
