@@ -2,16 +2,27 @@
  * the b200c_params the plugin hands to b200c_job_create and the inputs it adds as one JSON object per job (file named by the environment
  * variable B200C_MOCK_DUMP, appended), and then refuses to run with B200C_ERR_NOT_SUPPORTED -- so a DB opened with
  * `executor=b200+fallback` goes on to compact locally.  tests/test_plugin_params.py compares what the plugin translated
- * (CompactionParams + BlockBasedTableOptions -> b200c_params) with what the reference itself reports about the same job. */
+ * (CompactionParams + BlockBasedTableOptions -> b200c_params) with what the reference itself reports about the same job.
+ *
+ * Second mode, B200C_MOCK_OUTPUTS=<dir>: b200c_job_run succeeds and the job's outputs are the files of <dir> as listed in <dir>/meta.txt
+ * (written by tests/test_plugin_results.py from a run of the unmodified reference on the same data) -- a stand-in for a device that
+ * produced exactly the reference's files, so that the plugin's result path (output directory, FileMinMeta, statistics) and RunRemote's
+ * installation of the files can be exercised on the CPU.  No compaction logic of any kind lives here. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "b200c.h"
 
+#define MOCK_MAX_OUT 256
 struct b200c_job {
   FILE* f;
   int n_inputs;
+  uint64_t first_file_number;
+  int ran, n_out;
+  b200c_file_meta meta[MOCK_MAX_OUT];
+  unsigned char* data[MOCK_MAX_OUT];
+  b200c_stats stats;
 };
 static const char* g_err = "";
 
@@ -91,8 +102,73 @@ int b200c_job_create(const b200c_params* p, b200c_job** out) {
     fprintf(f, "\"has_range_start\": %u, \"has_range_end\": %u, \"paranoid_file_checks\": %u, \"bloom_millibits_per_key\": %u, \"inputs\": [",
             p->has_range_start, p->has_range_end, p->paranoid_file_checks, p->bloom_millibits_per_key);
   }
+  j->first_file_number = p->first_file_number;
   *out = j;
   return B200C_OK;
+}
+static uint32_t unhex(const char* h, uint8_t* out) {
+  uint32_t n = 0;
+  for (; h[0] && h[1]; h += 2) {
+    unsigned v;
+    sscanf(h, "%2x", &v);
+    out[n++] = (uint8_t)v;
+  }
+  return n;
+}
+static int load_canned(b200c_job* j, const char* dir) {
+  char path[4096], name[256], sk[256], lk[256];
+  snprintf(path, sizeof path, "%s/meta.txt", dir);
+  FILE* m = fopen(path, "r");
+  if (!m) return 0;
+  unsigned long long v[12];
+  while (j->n_out < MOCK_MAX_OUT && fscanf(m, "%255s", name) == 1) {
+    if (strcmp(name, "STATS") == 0) {
+      if (fscanf(m, "%llu %llu %llu %llu %llu %llu %llu %llu %llu %llu", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8], &v[9]) != 10) break;
+      j->stats.num_input_records = v[0];
+      j->stats.num_output_records = v[1];
+      j->stats.num_input_deletion_records = v[2];
+      j->stats.num_records_replaced = v[3];
+      j->stats.num_expired_deletion_records = v[4];
+      j->stats.total_input_raw_key_bytes = v[5];
+      j->stats.total_input_raw_value_bytes = v[6];
+      j->stats.total_input_bytes = v[7];
+      j->stats.total_output_bytes = v[8];
+      j->stats.num_input_files = v[9];
+      continue;
+    }
+    if (fscanf(m, "%255s %255s %llu %llu %llu %llu %llu %llu %llu %llu %llu", sk, lk, &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8]) != 11) break;
+    b200c_file_meta* fm = &j->meta[j->n_out];
+    memset(fm, 0, sizeof *fm);
+    snprintf(path, sizeof path, "%s/%s", dir, name);
+    FILE* f = fopen(path, "rb");
+    if (!f) break;
+    fseek(f, 0, SEEK_END);
+    long len = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    j->data[j->n_out] = (unsigned char*)malloc((size_t)len);
+    if (fread(j->data[j->n_out], 1, (size_t)len, f) != (size_t)len) {
+      fclose(f);
+      break;
+    }
+    fclose(f);
+    fm->file_number = j->first_file_number + (uint64_t)j->n_out;
+    fm->file_size = (uint64_t)len;
+    fm->smallest_ikey_len = unhex(sk, fm->smallest_ikey);
+    fm->largest_ikey_len = unhex(lk, fm->largest_ikey);
+    fm->smallest_seqno = v[0];
+    fm->largest_seqno = v[1];
+    fm->num_entries = v[2];
+    fm->num_deletions = v[3];
+    fm->raw_key_size = v[4];
+    fm->raw_value_size = v[5];
+    fm->num_data_blocks = v[6];
+    fm->data_size = v[7];
+    fm->index_size = v[8];
+    j->n_out++;
+  }
+  fclose(m);
+  j->stats.num_output_files = (uint64_t)j->n_out;
+  return 1;
 }
 int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const void* data, uint64_t len, int mem_kind) {
   (void)data;
@@ -103,21 +179,42 @@ int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const voi
   return B200C_OK;
 }
 int b200c_job_run(b200c_job* j) {
-  (void)j;
+  const char* dir = getenv("B200C_MOCK_OUTPUTS");
+  if (dir && load_canned(j, dir)) {
+    j->ran = 1;
+    return B200C_OK;
+  }
   g_err = "mock library: records the job and leaves it to the reference";
   return B200C_ERR_NOT_SUPPORTED;
 }
-int b200c_job_output_count(const b200c_job* j) { (void)j; return 0; }
-int b200c_job_output_meta(const b200c_job* j, int i, b200c_file_meta* m) { (void)j; (void)i; (void)m; return B200C_ERR_STATE; }
-int b200c_job_output_data(b200c_job* j, int i, const void** d, uint64_t* l) { (void)j; (void)i; (void)d; (void)l; return B200C_ERR_STATE; }
-int b200c_job_output_read(b200c_job* j, int i, void* d, uint64_t c) { (void)j; (void)i; (void)d; (void)c; return B200C_ERR_STATE; }
-int b200c_job_get_stats(const b200c_job* j, b200c_stats* s) { (void)j; memset(s, 0, sizeof *s); return B200C_OK; }
+int b200c_job_output_count(const b200c_job* j) { return j->ran ? j->n_out : 0; }
+int b200c_job_output_meta(const b200c_job* j, int i, b200c_file_meta* m) {
+  if (!j->ran || i < 0 || i >= j->n_out) return B200C_ERR_STATE;
+  *m = j->meta[i];
+  return B200C_OK;
+}
+int b200c_job_output_data(b200c_job* j, int i, const void** d, uint64_t* l) {
+  if (!j->ran || i < 0 || i >= j->n_out) return B200C_ERR_STATE;
+  *d = j->data[i];
+  *l = j->meta[i].file_size;
+  return B200C_OK;
+}
+int b200c_job_output_read(b200c_job* j, int i, void* d, uint64_t c) {
+  if (!j->ran || i < 0 || i >= j->n_out || c < j->meta[i].file_size) return B200C_ERR_STATE;
+  memcpy(d, j->data[i], j->meta[i].file_size);
+  return B200C_OK;
+}
+int b200c_job_get_stats(const b200c_job* j, b200c_stats* s) {
+  *s = j->stats;
+  return B200C_OK;
+}
 void b200c_job_destroy(b200c_job* j) {
   if (!j) return;
   if (j->f) {
     fprintf(j->f, "]}\n");
     fclose(j->f);
   }
+  for (int i = 0; i < j->n_out; i++) free(j->data[i]);
   free(j);
 }
 int b200c_job_run_until(b200c_job* j, int stage) { (void)stage; return b200c_job_run(j); }
