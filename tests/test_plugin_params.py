@@ -81,3 +81,15 @@ def test_grandparents_of_a_picker_built_job_reach_the_c_abi(seed, n):
     assert len(j["grandparents"]) >= 2
     assert (j["max_compaction_bytes"], j["target_output_file_size"]) == (man["max_compaction_bytes"], man["target_output_file_size"])
     assert j["level_compaction_dynamic_file_size"] == int(man["level_compaction_dynamic_file_size"])
+
+
+def test_a_refused_job_without_fallback_fails_with_the_library_message():
+    """AllowFallbackToLocal() == false: the executor's NotSupported status (with the library's own message) is the job's status"""
+    ops, opts = S.ALL["basic_bottommost"]()
+    with tempfile.TemporaryDirectory(prefix="b200c_mock_") as d:
+        with open(os.path.join(d, "ops.bin"), "wb") as f:
+            f.write(ops.bytes())
+        args = [MOCK_BIN, os.path.join(d, "ops.bin"), os.path.join(d, "w"), "executor=b200"] + [f"{k}={v}" for k, v in opts.items()]
+        r = subprocess.run(args, capture_output=True, text=True, env=dict(os.environ, B200C_MOCK_DUMP=os.path.join(d, "dump.jsonl")))
+    assert r.returncode != 0
+    assert "mock library: records the job" in r.stderr and "Not implemented" in r.stderr  # Status::NotSupported prints as "Not implemented"
