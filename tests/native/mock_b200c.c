@@ -180,6 +180,11 @@ int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const voi
 }
 int b200c_job_run(b200c_job* j) {
   const char* dir = getenv("B200C_MOCK_OUTPUTS");
+  const char* failcode = getenv("B200C_MOCK_FAIL");  /* third mode: fail the run with this enum b200c_status */
+  if (failcode) {
+    g_err = "mock library: injected failure";
+    return atoi(failcode);
+  }
   if (dir && load_canned(j, dir)) {
     j->ran = 1;
     return B200C_OK;

@@ -93,3 +93,17 @@ def test_a_refused_job_without_fallback_fails_with_the_library_message():
         r = subprocess.run(args, capture_output=True, text=True, env=dict(os.environ, B200C_MOCK_DUMP=os.path.join(d, "dump.jsonl")))
     assert r.returncode != 0
     assert "mock library: records the job" in r.stderr and "Not implemented" in r.stderr  # Status::NotSupported prints as "Not implemented"
+
+
+@pytest.mark.parametrize("code,status_text", [(4, "Corruption"), (1, "Invalid argument"), (6, "Memory limit"), (3, "Operation aborted"),
+                                              (2, "Operation aborted")])
+def test_library_status_codes_become_the_reference_statuses(code, status_text):
+    """FromB200(): enum b200c_status -> Status; the job fails with that status and the library's message"""
+    ops, opts = S.ALL["tiny"]()
+    with tempfile.TemporaryDirectory(prefix="b200c_mock_") as d:
+        with open(os.path.join(d, "ops.bin"), "wb") as f:
+            f.write(ops.bytes())
+        args = [MOCK_BIN, os.path.join(d, "ops.bin"), os.path.join(d, "w"), "executor=b200"] + [f"{k}={v}" for k, v in opts.items()]
+        r = subprocess.run(args, capture_output=True, text=True, env=dict(os.environ, B200C_MOCK_FAIL=str(code)))
+    assert r.returncode != 0
+    assert status_text in r.stderr and "injected failure" in r.stderr, r.stderr[-500:]
