@@ -23,15 +23,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # name: (k runs, raw KV bytes per run, value bytes, overlap, deletion fraction, bottommost)
-    "cfg2": dict(k=8, run_bytes=256 << 20, vlen=32, overlap=0.0, del_frac=0.0, bottommost=False,
-                 desc="8-way merge, 8x256MiB synthetic sorted runs, 16B keys / 32B values"),
-    "cfg3": dict(k=16, run_bytes=256 << 20, vlen=256, overlap=0.3, del_frac=0.1, bottommost=True,
-                 desc="16-way merge, 30% key overlap + 10% tombstones, 16B keys / 256B values"),
-    "cfg5": dict(k=4, run_bytes=64 << 20, vlen=128, overlap=0.0, del_frac=0.0, bottommost=False,
-                 desc="4-way x 64MiB sub-compaction, 16B keys / 128B values"),
-}
+from toplingdb_b200.synth_workloads import BENCH_JOB, WORKLOADS  # noqa: E402  (no torch import: the reference arm needs none)
 
 
 def peaks():
@@ -152,15 +144,11 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOADS[args.workload]
-    entry = 24 + w["vlen"]
-    n_run = int(w["run_bytes"] * args.scale) // entry
-    n_total = n_run * w["k"]
-    key_base = sharding.key_range_base(rank, n_total)  # disjoint, ordered key ranges per rank = independent sub-compactions
-    images, kv_bytes = synth.stage_runs(n_total, w["k"], w["vlen"], key_base=key_base, seed=2 + rank, overlap=w["overlap"],
-                                        del_frac=w["del_frac"], device_index=local)
+    # ranks hold disjoint, ordered key ranges = independent sub-compactions; tests/test_gpu_fullsize.py stages the same job (rank 0) and
+    # compares every output byte with the CPU oracle
+    images, kv_bytes = synth.stage_bench_inputs(args.workload, rank=rank, scale=args.scale, device_index=local)
     in_bytes = sum(int(t.numel()) for t in images)
-    common = dict(device=local, output_level=1, bottommost_level=w["bottommost"], max_output_file_size=64 << 20,
-                  file_creation_times=[1700000000], first_file_number=1, db_id="bench", db_session_id="BENCH", db_host_id="b200")
+    common = dict(device=local, bottommost_level=w["bottommost"], **BENCH_JOB)
     job = T.CompactionJob(output_mem="device", profile=1, **common)
     for i, img in enumerate(images):
         job.add_input(img, level=0, file_number=100 + i)
@@ -208,8 +196,17 @@ def main():
         step_s, wall_s = tt.tolist()
     value = world * kv_bytes / step_s / 1e6
 
-    # size-independent checks at full size (untimed): entry conservation, ordered non-overlapping files
-    assert st.num_input_records == sum(1 for _ in [0]) * st.num_input_records
+    # untimed checks: the outputs of the last step hash to the digest the CPU oracle produced for this very job (committed by
+    # tools/make_bench_digests.py, re-derived by tests/test_gpu_fullsize.py on every GPU test run); entry conservation; file order
+    digest = synth.outputs_digest(job)
+    dkey = f"{args.workload}:rank{rank}:scale{args.scale}"
+    want_digest = None
+    try:
+        want_digest = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_digests.json"))).get(dkey)
+    except Exception:
+        pass
+    if want_digest is not None and want_digest != digest:
+        raise SystemExit(f"bench outputs differ from the oracle's ({dkey}): {digest} != {want_digest}")
     if w["overlap"] == 0 and w["del_frac"] == 0:
         assert st.num_output_records == st.num_input_records, (st.num_output_records, st.num_input_records)
     prev = None
@@ -339,6 +336,7 @@ def main():
                            "parallelism": f"{world} independent sub-compactions, 1 per GPU" if world > 1 else "1 GPU"},
                 "wall_ms_per_step": round(wall_s * 1e3, 3), "e2e": e2e, "gpu_launches": int(launches) * args.steps, "roofline": roofline,
                 "kernels": kern, "cpu_baseline": cpu, "clocks": sampler.summary(),
+                "output_digest": {"sha256": digest, "oracle": want_digest, "matches_oracle": (want_digest == digest) if want_digest else None},
                 "stage_us": {"decode": round(st.decode_us, 1), "merge": round(st.merge_us, 1), "encode": round(st.encode_us, 1)}}
         print(json.dumps(line))
     if world > 1:

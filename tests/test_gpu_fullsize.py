@@ -1,5 +1,7 @@
-"""BASELINE.json-size jobs (GPU box): too large for the CPU oracle to run in full, so the checks are the
-size-independent properties of the path plus oracle spot checks on slices.
+"""BASELINE.json-size jobs (GPU box).  Byte-exact: the CPU oracle compacts the SAME full-size input images (cfg2, cfg3 with
+bottommost on / off, cfg5 -- the jobs bench.py times, staged by the same function) and every output file, FileMetaData and the
+statistics must be equal; the bench inputs themselves must equal what the oracle's table builder writes for the same entries.
+Plus the size-independent properties of the path:
 
   * conservation: with disjoint keys (cfg2) every input record comes out exactly once; with overlap + tombstones (cfg3)
     num_input = num_output + hidden + obsolete tombstones, as CompactionJobStats accounts them (compaction_job.cc:1290-1322)
@@ -168,3 +170,136 @@ def test_cfg1_shape_against_the_reference_itself():
         assert getattr(st, k) == man["stats"][k], k
     for m, want in zip(metas, man["outputs"]):
         assert (m.file_size, m.num_entries, m.num_deletions) == (want["size"], want["num_entries"], want["num_deletions"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Byte-exact against the CPU oracle at the benchmarked sizes (the jobs bench.py times: same staging function, same parameters)
+def _bench_params(bottommost):
+    from toplingdb_b200 import synth
+    return H.Params(bottommost_level=bool(bottommost), creation_time=0, **synth.BENCH_JOB)
+
+
+def _compare_with_oracle(workload, bottommost, scale=1.0):
+    import numpy as np
+    from gpu_harness import job_from_params
+    from toplingdb_b200 import synth
+    images, _ = synth.stage_bench_inputs(workload, rank=0, scale=scale)
+    p = _bench_params(bottommost)
+    job = job_from_params(p, output_mem="device")
+    for i, img in enumerate(images):
+        job.add_input(img, level=0, file_number=100 + i)
+    job.run()
+    st = job.stats()
+    n = job.output_count()
+    got = []
+    for i in range(n):
+        m = job.output_meta(i)
+        t = torch.empty(m.file_size, dtype=torch.uint8, device="cuda")
+        job.output_read_into(i, t)
+        got.append((t.cpu().numpy(), m))
+    digest = synth.outputs_digest(job)
+    job.close()
+    host_inputs = [t.cpu().numpy().tobytes() for t in images]
+    del images
+    torch.cuda.empty_cache()
+    ofiles, ometas, ost = H.oracle_compact(p, host_inputs)
+    del host_inputs
+    assert n == len(ofiles), (n, len(ofiles))
+    for i, ((a, m), b, om) in enumerate(zip(got, ofiles, ometas)):
+        bb = np.frombuffer(b, dtype=np.uint8)
+        assert a.size == bb.size, f"file {i}: {a.size} vs oracle {bb.size} bytes"
+        if not np.array_equal(a, bb):
+            at = int(np.flatnonzero(a != bb)[0])
+            raise AssertionError(f"{workload} bottommost={bottommost}: output {i} differs from the oracle at byte {at} of {a.size}")
+        assert (m.file_size, m.num_entries, m.num_deletions, m.raw_key_size, m.raw_value_size, m.num_data_blocks, m.smallest_seqno,
+                m.largest_seqno) == (om.file_size, om.num_entries, om.num_deletions, om.raw_key_size, om.raw_value_size, om.num_data_blocks,
+                                     om.smallest_seqno, om.largest_seqno), f"FileMetaData of output {i}"
+        assert bytes(m.smallest_ikey[:m.smallest_ikey_len]) == bytes(om.smallest[:om.smallest_len])
+        assert bytes(m.largest_ikey[:m.largest_ikey_len]) == bytes(om.largest[:om.largest_len])
+    for k in H.STAT_KEYS:
+        assert getattr(st, k) == getattr(ost, k), k
+    assert digest == synth.files_digest(ofiles)  # the digest bench.py prints is the digest of the oracle's files
+    return digest
+
+
+def test_cfg2_full_size_bytes_equal_oracle():
+    """configs[1] as bench.py runs it: 8 x 256 MiB, 16 B / 32 B; every output byte against the CPU oracle."""
+    d = _compare_with_oracle("cfg2", bottommost=False)
+    _check_committed_digest("cfg2", d)
+
+
+@pytest.mark.parametrize("bottommost", [True, False])
+def test_cfg3_full_size_bytes_equal_oracle(bottommost):
+    """configs[2]: 16 x 256 MiB, 30 % overlap, 10 % tombstones, 16 B / 256 B; bottommost on and off."""
+    d = _compare_with_oracle("cfg3", bottommost=bottommost)
+    if bottommost:
+        _check_committed_digest("cfg3", d)
+
+
+def test_cfg5_full_size_bytes_equal_oracle():
+    """one of configs[4]'s sub-compactions: 4 x 64 MiB, 16 B / 128 B."""
+    d = _compare_with_oracle("cfg5", bottommost=False)
+    _check_committed_digest("cfg5", d)
+
+
+def _check_committed_digest(workload, digest):
+    """tests/golden/bench_digests.json holds the oracle's digests of the bench jobs (rank 0, scale 1), written by
+    tools/make_bench_digests.py on a GPU box; bench.py compares its own outputs with them.  A stale file must not pass silently."""
+    import json
+    import os
+    path = os.path.join(H.GOLDEN_DIR, "bench_digests.json")
+    if os.path.exists(path):
+        want = json.load(open(path)).get(f"{workload}:rank0:scale1.0")
+        if want is not None:
+            assert want == digest, f"tests/golden/bench_digests.json is stale for {workload}: regenerate with tools/make_bench_digests.py"
+
+
+def _run_kvstream(n_total, k, r, vlen, key_base, seed, overlap=0.0, del_frac=0.0):
+    """kv stream (helpers.kvstream format) of run r as synth.stage_runs encodes it, assembled on the host with numpy"""
+    import numpy as np
+    from toplingdb_b200 import synth
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    values = torch.randint(0, 256, (max(1, n_total * vlen),), dtype=torch.uint8, device=dev, generator=g)
+    n, pfx, tr, vref, meta = synth.make_run_columns(n_total, k, r, vlen, key_base, values, overlap, del_frac, seed, dev)
+    vl = (meta.to(torch.int64) & ((1 << 27) - 1)).cpu().numpy()
+    voff = (vref - values.data_ptr()).cpu().numpy()
+    hi = pfx[:, 0].cpu().numpy().view(np.uint64).astype(">u8")
+    lo = pfx[:, 1].cpu().numpy().view(np.uint64).astype(">u8")
+    trn = tr.cpu().numpy().view(np.uint64).astype("<u8")
+    vals = values.cpu().numpy()
+    if (vl == vlen).all():
+        rec = np.zeros(n, dtype=[("kl", "<u4"), ("vl", "<u4"), ("hi", ">u8"), ("lo", ">u8"), ("tr", "<u8"), ("v", "u1", (vlen,))])
+        rec["kl"], rec["vl"], rec["hi"], rec["lo"], rec["tr"] = 24, vlen, hi, lo, trn
+        assert (voff % vlen == 0).all()
+        rec["v"] = vals.reshape(-1, vlen)[voff // vlen]
+        return rec.tobytes()
+    out = bytearray()
+    for i in range(n):
+        out += struct.pack("<II", 24, int(vl[i])) + hi[i].tobytes() + lo[i].tobytes() + trn[i].tobytes() + vals[voff[i]:voff[i] + vl[i]].tobytes()
+    return bytes(out)
+
+
+def test_bench_input_images_equal_oracle_built_tables():
+    """The bench inputs are written by the product's own encoder (synth.stage_runs -> b200c_job_encode_columns); an encoder / decoder
+    symmetric bug would be invisible to every round-trip check.  Here each image must equal, byte for byte, the table the oracle's
+    BlockBasedTableBuilder restatement (block_based_table_builder.cc:961-1133) writes for the same entries: one full-size cfg2 run
+    (4.8 M entries, 256 MiB) and a small cfg3-shaped run with overlap substitutions and tombstones."""
+    import numpy as np
+    from toplingdb_b200 import sharding, synth
+    cases = [("cfg2", 1.0, 3), ("cfg3", 1.0 / 64, 0), ("cfg3", 1.0 / 64, 15)]
+    for workload, scale, r in cases:
+        w = synth.WORKLOADS[workload]
+        _, n_total = synth.bench_shape(workload, scale)
+        key_base = sharding.key_range_base(0, n_total)
+        images, _ = synth.stage_runs(n_total, w["k"], w["vlen"], key_base=key_base, seed=2, overlap=w["overlap"], del_frac=w["del_frac"])
+        img = images[r].cpu().numpy()
+        del images
+        torch.cuda.empty_cache()
+        kv = _run_kvstream(n_total, w["k"], r, w["vlen"], key_base, 2, w["overlap"], w["del_frac"])
+        p = H.Params(output_level=0, creation_time=0, db_id="", db_session_id="", db_host_id="", file_creation_times=[1700000000],
+                     first_file_number=1000 + r)
+        want = np.frombuffer(H.oracle_build_sst(p, kv), dtype=np.uint8)
+        assert img.size == want.size, (workload, r, img.size, want.size)
+        assert np.array_equal(img, want), f"{workload} run {r}: staged image differs from the oracle-built table at byte {int(np.flatnonzero(img != want)[0])}"

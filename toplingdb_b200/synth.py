@@ -74,3 +74,50 @@ def stage_runs(n_total, k, vlen, key_base=0, seed=1, overlap=0.0, del_frac=0.0, 
     torch.cuda.synchronize(dev)
     del values
     return images, kv_bytes
+
+
+from .synth_workloads import BENCH_JOB, WORKLOADS  # noqa: E402,F401
+
+
+def bench_shape(workload, scale=1.0):
+    """(entries per run, entries per job) of a bench workload"""
+    w = WORKLOADS[workload]
+    n_run = int(w["run_bytes"] * scale) // (24 + w["vlen"])
+    return n_run, n_run * w["k"]
+
+
+def stage_bench_inputs(workload, rank=0, scale=1.0, device_index=0):
+    """the k input images bench.py compacts on rank `rank` (device resident).  Returns (images, input_kv_bytes)."""
+    from . import sharding
+    w = WORKLOADS[workload]
+    _, n_total = bench_shape(workload, scale)
+    key_base = sharding.key_range_base(rank, n_total)  # disjoint, ordered key ranges per rank = independent sub-compactions
+    return stage_runs(n_total, w["k"], w["vlen"], key_base=key_base, seed=2 + rank, overlap=w["overlap"], del_frac=w["del_frac"],
+                      device_index=device_index)
+
+
+def outputs_digest(job):
+    """sha256 over (file size, file bytes) of every output of a finished job, in order (host side, untimed)"""
+    import hashlib
+    h = hashlib.sha256()
+    for i in range(job.output_count()):
+        m = job.output_meta(i)
+        if job.params.output_mem == 1:  # device images
+            t = torch.empty(m.file_size, dtype=torch.uint8, device=torch.device("cuda", job.params.device))
+            job.output_read_into(i, t)
+            b = t.cpu().numpy()
+        else:
+            b = memoryview(job.output_bytes(i))
+        h.update(m.file_size.to_bytes(8, "little"))
+        h.update(b)
+    return h.hexdigest()
+
+
+def files_digest(files):
+    """the same digest over a list of bytes objects (what the oracle returns)"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in files:
+        h.update(len(f).to_bytes(8, "little"))
+        h.update(f)
+    return h.hexdigest()
