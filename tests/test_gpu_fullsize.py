@@ -276,8 +276,9 @@ def _run_kvstream(n_total, k, r, vlen, key_base, seed, overlap=0.0, del_frac=0.0
         rec["v"] = vals.reshape(-1, vlen)[voff // vlen]
         return rec.tobytes()
     out = bytearray()
+    hib, lob, trb, valb = hi.tobytes(), lo.tobytes(), trn.tobytes(), vals.tobytes()  # array-level tobytes keeps the declared byte order
     for i in range(n):
-        out += struct.pack("<II", 24, int(vl[i])) + hi[i].tobytes() + lo[i].tobytes() + trn[i].tobytes() + vals[voff[i]:voff[i] + vl[i]].tobytes()
+        out += struct.pack("<II", 24, int(vl[i])) + hib[8 * i:8 * i + 8] + lob[8 * i:8 * i + 8] + trb[8 * i:8 * i + 8] + valb[voff[i]:voff[i] + vl[i]]
     return bytes(out)
 
 

@@ -112,11 +112,13 @@ struct b200c_job {
   int stage_done = 0;
   int sms = 148;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;  // side stream (higher priority): serial / small kernels that overlap a bulk kernel on `st`
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evx[4] = {nullptr, nullptr, nullptr, nullptr};  // fork / join points between st and st2
   // device state
   DevBuf files_d, blk_off, blk_size, blk_state, scan_tmp, run_start, small;  // small: err, totals, counters...
   DevBuf dec[4], mrg[4], splits, tile_state, snaps_d;
-  DevBuf esz, eshared, tstat, nxt, disk, rows, tstate, grows, gstate, gflag, idx_contrib, idx_contrib_off, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
+  DevBuf esz, eshared, tstat, nxt, disk, rows, tstate, grows, gstate, gflag, gsync, idx_contrib, idx_contrib_off, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
   uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
   uint32_t nfiles_out = 0;
   std::vector<uint64_t> run_start_h;
@@ -133,8 +135,9 @@ struct b200c_job {
   std::vector<KernelTime> ktimes;
   size_t kt_used = 0;
   // profiling: bracket a named group of launches with events (only when params.profile != 0)
-  void kt_begin(const char* name) {
-    if (!p.profile) return;
+  // names that start with '~' run on the side stream, overlapped with the neighbouring group on the main stream
+  size_t kt_begin(const char* name, cudaStream_t s = nullptr) {
+    if (!p.profile) return 0;
     if (kt_used == ktimes.size()) {
       KernelTime k{name, nullptr, nullptr, 0.f};
       cudaEventCreate(&k.a);
@@ -142,12 +145,12 @@ struct b200c_job {
       ktimes.push_back(k);
     }
     ktimes[kt_used].name = name;
-    cudaEventRecord(ktimes[kt_used].a, st);
+    cudaEventRecord(ktimes[kt_used].a, s ? s : st);
+    return kt_used++;
   }
-  void kt_end() {
+  void kt_end(size_t slot = ~(size_t)0, cudaStream_t s = nullptr) {
     if (!p.profile) return;
-    cudaEventRecord(ktimes[kt_used].b, st);
-    kt_used++;
+    cudaEventRecord(ktimes[slot == ~(size_t)0 ? kt_used - 1 : slot].b, s ? s : st);
   }
 };
 
@@ -360,11 +363,27 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     W.disk = j->disk.as<uint32_t>();
     W.files = j->files_rec.as<FileRec>();
     W.scan_tmp = j->scan_tmp.as<uint64_t>();
+    CU(j->gsync.reserve(8 * egroups + 16));
+    CU(cudaMemsetAsync(j->gsync.p, 0, 8 * egroups + 16, st));
+    W.gdone = j->gsync.as<uint32_t>();
+    W.gready = W.gdone + egroups;
+    // The serial stitch walk runs on the side stream WHILE the tables kernel fills the tile / group rows: each group raises a flag
+    // when its rows are complete and the walk waits on the flags.  Launch order tables -> stitch: tools that serialise kernels
+    // (ncu, compute-sanitizer) then run the producer first.
+    CU(cudaEventRecord(j->evx[0], st));
     j->kt_begin("encode.tables");
     launch_encode_tables(mcols, ep, W, etiles, hc, max_s1, err, st);
     j->kt_end();
-    j->kt_begin("encode.stitch");
-    launch_encode_stitch(mcols, ep, W, etiles, hc, err, st, &launches);
+    CU(cudaStreamWaitEvent(j->st2, j->evx[0], 0));
+    {
+      const size_t slot = j->kt_begin("~encode.stitch", j->st2);
+      launch_encode_stitch(mcols, ep, W, etiles, hc, err, j->st2, &launches);
+      j->kt_end(slot, j->st2);
+    }
+    CU(cudaEventRecord(j->evx[1], j->st2));
+    CU(cudaStreamWaitEvent(st, j->evx[1], 0));
+    j->kt_begin("encode.tilestate");
+    launch_encode_tilestate(mcols, W, etiles, hc, err, st, &launches);
     j->kt_end();
     launches += 1;
     if (P.bloom_millibits_per_key) {  // filter entries per file decide where each file's index block starts
@@ -418,9 +437,17 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     j->kt_begin("encode.blocklist");
     launch_encode_blocklist(mcols, ep, W, etiles, nblocks, err, st);
     j->kt_end();
-    j->kt_begin("encode.filestats");
-    launch_encode_filestats(mcols, W, nfiles, j->sms, st);
-    j->kt_end();
+    // per-file statistics and the index blocks only need the block list: they run on the side stream while the main stream
+    // emits the data blocks (the index block of a file lies behind its data and filter blocks: disjoint bytes)
+    CU(cudaEventRecord(j->evx[2], st));
+    CU(cudaStreamWaitEvent(j->st2, j->evx[2], 0));
+    {
+      const size_t slot = j->kt_begin("~encode.filestats+index", j->st2);
+      launch_encode_filestats(mcols, W, nfiles, j->sms, j->st2);
+      launch_encode_index(mcols, ep, W, nblocks, nfiles, out_base_d, err, j->st2, &launches);
+      j->kt_end(slot, j->st2);
+    }
+    CU(cudaEventRecord(j->evx[3], j->st2));
     j->kt_begin("encode.emit");
     launch_encode_emit(mcols, ep, W, nblocks, out_base_d, err, j->sms, st);
     j->kt_end();
@@ -433,9 +460,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       j->kt_end();
       launches += 2;
     }
-    j->kt_begin("encode.index");
-    launch_encode_index(mcols, ep, W, nblocks, nfiles, out_base_d, err, st, &launches);
-    j->kt_end();
+    CU(cudaStreamWaitEvent(st, j->evx[3], 0));
     {
       int rc = read_small(j, small, h, W.files, &frs);  // sync #3: per-file records
       if (rc) return rc;
@@ -619,7 +644,13 @@ int run_job(b200c_job* j, int until) {
   CU(cudaSetDevice(P.device));
   if (!j->st) {
     CU(cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking));
+    {
+      int prio_lo = 0, prio_hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      CU(cudaStreamCreateWithPriority(&j->st2, cudaStreamNonBlocking, prio_hi));
+    }
     for (auto& e : j->ev) CU(cudaEventCreate(&e));
+    for (auto& e : j->evx) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, P.device));
     j->sms = prop.multiProcessorCount;
@@ -875,7 +906,13 @@ int job_prepare(b200c_job* j) {
   CU(cudaSetDevice(j->p.device));
   if (!j->st) {
     CU(cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking));
+    {
+      int prio_lo = 0, prio_hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      CU(cudaStreamCreateWithPriority(&j->st2, cudaStreamNonBlocking, prio_hi));
+    }
     for (auto& e : j->ev) CU(cudaEventCreate(&e));
+    for (auto& e : j->evx) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, j->p.device));
     j->sms = prop.multiProcessorCount;
@@ -1109,7 +1146,7 @@ void b200c_job_destroy(b200c_job* j) {
   cudaSetDevice(j->p.device);
   DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->small,
                    &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
-                   &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->tstat, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
+                   &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->tstat, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->gsync, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};
   for (DevBuf* b : all) b->release();
   j->gp_keys_d.release();
@@ -1132,6 +1169,9 @@ void b200c_job_destroy(b200c_job* j) {
   }
   for (auto& e : j->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : j->evx)
+    if (e) cudaEventDestroy(e);
+  if (j->st2) cudaStreamDestroy(j->st2);
   if (j->st) cudaStreamDestroy(j->st);
   delete j;
 }

@@ -362,6 +362,49 @@ __device__ __forceinline__ uint32_t next_block(const Window<PT>& w, uint32_t a, 
   return w.at_end ? wlen : 0xffffffffu;
 }
 
+constexpr int kEncGroup = kEncGroupTiles;  // tiles per group
+// loads that must see what OTHER CTAs of a still running kernel wrote (guarded by a flag / counter): L2 only, never a stale L1 line
+__device__ __forceinline__ TileRow ldcg_row(const TileRow* p) {
+  const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p));
+  TileRow r;
+  r.exit = v.x;
+  r.nblk = v.y;
+  r.bytes = (uint64_t)v.z | ((uint64_t)v.w << 32);
+  return r;
+}
+static_assert(sizeof(TileRow) == 16, "TileRow is moved as one 16-byte vector");
+// composes the transfer functions of the tiles [t0, t1) of group g per entry-point candidate (all threads of the CTA)
+__device__ void compose_group(const EncodeWork& wk, uint64_t n, uint64_t g, uint64_t t0, uint64_t t1, uint32_t hc) {
+  const uint64_t gstart = t0 * (uint64_t)kTT;
+  for (uint32_t c = threadIdx.x; c < hc; c += blockDim.x) {
+    uint64_t x = gstart + c, bytes = 0;
+    uint32_t nb = 0;
+    bool bad = false;
+    for (uint64_t t = t0; t < t1 && x < n; t++) {
+      const uint64_t tstart = t * (uint64_t)kTT, tend = (tstart + kTT) < n ? (tstart + kTT) : n;
+      if (x >= tend) continue;  // no block starts in this tile
+      const uint64_t cc = x - tstart;
+      if (cc >= hc) {
+        bad = true;
+        break;
+      }
+      const TileRow r = ldcg_row(&wk.rows[t * hc + cc]);
+      if (r.exit == 0xffffffffu) {
+        bad = true;
+        break;
+      }
+      x = tstart + r.exit;
+      nb += r.nblk;
+      bytes += r.bytes;
+    }
+    TileRow o;
+    o.exit = bad ? 0xffffffffu : (uint32_t)(x - gstart);  // relative to the group start
+    o.nblk = nb;
+    o.bytes = bytes;
+    wk.grows[g * hc + c] = o;
+  }
+}
+
 // per tile: nxt / disk for every block start inside the tile, then the transfer function for hc entry points
 template <typename PT>
 struct TablesSmem {
@@ -429,6 +472,21 @@ encode_tables_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
     wk.rows[tile * hc + c] = r;
   }
   (void)err;
+  // ---- group completion: the last tile CTA of a group of kEncGroup tiles composes the group's transfer function and raises the
+  // group's ready flag; the stitch kernel runs concurrently on its own stream and consumes the groups as they appear
+  __threadfence();  // this thread's nxt / disk / rows stores are visible device-wide before the counter moves
+  __syncthreads();
+  __shared__ uint32_t s_last;
+  const uint64_t g = tile / kEncGroupTiles, ntiles = (n + kTT - 1) / kTT;
+  const uint64_t t0 = g * kEncGroupTiles, t1 = (t0 + kEncGroupTiles) < ntiles ? (t0 + kEncGroupTiles) : ntiles;
+  if (threadIdx.x == 0) s_last = atomicAdd(&wk.gdone[g], 1u) + 1 == (uint32_t)(t1 - t0);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  compose_group(wk, n, g, t0, t1, hc);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicExch(&wk.gready[g], 1u);
 }
 
 // ------------------------------------------------------------------------------------------------ stitch
@@ -611,39 +669,6 @@ __device__ __forceinline__ bool chase_tile(const uint16_t* nxt, const uint32_t* 
   return ok;
 }
 
-constexpr int kEncGroup = 16;  // tiles per group
-__global__ void encode_compose_kernel(EncodeWork wk, uint64_t n, uint64_t ntiles, uint32_t hc) {
-  const uint64_t g = blockIdx.x, t0 = g * kEncGroup, t1 = (t0 + kEncGroup) < ntiles ? (t0 + kEncGroup) : ntiles;
-  const uint64_t gstart = t0 * (uint64_t)kTT;
-  for (uint32_t c = threadIdx.x; c < hc; c += blockDim.x) {
-    uint64_t x = gstart + c, bytes = 0;
-    uint32_t nb = 0;
-    bool bad = false;
-    for (uint64_t t = t0; t < t1 && x < n; t++) {
-      const uint64_t tstart = t * (uint64_t)kTT, tend = (tstart + kTT) < n ? (tstart + kTT) : n;
-      if (x >= tend) continue;  // no block starts in this tile
-      const uint64_t cc = x - tstart;
-      if (cc >= hc) {
-        bad = true;
-        break;
-      }
-      const TileRow r = wk.rows[t * hc + cc];
-      if (r.exit == 0xffffffffu) {
-        bad = true;
-        break;
-      }
-      x = tstart + r.exit;
-      nb += r.nblk;
-      bytes += r.bytes;
-    }
-    TileRow o;
-    o.exit = bad ? 0xffffffffu : (uint32_t)(x - gstart);  // relative to the group start
-    o.nblk = nb;
-    o.bytes = bytes;
-    wk.grows[g * hc + c] = o;
-  }
-}
-
 struct StitchSmem {
   uint16_t nxt[kTT];
   uint32_t disk[kTT];
@@ -655,15 +680,36 @@ struct StitchSmem {
   uint64_t req_idx;       // argument of the request
   uint32_t req;           // 0 none, 1 chase tile req_idx, 2 load group rows from req_idx, 3 load tile rows from req_idx
   uint32_t done;
+  uint32_t refill;        // groups taken by the current group-row refill
 };
-constexpr uint32_t kStitchCacheBytes = 72 * 1024;  // per row cache
+// cooperative global -> shared copy of flag-guarded data (written by CTAs of the concurrently running tables kernel): L2 loads
+template <typename T, int kDepth>
+__device__ __forceinline__ void coop_copy_cg(T* __restrict__ dst, const T* __restrict__ src, uint32_t n) {
+  const uint32_t nt = blockDim.x;
+  for (uint32_t base = 0; base < n; base += kDepth * nt) {
+    T v[kDepth];
+#pragma unroll
+    for (int k = 0; k < kDepth; k++) {
+      const uint32_t i = base + k * nt + threadIdx.x;
+      if (i < n) v[k] = __ldcg(src + i);
+    }
+#pragma unroll
+    for (int k = 0; k < kDepth; k++) {
+      const uint32_t i = base + k * nt + threadIdx.x;
+      if (i < n) dst[i] = v[k];
+    }
+  }
+}
+// The stitch CTA shares the device with the tables kernel (it is launched on its own high-priority stream and needs a free slot on
+// one SM next to two tables CTAs), so its row caches are small: 2 x cache_bytes, sized by the launcher from hc.
 __global__ void __launch_bounds__(kEncThreads)
-encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint64_t ntiles, uint32_t hc, uint32_t* __restrict__ err) {
+encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint64_t ntiles, uint32_t hc, uint32_t cache_bytes,
+                     uint32_t* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   StitchSmem& s = *reinterpret_cast<StitchSmem*>(smem_raw);
   TileRow* gcache = reinterpret_cast<TileRow*>(smem_raw + ((sizeof(StitchSmem) + 15) & ~(size_t)15));
-  TileRow* tcache = gcache + kStitchCacheBytes / sizeof(TileRow);
-  const uint32_t cache_rows = kStitchCacheBytes / sizeof(TileRow) / hc;  // groups / tiles per cache (>= 1: hc <= 2048)
+  TileRow* tcache = gcache + cache_bytes / sizeof(TileRow);
+  const uint32_t cache_rows = cache_bytes / (uint32_t)sizeof(TileRow) / hc;  // groups / tiles per cache (>= 1 by the launcher)
   const uint64_t ngroups = (ntiles + kEncGroup - 1) / kEncGroup;
   if (threadIdx.x == 0) {
     s.st = WalkState{0, 0, 0, 0, 0, 0};
@@ -774,10 +820,24 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
     if (req == 2 || req == 3) {  // refill a row cache
       // group rows: as many as fit (the walk consumes them quickly); tile rows: only the rest of the group being walked
       const uint64_t total = req == 2 ? ngroups : s.tend;
-      const uint32_t cnt = (uint32_t)((total - ridx) < cache_rows ? (total - ridx) : cache_rows);
+      uint32_t cnt = (uint32_t)((total - ridx) < cache_rows ? (total - ridx) : cache_rows);
+      if (req == 2) {
+        // the tables kernel is still running: wait for the first group needed, then take the consecutive groups that are ready too
+        if (threadIdx.x == 0) {
+          volatile uint32_t* rdy = wk.gready;
+          while (rdy[ridx] == 0) __nanosleep(256);
+          uint32_t have = 1;
+          while (have < cnt && rdy[ridx + have] != 0) have++;
+          s.refill = have;
+          __threadfence();
+        }
+        __syncthreads();
+        cnt = s.refill;
+      }
+      // tile rows (req == 3) belong to a group that was ready when its row entered the group cache
       const uint4* src = reinterpret_cast<const uint4*>((req == 2 ? wk.grows : wk.rows) + ridx * hc);
       uint4* dst = reinterpret_cast<uint4*>(req == 2 ? gcache : tcache);
-      coop_copy<uint4, 8>(dst, src, cnt * hc);
+      coop_copy_cg<uint4, 8>(dst, src, cnt * hc);
       if (threadIdx.x == 0) {
         if (req == 2) {
           s.ga = ridx;
@@ -790,8 +850,8 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
     } else if (req == 1) {
       const uint64_t tstart = ridx * (uint64_t)kTT;
       const uint32_t tl = (uint32_t)(((tstart + kTT) < n ? (tstart + kTT) : n) - tstart);
-      coop_copy<uint16_t, 16>(s.nxt, wk.nxt + tstart, tl);
-      coop_copy<uint32_t, 16>(s.disk, wk.disk + tstart, tl);
+      coop_copy_cg<uint16_t, 16>(s.nxt, wk.nxt + tstart, tl);
+      coop_copy_cg<uint32_t, 16>(s.disk, wk.disk + tstart, tl);
       __syncthreads();
       if (threadIdx.x == 0) {
         WalkState st = s.st;
@@ -1899,19 +1959,24 @@ void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nti
 void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st,
                           uint64_t* launches) {
   if (ntiles == 0) return;
-  const uint64_t ngroups = (ntiles + kEncGroup - 1) / kEncGroup;
-  unsigned ct = hc < 1024 ? ((hc + 31) & ~31u) : 1024;
-  encode_compose_kernel<<<(unsigned)ngroups, ct, 0, st>>>(w, m.n, ntiles, hc);
   static PerDeviceFlag attr;
   const uint64_t dev_bit = attr.bit_of_current_device();
-  const size_t smem = ((sizeof(StitchSmem) + 15) & ~(size_t)15) + 2 * (size_t)kStitchCacheBytes;
+  // row caches: at least one group / one tile, 16 KB when that is enough (the CTA then fits next to two tables CTAs)
+  uint32_t cache_bytes = 16 * 1024;
+  while (cache_bytes < hc * (uint32_t)sizeof(TileRow)) cache_bytes *= 2;
+  const size_t smem = ((sizeof(StitchSmem) + 15) & ~(size_t)15) + 2 * (size_t)cache_bytes;
   if (!attr.is_set(dev_bit)) {
-    cudaFuncSetAttribute(encode_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(encode_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr.set(dev_bit);
   }
-  encode_stitch_kernel<<<1, kEncThreads, smem, st>>>(m, ep, w, m.n, ntiles, hc, err);
+  encode_stitch_kernel<<<1, kEncThreads, smem, st>>>(m, ep, w, m.n, ntiles, hc, cache_bytes, err);
+  if (launches) *launches += 1;
+}
+void launch_encode_tilestate(KeyCols m, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st, uint64_t* launches) {
+  if (ntiles == 0) return;
+  const uint64_t ngroups = (ntiles + kEncGroup - 1) / kEncGroup;
   encode_tilestate_kernel<<<(unsigned)((ngroups + 63) / 64), 64, 0, st>>>(w, m.n, ntiles, hc, err);
-  if (launches) *launches += 3;
+  if (launches) *launches += 1;
 }
 void launch_encode_blocklist(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint64_t nblk_cap, uint32_t* err,
                              cudaStream_t st) {

@@ -172,6 +172,9 @@ struct EncodeWork {                  // device scratch owned by the job
   TileRow* grows;       // ngroups x hc: composed transfer functions of kEncGroup tiles (exit relative to the group start)
   TileState* gstate;    // ngroups: state at which the chain enters the group
   uint32_t* gflag;      // ngroups: 1 = the stitch kernel walked this group tile by tile (a file ends inside)
+  uint32_t* gdone;      // ngroups (zeroed): tile CTAs of the tables kernel that finished the group; the last one composes the group row
+  uint32_t* gready;     // ngroups (zeroed): 1 = rows / nxt / disk of the group's tiles and its composed row are complete -- the stitch
+                        // kernel runs CONCURRENTLY with the tables kernel (second stream) and waits on these flags
   TileState* tstate;    // ntiles
   uint64_t* totals;     // [0] = number of blocks, [1] = number of files
   BlockRec* blocks;     // capacity nblk_cap
@@ -188,8 +191,11 @@ struct EncodeWork {                  // device scratch owned by the job
 void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, uint64_t n_cap, cudaStream_t st);
 void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t max_s1, uint32_t* err,
                           cudaStream_t st);
+// stitch: launched on its own stream BEFORE / alongside launch_encode_tables (it consumes groups as their gready flag appears);
+// tilestate: after both have finished
 void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st,
                           uint64_t* launches);
+void launch_encode_tilestate(KeyCols m, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st, uint64_t* launches);
 void launch_encode_blocklist(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint64_t nblk_cap, uint32_t* err,
                              cudaStream_t st);
 void launch_encode_filestats(KeyCols m, EncodeWork w, uint32_t nfiles, int sms, cudaStream_t st);
