@@ -170,7 +170,9 @@ B200C_API void b200c_params_init(b200c_params* p); /* reference defaults (table.
 
 B200C_API int b200c_job_create(const b200c_params* p, b200c_job** out);
 /* Append one sorted run (a whole BlockBasedTable file image).  Order matters exactly as in MakeInputIterator:
- * L0 files newest first, then one run per deeper level.  `data` may be host or device memory (mem_kind). */
+ * L0 files newest first, then one run per deeper level.  `data` may be host or device memory (mem_kind).
+ * Device memory is read by the job's own non-blocking CUDA streams from b200c_job_run() on: whatever produces it (a copy or a
+ * kernel on the caller's stream) must have COMPLETED before the run call -- the library does not join the caller's streams. */
 B200C_API int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const void* data, uint64_t len, int mem_kind);
 /* decode -> k-way merge with the compaction-iterator rules -> encode, all on the device.  Synchronous. */
 B200C_API int b200c_job_run(b200c_job* j);

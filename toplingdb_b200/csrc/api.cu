@@ -20,9 +20,16 @@ using namespace b200c;
 namespace {
 
 thread_local std::string g_err;
+size_t g_last_want = 0;  // size of the last device allocation attempted (diagnostics of an out-of-memory status)
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
+}
+std::string mem_note() {
+  size_t fr = 0, tot = 0;
+  cudaMemGetInfo(&fr, &tot);
+  cudaGetLastError();
+  return " (requested " + std::to_string(g_last_want) + " bytes; device free " + std::to_string(fr) + " of " + std::to_string(tot) + ")";
 }
 #define CU(call)                                                                                                  \
   do {                                                                                                            \
@@ -30,7 +37,7 @@ int fail(int code, const std::string& msg) {
     if (e_ != cudaSuccess) {                                                                                      \
       cudaGetLastError();                                                                                         \
       return fail(e_ == cudaErrorMemoryAllocation ? B200C_ERR_OUT_OF_MEMORY : B200C_ERR_CUDA,                      \
-                  std::string(#call) + ": " + cudaGetErrorString(e_));                                            \
+                  std::string(#call) + ": " + cudaGetErrorString(e_) + (e_ == cudaErrorMemoryAllocation ? mem_note() : ""));  \
     }                                                                                                             \
   } while (0)
 
@@ -43,6 +50,7 @@ struct DevBuf {  // grow-only device allocation, reused across runs of the same 
     p = nullptr;
     cap = 0;
     size_t want = n + (n >> 4) + 256;
+    g_last_want = want;
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -418,6 +426,14 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       off += (cap + 255) & ~255ull;
     }
     base_off[nfiles] = off;
+    if (getenv("B200C_DEBUG_LAYOUT") || off > (1ull << 44)) {
+      fprintf(stderr, "[b200c] layout: n_out=%llu nblocks=%llu nfiles=%u off=%llu hc=%u etiles=%llu\n", (unsigned long long)n_out,
+              (unsigned long long)nblocks, nfiles, (unsigned long long)off, hc, (unsigned long long)etiles);
+      for (uint32_t f = 0; f < nfiles && f < 4; f++)
+        fprintf(stderr, "[b200c]  file %u: first_entry=%llu n_entries=%llu first_block=%llu n_blocks=%llu data_size=%llu filter_bytes=%llu\n", f,
+                (unsigned long long)frs[f].first_entry, (unsigned long long)frs[f].n_entries, (unsigned long long)frs[f].first_block,
+                (unsigned long long)frs[f].n_blocks, (unsigned long long)frs[f].data_size, (unsigned long long)frs[f].filter_bytes);
+    }
     CU(j->out_buf.reserve(off + 256));
     {  // scratch for the parallel part of the index-block checksum
       std::vector<uint64_t> coff(nfiles + 1, 0);
@@ -824,7 +840,7 @@ int run_merge_encode(b200c_job* j, int until, KeyCols decc, RunBounds runs, uint
   CU(j->mrg[3].reserve(4 * (N + 1)));
   CU(j->esz.reserve(4 * (N + 1)));
   CU(j->eshared.reserve(N + 1));
-  CU(j->tstat.reserve(sizeof(TileStat) * (N / kEncTile + 2)));
+  CU(j->tstat.reserve(sizeof(TileStat) * (mtiles + 2)));
   KeyColsMut mrg{j->mrg[0].as<ulonglong2>(), j->mrg[1].as<uint64_t>(), j->mrg[2].as<uint64_t>(), j->mrg[3].as<uint32_t>()};
   MergeParams mp;
   mp.nruns = (uint32_t)k;
@@ -847,20 +863,21 @@ int run_merge_encode(b200c_job* j, int until, KeyCols decc, RunBounds runs, uint
     j->kt_begin("merge.partition");
     launch_merge_partition(decc, runs, (uint32_t)k, N, mtiles, j->splits.as<uint64_t>(), err, st);
     j->kt_end();
+    // the merge kernel also writes what the encoder needs per entry (encoded size, shared-prefix length) and per tile (statistics)
+    const MergeSizes msz{W.esz, W.eshared, W.tstat, W.min_s1};
+    W.tprefix = j->tile_state.as<unsigned long long>();
+    W.nstat = mtiles;
     j->kt_begin("merge.tiles");
     launch_merge_tiles(decc, runs, mp, N, mtiles, j->splits.as<uint64_t>(),
-                       j->tile_state.as<unsigned long long>(), reinterpret_cast<uint32_t*>(small + kSlotTicket), mrg, counters, err, st);
+                       j->tile_state.as<unsigned long long>(), reinterpret_cast<uint32_t*>(small + kSlotTicket), mrg, counters, msz, err, st);
     j->kt_end();
-    launches += 2;
+    j->kt_begin("merge.sizes_fix");
+    launch_merge_sizes_fix(KeyCols{mrg.pfx, mrg.tr, mrg.vref, mrg.meta, 0}, j->tile_state.as<unsigned long long>(), mtiles, msz, st);
+    j->kt_end();
+    launches += 3;
   }
   CU(cudaEventRecord(j->ev[2], st));
   KeyCols mcols{mrg.pfx, mrg.tr, mrg.vref, mrg.meta, 0};
-  if (N) {
-    j->kt_begin("encode.sizes");
-    launch_encode_sizes(mcols, reinterpret_cast<const unsigned long long*>(&counters->n_out), W, N, st);
-    j->kt_end();
-    launches++;
-  }
   uint64_t h[kSmallSlots];
   {
     int rc = read_small(j, small, h, nullptr, nullptr);  // sync #1: survivors, smallest entry, error word
@@ -946,6 +963,7 @@ int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, co
   CU(j->esz.reserve(4 * (n + 1)));
   CU(j->eshared.reserve(n + 1));
   CU(j->tstat.reserve(sizeof(TileStat) * (n / kEncTile + 2)));
+  CU(j->tile_state.reserve(8 * (n / kEncTile + 2)));
   CU(j->scan_tmp.reserve(8 * ((n / kScanTile) + 2)));
   EncodeWork W;
   memset(&W, 0, sizeof W);
@@ -958,7 +976,9 @@ int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, co
                 static_cast<const uint32_t*>(meta), n};
   if (n) {
     j->kt_begin("encode.sizes");
-    launch_encode_sizes(mcols, reinterpret_cast<const unsigned long long*>(&counters->n_out), W, n, st);
+    W.tprefix = j->tile_state.as<unsigned long long>();
+    W.nstat = (n + kEncTile - 1) / kEncTile;
+    launch_encode_sizes(mcols, reinterpret_cast<const unsigned long long*>(&counters->n_out), W, j->tile_state.as<unsigned long long>(), n, st);
     j->kt_end();
     launches++;
   }

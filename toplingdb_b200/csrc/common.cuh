@@ -442,6 +442,34 @@ __device__ inline uint32_t block_checksum_warp(uint32_t type, const uint8_t* dat
   return 0;
 }
 
+// ---- encoded entry sizes (BlockBuilder::AddWithLastKey, block_builder.cc:177-253) --------------------------------------
+__device__ __forceinline__ uint32_t ikey_byte(uint64_t hi, uint64_t lo, uint32_t ulen, uint64_t tr, uint32_t j) {
+  if (j < ulen) return (uint32_t)(((j < 8) ? (hi >> (56 - 8 * j)) : (lo >> (56 - 8 * (j - 8)))) & 0xff);
+  return (uint32_t)((tr >> (8 * (j - ulen))) & 0xff);
+}
+// bytes shared by two internal keys (Slice::difference_offset on the raw key bytes, block_builder.cc:214)
+__device__ __forceinline__ uint32_t shared_prefix(uint64_t ahi, uint64_t alo, uint32_t alen, uint64_t atr, uint64_t bhi, uint64_t blo,
+                                                  uint32_t blen, uint64_t btr) {
+  if (alen == blen) {
+    uint32_t cb;
+    uint64_t x = ahi ^ bhi;
+    if (x) cb = (uint32_t)__clzll((long long)x) >> 3;
+    else {
+      uint64_t y = alo ^ blo;
+      cb = y ? 8 + ((uint32_t)__clzll((long long)y) >> 3) : 16;
+    }
+    if (cb < alen) return cb;
+    uint64_t z = atr ^ btr;
+    uint32_t tb = z ? ((uint32_t)(__ffsll((long long)z) - 1) >> 3) : 8;
+    return alen + tb;
+  }
+  uint32_t n = (alen < blen ? alen : blen) + 8, j = 0;
+  while (j < n && ikey_byte(ahi, alo, alen, atr, j) == ikey_byte(bhi, blo, blen, btr, j)) j++;
+  return j;
+}
+__device__ __forceinline__ uint32_t entry_size(uint32_t shared, uint32_t ks, uint32_t vs) {
+  return varint_len32(shared) + varint_len32(ks - shared) + varint_len32(vs) + (ks - shared) + vs;
+}
 // ---- warp scans ---------------------------------------------------------------------------------------------
 // Cooperative global -> shared copy with kDepth loads per thread in flight: a plain `dst[i] = src[i]` loop issues in
 // order, so each iteration would wait for its own DRAM round trip before the next load leaves.

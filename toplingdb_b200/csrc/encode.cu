@@ -34,40 +34,13 @@ constexpr int kW = kEncTile + kEncHalo;
 constexpr int kEncThreads = 256;
 
 // ------------------------------------------------------------------------------------------------ entry sizes
-__device__ __forceinline__ uint32_t ikey_byte(uint64_t hi, uint64_t lo, uint32_t ulen, uint64_t tr, uint32_t j) {
-  if (j < ulen) return (uint32_t)(((j < 8) ? (hi >> (56 - 8 * j)) : (lo >> (56 - 8 * (j - 8)))) & 0xff);
-  return (uint32_t)((tr >> (8 * (j - ulen))) & 0xff);
-}
-// bytes shared by two internal keys (Slice::difference_offset on the raw key bytes, block_builder.cc:214)
-__device__ __forceinline__ uint32_t shared_prefix(uint64_t ahi, uint64_t alo, uint32_t alen, uint64_t atr, uint64_t bhi, uint64_t blo,
-                                                  uint32_t blen, uint64_t btr) {
-  if (alen == blen) {
-    uint32_t cb;
-    uint64_t x = ahi ^ bhi;
-    if (x) cb = (uint32_t)__clzll((long long)x) >> 3;
-    else {
-      uint64_t y = alo ^ blo;
-      cb = y ? 8 + ((uint32_t)__clzll((long long)y) >> 3) : 16;
-    }
-    if (cb < alen) return cb;
-    uint64_t z = atr ^ btr;
-    uint32_t tb = z ? ((uint32_t)(__ffsll((long long)z) - 1) >> 3) : 8;
-    return alen + tb;
-  }
-  uint32_t n = (alen < blen ? alen : blen) + 8, j = 0;
-  while (j < n && ikey_byte(ahi, alo, alen, atr, j) == ikey_byte(bhi, blo, blen, btr, j)) j++;
-  return j;
-}
-__device__ __forceinline__ uint32_t entry_size(uint32_t shared, uint32_t ks, uint32_t vs) {
-  return varint_len32(shared) + varint_len32(ks - shared) + varint_len32(vs) + (ks - shared) + vs;
-}
-
+// (ikey_byte / shared_prefix / entry_size live in common.cuh: the merge kernel writes the sizes of the entries it emits)
 // One CTA per tile of kEncTile merged entries (grid-stride over tiles): shared-prefix length + encoded size of every entry, the
 // global min / max entry size, and the tile's partial sums for the per-file statistics (so that the statistics pass reads
 // 40 bytes per tile instead of 12 bytes per entry).
 __global__ void __launch_bounds__(256)
 encode_sizes_kernel(KeyCols m, const unsigned long long* __restrict__ n_dev, uint32_t* __restrict__ esz, uint8_t* __restrict__ eshared,
-                    TileStat* __restrict__ tstat, uint32_t* __restrict__ min_s1) {
+                    TileStat* __restrict__ tstat, unsigned long long* __restrict__ tprefix, uint32_t* __restrict__ min_s1) {
   const uint64_t n = *n_dev;
   const uint64_t ntiles = (n + kEncTile - 1) / kEncTile;
   uint32_t mn = 0xffffffffu, mxs = 0;
@@ -153,7 +126,10 @@ encode_sizes_kernel(KeyCols m, const unsigned long long* __restrict__ n_dev, uin
       atomicMax(&red[4], smax);
     }
     __syncthreads();
-    if (threadIdx.x == 0) tstat[tile] = TileStat{red[0], red[1], red[2], red[3], red[4]};
+    if (threadIdx.x == 0) {
+      tstat[tile] = TileStat{red[0], red[1], red[2], red[3], red[4]};
+      tprefix[tile] = t1;  // entries up to and including this stat tile
+    }
     __syncthreads();
   }
   mn = __reduce_min_sync(0xffffffffu, mn);
@@ -1007,8 +983,9 @@ encode_blocklist_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, u
 }
 
 // ------------------------------------------------------------------------------------------------ per-file statistics
-// One CTA per output file: whole tiles inside the file come from the sizes kernel's partial sums, the (at most two) partly
-// covered tiles at its ends are read entry by entry; also the file's smallest / largest key.
+// One CTA per output file: stat tiles (merge tiles, or kEncTile entries on the TableBuilder-only path) that lie inside the file come
+// from their partial sums, the partly covered ones at its ends are read entry by entry; also the file's smallest / largest key.
+// Stat tile t covers the entries [prefix(t - 1), prefix(t)).
 __global__ void encode_filestats_kernel(KeyCols m, EncodeWork wk, uint32_t nfiles) {
   const uint32_t f = blockIdx.x;
   if (f >= nfiles) return;
@@ -1016,9 +993,30 @@ __global__ void encode_filestats_kernel(KeyCols m, EncodeWork wk, uint32_t nfile
   __shared__ unsigned long long red[5];
   if (threadIdx.x < 5) red[threadIdx.x] = threadIdx.x == 3 ? ~0ull : 0ull;
   __syncthreads();
+  const unsigned long long kVal = (1ull << 62) - 1;
   unsigned long long kb = 0, vb = 0, nd = 0, smin = ~0ull, smax = 0;
   if (f1 > f0) {
-    const uint64_t tfull0 = (f0 + kEncTile - 1) / kEncTile, tfull1 = f1 / kEncTile;  // tiles [tfull0, tfull1) lie inside the file
+    auto tile_start = [&](uint64_t t) -> uint64_t { return t ? (wk.tprefix[t - 1] & kVal) : 0; };
+    auto first_tile_starting_at_or_after = [&](uint64_t e) -> uint64_t {  // tile starts are non-decreasing
+      uint64_t lo = 0, hi = wk.nstat;
+      while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (tile_start(mid) < e) lo = mid + 1;
+        else hi = mid;
+      }
+      return lo;
+    };
+    const uint64_t tA = first_tile_starting_at_or_after(f0);
+    uint64_t tB = 0;  // first tile that ends behind f1: the tiles [tA, tB) lie inside the file
+    {
+      uint64_t lo = 0, hi = wk.nstat;
+      while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if ((wk.tprefix[mid] & kVal) <= f1) lo = mid + 1;
+        else hi = mid;
+      }
+      tB = lo;
+    }
     auto scan_entries = [&](uint64_t lo, uint64_t hi) {
       for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         const uint64_t tr = m.tr[i];
@@ -1031,12 +1029,12 @@ __global__ void encode_filestats_kernel(KeyCols m, EncodeWork wk, uint32_t nfile
         smax = sq > smax ? sq : smax;
       }
     };
-    if (tfull0 >= tfull1) {
-      scan_entries(f0, f1);  // the file covers no whole tile
+    if (tA >= tB) {
+      scan_entries(f0, f1);  // the file covers no whole stat tile
     } else {
-      scan_entries(f0, tfull0 * kEncTile);
-      scan_entries(tfull1 * kEncTile, f1);
-      for (uint64_t t = tfull0 + threadIdx.x; t < tfull1; t += blockDim.x) {
+      scan_entries(f0, tile_start(tA));
+      scan_entries(wk.tprefix[tB - 1] & kVal, f1);
+      for (uint64_t t = tA + threadIdx.x; t < tB; t += blockDim.x) {
         const TileStat ts = wk.tstat[t];
         kb += ts.raw_key;
         vb += ts.raw_value;
@@ -1935,10 +1933,11 @@ void launch_copy_small(const void* src, void* dst, uint32_t n, cudaStream_t st) 
 void launch_scatter_tails(const TailCopy* recs, uint32_t n, const uint8_t* staged, uint8_t* out, cudaStream_t st) {
   if (n) scatter_tails_kernel<<<n, 256, 0, st>>>(recs, staged, out);
 }
-void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, uint64_t n_cap, cudaStream_t st) {
+void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, unsigned long long* tprefix_out, uint64_t n_cap,
+                         cudaStream_t st) {
   if (n_cap == 0) return;
   const uint64_t tiles = (n_cap + kEncTile - 1) / kEncTile;
-  encode_sizes_kernel<<<(unsigned)(tiles < 148 * 8 ? tiles : 148 * 8), 256, 0, st>>>(m, n_dev, w.esz, w.eshared, w.tstat, w.min_s1);
+  encode_sizes_kernel<<<(unsigned)(tiles < 148 * 8 ? tiles : 148 * 8), 256, 0, st>>>(m, n_dev, w.esz, w.eshared, w.tstat, tprefix_out, w.min_s1);
 }
 void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t max_s1, uint32_t* err,
                           cudaStream_t st) {

@@ -71,6 +71,19 @@ struct MergeParams {
   int32_t ttl;                       // B200C_FILTER_TTL
   int64_t now;
 };
+struct TileStat {            // partial sums for the per-file statistics over one "stat tile" of consecutive output entries
+  uint64_t raw_key, raw_value, deletions, smallest_seq, largest_seq;
+};
+// What the merge kernel writes for the encoder besides the merged columns (it holds every output entry and its predecessor in
+// shared memory anyway): the encoded size / shared-prefix length of every entry except the first one of a tile (its predecessor
+// is the previous tile's last survivor: merge_sizes_fix_kernel fills those in), the statistics of the tile's output entries, and
+// the smallest / largest entry size of the job.
+struct MergeSizes {
+  uint32_t* esz;        // n_out
+  uint8_t* eshared;     // n_out
+  TileStat* tstat;      // one per merge tile; the tile's output range is [prefix(t-1), prefix(t)) from tile_state
+  uint32_t* min_s1;     // [0] min, [1] max of esz
+};
 struct MergeCounters {               // device-side CompactionIterationStats
   unsigned long long n_out, n_input_deletions, n_hidden, n_obsolete, raw_key_bytes, raw_value_bytes, n_silent, n_user_drop;
 };
@@ -94,7 +107,9 @@ void launch_merge_partition(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t
                             uint64_t* splits, uint32_t* err, cudaStream_t st);
 void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                         const uint64_t* splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
-                        MergeCounters* counters, uint32_t* err, cudaStream_t st);
+                        MergeCounters* counters, MergeSizes ms, uint32_t* err, cudaStream_t st);
+// sizes of each tile's first output entry (needs the finished tile_state prefixes and merged columns)
+void launch_merge_sizes_fix(KeyCols merged, const unsigned long long* tile_state, uint64_t ntiles, MergeSizes ms, cudaStream_t st);
 
 // ---- encode.cu
 // Grandparent-aware output cutting (CompactionOutputs::ShouldStopBefore, compaction_outputs.cc:231-354).  The walk over the block
@@ -160,13 +175,12 @@ constexpr int kEncHalo = 2048;
 constexpr int kEncGroupTiles = 16;   // tiles per stitch group (encode.cu kEncGroup)       // look-ahead window = the longest block (in entries) the encoder accepts
 constexpr uint32_t kMaxOutFiles = 4096;
 
-struct TileStat {            // per kEncTile merged entries: partial sums for the per-file statistics
-  uint64_t raw_key, raw_value, deletions, smallest_seq, largest_seq;
-};
 struct EncodeWork {                  // device scratch owned by the job
   uint32_t* esz;        // n: encoded size of entry i as a non-restart entry (s1)
   uint8_t* eshared;     // n: bytes shared with the previous internal key
-  TileStat* tstat;      // ceil(n / kEncTile): written by the sizes kernel
+  TileStat* tstat;      // statistics per stat tile: merge tiles (written by the merge kernel) or kEncTile entries (sizes kernel)
+  const unsigned long long* tprefix;  // per stat tile: entries up to and including the tile (low 62 bits; the top bits are flags)
+  uint64_t nstat;       // number of stat tiles
   uint32_t* min_s1;     // 2: [0] global min of esz (bounds the entry-point candidate window), [1] global max
   TileRow* rows;        // ntiles x hc
   TileRow* grows;       // ngroups x hc: composed transfer functions of kEncGroup tiles (exit relative to the group start)
@@ -188,7 +202,8 @@ struct EncodeWork {                  // device scratch owned by the job
   uint16_t* nxt;        // n: tile-relative end of the block that would start at entry i
   uint32_t* disk;       // n: on-disk bytes of that block
 };
-void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, uint64_t n_cap, cudaStream_t st);
+// TableBuilder-only path (no merge in front): sizes + statistics per kEncTile entries + their prefix array (tprefix_out)
+void launch_encode_sizes(KeyCols m, const unsigned long long* n_dev, EncodeWork w, unsigned long long* tprefix_out, uint64_t n_cap, cudaStream_t st);
 void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t max_s1, uint32_t* err,
                           cudaStream_t st);
 // stitch: launched on its own stream BEFORE / alongside launch_encode_tables (it consumes groups as their gready flag appears);

@@ -119,18 +119,25 @@ merge_partition_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t n_to
 // The same split for up to 16 runs with ALL lanes busy: run r is owned by a group of g = 32 / pow2(nruns) lanes that
 // probe g points of its bracket per step (a (g+1)-ary search), which divides the depth of the dependent-load chain --
 // the whole cost of this kernel -- by log2(g + 1).
-__global__ void __launch_bounds__(128)
-merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint32_t gshift, uint64_t n_total,
-                               uint64_t ntiles, uint64_t* __restrict__ splits, uint32_t* __restrict__ err) {
-  const unsigned lane = threadIdx.x & 31;
-  const uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b > ntiles) return;
-  uint64_t d = b * (uint64_t)kMT;
-  if (d > n_total) d = n_total;
-  const uint32_t g = 1u << gshift, r = lane >> gshift, sub = lane & (g - 1), gbase = r << gshift;
-  const uint64_t base = r < nruns ? runs.begin[r] : 0;
-  const uint64_t nrun = r < nruns ? runs.end[r] - runs.begin[r] : 0;
-  uint64_t lo = (d == n_total) ? nrun : 0, hi = (d == 0) ? 0 : nrun;
+//
+// Two levels.  A split over 4.8 M-entry runs costs ~200 dependent DRAM round trips when it starts from the whole runs.  So the
+// selection first runs over every kPartStride-th entry of each run (the "samples": a few MB in total, served by the L2 after the
+// first touches), twice, for two sample ranks that bracket the wanted rank, and the exact selection then starts from brackets of
+// about kPartStride * (2k + 1) entries in total:
+//   sample j of run r = its entry kPartStride * j;  y = a sample, t_r = samples of run r that precede y, c_r = entries of run r
+//   that precede y.  Entry kPartStride * t_r does not precede y and entry kPartStride * (t_r - 1) does, so
+//       kPartStride * t_r - (kPartStride - 1) <= c_r <= min(kPartStride * t_r, n_r)            (c_r = 0 when t_r = 0).
+//   Selecting sample rank T makes y the T-th sample and t_r the split.  With T_lo = d / kPartStride the entries that precede y
+//   number at most kPartStride * T_lo <= d, so they all belong to the first d entries: s_r >= c_r.  With
+//   T_hi = ceil((d + (kPartStride - 1) k) / kPartStride) they number at least d: s_r <= c_r.
+constexpr uint32_t kPartStride = 64;
+struct GroupLanes {
+  uint32_t gshift, g, r, sub, gbase, nruns;
+};
+// multi-sequence selection of rank d over the runs' brackets [lo, hi) (units of `stride` entries; entry = base + stride * pos)
+__device__ __forceinline__ void msel_grouped(const KeyCols& in, const GroupLanes& L, uint64_t base, uint64_t stride, uint64_t d, uint64_t& lo,
+                                             uint64_t& hi) {
+  const uint32_t g = L.g, r = L.r, sub = L.sub, gbase = L.gbase, gshift = L.gshift;
   for (int guard = 0; guard < 64 * 70; guard++) {
     // widest bracket decides the pivot run
     const unsigned long long wdt = hi - lo;
@@ -144,7 +151,7 @@ merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint3
     const uint32_t p = (uint32_t)(best & 127);
     const uint64_t m = __shfl_sync(0xffffffffu, lo + ((hi - lo) >> 1), (int)(p << gshift));
     const uint64_t pbase = __shfl_sync(0xffffffffu, base, (int)(p << gshift));
-    const Key x = load_key(in, pbase + m);
+    const Key x = load_key(in, pbase + m * stride);
     // c = number of elements of run r that precede x in the total order (key, run index): (g+1)-ary search of [lo, hi)
     const bool before_equal = r < p;
     uint64_t clo = lo, chi = hi;
@@ -164,7 +171,7 @@ merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint3
       }
       bool prec = false;
       if (valid) {
-        const Key e = load_key(in, base + pos);
+        const Key e = load_key(in, base + pos * stride);
         prec = before_equal ? !ikey_less(x, e) : ikey_less(e, x);
       }
       const unsigned bal = __ballot_sync(0xffffffffu, prec);
@@ -183,11 +190,52 @@ merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint3
 #pragma unroll
     for (int dd = 16; dd; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
     const bool x_before = sum < d;  // pivot is among the first d elements
-    if (r < nruns) {
+    if (r < L.nruns) {
       if (x_before) lo = (r == p) ? m + 1 : c;
       else hi = (r == p) ? m : c;
     }
   }
+}
+__global__ void __launch_bounds__(128)
+merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint32_t gshift, uint64_t n_total,
+                               uint64_t ntiles, uint64_t* __restrict__ splits, uint32_t* __restrict__ err) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b > ntiles) return;
+  uint64_t d = b * (uint64_t)kMT;
+  if (d > n_total) d = n_total;
+  GroupLanes L;
+  L.gshift = gshift;
+  L.g = 1u << gshift;
+  L.r = lane >> gshift;
+  L.sub = lane & (L.g - 1);
+  L.gbase = L.r << gshift;
+  L.nruns = nruns;
+  const uint32_t r = L.r, sub = L.sub;
+  const uint64_t base = r < nruns ? runs.begin[r] : 0;
+  const uint64_t nrun = r < nruns ? runs.end[r] - runs.begin[r] : 0;
+  uint64_t lo = (d == n_total) ? nrun : 0, hi = (d == 0) ? 0 : nrun;
+  if (d != 0 && d != n_total) {
+    // ---- level 1: the samples
+    const uint64_t S = kPartStride, msamp = (nrun + S - 1) / S;
+    uint64_t M = sub == 0 ? msamp : 0;
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) M += __shfl_xor_sync(0xffffffffu, M, dd);
+    const uint64_t T_lo = d / S, T_hi = (d + (S - 1) * (uint64_t)nruns + S - 1) / S;
+    uint64_t tlo = 0, tlo_hi = msamp;
+    if (T_lo > 0) msel_grouped(in, L, base, S, T_lo, tlo, tlo_hi);  // T_lo < M because d < n_total
+    if (tlo) lo = S * tlo - (S - 1);
+    if (T_hi < M) {
+      // the split of sample rank T_hi lies at most T_hi - T_lo samples further in every run
+      uint64_t thi = tlo, thi_hi = tlo + (T_hi - T_lo) < msamp ? tlo + (T_hi - T_lo) : msamp;
+      msel_grouped(in, L, base, S, T_hi, thi, thi_hi);
+      const uint64_t h = S * thi;
+      hi = h < nrun ? h : nrun;
+    }
+    if (hi < lo) hi = lo;  // cannot happen for sorted runs; the rank check below reports it
+  }
+  // ---- level 2: exact
+  msel_grouped(in, L, base, 1, d, lo, hi);
   uint64_t tot = sub == 0 ? lo : 0;
 #pragma unroll
   for (int dd = 16; dd; dd >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, dd);
@@ -207,6 +255,8 @@ struct TileSmem {
   uint64_t sbeg[kMaxRuns];         // absolute index of each segment's first element
   uint64_t snaps[64];              // cached snapshots (first 64)
   unsigned long long red[8];       // per-CTA counter staging
+  unsigned long long stat[5];      // statistics of the tile's output entries (TileStat)
+  uint32_t smin, smax;             // smallest / largest encoded entry size of the tile
   uint32_t wsum[40];
   uint64_t base_out;
   uint32_t tile_id, kept_total;
@@ -357,13 +407,18 @@ __device__ bool group_head(const KeyCols& in, RunBounds runs, uint32_t nruns, ui
 __global__ void __launch_bounds__(kMThreads, 3)
 merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                    const uint64_t* __restrict__ splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
-                   MergeCounters* counters, uint32_t* __restrict__ err, uint32_t prefetch_dist) {
+                   MergeCounters* counters, MergeSizes ms, uint32_t* __restrict__ err, uint32_t prefetch_dist) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TileSmem& s = *reinterpret_cast<TileSmem*>(smem_raw);
   const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
   const uint32_t k = mp.nruns;
   if (t == 0) s.tile_id = atomicAdd(ticket, 1u);
   if (t < 8) s.red[t] = 0;
+  if (t < 5) s.stat[t] = t == 3 ? ~0ull : 0ull;
+  if (t == 0) {
+    s.smin = 0xffffffffu;
+    s.smax = 0;
+  }
   if (t < 64 && t < mp.nsnapshots) s.snaps[t] = mp.snapshots[t];
   __syncthreads();
   const uint64_t tile = s.tile_id;
@@ -729,16 +784,59 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     }
     __syncthreads();
     const uint64_t base_out = s.base_out;
+    // per-thread partial statistics of the output entries (TileStat) and entry-size extremes
+    uint32_t st_kb = 0, st_nd = 0, mn = 0xffffffffu, mx = 0;
+    unsigned long long st_vb = 0, st_smin = ~0ull, st_smax = 0;
 #pragma unroll
     for (int j = 0; j < kMV; j++) {
       const uint32_t i = t + j * kMThreads;
       if (i < kept_total) {
         const uint32_t pos = gp[j];
         const uint64_t dst = base_out + i;
-        out.pfx[dst] = make_ulonglong2(s.hi[pos], s.lo[pos]);
-        out.tr[dst] = s.tr[pos];
+        const uint64_t chi = s.hi[pos], clo = s.lo[pos], ctr = s.tr[pos];
+        const uint32_t cul = s.ulen[pos] & 0x3fu, vlen = meta_vlen(gm[j]);
+        out.pfx[dst] = make_ulonglong2(chi, clo);
+        out.tr[dst] = ctr;
         out.vref[dst] = gv[j];
         out.meta[dst] = gm[j];
+        // encoded size against the previous OUTPUT entry (BlockBuilder::AddWithLastKey); the tile's first entry is left to
+        // merge_sizes_fix_kernel: its predecessor is the last survivor of an earlier tile
+        if (i > 0) {
+          const uint32_t pp = s.idx[PH(i - 1)];
+          const uint32_t sh = shared_prefix(chi, clo, cul, ctr, s.hi[pp], s.lo[pp], s.ulen[pp] & 0x3fu, s.tr[pp]);
+          const uint32_t s1 = entry_size(sh, cul + 8, vlen);
+          ms.esz[dst] = s1;
+          ms.eshared[dst] = (uint8_t)sh;
+          mn = s1 < mn ? s1 : mn;
+          mx = s1 > mx ? s1 : mx;
+        }
+        st_kb += cul + 8;
+        st_vb += vlen;
+        st_nd += (ctr & 0xff) == kTypeDeletion;
+        const unsigned long long sq = ctr >> 8;
+        st_smin = sq < st_smin ? sq : st_smin;
+        st_smax = sq > st_smax ? sq : st_smax;
+      }
+    }
+    {
+      const unsigned kb = __reduce_add_sync(0xffffffffu, st_kb), nd = __reduce_add_sync(0xffffffffu, st_nd);
+      mn = __reduce_min_sync(0xffffffffu, mn);
+      mx = __reduce_max_sync(0xffffffffu, mx);
+#pragma unroll
+      for (int dd = 16; dd; dd >>= 1) {
+        st_vb += __shfl_xor_sync(0xffffffffu, st_vb, dd);
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, st_smin, dd), b = __shfl_xor_sync(0xffffffffu, st_smax, dd);
+        st_smin = a < st_smin ? a : st_smin;
+        st_smax = b > st_smax ? b : st_smax;
+      }
+      if (lane == 0) {
+        atomicAdd(&s.stat[0], (unsigned long long)kb);
+        atomicAdd(&s.stat[1], st_vb);
+        atomicAdd(&s.stat[2], (unsigned long long)nd);
+        atomicMin(&s.stat[3], st_smin);
+        atomicMax(&s.stat[4], st_smax);
+        atomicMin(&s.smin, mn);
+        atomicMax(&s.smax, mx);
       }
     }
   }
@@ -762,6 +860,42 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   }
   __syncthreads();
   if (t < 8 && s.red[t]) atomicAdd(((unsigned long long*)counters) + t, s.red[t]);
+  if (t == 0) {
+    ms.tstat[tile] = TileStat{s.stat[0], s.stat[1], s.stat[2], s.stat[3], s.stat[4]};
+    if (s.smin != 0xffffffffu) {
+      atomicMin(ms.min_s1, s.smin);
+      atomicMax(ms.min_s1 + 1, s.smax);
+    }
+  }
+}
+
+// The first output entry of every merge tile: its predecessor was written by an earlier tile.  One thread per tile.
+__global__ void merge_sizes_fix_kernel(KeyCols m, const unsigned long long* __restrict__ tile_state, uint64_t ntiles, MergeSizes ms) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long kVal = (1ull << 62) - 1;
+  uint32_t s1 = 0xffffffffu;
+  if (t < ntiles) {
+    const uint64_t e = t ? (tile_state[t - 1] & kVal) : 0, end = tile_state[t] & kVal;
+    if (end > e) {  // the tile has survivors; e is the first
+      const ulonglong2 c = m.pfx[e];
+      const uint64_t ctr = m.tr[e];
+      const uint32_t mt = m.meta[e], cul = meta_ulen(mt);
+      uint32_t sh = 0;
+      if (e > 0) {
+        const ulonglong2 p = m.pfx[e - 1];
+        sh = shared_prefix(c.x, c.y, cul, ctr, p.x, p.y, meta_ulen(m.meta[e - 1]), m.tr[e - 1]);
+      }
+      s1 = entry_size(sh, cul + 8, meta_vlen(mt));
+      ms.esz[e] = s1;
+      ms.eshared[e] = (uint8_t)sh;
+    }
+  }
+  const uint32_t mn = __reduce_min_sync(0xffffffffu, s1);
+  const uint32_t mx = __reduce_max_sync(0xffffffffu, s1 == 0xffffffffu ? 0u : s1);
+  if ((threadIdx.x & 31) == 0 && mn != 0xffffffffu) {
+    atomicMin(ms.min_s1, mn);
+    atomicMax(ms.min_s1 + 1, mx);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ sub-compaction key range
@@ -831,7 +965,7 @@ static_assert(sizeof(Key) * kMaxRuns <= sizeof(uint64_t) * kMT && 4 * kMaxRuns <
 static_assert(3 * (sizeof(TileSmem) + 1024) <= 227 * 1024, "merge tile must fit three CTAs per SM");
 void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                         const uint64_t* splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
-                        MergeCounters* counters, uint32_t* err, cudaStream_t st) {
+                        MergeCounters* counters, MergeSizes ms, uint32_t* err, cudaStream_t st) {
   if (ntiles == 0) return;
   static PerDeviceFlag attr;
   const uint64_t dev_bit = attr.bit_of_current_device();
@@ -840,7 +974,10 @@ void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_t
     attr.set(dev_bit);
   }
   merge_tiles_kernel<<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state,
-                                                                          ticket, out, counters, err, 148u * 3u);
+                                                                          ticket, out, counters, ms, err, 148u * 3u);
+}
+void launch_merge_sizes_fix(KeyCols merged, const unsigned long long* tile_state, uint64_t ntiles, MergeSizes ms, cudaStream_t st) {
+  if (ntiles) merge_sizes_fix_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(merged, tile_state, ntiles, ms);
 }
 
 }  // namespace b200c

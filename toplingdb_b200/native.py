@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200c.so")
+LIB_PATH = os.environ.get("B200C_LIB") or os.path.join(HERE, "libb200c.so")  # B200C_LIB: debugging override
 
 OK, ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_CORRUPTION, ERR_NOT_SUPPORTED, ERR_OOM, ERR_STATE = range(8)
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -187,6 +187,14 @@ class CompactionJob:
         self._h = C.c_void_p()
         _check(L.b200c_job_create(C.byref(p), C.byref(self._h)))
         self.ninputs = 0
+        self._torch_device_inputs = False
+
+    def _wait_for_torch(self):
+        """The library works on its own non-blocking streams: device tensors handed to it must be complete.  torch kernels that are
+        still producing them (on torch's streams) are waited for here, as any caller of a stream-based C API has to."""
+        if self._torch_device_inputs:
+            import torch
+            torch.cuda.synchronize(self.params.device)
 
     def add_input(self, data, level=0, file_number=0):
         """data: bytes (host image) or a CUDA uint8 torch tensor (device-resident image)."""
@@ -198,6 +206,7 @@ class CompactionJob:
         elif hasattr(data, "data_ptr"):
             self._keep.append(data)
             kind = MEM_DEVICE if data.is_cuda else MEM_HOST
+            self._torch_device_inputs = self._torch_device_inputs or bool(data.is_cuda)
             _check(L.b200c_job_add_input(self._h, level, file_number, C.c_void_p(data.data_ptr()), data.numel() * data.element_size(), kind))
         else:
             raise TypeError("input must be bytes or a torch tensor")
@@ -205,12 +214,15 @@ class CompactionJob:
 
     def run(self, until=3):
         L = lib()
+        self._wait_for_torch()
         _check(L.b200c_job_run(self._h) if until == 3 else L.b200c_job_run_until(self._h, until))
         return self
 
     def encode_columns(self, n, pfx, tr, vref, meta):
         """TableBuilder side alone: device columns (torch CUDA tensors) -> BlockBasedTable image(s)."""
         self._keep += [pfx, tr, vref, meta]
+        self._torch_device_inputs = True
+        self._wait_for_torch()
         _check(lib().b200c_job_encode_columns(self._h, n, C.c_void_p(pfx.data_ptr()), C.c_void_p(tr.data_ptr()),
                                                C.c_void_p(vref.data_ptr()), C.c_void_p(meta.data_ptr())))
         return self
