@@ -31,7 +31,10 @@ __device__ __forceinline__ int file_of_block(const FileDesc* files, int nfiles, 
 // ---------------------------------------------------------------------------------------------- index block
 // IndexValue decode (table/format.cc:120-140): shared == 0 -> varint64 offset, varint64 size; else (fv >= 4)
 // varsigned64 size delta and offset = prev_offset + prev_size + kBlockTrailerSize.
-__device__ void index_decode_sequential(const FileDesc& fd, const uint8_t* blk, uint32_t nr, uint64_t* blk_off,
+// blk_off[b] = offset of the block inside its file | file index << kBlkFileShift (the block decoder gets both with one load)
+constexpr int kBlkFileShift = 48;
+constexpr uint64_t kBlkOffMask = (1ull << kBlkFileShift) - 1;
+__device__ void index_decode_sequential(const FileDesc& fd, uint32_t file_idx, const uint8_t* blk, uint32_t nr, uint64_t* blk_off,
                                         uint32_t* blk_size, uint32_t* err) {
   const uint8_t* end = blk + fd.index_size - 4 - 4ull * nr;
   const uint8_t* p = blk;
@@ -67,7 +70,12 @@ __device__ void index_decode_sequential(const FileDesc& fd, const uint8_t* blk, 
       n++;
       break;
     }
-    blk_off[fd.gblk_first + n] = off;
+    if (off + size + 5 > fd.len || size < 4 || size > 0xffffffffull || off > kBlkOffMask) {
+      atomicOr(err, kErrCorruptBlock);
+      off = 0;
+      size = 4;
+    }
+    blk_off[fd.gblk_first + n] = off | ((uint64_t)file_idx << kBlkFileShift);
     blk_size[fd.gblk_first + n] = (uint32_t)size;
     poff = off;
     psize = size;
@@ -92,7 +100,7 @@ __global__ void index_decode_kernel(const FileDesc* __restrict__ files, int nfil
     return;
   }
   if (nr != fd.nblocks) {  // index_block_restart_interval != 1: rare, walk it with one thread
-    if (threadIdx.x == 0 && blockIdx.x == 0) index_decode_sequential(fd, blk, nr, blk_off, blk_size, err);
+    if (threadIdx.x == 0 && blockIdx.x == 0) index_decode_sequential(fd, (uint32_t)f, blk, nr, blk_off, blk_size, err);
     return;
   }
   const uint8_t* rs = blk + fd.index_size - 4 - 4ull * nr;
@@ -113,12 +121,12 @@ __global__ void index_decode_kernel(const FileDesc* __restrict__ files, int nfil
     ok = ok && p < rs && (c = get_varint(p, rs, &off));
     if (ok) p += c;
     ok = ok && (c = get_varint(p, rs, &size));
-    if (!ok || off + size + 5 > fd.len || size < 4 || size > 0xffffffffull) {
+    if (!ok || off + size + 5 > fd.len || size < 4 || size > 0xffffffffull || off > kBlkOffMask) {
       atomicOr(err, kErrCorruptBlock);
       off = 0;
       size = 4;
     }
-    blk_off[fd.gblk_first + j] = off;
+    blk_off[fd.gblk_first + j] = off | ((uint64_t)f << kBlkFileShift);
     blk_size[fd.gblk_first + j] = (uint32_t)size;
   }
 }
@@ -193,15 +201,52 @@ __device__ __forceinline__ uint32_t count_interval(const uint8_t* p, const uint8
 // Blocks outside the fast path's limits (larger than the staging slice, more than 16 restart intervals, more than 16
 // entries in an interval) take a slower lane-per-interval path that needs regular intervals (what BlockBuilder writes).
 constexpr int kDecWarps = 8;
-constexpr int kDecSlice = 4608;            // bytes staged per warp (block + trailer + phase); larger blocks are read in place
+constexpr int kDecSlice = 4608;            // bytes staged per warp and buffer (block + trailer + phase); larger blocks are read in place
 constexpr int kDecVecs = kDecSlice / 16;   // 288
-constexpr int kDecPerLane = kDecVecs / 32;  // 9 vectors per lane
 constexpr int kDecRows = 16, kDecRowLen = 16;  // fast path: restart intervals per block, entries per interval
+// Every warp owns TWO staging slices: while it parses block n out of one, the TMA engine (cp.async.bulk, completion on an mbarrier)
+// fills the other with block n + 1 -- the warp never waits for a DRAM round trip except for its very first block.
 struct DecWarpSmem {
-  uint4 slice[kDecVecs];
+  uint4 slice[2][kDecVecs];
   uint16_t tab[kDecRows * kDecRowLen];  // entry offsets, one row per restart interval
   uint16_t ex[32];                      // entries before each interval
+  uint64_t bar[2];                      // mbarriers: slice s has landed
 };
+// per-lane XXH3 constants (lane l: accumulator lane a = l & 7, stripe group g = l >> 3), computed once per CTA
+struct XxhLaneTab {
+  uint64_t k[4][32];   // secret words of the four stripes a lane owns inside a 1024-byte block
+  uint64_t kscr[32];   // scramble secret
+  uint64_t klast[32];  // secret of the last stripe
+  uint64_t kmrg[32];   // merge secret
+};
+
+// ---- mbarrier + TMA bulk copy (global -> shared), sm_90+ ----------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// size: multiple of 16; dst / src: 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
 
 // entry header (three varint32: shared, non_shared, value length) from the 8 bytes h at p; false on malformed / unsupported
 __device__ __forceinline__ bool parse_header(uint64_t h, const uint8_t* p, const uint8_t* end, uint32_t* shared, uint32_t* non_shared,

@@ -286,13 +286,33 @@ __host__ __device__ __forceinline__ CutParams make_cut(uint32_t bs, uint32_t lim
   return c;
 }
 __device__ __forceinline__ uint32_t div_r(uint32_t x, const CutParams& cp) { return cp.rshift < 32 ? x >> cp.rshift : x / cp.R; }
-// payload bytes of a block holding window entries [a, b)
+// payload bytes of a block holding window entries [a, b).  The terms that depend on the block start alone (P[a], Q[a - R]) are
+// loaded once per start (BlockStart) instead of once per probe: the bisection below evaluates this several times per start.
+template <typename PT>
+struct BlockStart {
+  uint32_t a;
+  PT pa;        // P[a]
+  uint32_t qa;  // Q[a - R] (0 when a < R)
+};
+template <typename PT>
+__device__ __forceinline__ BlockStart<PT> block_start(const Window<PT>& w, uint32_t a, const CutParams& cp) {
+  BlockStart<PT> s;
+  s.a = a;
+  s.pa = w.P[a];
+  s.qa = a >= cp.R ? w.Q[a - cp.R] : 0u;
+  return s;
+}
+template <typename PT>
+__device__ __forceinline__ uint64_t blk_payload(const Window<PT>& w, const BlockStart<PT>& s, uint32_t b, const CutParams& cp) {
+  const uint32_t nrm1 = div_r(b - 1 - s.a, cp);  // restarts - 1
+  const uint32_t last = s.a + cp.R * nrm1;
+  // Q is a per-residue prefix sum of 32-bit surcharges inside one window: the difference fits 32 bits
+  const uint32_t q = w.Q[last] - s.qa;
+  return (uint64_t)(PT)(w.P[b] - s.pa) + q + 4u * (nrm1 + 1) + 4u;  // == BlockBuilder::CurrentSizeEstimate() (block_builder.cc:97,251)
+}
 template <typename PT>
 __device__ __forceinline__ uint64_t blk_payload(const Window<PT>& w, uint32_t a, uint32_t b, const CutParams& cp) {
-  uint32_t nrm1 = div_r(b - 1 - a, cp);  // restarts - 1
-  uint32_t last = a + cp.R * nrm1;
-  uint64_t q = (uint64_t)w.Q[last] - (a >= cp.R ? (uint64_t)w.Q[a - cp.R] : 0);
-  return (uint64_t)(PT)(w.P[b] - w.P[a]) + q + 4ull * (nrm1 + 1) + 4;  // == BlockBuilder::CurrentSizeEstimate() (block_builder.cc:97,251)
+  return blk_payload(w, block_start(w, a, cp), b, cp);
 }
 // first b > a at which FlushBlockBySizePolicy::Update (flush_block_policy.cc:37-69) fires for a block started at a.
 // returns wlen at the end of the stream, 0xffffffff if the block does not end inside the window.
@@ -300,6 +320,7 @@ __device__ __forceinline__ uint64_t blk_payload(const Window<PT>& w, uint32_t a,
 template <typename PT>
 __device__ __forceinline__ uint32_t next_block(const Window<PT>& w, uint32_t a, const CutParams& cp, uint32_t hint) {
   const uint32_t wlen = w.wlen;
+  const BlockStart<PT> bs = block_start(w, a, cp);
   // below `thr` neither flush condition can fire: condition 2 needs CurrentSizeEstimate > LIM and
   // CurrentSizeEstimate + (size of the next entry, at most smax + 7) > BS
   uint64_t thr = cp.BS - 1;
@@ -311,17 +332,17 @@ __device__ __forceinline__ uint32_t next_block(const Window<PT>& w, uint32_t a, 
   uint32_t lo = a + 1, hi = wlen + 1;  // searching the first b in [lo, hi) with CurrentSizeEstimate(a, b) > thr; hi = none
   if (hint > a + 1 && hint <= wlen) {
     uint32_t l2 = hint > a + 4 ? hint - 3 : a + 1, h2 = hint + 5 < wlen ? hint + 5 : wlen;
-    if (l2 == a + 1 || blk_payload(w, a, l2 - 1, cp) <= thr) lo = l2;
-    if (blk_payload(w, a, h2, cp) > thr) hi = h2;
+    if (l2 == a + 1 || blk_payload(w, bs, l2 - 1, cp) <= thr) lo = l2;
+    if (blk_payload(w, bs, h2, cp) > thr) hi = h2;
   }
   while (lo < hi) {
     uint32_t mid = (lo + hi) >> 1;
-    if (blk_payload(w, a, mid, cp) > thr) hi = mid;
+    if (blk_payload(w, bs, mid, cp) > thr) hi = mid;
     else lo = mid + 1;
   }
   if (lo >= wlen) return w.at_end ? wlen : 0xffffffffu;
-  uint64_t ec = blk_payload(w, a, lo, cp);  // CurrentSizeEstimate before adding entry b; updated incrementally
-  uint32_t m = lo - a;                     // entries already in the block
+  uint64_t ec = blk_payload(w, bs, lo, cp);  // CurrentSizeEstimate before adding entry b; updated incrementally
+  uint32_t m = lo - a;                      // entries already in the block
   uint32_t mr = cp.rshift < 32 ? (m & (cp.R - 1)) : (m % cp.R);
   for (uint32_t b = lo; b < wlen; b++) {
     if (ec >= cp.BS) return b;

@@ -250,6 +250,7 @@ struct TileSmem {
   uint64_t hi[kMT], lo[kMT], tr[kMT];
   uint16_t idx[kMT];               // merge order: idx[o] = load position of the o-th smallest key
   uint8_t ulen[kMT];
+  uint8_t srun[kMT];               // run (segment) a load position came from
   uint32_t seg[kMaxRuns + 1];      // segment starts in load order
   uint32_t lst[2][kMaxRuns + 2];   // list bounds per merge round (ping-pong)
   uint64_t sbeg[kMaxRuns];         // absolute index of each segment's first element
@@ -494,6 +495,16 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         s.idx[PH(i)] = (uint16_t)i;
       }
     }
+    // source run of every load position (the column position of an entry is needed again for its value reference)
+    uint32_t lr2 = 0;
+#pragma unroll
+    for (int j = 0; j < kMV; j++) {
+      const uint32_t i = t + j * kMThreads;
+      if (i < cnt) {
+        while (i >= s.seg[lr2 + 1]) lr2++;
+        s.srun[i] = (uint8_t)lr2;
+      }
+    }
   }
   __syncthreads();
   // ---- pairwise merge rounds over the index list, in place through registers
@@ -562,13 +573,8 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   // ---- compaction-iterator rules per merged position
   const bool cond_possible = mp.bottommost && mp.nsnapshots > 0;
   auto col_of = [&](uint32_t pos) -> uint64_t {  // column position of the entry at load position pos
-    uint32_t lo = 0, hi = k;
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (s.seg[mid] <= pos) lo = mid;
-      else hi = mid;
-    }
-    return s.sbeg[lo] + (pos - s.seg[lo]);
+    const uint32_t r = s.srun[pos];
+    return s.sbeg[r] + (pos - s.seg[r]);
   };
   uint32_t keep_mask = 0, nkeep = 0;
   unsigned long long c_hidden = 0, c_obsolete = 0, c_indel = 0, c_kbytes = 0, c_vbytes = 0, c_silent = 0, c_userdrop = 0;
@@ -709,13 +715,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   for (int x = 0; x < kMV; x++) {
     uint32_t o = t * kMV + x;
     if (o < cnt && ((keep_mask >> (16 + x)) & 1)) {
-      uint32_t pos = oid[x], lo = 0, hi = k;
-      while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (s.seg[mid] <= pos) lo = mid;
-        else hi = mid;
-      }
-      c_vbytes += meta_vlen(in.meta[s.sbeg[lo] + (pos - s.seg[lo])]);
+      c_vbytes += meta_vlen(in.meta[col_of(oid[x])]);
     }
   }
   __syncthreads();  // every read of idx[] / tr[] in merged order is done: compact in place
@@ -742,13 +742,8 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
       gm[j] = 0;
       gp[j] = 0;
       if (i < kept_total) {
-        uint32_t pos = s.idx[PH(i)], lo = 0, hi = k;
-        while (hi - lo > 1) {
-          uint32_t mid = (lo + hi) >> 1;
-          if (s.seg[mid] <= pos) lo = mid;
-          else hi = mid;
-        }
-        const uint64_t src = s.sbeg[lo] + (pos - s.seg[lo]);
+        const uint32_t pos = s.idx[PH(i)];
+        const uint64_t src = col_of(pos);
         gp[j] = (uint16_t)pos;
         gv[j] = in.vref[src];
         gm[j] = in.meta[src];
