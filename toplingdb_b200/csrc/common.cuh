@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstddef>
+
 namespace b200c {
 
 // ---- error word (device) : first error wins per class, host maps to b200c_status ---------------------------
@@ -440,6 +442,182 @@ __device__ inline uint32_t block_checksum_warp(uint32_t type, const uint8_t* dat
     return crc32c_mask(c ^ 0xffffffffu);
   }
   return 0;
+}
+
+// ---- explicit shared-memory accesses by 32-bit shared address (keeps the hot loops free of generic 64-bit addressing)
+__device__ __forceinline__ uint64_t lds64(uint32_t a) {
+  uint64_t v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// 4 / 8 bytes at any alignment (reads up to 7 bytes past the value, inside the slice)
+__device__ __forceinline__ uint32_t lds32_any(uint32_t a) {
+  const uint32_t al = a & ~3u;
+  return __funnelshift_r(lds32(al), lds32(al + 4), (a & 3) * 8);
+}
+__device__ __forceinline__ uint64_t shr128(uint64_t lo, uint64_t hi, uint32_t s) {  // (hi:lo) >> s, s in {0, 8, .., 56}
+  return s ? (lo >> s) | (hi << (64 - s)) : lo;
+}
+__device__ __forceinline__ uint64_t lds64_any(uint32_t a) {
+  const uint32_t al = a & ~7u;
+  return shr128(lds64(al), lds64(al + 8), (a & 7) * 8);
+}
+// per-lane XXH3 constants (lane l: accumulator lane a = l & 7, stripe group g = l >> 3), computed once per CTA
+struct XxhLaneTab {
+  uint64_t k[4][32];   // secret words of the four stripes a lane owns inside a 1024-byte block
+  uint64_t kscr[32];   // scramble secret
+  uint64_t klast[32];  // secret of the last stripe
+  uint64_t kmrg[32];   // merge secret
+};
+
+// ---- mbarrier + TMA bulk copy (global -> shared), sm_90+ ----------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// size: multiple of 16; dst / src: 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+// shared -> global bulk copy (TMA): size multiple of 16, both addresses 16-byte aligned; completion by bulk groups
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the bulk stores this thread issued have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (TMA) / are ordered before its accesses
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- XXH3-64 (seed 0) of a block staged in shared memory, warp-cooperative, lean: the per-lane secrets come from a table the CTA
+// fills once (XxhLaneTab), the data is read with the cheapest loads the block's byte phase allows.  Same arithmetic as
+// xxh3_64_warp_t (common.cuh); inputs of at most 240 bytes take the generic routine.
+__device__ __forceinline__ void fill_xxh_lane_tab(XxhLaneTab* t) {
+  for (uint32_t i = threadIdx.x; i < 32; i += blockDim.x) {
+    const int a = i & 7, g = i >> 3;
+    for (int q = 0; q < 4; q++) t->k[q][i] = sec64g(8 * (g + 4 * q) + 8 * a);
+    t->kscr[i] = sec64g(192 - 64 + 8 * a);
+    t->klast[i] = sec64g(192 - 64 - 7 + 8 * a);
+    t->kmrg[i] = sec64g(11 + 8 * a);
+  }
+}
+// 8 bytes at shared address p; o = p & 7 is the same for every lane (kPhase: 0 aligned, 1 o in 1..3, 2 o in 4..7)
+template <int kPhase>
+__device__ __forceinline__ uint64_t lds64_phase(uint32_t p, uint32_t o) {
+  if (kPhase == 0) return lds64(p);
+  const uint32_t al = p - o;
+  if (kPhase == 1) {
+    const uint64_t w01 = lds64(al);
+    const uint32_t w2 = lds32(al + 8), bs = 8 * o;
+    return (uint64_t)__funnelshift_r((uint32_t)w01, (uint32_t)(w01 >> 32), bs) | ((uint64_t)__funnelshift_r((uint32_t)(w01 >> 32), w2, bs) << 32);
+  }
+  const uint32_t w1 = lds32(al + 4), bs = 8 * (o - 4);
+  const uint64_t w23 = lds64(al + 8);
+  return (uint64_t)__funnelshift_r(w1, (uint32_t)w23, bs) | ((uint64_t)__funnelshift_r((uint32_t)w23, (uint32_t)(w23 >> 32), bs) << 32);
+}
+template <int kPhase>
+__device__ __forceinline__ uint64_t xxh3_staged_t(uint32_t sp, uint32_t len, uint32_t tab, unsigned lane) {
+  const uint32_t a = lane & 7, g = lane >> 3, o = sp & 7;
+  const uint64_t init[8] = {kP32_3, kP64_1, kP64_2, kP64_3, kP64_4, kP32_2, kP64_5, kP32_1};
+  uint64_t acc = init[0];
+#pragma unroll
+  for (int i = 1; i < 8; i++) acc = a == (uint32_t)i ? init[i] : acc;
+  const uint32_t tl = tab + 8 * lane;  // this lane's column of the table
+  const uint64_t k0 = lds64(tl), k1 = lds64(tl + 256), k2 = lds64(tl + 512), k3 = lds64(tl + 768), kscr = lds64(tl + 1024);
+  const uint32_t nb_blocks = (len - 1) >> 10;
+  uint32_t p = sp + 64 * g + 8 * a;  // stripe g of the current 1024-byte block, this lane's word
+  for (uint32_t n = 0; n < nb_blocks; n++, p += 1024) {
+    const uint64_t d0 = lds64_phase<kPhase>(p, o), d1 = lds64_phase<kPhase>(p + 256, o), d2 = lds64_phase<kPhase>(p + 512, o),
+                   d3 = lds64_phase<kPhase>(p + 768, o);
+    const uint64_t e0 = d0 ^ k0, e1 = d1 ^ k1, e2 = d2 ^ k2, e3 = d3 ^ k3;
+    uint64_t mul = (e0 & 0xffffffffull) * (e0 >> 32);
+    mul += (e1 & 0xffffffffull) * (e1 >> 32);
+    mul += (e2 & 0xffffffffull) * (e2 >> 32);
+    mul += (e3 & 0xffffffffull) * (e3 >> 32);
+    const uint64_t add = d0 + d1 + d2 + d3;
+    uint64_t part = mul + __shfl_xor_sync(0xffffffffu, add, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 8);
+    part += __shfl_xor_sync(0xffffffffu, part, 16);
+    acc += part;
+    acc ^= acc >> 47;
+    acc ^= kscr;
+    acc *= kP32_1;
+  }
+  {  // the partial last block: stripes g + 4i < nstripes
+    const uint32_t nstripes = ((len - 1) - 1024 * nb_blocks) >> 6;
+    uint64_t mul = 0, add = 0;
+    const uint64_t kq[4] = {k0, k1, k2, k3};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (g + 4 * i < nstripes) {
+        const uint64_t dv = lds64_phase<kPhase>(p + 256 * i, o), dk = dv ^ kq[i];
+        mul += (dk & 0xffffffffull) * (dk >> 32);
+        add += dv;
+      }
+    }
+    uint64_t part = mul + __shfl_xor_sync(0xffffffffu, add, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 8);
+    part += __shfl_xor_sync(0xffffffffu, part, 16);
+    acc += part;
+  }
+  {  // last stripe: input + len - 64 with secret offset 192 - 64 - 7 (any phase)
+    const uint64_t dv = lds64_any(sp + len - 64 + 8 * a), dk = dv ^ lds64(tl + 1280);
+    acc += (dk & 0xffffffffull) * (dk >> 32) + __shfl_xor_sync(0xffffffffu, dv, 1);
+  }
+  const uint64_t keyed = acc ^ lds64(tl + 1536);
+  const uint64_t other = __shfl_xor_sync(0xffffffffu, keyed, 1);
+  uint64_t m = (a & 1) ? 0 : mul128_fold64(keyed, other);
+  m += __shfl_xor_sync(0xffffffffu, m, 2);
+  m += __shfl_xor_sync(0xffffffffu, m, 4);
+  return xxh3_avalanche((uint64_t)len * kP64_1 + m);  // lanes 0..7 of a group hold the sum; every lane with a == 0..7 has it after the xors
+}
+static_assert(offsetof(XxhLaneTab, k) == 0 && offsetof(XxhLaneTab, kscr) == 1024 && offsetof(XxhLaneTab, klast) == 1280 &&
+                  offsetof(XxhLaneTab, kmrg) == 1536,
+              "xxh3_staged_t addresses the lane table by these offsets");
+// block checksum (table/format.cc:468-509) of the staged block: type 4 = XXH3, 1 = CRC32C
+__device__ __forceinline__ uint32_t staged_block_checksum(uint32_t type, uint32_t sp, const uint8_t* p, uint32_t n, uint8_t last_byte, uint32_t xtab,
+                                                          unsigned lane) {
+  if (type == 4 && n > 240) {
+    const uint32_t o = sp & 7;
+    const uint64_t h = o == 0 ? xxh3_staged_t<0>(sp, n, xtab, lane) : o < 4 ? xxh3_staged_t<1>(sp, n, xtab, lane) : xxh3_staged_t<2>(sp, n, xtab, lane);
+    return (uint32_t)__shfl_sync(0xffffffffu, h, 0) ^ (uint32_t)last_byte * 0x6b9083d9u;
+  }
+  return block_checksum_warp(type, p, n, last_byte);
 }
 
 // ---- encoded entry sizes (BlockBuilder::AddWithLastKey, block_builder.cc:177-253) --------------------------------------

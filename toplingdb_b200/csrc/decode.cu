@@ -15,6 +15,7 @@
 //                              per interval), block checksum (warp-cooperative XXH3 / CRC32C), decoupled look-back for
 //                              the global entry position, one-entry-per-lane key reconstruction by a scan over the
 //                              prefix-decompression maps, coalesced column stores (details above the kernel)
+#include <cstddef>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -204,50 +205,16 @@ constexpr int kDecWarps = 8;
 constexpr int kDecSlice = 4608;            // bytes staged per warp and buffer (block + trailer + phase); larger blocks are read in place
 constexpr int kDecVecs = kDecSlice / 16;   // 288
 constexpr int kDecRows = 16, kDecRowLen = 16;  // fast path: restart intervals per block, entries per interval
-// Every warp owns TWO staging slices: while it parses block n out of one, the TMA engine (cp.async.bulk, completion on an mbarrier)
-// fills the other with block n + 1 -- the warp never waits for a DRAM round trip except for its very first block.
+// A warp stages its block with ONE bulk copy (TMA, cp.async.bulk) that completes on the warp's mbarrier.  (Measured: a second slice
+// per warp with the next block's copy in flight made the kernel slower -- a ticket taken ahead of time delays the moment its block's
+// entry count is published, and the successors' look-backs wait for it; see profiles/README.md.)
 struct DecWarpSmem {
-  uint4 slice[2][kDecVecs];
+  uint4 slice[kDecVecs];
   uint16_t tab[kDecRows * kDecRowLen];  // entry offsets, one row per restart interval
   uint16_t ex[32];                      // entries before each interval
-  uint64_t bar[2];                      // mbarriers: slice s has landed
+  uint64_t bar;                         // mbarrier: the slice has landed
+  uint64_t pad;
 };
-// per-lane XXH3 constants (lane l: accumulator lane a = l & 7, stripe group g = l >> 3), computed once per CTA
-struct XxhLaneTab {
-  uint64_t k[4][32];   // secret words of the four stripes a lane owns inside a 1024-byte block
-  uint64_t kscr[32];   // scramble secret
-  uint64_t klast[32];  // secret of the last stripe
-  uint64_t kmrg[32];   // merge secret
-};
-
-// ---- mbarrier + TMA bulk copy (global -> shared), sm_90+ ----------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// size: multiple of 16; dst / src: 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-               "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-
 // entry header (three varint32: shared, non_shared, value length) from the 8 bytes h at p; false on malformed / unsupported
 __device__ __forceinline__ bool parse_header(uint64_t h, const uint8_t* p, const uint8_t* end, uint32_t* shared, uint32_t* non_shared,
                                              uint32_t* vlen, uint32_t* hdr, uint32_t* __restrict__ err) {
@@ -423,35 +390,6 @@ __device__ __forceinline__ void record_run_starts(const FileDesc* __restrict__ f
   }
 }
 
-// ---- explicit shared-memory accesses by 32-bit shared address (keeps the hot loops free of generic 64-bit addressing)
-__device__ __forceinline__ uint64_t lds64(uint32_t a) {
-  uint64_t v;
-  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-// 4 / 8 bytes at any alignment (reads up to 7 bytes past the value, inside the slice)
-__device__ __forceinline__ uint32_t lds32_any(uint32_t a) {
-  const uint32_t al = a & ~3u;
-  return __funnelshift_r(lds32(al), lds32(al + 4), (a & 3) * 8);
-}
-__device__ __forceinline__ uint64_t shr128(uint64_t lo, uint64_t hi, uint32_t s) {  // (hi:lo) >> s, s in {0, 8, .., 56}
-  return s ? (lo >> s) | (hi << (64 - s)) : lo;
-}
-__device__ __forceinline__ uint64_t lds64_any(uint32_t a) {
-  const uint32_t al = a & ~7u;
-  return shr128(lds64(al), lds64(al + 8), (a & 7) * 8);
-}
 // entry header from its first 8 bytes; false when the three varints need more than 8 bytes or exceed the device format
 __device__ __forceinline__ bool parse_header8(uint64_t h, uint32_t* shared, uint32_t* non_shared, uint32_t* vlen, uint32_t* hdr) {
   if (((h | (h >> 8) | (h >> 16)) & 0x80) == 0) {  // DecodeEntry fast path (block.cc:44-50): three one-byte lengths
@@ -494,17 +432,37 @@ __device__ __forceinline__ void fill_key_mask_table(uint64_t* tab) {
   }
 }
 
-// Fast path for a block staged in the warp's slice at byte `shift`.  Returns false (nothing published) when the block
-// is outside the fast path's limits (restart intervals / entries per interval / header length) and has to take
+// inclusive scan of the prefix-decompression maps (m, D) inside a half-warp, over the first kNW key words only: word w of every
+// key of the row is its own suffix when no entry of the row shares more than 8 w bytes with its predecessor
+template <int kNW>
+__device__ __forceinline__ void scan_key_maps(uint32_t mask_tab, uint32_t i, uint32_t& m, uint64_t& D0, uint64_t& D1, uint64_t& D2) {
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    const uint32_t lm = __shfl_up_sync(0xffffffffu, m, d, 16);
+    uint64_t l0 = 0, l1 = 0, l2 = 0;
+    if (kNW > 0) l0 = __shfl_up_sync(0xffffffffu, D0, d, 16);
+    if (kNW > 1) l1 = __shfl_up_sync(0xffffffffu, D1, d, 16);
+    if (kNW > 2) l2 = __shfl_up_sync(0xffffffffu, D2, d, 16);
+    if (i >= (uint32_t)d) {
+      const uint32_t mt = mask_tab + 24 * m;
+      if (kNW > 0) D0 |= l0 & lds64(mt);
+      if (kNW > 1) D1 |= l1 & lds64(mt + 8);
+      if (kNW > 2) D2 |= l2 & lds64(mt + 16);
+      m = lm < m ? lm : m;
+    }
+  }
+}
+
+// Fast path for a block staged in shared memory at address sp (generic pointer p).  Returns false (nothing published) when the
+// block is outside the fast path's limits (restart intervals / entries per interval / header length) and has to take
 // decode_block_slow.
-__device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t mask_tab, uint32_t shift, const uint8_t* src, uint32_t size,
-                                                  uint32_t cksum, uint32_t verify, uint32_t b, int f, const FileDesc* __restrict__ files,
-                                                  int nfiles, uint32_t nblk, uint64_t n_total, KeyColsMut out,
+__device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t sp, const uint8_t* p, uint32_t mask_tab, uint32_t xtab, const uint8_t* src,
+                                                  uint32_t size, uint32_t cksum, uint32_t verify, uint32_t b, int f,
+                                                  const FileDesc* __restrict__ files, int nfiles, uint32_t nblk, uint64_t n_total, KeyColsMut out,
                                                   unsigned long long* blk_state, uint64_t* __restrict__ run_start,
                                                   uint64_t* __restrict__ total_out, uint32_t* __restrict__ err, unsigned lane) {
-  // shared addresses of the block's first byte, the offset table and the interval prefix.  The empty asm makes them opaque:
-  // under register pressure the compiler otherwise re-derives them (S2R + address arithmetic) inside the hot loops
-  uint32_t sp = (uint32_t)__cvta_generic_to_shared(ws.slice) + shift;
+  // shared addresses of the offset table and the interval prefix.  The empty asm makes them opaque: under register pressure
+  // the compiler otherwise re-derives them (S2R + address arithmetic) inside the hot loops
   uint32_t stab = (uint32_t)__cvta_generic_to_shared(ws.tab), sex = (uint32_t)__cvta_generic_to_shared(ws.ex);
   asm volatile("" : "+r"(sp), "+r"(stab), "+r"(sex), "+r"(mask_tab));
   const uint32_t foot = lds32_any(sp + size - 4);
@@ -520,14 +478,17 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t mask
     const uint32_t r1 = lane + 1 < nr ? lds32_any(srest + 4 * (lane + 1)) : data_end;
     if (!(r0 <= r1 && r1 <= data_end && (lane != 0 || r0 == 0))) bad = true;
     uint32_t q = r0;
+    const uint32_t trow = stab + 2 * (lane * kDecRowLen);
     while (!bad && q < r1) {
-      const uint32_t h4 = lds32_any(sp + q);  // the common header is three one-byte lengths
+      // the common header is three one-byte lengths (DecodeEntry fast path, block.cc:44-50): shared, non_shared, value length
+      const uint32_t a = sp + q;
+      const uint32_t h0 = lds8(a), h1 = lds8(a + 1), h2 = lds8(a + 2);
       uint32_t adv;
-      if ((h4 & 0x808080u) == 0) {
-        adv = 3 + ((h4 >> 8) & 0xff) + ((h4 >> 16) & 0xff);
+      if (((h0 | h1 | h2) & 0x80u) == 0) {
+        adv = 3 + h1 + h2;
       } else {
         uint32_t sh, ns, vl, hd;
-        if (!parse_header8(lds64_any(sp + q), &sh, &ns, &vl, &hd)) {
+        if (!parse_header8(lds64_any(a), &sh, &ns, &vl, &hd)) {
           exotic = true;
           break;
         }
@@ -537,7 +498,7 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t mask
         bad = true;
         break;
       }
-      if (c < (uint32_t)kDecRowLen) sts16(stab + 2 * (lane * kDecRowLen + c), q);
+      if (c < (uint32_t)kDecRowLen) sts16(trow + 2 * c, q);
       q += adv;
       c++;
     }
@@ -554,14 +515,13 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t mask
   if (lane <= nr) sts16(sex + 2 * lane, inc - c);  // ex[nr] = cnt
   publish_block_count(blk_state, b, cnt, lane);    // successors can look back while this warp checksums
   {
-    const uint8_t* p = reinterpret_cast<const uint8_t*>(ws.slice) + shift;
-    const uint8_t ctype = p[size];
+    const uint32_t ctype = lds8(sp + size);
     if (ctype != 0) {
       if (lane == 0) atomicOr(err, kErrCompressed);
       ok = false;
     } else if (verify && cksum != 0) {
       const uint32_t want = lds32_any(sp + size + 1);
-      const uint32_t got = block_checksum_warp(cksum, p, size, ctype);
+      const uint32_t got = staged_block_checksum(cksum, sp, p, size, (uint8_t)ctype, xtab, lane);
       if (want != got) {
         if (lane == 0) atomicOr(err, kErrChecksum);
         ok = false;
@@ -591,7 +551,18 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t mask
     if (valid) {
       const uint32_t q = lds16(stab + 2 * (row * kDecRowLen + i));
       uint32_t non_shared, hdr;
-      parse_header8(lds64_any(sp + q), &shared, &non_shared, &vlen, &hdr);  // validated by the walk
+      {
+        const uint32_t a = sp + q;
+        const uint32_t h0 = lds8(a), h1 = lds8(a + 1), h2 = lds8(a + 2);
+        if (((h0 | h1 | h2) & 0x80u) == 0) {
+          shared = h0;
+          non_shared = h1;
+          vlen = h2;
+          hdr = 3;
+        } else {
+          parse_header8(lds64_any(a), &shared, &non_shared, &vlen, &hdr);  // validated by the walk
+        }
+      }
       if (shared + non_shared < 8) {
         atomicOr(err, kErrCorruptBlock);
         ebad = true;
@@ -619,19 +590,14 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t mask
       atomicOr(err, kErrCorruptBlock);
       ebad = true;
     }
-    // inclusive scan of (m, D) inside the half-warp: left = earlier entries, right = own accumulated map
-#pragma unroll
-    for (int d = 1; d < 16; d <<= 1) {
-      const uint32_t lm = __shfl_up_sync(0xffffffffu, m, d, 16);
-      const uint64_t l0 = __shfl_up_sync(0xffffffffu, D0, d, 16), l1 = __shfl_up_sync(0xffffffffu, D1, d, 16),
-                     l2 = __shfl_up_sync(0xffffffffu, D2, d, 16);
-      if (i >= (uint32_t)d) {
-        const uint32_t mt = mask_tab + 24 * m;
-        D0 |= l0 & lds64(mt);
-        D1 |= l1 & lds64(mt + 8);
-        D2 |= l2 & lds64(mt + 16);
-        m = lm < m ? lm : m;
-      }
+    // inclusive scan of (m, D) inside the half-warp: left = earlier entries, right = own accumulated map.  Only the key words that
+    // some entry of these two rows shares with its predecessor take part (sorted keys usually share a few leading bytes only).
+    {
+      const uint32_t mx = __reduce_max_sync(0xffffffffu, shared);
+      if (mx == 0) {
+      } else if (mx <= 8) scan_key_maps<1>(mask_tab, i, m, D0, D1, D2);
+      else if (mx <= 16) scan_key_maps<2>(mask_tab, i, m, D0, D1, D2);
+      else scan_key_maps<3>(mask_tab, i, m, D0, D1, D2);
     }
     if (valid && !ebad) {  // the interval's first entry has shared == 0, so D is the whole key
       uint64_t hi, lo, tr;
@@ -730,40 +696,48 @@ block_decode_fused_kernel(const FileDesc* __restrict__ files, int nfiles, const 
                           const uint32_t* __restrict__ blk_size, uint32_t nblk, uint32_t verify, uint64_t n_total, KeyColsMut out,
                           unsigned long long* blk_state, uint32_t* ticket, uint64_t* __restrict__ run_start,
                           uint64_t* __restrict__ total_out, uint32_t* __restrict__ err) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t s_mask[25 * 3];
+  __shared__ XxhLaneTab s_xtab;
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   DecWarpSmem& ws = reinterpret_cast<DecWarpSmem*>(smem)[w];
   fill_key_mask_table(s_mask);
-  const uint32_t mask_tab = (uint32_t)__cvta_generic_to_shared(s_mask);
-  __syncthreads();  // mask table ready
+  fill_xxh_lane_tab(&s_xtab);
+  const uint32_t mask_tab = (uint32_t)__cvta_generic_to_shared(s_mask), xtab = (uint32_t)__cvta_generic_to_shared(&s_xtab);
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&ws.bar);
+  const uint32_t slice = (uint32_t)__cvta_generic_to_shared(&ws.slice[0]);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();  // tables and barriers ready
+  uint32_t parity = 0;
   for (;;) {
     // one ticket per warp and block: blocks are started in ticket order (the look-back needs every predecessor running),
     // and warps stay independent of each other -- no CTA-wide barrier couples a warp to its neighbours' look-back waits
     uint32_t tk = 0;
     if (lane == 0) tk = atomicAdd(ticket, 1u);
-    const uint64_t b64 = __shfl_sync(0xffffffffu, tk, 0);
-    if (b64 >= nblk) break;
-    const uint32_t b = (uint32_t)b64;
-    const int f = file_of_block(files, nfiles, b);
-    const uint8_t* src = files[f].base + blk_off[b];
+    const uint32_t b = __shfl_sync(0xffffffffu, tk, 0);
+    if (b >= nblk) break;
+    const uint64_t bo = blk_off[b];
+    const int f = (int)(bo >> kBlkFileShift);
+    const uint8_t* src = files[f].base + (bo & kBlkOffMask);
     const uint32_t size = blk_size[b], cksum = files[f].cksum;
     const uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15;
     const uint32_t shift = (uint32_t)((uintptr_t)src - a0);
     const uint32_t nvec = (shift + size + 5 + 15) >> 4;
     bool done = false;
-    if (nvec <= (uint32_t)kDecVecs - 3 && size >= 8) {  // 40-byte parse windows may run 32 bytes past the trailer
-      const uint4* g = reinterpret_cast<const uint4*>(a0);
-      const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ws.slice);
-#pragma unroll
-      for (int i = 0; i < kDecPerLane; i++) {
-        const uint32_t v = lane + 32 * i;
-        if (v < nvec) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16 * v), "l"(g + v) : "memory");
+    if (nvec <= (uint32_t)kDecVecs - 3 && size >= 8) {  // parse windows may run 32 bytes past the trailer
+      if (lane == 0) {
+        // every lane finished reading the slice (__syncwarp below); order those generic-proxy reads before the async-proxy write
+        fence_async_smem();
+        mbar_expect_tx(bar, nvec * 16);
+        bulk_g2s(slice, reinterpret_cast<const void*>(a0), nvec * 16, bar);
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      __syncwarp();
-      done = decode_block_fast(ws, mask_tab, shift, src, size, cksum, verify, b, f, files, nfiles, nblk, n_total, out, blk_state, run_start,
-                               total_out, err, lane);
+      mbar_wait(bar, parity);
+      parity ^= 1;
+      done = decode_block_fast(ws, slice + shift, reinterpret_cast<const uint8_t*>(&ws.slice[0]) + shift, mask_tab, xtab, src, size, cksum, verify, b, f,
+                               files, nfiles, nblk, n_total, out, blk_state, run_start, total_out, err, lane);
       __syncwarp();  // all lanes are done with the slice before the next block overwrites it
     }
     if (!done) decode_block_slow(src, size, cksum, verify, b, f, files, nfiles, nblk, n_total, out, blk_state, run_start, total_out, err, lane);
@@ -793,32 +767,20 @@ void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blo
 void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk,
                                uint32_t verify, uint64_t n_total, KeyColsMut out, unsigned long long* blk_state, uint32_t* ticket,
                                uint64_t* run_start, uint64_t* total_out, uint32_t* err, int sms, cudaStream_t st) {
-  static int occ = 0;
+  constexpr int kCtasPerSm = 4;  // 64 registers (a small spill), but 32 independent warps per SM
   const int smem = kDecWarps * (int)sizeof(DecWarpSmem);
-  if (!occ) {
-    const char* e = getenv("B200C_DECODE_CTAS_PER_SM");  // tuning knob: 2 = no register spills, 3 / 4 = more warps
-    occ = e && atoi(e) >= 2 && atoi(e) <= 5 ? atoi(e) : 4;  // 4: 64 registers with a small spill, but 32 independent warps per SM
-  }
+  static_assert(kCtasPerSm * (kDecWarps * sizeof(DecWarpSmem) + 4096) <= 227 * 1024, "four decode CTAs must fit one SM");
   static PerDeviceFlag attr;
   const uint64_t dev_bit = attr.bit_of_current_device();
   if (!attr.is_set(dev_bit)) {
-    cudaFuncSetAttribute(block_decode_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(block_decode_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(block_decode_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(block_decode_fused_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(block_decode_fused_kernel<kCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr.set(dev_bit);
   }
   const unsigned per = kDecWarps;
-  unsigned want = (nblk + per - 1) / per, cap = (unsigned)sms * (unsigned)occ;
+  unsigned want = (nblk + per - 1) / per, cap = (unsigned)sms * (unsigned)kCtasPerSm;
   const unsigned grid = want < cap ? (want ? want : 1) : cap;
-#define B200C_LAUNCH_DEC(N)                                                                                                       \
-  block_decode_fused_kernel<N><<<grid, kDecWarps * 32, smem, st>>>(files_dev, nfiles, blk_off, blk_size, nblk, verify, n_total, out, \
-                                                                    blk_state, ticket, run_start, total_out, err)
-  if (occ == 2) B200C_LAUNCH_DEC(2);
-  else if (occ == 4) B200C_LAUNCH_DEC(4);
-  else if (occ == 5) B200C_LAUNCH_DEC(5);
-  else B200C_LAUNCH_DEC(3);
-#undef B200C_LAUNCH_DEC
+  block_decode_fused_kernel<kCtasPerSm><<<grid, kDecWarps * 32, smem, st>>>(files_dev, nfiles, blk_off, blk_size, nblk, verify, n_total, out,
+                                                                             blk_state, ticket, run_start, total_out, err);
 }
 void launch_gather_values(KeyCols in, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st) {
   if (in.n == 0) return;

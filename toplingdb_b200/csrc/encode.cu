@@ -1410,9 +1410,13 @@ template <int kMinCtas>
 __global__ void __launch_bounds__(kEmitWarps * 32, kMinCtas)
 encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, uint8_t* const* __restrict__ out_base,
                    uint32_t slot_bytes, uint32_t* __restrict__ err) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ XxhLaneTab s_xtab;
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint8_t* img = smem + (size_t)w * slot_bytes;
+  uint8_t* const slot = smem + (size_t)w * slot_bytes;  // 16-byte aligned (slot_bytes is a multiple of 256)
+  fill_xxh_lane_tab(&s_xtab);
+  __syncthreads();
+  const uint32_t xtab = (uint32_t)__cvta_generic_to_shared(&s_xtab);
   const uint32_t R = ep.restart_interval;
   const uint32_t rmask = (R & (R - 1)) == 0 ? R - 1 : 0xffffffffu;  // power-of-two restart interval: mask instead of %
   const uint64_t stride = (uint64_t)gridDim.x * kEmitWarps;
@@ -1420,9 +1424,15 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
     const BlockRec br = wk.blocks[b];
     const uint32_t E = br.n_entries;
     const uint64_t e0 = br.first_entry;
-    __syncwarp();  // the previous block's image has been stored
+    // The image is built at the destination's 16-byte phase, so that everything between the first and the last 16-byte boundary
+    // of the block leaves shared memory as ONE bulk copy (TMA) instead of a load / re-align / store loop.
+    uint8_t* const gdst = out_base[br.file_idx] + br.file_off;
+    const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15);
+    uint8_t* const img = slot + shift;
     if (E > (uint32_t)kEmitMaxEntries) {
-      emit_block_warp(m, ep, wk, b, out_base, img, slot_bytes);
+      if (lane == 0) bulk_wait_read0();  // the previous block's bulk store has finished reading the slot
+      __syncwarp();
+      emit_block_warp(m, ep, wk, b, out_base, slot, slot_bytes);
       continue;
     }
     // ---- pass 1: sizes.  All column loads of the lane's entries are issued before the first use.
@@ -1461,10 +1471,14 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
     const uint64_t inc = warp_incl_scan64(tsum);
     const uint64_t body64 = __shfl_sync(0xffffffffu, inc, 31);
     const uint32_t nrest = (E + R - 1) / R;
-    if (body64 + 4ull * nrest + 4 + 5 + 32 > slot_bytes) {  // uniform
-      emit_block_warp(m, ep, wk, b, out_base, img, slot_bytes);
+    if (body64 + 4ull * nrest + 4 + 5 + 32 + 16 > slot_bytes) {  // uniform
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      emit_block_warp(m, ep, wk, b, out_base, slot, slot_bytes);
       continue;
     }
+    if (lane == 0) bulk_wait_read0();  // (the column loads above overlapped the previous block's bulk store)
+    __syncwarp();
     const uint32_t body = (uint32_t)body64;
     uint32_t off[kEmitPerLane];
     {
@@ -1577,7 +1591,6 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
       }
     }
     // ---- restart footer, checksum trailer, store
-    uint8_t* gdst = out_base[br.file_idx] + br.file_off;
     const uint32_t payload = body + 4 * nrest + 4;
     if (lane == 0) {
       uint8_t* fp = img + body + 4u * nrest;
@@ -1587,7 +1600,7 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
       fp[3] = (uint8_t)(nrest >> 24);
     }
     __syncwarp();
-    const uint32_t ck = block_checksum_warp(ep.checksum, img, payload, 0);
+    const uint32_t ck = staged_block_checksum(ep.checksum, (uint32_t)__cvta_generic_to_shared(img), img, payload, 0, xtab, lane);
     __syncwarp();  // the checksum's 8-byte loads may touch the trailer bytes written next
     if (lane == 0) {
       uint8_t* tp = img + payload;
@@ -1597,23 +1610,18 @@ encode_emit_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t nblocks, 
       tp[3] = (uint8_t)(ck >> 16);
       tp[4] = (uint8_t)(ck >> 24);
     }
+    fence_async_smem();  // this lane's image bytes are visible to the TMA engine
     __syncwarp();
     const uint32_t total = payload + 5;
-    const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15);
     uint32_t head = shift ? 16 - shift : 0;
     if (head > total) head = total;
+    const uint32_t mid = (total - head) & ~15u;
+    if (lane == 0 && mid) bulk_s2g(gdst + head, (uint32_t)__cvta_generic_to_shared(img + head), mid);
     if (lane < head) gdst[lane] = img[lane];
-    const uint32_t nvec = (total - head) >> 4;
-    const uint4* sv = reinterpret_cast<const uint4*>(img);
-    uint4* gv = reinterpret_cast<uint4*>(gdst + head);
-    if (head == 0) {
-      for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
-    } else {
-      for (uint32_t i = lane; i < nvec; i += 32) gv[i] = shift16(sv[i], sv[i + 1], head);
-    }
-    const uint32_t done = head + (nvec << 4);
+    const uint32_t done = head + mid;
     if (done + lane < total) gdst[done + lane] = img[done + lane];
   }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // no bulk store may outlive the CTA's shared memory
   (void)err;
 }
 
@@ -2026,14 +2034,15 @@ void launch_encode_emit(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nbloc
   static PerDeviceFlag attr;
   const uint64_t dev_bit = attr.bit_of_current_device();
   if (!attr.is_set(dev_bit)) {
-    cudaFuncSetAttribute(encode_emit_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(encode_emit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(encode_emit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // (the kernel also has ~2 KB of static shared memory: the XXH3 lane table)
+    cudaFuncSetAttribute(encode_emit_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(encode_emit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(encode_emit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr.set(dev_bit);
   }
   const uint32_t slot = encode_emit_slice(ep.block_size);
   const size_t smem = (size_t)slot * kEmitWarps;
-  unsigned per_sm = (unsigned)((228 * 1024) / (smem + 1024));
+  unsigned per_sm = (unsigned)((228 * 1024) / (smem + 1024 + 2048));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > (unsigned)occ) per_sm = (unsigned)occ;
   const uint64_t want = (nblocks + kEmitWarps - 1) / kEmitWarps;

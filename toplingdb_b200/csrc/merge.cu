@@ -14,6 +14,8 @@
 //                           output offset (count published early, offset resolved after the value-reference gathers),
 //                           coalesced write of the surviving (key, value-ref) records.
 // HBM-bound: algorithmic bytes = 36 B read per input entry + 36 B written per surviving entry.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -196,14 +198,16 @@ __device__ __forceinline__ void msel_grouped(const KeyCols& in, const GroupLanes
     }
   }
 }
+// One warp resolves kPartChunk CONSECUTIVE boundaries: the first one with the two-level search, every further one starting from
+// its predecessor's split -- between rank d and rank d' >= d every run advances by at most d' - d entries, so the brackets are
+// kMergeTile wide and lie in cache lines the previous search just touched.
+constexpr uint32_t kPartChunk = 4;
 __global__ void __launch_bounds__(128)
 merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint32_t gshift, uint64_t n_total,
                                uint64_t ntiles, uint64_t* __restrict__ splits, uint32_t* __restrict__ err) {
   const unsigned lane = threadIdx.x & 31;
-  const uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b > ntiles) return;
-  uint64_t d = b * (uint64_t)kMT;
-  if (d > n_total) d = n_total;
+  const uint64_t b0 = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPartChunk;
+  if (b0 > ntiles) return;
   GroupLanes L;
   L.gshift = gshift;
   L.g = 1u << gshift;
@@ -214,47 +218,61 @@ merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint3
   const uint32_t r = L.r, sub = L.sub;
   const uint64_t base = r < nruns ? runs.begin[r] : 0;
   const uint64_t nrun = r < nruns ? runs.end[r] - runs.begin[r] : 0;
-  uint64_t lo = (d == n_total) ? nrun : 0, hi = (d == 0) ? 0 : nrun;
-  if (d != 0 && d != n_total) {
-    // ---- level 1: the samples
-    const uint64_t S = kPartStride, msamp = (nrun + S - 1) / S;
-    uint64_t M = sub == 0 ? msamp : 0;
+  uint64_t prev_lo = 0, prev_d = 0;
+  for (uint32_t c = 0; c < kPartChunk; c++) {
+    const uint64_t b = b0 + c;
+    if (b > ntiles) break;
+    uint64_t d = b * (uint64_t)kMT;
+    if (d > n_total) d = n_total;
+    uint64_t lo = (d == n_total) ? nrun : 0, hi = (d == 0) ? 0 : nrun;
+    if (d != 0 && d != n_total) {
+      if (c != 0) {
+        lo = prev_lo;
+        hi = prev_lo + (d - prev_d) < nrun ? prev_lo + (d - prev_d) : nrun;
+      } else {
+        // ---- level 1: the samples
+        const uint64_t S = kPartStride, msamp = (nrun + S - 1) / S;
+        uint64_t M = sub == 0 ? msamp : 0;
 #pragma unroll
-    for (int dd = 16; dd; dd >>= 1) M += __shfl_xor_sync(0xffffffffu, M, dd);
-    const uint64_t T_lo = d / S, T_hi = (d + (S - 1) * (uint64_t)nruns + S - 1) / S;
-    uint64_t tlo = 0, tlo_hi = msamp;
-    if (T_lo > 0) msel_grouped(in, L, base, S, T_lo, tlo, tlo_hi);  // T_lo < M because d < n_total
-    if (tlo) lo = S * tlo - (S - 1);
-    if (T_hi < M) {
-      // the split of sample rank T_hi lies at most T_hi - T_lo samples further in every run
-      uint64_t thi = tlo, thi_hi = tlo + (T_hi - T_lo) < msamp ? tlo + (T_hi - T_lo) : msamp;
-      msel_grouped(in, L, base, S, T_hi, thi, thi_hi);
-      const uint64_t h = S * thi;
-      hi = h < nrun ? h : nrun;
+        for (int dd = 16; dd; dd >>= 1) M += __shfl_xor_sync(0xffffffffu, M, dd);
+        const uint64_t T_lo = d / S, T_hi = (d + (S - 1) * (uint64_t)nruns + S - 1) / S;
+        uint64_t tlo = 0, tlo_hi = msamp;
+        if (T_lo > 0) msel_grouped(in, L, base, S, T_lo, tlo, tlo_hi);  // T_lo < M because d < n_total
+        if (tlo) lo = S * tlo - (S - 1);
+        if (T_hi < M) {
+          // the split of sample rank T_hi lies at most T_hi - T_lo samples further in every run
+          uint64_t thi = tlo, thi_hi = tlo + (T_hi - T_lo) < msamp ? tlo + (T_hi - T_lo) : msamp;
+          msel_grouped(in, L, base, S, T_hi, thi, thi_hi);
+          const uint64_t h = S * thi;
+          hi = h < nrun ? h : nrun;
+        }
+        if (hi < lo) hi = lo;  // cannot happen for sorted runs; the rank check below reports it
+      }
     }
-    if (hi < lo) hi = lo;  // cannot happen for sorted runs; the rank check below reports it
-  }
-  // ---- level 2: exact
-  msel_grouped(in, L, base, 1, d, lo, hi);
-  uint64_t tot = sub == 0 ? lo : 0;
+    // ---- exact
+    msel_grouped(in, L, base, 1, d, lo, hi);
+    uint64_t tot = sub == 0 ? lo : 0;
 #pragma unroll
-  for (int dd = 16; dd; dd >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, dd);
-  if (tot != d && lane == 0) atomicOr(err, kErrKeyOrder);
-  if (r < nruns && sub == 0) splits[b * nruns + r] = lo;
+    for (int dd = 16; dd; dd >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, dd);
+    if (tot != d && lane == 0) atomicOr(err, kErrKeyOrder);
+    if (r < nruns && sub == 0) splits[b * nruns + r] = lo;
+    prev_lo = lo;
+    prev_d = d;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ tile merge
 // Keys stay where the coalesced load put them (structure of arrays in shared memory); the merge rounds permute a list
 // of 16-bit indices.  A comparison loads the high key word of both candidates and touches the other words only on a tie.
+constexpr uint32_t kSnapCache = 16;
 struct TileSmem {
   uint64_t hi[kMT], lo[kMT], tr[kMT];
   uint16_t idx[kMT];               // merge order: idx[o] = load position of the o-th smallest key
   uint8_t ulen[kMT];
-  uint8_t srun[kMT];               // run (segment) a load position came from
   uint32_t seg[kMaxRuns + 1];      // segment starts in load order
   uint32_t lst[2][kMaxRuns + 2];   // list bounds per merge round (ping-pong)
   uint64_t sbeg[kMaxRuns];         // absolute index of each segment's first element
-  uint64_t snaps[64];              // cached snapshots (first 64)
+  uint64_t snaps[kSnapCache];      // cached snapshots (the first kSnapCache)
   unsigned long long red[8];       // per-CTA counter staging
   unsigned long long stat[5];      // statistics of the tile's output entries (TileStat)
   uint32_t smin, smax;             // smallest / largest encoded entry size of the tile
@@ -331,12 +349,12 @@ __device__ __forceinline__ uint64_t stripe_of(const uint64_t* snaps_s, const uin
   uint32_t lo = 0, hi = ns;
   while (lo < hi) {
     uint32_t mid = (lo + hi) >> 1;
-    uint64_t v = mid < 64 ? snaps_s[mid] : snaps_g[mid];
+    uint64_t v = mid < kSnapCache ? snaps_s[mid] : snaps_g[mid];
     if (v < seq) lo = mid + 1;
     else hi = mid;
   }
-  *prev = lo == 0 ? 0 : (lo - 1 < 64 ? snaps_s[lo - 1] : snaps_g[lo - 1]);
-  return lo < ns ? (lo < 64 ? snaps_s[lo] : snaps_g[lo]) : kMaxSeq;
+  *prev = lo == 0 ? 0 : (lo - 1 < kSnapCache ? snaps_s[lo - 1] : snaps_g[lo - 1]);
+  return lo < ns ? (lo < kSnapCache ? snaps_s[lo] : snaps_g[lo]) : kMaxSeq;
 }
 
 // slow path helpers for groups that leave the tile (only with snapshots at the bottommost level)
@@ -405,7 +423,8 @@ __device__ bool group_head(const KeyCols& in, RunBounds runs, uint32_t nruns, ui
   return found;
 }
 
-__global__ void __launch_bounds__(kMThreads, 3)
+template <int kMinCtas>
+__global__ void __launch_bounds__(kMThreads, kMinCtas)
 merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                    const uint64_t* __restrict__ splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
                    MergeCounters* counters, MergeSizes ms, uint32_t* __restrict__ err, uint32_t prefetch_dist) {
@@ -420,7 +439,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     s.smin = 0xffffffffu;
     s.smax = 0;
   }
-  if (t < 64 && t < mp.nsnapshots) s.snaps[t] = mp.snapshots[t];
+  if (t < kSnapCache && t < mp.nsnapshots) s.snaps[t] = mp.snapshots[t];
   __syncthreads();
   const uint64_t tile = s.tile_id;
   if (tile >= ntiles) return;
@@ -495,16 +514,6 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         s.idx[PH(i)] = (uint16_t)i;
       }
     }
-    // source run of every load position (the column position of an entry is needed again for its value reference)
-    uint32_t lr2 = 0;
-#pragma unroll
-    for (int j = 0; j < kMV; j++) {
-      const uint32_t i = t + j * kMThreads;
-      if (i < cnt) {
-        while (i >= s.seg[lr2 + 1]) lr2++;
-        s.srun[i] = (uint8_t)lr2;
-      }
-    }
   }
   __syncthreads();
   // ---- pairwise merge rounds over the index list, in place through registers
@@ -573,8 +582,13 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   // ---- compaction-iterator rules per merged position
   const bool cond_possible = mp.bottommost && mp.nsnapshots > 0;
   auto col_of = [&](uint32_t pos) -> uint64_t {  // column position of the entry at load position pos
-    const uint32_t r = s.srun[pos];
-    return s.sbeg[r] + (pos - s.seg[r]);
+    uint32_t lo = 0, hi = k;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s.seg[mid] <= pos) lo = mid;
+      else hi = mid;
+    }
+    return s.sbeg[lo] + (pos - s.seg[lo]);
   };
   uint32_t keep_mask = 0, nkeep = 0;
   unsigned long long c_hidden = 0, c_obsolete = 0, c_indel = 0, c_kbytes = 0, c_vbytes = 0, c_silent = 0, c_userdrop = 0;
@@ -951,13 +965,14 @@ void launch_merge_partition(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t
     while (kp2 < nruns) kp2 <<= 1;
     uint32_t gshift = 0;
     while ((kp2 << (gshift + 1)) <= 32) gshift++;  // lanes per run = 32 / pow2(nruns)
-    merge_partition_grouped_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, runs, nruns, gshift, n_total, ntiles, splits, err);
+    const unsigned chunks = (warps + kPartChunk - 1) / kPartChunk;
+    merge_partition_grouped_kernel<<<(chunks + 3) / 4, 128, 0, st>>>(in, runs, nruns, gshift, n_total, ntiles, splits, err);
     return;
   }
   merge_partition_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, runs, nruns, n_total, ntiles, splits, err);
 }
 static_assert(sizeof(Key) * kMaxRuns <= sizeof(uint64_t) * kMT && 4 * kMaxRuns <= 2 * kMT, "candidate staging must fit");
-static_assert(3 * (sizeof(TileSmem) + 1024) <= 227 * 1024, "merge tile must fit three CTAs per SM");
+static_assert(4 * (sizeof(TileSmem) + 1024) <= 227 * 1024, "merge tile must fit four CTAs per SM");
 void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                         const uint64_t* splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
                         MergeCounters* counters, MergeSizes ms, uint32_t* err, cudaStream_t st) {
@@ -965,11 +980,21 @@ void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_t
   static PerDeviceFlag attr;
   const uint64_t dev_bit = attr.bit_of_current_device();
   if (!attr.is_set(dev_bit)) {
-    cudaFuncSetAttribute(merge_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    cudaFuncSetAttribute(merge_tiles_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    cudaFuncSetAttribute(merge_tiles_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
     attr.set(dev_bit);
   }
-  merge_tiles_kernel<<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state,
-                                                                          ticket, out, counters, ms, err, 148u * 3u);
+  static int occ = 0;
+  if (!occ) {
+    const char* e = getenv("B200C_MERGE_CTAS_PER_SM");  // tuning knob: 3 = 80 registers, 4 = 64 registers (spills) but 32 warps per SM
+    occ = e && atoi(e) == 4 ? 4 : 3;
+  }
+  if (occ == 4)
+    merge_tiles_kernel<4><<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state, ticket, out,
+                                                                                 counters, ms, err, 148u * 4u);
+  else
+    merge_tiles_kernel<3><<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state, ticket, out,
+                                                                                 counters, ms, err, 148u * 3u);
 }
 void launch_merge_sizes_fix(KeyCols merged, const unsigned long long* tile_state, uint64_t ntiles, MergeSizes ms, cudaStream_t st) {
   if (ntiles) merge_sizes_fix_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(merged, tile_state, ntiles, ms);
