@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200C_ABI_VERSION 6
+#define B200C_ABI_VERSION 7
 #if defined(__GNUC__)
 #define B200C_API __attribute__((visibility("default")))
 #else
@@ -174,6 +174,16 @@ B200C_API int b200c_job_create(const b200c_params* p, b200c_job** out);
  * Device memory is read by the job's own non-blocking CUDA streams from b200c_job_run() on: whatever produces it (a copy or a
  * kernel on the caller's stream) must have COMPLETED before the run call -- the library does not join the caller's streams. */
 B200C_API int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const void* data, uint64_t len, int mem_kind);
+/* Files added with the same level > 0 one after the other form ONE sorted run, like the LevelIterator MakeInputIterator builds for a
+ * level (db/version_set.cc:1076,7311-7352): they must be disjoint and in key order (checked on the device).  A job may hold any number
+ * of files but at most 64 runs (L0 files + deeper levels).  For a host image of at least 1 MiB the host -> device copy starts inside
+ * this call on a copy stream of the job (the caller's next file read overlaps it); the buffer must stay unchanged until the run ends. */
+
+/* Page-locked host memory for input images (cudaHostAlloc, portable): copies from it run at full PCIe speed and truly asynchronously.
+ * A thread that set a NUMA memory policy before the call gets the pages from that node.  ReadFile targets of the executor plugin
+ * (plugin/b200_compaction_executor.cc) come from here; replaces nothing in the reference (its local path reads through the block cache). */
+B200C_API int b200c_host_alloc(int device, uint64_t bytes, void** out);
+B200C_API void b200c_host_free(void* p);
 /* decode -> k-way merge with the compaction-iterator rules -> encode, all on the device.  Synchronous. */
 B200C_API int b200c_job_run(b200c_job* j);
 B200C_API int b200c_job_output_count(const b200c_job* j);

@@ -21,17 +21,19 @@ def job_from_params(p, output_mem="host", **extra):
     return T.CompactionJob(**kw)
 
 
-def run_product(p, inputs, device_inputs=False, **extra):
+def run_product(p, inputs, device_inputs=False, levels=None, **extra):
+    """levels: the level of every input (files of one level > 0, listed one after the other, form one sorted run); default: all L0"""
     job = job_from_params(p, **extra)
     keep = []
     for i, data in enumerate(inputs):
+        lvl = 0 if levels is None else levels[i]
         if device_inputs:
             import torch
             t = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
             keep.append(t)
-            job.add_input(t, level=0, file_number=i)
+            job.add_input(t, level=lvl, file_number=i)
         else:
-            job.add_input(data, level=0, file_number=i)
+            job.add_input(data, level=lvl, file_number=i)
     job.run()
     files = job.outputs()
     metas = [job.output_meta(i) for i in range(job.output_count())]

@@ -42,6 +42,12 @@ static void str(FILE* f, const char* s) {
 }
 
 const char* b200c_last_error(void) { return g_err; }
+int b200c_host_alloc(int device, uint64_t bytes, void** out) {
+  (void)device;
+  *out = malloc(bytes ? bytes : 1);
+  return *out ? B200C_OK : B200C_ERR_OUT_OF_MEMORY;
+}
+void b200c_host_free(void* p) { free(p); }
 uint32_t b200c_abi_version(void) { return B200C_ABI_VERSION; }
 int b200c_device_count(void) { return 1; }
 void b200c_params_init(b200c_params* p) { /* the defaults of the real library (api.cu) */

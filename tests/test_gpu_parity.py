@@ -201,3 +201,54 @@ def test_in_kernel_compaction_filter_counts_like_the_oracle(case):
     p.compaction_filter = "none"
     files2, _, st2 = run_product(p, g["inputs"])
     assert st2.num_record_drop_user == 0 and files2 != files
+
+
+def test_level_runs_lift_the_file_cap():
+    """MakeInputIterator gives every L0 file its own child and every deeper level ONE LevelIterator over its disjoint, ordered files
+    (db/version_set.cc:1076,7311-7352).  Two L0 files + 100 L1 files + 40 L2 files = 142 files but 4 sorted runs: the device takes the
+    job (round 1 refused more than 64 files); the oracle merges the same files as 142 runs, which yields the same stream because the
+    files of a level do not overlap."""
+    from gpu_harness import run_product
+    T = _T()
+    rnd = random.Random(77)
+    seq = [1]
+
+    def make_run(keys, delete_frac=0.1):
+        out = []
+        for k in keys:
+            t = 0 if rnd.random() < delete_frac else 1
+            out.append((struct.pack(">QQ", 1, k) + struct.pack("<Q", (seq[0] << 8) | t), b"" if t == 0 else rnd.randbytes(40)))
+            seq[0] += 1
+        return out
+
+    universe = 60000
+    l2_keys = sorted(rnd.sample(range(universe), 24000))
+    l1_keys = sorted(rnd.sample(range(universe), 20000))
+    l2 = make_run(l2_keys)
+    l1 = make_run(l1_keys)
+    l0b = make_run(sorted(rnd.sample(range(universe), 3000)))
+    l0a = make_run(sorted(rnd.sample(range(universe), 3000)))  # newest
+
+    def split(run, n):
+        per = (len(run) + n - 1) // n
+        return [run[i:i + per] for i in range(0, len(run), per)]
+
+    files = [l0a, l0b] + split(l1, 100) + split(l2, 40)
+    levels = [0, 0] + [1] * 100 + [2] * 40
+    assert len(files) == 142 and len(levels) == 142
+    inputs = [H.oracle_build_sst(H.Params(), H.kvstream(f)) for f in files]
+    p = H.Params(bottommost_level=True, max_output_file_size=256 << 10, output_level=2, file_creation_times=[5])
+    want, _, wst = H.oracle_compact(p, inputs)
+    files_out, _, st = run_product(p, inputs, levels=levels)
+    assert files_out == want
+    for k in H.STAT_KEYS:
+        assert getattr(st, k) == getattr(wst, k), k
+    # the same files all declared L0 are 142 runs: still refused
+    with pytest.raises(T.B200cError) as ei:
+        run_product(p, inputs)
+    assert ei.value.code == T.native.ERR_NOT_SUPPORTED
+    # files of one level that are out of order are reported, not merged wrongly
+    bad_inputs = [inputs[0], inputs[1], inputs[3], inputs[2]] + inputs[4:]
+    with pytest.raises(T.B200cError) as ei:
+        run_product(p, bad_inputs, levels=levels)
+    assert ei.value.code == T.native.ERR_CORRUPTION

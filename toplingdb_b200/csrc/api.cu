@@ -73,6 +73,8 @@ struct Input {
   uint64_t len;
   int mem_kind;
   DevBuf staged;  // device copy of a host input
+  cudaEvent_t up_ev = nullptr;  // eager upload (started by b200c_job_add_input on the copy stream) has finished
+  bool uploaded = false;        // the staged copy is current for the NEXT run (consumed by it)
   const uint8_t* dev = nullptr;
   InputTail tail;
 };
@@ -121,6 +123,7 @@ struct b200c_job {
   int sms = 148;
   cudaStream_t st = nullptr;
   cudaStream_t st2 = nullptr;  // side stream (higher priority): serial / small kernels that overlap a bulk kernel on `st`
+  cudaStream_t st_up = nullptr;  // copy stream of the eager input uploads
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evx[4] = {nullptr, nullptr, nullptr, nullptr};  // fork / join points between st and st2
   // device state
@@ -128,7 +131,8 @@ struct b200c_job {
   DevBuf dec[4], mrg[4], splits, tile_state, snaps_d;
   DevBuf esz, eshared, tstat, nxt, disk, rows, tstate, grows, gstate, gflag, gsync, idx_contrib, idx_contrib_off, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
   uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
-  uint32_t nfiles_out = 0;
+  uint32_t nfiles_out = 0, nruns = 0;
+  DevBuf run_bounds, run_first_d;  // [begin[K] | end[K]] of the sorted runs in the decoded columns; first file of each run
   std::vector<uint64_t> run_start_h;
   HostBuf host_out;
   std::vector<GpKey> gp_small, gp_large;  // grandparent boundaries in column form (packed at job creation)
@@ -440,8 +444,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       for (uint32_t f = 0; f < nfiles; f++) coff[f + 1] = coff[f] + (frs[f].n_blocks * 48 + 64) / 1024 + 1;
       CU(j->idx_contrib.reserve(64 * (coff[nfiles] + 1)));
       CU(j->idx_contrib_off.reserve(8 * (nfiles + 1)));
-      if (int rc = upload_small(j, j->idx_contrib_off.p, coff.data(), 8 * (nfiles + 1))) return rc;
-      CU(cudaStreamSynchronize(st));  // coff is a temporary
+      if (int rc = upload_small(j, j->idx_contrib_off.p, coff.data(), 8 * (nfiles + 1))) return rc;  // (copied into pinned staging)
       W.idx_contrib = j->idx_contrib.as<uint64_t>();
       W.idx_contrib_off = j->idx_contrib_off.as<uint64_t>();
     }
@@ -681,7 +684,6 @@ int run_job(b200c_job* j, int until) {
   memset(&j->stats, 0, sizeof j->stats);
   const int k = (int)j->inputs.size();
   if (k == 0) return fail(B200C_ERR_INVALID_ARGUMENT, "job has no inputs");
-  if (k > kMaxRuns) return fail(B200C_ERR_NOT_SUPPORTED, "more than 64 input runs");
 
   // ---------------- inputs: resident image + tail
   CU(cudaEventRecord(j->ev[0], st));
@@ -706,8 +708,13 @@ int run_job(b200c_job* j, int until) {
     int rc = fetch_tail(j, in, in.mem_kind != B200C_MEM_HOST && in.len >= 53 ? j->pin_small.p + (size_t)i * kTailFetch : nullptr);
     if (rc) return rc;
     if (in.mem_kind == B200C_MEM_HOST) {
-      CU(in.staged.reserve(in.len + 64));
-      CU(cudaMemcpyAsync(in.staged.p, in.data, in.len, cudaMemcpyHostToDevice, st));
+      if (in.uploaded) {  // b200c_job_add_input already started the copy (it overlapped the caller's file reads)
+        CU(cudaStreamWaitEvent(st, in.up_ev, 0));
+        in.uploaded = false;  // a later run of the same job copies again: the host buffer may have changed
+      } else {
+        CU(in.staged.reserve(in.len + 64));
+        CU(cudaMemcpyAsync(in.staged.p, in.data, in.len, cudaMemcpyHostToDevice, st));
+      }
       in.dev = in.staged.as<uint8_t>();
     } else {
       if ((uintptr_t)in.data & 15) return fail(B200C_ERR_INVALID_ARGUMENT, "device input images must be 16-byte aligned");
@@ -794,15 +801,29 @@ int run_job(b200c_job* j, int until) {
     return B200C_OK;
   }
 
+  // ---------------- runs: an L0 file is a run of its own, all files of a deeper level form ONE run (they are disjoint and ordered:
+  // LevelIterator, db/version_set.cc:1076,7311-7352).  The files were decoded back to back, so a run is a range of the columns.
+  std::vector<uint32_t> run_first;  // first file of every run, plus the file count
+  for (int i = 0; i < k; i++)
+    if (i == 0 || j->inputs[i].level <= 0 || j->inputs[i].level != j->inputs[i - 1].level) run_first.push_back((uint32_t)i);
+  const uint32_t K = (uint32_t)run_first.size();
+  run_first.push_back((uint32_t)k);
+  if (K > (uint32_t)kMaxRuns) return fail(B200C_ERR_NOT_SUPPORTED, "more than 64 sorted runs (L0 files + levels)");
+  j->nruns = K;
+  CU(j->run_bounds.reserve(16 * (size_t)(K + 1)));
+  CU(j->run_first_d.reserve(4 * (size_t)(K + 2)));
+  if (int rc = upload_small(j, j->run_first_d.p, run_first.data(), 4 * (size_t)(K + 1))) return rc;
+  launch_run_bounds(decc, j->run_start.as<uint64_t>(), j->run_first_d.as<uint32_t>(), K, j->run_bounds.as<uint64_t>(), err, st);
+  launches++;
+  RunBounds runs{j->run_bounds.as<uint64_t>(), j->run_bounds.as<uint64_t>() + K};
   // ---------------- sub-compaction key range: clip every run, the merge and everything behind it only see [start, end)
-  RunBounds runs{j->run_start.as<uint64_t>(), j->run_start.as<uint64_t>() + 1};
   const bool clipped = P.has_range_start || P.has_range_end;
   const uint64_t n_decoded = N;
   uint64_t N_in = N, range_value_bytes = 0;
   if (clipped) {
-    CU(j->clip_d.reserve(16 * (k + 1)));
+    CU(j->clip_d.reserve(16 * (size_t)(K + 1)));
     j->kt_begin("merge.clip");
-    launch_clip_runs(decc, j->run_start.as<uint64_t>(), (uint32_t)k, j->range_lo, P.has_range_start, j->range_hi, P.has_range_end,
+    launch_clip_runs(decc, runs, K, j->range_lo, P.has_range_start, j->range_hi, P.has_range_end,
                      j->clip_d.as<uint64_t>(), reinterpret_cast<unsigned long long*>(small + kSlotClip), st);
     j->kt_end();
     launches++;
@@ -814,7 +835,7 @@ int run_job(b200c_job* j, int until) {
     N_in = hc[kSlotClip];
     range_value_bytes = hc[kSlotClip + 1];
     if (N_in > n_decoded) return fail(B200C_ERR_CUDA, "internal: clipped entry count exceeds the input");
-    runs = RunBounds{j->clip_d.as<uint64_t>(), j->clip_d.as<uint64_t>() + k};
+    runs = RunBounds{j->clip_d.as<uint64_t>(), j->clip_d.as<uint64_t>() + K};
     j->stats.num_input_records = N_in;
   }
   return run_merge_encode(j, until, decc, runs, n_decoded, N_in, clipped, range_value_bytes, small, err, launches);
@@ -825,7 +846,7 @@ int run_merge_encode(b200c_job* j, int until, KeyCols decc, RunBounds runs, uint
                      uint64_t range_value_bytes, uint64_t* small, uint32_t* err, uint64_t launches) {
   const b200c_params& P = j->p;
   cudaStream_t st = j->st;
-  const size_t k = j->inputs.size();
+  const size_t k = j->nruns;  // sorted runs (not files)
   // ---------------- merge
   const uint64_t mtiles = (N + kMergeTile - 1) / kMergeTile;
   CU(j->splits.reserve(8 * (mtiles + 1) * k));
@@ -1120,7 +1141,32 @@ int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const voi
   in.data = static_cast<const uint8_t*>(data);
   in.len = len;
   in.mem_kind = mem_kind;
+  if (mem_kind == B200C_MEM_HOST && len >= (1u << 20) && !getenv("B200C_NO_EAGER_UPLOAD")) {
+    // Start the host -> device copy now, on the job's copy stream: a caller that reads its input files one after the other (the
+    // executor plugin) gets the PCIe transfer of file i overlapped with the read of file i + 1.  Failures here are not errors: the
+    // run copies the file itself when no eager copy is pending.
+    if (cudaSetDevice(j->p.device) == cudaSuccess && (j->st_up || cudaStreamCreateWithFlags(&j->st_up, cudaStreamNonBlocking) == cudaSuccess) &&
+        in.staged.reserve(len + 64) == cudaSuccess && cudaEventCreateWithFlags(&in.up_ev, cudaEventDisableTiming) == cudaSuccess &&
+        cudaMemcpyAsync(in.staged.p, data, len, cudaMemcpyHostToDevice, j->st_up) == cudaSuccess &&
+        cudaEventRecord(in.up_ev, j->st_up) == cudaSuccess) {
+      in.uploaded = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
   return B200C_OK;
+}
+
+int b200c_host_alloc(int device, uint64_t bytes, void** out) {
+  if (!out) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (b200c_device_count() <= 0) return fail(B200C_ERR_NO_DEVICE, "no CUDA device");
+  CU(cudaSetDevice(device));
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return B200C_OK;
+}
+void b200c_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 int b200c_job_run(b200c_job* j) {
@@ -1164,7 +1210,7 @@ int b200c_job_get_stats(const b200c_job* j, b200c_stats* s) {
 void b200c_job_destroy(b200c_job* j) {
   if (!j) return;
   cudaSetDevice(j->p.device);
-  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->small,
+  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->run_bounds, &j->run_first_d, &j->small,
                    &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
                    &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->tstat, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->gsync, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};
@@ -1177,7 +1223,12 @@ void b200c_job_destroy(b200c_job* j) {
   j->clip_d.release();
   j->vfiles_d.release();
   j->vrun_start.release();
-  for (auto& in : j->inputs) in.staged.release();
+  if (j->st_up) cudaStreamSynchronize(j->st_up);  // an eager upload may still be reading a caller's buffer
+  for (auto& in : j->inputs) {
+    in.staged.release();
+    if (in.up_ev) cudaEventDestroy(in.up_ev);
+  }
+  if (j->st_up) cudaStreamDestroy(j->st_up);
   j->host_out.release();
   j->pin_small.release();
   j->pin_rd.release();

@@ -331,9 +331,16 @@ __device__ __forceinline__ uint32_t next_block(const Window<PT>& w, uint32_t a, 
   }
   uint32_t lo = a + 1, hi = wlen + 1;  // searching the first b in [lo, hi) with CurrentSizeEstimate(a, b) > thr; hi = none
   if (hint > a + 1 && hint <= wlen) {
-    uint32_t l2 = hint > a + 4 ? hint - 3 : a + 1, h2 = hint + 5 < wlen ? hint + 5 : wlen;
-    if (l2 == a + 1 || blk_payload(w, bs, l2 - 1, cp) <= thr) lo = l2;
-    if (blk_payload(w, bs, h2, cp) > thr) hi = h2;
+    // the estimate grows with b, and the block of the neighbouring start ended at `hint`: walk from there (a step or two) instead
+    // of bisecting the whole window
+    uint32_t b = hint;
+    if (blk_payload(w, bs, b, cp) > thr) {
+      while (b > a + 1 && blk_payload(w, bs, b - 1, cp) > thr) b--;
+    } else {
+      do b++;
+      while (b <= wlen && blk_payload(w, bs, b, cp) <= thr);
+    }
+    lo = hi = b;
   }
   while (lo < hi) {
     uint32_t mid = (lo + hi) >> 1;

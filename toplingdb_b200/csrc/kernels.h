@@ -101,8 +101,12 @@ struct BoundKey {              // a user key in column form (grandparent boundar
 // Sub-compaction key range (ClippingIterator, db/compaction/clipping_iterator.h:55-358): per run the entries with
 // start <= user key < end.  clip[r] / clip[nruns + r] = first / one-past-last entry of run r in range; totals[0] += entries in
 // range, totals[1] += their value bytes.
-void launch_clip_runs(KeyCols in, const uint64_t* run_start, uint32_t nruns, BoundKey start, uint32_t has_start, BoundKey end,
+void launch_clip_runs(KeyCols in, RunBounds runs, uint32_t nruns, BoundKey start, uint32_t has_start, BoundKey end,
                       uint32_t has_end, uint64_t* clip, unsigned long long* totals, cudaStream_t st);
+// Sorted runs from decoded files: run r = the files [run_first[r], run_first[r + 1]), decoded back to back; bounds = begin[nruns] |
+// end[nruns].  Checks that consecutive files of one run are in order (a level's files are disjoint and sorted): kErrKeyOrder.
+void launch_run_bounds(KeyCols in, const uint64_t* file_start, const uint32_t* run_first, uint32_t nruns, uint64_t* bounds, uint32_t* err,
+                       cudaStream_t st);
 void launch_merge_partition(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t n_total, uint64_t ntiles,
                             uint64_t* splits, uint32_t* err, cudaStream_t st);
 void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,

@@ -915,13 +915,13 @@ __global__ void merge_sizes_fix_kernel(KeyCols m, const unsigned long long* __re
 // the run's entries in range (CompactionJobStats::total_input_raw_value_bytes counts what the iterator consumed).
 constexpr int kClipSlices = 64;
 __global__ void __launch_bounds__(256)
-clip_runs_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint32_t nruns, BoundKey start, uint32_t has_start, BoundKey end,
+clip_runs_kernel(KeyCols in, RunBounds runs, uint32_t nruns, BoundKey start, uint32_t has_start, BoundKey end,
                  uint32_t has_end, uint64_t* __restrict__ clip, unsigned long long* __restrict__ totals) {
   __shared__ uint64_t sb[2];
   const uint32_t r = blockIdx.y;
   if (threadIdx.x < 2) {
     const bool is_end = threadIdx.x == 1;
-    const uint64_t a0 = run_start[r], b0 = run_start[r + 1];
+    const uint64_t a0 = runs.begin[r], b0 = runs.end[r];
     uint64_t pos = is_end ? b0 : a0;
     if (is_end ? has_end : has_start) {  // first entry of the run with user key >= bound
       const BoundKey k = is_end ? end : start;
@@ -951,9 +951,26 @@ clip_runs_kernel(KeyCols in, const uint64_t* __restrict__ run_start, uint32_t nr
   for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
   if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&totals[1], sum);
 }
-void launch_clip_runs(KeyCols in, const uint64_t* run_start, uint32_t nruns, BoundKey start, uint32_t has_start, BoundKey end,
+void launch_clip_runs(KeyCols in, RunBounds runs, uint32_t nruns, BoundKey start, uint32_t has_start, BoundKey end,
                       uint32_t has_end, uint64_t* clip, unsigned long long* totals, cudaStream_t st) {
-  if (nruns) clip_runs_kernel<<<dim3(kClipSlices, nruns), 256, 0, st>>>(in, run_start, nruns, start, has_start, end, has_end, clip, totals);
+  if (nruns) clip_runs_kernel<<<dim3(kClipSlices, nruns), 256, 0, st>>>(in, runs, nruns, start, has_start, end, has_end, clip, totals);
+}
+// one thread per run: its column range, and the order of the files inside it
+__global__ void run_bounds_kernel(KeyCols in, const uint64_t* __restrict__ file_start, const uint32_t* __restrict__ run_first, uint32_t nruns,
+                                  uint64_t* __restrict__ bounds, uint32_t* __restrict__ err) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nruns) return;
+  const uint32_t f0 = run_first[r], f1 = run_first[r + 1];
+  bounds[r] = file_start[f0];
+  bounds[nruns + r] = file_start[f1];
+  for (uint32_t f = f0 + 1; f < f1; f++) {
+    const uint64_t e = file_start[f];  // first entry of file f; the entry before it is the last one of an earlier file of the run
+    if (e > file_start[f0] && e < file_start[f1] && !ikey_less(load_key(in, e - 1), load_key(in, e))) atomicOr(err, (uint32_t)kErrKeyOrder);
+  }
+}
+void launch_run_bounds(KeyCols in, const uint64_t* file_start, const uint32_t* run_first, uint32_t nruns, uint64_t* bounds, uint32_t* err,
+                       cudaStream_t st) {
+  if (nruns) run_bounds_kernel<<<(nruns + 63) / 64, 64, 0, st>>>(in, file_start, run_first, nruns, bounds, err);
 }
 
 // ------------------------------------------------------------------------------------------------ launchers

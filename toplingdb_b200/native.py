@@ -65,7 +65,7 @@ EXPORTS = ["b200c_last_error", "b200c_abi_version", "b200c_device_count", "b200c
            "b200c_job_add_input", "b200c_job_run", "b200c_job_output_count", "b200c_job_output_meta",
            "b200c_job_output_data", "b200c_job_output_read", "b200c_job_get_stats", "b200c_job_destroy",
            "b200c_job_run_until", "b200c_job_debug_read", "b200c_block_checksums", "b200c_job_kernel_time_count",
-           "b200c_job_kernel_time", "b200c_job_encode_columns"]
+           "b200c_job_kernel_time", "b200c_job_encode_columns", "b200c_host_alloc", "b200c_host_free"]
 
 
 def load_library(build_if_missing=True):

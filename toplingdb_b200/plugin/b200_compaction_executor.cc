@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <set>
 #include <vector>
 
 #include "b200c.h"
@@ -21,6 +23,7 @@
 #include "file/filename.h"
 #include "rocksdb/comparator.h"
 #include "rocksdb/env.h"
+#include "rocksdb/file_system.h"
 #include "rocksdb/table.h"
 #include "table/block_based/filter_policy_internal.h"
 
@@ -100,19 +103,81 @@ Status FromB200(int rc) {
   }
 }
 
-Status ReadWholeFile(const std::string& fname, std::string* out) {
-  FILE* f = fopen(fname.c_str(), "rb");
-  if (!f) return Status::IOError("open", fname);
-  struct stat st;
-  if (fstat(fileno(f), &st) != 0) {
-    fclose(f);
-    return Status::IOError("stat", fname);
+// All file I/O goes through the DB's own FileSystem (ImmutableDBOptions::fs): an EncryptedEnv, a custom file system, a mock Env in
+// tests see every byte, exactly as they do for the reference's local compaction (file/writable_file_writer.cc, table_cache.cc).
+IOStatus ReadFileFS(FileSystem* fs, const std::string& fname, char* dst, uint64_t size) {
+  std::unique_ptr<FSRandomAccessFile> f;
+  FileOptions fo;
+  IOStatus s = fs->NewRandomAccessFile(fname, fo, &f, nullptr);
+  if (!s.ok()) return s;
+  uint64_t off = 0;
+  while (off < size) {
+    const size_t n = (size_t)std::min<uint64_t>(size - off, 64ull << 20);
+    Slice res;
+    s = f->Read(off, n, IOOptions(), &res, dst + off, nullptr);
+    if (!s.ok()) return s;
+    if (res.size() == 0) return IOStatus::Corruption("short read", fname);
+    if (res.data() != dst + off) memmove(dst + off, res.data(), res.size());
+    off += res.size();
   }
-  out->resize((size_t)st.st_size);
-  size_t n = st.st_size ? fread(&(*out)[0], 1, (size_t)st.st_size, f) : 0;
-  fclose(f);
-  return n == (size_t)st.st_size ? Status::OK() : Status::IOError("short read", fname);
+  return IOStatus::OK();
 }
+// An output table is durable before Execute returns: appended, synced (fsync when DBOptions::use_fsync), closed with the close
+// status checked -- what CompactionOutputs::Finish / WritableFileWriter::Sync do on the local path (compaction_outputs.cc:63,
+// compaction_job.cc:1905-1921).  RunRemote installs the file in a synced MANIFEST right after the rename.
+IOStatus WriteFileFS(FileSystem* fs, const std::string& fname, const char* data, uint64_t len, bool use_fsync) {
+  std::unique_ptr<FSWritableFile> f;
+  FileOptions fo;
+  IOStatus s = fs->NewWritableFile(fname, fo, &f, nullptr);
+  if (!s.ok()) return s;
+  uint64_t off = 0;
+  while (s.ok() && off < len) {
+    const size_t n = (size_t)std::min<uint64_t>(len - off, 64ull << 20);
+    s = f->Append(Slice(data + off, n), IOOptions(), nullptr);
+    off += n;
+  }
+  if (s.ok()) s = use_fsync ? f->Fsync(IOOptions(), nullptr) : f->Sync(IOOptions(), nullptr);
+  IOStatus c = f->Close(IOOptions(), nullptr);
+  return s.ok() ? c : s;
+}
+IOStatus SyncDirFS(FileSystem* fs, const std::string& dir) {
+  std::unique_ptr<FSDirectory> d;
+  IOStatus s = fs->NewDirectory(dir, IOOptions(), &d, nullptr);
+  if (!s.ok()) return s;
+  s = d->FsyncWithDirOptions(IOOptions(), nullptr, DirFsyncOptions());
+  IOStatus c = d->Close(IOOptions(), nullptr);
+  return s.ok() ? c : s;
+}
+std::string DirOf(const std::string& path) {
+  const size_t p = path.find_last_of('/');
+  return p == std::string::npos ? std::string(".") : (p == 0 ? std::string("/") : path.substr(0, p));
+}
+
+// pinned host buffer from the library (cudaHostAlloc behind the C ABI: the plugin itself stays free of CUDA headers); a plain
+// allocation when pinning fails (the copy is slower then, nothing else changes)
+struct HostImage {
+  char* p = nullptr;
+  uint64_t len = 0;
+  bool pinned = false;
+  HostImage() = default;
+  HostImage(const HostImage&) = delete;
+  HostImage& operator=(const HostImage&) = delete;
+  bool Alloc(int device, uint64_t n) {
+    len = n;
+    void* q = nullptr;
+    if (b200c_host_alloc(device, n ? n : 1, &q) == B200C_OK) {
+      p = static_cast<char*>(q);
+      pinned = true;
+    } else {
+      p = static_cast<char*>(malloc(n ? n : 1));
+    }
+    return p != nullptr;
+  }
+  ~HostImage() {
+    if (p && pinned) b200c_host_free(p);
+    else free(p);
+  }
+};
 
 class B200CompactionExecutor : public CompactionExecutor {
  public:
@@ -185,7 +250,11 @@ class B200CompactionExecutor : public CompactionExecutor {
     uint64_t fct = (uint64_t)now;
     bp.file_creation_times = &fct;
     bp.num_file_creation_times = 1;
-    bp.first_file_number = 1;  // numbers are local to output_dir; RunRemote renames every file (compaction_job.cc:1019-1033)
+    // Numbers are local to output_dir -- RunRemote gives every file a fresh number and renames it (compaction_job.cc:1019-1033) --
+    // but the number also lands in the table property rocksdb.original.file.number, which together with the session id derives
+    // the file's unique id and (in builds with stable cache keys) its block-cache key.  It is therefore unique per job within a DB
+    // session: job ids are, and no job writes 2^20 files.
+    bp.first_file_number = ((uint64_t)(uint32_t)p.job_id << 20) | 1;
     bp.output_mem = B200C_MEM_HOST;
     // grandparents: CompactionOutputs::ShouldStopBefore cuts output files at their boundaries (compaction_outputs.cc:294-351)
     std::vector<b200c_grandparent> gps;
@@ -221,29 +290,41 @@ class B200CompactionExecutor : public CompactionExecutor {
     Status s = FromB200(b200c_job_create(&bp, &job));
     if (!s.ok()) return Fail(r, s);
     // child order of VersionSet::MakeInputIterator (db/version_set.cc:7269-7352): L0 files as listed, then each level
-    std::vector<std::string> images;
+    FileSystem* fs = c_->immutable_options()->fs.get();
+    const bool use_fsync = c_->immutable_options()->use_fsync;
+    size_t nfiles_in = 0;
+    for (const auto& lvl : *p.inputs) nfiles_in += lvl.files.size();
+    // one pinned buffer per input file; they never move (the library keeps the pointers until the job is destroyed) and the
+    // library starts the host -> device copy of a file as soon as it is added, while the next file is still being read
+    std::vector<std::unique_ptr<HostImage>> images;
+    images.reserve(nfiles_in);
     uint64_t in_bytes = 0;
-    for (const auto& lvl : *p.inputs) images.reserve(images.size() + lvl.files.size());
     for (const auto& lvl : *p.inputs) {
       for (const FileMetaData* fm : lvl.files) {
         if (fm->num_range_deletions) s = Status::NotSupported("B200Compact: range tombstones in input");
         if (!s.ok()) break;
-        images.emplace_back();
-        s = ReadWholeFile(TableFileName(p.cf_paths, fm->fd.GetNumber(), fm->fd.GetPathId()), &images.back());
+        const uint64_t fsize = fm->fd.GetFileSize();
+        images.emplace_back(new HostImage());
+        if (!images.back()->Alloc(opt_.device, fsize)) s = Status::MemoryLimit("B200Compact: input buffer");
+        if (s.ok()) s = ReadFileFS(fs, TableFileName(p.cf_paths, fm->fd.GetNumber(), fm->fd.GetPathId()), images.back()->p, fsize);
         if (!s.ok()) break;
-        in_bytes += images.back().size();
-        s = FromB200(b200c_job_add_input(job, lvl.level, fm->fd.GetNumber(), images.back().data(), images.back().size(), B200C_MEM_HOST));
+        in_bytes += fsize;
+        s = FromB200(b200c_job_add_input(job, lvl.level, fm->fd.GetNumber(), images.back()->p, fsize, B200C_MEM_HOST));
         if (!s.ok()) break;
       }
       if (!s.ok()) break;
     }
-    if (s.ok() && p.shutting_down && p.shutting_down->load(std::memory_order_acquire)) s = Status::ShutdownInProgress();
+    auto shutting_down = [&]() { return p.shutting_down && p.shutting_down->load(std::memory_order_acquire); };
+    if (s.ok() && shutting_down()) s = Status::ShutdownInProgress();
     if (s.ok()) s = FromB200(b200c_job_run(job));
+    if (s.ok() && shutting_down()) s = Status::ShutdownInProgress();  // do not materialise files for a DB that is closing
+    std::vector<std::string> written;
     if (s.ok()) {
-      r->output_dir = opt_.scratch_dir.empty() ? p.dbname + "/b200c-tmp" : opt_.scratch_dir;
-      r->output_dir += "/job-" + std::to_string(p.job_id);
-      mkdir((opt_.scratch_dir.empty() ? p.dbname + "/b200c-tmp" : opt_.scratch_dir).c_str(), 0755);
-      mkdir(r->output_dir.c_str(), 0755);
+      // scratch directory: unique per DB session and job, so that DBs sharing a factory / scratch_dir cannot collide
+      const std::string root = opt_.scratch_dir.empty() ? p.dbname + "/b200c-tmp" : opt_.scratch_dir;
+      r->output_dir = root + "/job-" + (p.db_session_id.empty() ? std::string("s") : p.db_session_id) + "-" + std::to_string(p.job_id);
+      fs->CreateDirIfMissing(root, IOOptions(), nullptr).PermitUncheckedError();
+      s = fs->CreateDirIfMissing(r->output_dir, IOOptions(), nullptr);
       r->output_files.resize(1);  // one sub-compaction: the device splits the job internally (merge-path tiles)
       const int n = b200c_job_output_count(job);
       for (int i = 0; i < n && s.ok(); i++) {
@@ -254,9 +335,9 @@ class B200CompactionExecutor : public CompactionExecutor {
         if (s.ok()) s = FromB200(b200c_job_output_data(job, i, &data, &len));
         if (!s.ok()) break;
         const std::string fname = MakeTableFileName(r->output_dir, m.file_number);
-        FILE* f = fopen(fname.c_str(), "wb");
-        if (!f || fwrite(data, 1, len, f) != len) s = Status::IOError("write", fname);
-        if (f) fclose(f);
+        written.push_back(fname);
+        s = WriteFileFS(fs, fname, static_cast<const char*>(data), len, use_fsync);
+        if (!s.ok()) break;
         CompactionResults::FileMinMeta fm;
         fm.file_number = m.file_number;
         fm.file_size = m.file_size;
@@ -266,6 +347,12 @@ class B200CompactionExecutor : public CompactionExecutor {
         fm.largest_ikey.DecodeFrom(Slice((const char*)m.largest_ikey, m.largest_ikey_len));
         fm.marked_for_compaction = false;
         r->output_files[0].push_back(std::move(fm));
+      }
+      if (s.ok()) s = SyncDirFS(fs, r->output_dir);  // the new names are durable too
+      if (!s.ok()) {  // nothing of a failed job stays behind
+        for (const auto& f : written) fs->DeleteFile(f, IOOptions(), nullptr).PermitUncheckedError();
+        fs->DeleteDir(r->output_dir, IOOptions(), nullptr).PermitUncheckedError();
+        r->output_files.clear();
       }
     }
     if (s.ok()) {
@@ -317,21 +404,34 @@ class B200CompactionExecutor : public CompactionExecutor {
     return s.ok() ? s : Fail(r, s);
   }
 
-  Status RenameFile(const std::string& src, const std::string& dst, off_t) override {
-    if (rename(src.c_str(), dst.c_str()) == 0) return Status::OK();
-    return CopyOneFile(src, dst, 0).ok() && unlink(src.c_str()) == 0 ? Status::OK() : Status::IOError("rename", src);
+  Status RenameFile(const std::string& src, const std::string& dst, off_t fsize) override {
+    FileSystem* fs = c_->immutable_options()->fs.get();
+    IOStatus s = fs->RenameFile(src, dst, IOOptions(), nullptr);
+    if (!s.ok()) {  // scratch directory on another file system: copy (synced), then drop the source
+      Status c = CopyOneFile(src, dst, fsize);
+      if (!c.ok()) return c;
+      fs->DeleteFile(src, IOOptions(), nullptr).PermitUncheckedError();
+    }
+    renamed_dirs_.insert(DirOf(dst));
+    return Status::OK();
   }
   Status CopyOneFile(const std::string& src, const std::string& dst, off_t) override {
-    std::string data;
-    Status s = ReadWholeFile(src, &data);
+    FileSystem* fs = c_->immutable_options()->fs.get();
+    uint64_t size = 0;
+    IOStatus s = fs->GetFileSize(src, IOOptions(), &size, nullptr);
     if (!s.ok()) return s;
-    FILE* f = fopen(dst.c_str(), "wb");
-    if (!f || fwrite(data.data(), 1, data.size(), f) != data.size()) s = Status::IOError("write", dst);
-    if (f) fclose(f);
+    std::unique_ptr<char[]> buf(new char[size ? size : 1]);
+    s = ReadFileFS(fs, src, buf.get(), size);
+    if (s.ok()) s = WriteFileFS(fs, dst, buf.get(), size, c_->immutable_options()->use_fsync);
     return s;
   }
+  // RunRemote calls this after the last rename and before Install(): the destination directories are synced here (the local path
+  // syncs the output directory at the end of CompactionJob::Run, compaction_job.cc:766), then the scratch directory goes away
   void CleanFiles(const CompactionParams&, const CompactionResults& r) override {
-    if (!r.output_dir.empty()) rmdir(r.output_dir.c_str());  // outputs were renamed away; the directory is empty
+    FileSystem* fs = c_->immutable_options()->fs.get();
+    for (const auto& d : renamed_dirs_) SyncDirFS(fs, d).PermitUncheckedError();
+    renamed_dirs_.clear();
+    if (!r.output_dir.empty()) fs->DeleteDir(r.output_dir, IOOptions(), nullptr).PermitUncheckedError();  // outputs were renamed away
   }
 
  private:
@@ -341,6 +441,7 @@ class B200CompactionExecutor : public CompactionExecutor {
   }
   B200CompactOptions opt_;
   const Compaction* c_;
+  std::set<std::string> renamed_dirs_;  // directories that received an output file of this job
 };
 
 }  // namespace
@@ -379,14 +480,15 @@ static const char* WhyLocal(const Compaction* c) {
       t->index_block_restart_interval != 1 || t->block_align || t->format_version < 3 || t->format_version > 5 ||
       (t->checksum != kXXH3 && t->checksum != kCRC32c && t->checksum != kNoChecksum))
     return "BlockBasedTableOptions outside the device's format subset";
-  size_t runs = 0;
+  size_t runs = 0, files = 0;  // sorted runs as MakeInputIterator forms them: every L0 file, every deeper level (version_set.cc:7311-7352)
   for (const auto& lvl : *c->inputs()) {
-    runs += lvl.files.size();
+    files += lvl.files.size();
+    runs += lvl.level == 0 ? lvl.files.size() : (lvl.files.empty() ? 0 : 1);
     for (const FileMetaData* fm : lvl.files)
       if (fm->num_range_deletions) return "range tombstones in an input file";
   }
-  if (runs == 0) return "no input files";
-  if (runs > 64) return "more than 64 input files";
+  if (files == 0) return "no input files";
+  if (runs > 64) return "more than 64 sorted runs (L0 files + levels)";
   return nullptr;
 }
 
