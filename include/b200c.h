@@ -220,6 +220,13 @@ B200C_API int b200c_job_kernel_time(const b200c_job* j, int i, const char** name
  *                           meta  4 B  user_key_len << 27 | value_len
  * Results are read with b200c_job_output_*.  Used by the table-factory plugin and to pre-stage synthetic inputs. */
 B200C_API int b200c_job_encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta);
+/* The same for a caller that holds its entries in HOST memory, as a TableBuilder does between Add() calls (table/table_builder.h:168-
+ * 239; BlockBasedTableBuilder::Add / Finish, block_based_table_builder.cc:961-1133, 1921-1977): n entries in internal-key order; entry i
+ * is its internal key (klens[i] bytes, user key + 8-byte trailer) immediately followed by its value and starts at arena + offs[i]; the
+ * value ends where entry i + 1 starts, offs[n] = bytes used.  The plugin's B200TableBuilder (plugin/b200_table_factory.cc) calls this
+ * from Finish().  B200C_ERR_NOT_SUPPORTED for what the device encoder does not take (user keys > 16 bytes, types other than
+ * kTypeValue / kTypeDeletion): the builder then replays its records into the reference's own BlockBasedTableBuilder. */
+B200C_API int b200c_job_encode_kv(b200c_job* j, uint64_t n, const void* arena, const uint64_t* offs, const uint32_t* klens);
 
 /* Block checksum of table/format.cc:468-509 computed on the device for n independent buffers laid out
  * back to back (offsets[n+1]); results in out[n].  type = enum b200c_checksum. */

@@ -41,6 +41,7 @@
 #ifdef WITH_B200_PLUGIN
 #include "rocksdb/statistics.h"
 #include "toplingdb_b200/plugin/b200_compaction_executor.h"
+#include "toplingdb_b200/plugin/b200_table_factory.h"
 #endif
 
 using namespace ROCKSDB_NAMESPACE;
@@ -67,6 +68,7 @@ struct Opts {
   std::string filter = "none";  // remove_empty_value: the reference's RemoveEmptyValueCompactionFilter through a factory
   std::string barrier_dir;  // with barrier_n: wait until barrier_n processes have finished writing their inputs, so that
   int barrier_n = 0;        // concurrent timing runs compact at the same time
+  std::string table_factory;  // "b200" / "b200+nofallback": flushes and (local) compactions write their tables through B200TableFactory
   std::string executor;  // "b200": route the job through the B200 CompactionExecutor plugin (ref_compact_b200 build only)
 };
 
@@ -210,6 +212,7 @@ int main(int argc, char** argv) {
     else if (k == "ribbon") o.ribbon = atoi(v.c_str());
     else if (k == "partition_filters") o.partition_filters = atoi(v.c_str());
     else if (k == "executor") o.executor = v;
+    else if (k == "table_factory") o.table_factory = v;
     else if (k == "copy") o.copy = atoi(v.c_str());
     else if (k == "filter") o.filter = v;
     else if (k == "mode") o.mode = v;
@@ -272,6 +275,20 @@ int main(int argc, char** argv) {
   auto listener = std::make_shared<StatsListener>();
   opt.listeners.push_back(listener);
   bool use_b200 = false;
+#ifdef WITH_B200_PLUGIN
+  std::shared_ptr<TableFactory> b200_tf;
+  if (o.table_factory == "b200" || o.table_factory == "b200+nofallback") {
+    B200TableFactoryOptions to;
+    to.allow_fallback = o.table_factory == "b200";
+    b200_tf = NewB200TableFactory(t, to);
+    opt.table_factory = b200_tf;
+  }
+#else
+  if (!o.table_factory.empty()) {
+    fprintf(stderr, "ref_compact: table_factory=%s needs the ref_compact_b200 build\n", o.table_factory.c_str());
+    return 1;
+  }
+#endif
 #ifdef WITH_B200_PLUGIN
   if (o.executor == "b200" || o.executor == "b200+fallback") {
     opt.statistics = CreateDBStatistics();
@@ -515,6 +532,13 @@ int main(int argc, char** argv) {
     if (opt.statistics) remote_read = opt.statistics->getTickerCount(REMOTE_COMPACT_READ_BYTES);
 #endif
     fprintf(m, "  \"executor\": \"%s\",\n  \"remote_compact_read_bytes\": %" PRIu64 ",\n", use_b200 ? "B200Compact" : "local", remote_read);
+#ifdef WITH_B200_PLUGIN
+    if (b200_tf) {
+      auto* tf = static_cast<B200TableFactory*>(b200_tf.get());
+      fprintf(m, "  \"table_factory\": \"%s\",\n  \"b200_device_tables\": %" PRIu64 ",\n  \"b200_fallback_tables\": %" PRIu64 ",\n", tf->Name(),
+              tf->device_tables(), tf->fallback_tables());
+    }
+#endif
   }
   {
     // Read the whole DB back through the reference's own table reader (block checksums verified): a digest of what a

@@ -48,6 +48,11 @@ int b200c_host_alloc(int device, uint64_t bytes, void** out) {
   return *out ? B200C_OK : B200C_ERR_OUT_OF_MEMORY;
 }
 void b200c_host_free(void* p) { free(p); }
+int b200c_job_encode_kv(b200c_job* j, uint64_t n, const void* arena, const uint64_t* offs, const uint32_t* klens) {
+  (void)j; (void)n; (void)arena; (void)offs; (void)klens;
+  g_err = "test double: no encoder";
+  return B200C_ERR_NOT_SUPPORTED;
+}
 uint32_t b200c_abi_version(void) { return B200C_ABI_VERSION; }
 int b200c_device_count(void) { return 1; }
 void b200c_params_init(b200c_params* p) { /* the defaults of the real library (api.cu) */

@@ -132,6 +132,7 @@ struct b200c_job {
   DevBuf esz, eshared, tstat, nxt, disk, rows, tstate, grows, gstate, gflag, gsync, idx_contrib, idx_contrib_off, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
   uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
   uint32_t nfiles_out = 0, nruns = 0;
+  DevBuf kv_arena, kv_offs, kv_klens;  // b200c_job_encode_kv: the caller's records on the device
   DevBuf run_bounds, run_first_d;  // [begin[K] | end[K]] of the sorted runs in the decoded columns; first file of each run
   std::vector<uint64_t> run_start_h;
   HostBuf host_out;
@@ -653,7 +654,7 @@ int finish_run(b200c_job* j, uint64_t launches, uint64_t nblocks, uint32_t nfile
   return B200C_OK;
 }
 
-int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta);
+int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta, bool prepared = false);
 
 int run_merge_encode(b200c_job* j, int until, KeyCols decc, RunBounds runs, uint64_t n_decoded, uint64_t N, bool clipped,
                      uint64_t range_value_bytes, uint64_t* small, uint32_t* err, uint64_t launches);
@@ -965,8 +966,8 @@ int job_prepare(b200c_job* j) {
 }
 
 // TableBuilder side only: one sorted run given as device columns -> BlockBasedTable image(s)
-int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta) {
-  int rc = job_prepare(j);
+int encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta, bool prepared) {
+  int rc = prepared ? B200C_OK : job_prepare(j);
   if (rc) return rc;
   cudaStream_t st = j->st;
   uint64_t launches = 0;
@@ -1210,7 +1211,7 @@ int b200c_job_get_stats(const b200c_job* j, b200c_stats* s) {
 void b200c_job_destroy(b200c_job* j) {
   if (!j) return;
   cudaSetDevice(j->p.device);
-  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->run_bounds, &j->run_first_d, &j->small,
+  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->run_bounds, &j->run_first_d, &j->kv_arena, &j->kv_offs, &j->kv_klens, &j->small,
                    &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
                    &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->tstat, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->gsync, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};
@@ -1258,6 +1259,40 @@ int b200c_job_kernel_time(const b200c_job* j, int i, const char** name, double* 
 int b200c_job_encode_columns(b200c_job* j, uint64_t n, const void* pfx, const void* tr, const void* vref, const void* meta) {
   if (!j || (n && (!pfx || !tr || !vref || !meta))) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
   return encode_columns(j, n, pfx, tr, vref, meta);
+}
+
+int b200c_job_encode_kv(b200c_job* j, uint64_t n, const void* arena, const uint64_t* offs, const uint32_t* klens) {
+  if (!j || (n && (!arena || !offs || !klens))) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  int rc = job_prepare(j);
+  if (rc) return rc;
+  cudaStream_t st = j->st;
+  const uint64_t bytes = n ? offs[n] : 0;
+  // records, offsets and key lengths move to the device; the columns are built there (one thread per entry) in the buffers the
+  // merge stage writes on the compaction path (paranoid_file_checks re-reads into the decoder's)
+  CU(j->kv_arena.reserve(bytes + 64));
+  CU(j->kv_offs.reserve(8 * (n + 1)));
+  CU(j->kv_klens.reserve(4 * (n + 1)));
+  CU(j->mrg[0].reserve(16 * (n + 1)));
+  CU(j->mrg[1].reserve(8 * (n + 1)));
+  CU(j->mrg[2].reserve(8 * (n + 1)));
+  CU(j->mrg[3].reserve(4 * (n + 1)));
+  CU(j->small.reserve(kSmallSlots * 8));
+  CU(cudaMemsetAsync(j->small.p, 0, kSmallSlots * 8, st));
+  if (n) {
+    CU(cudaMemcpyAsync(j->kv_arena.p, arena, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(j->kv_offs.p, offs, 8 * (n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(j->kv_klens.p, klens, 4 * n, cudaMemcpyHostToDevice, st));
+  }
+  KeyColsMut cols{j->mrg[0].as<ulonglong2>(), j->mrg[1].as<uint64_t>(), j->mrg[2].as<uint64_t>(), j->mrg[3].as<uint32_t>()};
+  uint32_t* err = reinterpret_cast<uint32_t*>(j->small.as<uint64_t>() + kSlotErr);
+  launch_kv_to_columns(j->kv_arena.as<uint8_t>(), j->kv_offs.as<uint64_t>(), j->kv_klens.as<uint32_t>(), n, cols, err, st);
+  uint32_t herr = 0;
+  CU(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  rc = map_dev_err(herr);
+  if (rc) return rc;
+  return encode_columns(j, n, cols.pfx, cols.tr, cols.vref, cols.meta, /*prepared=*/true);
 }
 
 int b200c_job_debug_read(b200c_job* j, int what, int run, void* dst, uint64_t cap, uint64_t* len) {

@@ -752,6 +752,42 @@ __global__ void gather_values_kernel(KeyCols in, const uint64_t* __restrict__ ds
     for (uint32_t t = 0; t < n; t++) d[t] = s[t];
   }
 }
+// TableBuilder side with host records: entry i = internal key (klen[i] bytes) followed by its value, at arena + offs[i]; the next
+// entry starts where the value ends.  One thread per entry: the key columns + a value reference into the (device) arena.
+__global__ void kv_to_columns_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ offs, const uint32_t* __restrict__ klens,
+                                     uint64_t n, KeyColsMut out, uint32_t* __restrict__ err) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t o = offs[i], e = offs[i + 1];
+    const uint32_t kl = klens[i];
+    uint64_t hi = 0, lo = 0, tr = 0;
+    uint32_t ulen = 0, vlen = 0;
+    if (kl < 8 || o + kl > e) {
+      atomicOr(err, (uint32_t)kErrCorruptBlock);
+    } else if (kl > (uint32_t)kMaxUserKey + 8) {
+      atomicOr(err, (uint32_t)kErrKeyTooLong);
+    } else if (e - o - kl > kMetaVlenMask) {
+      atomicOr(err, (uint32_t)kErrValueTooLong);
+    } else {
+      ulen = kl - 8;
+      vlen = (uint32_t)(e - o - kl);
+      const uint8_t* k = arena + o;
+      for (uint32_t t = 0; t < 8; t++) hi = (hi << 8) | (t < ulen ? k[t] : 0);
+      for (uint32_t t = 8; t < 16; t++) lo = (lo << 8) | (t < ulen ? k[t] : 0);
+      tr = ld_u64(k + ulen);
+      if ((tr & 0xff) > 1) atomicOr(err, (uint32_t)kErrBadType);
+    }
+    out.pfx[i] = make_ulonglong2(hi, lo);
+    out.tr[i] = tr;
+    out.vref[i] = (uint64_t)(uintptr_t)(arena + o + kl);
+    out.meta[i] = make_meta(ulen, vlen);
+  }
+}
+void launch_kv_to_columns(const uint8_t* arena, const uint64_t* offs, const uint32_t* klens, uint64_t n, KeyColsMut out, uint32_t* err,
+                          cudaStream_t st) {
+  if (n == 0) return;
+  const uint64_t g = (n + 255) / 256;
+  kv_to_columns_kernel<<<(unsigned)(g > 148 * 16 ? 148 * 16 : g), 256, 0, st>>>(arena, offs, klens, n, out, err);
+}
 __global__ void meta_vlen_kernel(const uint32_t* __restrict__ meta, uint64_t n, uint32_t* __restrict__ vlen) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
     vlen[i] = meta_vlen(meta[i]);

@@ -47,6 +47,9 @@ void launch_flip_byte(uint8_t* p, cudaStream_t st);  // test hook of paranoid_fi
 void launch_compare_columns(KeyCols written, KeyCols reread, uint64_t n, uint32_t* err, cudaStream_t st);
 void launch_gather_values(KeyCols in, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st);
 void launch_meta_vlen(const uint32_t* meta, uint64_t n, uint32_t* vlen, cudaStream_t st);
+// host records (internal key + value, back to back) -> key columns with value references into the device arena
+void launch_kv_to_columns(const uint8_t* arena, const uint64_t* offs, const uint32_t* klens, uint64_t n, KeyColsMut out, uint32_t* err,
+                          cudaStream_t st);
 
 struct TailCopy {  // one finished file tail: staged bytes [src_off, src_off + len) -> output buffer at dst_off
   uint64_t dst_off;

@@ -136,6 +136,18 @@ constexpr uint32_t kPartStride = 64;
 struct GroupLanes {
   uint32_t gshift, g, r, sub, gbase, nruns;
 };
+// Does entry i precede the pivot x (before_equal: or equal it)?  The 16-byte key prefix decides almost every probe; the length and
+// the trailer columns are only touched on a tie (one DRAM sector per probe instead of three).
+__device__ __forceinline__ bool entry_precedes(const KeyCols& c, uint64_t i, const Key& x, bool before_equal) {
+  const ulonglong2 p = c.pfx[i];
+  if (p.x != x.hi) return p.x < x.hi;
+  if (p.y != x.lo) return p.y < x.lo;
+  const uint32_t ul = meta_ulen(c.meta[i]);
+  if (ul != x.ulen) return ul < x.ulen;
+  const uint64_t tr = c.tr[i];
+  if (tr != x.tr) return tr > x.tr;  // larger (seq, type) first
+  return before_equal;
+}
 // multi-sequence selection of rank d over the runs' brackets [lo, hi) (units of `stride` entries; entry = base + stride * pos)
 __device__ __forceinline__ void msel_grouped(const KeyCols& in, const GroupLanes& L, uint64_t base, uint64_t stride, uint64_t d, uint64_t& lo,
                                              uint64_t& hi) {
@@ -172,10 +184,7 @@ __device__ __forceinline__ void msel_grouped(const KeyCols& in, const GroupLanes
         }
       }
       bool prec = false;
-      if (valid) {
-        const Key e = load_key(in, base + pos * stride);
-        prec = before_equal ? !ikey_less(x, e) : ikey_less(e, x);
-      }
+      if (valid) prec = entry_precedes(in, base + pos * stride, x, before_equal);
       const unsigned bal = __ballot_sync(0xffffffffu, prec);
       const uint32_t cp = __popc((bal >> gbase) & ((1u << g) - 1u));  // probes are increasing: the preceding ones form a prefix
       const uint32_t nvalid = w == 0 ? 0 : (w <= g ? (uint32_t)w : g);

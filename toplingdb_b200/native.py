@@ -65,7 +65,7 @@ EXPORTS = ["b200c_last_error", "b200c_abi_version", "b200c_device_count", "b200c
            "b200c_job_add_input", "b200c_job_run", "b200c_job_output_count", "b200c_job_output_meta",
            "b200c_job_output_data", "b200c_job_output_read", "b200c_job_get_stats", "b200c_job_destroy",
            "b200c_job_run_until", "b200c_job_debug_read", "b200c_block_checksums", "b200c_job_kernel_time_count",
-           "b200c_job_kernel_time", "b200c_job_encode_columns", "b200c_host_alloc", "b200c_host_free"]
+           "b200c_job_kernel_time", "b200c_job_encode_columns", "b200c_host_alloc", "b200c_host_free", "b200c_job_encode_kv"]
 
 
 def load_library(build_if_missing=True):
@@ -98,6 +98,7 @@ def load_library(build_if_missing=True):
     L.b200c_job_kernel_time_count.argtypes = [C.c_void_p]
     L.b200c_job_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double)]
     L.b200c_job_encode_columns.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200c_job_encode_kv.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200c_params_init.argtypes = [C.POINTER(Params)]
     L.b200c_params_init.restype = None
     _lib = L
@@ -225,6 +226,24 @@ class CompactionJob:
         self._wait_for_torch()
         _check(lib().b200c_job_encode_columns(self._h, n, C.c_void_p(pfx.data_ptr()), C.c_void_p(tr.data_ptr()),
                                                C.c_void_p(vref.data_ptr()), C.c_void_p(meta.data_ptr())))
+        return self
+
+    def encode_kv(self, entries):
+        """TableBuilder side with host records: entries = [(internal key bytes, value bytes)] in order -> BlockBasedTable image(s)"""
+        import array
+        arena = bytearray()
+        offs, klens = array.array("Q"), array.array("I")
+        for k, v in entries:
+            offs.append(len(arena))
+            klens.append(len(k))
+            arena += k + v
+        offs.append(len(arena))
+        if not klens:
+            klens.append(0)
+        ab = (C.c_char * max(1, len(arena))).from_buffer(arena) if arena else (C.c_char * 1)()
+        ob = (C.c_uint64 * len(offs)).from_buffer(offs)
+        kb = (C.c_uint32 * len(klens)).from_buffer(klens)
+        _check(lib().b200c_job_encode_kv(self._h, len(entries), ab, ob, kb))
         return self
 
     def kernel_times(self):

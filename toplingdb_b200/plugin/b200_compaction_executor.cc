@@ -87,7 +87,9 @@ bool HasHostOnlyFileCutRule(const Compaction* c) {
 
 const BlockBasedTableOptions* BlockBasedOptionsOf(const Compaction* c) {
   auto* tf = c->immutable_options()->table_factory.get();
-  if (tf == nullptr || strcmp(tf->Name(), TableFactory::kBlockBasedTableName()) != 0) return nullptr;
+  if (tf == nullptr) return nullptr;
+  // the stock factory, or the B200 table factory (plugin/b200_table_factory.h), which answers with its stock factory's options
+  if (strcmp(tf->Name(), TableFactory::kBlockBasedTableName()) != 0 && strcmp(tf->Name(), "B200BlockBasedTable") != 0) return nullptr;
   return tf->GetOptions<BlockBasedTableOptions>();
 }
 
