@@ -44,8 +44,8 @@ enum b200c_status {
   B200C_ERR_NO_DEVICE = 2,       /* no CUDA device / driver: the path has no CPU implementation */
   B200C_ERR_CUDA = 3,            /* a CUDA runtime call failed (message has the call and error string) */
   B200C_ERR_CORRUPTION = 4,      /* bad magic / handle / block checksum / key order in an input file */
-  B200C_ERR_NOT_SUPPORTED = 5,   /* input needs a rule outside the device rule set (merge operands, single
-                                    deletes, range tombstones, compressed blocks, user keys > 16 bytes, ...):
+  B200C_ERR_NOT_SUPPORTED = 5,   /* input needs a rule outside the device rule set (merge operands, range
+                                    tombstones, compressed blocks, user keys > 16 bytes, ...):
                                     the executor must report ShouldRunLocal()==true / fall back (compaction_job.cc:649-652) */
   B200C_ERR_OUT_OF_MEMORY = 6,
   B200C_ERR_STATE = 7            /* call order violated (e.g. output queried before run) */
@@ -134,6 +134,10 @@ typedef struct b200c_params {
    * "fullfilter.rocksdb.BuiltinBloomFilter" and the filter properties.  Needs format_version >= 5 (older versions build the legacy
    * Bloom filter), whole_key_filtering, no prefix extractor, optimize_filters_for_memory = false (the defaults). */
   uint32_t bloom_millibits_per_key;
+  /* CompactionParams::earliest_write_conflict_snapshot (compaction_executor.h:70): 0 or kMaxSequenceNumber = none.  It only changes
+   * what happens to a SingleDelete (compaction_iterator.cc:801-838); with one set (transaction DBs) an input that holds a
+   * SingleDelete is answered with B200C_ERR_NOT_SUPPORTED. */
+  uint64_t earliest_write_conflict_snapshot;
 } b200c_params;
 
 /* FileMinMeta (compaction_executor.h:120-131) + the TableProperties RunRemote re-reads (compaction_job.cc:1043-1061) */

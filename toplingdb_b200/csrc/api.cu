@@ -173,6 +173,7 @@ namespace {
 enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotDecTicket = 6, kSlotGpCuts = 7, kSlotCounters = 8 /* 8 */, kSlotClip = 16 /* 2: entries, value bytes in range */, kSmallSlots = 32 };
 
 int map_dev_err(uint32_t e) {
+  e &= ~(uint32_t)kFlagHasSingleDelete;  // a note of the decoder, not an error
   if (e == 0) return B200C_OK;
   std::string m = "device reported:";
   int code = B200C_ERR_CORRUPTION;
@@ -181,12 +182,16 @@ int map_dev_err(uint32_t e) {
   if (e & kErrKeyOrder) m += " key-order/partition";
   if (e & kErrCountMismatch) m += " entry-count-mismatch";
   if (e & kErrParanoid) m += " Paranoid checksums do not match (an output file does not read back as written)";
-  const uint32_t unsup = kErrKeyTooLong | kErrValueTooLong | kErrBadType | kErrCompressed | kErrBlockTooLong | kErrIrregularRestarts;
+  if (e & kErrSingleDelContract) m += " SingleDelete and Delete of the same key in one snapshot stripe (enforce_single_del_contracts)";
+  const uint32_t unsup = kErrKeyTooLong | kErrValueTooLong | kErrBadType | kErrCompressed | kErrBlockTooLong | kErrIrregularRestarts |
+                         kErrGroupTooLong | kErrSdWriteConflict;
   if (e & unsup) {
     if (!(e & ~(unsup))) code = B200C_ERR_NOT_SUPPORTED;
     if (e & kErrKeyTooLong) m += " user-key-longer-than-16-bytes";
     if (e & kErrValueTooLong) m += " value>=128MiB";
-    if (e & kErrBadType) m += " value-type-outside-{Value,Deletion}";
+    if (e & kErrBadType) m += " value-type-outside-{Value,Deletion,SingleDeletion}";
+    if (e & kErrGroupTooLong) m += " SingleDelete-on-a-key-with-too-many-versions-or-with-more-than-16-runs";
+    if (e & kErrSdWriteConflict) m += " SingleDelete-with-an-earliest_write_conflict_snapshot";
     if (e & kErrCompressed) m += " compressed-block";
     if (e & kErrBlockTooLong) m += " output-block-with-too-many-entries";
     if (e & kErrIrregularRestarts) m += " restart-intervals-of-unequal-length";
@@ -603,7 +608,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       uint64_t hv[kSmallSlots];
       int rc = read_small(j, small, hv, nullptr, nullptr);
       if (rc) return rc;
-      if ((uint32_t)hv[kSlotErr]) {  // whatever the reader tripped over, the file is not what was written
+      if ((uint32_t)hv[kSlotErr] & ~(uint32_t)kFlagHasSingleDelete) {  // whatever the reader tripped over, the file is not what was written
         map_dev_err((uint32_t)hv[kSlotErr]);
         const std::string detail = g_err;
         return fail(B200C_ERR_CORRUPTION, "Paranoid checksums do not match: " + detail);
@@ -849,7 +854,7 @@ int run_merge_encode(b200c_job* j, int until, KeyCols decc, RunBounds runs, uint
   cudaStream_t st = j->st;
   const size_t k = j->nruns;  // sorted runs (not files)
   // ---------------- merge
-  const uint64_t mtiles = (N + kMergeTile - 1) / kMergeTile;
+  const uint64_t mtiles = (N + kMergeNominal - 1) / kMergeNominal;  // tiles are cut every kMergeNominal entries (kernels.h)
   CU(j->splits.reserve(8 * (mtiles + 1) * k));
   CU(j->tile_state.reserve(8 * (mtiles + 1)));
   CU(cudaMemsetAsync(j->tile_state.p, 0, 8 * (mtiles + 1), st));
@@ -873,6 +878,7 @@ int run_merge_encode(b200c_job* j, int until, KeyCols decc, RunBounds runs, uint
   mp.filter = P.compaction_filter;
   mp.ttl = P.ttl;
   mp.now = P.ttl_now;
+  mp.write_conflict_snapshot = P.earliest_write_conflict_snapshot != 0 && P.earliest_write_conflict_snapshot < kMaxSeq;
   MergeCounters* counters = reinterpret_cast<MergeCounters*>(small + kSlotCounters);
   EncodeWork W;
   memset(&W, 0, sizeof W);

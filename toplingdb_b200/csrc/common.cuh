@@ -25,13 +25,21 @@ enum DevErr : uint32_t {
   kErrCountMismatch = 1u << 9,   // entry count differs from rocksdb.num.entries
   kErrIrregularRestarts = 1u << 10,  // restart intervals of one block hold different numbers of entries
   kErrParanoid = 1u << 11,       // paranoid_file_checks: an output file does not read back as what was written
+  kErrSingleDelContract = 1u << 12,  // a SingleDelete met a Delete of the same key in one snapshot stripe (enforce_single_del_contracts)
+  kErrGroupTooLong = 1u << 13,   // a user key with a SingleDelete has more versions than the device walks serially
+  kErrSdWriteConflict = 1u << 14,  // SingleDelete with an earliest_write_conflict_snapshot (transaction DB): not on the device
+  // not an error: some input entry is a kTypeSingleDeletion (the merge then keeps every user key's versions inside one tile)
+  kFlagHasSingleDelete = 1u << 31,
 };
 
 constexpr int kMaxUserKey = 16;
 constexpr uint32_t kMetaVlenBits = 27;
 constexpr uint32_t kMetaVlenMask = (1u << kMetaVlenBits) - 1;
 constexpr uint64_t kMaxSeq = (1ull << 56) - 1;
-constexpr uint8_t kTypeDeletion = 0, kTypeValue = 1;
+constexpr uint8_t kTypeDeletion = 0, kTypeValue = 1, kTypeSingleDeletion = 7;
+// value types the device rule set covers (everything else: kErrBadType -> NOT_SUPPORTED)
+__host__ __device__ __forceinline__ bool device_value_type(uint32_t t) { return t <= 1 || t == kTypeSingleDeletion; }
+__host__ __device__ __forceinline__ bool is_deletion_type(uint32_t t) { return t == kTypeDeletion || t == kTypeSingleDeletion; }
 
 __host__ __device__ __forceinline__ uint32_t make_meta(uint32_t ulen, uint32_t vlen) { return (ulen << kMetaVlenBits) | vlen; }
 __host__ __device__ __forceinline__ uint32_t meta_ulen(uint32_t m) { return m >> kMetaVlenBits; }

@@ -328,7 +328,8 @@ __device__ __noinline__ uint32_t decode_interval_seq(const uint8_t* p, const uin
     klen = shared + non_shared;
     uint64_t hi, lo, tr;
     key_columns(K0, K1, K2, klen, &hi, &lo, &tr);
-    if ((tr & 0xff) > 1) atomicOr(err, kErrBadType);
+    if (!device_value_type((uint32_t)(tr & 0xff))) atomicOr(err, kErrBadType);
+    else if ((tr & 0xff) == kTypeSingleDeletion) atomicOr(err, (uint32_t)kFlagHasSingleDelete);
     const uint8_t* val = p + hdr + non_shared;
     if ((uint64_t)(end - val) < vlen) {
       atomicOr(err, kErrCorruptBlock);
@@ -602,7 +603,8 @@ __device__ __forceinline__ bool decode_block_fast(DecWarpSmem& ws, uint32_t sp, 
     if (valid && !ebad) {  // the interval's first entry has shared == 0, so D is the whole key
       uint64_t hi, lo, tr;
       key_columns(D0, D1, D2, klen, &hi, &lo, &tr);
-      if ((tr & 0xff) > 1) atomicOr(err, kErrBadType);
+      if (!device_value_type((uint32_t)(tr & 0xff))) atomicOr(err, kErrBadType);
+      else if ((tr & 0xff) == kTypeSingleDeletion) atomicOr(err, (uint32_t)kFlagHasSingleDelete);
       const uint64_t e = base + ex0 + i;
       out.pfx[e] = make_ulonglong2(hi, lo);
       out.tr[e] = tr;
@@ -774,7 +776,7 @@ __global__ void kv_to_columns_kernel(const uint8_t* __restrict__ arena, const ui
       for (uint32_t t = 0; t < 8; t++) hi = (hi << 8) | (t < ulen ? k[t] : 0);
       for (uint32_t t = 8; t < 16; t++) lo = (lo << 8) | (t < ulen ? k[t] : 0);
       tr = ld_u64(k + ulen);
-      if ((tr & 0xff) > 1) atomicOr(err, (uint32_t)kErrBadType);
+      if (!device_value_type((uint32_t)(tr & 0xff))) atomicOr(err, (uint32_t)kErrBadType);  // (the table encoder itself is type-blind)
     }
     out.pfx[i] = make_ulonglong2(hi, lo);
     out.tr[i] = tr;

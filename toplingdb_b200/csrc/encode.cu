@@ -102,7 +102,7 @@ encode_sizes_kernel(KeyCols m, const unsigned long long* __restrict__ n_dev, uin
           mxs = s1 > mxs ? s1 : mxs;
           kb += ks;
           vb += vs;
-          nd += (ctr[q] & 0xff) == kTypeDeletion;
+          nd += is_deletion_type((uint32_t)(ctr[q] & 0xff));
           const uint64_t sq = ctr[q] >> 8;
           smin = sq < smin ? sq : smin;
           smax = sq > smax ? sq : smax;
@@ -1051,7 +1051,7 @@ __global__ void encode_filestats_kernel(KeyCols m, EncodeWork wk, uint32_t nfile
         const uint32_t mt = m.meta[i];
         kb += meta_ulen(mt) + 8;
         vb += meta_vlen(mt);
-        nd += (tr & 0xff) == kTypeDeletion;
+        nd += is_deletion_type((uint32_t)(tr & 0xff));
         const uint64_t sq = tr >> 8;
         smin = sq < smin ? sq : smin;
         smax = sq > smax ? sq : smax;

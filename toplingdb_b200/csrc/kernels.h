@@ -62,7 +62,12 @@ void launch_copy_small(const void* src, void* dst, uint32_t n, cudaStream_t st);
 void launch_scatter_tails(const TailCopy* recs, uint32_t n, const uint8_t* staged, uint8_t* out, cudaStream_t st);
 
 // ---- merge.cu
-constexpr int kMergeTile = 2048;     // merged entries per CTA tile
+constexpr int kMergeTile = 2048;     // capacity of a CTA tile (merged entries)
+// Tiles are cut every kMergeNominal merged entries.  When an input holds a kTypeSingleDeletion the cut moves forward to the end of the
+// user key it falls into (at most kSdSpill entries), so that all versions of a key meet in one tile: the SingleDelete rules are a
+// chain through the versions of a key (compaction_iterator.cc:662-887) and are walked serially per key (group_rules.h).
+constexpr int kSdSpill = 32;
+constexpr int kMergeNominal = kMergeTile - kSdSpill;
 constexpr int kMaxRuns = 64;
 struct MergeParams {
   uint32_t nruns;
@@ -73,6 +78,7 @@ struct MergeParams {
   uint32_t filter;                   // b200c_compaction_filter
   int32_t ttl;                       // B200C_FILTER_TTL
   int64_t now;
+  uint32_t write_conflict_snapshot;  // CompactionParams::earliest_write_conflict_snapshot is set (transaction DB): SingleDelete -> CPU
 };
 struct TileStat {            // partial sums for the per-file statistics over one "stat tile" of consecutive output entries
   uint64_t raw_key, raw_value, deletions, smallest_seq, largest_seq;

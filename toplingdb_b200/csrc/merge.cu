@@ -17,6 +17,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "group_rules.h"
 #include "kernels.h"
 
 namespace b200c {
@@ -55,7 +56,7 @@ merge_partition_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t n_to
   const unsigned lane = threadIdx.x & 31;
   const uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b > ntiles) return;
-  uint64_t d = b * (uint64_t)kMT;
+  uint64_t d = b * (uint64_t)kMergeNominal;
   if (d > n_total) d = n_total;
   uint64_t base[2], lo[2], hi[2];
 #pragma unroll
@@ -111,6 +112,8 @@ merge_partition_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t n_to
 #pragma unroll
   for (int dd = 16; dd; dd >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, dd);
   if (tot != d && lane == 0) atomicOr(err, kErrKeyOrder);
+  // (tile cuts are not aligned to user keys here: SingleDeletes with more than 16 runs stay on the CPU)
+  if (lane == 0 && (*reinterpret_cast<volatile uint32_t*>(err) & (uint32_t)kFlagHasSingleDelete)) atomicOr(err, (uint32_t)kErrGroupTooLong);
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     uint32_t r = lane + 32 * s;
@@ -228,16 +231,17 @@ merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint3
   const uint64_t base = r < nruns ? runs.begin[r] : 0;
   const uint64_t nrun = r < nruns ? runs.end[r] - runs.begin[r] : 0;
   uint64_t prev_lo = 0, prev_d = 0;
+  const bool sd_mode = (*reinterpret_cast<volatile uint32_t*>(err) & (uint32_t)kFlagHasSingleDelete) != 0;  // set by the decoder
   for (uint32_t c = 0; c < kPartChunk; c++) {
     const uint64_t b = b0 + c;
     if (b > ntiles) break;
-    uint64_t d = b * (uint64_t)kMT;
+    uint64_t d = b * (uint64_t)kMergeNominal;
     if (d > n_total) d = n_total;
     uint64_t lo = (d == n_total) ? nrun : 0, hi = (d == 0) ? 0 : nrun;
     if (d != 0 && d != n_total) {
-      if (c != 0) {
+      if (c != 0) {  // (prev_d may lie a few entries behind its nominal rank: see the alignment below)
         lo = prev_lo;
-        hi = prev_lo + (d - prev_d) < nrun ? prev_lo + (d - prev_d) : nrun;
+        hi = d > prev_d ? (prev_lo + (d - prev_d) < nrun ? prev_lo + (d - prev_d) : nrun) : prev_lo;
       } else {
         // ---- level 1: the samples
         const uint64_t S = kPartStride, msamp = (nrun + S - 1) / S;
@@ -264,6 +268,45 @@ merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint3
 #pragma unroll
     for (int dd = 16; dd; dd >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, dd);
     if (tot != d && lane == 0) atomicOr(err, kErrKeyOrder);
+    // ---- inputs with SingleDeletes: no user key may straddle a tile boundary.  The entry in front of the cut and the one behind it
+    // share a user key => the cut moves behind that key's last version, in every run (they are the smallest entries left).
+    if (sd_mode && d != 0 && d != n_total) {
+      Key head, tail;  // per run: first entry behind / last entry in front of the cut (one lane per run: sub == 0)
+      head.hi = head.lo = ~0ull, head.ulen = 0xffffffffu, head.tr = 0;
+      tail.hi = tail.lo = 0, tail.ulen = 0, tail.tr = ~0ull;
+      const bool have_head = r < nruns && sub == 0 && lo < nrun, have_tail = r < nruns && sub == 0 && lo > 0;
+      if (have_head) head = load_key(in, base + lo);
+      if (have_tail) tail = load_key(in, base + lo - 1);
+      // smallest head user key / largest tail user key over the runs (user-key order; trailers do not matter here)
+      Key mh = head, mt = tail;
+      bool anyh = have_head, anyt = have_tail;
+#pragma unroll
+      for (int dd = 16; dd; dd >>= 1) {
+        Key oh, ot;
+        oh.hi = __shfl_xor_sync(0xffffffffu, mh.hi, dd), oh.lo = __shfl_xor_sync(0xffffffffu, mh.lo, dd), oh.ulen = __shfl_xor_sync(0xffffffffu, mh.ulen, dd);
+        ot.hi = __shfl_xor_sync(0xffffffffu, mt.hi, dd), ot.lo = __shfl_xor_sync(0xffffffffu, mt.lo, dd), ot.ulen = __shfl_xor_sync(0xffffffffu, mt.ulen, dd);
+        const bool ohv = __shfl_xor_sync(0xffffffffu, (int)anyh, dd) != 0, otv = __shfl_xor_sync(0xffffffffu, (int)anyt, dd) != 0;
+        if (ohv && (!anyh || ukey_cmp(oh.hi, oh.lo, oh.ulen, mh.hi, mh.lo, mh.ulen) < 0)) mh = oh, anyh = true;
+        if (otv && (!anyt || ukey_cmp(ot.hi, ot.lo, ot.ulen, mt.hi, mt.lo, mt.ulen) > 0)) mt = ot, anyt = true;
+      }
+      if (anyh && anyt && ukey_cmp(mh.hi, mh.lo, mh.ulen, mt.hi, mt.lo, mt.ulen) == 0) {
+        uint32_t adv = 0;
+        if (r < nruns && sub == 0) {
+          while (lo < nrun && adv <= (uint32_t)kSdSpill) {
+            const ulonglong2 p = in.pfx[base + lo];
+            if (p.x != mh.hi || p.y != mh.lo || meta_ulen(in.meta[base + lo]) != mh.ulen) break;
+            lo++;
+            adv++;
+          }
+        }
+        uint32_t tadv = adv;
+#pragma unroll
+        for (int dd = 16; dd; dd >>= 1) tadv += __shfl_xor_sync(0xffffffffu, tadv, dd);
+        if (tadv > (uint32_t)kSdSpill && lane == 0) atomicOr(err, (uint32_t)kErrGroupTooLong);
+        d += tadv;
+        lo = __shfl_sync(0xffffffffu, lo, (int)L.gbase);  // every lane of the run's group carries the moved cut
+      }
+    }
     if (r < nruns && sub == 0) splits[b * nruns + r] = lo;
     prev_lo = lo;
     prev_d = d;
@@ -278,6 +321,7 @@ struct TileSmem {
   uint64_t hi[kMT], lo[kMT], tr[kMT];
   uint16_t idx[kMT];               // merge order: idx[o] = load position of the o-th smallest key
   uint8_t ulen[kMT];
+  uint8_t verd[kMT];               // per merged position: verdict of the serial SingleDelete walk (bit 7: walked)
   uint32_t seg[kMaxRuns + 1];      // segment starts in load order
   uint32_t lst[2][kMaxRuns + 2];   // list bounds per merge round (ping-pong)
   uint64_t sbeg[kMaxRuns];         // absolute index of each segment's first element
@@ -588,6 +632,85 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     nlists = nn;
     cur ^= 1;
   }
+  // ---- SingleDelete (compaction_iterator.cc:662-887): whether a SingleDelete and the version below it cancel depends on what
+  // happened to the versions above them -- a chain through all versions of the user key.  Tiles are cut at user-key boundaries
+  // when an input holds one (merge_partition_grouped_kernel), so a key's versions are all here; the thread that owns a key's first
+  // position walks the key with group_walk (group_rules.h, the reference's rules for one key) and leaves a verdict per version.
+  constexpr uint32_t kMaxGroup = 64;
+  bool my_sd = false;
+#pragma unroll
+  for (int x = 0; x < kMV; x++) {
+    const uint32_t o = t * kMV + x;
+    if (o < cnt && (s.tr[s.idx[PH(o)]] & 0xff) == kTypeSingleDeletion) my_sd = true;
+  }
+  const bool tile_sd = __syncthreads_or(my_sd) != 0;
+  unsigned long long w_hidden = 0, w_obsolete = 0, w_userdrop = 0;
+  if (tile_sd) {
+    if (t == 0 && mp.write_conflict_snapshot) atomicOr(err, (uint32_t)kErrSdWriteConflict);
+    for (int x = 0; x < kMV; x++) {
+      const uint32_t o = t * kMV + x;
+      if (o < cnt) s.verd[o] = 0;
+    }
+    __syncthreads();
+    for (int x = 0; x < kMV; x++) {
+      const uint32_t o = t * kMV + x;
+      if (o >= cnt) break;
+      const uint32_t id0 = s.idx[PH(o)];
+      const Key k0 = skey(s, id0);
+      bool head = true;
+      if (o > 0) {
+        const Key p = skey(s, s.idx[PH(o - 1)]);
+        head = !(p.hi == k0.hi && p.lo == k0.lo && p.ulen == k0.ulen);
+      } else if (s.has_pred && s.pred.hi == k0.hi && s.pred.lo == k0.lo && s.pred.ulen == k0.ulen) {
+        atomicOr(err, (uint32_t)kErrInternal);  // the partition keeps keys inside one tile in this mode
+      }
+      if (!head) continue;
+      GroupVersion gv[kMaxGroup];
+      uint32_t n = 0;
+      bool has_sd = false;
+      for (uint32_t q = o; q < cnt; q++) {
+        const uint32_t id = s.idx[PH(q)];
+        if (q != o && !(s.hi[id] == k0.hi && s.lo[id] == k0.lo && (s.ulen[id] & 0x3fu) == k0.ulen)) break;
+        const uint64_t tr = s.tr[id];
+        has_sd = has_sd || (tr & 0xff) == kTypeSingleDeletion;
+        if (n < kMaxGroup) gv[n] = GroupVersion{tr >> 8, (uint8_t)(tr & 0xff)};
+        n++;
+      }
+      if (!has_sd) continue;
+      if (n > kMaxGroup) {
+        atomicOr(err, (uint32_t)kErrGroupTooLong);
+        continue;
+      }
+      GroupRules gr;
+      gr.snapshots = mp.snapshots;
+      gr.num_snapshots = mp.nsnapshots;
+      gr.bottommost = mp.bottommost;
+      gr.earliest_write_conflict_snapshot = kGrMaxSeq;
+      gr.key_not_exists_beyond_output_level = mp.bottommost;  // worker semantics (compaction.cc:555-556)
+      gr.filter_removes_newest = 0;
+      if (mp.filter != 0 && gv[0].type == kGrValue)
+        gr.filter_removes_newest = mp.filter == 1 ? (s.ulen[id0] & 0x80u) != 0 : filter_removes(mp, in, [&]() -> uint64_t {
+          uint32_t lo = 0, hi = k;
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s.seg[mid] <= id0) lo = mid;
+            else hi = mid;
+          }
+          return s.sbeg[lo] + (id0 - s.seg[lo]);
+        }());
+      gr.first_key_of_the_job = 0;  // only matters with a write-conflict snapshot (rejected above)
+      GroupVerdict vd[kMaxGroup];
+      GroupCounters gc{0, 0, 0, 0};
+      if (group_walk(gv, n, gr, vd, &gc) != 0) atomicOr(err, (uint32_t)kErrSingleDelContract);
+      for (uint32_t i = 0; i < n; i++)
+        s.verd[o + i] = (uint8_t)(0x80u | (vd[i].keep ? 1u : 0u) | (vd[i].zero_seq ? 2u : 0u) | (vd[i].clear_value ? 4u : 0u) |
+                                  (vd[i].out_type != gv[i].type ? 8u : 0u));
+      w_hidden += gc.drop_hidden;
+      w_obsolete += gc.drop_obsolete;
+      w_userdrop += gc.drop_user;
+    }
+    __syncthreads();
+  }
   // ---- compaction-iterator rules per merged position
   const bool cond_possible = mp.bottommost && mp.nsnapshots > 0;
   auto col_of = [&](uint32_t pos) -> uint64_t {  // column position of the entry at load position pos
@@ -612,6 +735,19 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     const uint32_t id = s.idx[PH(o)];
     oid[x] = (uint16_t)id;
     Key c = skey(s, id);
+    if (tile_sd && (s.verd[o] & 0x80u)) {  // a version of a key with a SingleDelete: the serial walk decided
+      const uint32_t vd = s.verd[o], type0w = (uint32_t)(c.tr & 0xff);
+      c_kbytes += c.ulen + 8;
+      if (is_deletion_type(type0w)) c_indel++;
+      if (vd & 1u) {
+        const uint64_t out_type = (vd & 8u) ? (uint64_t)kTypeDeletion : (uint64_t)type0w;  // a filtered Put leaves as a tombstone
+        keep_mask |= 1u << x;
+        nkeep++;
+        otr[x] = (vd & 2u) ? out_type : (((c.tr >> 8) << 8) | out_type);
+        if (vd & 4u) keep_mask |= 1u << (24 + x);  // written without its value
+      }
+      continue;
+    }
     Key p;
     bool has_prev = true;
     if (o > 0) p = skey(s, s.idx[PH(o - 1)]);
@@ -701,7 +837,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     }
     if (!silent) {
       c_kbytes += c.ulen + 8;
-      if (type0 == kTypeDeletion) c_indel++;
+      if (is_deletion_type(type0)) c_indel++;
     }
     if (silent) c_silent++;
     if (keep) {
@@ -830,7 +966,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         }
         st_kb += cul + 8;
         st_vb += vlen;
-        st_nd += (ctr & 0xff) == kTypeDeletion;
+        st_nd += is_deletion_type((uint32_t)(ctr & 0xff));
         const unsigned long long sq = ctr >> 8;
         st_smin = sq < st_smin ? sq : st_smin;
         st_smax = sq > st_smax ? sq : st_smax;
@@ -861,6 +997,9 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   // ---- counters: one atomic per CTA and counter.  Per-thread partial counts are small (<= kMV entries), so the warp
   // reduction is a single redux instruction per counter; only the (rare) value-byte correction needs 64 bits.
   {
+    c_hidden += w_hidden;
+    c_obsolete += w_obsolete;
+    c_userdrop += w_userdrop;
     const unsigned vals[7] = {nkeep, (unsigned)c_indel, (unsigned)c_hidden, (unsigned)c_obsolete, (unsigned)c_kbytes, (unsigned)c_silent,
                               (unsigned)c_userdrop};
     const int slot[7] = {0, 1, 2, 3, 4, 6, 7};
@@ -998,7 +1137,7 @@ void launch_merge_partition(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t
   merge_partition_kernel<<<(warps + 3) / 4, 128, 0, st>>>(in, runs, nruns, n_total, ntiles, splits, err);
 }
 static_assert(sizeof(Key) * kMaxRuns <= sizeof(uint64_t) * kMT && 4 * kMaxRuns <= 2 * kMT, "candidate staging must fit");
-static_assert(4 * (sizeof(TileSmem) + 1024) <= 227 * 1024, "merge tile must fit four CTAs per SM");
+static_assert(3 * (sizeof(TileSmem) + 1024) <= 227 * 1024, "merge tile must fit three CTAs per SM");
 void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                         const uint64_t* splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
                         MergeCounters* counters, MergeSizes ms, uint32_t* err, cudaStream_t st) {
@@ -1007,20 +1146,11 @@ void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_t
   const uint64_t dev_bit = attr.bit_of_current_device();
   if (!attr.is_set(dev_bit)) {
     cudaFuncSetAttribute(merge_tiles_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
-    cudaFuncSetAttribute(merge_tiles_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
     attr.set(dev_bit);
   }
-  static int occ = 0;
-  if (!occ) {
-    const char* e = getenv("B200C_MERGE_CTAS_PER_SM");  // tuning knob: 3 = 80 registers, 4 = 64 registers (spills) but 32 warps per SM
-    occ = e && atoi(e) == 4 ? 4 : 3;
-  }
-  if (occ == 4)
-    merge_tiles_kernel<4><<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state, ticket, out,
-                                                                                 counters, ms, err, 148u * 4u);
-  else
-    merge_tiles_kernel<3><<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state, ticket, out,
-                                                                                 counters, ms, err, 148u * 3u);
+  // three CTAs per SM at 80 registers (measured: four at 64 registers with spills are slower, profiles/README.md)
+  merge_tiles_kernel<3><<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state, ticket, out,
+                                                                               counters, ms, err, 148u * 3u);
 }
 void launch_merge_sizes_fix(KeyCols merged, const unsigned long long* tile_state, uint64_t ntiles, MergeSizes ms, cudaStream_t st) {
   if (ntiles) merge_sizes_fix_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(merged, tile_state, ntiles, ms);

@@ -39,6 +39,7 @@ class Params(C.Structure):
         ("range_start_user_key", C.c_char_p), ("range_start_len", C.c_uint32), ("has_range_start", C.c_uint32),
         ("range_end_user_key", C.c_char_p), ("range_end_len", C.c_uint32), ("has_range_end", C.c_uint32),
         ("paranoid_file_checks", C.c_uint32), ("bloom_millibits_per_key", C.c_uint32),
+        ("earliest_write_conflict_snapshot", C.c_uint64),
     ]
 
 

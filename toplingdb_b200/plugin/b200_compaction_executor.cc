@@ -231,6 +231,7 @@ class B200CompactionExecutor : public CompactionExecutor {
     bp.verify_input_checksums = opt_.verify_input_checksums;
     bp.paranoid_file_checks = p.paranoid_file_checks;  // RunRemote cannot hash what it did not write (compaction_job.cc:1065-1068)
     bp.bloom_millibits_per_key = (uint32_t)std::max(0, DeviceBloomMillibits(c_, bbt));
+    bp.earliest_write_conflict_snapshot = p.earliest_write_conflict_snapshot;
     std::vector<uint64_t> snaps;
     if (p.existing_snapshots) snaps.assign(p.existing_snapshots->begin(), p.existing_snapshots->end());
     bp.snapshots = snaps.data();
