@@ -30,6 +30,13 @@ struct fstring {
     return i;
   }
   bool startsWith(fstring x) const { return n >= x.n && memcmp(p, x.p, (size_t)x.n) == 0; }
+  bool starts_with(fstring x) const { return startsWith(x); }
+  fstring substr(size_t pos) const { return pos < (size_t)n ? fstring(p + pos, (size_t)n - pos) : fstring(); }
+  fstring substr(size_t pos, size_t len) const {
+    if (pos >= (size_t)n) return fstring();
+    const size_t m = (size_t)n - pos;
+    return fstring(p + pos, len < m ? len : m);
+  }
   int compare(fstring y) const {
     size_t m = (size_t)(n < y.n ? n : y.n);
     int r = memcmp(p, y.p, m);
@@ -58,13 +65,5 @@ inline long getEnvLong(const char* name, long dflt = 0) {
 inline double getEnvDouble(const char* name, double dflt = 0) {
   const char* v = getenv(name);
   return v ? strtod(v, nullptr) : dflt;
-}
-inline void ReplaceSubStr(std::string& s, fstring from, fstring to) {
-  if (from.empty()) return;
-  size_t pos = 0;
-  while ((pos = s.find(from.p, pos, from.size())) != std::string::npos) {
-    s.replace(pos, from.size(), to.p, to.size());
-    pos += to.size();
-  }
 }
 }

@@ -408,3 +408,10 @@ def load_golden(name):
 
 STAT_KEYS = ("num_input_records", "num_output_records", "num_records_replaced", "num_expired_deletion_records",
              "num_input_deletion_records", "total_input_raw_key_bytes", "total_input_raw_value_bytes")
+
+
+def sizes_without_file_number(outputs):
+    """file sizes minus the width of rocksdb.original.file.number: on the RunRemote branch that property is the executor's own job-unique
+    number (the DB renames the file to a number it allocates afterwards, compaction_job.cc:1022-1034), so its varint may be wider than
+    the one the local path writes -- everything else in the files is compared byte for byte"""
+    return [len(o) - len(sstfmt.parse_sst(o)["properties"]["rocksdb.original.file.number"]) for o in outputs]

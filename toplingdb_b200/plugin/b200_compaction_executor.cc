@@ -524,10 +524,10 @@ std::shared_ptr<CompactionExecutorFactory> NewB200CompactionExecutorFactory(cons
 namespace ROCKSDB_NAMESPACE {
 static std::shared_ptr<CompactionExecutorFactory> JS_NewB200Compact(const json& js, const SidePluginRepo&) {
   B200CompactOptions o;
-  ROCKSDB_JSON_OPT_PROP(js, o.device);
-  ROCKSDB_JSON_OPT_PROP(js, o.allow_fallback_to_local);
-  ROCKSDB_JSON_OPT_PROP(js, o.verify_input_checksums);
-  ROCKSDB_JSON_OPT_PROP(js, o.scratch_dir);
+  ROCKSDB_JSON_OPT_PROP_3(js, o.device, "device");
+  ROCKSDB_JSON_OPT_PROP_3(js, o.allow_fallback_to_local, "allow_fallback_to_local");
+  ROCKSDB_JSON_OPT_PROP_3(js, o.verify_input_checksums, "verify_input_checksums");
+  ROCKSDB_JSON_OPT_PROP_3(js, o.scratch_dir, "scratch_dir");
   return std::make_shared<B200CompactionExecutorFactory>(o);
 }
 ROCKSDB_FACTORY_REG("B200Compact", JS_NewB200Compact);

@@ -333,13 +333,13 @@ namespace ROCKSDB_NAMESPACE {
 static std::shared_ptr<TableFactory> JS_NewB200TableFactory(const json& js, const SidePluginRepo&) {
   B200TableFactoryOptions o;
   BlockBasedTableOptions t;
-  ROCKSDB_JSON_OPT_PROP(js, o.device);
-  ROCKSDB_JSON_OPT_PROP(js, o.allow_fallback);
-  ROCKSDB_JSON_OPT_PROP(js, o.min_device_bytes);
-  ROCKSDB_JSON_OPT_PROP(js, t.block_size);
-  ROCKSDB_JSON_OPT_PROP(js, t.block_size_deviation);
-  ROCKSDB_JSON_OPT_PROP(js, t.block_restart_interval);
-  ROCKSDB_JSON_OPT_PROP(js, t.format_version);
+  ROCKSDB_JSON_OPT_PROP_3(js, o.device, "device");
+  ROCKSDB_JSON_OPT_PROP_3(js, o.allow_fallback, "allow_fallback");
+  ROCKSDB_JSON_OPT_PROP_3(js, o.min_device_bytes, "min_device_bytes");
+  ROCKSDB_JSON_OPT_PROP_3(js, t.block_size, "block_size");
+  ROCKSDB_JSON_OPT_PROP_3(js, t.block_size_deviation, "block_size_deviation");
+  ROCKSDB_JSON_OPT_PROP_3(js, t.block_restart_interval, "block_restart_interval");
+  ROCKSDB_JSON_OPT_PROP_3(js, t.format_version, "format_version");
   return std::make_shared<B200TableFactory>(t, o);
 }
 ROCKSDB_FACTORY_REG("B200BlockBasedTable", JS_NewB200TableFactory);
