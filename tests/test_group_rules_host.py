@@ -49,6 +49,7 @@ def walk_stream(sim, p, stream, key_not_exists=None):
     snaps = (C.c_uint64 * max(1, len(p.snapshots)))(*p.snapshots)
     counters = (C.c_uint32 * 4)()
     out, job_has_output = [], False
+    walk_stream.examined_key_bytes = 0  # key bytes of the versions the iterator examined (total_input_raw_key_bytes)
     for uk, grp in itertools.groupby(stream, key=lambda e: e[0][:-8]):
         grp = list(grp)
         # identical internal keys (same user key and sequence number in two files) are one version to the iterator's rules: the second
@@ -64,9 +65,11 @@ def walk_stream(sim, p, stream, key_not_exists=None):
         assert rc == 0
         for i, (ik, v) in enumerate(grp):
             keep, otype, clear, zero = verd[4 * i:4 * i + 4]
+            if not clear & 2:  # kGrSkipped: stepped over inside another version's branch
+                walk_stream.examined_key_bytes += len(ik)
             if keep:
                 seq = 0 if zero else struct.unpack("<Q", ik[-8:])[0] >> 8
-                out.append((uk + struct.pack("<Q", (seq << 8) | otype), b"" if clear else v))
+                out.append((uk + struct.pack("<Q", (seq << 8) | otype), b"" if clear & 1 else v))
                 job_has_output = True
     return out, list(counters)
 
@@ -100,6 +103,7 @@ def test_group_walk_with_single_deletes_matches_the_oracle(sim, seed):
     got, cnt = walk_stream(sim, p, stream)
     assert got == H.parse_kvstream(want_kv)
     assert cnt[0] == st.num_records_replaced and cnt[1] == st.num_expired_deletion_records
+    assert walk_stream.examined_key_bytes == st.total_input_raw_key_bytes
 
 
 KAT = json.load(open(os.path.join(H.GOLDEN_DIR, "compaction_job_kat.json")))["cases"]

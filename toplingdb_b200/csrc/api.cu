@@ -132,6 +132,7 @@ struct b200c_job {
   DevBuf esz, eshared, tstat, nxt, disk, rows, tstate, grows, gstate, gflag, gsync, idx_contrib, idx_contrib_off, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
   uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
   uint32_t nfiles_out = 0, nruns = 0;
+  DevBuf bloom_contrib, bloom_contrib_off;  // scratch of the filter blocks' checksums
   DevBuf kv_arena, kv_offs, kv_klens;  // b200c_job_encode_kv: the caller's records on the device
   DevBuf run_bounds, run_first_d;  // [begin[K] | end[K]] of the sorted runs in the decoded columns; first file of each run
   std::vector<uint64_t> run_start_h;
@@ -479,11 +480,20 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     launches += 3;
     if (P.bloom_millibits_per_key) {
       j->kt_begin("encode.bloom_build");
-      for (uint32_t f = 0; f < nfiles; f++)
-        if (frs[f].filter_bytes) CU(cudaMemsetAsync(bases[f] + frs[f].data_size, 0, frs[f].filter_bytes, st));
-      launch_bloom_build(mcols, n_out, W.files, nfiles, P.bloom_millibits_per_key, P.checksum, out_base_d, st);
+      // scratch for the parallel part of the filter blocks' checksums: 8 u64 per full 1024-byte block
+      std::vector<uint64_t> boff(nfiles + 1, 0);
+      uint64_t max_fb = 0;
+      for (uint32_t f = 0; f < nfiles; f++) {
+        boff[f + 1] = boff[f] + frs[f].filter_bytes / 1024 + 1;
+        max_fb = std::max<uint64_t>(max_fb, frs[f].filter_bytes);
+      }
+      CU(j->bloom_contrib.reserve(64 * (boff[nfiles] + 1)));
+      CU(j->bloom_contrib_off.reserve(8 * (nfiles + 1)));
+      if (int rc = upload_small(j, j->bloom_contrib_off.p, boff.data(), 8 * (nfiles + 1))) return rc;
+      launch_bloom_build(mcols, n_out, W.files, nfiles, (uint32_t)std::min<uint64_t>(max_fb, 0xffffffffull), P.bloom_millibits_per_key, P.checksum,
+                         out_base_d, j->bloom_contrib.as<uint64_t>(), j->bloom_contrib_off.as<uint64_t>(), st);
       j->kt_end();
-      launches += 2;
+      launches += 3;
     }
     CU(cudaStreamWaitEvent(st, j->evx[3], 0));
     {
@@ -1217,7 +1227,7 @@ int b200c_job_get_stats(const b200c_job* j, b200c_stats* s) {
 void b200c_job_destroy(b200c_job* j) {
   if (!j) return;
   cudaSetDevice(j->p.device);
-  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->run_bounds, &j->run_first_d, &j->kv_arena, &j->kv_offs, &j->kv_klens, &j->small,
+  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->run_bounds, &j->run_first_d, &j->kv_arena, &j->kv_offs, &j->kv_klens, &j->bloom_contrib, &j->bloom_contrib_off, &j->small,
                    &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
                    &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->tstat, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->gsync, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};

@@ -1849,48 +1849,104 @@ void launch_bloom_count(KeyCols m, uint64_t n, FileRec* files, const uint64_t* n
   bloom_count_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(m, n, files, nfiles_dev);
   bloom_layout_kernel<<<(kMaxOutFiles + 255) / 256, 256, 0, st>>>(files, nfiles_dev, millibits);
 }
-// the filter bytes were zeroed by the host (cudaMemsetAsync per file); bits are OR-ed in through the aligned 32-bit word that holds
-// the byte (the block starts wherever the data blocks ended, so its bytes are not word aligned; OR-ing zeros into the neighbouring
-// bytes of a word leaves them as they are)
-__global__ void __launch_bounds__(256)
-bloom_bits_kernel(KeyCols m, uint64_t n, const FileRec* __restrict__ files, uint32_t nfiles, int probes, uint8_t* const* __restrict__ out_base) {
-  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t f = file_of_entry(files, nfiles, e);
-    const FileRec& fr = files[f];
-    uint64_t h;
-    if (!entry_adds_hash(m, e, fr.first_entry, &h)) continue;
-    if (fr.filter_bytes <= kBloomMetadataLen + 5) continue;  // zero-length bit array (cannot happen with >= 1 entry)
-    const uint32_t bits_bytes = (uint32_t)(fr.filter_bytes - kBloomMetadataLen - 5);
-    uint8_t* line = out_base[f] + fr.data_size + bloom_line_offset(h, bits_bytes);
+// ---- filter bits.  FastLocalBloom puts all probes of a key into ONE 64-byte line of the filter (util/bloom_impl.h:200-214), and a
+// file's whole filter is small (1.25 bytes per key at 10 bits).  So the filter is built in SLICES of shared memory: a CTA owns
+// kBloomSliceBytes of one file's filter, scans all of the file's keys (hash = a few integer operations on the key columns), applies the
+// keys whose line falls into its slice with shared-memory atomics and writes the finished slice with one bulk store.  (Round 1 OR-ed
+// 230 M bits into L2 with global atomics: 5 ms on the cfg2 job; this is a scan of L2-resident key columns per slice.)
+constexpr uint32_t kBloomSliceBytes = 192 * 1024;
+constexpr int kBloomThreads = 1024;
+__global__ void __launch_bounds__(kBloomThreads, 1)
+bloom_slices_kernel(KeyCols m, const FileRec* __restrict__ files, uint32_t nfiles, int probes, uint8_t* const* __restrict__ out_base) {
+  extern __shared__ __align__(128) uint8_t bsm[];
+  const uint32_t f = blockIdx.y;
+  if (f >= nfiles) return;
+  const FileRec& fr = files[f];
+  if (fr.filter_bytes <= kBloomMetadataLen + 5) return;
+  const uint32_t bits_bytes = (uint32_t)(fr.filter_bytes - kBloomMetadataLen - 5);
+  const uint32_t s0 = blockIdx.x * kBloomSliceBytes;
+  if (s0 >= bits_bytes) return;
+  const uint32_t s1 = s0 + kBloomSliceBytes < bits_bytes ? s0 + kBloomSliceBytes : bits_bytes;
+  uint8_t* const gdst = out_base[f] + fr.data_size + s0;  // the filter block follows the data blocks, at any byte alignment
+  const uint32_t shift = (uint32_t)((uintptr_t)gdst & 15);
+  uint8_t* const img = bsm + shift;  // the slice at the destination's 16-byte phase (so that it leaves as one bulk copy)
+  uint32_t* const w32 = reinterpret_cast<uint32_t*>(bsm);
+  for (uint32_t i = threadIdx.x; i < (kBloomSliceBytes + 16) / 4; i += kBloomThreads) w32[i] = 0;
+  __syncthreads();
+  const uint64_t e0 = fr.first_entry, e1 = e0 + fr.n_entries;
+  const unsigned lane = threadIdx.x & 31;
+  for (uint64_t eb = e0; eb < e1; eb += kBloomThreads) {
+    const uint64_t e = eb + threadIdx.x;
+    uint64_t h = 0;
+    const bool valid = e < e1;
+    if (valid) h = entry_key_hash(m, e);
+    // XXPH3FilterBitsBuilder::AddKey (filter_policy.cc:73-92) drops a key whose hash equals that of the key added before it
+    uint64_t ph = __shfl_up_sync(0xffffffffu, h, 1);
+    if (lane == 0 && valid && e > e0) ph = entry_key_hash(m, e - 1);
+    if (!valid || (e > e0 && ph == h)) continue;
+    const uint32_t line = bloom_line_offset(h, bits_bytes);
+    if (line < s0 || line >= s1) continue;
     uint32_t p = bloom_first_probe(h);
     for (int k = 0; k < probes; k++, p = bloom_next_probe(p)) {
       const uint32_t bit = bloom_probe_bit(p);
-      const uintptr_t addr = (uintptr_t)(line + (bit >> 3));
-      atomicOr(reinterpret_cast<unsigned int*>(addr & ~(uintptr_t)3), 1u << (8 * (uint32_t)(addr & 3) + (bit & 7)));
+      const uint32_t byte = shift + (line - s0) + (bit >> 3);  // offset inside bsm
+      atomicOr(&w32[byte >> 2], 1u << (8 * (byte & 3) + (bit & 7)));
     }
   }
-}
-// one warp per file: metadata bytes, then the block trailer (WriteMaybeCompressedBlock: type kNoCompression + checksum)
-__global__ void bloom_finish_kernel(const FileRec* __restrict__ files, uint32_t nfiles, int probes, uint32_t cksum,
-                                    uint8_t* const* __restrict__ out_base) {
-  const uint32_t f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (f >= nfiles) return;
-  const FileRec fr = files[f];
-  if (fr.filter_bytes == 0) return;
-  uint8_t* fb = out_base[f] + fr.data_size;
-  const uint64_t content = fr.filter_bytes - 5;  // bits + metadata
-  if ((threadIdx.x & 31) == 0) {
-    uint8_t* md = fb + content - kBloomMetadataLen;
+  __syncthreads();
+  // store: head bytes up to the first 16-byte boundary, the aligned middle as one bulk copy (TMA), tail bytes
+  const uint32_t total = s1 - s0;
+  uint32_t head = shift ? 16 - shift : 0;
+  if (head > total) head = total;
+  const uint32_t mid = (total - head) & ~15u;
+  fence_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0 && mid) {
+    bulk_s2g(gdst + head, (uint32_t)__cvta_generic_to_shared(img + head), mid);
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  if (threadIdx.x < head) gdst[threadIdx.x] = img[threadIdx.x];
+  const uint32_t done = head + mid;
+  if (done + threadIdx.x < total) gdst[done + threadIdx.x] = img[done + threadIdx.x];
+  if (s1 == bits_bytes && threadIdx.x == 32) {  // the CTA of the last slice also writes the metadata bytes behind the bits
+    uint8_t* md = out_base[f] + fr.data_size + bits_bytes;
     md[0] = 0xff;  // marker: newer Bloom implementations (filter_policy.cc:378-385)
     md[1] = 0;     // sub-implementation: FastLocalBloom
     md[2] = (uint8_t)probes;
     md[3] = 0;
     md[4] = 0;
   }
-  __threadfence();
-  __syncwarp();
-  const uint32_t ck = block_checksum_warp(cksum, fb, content, 0);
-  __syncwarp();
+}
+// XXH3 accumulator contributions of the full 1024-byte blocks of every filter block (bits + metadata), one warp per block: the
+// checksum of a 1.5 MB filter by a single warp would be a chain of 1500 dependent memory round trips
+__global__ void bloom_contrib_kernel(const FileRec* __restrict__ files, uint32_t nfiles, uint8_t* const* __restrict__ out_base,
+                                     uint64_t* __restrict__ contrib, const uint64_t* __restrict__ contrib_off) {
+  const uint32_t f = blockIdx.y;
+  if (f >= nfiles) return;
+  const FileRec fr = files[f];
+  if (fr.filter_bytes <= 5 + 240) return;
+  const uint64_t content = fr.filter_bytes - 5;
+  const uint8_t* fb = out_base[f] + fr.data_size;
+  const uint64_t nb_blocks = (content - 1) / 1024;
+  const unsigned lane = threadIdx.x & 31;
+  const XxhLaneSecret ks = xxh_lane_secret();
+  for (uint64_t k = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nb_blocks; k += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+    const uint64_t part = xxh3_block_contrib<false>(fb + 1024 * k, 16, ks);
+    if (lane < 8) contrib[(contrib_off[f] + k) * 8 + lane] = part;
+  }
+}
+// one warp per file: the block trailer (WriteMaybeCompressedBlock: type kNoCompression + checksum)
+__global__ void bloom_finish_kernel(const FileRec* __restrict__ files, uint32_t nfiles, uint32_t cksum, uint8_t* const* __restrict__ out_base,
+                                    const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ contrib_off) {
+  const uint32_t f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= nfiles) return;
+  const FileRec fr = files[f];
+  if (fr.filter_bytes == 0) return;
+  uint8_t* fb = out_base[f] + fr.data_size;
+  const uint64_t content = fr.filter_bytes - 5;  // bits + metadata
+  uint32_t ck;
+  if (cksum == 4) ck = (uint32_t)xxh3_64_warp_t<false>(fb, content, contrib + contrib_off[f] * 8);  // last byte (type 0) adds nothing
+  else ck = block_checksum_warp(cksum, fb, content, 0);
   if ((threadIdx.x & 31) == 0) {
     uint8_t* tp = fb + content;
     tp[0] = 0;
@@ -1900,13 +1956,21 @@ __global__ void bloom_finish_kernel(const FileRec* __restrict__ files, uint32_t 
     tp[4] = (uint8_t)(ck >> 24);
   }
 }
-void launch_bloom_build(KeyCols m, uint64_t n, const FileRec* files, uint32_t nfiles, uint32_t millibits, uint32_t cksum,
-                        uint8_t* const* out_base, cudaStream_t st) {
+void launch_bloom_build(KeyCols m, uint64_t n, const FileRec* files, uint32_t nfiles, uint32_t max_filter_bytes, uint32_t millibits, uint32_t cksum,
+                        uint8_t* const* out_base, uint64_t* contrib, const uint64_t* contrib_off, cudaStream_t st) {
   if (n == 0 || nfiles == 0) return;
   const int probes = bloom_num_probes((int)millibits);
-  const uint64_t blocks = (n + 255) / 256;
-  bloom_bits_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(m, n, files, nfiles, probes, out_base);
-  bloom_finish_kernel<<<(nfiles + 3) / 4, 128, 0, st>>>(files, nfiles, probes, cksum, out_base);
+  static PerDeviceFlag attr;
+  const uint64_t dev_bit = attr.bit_of_current_device();
+  const int smem = (int)kBloomSliceBytes + 16;
+  if (!attr.is_set(dev_bit)) {
+    cudaFuncSetAttribute(bloom_slices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr.set(dev_bit);
+  }
+  const unsigned slices = (max_filter_bytes + kBloomSliceBytes - 1) / kBloomSliceBytes;
+  bloom_slices_kernel<<<dim3(slices ? slices : 1, nfiles), kBloomThreads, smem, st>>>(m, files, nfiles, probes, out_base);
+  if (cksum == 4) bloom_contrib_kernel<<<dim3(32, nfiles), 256, 0, st>>>(files, nfiles, out_base, contrib, contrib_off);
+  bloom_finish_kernel<<<(nfiles + 3) / 4, 128, 0, st>>>(files, nfiles, cksum, out_base, contrib, contrib_off);
 }
 
 // ranks of the grandparent boundary keys in the merged stream (one thread per grandparent file)

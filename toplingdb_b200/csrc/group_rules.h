@@ -30,7 +30,9 @@ struct GroupVersion {   // one version of the key, newest first
 struct GroupVerdict {
   uint8_t keep;         // the version is written out
   uint8_t out_type;     // its type on output (a filtered Put becomes a tombstone)
-  uint8_t clear_value;  // written without its value (:635-661 the Put behind a kept SingleDelete; :385-391 a filtered Put)
+  uint8_t clear_value;  // bit 0: written without its value (:635-661 the Put behind a kept SingleDelete; :385-391 a filtered Put)
+                        // bit 1 (kGrSkipped): consumed without being examined -- the iterator stepped over it inside another version's
+                        // branch, so it is in none of the input statistics (total_input_raw_key_bytes, ..., :509-516)
   uint8_t zero_seq;     // sequence number zeroed (PrepareOutput :1296-1340)
 };
 struct GroupRules {
@@ -46,6 +48,7 @@ struct GroupCounters {  // CompactionIterationStats
   uint32_t drop_hidden, drop_obsolete, optimized_del_drop_obsolete, drop_user;
 };
 constexpr uint64_t kGrMaxSeq = (1ull << 56) - 1;
+constexpr uint8_t kGrSkipped = 2;
 
 // findEarliestVisibleSnapshot (:1343-1396) without a snapshot checker
 B200C_GR_HD uint64_t gr_earliest_visible_snapshot(const GroupRules& r, uint64_t seq, uint64_t* prev) {
@@ -105,6 +108,7 @@ B200C_GR_HD int group_walk(const GroupVersion* v, uint32_t n, const GroupRules& 
         if (last_key_seq_zeroed) {
           cnt->drop_hidden++;
           cnt->drop_obsolete++;
+          out[i + 1].clear_value |= kGrSkipped;
           i += 2;
         } else if (prev_snapshot == 0 || nseq > prev_snapshot) {
           if (ntype == kGrSingleDeletion) {
@@ -117,6 +121,7 @@ B200C_GR_HD int group_walk(const GroupVersion* v, uint32_t n, const GroupRules& 
                      (earliest_snapshot < r.earliest_write_conflict_snapshot && seq <= earliest_snapshot)) {
             cnt->drop_hidden++;
             cnt->drop_obsolete++;
+            out[i + 1].clear_value |= kGrSkipped;
             i += 2;
           } else {
             clear_and_output_next_key = true;
@@ -148,7 +153,7 @@ B200C_GR_HD int group_walk(const GroupVersion* v, uint32_t n, const GroupRules& 
       i++;
     } else if (type == kGrDeletion && r.bottommost) {  // :947-990 everything the tombstone covers in its stripe goes unseen; the
       const uint32_t d = i++;                          // tombstone itself stays only if an older snapshot still sees a version below it
-      while (i < n && (prev_snapshot == 0 || v[i].seq > prev_snapshot)) i++;
+      while (i < n && (prev_snapshot == 0 || v[i].seq > prev_snapshot)) out[i++].clear_value |= kGrSkipped;
       if (i < n) emit(d);
     } else {
       emit(i);

@@ -322,6 +322,7 @@ struct TileSmem {
   uint16_t idx[kMT];               // merge order: idx[o] = load position of the o-th smallest key
   uint8_t ulen[kMT];
   uint8_t verd[kMT];               // per merged position: verdict of the serial SingleDelete walk (bit 7: walked)
+  uint8_t esh[kMT];                // per tile-local output rank: bytes the entry shares with the previous OUTPUT entry
   uint32_t seg[kMaxRuns + 1];      // segment starts in load order
   uint32_t lst[2][kMaxRuns + 2];   // list bounds per merge round (ping-pong)
   uint64_t sbeg[kMaxRuns];         // absolute index of each segment's first element
@@ -476,6 +477,78 @@ __device__ bool group_head(const KeyCols& in, RunBounds runs, uint32_t nruns, ui
   return found;
 }
 
+// Serial walk of the user keys that hold a SingleDelete (one thread per key: the owner of the key's first merged position); leaves a
+// verdict per version in s.verd.  Only called for tiles that contain a SingleDelete; kept out of line so that its local arrays do not
+// weigh on the kernel's common path.
+constexpr uint32_t kMaxGroup = 64;
+__device__ __noinline__ void sd_walk_tile(TileSmem& s, const KeyCols& in, const MergeParams& mp, uint32_t cnt, uint32_t k, uint32_t* err,
+                                          unsigned long long* w_hidden, unsigned long long* w_obsolete, unsigned long long* w_userdrop) {
+  const uint32_t t = threadIdx.x;
+  if (t == 0 && mp.write_conflict_snapshot) atomicOr(err, (uint32_t)kErrSdWriteConflict);
+  for (int x = 0; x < kMV; x++) {
+    const uint32_t o = t * kMV + x;
+    if (o < cnt) s.verd[o] = 0;
+  }
+  __syncthreads();
+  for (int x = 0; x < kMV; x++) {
+    const uint32_t o = t * kMV + x;
+    if (o >= cnt) break;
+    const uint32_t id0 = s.idx[PH(o)];
+    const Key k0 = skey(s, id0);
+    bool head = true;
+    if (o > 0) {
+      const Key p = skey(s, s.idx[PH(o - 1)]);
+      head = !(p.hi == k0.hi && p.lo == k0.lo && p.ulen == k0.ulen);
+    } else if (s.has_pred && s.pred.hi == k0.hi && s.pred.lo == k0.lo && s.pred.ulen == k0.ulen) {
+      atomicOr(err, (uint32_t)kErrInternal);  // the partition keeps keys inside one tile in this mode
+    }
+    if (!head) continue;
+    GroupVersion gv[kMaxGroup];
+    uint32_t n = 0;
+    bool has_sd = false;
+    for (uint32_t q = o; q < cnt; q++) {
+      const uint32_t id = s.idx[PH(q)];
+      if (q != o && !(s.hi[id] == k0.hi && s.lo[id] == k0.lo && (s.ulen[id] & 0x3fu) == k0.ulen)) break;
+      const uint64_t tr = s.tr[id];
+      has_sd = has_sd || (tr & 0xff) == kTypeSingleDeletion;
+      if (n < kMaxGroup) gv[n] = GroupVersion{tr >> 8, (uint8_t)(tr & 0xff)};
+      n++;
+    }
+    if (!has_sd) continue;
+    if (n > kMaxGroup) {
+      atomicOr(err, (uint32_t)kErrGroupTooLong);
+      continue;
+    }
+    GroupRules gr;
+    gr.snapshots = mp.snapshots;
+    gr.num_snapshots = mp.nsnapshots;
+    gr.bottommost = mp.bottommost;
+    gr.earliest_write_conflict_snapshot = kGrMaxSeq;
+    gr.key_not_exists_beyond_output_level = mp.bottommost;  // worker semantics (compaction.cc:555-556)
+    gr.filter_removes_newest = 0;
+    if (mp.filter != 0 && gv[0].type == kGrValue) {
+      uint32_t lo = 0, hi = k;  // column position of the newest version (the filter may have to look at its value)
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s.seg[mid] <= id0) lo = mid;
+        else hi = mid;
+      }
+      gr.filter_removes_newest = mp.filter == 1 ? (s.ulen[id0] & 0x80u) != 0 : filter_removes(mp, in, s.sbeg[lo] + (id0 - s.seg[lo]));
+    }
+    gr.first_key_of_the_job = 0;  // only matters with a write-conflict snapshot (rejected above)
+    GroupVerdict vd[kMaxGroup];
+    GroupCounters gc{0, 0, 0, 0};
+    if (group_walk(gv, n, gr, vd, &gc) != 0) atomicOr(err, (uint32_t)kErrSingleDelContract);
+    for (uint32_t i = 0; i < n; i++)
+      s.verd[o + i] = (uint8_t)(0x80u | (vd[i].keep ? 1u : 0u) | (vd[i].zero_seq ? 2u : 0u) | ((vd[i].clear_value & 1u) ? 4u : 0u) |
+                                (vd[i].out_type != gv[i].type ? 8u : 0u) | ((vd[i].clear_value & kGrSkipped) ? 16u : 0u));
+    *w_hidden += gc.drop_hidden;
+    *w_obsolete += gc.drop_obsolete;
+    *w_userdrop += gc.drop_user;
+  }
+  __syncthreads();
+}
+
 template <int kMinCtas>
 __global__ void __launch_bounds__(kMThreads, kMinCtas)
 merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
@@ -535,6 +608,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   }
   __syncthreads();
   const uint32_t cnt = s.seg[k];
+  bool tile_sd = false;  // some entry of the tile is a kTypeSingleDeletion
   // ---- coalesced load of the k segments.  All of a thread's loads are issued before the first one is consumed: a
   // warp issues in order, so a load-then-store loop body would pay one DRAM round trip per iteration.
   {
@@ -542,6 +616,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     uint64_t ltr[kMV];
     uint32_t lmt[kMV];
     uint32_t lr = 0;
+    bool my_sd = false;
 #pragma unroll
     for (int j = 0; j < kMV; j++) {
       const uint32_t i = t + j * kMThreads;
@@ -563,12 +638,13 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         s.hi[i] = lp[j].x;
         s.lo[i] = lp[j].y;
         s.tr[i] = ltr[j];
+        my_sd = my_sd || (ltr[j] & 0xff) == kTypeSingleDeletion;
         s.ulen[i] = (uint8_t)(meta_ulen(lmt[j]) | (meta_vlen(lmt[j]) == 0 ? 0x80u : 0u));  // bit 7: empty value (compaction filter); bit 6 is set later: value removed by the filter
         s.idx[PH(i)] = (uint16_t)i;
       }
     }
+    tile_sd = __syncthreads_or(my_sd) != 0;  // (also the barrier behind the load phase)
   }
-  __syncthreads();
   // ---- pairwise merge rounds over the index list, in place through registers
   uint32_t nlists = k;
   int cur = 0;
@@ -636,81 +712,8 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   // happened to the versions above them -- a chain through all versions of the user key.  Tiles are cut at user-key boundaries
   // when an input holds one (merge_partition_grouped_kernel), so a key's versions are all here; the thread that owns a key's first
   // position walks the key with group_walk (group_rules.h, the reference's rules for one key) and leaves a verdict per version.
-  constexpr uint32_t kMaxGroup = 64;
-  bool my_sd = false;
-#pragma unroll
-  for (int x = 0; x < kMV; x++) {
-    const uint32_t o = t * kMV + x;
-    if (o < cnt && (s.tr[s.idx[PH(o)]] & 0xff) == kTypeSingleDeletion) my_sd = true;
-  }
-  const bool tile_sd = __syncthreads_or(my_sd) != 0;
   unsigned long long w_hidden = 0, w_obsolete = 0, w_userdrop = 0;
-  if (tile_sd) {
-    if (t == 0 && mp.write_conflict_snapshot) atomicOr(err, (uint32_t)kErrSdWriteConflict);
-    for (int x = 0; x < kMV; x++) {
-      const uint32_t o = t * kMV + x;
-      if (o < cnt) s.verd[o] = 0;
-    }
-    __syncthreads();
-    for (int x = 0; x < kMV; x++) {
-      const uint32_t o = t * kMV + x;
-      if (o >= cnt) break;
-      const uint32_t id0 = s.idx[PH(o)];
-      const Key k0 = skey(s, id0);
-      bool head = true;
-      if (o > 0) {
-        const Key p = skey(s, s.idx[PH(o - 1)]);
-        head = !(p.hi == k0.hi && p.lo == k0.lo && p.ulen == k0.ulen);
-      } else if (s.has_pred && s.pred.hi == k0.hi && s.pred.lo == k0.lo && s.pred.ulen == k0.ulen) {
-        atomicOr(err, (uint32_t)kErrInternal);  // the partition keeps keys inside one tile in this mode
-      }
-      if (!head) continue;
-      GroupVersion gv[kMaxGroup];
-      uint32_t n = 0;
-      bool has_sd = false;
-      for (uint32_t q = o; q < cnt; q++) {
-        const uint32_t id = s.idx[PH(q)];
-        if (q != o && !(s.hi[id] == k0.hi && s.lo[id] == k0.lo && (s.ulen[id] & 0x3fu) == k0.ulen)) break;
-        const uint64_t tr = s.tr[id];
-        has_sd = has_sd || (tr & 0xff) == kTypeSingleDeletion;
-        if (n < kMaxGroup) gv[n] = GroupVersion{tr >> 8, (uint8_t)(tr & 0xff)};
-        n++;
-      }
-      if (!has_sd) continue;
-      if (n > kMaxGroup) {
-        atomicOr(err, (uint32_t)kErrGroupTooLong);
-        continue;
-      }
-      GroupRules gr;
-      gr.snapshots = mp.snapshots;
-      gr.num_snapshots = mp.nsnapshots;
-      gr.bottommost = mp.bottommost;
-      gr.earliest_write_conflict_snapshot = kGrMaxSeq;
-      gr.key_not_exists_beyond_output_level = mp.bottommost;  // worker semantics (compaction.cc:555-556)
-      gr.filter_removes_newest = 0;
-      if (mp.filter != 0 && gv[0].type == kGrValue)
-        gr.filter_removes_newest = mp.filter == 1 ? (s.ulen[id0] & 0x80u) != 0 : filter_removes(mp, in, [&]() -> uint64_t {
-          uint32_t lo = 0, hi = k;
-          while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s.seg[mid] <= id0) lo = mid;
-            else hi = mid;
-          }
-          return s.sbeg[lo] + (id0 - s.seg[lo]);
-        }());
-      gr.first_key_of_the_job = 0;  // only matters with a write-conflict snapshot (rejected above)
-      GroupVerdict vd[kMaxGroup];
-      GroupCounters gc{0, 0, 0, 0};
-      if (group_walk(gv, n, gr, vd, &gc) != 0) atomicOr(err, (uint32_t)kErrSingleDelContract);
-      for (uint32_t i = 0; i < n; i++)
-        s.verd[o + i] = (uint8_t)(0x80u | (vd[i].keep ? 1u : 0u) | (vd[i].zero_seq ? 2u : 0u) | (vd[i].clear_value ? 4u : 0u) |
-                                  (vd[i].out_type != gv[i].type ? 8u : 0u));
-      w_hidden += gc.drop_hidden;
-      w_obsolete += gc.drop_obsolete;
-      w_userdrop += gc.drop_user;
-    }
-    __syncthreads();
-  }
+  if (tile_sd) sd_walk_tile(s, in, mp, cnt, k, err, &w_hidden, &w_obsolete, &w_userdrop);
   // ---- compaction-iterator rules per merged position
   const bool cond_possible = mp.bottommost && mp.nsnapshots > 0;
   auto col_of = [&](uint32_t pos) -> uint64_t {  // column position of the entry at load position pos
@@ -737,6 +740,11 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     Key c = skey(s, id);
     if (tile_sd && (s.verd[o] & 0x80u)) {  // a version of a key with a SingleDelete: the serial walk decided
       const uint32_t vd = s.verd[o], type0w = (uint32_t)(c.tr & 0xff);
+      if (vd & 16u) {  // stepped over inside another version's branch: in none of the input statistics
+        c_silent++;
+        keep_mask |= 1u << (16 + x);
+        continue;
+      }
       c_kbytes += c.ulen + 8;
       if (is_deletion_type(type0w)) c_indel++;
       if (vd & 1u) {
@@ -878,16 +886,39 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     }
   }
   __syncthreads();  // every read of idx[] / tr[] in merged order is done: compact in place
+  // A thread's survivors are consecutive output entries: the shared-prefix length of each with its predecessor (what the encoder
+  // needs for the entry size, BlockBuilder::AddWithLastKey) comes out of registers here; only the thread's first survivor has its
+  // predecessor in another thread and is done behind the barrier.
+  Key pk{0, 0, 0, 0}, fk{0, 0, 0, 0};
+  bool have_pk = false;
+  uint32_t first_rank = 0xffffffffu;
 #pragma unroll
   for (int x = 0; x < kMV; x++) {
     if ((keep_mask >> x) & 1) {
+      const uint32_t id = oid[x];
+      Key kx;
+      kx.hi = s.hi[id];
+      kx.lo = s.lo[id];
+      kx.tr = otr[x];
+      kx.ulen = s.ulen[id] & 0x3fu;
+      if (have_pk) s.esh[rank] = (uint8_t)shared_prefix(kx.hi, kx.lo, kx.ulen, kx.tr, pk.hi, pk.lo, pk.ulen, pk.tr);
+      else {
+        first_rank = rank;
+        fk = kx;
+      }
+      pk = kx;
+      have_pk = true;
       s.idx[PH(rank)] = oid[x];
-      s.tr[oid[x]] = otr[x];  // each load position is owned by exactly one merged position
-      if ((keep_mask >> (24 + x)) & 1) s.ulen[oid[x]] |= 0x40u;
+      s.tr[id] = otr[x];  // each load position is owned by exactly one merged position
+      if ((keep_mask >> (24 + x)) & 1) s.ulen[id] |= 0x40u;
       rank++;
     }
   }
   __syncthreads();
+  if (first_rank != 0xffffffffu && first_rank != 0) {  // (the tile's very first survivor: merge_sizes_fix_kernel)
+    const uint32_t pp = s.idx[PH(first_rank - 1)];
+    s.esh[first_rank] = (uint8_t)shared_prefix(fk.hi, fk.lo, fk.ulen, fk.tr, s.hi[pp], s.lo[pp], s.ulen[pp] & 0x3fu, s.tr[pp]);
+  }
   {
     // gather the value references of the survivors (random within k contiguous segments) for all of the thread's
     // output slots first, then write: again one round trip instead of kMV
@@ -956,8 +987,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         // encoded size against the previous OUTPUT entry (BlockBuilder::AddWithLastKey); the tile's first entry is left to
         // merge_sizes_fix_kernel: its predecessor is the last survivor of an earlier tile
         if (i > 0) {
-          const uint32_t pp = s.idx[PH(i - 1)];
-          const uint32_t sh = shared_prefix(chi, clo, cul, ctr, s.hi[pp], s.lo[pp], s.ulen[pp] & 0x3fu, s.tr[pp]);
+          const uint32_t sh = s.esh[i];
           const uint32_t s1 = entry_size(sh, cul + 8, vlen);
           ms.esz[dst] = s1;
           ms.eshared[dst] = (uint8_t)sh;
