@@ -120,6 +120,148 @@ def reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def plugin_arm(args, rank):
+    """bench.py --impl plugin: the CompactionExecutor plugin path of the reference DB (oracle/_ref/ref_compact_b200) on one job, with the
+    stock binary's local compaction beside it.  Wall time of the executor's Execute (CompactionJobStats.elapsed_micros)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_baseline as CB
+    w = WORKLOADS[args.workload]
+    r = CB.run_plugin_sample(w, sample_bytes=max(args.sample_mb, 512) << 20)
+    if r is None:
+        print(json.dumps({"impl": "plugin", "unavailable": "oracle/_ref/ref_compact_b200 is not built"}))
+        return
+    line = {"impl": "plugin", "metric": "compaction_input_kv_MB_per_s", "value": round(r["plugin"]["mbps"], 1), "unit": "MB/s", "n_gpus": 1,
+            "ms_per_step": round(r["plugin"]["seconds"] * 1e3, 2), "higher_is_better": True, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": w["desc"], "sample": r["sample"]},
+            "executor": r["plugin"]["executor"], "remote_compact_read_bytes": r["plugin"]["remote_compact_read_bytes"],
+            "local_cpu_compaction": {"value": round(r["local"]["mbps"], 1), "unit": "MB/s", "ms": round(r["local"]["seconds"] * 1e3, 2)},
+            "speedup_vs_local": round(r["plugin"]["mbps"] / r["local"]["mbps"], 2)}
+    print(json.dumps(line))
+
+
+def concurrent_jobs_arm(args, w, rank, world, local, numa_info):
+    """BASELINE.json configs[4]: J independent sub-compactions per GPU, all in flight at once (one host thread and one stream pair per
+    job), ranks hold disjoint key ranges.  A step = every job of the rank run once; device time between two events that bracket the
+    step (all streams drained on both sides), max over ranks."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    import toplingdb_b200 as T
+    from toplingdb_b200 import synth
+    J, base = w["jobs"], w["base"]
+    common = dict(device=local, bottommost_level=w["bottommost"], **BENCH_JOB)
+    sets, kv_bytes, in_bytes = [], 0, 0
+    for jx in range(J):
+        images, kv = synth.stage_bench_inputs(base, rank=rank * J + jx, scale=args.scale, device_index=local)
+        sets.append(images)
+        kv_bytes += kv
+        in_bytes += sum(int(t.numel()) for t in images)
+    jobs = []
+    for jx, images in enumerate(sets):
+        job = T.CompactionJob(output_mem="device", profile=1 if jx == 0 else 0, **common)
+        for i, img in enumerate(images):
+            job.add_input(img, level=0, file_number=100 + i)
+        jobs.append(job)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def run_all(js):
+        errs = []
+
+        def one(j):
+            try:
+                j.run()
+                _ = j.stats().num_output_records
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ths = [threading.Thread(target=one, args=(j,)) for j in js]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        if errs:
+            raise errs[0]
+
+    for _ in range(args.warmup):
+        run_all(jobs)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_all(jobs)
+    torch.cuda.synchronize()
+    ev1.record()
+    barrier()
+    wall_s = (time.perf_counter() - t0) / args.steps
+    step_s = ev0.elapsed_time(ev1) / 1e3 / args.steps
+    sampler.stop_flag = True
+    out_bytes = sum(j.output_meta(i).file_size for j in jobs for i in range(j.output_count()))
+    nout = sum(j.output_count() for j in jobs)
+    launches = sum(j.stats().kernel_launches for j in jobs)
+    kern = [{"name": n, "us": round(us, 1)} for n, us in jobs[0].kernel_times()]
+    if world > 1:
+        tt = torch.tensor([step_s, wall_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_s, wall_s = tt.tolist()
+    value = world * kv_bytes / step_s / 1e6
+    pk, pk_src = peaks()
+    # whole-step figure against the HBM roofline: every input byte read once + every output byte written once
+    ach = (in_bytes + out_bytes) / step_s / 1e9
+    roofline = {"bound": "hbm", "kernel": "whole step (8 jobs in flight)", "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None, "peak_source": pk_src}
+    e2e = None
+    if not args.no_e2e:
+        host_sets = [[t.cpu().pin_memory() for t in images] for images in sets]
+        for j in jobs:
+            j.close()
+        del sets
+        torch.cuda.empty_cache()
+        ejs = []
+        for images in host_sets:
+            ej = T.CompactionJob(output_mem="host", **common)
+            for i, img in enumerate(images):
+                ej.add_input(img, level=0, file_number=100 + i)
+            ejs.append(ej)
+        run_all(ejs)
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(2, min(args.steps, 4))
+        for _ in range(reps):
+            run_all(ejs)
+        barrier()
+        es = (time.perf_counter() - t0) / reps
+        if world > 1:
+            tt = torch.tensor([es], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            es = tt.item()
+        e2e = {"value": round(world * kv_bytes / es / 1e6, 1), "unit": "MB/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+               "ms_per_step": round(es * 1e3, 2), "steps": reps, "jobs_in_flight": J}
+        for ej in ejs:
+            ej.close()
+    if rank == 0:
+        line = {"metric": "compaction_input_kv_MB_per_s", "value": round(value, 1), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(step_s * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": w["desc"] + (f" (scale {args.scale})" if args.scale != 1.0 else ""), "jobs_per_gpu": J, "k": w["k"],
+                           "input_kv_bytes_per_gpu": kv_bytes, "input_sst_bytes_per_gpu": in_bytes, "output_files_per_gpu": nout,
+                           "output_sst_bytes_per_gpu": out_bytes, "l2_policy": "inputs (2.2 GB per GPU) >> 126 MB L2",
+                           "parallelism": f"{world} GPUs x {J} independent sub-compactions", "numa": numa_info},
+                "wall_ms_per_step": round(wall_s * 1e3, 3), "e2e": e2e, "gpu_launches": int(launches) * args.steps, "roofline": roofline,
+                "kernels_of_job0_while_8_run": kern, "cpu_baseline": None, "clocks": sampler.summary()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -132,12 +274,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-depth", type=int, default=4, help="compaction jobs in flight in the end-to-end measurement")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         return reference_arm(args, rank, world)
+    if args.impl == "plugin":
+        return plugin_arm(args, rank)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -148,6 +293,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the compaction path has no CPU implementation)")
     torch.cuda.set_device(local)
+    # host buffers next to the GPU: CPU affinity + memory policy of this rank go to the GPU's NUMA node before anything is pinned
+    from toplingdb_b200 import numa
+    numa_info = numa.bind_to_gpu_node(local) if not args.no_numa else {"gpu": local, "node": None, "cpus": None, "mempolicy": False}
     if world > 1:
         # the bench prints exactly one JSON line on stdout: keep NCCL's own banner / logs on stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -155,6 +303,8 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOADS[args.workload]
+    if w.get("jobs", 1) > 1:
+        return concurrent_jobs_arm(args, w, rank, world, local, numa_info)
     # ranks hold disjoint, ordered key ranges = independent sub-compactions; tests/test_gpu_fullsize.py stages the same job (rank 0) and
     # compares every output byte with the CPU oracle
     images, kv_bytes = synth.stage_bench_inputs(args.workload, rank=rank, scale=args.scale, device_index=local)
@@ -352,7 +502,7 @@ def main():
                 "config": {"workload": w["desc"] + (f" (scale {args.scale})" if args.scale != 1.0 else ""), "k": w["k"],
                            "entries_per_gpu": n_in, "input_kv_bytes_per_gpu": kv_bytes, "input_sst_bytes_per_gpu": in_bytes,
                            "output_files_per_gpu": nout, "output_sst_bytes_per_gpu": out_bytes, "l2_policy": "inputs (2.2 GB) >> 126 MB L2",
-                           "parallelism": f"{world} independent sub-compactions, 1 per GPU" if world > 1 else "1 GPU"},
+                           "parallelism": f"{world} independent sub-compactions, 1 per GPU" if world > 1 else "1 GPU", "numa": numa_info},
                 "wall_ms_per_step": round(wall_s * 1e3, 3), "e2e": e2e, "gpu_launches": int(launches) * args.steps, "roofline": roofline,
                 "kernels": kern, "cpu_baseline": cpu, "clocks": sampler.summary(),
                 "output_digest": {"sha256": digest, "oracle": want_digest, "matches_oracle": (want_digest == digest) if want_digest else None},

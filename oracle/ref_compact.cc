@@ -68,6 +68,7 @@ struct Opts {
   std::string filter = "none";  // remove_empty_value: the reference's RemoveEmptyValueCompactionFilter through a factory
   std::string barrier_dir;  // with barrier_n: wait until barrier_n processes have finished writing their inputs, so that
   int barrier_n = 0;        // concurrent timing runs compact at the same time
+  int warm = 0;             // run script + job once through a throw-away DB first (timing runs: steady state of a long-lived process)
   std::string table_factory;  // "b200" / "b200+nofallback": flushes and (local) compactions write their tables through B200TableFactory
   std::string executor;  // "b200": route the job through the B200 CompactionExecutor plugin (ref_compact_b200 build only)
 };
@@ -218,6 +219,7 @@ int main(int argc, char** argv) {
     else if (k == "mode") o.mode = v;
     else if (k == "setup_file_size") o.setup_file_size = strtoull(v.c_str(), nullptr, 0);
     else if (k == "ttl") o.ttl = atoi(v.c_str());
+    else if (k == "warm") o.warm = atoi(v.c_str());
     else if (k == "barrier_dir") o.barrier_dir = v;
     else if (k == "barrier_n") o.barrier_n = atoi(v.c_str());
     else {
@@ -324,6 +326,7 @@ int main(int argc, char** argv) {
   }
   if (!s.ok()) Die("open", s);
 
+  auto load_ops = [&](DB* db, std::vector<const Snapshot*>& snaps) -> int {
   FILE* f = fopen(argv[1], "rb");
   if (!f) {
     perror(argv[1]);
@@ -335,7 +338,6 @@ int main(int argc, char** argv) {
     return 2;
   }
   Reader rd{f};
-  std::vector<const Snapshot*> snaps;
   WriteOptions wo;
   wo.disableWAL = true;
   WriteBatch batch;
@@ -416,6 +418,39 @@ int main(int argc, char** argv) {
   }
   flush_batch();
   fclose(f);
+  return 0;
+  };
+
+  if (o.warm) {
+    // warm=1: the same script and job once through a throw-away DB first (same Options object, so the same executor / table factory):
+    // the device context, the kernels' module and the library's buffer cache are those of a process that has compacted before,
+    // which is what a DB sees from its second compaction on
+    const std::string wdir = work + "/warmdb";
+    DestroyDB(wdir, opt).PermitUncheckedError();
+    DB* wdb = nullptr;
+    Status ws = DB::Open(opt, wdir, &wdb);
+    if (!ws.ok()) Die("open (warm)", ws);
+    std::vector<const Snapshot*> wsnaps;
+    if (int rc = load_ops(wdb, wsnaps)) return rc;
+    std::vector<LiveFileMetaData> live;
+    wdb->GetLiveFilesMetaData(&live);
+    std::vector<std::string> names;
+    for (auto& m : live)
+      if (m.level == 0) names.push_back(m.name);
+    if (!names.empty()) {
+      CompactionOptions wco;
+      wco.compression = kNoCompression;
+      wco.output_file_size_limit = o.target_file_size;
+      wco.max_subcompactions = o.max_subcompactions;
+      ws = wdb->CompactFiles(wco, names, o.output_level);
+      if (!ws.ok()) Die("warm compaction", ws);
+    }
+    for (auto* sn : wsnaps) wdb->ReleaseSnapshot(sn);
+    delete wdb;
+    DestroyDB(wdir, opt).PermitUncheckedError();
+  }
+  std::vector<const Snapshot*> snaps;
+  if (int rc = load_ops(db, snaps)) return rc;
 
   // The job: every L0 file -> output_level.  Input order = newest L0 file first, which is the
   // order VersionSet::MakeInputIterator hands the children to the merging iterator

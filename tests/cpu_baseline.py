@@ -151,6 +151,44 @@ def run_subcompactions(w, sample_bytes, threads):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def run_plugin_sample(w, sample_bytes):
+    """The executor-plugin path end to end: ONE job of the reference DB (oracle/_ref/ref_compact_b200, executor=b200) -- the DB picks the
+    inputs, RunRemote hands them to B200CompactionExecutor::Execute, which reads the files through the DB's FileSystem into pinned
+    buffers, runs the job on the GPU, writes + syncs the output files; the DB renames and installs them.  The clock is
+    CompactionJobStats.elapsed_micros (set by Execute: file reads, H2D, kernels, D2H, file writes, fsync).  The same job of the stock
+    binary (local CPU compaction) is timed beside it.  Returns None when the binaries are missing."""
+    b200_bin = os.path.join(ROOT, "oracle", "_ref", "ref_compact_b200")
+    if not (os.path.exists(REF_BIN) and os.path.exists(b200_bin)):
+        return None
+    entry = 24 + w["vlen"]
+    n_total = max(w["k"] * 1000, sample_bytes // entry)
+    d = tempfile.mkdtemp(prefix="b200c_plugin_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    out = {"sample": f"one job of the reference DB, {w['k']} L0 files x {n_total // w['k']} entries = {n_total * entry / 2**20:.0f} MiB raw KV "
+                     f"({w['desc']}), files on {'tmpfs' if d.startswith('/dev/shm') else 'disk'}; the process has run the same job once "
+                     f"before the timed one (warm=1)"}
+    try:
+        _ops_file(os.path.join(d, "ops.bin"), w, n_total, seed=2)
+        # warm=1: script + job once through a throw-away DB of the same process first -- a DB's second and later compactions
+        for name, binary, extra in (("plugin", b200_bin, ["executor=b200", "warm=1"]), ("local", REF_BIN, ["warm=1"])):
+            best = None
+            for rep in range(1):
+                wd = os.path.join(d, f"{name}{rep}")
+                subprocess.check_call([binary, os.path.join(d, "ops.bin"), wd, "output_level=1", "max_subcompactions=1",
+                                       "target_file_size=67108864", "copy=0"] + extra, stdout=subprocess.DEVNULL)
+                man = json.load(open(os.path.join(wd, "manifest.json")))
+                stt = man["stats"]
+                kv = stt["total_input_raw_key_bytes"] + stt["total_input_raw_value_bytes"]
+                secs = stt["elapsed_micros"] / 1e6
+                if best is None or secs < best["seconds"]:
+                    best = {"mbps": kv / secs / 1e6, "seconds": secs, "executor": man.get("executor", "local"),
+                            "remote_compact_read_bytes": man.get("remote_compact_read_bytes", 0), "kv_bytes": kv}
+                shutil.rmtree(wd, ignore_errors=True)
+            out[name] = best
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 if __name__ == "__main__":  # scaling probe: python tests/cpu_baseline.py 1 8 32 128
     import sys
     W = dict(k=8, run_bytes=256 << 20, vlen=32, overlap=0.0, del_frac=0.0, bottommost=False, desc="cfg2")

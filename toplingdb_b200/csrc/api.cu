@@ -3,10 +3,13 @@
 // output.  Everything per entry / per block is a kernel launch (decode.cu, merge.cu, encode.cu).  No CPU data path exists.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <map>
+#include <mutex>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -21,6 +24,8 @@ namespace {
 
 thread_local std::string g_err;
 size_t g_last_want = 0;  // size of the last device allocation attempted (diagnostics of an out-of-memory status)
+std::mutex g_host_allocs_mu;
+std::unordered_map<void*, std::pair<size_t, int>> g_host_allocs;  // b200c_host_alloc: size class and device of every live buffer
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -41,22 +46,123 @@ std::string mem_note() {
     }                                                                                                             \
   } while (0)
 
-struct DevBuf {  // grow-only device allocation, reused across runs of the same job
+// Buffers of finished jobs are kept for the next one.  A DB hands the executor a fresh job handle per compaction, and allocating a
+// job's working set anew costs more than the job itself: cudaHostAlloc pins page by page (~0.3 ms per MiB), cudaMalloc / cudaFree of
+// gigabytes synchronise the device.  One cache per kind (device / pinned host) and device, bounded (B200C_CACHE_DEVICE_MB, default
+// 49152; B200C_CACHE_HOST_MB, default 16384; 0 = off).  Requests are rounded to a few size classes; a cached buffer serves requests
+// between half its size and its size.  Nothing is zeroed: every kernel writes what it later reads (the same rule a job handle that
+// runs twice already relies on).  When an allocation fails the caches of the device are emptied and the call is retried once.
+constexpr int kCacheDevices = 16;
+inline size_t size_class(size_t n) {
+  size_t c = 4096;
+  while (c < n) c <<= 1;
+  if (c >= (size_t(1) << 20)) {  // above 1 MiB: eighths of the power of two
+    const size_t step = c >> 4;  // (c/2)/8
+    c = (c >> 1) + ((n - (c >> 1) + step - 1) / step) * step;
+  }
+  return c;
+}
+class BufCache {
+ public:
+  BufCache(bool host, const char* env, size_t default_mb) : host_(host) {
+    const char* e = getenv(env);
+    cap_ = (e ? strtoull(e, nullptr, 10) : default_mb) << 20;
+  }
+  void* take(int dev, size_t n, size_t* got) {
+    if (dev < 0 || dev >= kCacheDevices || cap_ == 0) return nullptr;
+    std::lock_guard<std::mutex> l(mu_);
+    auto it = free_[dev].lower_bound(n);
+    if (it == free_[dev].end() || it->first > 2 * n) return nullptr;
+    void* p = it->second;
+    *got = it->first;
+    held_[dev] -= it->first;
+    free_[dev].erase(it);
+    return p;
+  }
+  bool give(int dev, void* p, size_t n) {  // false: not kept, the caller frees
+    if (dev < 0 || dev >= kCacheDevices || cap_ == 0) return false;
+    std::lock_guard<std::mutex> l(mu_);
+    if (held_[dev] + n > cap_) return false;
+    free_[dev].emplace(n, p);
+    held_[dev] += n;
+    return true;
+  }
+  void flush(int dev) {
+    if (dev < 0 || dev >= kCacheDevices) return;
+    std::multimap<size_t, void*> drop;
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      drop.swap(free_[dev]);
+      held_[dev] = 0;
+    }
+    for (auto& kv : drop) {
+      if (host_) cudaFreeHost(kv.second);
+      else cudaFree(kv.second);
+    }
+  }
+
+ private:
+  bool host_;
+  size_t cap_ = 0;
+  std::mutex mu_;
+  std::multimap<size_t, void*> free_[kCacheDevices];
+  size_t held_[kCacheDevices] = {};
+};
+BufCache& dev_cache() {
+  static BufCache* c = new BufCache(false, "B200C_CACHE_DEVICE_MB", 49152);  // leaked on purpose: no CUDA calls at process exit
+  return *c;
+}
+BufCache& host_cache() {
+  static BufCache* c = new BufCache(true, "B200C_CACHE_HOST_MB", 16384);
+  return *c;
+}
+inline int current_device() {
+  int d = -1;
+  cudaGetDevice(&d);
+  return d;
+}
+cudaError_t cached_alloc(bool host, size_t n, void** out, size_t* cap, int* dev_out) {
+  const int dev = current_device();
+  const size_t want = size_class(n);
+  *dev_out = dev;
+  BufCache& c = host ? host_cache() : dev_cache();
+  if (void* p = c.take(dev, want, cap)) {
+    *out = p;
+    return cudaSuccess;
+  }
+  g_last_want = want;
+  // (pinned buffers are mapped: kernels read / write them directly -- same address under UVA, see read_small())
+  auto raw = [&]() { return host ? cudaHostAlloc(out, want, cudaHostAllocMapped | cudaHostAllocPortable) : cudaMalloc(out, want); };
+  cudaError_t e = raw();
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    dev_cache().flush(dev);
+    host_cache().flush(dev);
+    e = raw();
+  }
+  if (e == cudaSuccess) *cap = want;
+  return e;
+}
+void cached_free(bool host, void* p, size_t cap, int dev) {
+  if (!p) return;
+  if ((host ? host_cache() : dev_cache()).give(dev, p, cap)) return;
+  if (host) cudaFreeHost(p);
+  else cudaFree(p);
+}
+
+struct DevBuf {  // grow-only device allocation, reused across runs of the same job (and, through the cache, by later jobs)
   void* p = nullptr;
   size_t cap = 0;
+  int dev = -1;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) cudaFree(p);  // growing in the middle of a job: earlier launches may still use it, cudaFree waits for them
     p = nullptr;
     cap = 0;
-    size_t want = n + (n >> 4) + 256;
-    g_last_want = want;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
+    return cached_alloc(false, n + (n >> 4) + 256, &p, &cap, &dev);
   }
-  void release() {
-    if (p) cudaFree(p);
+  void release() {  // only when nothing of the job is in flight any more (b200c_job_destroy drains the streams first)
+    cached_free(false, p, cap, dev);
     p = nullptr;
     cap = 0;
   }
@@ -79,21 +185,22 @@ struct Input {
   InputTail tail;
 };
 constexpr uint64_t kTailFetch = 4096;  // bytes read from the end of an input: footer + metaindex + properties live there
-struct HostBuf {  // grow-only pinned host allocation (D2H target of the finished images)
+struct HostBuf {  // grow-only pinned host allocation (D2H target of the finished images, small staging areas)
   uint8_t* p = nullptr;
   size_t cap = 0;
+  int dev = -1;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFreeHost(p);
     p = nullptr;
     cap = 0;
-    // mapped: kernels read / write it directly (same address under UVA), see read_small()
-    cudaError_t e = cudaHostAlloc((void**)&p, n + (n >> 4) + 256, cudaHostAllocMapped | cudaHostAllocPortable);
-    if (e == cudaSuccess) cap = n + (n >> 4) + 256;
+    void* q = nullptr;
+    cudaError_t e = cached_alloc(true, n + (n >> 4) + 256, &q, &cap, &dev);
+    p = static_cast<uint8_t*>(q);
     return e;
   }
   void release() {
-    if (p) cudaFreeHost(p);
+    cached_free(true, p, cap, dev);
     p = nullptr;
     cap = 0;
   }
@@ -132,6 +239,7 @@ struct b200c_job {
   DevBuf esz, eshared, tstat, nxt, disk, rows, tstate, grows, gstate, gflag, gsync, idx_contrib, idx_contrib_off, blocks, files_rec, idx_esz, idx_eoff, idx_sep, out_buf, out_base_d;
   uint64_t n_total = 0, n_out = 0, nblk_in = 0, nblocks_out = 0;
   uint32_t nfiles_out = 0, nruns = 0;
+  DevBuf tprefix2;  // stat-tile prefixes of the sizes pass (B200C_MERGE_FOLD=0)
   DevBuf bloom_contrib, bloom_contrib_off;  // scratch of the filter blocks' checksums
   DevBuf kv_arena, kv_offs, kv_klens;  // b200c_job_encode_kv: the caller's records on the device
   DevBuf run_bounds, run_first_d;  // [begin[K] | end[K]] of the sorted runs in the decoded columns; first file of each run
@@ -257,8 +365,18 @@ int fetch_tail(b200c_job* j, Input& in, const uint8_t* prefetched = nullptr) {
   if (in.tail.props_off + in.tail.props_size + 5 > in.len) return fail(B200C_ERR_CORRUPTION, "properties handle out of range");
   rc = view(in.tail.props_off, in.tail.props_size + 5, &blk);
   if (rc) return rc;
+  // num_entries / num_data_blocks from this block size every device buffer: its checksum is verified like the metaindex block's
+  if (in.tail.checksum_type &&
+      host_block_checksum(in.tail.checksum_type, blk, in.tail.props_size, blk[in.tail.props_size]) !=
+          ((uint32_t)blk[in.tail.props_size + 1] | (uint32_t)blk[in.tail.props_size + 2] << 8 |
+           (uint32_t)blk[in.tail.props_size + 3] << 16 | (uint32_t)blk[in.tail.props_size + 4] << 24))
+    return fail(B200C_ERR_CORRUPTION, "properties block checksum mismatch");
   e = parse_properties(blk, in.tail.props_size, &in.tail);
   if (!e.empty()) return fail(B200C_ERR_CORRUPTION, e);
+  // a file written earlier under other table options (two-level / hash index) must be refused as such, not fed to the flat index
+  // decoder (it would fail late as a count mismatch = Corruption, which AllowFallbackToLocal() does not cover)
+  if (in.tail.index_type != 0)
+    return fail(B200C_ERR_NOT_SUPPORTED, "input index type " + std::to_string(in.tail.index_type) + " (only kBinarySearch runs on the device)");
   if (in.tail.has_range_del || in.tail.num_range_deletions)
     return fail(B200C_ERR_NOT_SUPPORTED, "input holds range tombstones (CompactionRangeDelAggregator is not on the device path)");
   if (in.tail.num_merge_operands) return fail(B200C_ERR_NOT_SUPPORTED, "input holds merge operands");
@@ -581,6 +699,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
         d.cksum = P.checksum;
         d.gblk_first = g;
         d.nblocks = (uint32_t)fr.n_blocks;
+        d.index_user_key = (!fr.index_has_seq && P.format_version > 2) ? 1u : 0u;
         g += d.nblocks;
         maxb = std::max(maxb, d.nblocks);
         ofd[f] = d;
@@ -608,7 +727,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       const FileDesc* vf = j->vfiles_d.as<FileDesc>();
       KeyColsMut re{j->dec[0].as<ulonglong2>(), j->dec[1].as<uint64_t>(), j->dec[2].as<uint64_t>(), j->dec[3].as<uint32_t>()};
       j->kt_begin("verify.reread");
-      launch_index_decode(vf, (int)nfiles, maxb, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), err, st);
+      launch_index_decode(vf, (int)nfiles, maxb, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), BoundKey{}, 0, BoundKey{}, 0, err, st);
       launch_block_decode_fused(vf, (int)nfiles, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), (uint32_t)nblocks, 1, n_out, re,
                                 j->blk_state.as<unsigned long long>(), reinterpret_cast<uint32_t*>(small + kSlotDecTicket),
                                 j->vrun_start.as<uint64_t>(), small + kSlotTotalIn, err, j->sms, st);
@@ -745,7 +864,7 @@ int run_job(b200c_job* j, int until) {
     fd.cksum = in.tail.checksum_type;
     fd.gblk_first = (uint32_t)nblk;
     fd.nblocks = (uint32_t)in.tail.num_data_blocks;
-    fd.pad = 0;
+    fd.index_user_key = in.tail.index_key_is_user_key ? 1u : 0u;
     nblk += in.tail.num_data_blocks;
     n_props += in.tail.num_entries;
     in_bytes += in.len;
@@ -785,7 +904,9 @@ int run_job(b200c_job* j, int until) {
   for (auto& f : fds) maxb = std::max(maxb, f.nblocks);
   if (nblk) {
     j->kt_begin("decode.index");
-    launch_index_decode(files_d, k, maxb, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), err, st);
+    // a sub-compaction's key range: data blocks that cannot hold a key of [start, end) are dropped here, before anything of them is read
+    launch_index_decode(files_d, k, maxb, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), j->range_lo, P.has_range_start, j->range_hi,
+                        P.has_range_end, err, st);
     j->kt_end();
     launches++;
   }
@@ -811,7 +932,8 @@ int run_job(b200c_job* j, int until) {
     CU(cudaGetLastError());
     int rc = map_dev_err((uint32_t)h[kSlotErr]);
     if (rc) return rc;
-    if (h[kSlotTotalIn] != N) return fail(B200C_ERR_CORRUPTION, "decoded entry count differs from rocksdb.num.entries");
+    if (h[kSlotTotalIn] != N && !(P.has_range_start || P.has_range_end))  // (a key range skips the blocks outside it)
+      return fail(B200C_ERR_CORRUPTION, "decoded entry count differs from rocksdb.num.entries");
     j->stage_done = 1;
     j->stats.kernel_launches = launches;
     return B200C_OK;
@@ -897,21 +1019,37 @@ int run_merge_encode(b200c_job* j, int until, KeyCols decc, RunBounds runs, uint
   W.tstat = j->tstat.as<TileStat>();
   W.min_s1 = reinterpret_cast<uint32_t*>(small + kSlotMinS1);
   W.totals = small + kSlotTotals;
+  bool unfolded = false;
   if (N) {
     j->kt_begin("merge.partition");
     launch_merge_partition(decc, runs, (uint32_t)k, N, mtiles, j->splits.as<uint64_t>(), err, st);
     j->kt_end();
-    // the merge kernel also writes what the encoder needs per entry (encoded size, shared-prefix length) and per tile (statistics)
-    const MergeSizes msz{W.esz, W.eshared, W.tstat, W.min_s1};
+    // the merge kernel also writes what the encoder needs per entry (encoded size, shared-prefix length) and per tile (statistics);
+    // B200C_MERGE_FOLD=0 keeps that in a pass of its own behind the merge (encode_sizes_kernel) -- measured, see profiles/README.md
+    static const bool fold = !(getenv("B200C_MERGE_FOLD") && atoi(getenv("B200C_MERGE_FOLD")) == 0);
+    const MergeSizes msz = fold ? MergeSizes{W.esz, W.eshared, W.tstat, W.min_s1} : MergeSizes{nullptr, nullptr, nullptr, nullptr};
     W.tprefix = j->tile_state.as<unsigned long long>();
     W.nstat = mtiles;
     j->kt_begin("merge.tiles");
     launch_merge_tiles(decc, runs, mp, N, mtiles, j->splits.as<uint64_t>(),
                        j->tile_state.as<unsigned long long>(), reinterpret_cast<uint32_t*>(small + kSlotTicket), mrg, counters, msz, err, st);
     j->kt_end();
-    j->kt_begin("merge.sizes_fix");
-    launch_merge_sizes_fix(KeyCols{mrg.pfx, mrg.tr, mrg.vref, mrg.meta, 0}, j->tile_state.as<unsigned long long>(), mtiles, msz, st);
-    j->kt_end();
+    if (fold) {
+      j->kt_begin("merge.sizes_fix");
+      launch_merge_sizes_fix(KeyCols{mrg.pfx, mrg.tr, mrg.vref, mrg.meta, 0}, j->tile_state.as<unsigned long long>(), mtiles, msz, st);
+      j->kt_end();
+    } else {
+      CU(j->tprefix2.reserve(8 * (N / kEncTile + 2)));
+      CU(j->tstat.reserve(sizeof(TileStat) * (std::max<uint64_t>(mtiles, N / kEncTile) + 2)));
+      W.tstat = j->tstat.as<TileStat>();
+      W.tprefix = j->tprefix2.as<unsigned long long>();
+      W.nstat = 0;  // set below from the survivor count
+      j->kt_begin("encode.sizes");
+      launch_encode_sizes(KeyCols{mrg.pfx, mrg.tr, mrg.vref, mrg.meta, 0}, reinterpret_cast<const unsigned long long*>(&counters->n_out), W,
+                          j->tprefix2.as<unsigned long long>(), N, st);
+      j->kt_end();
+      unfolded = true;
+    }
     launches += 3;
   }
   CU(cudaEventRecord(j->ev[2], st));
@@ -923,10 +1061,12 @@ int run_merge_encode(b200c_job* j, int until, KeyCols decc, RunBounds runs, uint
     rc = map_dev_err((uint32_t)h[kSlotErr]);
     if (rc) return rc;
   }
-  if (h[kSlotTotalIn] != n_decoded) return fail(B200C_ERR_CORRUPTION, "decoded entry count differs from rocksdb.num.entries");
+  if (clipped ? h[kSlotTotalIn] > n_decoded : h[kSlotTotalIn] != n_decoded)  // (a key range skips the data blocks outside it)
+    return fail(B200C_ERR_CORRUPTION, "decoded entry count differs from rocksdb.num.entries");
   MergeCounters mc;
   memcpy(&mc, h + kSlotCounters, sizeof mc);
   const uint64_t n_out = mc.n_out;
+  if (unfolded) W.nstat = (n_out + kEncTile - 1) / kEncTile;  // statistics per kEncTile output entries (encode_sizes_kernel)
   j->n_out = n_out;
   mcols.n = n_out;
   j->stats.num_output_records = n_out;
@@ -1179,11 +1319,24 @@ int b200c_host_alloc(int device, uint64_t bytes, void** out) {
   *out = nullptr;
   if (b200c_device_count() <= 0) return fail(B200C_ERR_NO_DEVICE, "no CUDA device");
   CU(cudaSetDevice(device));
-  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  size_t cap = 0;
+  int dev = -1;
+  CU(cached_alloc(true, bytes ? bytes : 1, out, &cap, &dev));
+  std::lock_guard<std::mutex> l(g_host_allocs_mu);
+  g_host_allocs[*out] = {cap, dev};
   return B200C_OK;
 }
 void b200c_host_free(void* p) {
-  if (p) cudaFreeHost(p);
+  if (!p) return;
+  std::pair<size_t, int> rec{0, -1};
+  {
+    std::lock_guard<std::mutex> l(g_host_allocs_mu);
+    auto it = g_host_allocs.find(p);
+    if (it == g_host_allocs.end()) return;  // not ours
+    rec = it->second;
+    g_host_allocs.erase(it);
+  }
+  cached_free(true, p, rec.first, rec.second);
 }
 
 int b200c_job_run(b200c_job* j) {
@@ -1227,7 +1380,11 @@ int b200c_job_get_stats(const b200c_job* j, b200c_stats* s) {
 void b200c_job_destroy(b200c_job* j) {
   if (!j) return;
   cudaSetDevice(j->p.device);
-  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->run_bounds, &j->run_first_d, &j->kv_arena, &j->kv_offs, &j->kv_klens, &j->bloom_contrib, &j->bloom_contrib_off, &j->small,
+  // nothing of the job may be in flight when its buffers go back to the cache
+  if (j->st) cudaStreamSynchronize(j->st);
+  if (j->st2) cudaStreamSynchronize(j->st2);
+  if (j->st_up) cudaStreamSynchronize(j->st_up);  // (an eager upload may also still be reading a caller's buffer)
+  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->run_bounds, &j->run_first_d, &j->kv_arena, &j->kv_offs, &j->kv_klens, &j->bloom_contrib, &j->bloom_contrib_off, &j->tprefix2, &j->small,
                    &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
                    &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->tstat, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->gsync, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};
@@ -1240,7 +1397,6 @@ void b200c_job_destroy(b200c_job* j) {
   j->clip_d.release();
   j->vfiles_d.release();
   j->vrun_start.release();
-  if (j->st_up) cudaStreamSynchronize(j->st_up);  // an eager upload may still be reading a caller's buffer
   for (auto& in : j->inputs) {
     in.staged.release();
     if (in.up_ev) cudaEventDestroy(in.up_ev);

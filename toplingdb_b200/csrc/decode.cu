@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "range_rules.h"
 
 namespace b200c {
 
@@ -85,8 +86,35 @@ __device__ void index_decode_sequential(const FileDesc& fd, uint32_t file_idx, c
   if (p != end || n != fd.nblocks) atomicOr(err, kErrCorruptBlock);
 }
 
+// separator key of the index entry at p (restart interval 1: shared == 0) as a range key; false when it is longer than 16 bytes
+// (or malformed: the handle parse reports that) -- the block is then kept
+__device__ __forceinline__ bool index_separator(const FileDesc& fd, const uint8_t* p, const uint8_t* rs, RangeKey* out) {
+  uint64_t shared, non_shared, vl;
+  int c;
+  if (!(c = get_varint(p, rs, &shared)) || shared != 0) return false;
+  p += c;
+  if (!(c = get_varint(p, rs, &non_shared))) return false;
+  p += c;
+  if (!fd.value_delta) {
+    if (!(c = get_varint(p, rs, &vl))) return false;
+    p += c;
+  }
+  uint64_t ulen = non_shared;
+  if (!fd.index_user_key) {
+    if (ulen < 8) return false;
+    ulen -= 8;
+  }
+  if (ulen > (uint64_t)kMaxUserKey || p + non_shared > rs) return false;
+  uint64_t hi = 0, lo = 0;
+  for (uint32_t t = 0; t < 8; t++) hi = (hi << 8) | (t < ulen ? p[t] : 0);
+  for (uint32_t t = 8; t < 16; t++) lo = (lo << 8) | (t < ulen ? p[t] : 0);
+  *out = RangeKey{hi, lo, (uint32_t)ulen};
+  return true;
+}
+
 __global__ void index_decode_kernel(const FileDesc* __restrict__ files, int nfiles, uint64_t* __restrict__ blk_off,
-                                    uint32_t* __restrict__ blk_size, uint32_t* __restrict__ err) {
+                                    uint32_t* __restrict__ blk_size, BoundKey start, uint32_t has_start, BoundKey end, uint32_t has_end,
+                                    uint32_t* __restrict__ err) {
   const int f = blockIdx.y;
   if (f >= nfiles) return;
   const FileDesc fd = files[f];
@@ -105,6 +133,7 @@ __global__ void index_decode_kernel(const FileDesc* __restrict__ files, int nfil
     return;
   }
   const uint8_t* rs = blk + fd.index_size - 4 - 4ull * nr;
+  const RangeKey rstart{start.hi, start.lo, start.ulen}, rend{end.hi, end.lo, end.ulen};
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nr; j += gridDim.x * blockDim.x) {
     uint32_t ro = ld_u32(rs + 4ull * j);
     const uint8_t* p = blk + ro;
@@ -126,6 +155,19 @@ __global__ void index_decode_kernel(const FileDesc* __restrict__ files, int nfil
       atomicOr(err, kErrCorruptBlock);
       off = 0;
       size = 4;
+    } else if (has_start || has_end) {
+      // sub-compaction key range: block j holds only user keys in (separator j - 1, separator j] (range_rules.h)
+      RangeKey sep, prev;
+      bool have_prev = false;
+      if (index_separator(fd, blk + ro, rs, &sep)) {
+        bool usable = true;
+        if (j > 0) {
+          const uint32_t pro = ld_u32(rs + 4ull * (j - 1));
+          have_prev = pro < fd.index_size && index_separator(fd, blk + pro, rs, &prev);
+          usable = have_prev;  // an unreadable predecessor: keep the block
+        }
+        if (usable && !block_may_touch_range(sep, have_prev, prev, has_start != 0, rstart, has_end != 0, rend)) size = 0;  // skipped
+      }
     }
     blk_off[fd.gblk_first + j] = off | ((uint64_t)f << kBlkFileShift);
     blk_size[fd.gblk_first + j] = (uint32_t)size;
@@ -725,6 +767,16 @@ block_decode_fused_kernel(const FileDesc* __restrict__ files, int nfiles, const 
     const int f = (int)(bo >> kBlkFileShift);
     const uint8_t* src = files[f].base + (bo & kBlkOffMask);
     const uint32_t size = blk_size[b], cksum = files[f].cksum;
+    if (size == 0) {  // outside the sub-compaction's key range (index_decode_kernel): an empty block, nothing is read
+      publish_block_count(blk_state, b, 0, lane);
+      // its position only matters where a run starts / the stream ends; every 32nd skipped block still resolves its prefix so that
+      // the look-back of the next real block does not have to walk a whole skipped stretch
+      if (files[f].gblk_first == b || b + 1 == nblk || (b & 31u) == 31u) {
+        const uint64_t base0 = block_lookback(blk_state, b, 0, lane);
+        if (lane == 0) record_run_starts(files, nfiles, f, b, nblk, base0, 0, run_start, total_out);
+      }
+      continue;
+    }
     const uintptr_t a0 = (uintptr_t)src & ~(uintptr_t)15;
     const uint32_t shift = (uint32_t)((uintptr_t)src - a0);
     const uint32_t nvec = (shift + size + 5 + 15) >> 4;
@@ -797,10 +849,10 @@ __global__ void meta_vlen_kernel(const uint32_t* __restrict__ meta, uint64_t n, 
 
 // ---------------------------------------------------------------------------------------------- host launchers
 void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blocks_per_file, uint64_t* blk_off,
-                         uint32_t* blk_size, uint32_t* err, cudaStream_t st) {
+                         uint32_t* blk_size, BoundKey start, uint32_t has_start, BoundKey end, uint32_t has_end, uint32_t* err, cudaStream_t st) {
   dim3 grid((max_blocks_per_file + 255) / 256 ? (max_blocks_per_file + 255) / 256 : 1, nfiles);
   if (grid.x > 1024) grid.x = 1024;
-  index_decode_kernel<<<grid, 256, 0, st>>>(files_dev, nfiles, blk_off, blk_size, err);
+  index_decode_kernel<<<grid, 256, 0, st>>>(files_dev, nfiles, blk_off, blk_size, start, has_start, end, has_end, err);
 }
 void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk,
                                uint32_t verify, uint64_t n_total, KeyColsMut out, unsigned long long* blk_state, uint32_t* ticket,

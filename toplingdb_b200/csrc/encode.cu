@@ -1804,35 +1804,51 @@ __device__ __forceinline__ uint32_t file_of_entry(const FileRec* __restrict__ fi
   }
   return lo;
 }
-// does entry e add a hash to the filter of its file?  (XXPH3FilterBitsBuilder::AddKey, filter_policy.cc:73-92: not if the previous
-// key ADDED TO THIS FILTER hashed the same; every entry of a file is offered to it, so that is the previous entry of the file)
-__device__ __forceinline__ bool entry_adds_hash(const KeyCols& m, uint64_t e, uint64_t file_first, uint64_t* h_out) {
-  const uint64_t h = entry_key_hash(m, e);
-  *h_out = h;
-  return e == file_first || entry_key_hash(m, e - 1) != h;
-}
+// Which entries add a hash to the filter of their file (XXPH3FilterBitsBuilder::AddKey, filter_policy.cc:73-92): all but those whose
+// hash equals that of the key ADDED TO THIS FILTER before; every entry of a file is offered to it, so that is the file's previous entry.
 __global__ void __launch_bounds__(256)
 bloom_count_kernel(KeyCols m, uint64_t n, FileRec* __restrict__ files, const uint64_t* __restrict__ nfiles_dev) {
   const uint32_t nfiles = (uint32_t)*nfiles_dev;
   if (nfiles == 0 || nfiles > kMaxOutFiles) return;
   const unsigned lane = threadIdx.x & 31;
-  for (uint64_t e0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; e0 < n; e0 += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t e = e0 + lane;
-    uint32_t f = 0xffffffffu;
-    bool add = false;
-    if (e < n) {
-      f = file_of_entry(files, nfiles, e);
-      uint64_t h;
-      add = entry_adds_hash(m, e, files[f].first_entry, &h);
+  constexpr int kU = 4;  // a warp takes 4 x 32 consecutive entries per step, all key loads issued before the first hash
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t e0 = warp0 * (32 * kU); e0 < n; e0 += nwarps * (32 * kU)) {
+    ulonglong2 kp[kU];
+    uint32_t km[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const uint64_t e = e0 + 32 * u + lane;
+      if (e < n) {
+        kp[u] = m.pfx[e];
+        km[u] = m.meta[e];
+      }
     }
-    // a warp's 32 consecutive entries almost always belong to one file: one atomic per warp then
-    const uint32_t f0 = __shfl_sync(0xffffffffu, f, 0);
-    const bool uniform = __all_sync(0xffffffffu, f == f0 || f == 0xffffffffu);
-    if (uniform) {
-      const unsigned cnt = __popc(__ballot_sync(0xffffffffu, add));
-      if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&files[f0].filter_entries), (unsigned long long)cnt);
-    } else if (add) {
-      atomicAdd(reinterpret_cast<unsigned long long*>(&files[f].filter_entries), 1ull);
+    uint64_t carry = 0;  // hash of the entry in front of this group of 32 (lane 31 of the previous group)
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const uint64_t e = e0 + 32 * u + lane;
+      uint32_t f = 0xffffffffu;
+      bool add = false;
+      const uint64_t h = e < n ? xxph3_of_key(kp[u].x, kp[u].y, meta_ulen(km[u])) : 0;
+      uint64_t ph = __shfl_up_sync(0xffffffffu, h, 1);
+      if (lane == 0) ph = carry;
+      if (e < n) {
+        f = file_of_entry(files, nfiles, e);
+        const uint64_t ff = files[f].first_entry;
+        if (u == 0 && lane == 0 && e > ff) ph = entry_key_hash(m, e - 1);
+        add = e == ff || ph != h;
+      }
+      carry = __shfl_sync(0xffffffffu, h, 31);
+      // a warp's 32 consecutive entries almost always belong to one file: one atomic per warp then
+      const uint32_t f0 = __shfl_sync(0xffffffffu, f, 0);
+      const bool uniform = __all_sync(0xffffffffu, f == f0 || f == 0xffffffffu);
+      if (uniform) {
+        const unsigned cnt = __popc(__ballot_sync(0xffffffffu, add));
+        if (lane == 0 && cnt && f0 != 0xffffffffu) atomicAdd(reinterpret_cast<unsigned long long*>(&files[f0].filter_entries), (unsigned long long)cnt);
+      } else if (add) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&files[f].filter_entries), 1ull);
+      }
     }
   }
 }
@@ -1845,7 +1861,7 @@ __global__ void bloom_layout_kernel(FileRec* __restrict__ files, const uint64_t*
 }
 void launch_bloom_count(KeyCols m, uint64_t n, FileRec* files, const uint64_t* nfiles_dev, uint32_t millibits, cudaStream_t st) {
   if (n == 0) return;
-  const uint64_t blocks = (n + 255) / 256;
+  const uint64_t blocks = (n + 1023) / 1024;
   bloom_count_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(m, n, files, nfiles_dev);
   bloom_layout_kernel<<<(kMaxOutFiles + 255) / 256, 256, 0, st>>>(files, nfiles_dev, millibits);
 }
@@ -1875,22 +1891,35 @@ bloom_slices_kernel(KeyCols m, const FileRec* __restrict__ files, uint32_t nfile
   __syncthreads();
   const uint64_t e0 = fr.first_entry, e1 = e0 + fr.n_entries;
   const unsigned lane = threadIdx.x & 31;
-  for (uint64_t eb = e0; eb < e1; eb += kBloomThreads) {
-    const uint64_t e = eb + threadIdx.x;
-    uint64_t h = 0;
-    const bool valid = e < e1;
-    if (valid) h = entry_key_hash(m, e);
-    // XXPH3FilterBitsBuilder::AddKey (filter_policy.cc:73-92) drops a key whose hash equals that of the key added before it
-    uint64_t ph = __shfl_up_sync(0xffffffffu, h, 1);
-    if (lane == 0 && valid && e > e0) ph = entry_key_hash(m, e - 1);
-    if (!valid || (e > e0 && ph == h)) continue;
-    const uint32_t line = bloom_line_offset(h, bits_bytes);
-    if (line < s0 || line >= s1) continue;
-    uint32_t p = bloom_first_probe(h);
-    for (int k = 0; k < probes; k++, p = bloom_next_probe(p)) {
-      const uint32_t bit = bloom_probe_bit(p);
-      const uint32_t byte = shift + (line - s0) + (bit >> 3);  // offset inside bsm
-      atomicOr(&w32[byte >> 2], 1u << (8 * (byte & 3) + (bit & 7)));
+  constexpr int kU = 4;  // key loads in flight per thread: the scan is a chain of L2 round trips otherwise
+  for (uint64_t eb = e0; eb < e1; eb += (uint64_t)kU * kBloomThreads) {
+    ulonglong2 kp[kU];
+    uint32_t km[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const uint64_t e = eb + (uint64_t)u * kBloomThreads + threadIdx.x;
+      if (e < e1) {
+        kp[u] = m.pfx[e];
+        km[u] = m.meta[e];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const uint64_t e = eb + (uint64_t)u * kBloomThreads + threadIdx.x;
+      const bool valid = e < e1;
+      const uint64_t h = valid ? xxph3_of_key(kp[u].x, kp[u].y, meta_ulen(km[u])) : 0;
+      // XXPH3FilterBitsBuilder::AddKey (filter_policy.cc:73-92) drops a key whose hash equals that of the key added before it
+      uint64_t ph = __shfl_up_sync(0xffffffffu, h, 1);
+      if (lane == 0 && valid && e > e0) ph = entry_key_hash(m, e - 1);
+      if (!valid || (e > e0 && ph == h)) continue;
+      const uint32_t line = bloom_line_offset(h, bits_bytes);
+      if (line < s0 || line >= s1) continue;
+      uint32_t p = bloom_first_probe(h);
+      for (int k = 0; k < probes; k++, p = bloom_next_probe(p)) {
+        const uint32_t bit = bloom_probe_bit(p);
+        const uint32_t byte = shift + (line - s0) + (bit >> 3);  // offset inside bsm
+        atomicOr(&w32[byte >> 2], 1u << (8 * (byte & 3) + (bit & 7)));
+      }
     }
   }
   __syncthreads();

@@ -2,10 +2,10 @@
 //
 // merge.cu evaluates the kTypeValue / kTypeDeletion rules of CompactionIterator::NextFromInput (db/compaction/compaction_iterator.cc:
 // 475-1087) in parallel, entry by entry.  SingleDelete does not fit that shape: whether a SingleDelete and the Put below it cancel
-// depends on what happened to the versions above them (:662-887), a chain through the whole key.  Versions of one key are few, so the
-// plan for the device is: groups that contain a kTypeSingleDeletion are walked serially by one lane with this function; all other
-// groups keep the parallel path.  NOT wired into the kernels yet (the device still rejects the type); tests/test_group_rules_host.py
-// runs it on the CPU against the oracle's iterator on every scenario, SingleDelete or not, so that the wiring is the only thing left.
+// depends on what happened to the versions above them (:662-887), a chain through the whole key.  Versions of one key are few: keys
+// that hold a kTypeSingleDeletion are walked serially by one thread with this function (merge.cu sd_walk_tile; the partition keeps a
+// key's versions inside one tile then), all other keys take the parallel path.  tests/test_group_rules_host.py runs the same code on
+// the CPU against the oracle's iterator on every scenario, SingleDelete or not.
 //
 // State that the reference keeps across keys and that matters here is per key: has_outputted_key_ and last_key_seq_zeroed_ are reset at
 // every new user key (:578-580); clear_and_output_next_key_ never survives a key.  One wrinkle is global: has_outputted_key_ is set in

@@ -32,12 +32,19 @@ struct FileDesc {          // one input BlockBasedTable image resident in HBM
   uint32_t cksum;          // footer checksum type
   uint32_t gblk_first;     // first global data-block number of this file
   uint32_t nblocks;        // rocksdb.num.data.blocks
-  uint32_t pad;
+  uint32_t index_user_key; // rocksdb.index.key.is.user.key: index separators are user keys (no trailer)
+};
+
+struct BoundKey {              // a user key in column form (grandparent boundary, sub-compaction range bound)
+  uint64_t hi, lo;
+  uint32_t ulen, pad;
 };
 
 // ---- decode.cu
+// blk_size[b] == 0 marks a data block that a sub-compaction's key range [start, end) cannot touch (range_rules.h): the block decoder
+// publishes an empty block for it without reading the image
 void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blocks_per_file, uint64_t* blk_off,
-                         uint32_t* blk_size, uint32_t* err, cudaStream_t st);
+                         uint32_t* blk_size, BoundKey start, uint32_t has_start, BoundKey end, uint32_t has_end, uint32_t* err, cudaStream_t st);
 void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk,
                                uint32_t verify, uint64_t n_total, KeyColsMut out, unsigned long long* blk_state, uint32_t* ticket,
                                uint64_t* run_start, uint64_t* total_out, uint32_t* err, int sms, cudaStream_t st);
@@ -102,10 +109,6 @@ struct MergeCounters {               // device-side CompactionIterationStats
 struct RunBounds {
   const uint64_t* begin;
   const uint64_t* end;
-};
-struct BoundKey {              // a user key in column form (grandparent boundary, sub-compaction range bound)
-  uint64_t hi, lo;
-  uint32_t ulen, pad;
 };
 // Sub-compaction key range (ClippingIterator, db/compaction/clipping_iterator.h:55-358): per run the entries with
 // start <= user key < end.  clip[r] / clip[nruns + r] = first / one-past-last entry of run r in range; totals[0] += entries in

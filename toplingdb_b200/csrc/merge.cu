@@ -322,7 +322,6 @@ struct TileSmem {
   uint16_t idx[kMT];               // merge order: idx[o] = load position of the o-th smallest key
   uint8_t ulen[kMT];
   uint8_t verd[kMT];               // per merged position: verdict of the serial SingleDelete walk (bit 7: walked)
-  uint8_t esh[kMT];                // per tile-local output rank: bytes the entry shares with the previous OUTPUT entry
   uint32_t seg[kMaxRuns + 1];      // segment starts in load order
   uint32_t lst[2][kMaxRuns + 2];   // list bounds per merge round (ping-pong)
   uint64_t sbeg[kMaxRuns];         // absolute index of each segment's first element
@@ -549,7 +548,10 @@ __device__ __noinline__ void sd_walk_tile(TileSmem& s, const KeyCols& in, const 
   __syncthreads();
 }
 
-template <int kMinCtas>
+// kSD: the variant for jobs whose inputs hold a kTypeSingleDeletion (the decoder notes that in the error word).  Both variants are
+// launched; the one that does not apply leaves at once.  Keeping the serial walk and its bookkeeping out of the common variant is
+// worth 0.4 ms on the cfg2 job (profiles/README.md).
+template <int kMinCtas, bool kSD>
 __global__ void __launch_bounds__(kMThreads, kMinCtas)
 merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total, uint64_t ntiles,
                    const uint64_t* __restrict__ splits, unsigned long long* tile_state, uint32_t* ticket, KeyColsMut out,
@@ -558,6 +560,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   TileSmem& s = *reinterpret_cast<TileSmem*>(smem_raw);
   const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
   const uint32_t k = mp.nruns;
+  if (((*reinterpret_cast<volatile uint32_t*>(err) & (uint32_t)kFlagHasSingleDelete) != 0) != kSD) return;
   if (t == 0) s.tile_id = atomicAdd(ticket, 1u);
   if (t < 8) s.red[t] = 0;
   if (t < 5) s.stat[t] = t == 3 ? ~0ull : 0ull;
@@ -638,12 +641,13 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         s.hi[i] = lp[j].x;
         s.lo[i] = lp[j].y;
         s.tr[i] = ltr[j];
-        my_sd = my_sd || (ltr[j] & 0xff) == kTypeSingleDeletion;
+        if (kSD) my_sd = my_sd || (ltr[j] & 0xff) == kTypeSingleDeletion;
         s.ulen[i] = (uint8_t)(meta_ulen(lmt[j]) | (meta_vlen(lmt[j]) == 0 ? 0x80u : 0u));  // bit 7: empty value (compaction filter); bit 6 is set later: value removed by the filter
         s.idx[PH(i)] = (uint16_t)i;
       }
     }
-    tile_sd = __syncthreads_or(my_sd) != 0;  // (also the barrier behind the load phase)
+    if (kSD) tile_sd = __syncthreads_or(my_sd) != 0;  // (also the barrier behind the load phase)
+    else __syncthreads();
   }
   // ---- pairwise merge rounds over the index list, in place through registers
   uint32_t nlists = k;
@@ -713,7 +717,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   // when an input holds one (merge_partition_grouped_kernel), so a key's versions are all here; the thread that owns a key's first
   // position walks the key with group_walk (group_rules.h, the reference's rules for one key) and leaves a verdict per version.
   unsigned long long w_hidden = 0, w_obsolete = 0, w_userdrop = 0;
-  if (tile_sd) sd_walk_tile(s, in, mp, cnt, k, err, &w_hidden, &w_obsolete, &w_userdrop);
+  if (kSD && tile_sd) sd_walk_tile(s, in, mp, cnt, k, err, &w_hidden, &w_obsolete, &w_userdrop);
   // ---- compaction-iterator rules per merged position
   const bool cond_possible = mp.bottommost && mp.nsnapshots > 0;
   auto col_of = [&](uint32_t pos) -> uint64_t {  // column position of the entry at load position pos
@@ -738,7 +742,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     const uint32_t id = s.idx[PH(o)];
     oid[x] = (uint16_t)id;
     Key c = skey(s, id);
-    if (tile_sd && (s.verd[o] & 0x80u)) {  // a version of a key with a SingleDelete: the serial walk decided
+    if (kSD && tile_sd && (s.verd[o] & 0x80u)) {  // a version of a key with a SingleDelete: the serial walk decided
       const uint32_t vd = s.verd[o], type0w = (uint32_t)(c.tr & 0xff);
       if (vd & 16u) {  // stepped over inside another version's branch: in none of the input statistics
         c_silent++;
@@ -886,39 +890,16 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     }
   }
   __syncthreads();  // every read of idx[] / tr[] in merged order is done: compact in place
-  // A thread's survivors are consecutive output entries: the shared-prefix length of each with its predecessor (what the encoder
-  // needs for the entry size, BlockBuilder::AddWithLastKey) comes out of registers here; only the thread's first survivor has its
-  // predecessor in another thread and is done behind the barrier.
-  Key pk{0, 0, 0, 0}, fk{0, 0, 0, 0};
-  bool have_pk = false;
-  uint32_t first_rank = 0xffffffffu;
 #pragma unroll
   for (int x = 0; x < kMV; x++) {
     if ((keep_mask >> x) & 1) {
-      const uint32_t id = oid[x];
-      Key kx;
-      kx.hi = s.hi[id];
-      kx.lo = s.lo[id];
-      kx.tr = otr[x];
-      kx.ulen = s.ulen[id] & 0x3fu;
-      if (have_pk) s.esh[rank] = (uint8_t)shared_prefix(kx.hi, kx.lo, kx.ulen, kx.tr, pk.hi, pk.lo, pk.ulen, pk.tr);
-      else {
-        first_rank = rank;
-        fk = kx;
-      }
-      pk = kx;
-      have_pk = true;
       s.idx[PH(rank)] = oid[x];
-      s.tr[id] = otr[x];  // each load position is owned by exactly one merged position
-      if ((keep_mask >> (24 + x)) & 1) s.ulen[id] |= 0x40u;
+      s.tr[oid[x]] = otr[x];  // each load position is owned by exactly one merged position
+      if ((keep_mask >> (24 + x)) & 1) s.ulen[oid[x]] |= 0x40u;
       rank++;
     }
   }
   __syncthreads();
-  if (first_rank != 0xffffffffu && first_rank != 0) {  // (the tile's very first survivor: merge_sizes_fix_kernel)
-    const uint32_t pp = s.idx[PH(first_rank - 1)];
-    s.esh[first_rank] = (uint8_t)shared_prefix(fk.hi, fk.lo, fk.ulen, fk.tr, s.hi[pp], s.lo[pp], s.ulen[pp] & 0x3fu, s.tr[pp]);
-  }
   {
     // gather the value references of the survivors (random within k contiguous segments) for all of the thread's
     // output slots first, then write: again one round trip instead of kMV
@@ -969,6 +950,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     }
     __syncthreads();
     const uint64_t base_out = s.base_out;
+    const bool fold = ms.esz != nullptr;  // the merge also writes the encoder's per-entry sizes and per-tile statistics
     // per-thread partial statistics of the output entries (TileStat) and entry-size extremes
     uint32_t st_kb = 0, st_nd = 0, mn = 0xffffffffu, mx = 0;
     unsigned long long st_vb = 0, st_smin = ~0ull, st_smax = 0;
@@ -986,8 +968,9 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         out.meta[dst] = gm[j];
         // encoded size against the previous OUTPUT entry (BlockBuilder::AddWithLastKey); the tile's first entry is left to
         // merge_sizes_fix_kernel: its predecessor is the last survivor of an earlier tile
-        if (i > 0) {
-          const uint32_t sh = s.esh[i];
+        if (fold && i > 0) {
+          const uint32_t pp = s.idx[PH(i - 1)];
+          const uint32_t sh = shared_prefix(chi, clo, cul, ctr, s.hi[pp], s.lo[pp], s.ulen[pp] & 0x3fu, s.tr[pp]);
           const uint32_t s1 = entry_size(sh, cul + 8, vlen);
           ms.esz[dst] = s1;
           ms.eshared[dst] = (uint8_t)sh;
@@ -1002,7 +985,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         st_smax = sq > st_smax ? sq : st_smax;
       }
     }
-    {
+    if (fold) {
       const unsigned kb = __reduce_add_sync(0xffffffffu, st_kb), nd = __reduce_add_sync(0xffffffffu, st_nd);
       mn = __reduce_min_sync(0xffffffffu, mn);
       mx = __reduce_max_sync(0xffffffffu, mx);
@@ -1047,7 +1030,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   }
   __syncthreads();
   if (t < 8 && s.red[t]) atomicAdd(((unsigned long long*)counters) + t, s.red[t]);
-  if (t == 0) {
+  if (t == 0 && ms.esz != nullptr) {
     ms.tstat[tile] = TileStat{s.stat[0], s.stat[1], s.stat[2], s.stat[3], s.stat[4]};
     if (s.smin != 0xffffffffu) {
       atomicMin(ms.min_s1, s.smin);
@@ -1175,12 +1158,15 @@ void launch_merge_tiles(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_t
   static PerDeviceFlag attr;
   const uint64_t dev_bit = attr.bit_of_current_device();
   if (!attr.is_set(dev_bit)) {
-    cudaFuncSetAttribute(merge_tiles_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    cudaFuncSetAttribute(merge_tiles_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    cudaFuncSetAttribute(merge_tiles_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
     attr.set(dev_bit);
   }
   // three CTAs per SM at 80 registers (measured: four at 64 registers with spills are slower, profiles/README.md)
-  merge_tiles_kernel<3><<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state, ticket, out,
-                                                                               counters, ms, err, 148u * 3u);
+  merge_tiles_kernel<3, false><<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state, ticket,
+                                                                                      out, counters, ms, err, 148u * 3u);
+  merge_tiles_kernel<3, true><<<(unsigned)ntiles, kMThreads, sizeof(TileSmem), st>>>(in, runs, mp, n_total, ntiles, splits, tile_state, ticket,
+                                                                                     out, counters, ms, err, 148u * 3u);
 }
 void launch_merge_sizes_fix(KeyCols merged, const unsigned long long* tile_state, uint64_t ntiles, MergeSizes ms, cudaStream_t st) {
   if (ntiles) merge_sizes_fix_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, st>>>(merged, tile_state, ntiles, ms);

@@ -1,7 +1,7 @@
 // toplingdb_b200/csrc/range_rules.h — which data blocks of an input file a sub-compaction's key range [start, end) can touch (host +
-// device).  NOT wired into the kernels yet: today a job with a key range decodes every block of its inputs and clips the decoded runs
-// (merge.cu clip_runs_kernel); with this predicate the index decoder can drop the blocks outside the range before anything is read
-// (the reference gets the same effect from ClippingIterator's Seek, db/compaction/clipping_iterator.h:69-93).
+// device).  index_decode_kernel (decode.cu) marks the blocks outside the range as empty before anything of them is read; what is decoded
+// is still clipped exactly (merge.cu clip_runs_kernel).  The reference gets the same effect from ClippingIterator's Seek
+// (db/compaction/clipping_iterator.h:69-93).
 //
 // Index entry i of a BlockBasedTable holds a separator s_i with  last_key(block i) <= s_i < first_key(block i + 1)  in internal-key
 // order (ShortenedIndexBuilder, table/block_based/index_builder.h:165-233); whether the 8-byte trailer is kept does not matter for a

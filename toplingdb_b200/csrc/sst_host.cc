@@ -260,6 +260,9 @@ std::string parse_properties(const uint8_t* blk, uint64_t size, InputTail* t) {
     else if (k == "rocksdb.num.range-deletions") num(&t->num_range_deletions);
     else if (k == "rocksdb.merge.operands") num(&t->num_merge_operands);
     else if (k == "rocksdb.data.size") num(&t->data_size);
+    else if (k == "rocksdb.index.key.is.user.key") num(&t->index_key_is_user_key);
+    else if (k == "rocksdb.block.based.table.index.type" && vl >= 4)
+      t->index_type = (uint32_t)v[0] | (uint32_t)v[1] << 8 | (uint32_t)v[2] << 16 | (uint32_t)v[3] << 24;
     else if (k == "rocksdb.compression") t->compression_name.assign((const char*)v, vl);
     else if (k == "rocksdb.comparator") t->comparator_name.assign((const char*)v, vl);
   });

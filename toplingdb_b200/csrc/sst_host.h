@@ -20,6 +20,8 @@ struct InputTail {            // what the decoder needs to know about one input 
   bool has_range_del = false, has_filter = false, has_dict = false;
   uint64_t num_entries = 0, num_data_blocks = 0, raw_key_size = 0, raw_value_size = 0, num_range_deletions = 0,
            num_merge_operands = 0, data_size = 0;
+  uint64_t index_key_is_user_key = 0;  // rocksdb.index.key.is.user.key: index separators carry no 8-byte trailer
+  uint32_t index_type = 0;             // rocksdb.block.based.table.index.type (BlockBasedTableOptions::IndexType); 0 = kBinarySearch
   std::string compression_name, comparator_name;
 };
 

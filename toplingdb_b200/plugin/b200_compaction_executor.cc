@@ -451,6 +451,12 @@ class B200CompactionExecutor : public CompactionExecutor {
 
 B200CompactionExecutorFactory::B200CompactionExecutorFactory(const B200CompactOptions& o) : opt_(o) {
   have_device_ = b200c_device_count() > opt_.device;
+  if (have_device_) {
+    // create the device context now (hundreds of milliseconds) instead of inside the first compaction job; the buffer goes to the
+    // library's cache of pinned memory
+    void* p = nullptr;
+    if (b200c_host_alloc(opt_.device, 1 << 20, &p) == B200C_OK) b200c_host_free(p);
+  }
 }
 B200CompactionExecutorFactory::~B200CompactionExecutorFactory() = default;
 
