@@ -241,6 +241,7 @@ struct b200c_job {
   uint32_t nfiles_out = 0, nruns = 0;
   DevBuf tprefix2;  // stat-tile prefixes of the sizes pass (B200C_MERGE_FOLD=0)
   DevBuf bloom_contrib, bloom_contrib_off;  // scratch of the filter blocks' checksums
+  DevBuf bloom_hashes;                      // key hashes of the output entries (filter policy jobs)
   DevBuf kv_arena, kv_offs, kv_klens;  // b200c_job_encode_kv: the caller's records on the device
   DevBuf run_bounds, run_first_d;  // [begin[K] | end[K]] of the sorted runs in the decoded columns; first file of each run
   std::vector<uint64_t> run_start_h;
@@ -279,7 +280,7 @@ struct b200c_job {
 namespace {
 
 // layout of the `small` buffer (u64 slots)
-enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotDecTicket = 6, kSlotGpCuts = 7, kSlotCounters = 8 /* 8 */, kSlotClip = 16 /* 2: entries, value bytes in range */, kSmallSlots = 32 };
+enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotDecTicket = 6, kSlotGpCuts = 7, kSlotCounters = 8 /* 8 */, kSlotClip = 16 /* 2: entries, value bytes in range */, kSlotStitchDone = 18, kSmallSlots = 32 };
 
 int map_dev_err(uint32_t e) {
   e &= ~(uint32_t)kFlagHasSingleDelete;  // a note of the decoder, not an error
@@ -505,16 +506,22 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     W.gdone = j->gsync.as<uint32_t>();
     W.gready = W.gdone + egroups;
     // The serial stitch walk runs on the side stream WHILE the tables kernel fills the tile / group rows: each group raises a flag
-    // when its rows are complete and the walk waits on the flags.  Launch order tables -> stitch: tools that serialise kernels
-    // (ncu, compute-sanitizer) then run the producer first.
+    // when its rows are complete and the walk waits on the flags.  It is launched twice, in front of the tables kernel (so that it
+    // gets an SM to itself) and behind it (for tools that serialise kernels: ncu, compute-sanitizer) -- see encode_stitch_kernel.
+    uint32_t* sflag = reinterpret_cast<uint32_t*>(small + kSlotStitchDone);
     CU(cudaEventRecord(j->evx[0], st));
-    j->kt_begin("encode.tables");
-    launch_encode_tables(mcols, ep, W, etiles, hc, max_s1, err, st);
-    j->kt_end();
     CU(cudaStreamWaitEvent(j->st2, j->evx[0], 0));
     {
       const size_t slot = j->kt_begin("~encode.stitch", j->st2);
-      launch_encode_stitch(mcols, ep, W, etiles, hc, err, j->st2, &launches);
+      launch_encode_stitch(mcols, ep, W, etiles, hc, err, 1, sflag, j->st2, &launches);
+      j->kt_end(slot, j->st2);
+    }
+    j->kt_begin("encode.tables");
+    launch_encode_tables(mcols, ep, W, etiles, hc, max_s1, err, st);
+    j->kt_end();
+    {
+      const size_t slot = j->kt_begin("~encode.stitch_retry", j->st2);
+      launch_encode_stitch(mcols, ep, W, etiles, hc, err, 2, sflag, j->st2, &launches);
       j->kt_end(slot, j->st2);
     }
     CU(cudaEventRecord(j->evx[1], j->st2));
@@ -525,7 +532,8 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     launches += 1;
     if (P.bloom_millibits_per_key) {  // filter entries per file decide where each file's index block starts
       j->kt_begin("encode.bloom_count");
-      launch_bloom_count(mcols, n_out, W.files, small + kSlotTotals + 1, P.bloom_millibits_per_key, st);
+      CU(j->bloom_hashes.reserve(8 * (n_out + 1)));  // XXPH3 of every output key: computed once, read by the slices of the filter build
+      launch_bloom_count(mcols, n_out, W.files, small + kSlotTotals + 1, P.bloom_millibits_per_key, j->bloom_hashes.as<uint64_t>(), st);
       j->kt_end();
       launches += 2;
     }
@@ -537,6 +545,11 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
     }
     nblocks = h[kSlotTotals];
     nfiles = (uint32_t)h[kSlotTotals + 1];
+#ifdef B200C_STITCH_TRACE
+    fprintf(stderr, "stitch trace (cycles): walk %llu wait %llu refill_groups %llu (%llu) refill_tiles %llu (%llu) chase %llu (%llu); hc %u\n",
+            (unsigned long long)h[20], (unsigned long long)h[21], (unsigned long long)h[22], (unsigned long long)h[25], (unsigned long long)h[23],
+            (unsigned long long)h[26], (unsigned long long)h[24], (unsigned long long)h[27], hc);
+#endif
     if (nfiles == 0 || nfiles > kMaxOutFiles) return fail(B200C_ERR_CUDA, "internal: bad output file count");
     CU(j->blocks.reserve(sizeof(BlockRec) * (nblocks + 1)));
     CU(j->idx_esz.reserve(4 * (nblocks + 1)));
@@ -608,7 +621,7 @@ int encode_stage(b200c_job* j, KeyCols mcols, uint64_t n_out, uint32_t min_s1, u
       CU(j->bloom_contrib.reserve(64 * (boff[nfiles] + 1)));
       CU(j->bloom_contrib_off.reserve(8 * (nfiles + 1)));
       if (int rc = upload_small(j, j->bloom_contrib_off.p, boff.data(), 8 * (nfiles + 1))) return rc;
-      launch_bloom_build(mcols, n_out, W.files, nfiles, (uint32_t)std::min<uint64_t>(max_fb, 0xffffffffull), P.bloom_millibits_per_key, P.checksum,
+      launch_bloom_build(j->bloom_hashes.as<uint64_t>(), n_out, W.files, nfiles, (uint32_t)std::min<uint64_t>(max_fb, 0xffffffffull), P.bloom_millibits_per_key, P.checksum,
                          out_base_d, j->bloom_contrib.as<uint64_t>(), j->bloom_contrib_off.as<uint64_t>(), st);
       j->kt_end();
       launches += 3;
@@ -1384,7 +1397,7 @@ void b200c_job_destroy(b200c_job* j) {
   if (j->st) cudaStreamSynchronize(j->st);
   if (j->st2) cudaStreamSynchronize(j->st2);
   if (j->st_up) cudaStreamSynchronize(j->st_up);  // (an eager upload may also still be reading a caller's buffer)
-  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->run_bounds, &j->run_first_d, &j->kv_arena, &j->kv_offs, &j->kv_klens, &j->bloom_contrib, &j->bloom_contrib_off, &j->tprefix2, &j->small,
+  DevBuf* all[] = {&j->files_d, &j->blk_off, &j->blk_size, &j->blk_state, &j->scan_tmp, &j->run_start, &j->run_bounds, &j->run_first_d, &j->kv_arena, &j->kv_offs, &j->kv_klens, &j->bloom_contrib, &j->bloom_contrib_off, &j->bloom_hashes, &j->tprefix2, &j->small,
                    &j->dec[0], &j->dec[1], &j->dec[2], &j->dec[3], &j->mrg[0], &j->mrg[1], &j->mrg[2], &j->mrg[3], &j->splits,
                    &j->tile_state, &j->snaps_d, &j->esz, &j->eshared, &j->tstat, &j->nxt, &j->disk, &j->rows, &j->tstate, &j->grows, &j->gstate, &j->gflag, &j->gsync, &j->idx_contrib, &j->idx_contrib_off, &j->blocks,
                    &j->files_rec, &j->idx_esz, &j->idx_eoff, &j->idx_sep, &j->out_buf, &j->out_base_d};

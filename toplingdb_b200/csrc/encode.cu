@@ -21,8 +21,8 @@
 // HBM-bound; algorithmic bytes of encode_emit = 36 B of columns + value bytes read + block bytes written per entry.
 #include <cstdlib>
 
-#include "common.cuh"
 #include "bloom_rules.h"
+#include "common.cuh"
 #include "gp_rules.h"
 #include "kernels.h"
 #include "scan.cuh"
@@ -302,68 +302,111 @@ __device__ __forceinline__ BlockStart<PT> block_start(const Window<PT>& w, uint3
   s.qa = a >= cp.R ? w.Q[a - cp.R] : 0u;
   return s;
 }
+// Block sizes are computed in the window's own integer type: 32 bits in the narrow window (the launcher picks it only when
+// (largest entry + 64) x window length < 2^32, which bounds every sum formed here), 64 bits otherwise.
 template <typename PT>
-__device__ __forceinline__ uint64_t blk_payload(const Window<PT>& w, const BlockStart<PT>& s, uint32_t b, const CutParams& cp) {
+__device__ __forceinline__ PT blk_payload(const Window<PT>& w, const BlockStart<PT>& s, uint32_t b, const CutParams& cp) {
   const uint32_t nrm1 = div_r(b - 1 - s.a, cp);  // restarts - 1
   const uint32_t last = s.a + cp.R * nrm1;
   // Q is a per-residue prefix sum of 32-bit surcharges inside one window: the difference fits 32 bits
   const uint32_t q = w.Q[last] - s.qa;
-  return (uint64_t)(PT)(w.P[b] - s.pa) + q + 4u * (nrm1 + 1) + 4u;  // == BlockBuilder::CurrentSizeEstimate() (block_builder.cc:97,251)
+  return (PT)(w.P[b] - s.pa) + (PT)q + (PT)(4u * (nrm1 + 1) + 4u);  // == BlockBuilder::CurrentSizeEstimate() (block_builder.cc:97,251)
 }
 template <typename PT>
-__device__ __forceinline__ uint64_t blk_payload(const Window<PT>& w, uint32_t a, uint32_t b, const CutParams& cp) {
+__device__ __forceinline__ PT blk_payload(const Window<PT>& w, uint32_t a, uint32_t b, const CutParams& cp) {
   return blk_payload(w, block_start(w, a, cp), b, cp);
 }
 // first b > a at which FlushBlockBySizePolicy::Update (flush_block_policy.cc:37-69) fires for a block started at a.
-// returns wlen at the end of the stream, 0xffffffff if the block does not end inside the window.
-// hint: where the block of the previous start ended (0 = none); blocks of neighbouring starts end close to each other.
+// returns wlen at the end of the stream, 0xffffffff if the block does not end inside the window; *pay_out = payload bytes of [a, b).
+// hint: a position near the answer (where the block of the neighbouring start ended, or start + block bytes / mean entry size):
+// the search gallops away from it and bisects the bracket -- two probes when the hint is one off.  0 = none.
 template <typename PT>
-__device__ __forceinline__ uint32_t next_block(const Window<PT>& w, uint32_t a, const CutParams& cp, uint32_t hint) {
+__device__ __forceinline__ uint32_t next_block(const Window<PT>& w, uint32_t a, const CutParams& cp, uint32_t hint, PT* pay_out) {
   const uint32_t wlen = w.wlen;
   const BlockStart<PT> bs = block_start(w, a, cp);
   // below `thr` neither flush condition can fire: condition 2 needs CurrentSizeEstimate > LIM and
   // CurrentSizeEstimate + (size of the next entry, at most smax + 7) > BS
-  uint64_t thr = cp.BS - 1;
+  PT thr = (PT)(cp.BS - 1);
   if (cp.LIM) {
-    thr = cp.LIM;
+    thr = (PT)cp.LIM;
     const uint64_t guard = (uint64_t)w.smax + 7;
-    if (cp.BS > guard && cp.BS - guard - 1 > thr) thr = cp.BS - guard - 1;
+    if (cp.BS > guard && cp.BS - guard - 1 > thr) thr = (PT)(cp.BS - guard - 1);
   }
-  uint32_t lo = a + 1, hi = wlen + 1;  // searching the first b in [lo, hi) with CurrentSizeEstimate(a, b) > thr; hi = none
+  // the first b in [lo, hi) with CurrentSizeEstimate(a, b) > thr (the estimate grows with b); hi = wlen + 1: none seen yet
+  uint32_t lo = a + 1, hi = wlen + 1;
+  PT ec_hi = 0;  // the estimate at hi (when hi <= wlen)
   if (hint > a + 1 && hint <= wlen) {
-    // the estimate grows with b, and the block of the neighbouring start ended at `hint`: walk from there (a step or two) instead
-    // of bisecting the whole window
-    uint32_t b = hint;
-    if (blk_payload(w, bs, b, cp) > thr) {
-      while (b > a + 1 && blk_payload(w, bs, b - 1, cp) > thr) b--;
+    const PT ph = blk_payload(w, bs, hint, cp);
+    uint32_t step = 1;
+    if (ph > thr) {
+      hi = hint;
+      ec_hi = ph;
+      while (hi - lo >= step) {
+        const uint32_t mid = hi - step;
+        const PT pm = blk_payload(w, bs, mid, cp);
+        if (pm > thr) {
+          hi = mid;
+          ec_hi = pm;
+          step <<= 1;
+        } else {
+          lo = mid + 1;
+          break;
+        }
+      }
     } else {
-      do b++;
-      while (b <= wlen && blk_payload(w, bs, b, cp) <= thr);
+      lo = hint + 1;
+      while (lo + step - 1 <= wlen) {
+        const uint32_t mid = lo + step - 1;
+        const PT pm = blk_payload(w, bs, mid, cp);
+        if (pm > thr) {
+          hi = mid;
+          ec_hi = pm;
+          break;
+        }
+        lo = mid + 1;
+        step <<= 1;
+      }
     }
-    lo = hi = b;
   }
   while (lo < hi) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (blk_payload(w, bs, mid, cp) > thr) hi = mid;
-    else lo = mid + 1;
+    const uint32_t mid = (lo + hi) >> 1;
+    const PT pm = blk_payload(w, bs, mid, cp);
+    if (pm > thr) {
+      hi = mid;
+      ec_hi = pm;
+    } else {
+      lo = mid + 1;
+    }
   }
-  if (lo >= wlen) return w.at_end ? wlen : 0xffffffffu;
-  uint64_t ec = blk_payload(w, bs, lo, cp);  // CurrentSizeEstimate before adding entry b; updated incrementally
-  uint32_t m = lo - a;                      // entries already in the block
+  if (lo >= wlen) {
+    if (!w.at_end) return 0xffffffffu;
+    *pay_out = blk_payload(w, bs, wlen, cp);
+    return wlen;
+  }
+  PT ec = ec_hi;            // CurrentSizeEstimate before adding entry lo (lo == hi <= wlen was probed); updated incrementally
+  uint32_t m = lo - a;      // entries already in the block
   uint32_t mr = cp.rshift < 32 ? (m & (cp.R - 1)) : (m % cp.R);
   for (uint32_t b = lo; b < wlen; b++) {
-    if (ec >= cp.BS) return b;
-    const uint64_t s1 = (uint64_t)(PT)(w.P[b + 1] - w.P[b]);
+    if (ec >= cp.BS) {
+      *pay_out = ec;
+      return b;
+    }
+    const PT s1 = (PT)(w.P[b + 1] - w.P[b]);
     const bool at_restart = mr == 0;  // entry b would open a new restart interval
-    const uint64_t d = at_restart ? (uint64_t)w.Q[b] - (b >= cp.R ? (uint64_t)w.Q[b - cp.R] : 0) : 0;
+    const PT d = at_restart ? (PT)(w.Q[b] - (b >= cp.R ? w.Q[b - cp.R] : 0u)) : (PT)0;
     if (cp.LIM) {  // BlockAlmostFull: EstimateSizeAfterKV (block_builder.cc:97-126) = ec + |k|+|v|+4+varints (+4 at a restart)
-      const uint64_t dfull = at_restart ? d : (uint64_t)w.Q[b] - (b >= cp.R ? (uint64_t)w.Q[b - cp.R] : 0);
-      if (ec + s1 + dfull + 3 + (at_restart ? 4 : 0) > cp.BS) return b;
+      const PT dfull = at_restart ? d : (PT)(w.Q[b] - (b >= cp.R ? w.Q[b - cp.R] : 0u));
+      if (ec + s1 + dfull + 3 + (at_restart ? 4 : 0) > cp.BS) {
+        *pay_out = ec;
+        return b;
+      }
     }
     ec += s1 + (at_restart ? d + 4 : 0);
     mr = mr + 1 == cp.R ? 0 : mr + 1;
   }
-  return w.at_end ? wlen : 0xffffffffu;
+  if (!w.at_end) return 0xffffffffu;
+  *pay_out = ec;
+  return wlen;
 }
 
 constexpr int kEncGroup = kEncGroupTiles;  // tiles per group
@@ -431,19 +474,27 @@ encode_tables_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
     // start; it visits them in the rotated order (i + t) mod 16, which spreads the lanes of a warp over the
     // shared-memory banks (plain blocked order would put all 32 lanes on the same bank pair)
     constexpr int kPer = kTT / kEncThreads;
-    uint32_t prev_pos = 0xfffffff0u, prev_b = 0;
+    // hint of a thread's first start: start + (block bytes / mean entry size of the window); of every later one: where the
+    // neighbour's block ended (shifted by their distance when the rotation wraps from start 15 to start 0)
+    const PT total = s.w.P[s.w.wlen];
+    const uint32_t per_block = total ? (uint32_t)(((uint64_t)ep.block_size * s.w.wlen) / total) : 0;
+    uint32_t prev_pos = 0, prev_b = 0;
     for (int i = 0; i < kPer; i++) {
       const uint32_t j = threadIdx.x * kPer + ((i + threadIdx.x) & (kPer - 1));
       if (j >= tl) continue;
-      uint32_t b = next_block(s.w, j, cp, prev_pos + 1 == j ? prev_b : 0);
+      uint32_t hint = j + 1 + per_block;
+      if (prev_b) hint = prev_b + j - prev_pos;  // (unsigned wrap when j < prev_pos is intended)
+      if (hint > s.w.wlen) hint = s.w.wlen;
+      PT pay = 0;
+      uint32_t b = next_block(s.w, j, cp, hint, &pay);
       prev_pos = j;
       prev_b = b == 0xffffffffu ? 0 : b;
       uint16_t nx = 0xffff;
       uint32_t dk = 0;
       if (b != 0xffffffffu) {
         nx = (uint16_t)b;
-        uint64_t pay = blk_payload(s.w, j, b, cp) + 5;
-        dk = pay > 0xffffffffull ? 0xffffffffu : (uint32_t)pay;
+        const uint64_t pay5 = (uint64_t)pay + 5;
+        dk = pay5 > 0xffffffffull ? 0xffffffffu : (uint32_t)pay5;
       }
       s.nxt[j] = nx;
       s.disk[j] = dk;
@@ -706,11 +757,20 @@ __device__ __forceinline__ void coop_copy_cg(T* __restrict__ dst, const T* __res
 }
 // The stitch CTA shares the device with the tables kernel (it is launched on its own high-priority stream and needs a free slot on
 // one SM next to two tables CTAs), so its row caches are small: 2 x cache_bytes, sized by the launcher from hc.
+// Two launches per job.  The walk is one thread chasing dependent loads; next to the warps of a bulk kernel on the same SM it gets
+// an issue slot every few cycles only and runs several times slower than alone (measured: 0.8 ms next to two tables CTAs).  So
+//   attempt 1 is launched BEFORE the tables kernel with enough shared memory to keep an SM to itself, and consumes the groups as the
+//             tables kernel (on the other 147 SMs) completes them.  A tool that serialises kernels (ncu, compute-sanitizer) would
+//             never start the producer while this waits: if the first group does not appear within `timeout_ns` it leaves
+//             without having written anything;
+//   attempt 2 is launched behind both: it returns at once when attempt 1 finished the walk (`sflag`), else does it.
 __global__ void __launch_bounds__(kEncThreads)
 encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint64_t ntiles, uint32_t hc, uint32_t cache_bytes,
-                     uint32_t* __restrict__ err) {
+                     uint32_t* __restrict__ err, uint32_t attempt, uint32_t* __restrict__ sflag, uint32_t timeout_ns) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   StitchSmem& s = *reinterpret_cast<StitchSmem*>(smem_raw);
+  if (attempt == 2 && *reinterpret_cast<volatile uint32_t*>(sflag) != 0) return;
+  bool first_wait = attempt == 1;
   TileRow* gcache = reinterpret_cast<TileRow*>(smem_raw + ((sizeof(StitchSmem) + 15) & ~(size_t)15));
   TileRow* tcache = gcache + cache_bytes / sizeof(TileRow);
   const uint32_t cache_rows = cache_bytes / (uint32_t)sizeof(TileRow) / hc;  // groups / tiles per cache (>= 1 by the launcher)
@@ -729,8 +789,17 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
     s.gn = s.tn = 0;
   }
   __syncthreads();
+#ifdef B200C_STITCH_TRACE
+  long long tr_walk = 0, tr_wait = 0, tr_ref2 = 0, tr_ref3 = 0, tr_chase = 0, tr_n2 = 0, tr_n3 = 0, tr_nc = 0, tr_t = 0;
+#define TR_BEGIN() (tr_t = clock64())
+#define TR_END(acc) ((acc) += clock64() - tr_t)
+#else
+#define TR_BEGIN() ((void)0)
+#define TR_END(acc) ((void)0)
+#endif
   for (;;) {
     if (threadIdx.x == 0) {
+      TR_BEGIN();
       // everything the serial walk touches per step lives in registers; shared memory is read / written once per section
       WalkState st = s.st;
       const GpState gps = s.gp;  // only read here: boundaries are crossed (and the state changes) inside chase_tile
@@ -816,6 +885,7 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
       s.req = req;
       s.req_idx = req_idx;
       if (fin) s.done = 1;
+      TR_END(tr_walk);
     }
     __syncthreads();
     const uint32_t req = s.req;  // stable: thread 0 writes these again only after the barrier that ends the iteration
@@ -828,20 +898,41 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
       if (req == 2) {
         // the tables kernel is still running: wait for the first group needed, then take the consecutive groups that are ready too
         if (threadIdx.x == 0) {
+          TR_BEGIN();
           volatile uint32_t* rdy = wk.gready;
-          while (rdy[ridx] == 0) __nanosleep(256);
+          if (first_wait) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+            while (rdy[ridx] == 0) {
+              __nanosleep(256);
+              asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+              if (t1 - t0 > timeout_ns) {
+                s.done = 2;  // give up: the producer is not running
+                break;
+              }
+            }
+          } else {
+            while (rdy[ridx] == 0) __nanosleep(256);
+          }
+          TR_END(tr_wait);
           uint32_t have = 1;
           while (have < cnt && rdy[ridx + have] != 0) have++;
           s.refill = have;
           __threadfence();
         }
         __syncthreads();
+        if (s.done == 2) return;  // (nothing has been written yet: attempt 2 starts from scratch)
+        first_wait = false;
         cnt = s.refill;
       }
       // tile rows (req == 3) belong to a group that was ready when its row entered the group cache
       const uint4* src = reinterpret_cast<const uint4*>((req == 2 ? wk.grows : wk.rows) + ridx * hc);
       uint4* dst = reinterpret_cast<uint4*>(req == 2 ? gcache : tcache);
+      TR_BEGIN();
       coop_copy_cg<uint4, 8>(dst, src, cnt * hc);
+#ifdef B200C_STITCH_TRACE
+      if (req == 2) { TR_END(tr_ref2); tr_n2++; } else { TR_END(tr_ref3); tr_n3++; }
+#endif
       if (threadIdx.x == 0) {
         if (req == 2) {
           s.ga = ridx;
@@ -854,6 +945,7 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
     } else if (req == 1) {
       const uint64_t tstart = ridx * (uint64_t)kTT;
       const uint32_t tl = (uint32_t)(((tstart + kTT) < n ? (tstart + kTT) : n) - tstart);
+      TR_BEGIN();
       coop_copy_cg<uint16_t, 16>(s.nxt, wk.nxt + tstart, tl);
       coop_copy_cg<uint32_t, 16>(s.disk, wk.disk + tstart, tl);
       __syncthreads();
@@ -870,11 +962,21 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
         s.st = st;
       }
       __syncthreads();
+#ifdef B200C_STITCH_TRACE
+      TR_END(tr_chase);
+      tr_nc++;
+#endif
       done = s.done;
     }
     __syncthreads();
     if (done) break;
   }
+#ifdef B200C_STITCH_TRACE
+  if (threadIdx.x == 0) {
+    wk.totals[16] = tr_walk, wk.totals[17] = tr_wait, wk.totals[18] = tr_ref2, wk.totals[19] = tr_ref3, wk.totals[20] = tr_chase;
+    wk.totals[21] = tr_n2, wk.totals[22] = tr_n3, wk.totals[23] = tr_nc;
+  }
+#endif
   if (threadIdx.x == 0) {
     wk.totals[0] = s.st.blk;
     wk.totals[1] = s.st.f;
@@ -885,6 +987,8 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
       wk.gstate[gg] = ts;
       wk.gflag[gg] = 0;
     }
+    __threadfence();
+    if (attempt == 1) atomicExch(sflag, 1u);
   }
 }
 
@@ -1807,13 +1911,19 @@ __device__ __forceinline__ uint32_t file_of_entry(const FileRec* __restrict__ fi
 // Which entries add a hash to the filter of their file (XXPH3FilterBitsBuilder::AddKey, filter_policy.cc:73-92): all but those whose
 // hash equals that of the key ADDED TO THIS FILTER before; every entry of a file is offered to it, so that is the file's previous entry.
 __global__ void __launch_bounds__(256)
-bloom_count_kernel(KeyCols m, uint64_t n, FileRec* __restrict__ files, const uint64_t* __restrict__ nfiles_dev) {
+bloom_count_kernel(KeyCols m, uint64_t n, FileRec* __restrict__ files, const uint64_t* __restrict__ nfiles_dev, uint64_t* __restrict__ hashes) {
   const uint32_t nfiles = (uint32_t)*nfiles_dev;
   if (nfiles == 0 || nfiles > kMaxOutFiles) return;
   const unsigned lane = threadIdx.x & 31;
   constexpr int kU = 4;  // a warp takes 4 x 32 consecutive entries per step, all key loads issued before the first hash
+  // every warp owns one contiguous range of entries, so it stays inside one file almost always and adds its count to the file's
+  // record once (thousands of warps adding after every 32 entries serialise on the 32 counters: that was most of this kernel)
   const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (uint64_t e0 = warp0 * (32 * kU); e0 < n; e0 += nwarps * (32 * kU)) {
+  const uint64_t per_warp = ((n + nwarps - 1) / nwarps + 32 * kU - 1) / (32 * kU) * (32 * kU);
+  const uint64_t w_begin = warp0 * per_warp, w_end = w_begin + per_warp < n ? w_begin + per_warp : n;
+  unsigned long long acc = 0;
+  uint32_t acc_f = 0xffffffffu;
+  for (uint64_t e0 = w_begin; e0 < w_end; e0 += 32 * kU) {
     ulonglong2 kp[kU];
     uint32_t km[kU];
 #pragma unroll
@@ -1824,6 +1934,9 @@ bloom_count_kernel(KeyCols m, uint64_t n, FileRec* __restrict__ files, const uin
         km[u] = m.meta[e];
       }
     }
+    // the 128 entries of a step almost always belong to one file: one lookup for all of them then
+    const uint64_t e_last = e0 + 32 * kU - 1 < n ? e0 + 32 * kU - 1 : n - 1;
+    const uint32_t f_lo = file_of_entry(files, nfiles, e0), f_hi = file_of_entry(files, nfiles, e_last);
     uint64_t carry = 0;  // hash of the entry in front of this group of 32 (lane 31 of the previous group)
 #pragma unroll
     for (int u = 0; u < kU; u++) {
@@ -1831,10 +1944,11 @@ bloom_count_kernel(KeyCols m, uint64_t n, FileRec* __restrict__ files, const uin
       uint32_t f = 0xffffffffu;
       bool add = false;
       const uint64_t h = e < n ? xxph3_of_key(kp[u].x, kp[u].y, meta_ulen(km[u])) : 0;
+      if (e < n) hashes[e] = h;  // the filter build reads these instead of hashing the keys again
       uint64_t ph = __shfl_up_sync(0xffffffffu, h, 1);
       if (lane == 0) ph = carry;
       if (e < n) {
-        f = file_of_entry(files, nfiles, e);
+        f = f_lo == f_hi ? f_lo : file_of_entry(files, nfiles, e);
         const uint64_t ff = files[f].first_entry;
         if (u == 0 && lane == 0 && e > ff) ph = entry_key_hash(m, e - 1);
         add = e == ff || ph != h;
@@ -1845,12 +1959,20 @@ bloom_count_kernel(KeyCols m, uint64_t n, FileRec* __restrict__ files, const uin
       const bool uniform = __all_sync(0xffffffffu, f == f0 || f == 0xffffffffu);
       if (uniform) {
         const unsigned cnt = __popc(__ballot_sync(0xffffffffu, add));
-        if (lane == 0 && cnt && f0 != 0xffffffffu) atomicAdd(reinterpret_cast<unsigned long long*>(&files[f0].filter_entries), (unsigned long long)cnt);
+        if (f0 != 0xffffffffu) {
+          if (f0 != acc_f) {
+            if (lane == 0 && acc) atomicAdd(reinterpret_cast<unsigned long long*>(&files[acc_f].filter_entries), acc);
+            acc = 0;
+            acc_f = f0;
+          }
+          acc += cnt;
+        }
       } else if (add) {
         atomicAdd(reinterpret_cast<unsigned long long*>(&files[f].filter_entries), 1ull);
       }
     }
   }
+  if (lane == 0 && acc) atomicAdd(reinterpret_cast<unsigned long long*>(&files[acc_f].filter_entries), acc);
 }
 __global__ void bloom_layout_kernel(FileRec* __restrict__ files, const uint64_t* __restrict__ nfiles_dev, uint32_t millibits) {
   const uint32_t nfiles = (uint32_t)*nfiles_dev;
@@ -1859,21 +1981,24 @@ __global__ void bloom_layout_kernel(FileRec* __restrict__ files, const uint64_t*
     files[f].filter_bytes = cnt ? (uint64_t)bloom_bits_bytes(cnt, millibits) + kBloomMetadataLen + 5 : 0;
   }
 }
-void launch_bloom_count(KeyCols m, uint64_t n, FileRec* files, const uint64_t* nfiles_dev, uint32_t millibits, cudaStream_t st) {
+void launch_bloom_count(KeyCols m, uint64_t n, FileRec* files, const uint64_t* nfiles_dev, uint32_t millibits, uint64_t* hashes, cudaStream_t st) {
   if (n == 0) return;
   const uint64_t blocks = (n + 1023) / 1024;
-  bloom_count_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(m, n, files, nfiles_dev);
+  bloom_count_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(m, n, files, nfiles_dev, hashes);
   bloom_layout_kernel<<<(kMaxOutFiles + 255) / 256, 256, 0, st>>>(files, nfiles_dev, millibits);
 }
 // ---- filter bits.  FastLocalBloom puts all probes of a key into ONE 64-byte line of the filter (util/bloom_impl.h:200-214), and a
 // file's whole filter is small (1.25 bytes per key at 10 bits).  So the filter is built in SLICES of shared memory: a CTA owns
-// kBloomSliceBytes of one file's filter, scans all of the file's keys (hash = a few integer operations on the key columns), applies the
-// keys whose line falls into its slice with shared-memory atomics and writes the finished slice with one bulk store.  (Round 1 OR-ed
-// 230 M bits into L2 with global atomics: 5 ms on the cfg2 job; this is a scan of L2-resident key columns per slice.)
-constexpr uint32_t kBloomSliceBytes = 192 * 1024;
+// kBloomSliceBytes of one file's filter, scans the hashes of all of the file's keys (8 bytes per key, written by bloom_count_kernel and
+// served by the L2 to the slice CTAs of a file), applies the keys whose line falls into its slice with shared-memory atomics and
+// writes the finished slice with one bulk store.  (Round 1 OR-ed 230 M bits into L2 with global atomics: 5 ms on the cfg2 job; slice
+// CTAs that re-hashed the key columns: 3 ms; a cluster of eight CTAs setting bits in each other's shared memory: 4 ms.)
+constexpr uint32_t kBloomSliceBytes = 176 * 1024;
 constexpr int kBloomThreads = 1024;
+constexpr uint32_t kBloomStage = 64;  // hashes a warp can queue
 __global__ void __launch_bounds__(kBloomThreads, 1)
-bloom_slices_kernel(KeyCols m, const FileRec* __restrict__ files, uint32_t nfiles, int probes, uint8_t* const* __restrict__ out_base) {
+bloom_slices_kernel(const uint64_t* __restrict__ hashes, const FileRec* __restrict__ files, uint32_t nfiles, int probes,
+                    uint8_t* const* __restrict__ out_base) {
   extern __shared__ __align__(128) uint8_t bsm[];
   const uint32_t f = blockIdx.y;
   if (f >= nfiles) return;
@@ -1890,38 +2015,58 @@ bloom_slices_kernel(KeyCols m, const FileRec* __restrict__ files, uint32_t nfile
   for (uint32_t i = threadIdx.x; i < (kBloomSliceBytes + 16) / 4; i += kBloomThreads) w32[i] = 0;
   __syncthreads();
   const uint64_t e0 = fr.first_entry, e1 = e0 + fr.n_entries;
+  constexpr int kU = 8;  // hash loads in flight per thread: the scan is a chain of L2 round trips otherwise
+  // Only one key in `slices` belongs to this slice.  Setting its bits right away would issue every shared-memory atomic with a few
+  // active lanes; instead a warp queues the hashes that fall into the slice and sets the bits of 32 keys at a time.
+  uint64_t* const stage = reinterpret_cast<uint64_t*>(bsm + kBloomSliceBytes + 16) + (threadIdx.x >> 5) * kBloomStage;
   const unsigned lane = threadIdx.x & 31;
-  constexpr int kU = 4;  // key loads in flight per thread: the scan is a chain of L2 round trips otherwise
+  uint32_t queued = 0;  // (warp-uniform)
+  auto set_bits = [&](uint64_t h) {
+    const uint32_t line = bloom_line_offset(h, bits_bytes);
+    uint32_t p = bloom_first_probe(h);
+    for (int k = 0; k < probes; k++, p = bloom_next_probe(p)) {
+      const uint32_t bit = bloom_probe_bit(p);
+      const uint32_t byte = shift + (line - s0) + (bit >> 3);  // offset inside bsm
+      atomicOr(&w32[byte >> 2], 1u << (8 * (byte & 3) + (bit & 7)));
+    }
+  };
   for (uint64_t eb = e0; eb < e1; eb += (uint64_t)kU * kBloomThreads) {
-    ulonglong2 kp[kU];
-    uint32_t km[kU];
+    uint64_t hv[kU], pv[kU];
 #pragma unroll
     for (int u = 0; u < kU; u++) {
       const uint64_t e = eb + (uint64_t)u * kBloomThreads + threadIdx.x;
+      hv[u] = pv[u] = 0;
       if (e < e1) {
-        kp[u] = m.pfx[e];
-        km[u] = m.meta[e];
+        hv[u] = hashes[e];
+        if (e > e0) pv[u] = hashes[e - 1];  // (the neighbouring lane's line: an L1 hit)
       }
     }
 #pragma unroll
     for (int u = 0; u < kU; u++) {
       const uint64_t e = eb + (uint64_t)u * kBloomThreads + threadIdx.x;
-      const bool valid = e < e1;
-      const uint64_t h = valid ? xxph3_of_key(kp[u].x, kp[u].y, meta_ulen(km[u])) : 0;
+      const uint64_t h = hv[u];
       // XXPH3FilterBitsBuilder::AddKey (filter_policy.cc:73-92) drops a key whose hash equals that of the key added before it
-      uint64_t ph = __shfl_up_sync(0xffffffffu, h, 1);
-      if (lane == 0 && valid && e > e0) ph = entry_key_hash(m, e - 1);
-      if (!valid || (e > e0 && ph == h)) continue;
-      const uint32_t line = bloom_line_offset(h, bits_bytes);
-      if (line < s0 || line >= s1) continue;
-      uint32_t p = bloom_first_probe(h);
-      for (int k = 0; k < probes; k++, p = bloom_next_probe(p)) {
-        const uint32_t bit = bloom_probe_bit(p);
-        const uint32_t byte = shift + (line - s0) + (bit >> 3);  // offset inside bsm
-        atomicOr(&w32[byte >> 2], 1u << (8 * (byte & 3) + (bit & 7)));
+      bool mine = e < e1 && !(e > e0 && pv[u] == h);
+      if (mine) {
+        const uint32_t line = bloom_line_offset(h, bits_bytes);
+        mine = line >= s0 && line < s1;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, mine);
+      if (mine) stage[queued + __popc(mask & ((1u << lane) - 1u))] = h;
+      queued += __popc(mask);
+      __syncwarp();
+      if (queued >= 32) {
+        const uint64_t hq = stage[lane];
+        const uint64_t rest = lane + 32 < queued ? stage[lane + 32] : 0;
+        __syncwarp();
+        queued -= 32;
+        if (lane < queued) stage[lane] = rest;
+        set_bits(hq);
+        __syncwarp();
       }
     }
   }
+  if (lane < queued) set_bits(stage[lane]);
   __syncthreads();
   // store: head bytes up to the first 16-byte boundary, the aligned middle as one bulk copy (TMA), tail bytes
   const uint32_t total = s1 - s0;
@@ -1985,19 +2130,19 @@ __global__ void bloom_finish_kernel(const FileRec* __restrict__ files, uint32_t 
     tp[4] = (uint8_t)(ck >> 24);
   }
 }
-void launch_bloom_build(KeyCols m, uint64_t n, const FileRec* files, uint32_t nfiles, uint32_t max_filter_bytes, uint32_t millibits, uint32_t cksum,
-                        uint8_t* const* out_base, uint64_t* contrib, const uint64_t* contrib_off, cudaStream_t st) {
+void launch_bloom_build(const uint64_t* hashes, uint64_t n, const FileRec* files, uint32_t nfiles, uint32_t max_filter_bytes, uint32_t millibits,
+                        uint32_t cksum, uint8_t* const* out_base, uint64_t* contrib, const uint64_t* contrib_off, cudaStream_t st) {
   if (n == 0 || nfiles == 0) return;
   const int probes = bloom_num_probes((int)millibits);
   static PerDeviceFlag attr;
   const uint64_t dev_bit = attr.bit_of_current_device();
-  const int smem = (int)kBloomSliceBytes + 16;
+  const int smem = (int)kBloomSliceBytes + 16 + (kBloomThreads / 32) * kBloomStage * 8;
   if (!attr.is_set(dev_bit)) {
     cudaFuncSetAttribute(bloom_slices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr.set(dev_bit);
   }
   const unsigned slices = (max_filter_bytes + kBloomSliceBytes - 1) / kBloomSliceBytes;
-  bloom_slices_kernel<<<dim3(slices ? slices : 1, nfiles), kBloomThreads, smem, st>>>(m, files, nfiles, probes, out_base);
+  bloom_slices_kernel<<<dim3(slices ? slices : 1, nfiles), kBloomThreads, smem, st>>>(hashes, files, nfiles, probes, out_base);
   if (cksum == 4) bloom_contrib_kernel<<<dim3(32, nfiles), 256, 0, st>>>(files, nfiles, out_base, contrib, contrib_off);
   bloom_finish_kernel<<<(nfiles + 3) / 4, 128, 0, st>>>(files, nfiles, cksum, out_base, contrib, contrib_off);
 }
@@ -2084,20 +2229,30 @@ void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nti
   else
     encode_tables_kernel<uint64_t><<<(unsigned)ntiles, kEncThreads, sizeof(TablesSmem<uint64_t>), st>>>(m, ep, w, m.n, hc, w.nxt, w.disk, err);
 }
-void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st,
-                          uint64_t* launches) {
+void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, uint32_t attempt,
+                          uint32_t* sflag, cudaStream_t st, uint64_t* launches) {
   if (ntiles == 0) return;
+  static const bool solo = !(getenv("B200C_STITCH_SOLO") && atoi(getenv("B200C_STITCH_SOLO")) == 0);  // 0: only the launch behind the tables kernel
+  if (attempt == 1 && !solo) return;
   static PerDeviceFlag attr;
   const uint64_t dev_bit = attr.bit_of_current_device();
-  // row caches: at least one group / one tile, 16 KB when that is enough (the CTA then fits next to two tables CTAs)
-  uint32_t cache_bytes = 16 * 1024;
-  while (cache_bytes < hc * (uint32_t)sizeof(TileRow)) cache_bytes *= 2;
-  const size_t smem = ((sizeof(StitchSmem) + 15) & ~(size_t)15) + 2 * (size_t)cache_bytes;
+  constexpr size_t kSolo = 200 * 1024;  // attempt 1: no tables CTA (>= 60 KB of shared memory) fits next to it
   if (!attr.is_set(dev_bit)) {
-    cudaFuncSetAttribute(encode_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(encode_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolo);
     attr.set(dev_bit);
   }
-  encode_stitch_kernel<<<1, kEncThreads, smem, st>>>(m, ep, w, m.n, ntiles, hc, cache_bytes, err);
+  const size_t fixed = (sizeof(StitchSmem) + 15) & ~(size_t)15;
+  // row caches: at least one group / one tile.  Attempt 2 may have to run next to two tables CTAs: 16 KB each when that is enough;
+  // attempt 1 owns its SM: half of what is left each (a whole group of tile rows per refill)
+  uint32_t cache_bytes = 16 * 1024;
+  while (cache_bytes < hc * (uint32_t)sizeof(TileRow)) cache_bytes *= 2;
+  size_t smem = fixed + 2 * (size_t)cache_bytes;
+  if (attempt == 1) {
+    const uint32_t big = (uint32_t)(((kSolo - fixed) / 2) & ~(size_t)15);
+    if (big > cache_bytes) cache_bytes = big;
+    smem = kSolo;
+  }
+  encode_stitch_kernel<<<1, kEncThreads, smem, st>>>(m, ep, w, m.n, ntiles, hc, cache_bytes, err, attempt, sflag, 300000u);
   if (launches) *launches += 1;
 }
 void launch_encode_tilestate(KeyCols m, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st, uint64_t* launches) {

@@ -146,10 +146,10 @@ struct EncodeParams {
 using GpKey = BoundKey;       // grandparent boundary key in column form
 // ---- full Bloom filter block (bloom_rules.h).  count: per file the number of entries whose key hash differs from the predecessor's
 // (XXPH3FilterBitsBuilder::AddKey drops consecutive duplicates) and from it the block size; build: set the bits, metadata, trailer.
-void launch_bloom_count(KeyCols m, uint64_t n, FileRec* files, const uint64_t* nfiles_dev, uint32_t millibits, cudaStream_t st);
+void launch_bloom_count(KeyCols m, uint64_t n, FileRec* files, const uint64_t* nfiles_dev, uint32_t millibits, uint64_t* hashes, cudaStream_t st);
 // max_filter_bytes: largest filter_bytes of a file (grid sizing); contrib / contrib_off: scratch for the parallel part of the XXH3 of
 // every filter block (8 u64 per full 1024-byte block; per file its first slot)
-void launch_bloom_build(KeyCols m, uint64_t n, const FileRec* files, uint32_t nfiles, uint32_t max_filter_bytes, uint32_t millibits, uint32_t cksum,
+void launch_bloom_build(const uint64_t* hashes, uint64_t n, const FileRec* files, uint32_t nfiles, uint32_t max_filter_bytes, uint32_t millibits, uint32_t cksum,
                         uint8_t* const* out_base, uint64_t* contrib, const uint64_t* contrib_off, cudaStream_t st);
 void launch_gp_ranks(KeyCols m, const GpKey* smallest, const GpKey* largest, uint32_t n, uint64_t* lo, uint64_t* eq, uint64_t* hi,
                      cudaStream_t st);
@@ -226,8 +226,8 @@ void launch_encode_tables(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nti
                           cudaStream_t st);
 // stitch: launched on its own stream BEFORE / alongside launch_encode_tables (it consumes groups as their gready flag appears);
 // tilestate: after both have finished
-void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st,
-                          uint64_t* launches);
+void launch_encode_stitch(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, uint32_t attempt,
+                          uint32_t* sflag, cudaStream_t st, uint64_t* launches);
 void launch_encode_tilestate(KeyCols m, EncodeWork w, uint64_t ntiles, uint32_t hc, uint32_t* err, cudaStream_t st, uint64_t* launches);
 void launch_encode_blocklist(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t ntiles, uint64_t nblk_cap, uint32_t* err,
                              cudaStream_t st);

@@ -7,12 +7,16 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <set>
+#include <thread>
 #include <vector>
 
 #include "b200c.h"
@@ -297,25 +301,75 @@ class B200CompactionExecutor : public CompactionExecutor {
     const bool use_fsync = c_->immutable_options()->use_fsync;
     size_t nfiles_in = 0;
     for (const auto& lvl : *p.inputs) nfiles_in += lvl.files.size();
-    // one pinned buffer per input file; they never move (the library keeps the pointers until the job is destroyed) and the
-    // library starts the host -> device copy of a file as soon as it is added, while the next file is still being read
-    std::vector<std::unique_ptr<HostImage>> images;
-    images.reserve(nfiles_in);
-    uint64_t in_bytes = 0;
-    for (const auto& lvl : *p.inputs) {
+    // one pinned buffer per input file; they never move (the library keeps the pointers until the job is destroyed).  The files are
+    // read by up to io_threads threads; this thread hands each file to the library as soon as it and all files before it are in
+    // memory (the order of the calls is the order of the merge's children), and the library starts its host -> device copy at once
+    struct InFile {
+      int level;
+      const FileMetaData* fm;
+    };
+    std::vector<InFile> in_files;
+    in_files.reserve(nfiles_in);
+    for (const auto& lvl : *p.inputs)
       for (const FileMetaData* fm : lvl.files) {
         if (fm->num_range_deletions) s = Status::NotSupported("B200Compact: range tombstones in input");
-        if (!s.ok()) break;
-        const uint64_t fsize = fm->fd.GetFileSize();
-        images.emplace_back(new HostImage());
-        if (!images.back()->Alloc(opt_.device, fsize)) s = Status::MemoryLimit("B200Compact: input buffer");
-        if (s.ok()) s = ReadFileFS(fs, TableFileName(p.cf_paths, fm->fd.GetNumber(), fm->fd.GetPathId()), images.back()->p, fsize);
-        if (!s.ok()) break;
-        in_bytes += fsize;
-        s = FromB200(b200c_job_add_input(job, lvl.level, fm->fd.GetNumber(), images.back()->p, fsize, B200C_MEM_HOST));
-        if (!s.ok()) break;
+        in_files.push_back(InFile{lvl.level, fm});
       }
-      if (!s.ok()) break;
+    std::vector<std::unique_ptr<HostImage>> images(in_files.size());
+    uint64_t in_bytes = 0;
+    for (size_t i = 0; i < in_files.size() && s.ok(); i++) {
+      images[i].reset(new HostImage());
+      if (!images[i]->Alloc(opt_.device, in_files[i].fm->fd.GetFileSize())) s = Status::MemoryLimit("B200Compact: input buffer");
+    }
+    if (s.ok() && !in_files.empty()) {
+      const size_t nf = in_files.size();
+      std::vector<Status> rstat(nf);
+      std::vector<char> ready(nf, 0);
+      std::mutex mu;
+      std::condition_variable cv;
+      std::atomic<size_t> next{0};
+      std::atomic<bool> stop{false};
+      auto reader = [&]() {
+        for (size_t i; !stop.load(std::memory_order_relaxed) && (i = next.fetch_add(1)) < nf;) {
+          const FileMetaData* fm = in_files[i].fm;
+          Status rs = ReadFileFS(fs, TableFileName(p.cf_paths, fm->fd.GetNumber(), fm->fd.GetPathId()), images[i]->p, fm->fd.GetFileSize());
+          std::lock_guard<std::mutex> l(mu);
+          rstat[i] = rs;
+          ready[i] = 1;
+          cv.notify_all();
+        }
+      };
+      const size_t nthreads = std::min<size_t>((size_t)std::max(1, opt_.io_threads), nf);
+      std::vector<std::thread> pool;
+      for (size_t t = 1; t < nthreads; t++) pool.emplace_back(reader);
+      if (nthreads == 1) reader();
+      for (size_t i = 0; i < nf && s.ok(); i++) {
+        if (nthreads > 1) {
+          std::unique_lock<std::mutex> l(mu);
+          // with helpers running, this thread reads too whenever the file it waits for has not been claimed yet
+          while (!ready[i]) {
+            size_t mine = next.load();
+            if (mine < nf && next.compare_exchange_strong(mine, mine + 1)) {
+              l.unlock();
+              const FileMetaData* fm = in_files[mine].fm;
+              Status rs = ReadFileFS(fs, TableFileName(p.cf_paths, fm->fd.GetNumber(), fm->fd.GetPathId()), images[mine]->p, fm->fd.GetFileSize());
+              l.lock();
+              rstat[mine] = rs;
+              ready[mine] = 1;
+              cv.notify_all();
+            } else {
+              cv.wait(l, [&] { return ready[i] != 0; });
+            }
+          }
+        }
+        s = rstat[i];
+        if (!s.ok()) break;
+        const uint64_t fsize = in_files[i].fm->fd.GetFileSize();
+        in_bytes += fsize;
+        s = FromB200(b200c_job_add_input(job, in_files[i].level, in_files[i].fm->fd.GetNumber(), images[i]->p, fsize, B200C_MEM_HOST));
+      }
+      stop.store(true);
+      for (auto& th : pool) th.join();
     }
     auto shutting_down = [&]() { return p.shutting_down && p.shutting_down->load(std::memory_order_acquire); };
     if (s.ok() && shutting_down()) s = Status::ShutdownInProgress();
@@ -330,17 +384,35 @@ class B200CompactionExecutor : public CompactionExecutor {
       s = fs->CreateDirIfMissing(r->output_dir, IOOptions(), nullptr);
       r->output_files.resize(1);  // one sub-compaction: the device splits the job internally (merge-path tiles)
       const int n = b200c_job_output_count(job);
-      for (int i = 0; i < n && s.ok(); i++) {
+      struct OutFile {
         b200c_file_meta m;
         const void* data;
         uint64_t len;
-        s = FromB200(b200c_job_output_meta(job, i, &m));
-        if (s.ok()) s = FromB200(b200c_job_output_data(job, i, &data, &len));
-        if (!s.ok()) break;
-        const std::string fname = MakeTableFileName(r->output_dir, m.file_number);
-        written.push_back(fname);
-        s = WriteFileFS(fs, fname, static_cast<const char*>(data), len, use_fsync);
-        if (!s.ok()) break;
+        std::string fname;
+      };
+      std::vector<OutFile> outs((size_t)std::max(0, n));
+      for (int i = 0; i < n && s.ok(); i++) {
+        s = FromB200(b200c_job_output_meta(job, i, &outs[i].m));
+        if (s.ok()) s = FromB200(b200c_job_output_data(job, i, &outs[i].data, &outs[i].len));
+        if (s.ok()) outs[i].fname = MakeTableFileName(r->output_dir, outs[i].m.file_number);
+      }
+      if (s.ok() && n > 0) {  // write + sync the files, up to io_threads at a time
+        for (auto& o : outs) written.push_back(o.fname);
+        std::vector<Status> wstat((size_t)n);
+        std::atomic<int> next{0};
+        auto writer = [&]() {
+          for (int i; (i = next.fetch_add(1)) < n;)
+            wstat[i] = WriteFileFS(fs, outs[i].fname, static_cast<const char*>(outs[i].data), outs[i].len, use_fsync);
+        };
+        const int nthreads = std::min(std::max(1, opt_.io_threads), n);
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads; t++) pool.emplace_back(writer);
+        writer();
+        for (auto& th : pool) th.join();
+        for (int i = 0; i < n && s.ok(); i++) s = wstat[i];
+      }
+      for (int i = 0; i < n && s.ok(); i++) {
+        const b200c_file_meta& m = outs[i].m;
         CompactionResults::FileMinMeta fm;
         fm.file_number = m.file_number;
         fm.file_size = m.file_size;
@@ -534,6 +606,7 @@ static std::shared_ptr<CompactionExecutorFactory> JS_NewB200Compact(const json& 
   ROCKSDB_JSON_OPT_PROP_3(js, o.allow_fallback_to_local, "allow_fallback_to_local");
   ROCKSDB_JSON_OPT_PROP_3(js, o.verify_input_checksums, "verify_input_checksums");
   ROCKSDB_JSON_OPT_PROP_3(js, o.scratch_dir, "scratch_dir");
+  ROCKSDB_JSON_OPT_PROP_3(js, o.io_threads, "io_threads");
   return std::make_shared<B200CompactionExecutorFactory>(o);
 }
 ROCKSDB_FACTORY_REG("B200Compact", JS_NewB200Compact);

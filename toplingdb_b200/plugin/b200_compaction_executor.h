@@ -24,6 +24,7 @@ struct B200CompactOptions {
   bool allow_fallback_to_local = true;  // AllowFallbackToLocal(): NOT_SUPPORTED / device errors fall back to RunLocal()
   bool verify_input_checksums = true;   // ReadOptions::verify_checksums of the compaction read
   std::string scratch_dir;              // where output files are materialised before RenameFile(); default: <dbname>/b200c-tmp
+  int io_threads = 8;                   // input files are read and output files written + synced by up to this many threads per job
 };
 
 class B200CompactionExecutorFactory : public CompactionExecutorFactory {
