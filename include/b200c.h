@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200C_ABI_VERSION 7
+#define B200C_ABI_VERSION 8
 #if defined(__GNUC__)
 #define B200C_API __attribute__((visibility("default")))
 #else
@@ -198,6 +198,20 @@ B200C_API int b200c_job_output_data(b200c_job* j, int i, const void** data, uint
 B200C_API int b200c_job_output_read(b200c_job* j, int i, void* dst, uint64_t cap);
 B200C_API int b200c_job_get_stats(const b200c_job* j, b200c_stats* s);
 B200C_API void b200c_job_destroy(b200c_job* j);
+
+/* ---- one job over several key ranges: the reference's sub-compactions (CompactionJob::Prepare / GenSubcompactionBoundaries,
+ * db/compaction/compaction_job.cc:264-281,465-640; CompactionResults::output_files[sub], compaction_executor.h:120-158) ----
+ * b200c_job_plan_ranges: up to max_ranges - 1 boundary user keys (ascending; keys: 16 bytes per slot, key_lens: their lengths) that
+ * cut the job's inputs into ranges [.., k0) [k0, k1) ... [k_last, ..) of about equal input bytes, none smaller than min_range_bytes
+ * (the reference: at least one output file per range).  The boundaries come from ~128 anchors per input file read off its index
+ * block, as GenSubcompactionBoundaries reads them from TableReader::ApproximateKeyAnchors.  Host work only (O(index blocks)).
+ * b200c_job_create_sub: a job over the SAME inputs as `parent` -- their device copies are made once, by the parent -- restricted to
+ * the key range in `p` (range_start / range_end) on the parent's device, with its own streams and buffers: sub-jobs of one parent may
+ * run concurrently from different host threads.  The parent must outlive its sub-jobs; it does not have to run itself.  Create the
+ * sub-jobs from one thread, after the last b200c_job_add_input on the parent. */
+B200C_API int b200c_job_plan_ranges(b200c_job* j, uint32_t max_ranges, uint64_t min_range_bytes, uint8_t* keys, uint32_t* key_lens,
+                                    uint32_t* n_boundaries);
+B200C_API int b200c_job_create_sub(b200c_job* parent, const b200c_params* p, b200c_job** out);
 
 /* ---- stage-level entry points (used by the parity tests and by bench.py's per-kernel roofline) ---- */
 enum b200c_debug_array {

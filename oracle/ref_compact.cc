@@ -70,6 +70,8 @@ struct Opts {
   int barrier_n = 0;        // concurrent timing runs compact at the same time
   int warm = 0;             // run script + job once through a throw-away DB first (timing runs: steady state of a long-lived process)
   std::string table_factory;  // "b200" / "b200+nofallback": flushes and (local) compactions write their tables through B200TableFactory
+  int b200_subs = 0;          // B200CompactOptions::max_subcompactions
+  std::string b200_devices;   // B200CompactOptions::devices, comma separated
   std::string executor;  // "b200": route the job through the B200 CompactionExecutor plugin (ref_compact_b200 build only)
 };
 
@@ -213,6 +215,8 @@ int main(int argc, char** argv) {
     else if (k == "ribbon") o.ribbon = atoi(v.c_str());
     else if (k == "partition_filters") o.partition_filters = atoi(v.c_str());
     else if (k == "executor") o.executor = v;
+    else if (k == "b200_subs") o.b200_subs = atoi(v.c_str());
+    else if (k == "b200_devices") o.b200_devices = v;
     else if (k == "table_factory") o.table_factory = v;
     else if (k == "copy") o.copy = atoi(v.c_str());
     else if (k == "filter") o.filter = v;
@@ -298,6 +302,13 @@ int main(int argc, char** argv) {
     // "b200": a job the device path rejects fails the compaction (the tests want to see the device path, not a silent
     // fallback); "b200+fallback": the reference re-runs such a job on its own CPU path (compaction_job.cc RunRemote -> RunLocal)
     bo.allow_fallback_to_local = o.executor == "b200+fallback";
+    bo.max_subcompactions = o.b200_subs;  // 0: what the job asks for (max_subcompactions); 1: never split
+    for (size_t a = 0; a < o.b200_devices.size();) {  // "0,1": the devices the ranges of one job are dealt to
+      size_t b = o.b200_devices.find(',', a);
+      if (b == std::string::npos) b = o.b200_devices.size();
+      bo.devices.push_back(atoi(o.b200_devices.substr(a, b - a).c_str()));
+      a = b + 1;
+    }
     opt.compaction_executor_factory = NewB200CompactionExecutorFactory(bo);
     use_b200 = true;
   }

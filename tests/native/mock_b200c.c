@@ -17,7 +17,7 @@
 #define MOCK_MAX_OUT 256
 struct b200c_job {
   FILE* f;
-  int n_inputs;
+  int n_inputs, n_subs, sub_index; /* sub_index: -1 for a job of its own, else the position among its parent's sub-jobs */
   uint64_t first_file_number;
   int ran, n_out;
   b200c_file_meta meta[MOCK_MAX_OUT];
@@ -25,6 +25,7 @@ struct b200c_job {
   b200c_stats stats;
 };
 static const char* g_err = "";
+static uint32_t unhex(const char* h, uint8_t* out);
 
 static void hex(FILE* f, const void* p, uint32_t n) {
   const unsigned char* b = (const unsigned char*)p;
@@ -110,12 +111,39 @@ int b200c_job_create(const b200c_params* p, b200c_job** out) {
     fprintf(f, "], \"level_compaction_dynamic_file_size\": %u, \"max_compaction_bytes\": %llu, \"target_output_file_size\": %llu, ",
             p->level_compaction_dynamic_file_size, (unsigned long long)p->max_compaction_bytes,
             (unsigned long long)p->target_output_file_size);
-    fprintf(f, "\"has_range_start\": %u, \"has_range_end\": %u, \"paranoid_file_checks\": %u, \"bloom_millibits_per_key\": %u, \"inputs\": [",
-            p->has_range_start, p->has_range_end, p->paranoid_file_checks, p->bloom_millibits_per_key);
+    fprintf(f, "\"has_range_start\": %u, \"has_range_end\": %u, \"range_start\": ", p->has_range_start, p->has_range_end);
+    hex(f, p->range_start_user_key, p->has_range_start ? p->range_start_len : 0);
+    fprintf(f, ", \"range_end\": ");
+    hex(f, p->range_end_user_key, p->has_range_end ? p->range_end_len : 0);
+    fprintf(f, ", \"paranoid_file_checks\": %u, \"bloom_millibits_per_key\": %u, \"inputs\": [", p->paranoid_file_checks, p->bloom_millibits_per_key);
   }
   j->first_file_number = p->first_file_number;
+  j->sub_index = -1;
   *out = j;
   return B200C_OK;
+}
+/* B200C_MOCK_BOUNDARIES=<hex user key>,<hex user key>,...: the ranges the "planner" answers with (none: the job stays in one piece) */
+int b200c_job_plan_ranges(b200c_job* j, uint32_t max_ranges, uint64_t min_range_bytes, uint8_t* keys, uint32_t* key_lens, uint32_t* n_boundaries) {
+  (void)j; (void)min_range_bytes;
+  *n_boundaries = 0;
+  const char* b = getenv("B200C_MOCK_BOUNDARIES");
+  if (!b || max_ranges < 2) return B200C_OK;
+  char buf[1024];
+  snprintf(buf, sizeof buf, "%s", b);
+  for (char* tok = strtok(buf, ","); tok && *n_boundaries + 1 < max_ranges; tok = strtok(NULL, ",")) {
+    uint8_t k[64];
+    uint32_t n = unhex(tok, k);
+    if (n > 16) n = 16;
+    memcpy(keys + 16 * (size_t)*n_boundaries, k, n);
+    key_lens[*n_boundaries] = n;
+    (*n_boundaries)++;
+  }
+  return B200C_OK;
+}
+int b200c_job_create_sub(b200c_job* parent, const b200c_params* p, b200c_job** out) {
+  int rc = b200c_job_create(p, out);
+  if (rc == B200C_OK) (*out)->sub_index = parent->n_subs++;
+  return rc;
 }
 static uint32_t unhex(const char* h, uint8_t* out) {
   uint32_t n = 0;
@@ -195,6 +223,11 @@ int b200c_job_run(b200c_job* j) {
   if (failcode) {
     g_err = "mock library: injected failure";
     return atoi(failcode);
+  }
+  char sub[4096];
+  if (dir && j->sub_index >= 0) { /* a sub-job "produces" the files of <dir>/sub<k> */
+    snprintf(sub, sizeof sub, "%s/sub%d", dir, j->sub_index);
+    dir = sub;
   }
   if (dir && load_canned(j, dir)) {
     j->ran = 1;

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert set(T.native.EXPORTS) == declared
-    assert L.b200c_abi_version() == 7
+    assert L.b200c_abi_version() == 8
 
 
 def test_params_defaults_match_reference_defaults():

@@ -38,7 +38,7 @@ def run(fn, **extra):
 
 
 def check_common(j, man, opts):
-    assert j["abi_version"] == 7 and j["device"] == 0 and j["output_mem"] == 0
+    assert j["abi_version"] == 8 and j["device"] == 0 and j["output_mem"] == 0
     assert j["bottommost_level"] == int(man["bottommost_level"])
     assert j["max_output_file_size"] == man.get("max_output_file_size", man["target_file_size"])
     assert (j["block_size"], j["block_restart_interval"], j["format_version"]) == (man["block_size"], man["restart_interval"], man["format_version"])

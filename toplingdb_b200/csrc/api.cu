@@ -181,6 +181,7 @@ struct Input {
   DevBuf staged;  // device copy of a host input
   cudaEvent_t up_ev = nullptr;  // eager upload (started by b200c_job_add_input on the copy stream) has finished
   bool uploaded = false;        // the staged copy is current for the NEXT run (consumed by it)
+  bool shared_copy = false;     // the staged copy is complete and in use by sub-jobs (b200c_job_create_sub)
   const uint8_t* dev = nullptr;
   InputTail tail;
 };
@@ -1324,6 +1325,158 @@ int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const voi
       cudaGetLastError();
     }
   }
+  return B200C_OK;
+}
+
+// ---- one job over several key ranges (sub-compactions, db/compaction/compaction_job.cc:264-281,465-640)
+namespace {
+struct Anchor {
+  uint8_t key[kMaxUserKey];
+  uint32_t klen;
+  uint64_t bytes;  // data-block bytes of the anchor's file since its previous anchor
+};
+bool host_varint(const uint8_t*& p, const uint8_t* end, uint64_t* v) {
+  uint64_t r = 0;
+  for (int sft = 0; sft <= 63 && p < end; sft += 7) {
+    const uint8_t c = *p++;
+    r |= (uint64_t)(c & 127) << sft;
+    if (c < 128) {
+      *v = r;
+      return true;
+    }
+  }
+  return false;
+}
+// Walks one index block on the host (entry layout: table/block_based/block_builder.cc:21-32, values: table/format.cc:102-140) and
+// appends about `per_file` anchors: the separator of every (nblocks / per_file)-th data block as a user key with the data bytes
+// since the previous anchor -- what TableReader::ApproximateKeyAnchors gives GenSubcompactionBoundaries (compaction_job.cc:520-560).
+std::string index_anchors(const uint8_t* blk, uint64_t size, const InputTail& t, uint32_t per_file, std::vector<Anchor>* out) {
+  if (size < 8) return "index block too short";
+  const uint32_t nr = ((uint32_t)blk[size - 4] | (uint32_t)blk[size - 3] << 8 | (uint32_t)blk[size - 2] << 16 | (uint32_t)blk[size - 1] << 24) & 0x7fffffffu;
+  if (4ull * nr + 4 > size) return "index block restart array out of range";
+  const uint8_t* p = blk;
+  const uint8_t* end = blk + size - 4 - 4ull * nr;
+  const bool value_delta = t.format_version >= 4;
+  const uint64_t step = std::max<uint64_t>(1, t.num_data_blocks / std::max<uint32_t>(per_file, 1));
+  std::string key;
+  uint64_t poff = 0, psize = 0, n = 0, last_end = 0;
+  while (p < end) {
+    uint64_t shared, non_shared, vl = 0, off, bsize;
+    if (!host_varint(p, end, &shared) || !host_varint(p, end, &non_shared)) return "malformed index entry";
+    if (!value_delta && !host_varint(p, end, &vl)) return "malformed index entry";
+    if (shared > key.size() || non_shared > (uint64_t)(end - p)) return "malformed index entry";
+    key.resize(shared);
+    key.append(reinterpret_cast<const char*>(p), non_shared);
+    p += non_shared;
+    if (shared == 0 || !value_delta) {
+      if (!host_varint(p, end, &off) || !host_varint(p, end, &bsize)) return "malformed index value";
+    } else {
+      uint64_t d;
+      if (!host_varint(p, end, &d)) return "malformed index value";
+      bsize = psize + (uint64_t)((int64_t)(d >> 1) ^ -(int64_t)(d & 1));
+      off = poff + psize + 5;
+    }
+    poff = off;
+    psize = bsize;
+    n++;
+    if (n % step == 0 && n < t.num_data_blocks) {  // (the last separator is the file's last key: nothing lies behind it)
+      size_t ulen = key.size();
+      if (!t.index_key_is_user_key) {
+        if (ulen < 8) return "index separator shorter than a trailer";
+        ulen -= 8;
+      }
+      if (ulen <= (size_t)kMaxUserKey) {  // longer separators cannot bound a device range: their bytes go to the next anchor
+        Anchor a;
+        memset(&a, 0, sizeof a);
+        memcpy(a.key, key.data(), ulen);
+        a.klen = (uint32_t)ulen;
+        a.bytes = off + bsize + 5 - last_end;
+        last_end = off + bsize + 5;
+        out->push_back(a);
+      }
+    }
+  }
+  return "";
+}
+int anchor_cmp(const Anchor& a, const Anchor& b) {
+  const int c = memcmp(a.key, b.key, std::min(a.klen, b.klen));
+  return c ? c : (int)a.klen - (int)b.klen;
+}
+}  // namespace
+
+int b200c_job_plan_ranges(b200c_job* j, uint32_t max_ranges, uint64_t min_range_bytes, uint8_t* keys, uint32_t* key_lens, uint32_t* n_boundaries) {
+  if (!j || !n_boundaries || (max_ranges > 1 && (!keys || !key_lens))) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  *n_boundaries = 0;
+  if (max_ranges <= 1 || j->inputs.empty()) return B200C_OK;
+  if (b200c_device_count() <= 0) return fail(B200C_ERR_NO_DEVICE, "no CUDA device");
+  CU(cudaSetDevice(j->p.device));
+  std::vector<Anchor> anchors;
+  uint64_t total = 0;
+  std::vector<uint8_t> idx;
+  for (Input& in : j->inputs) {
+    if (int rc = fetch_tail(j, in)) return rc;
+    total += in.tail.data_size ? in.tail.data_size : in.len;
+    if (in.tail.num_data_blocks < 2) continue;
+    if (in.tail.index_off + in.tail.index_size > in.len) return fail(B200C_ERR_CORRUPTION, "index handle out of range");
+    const uint8_t* blk = in.data + in.tail.index_off;
+    if (in.mem_kind != B200C_MEM_HOST) {
+      idx.resize(in.tail.index_size);
+      CU(cudaMemcpy(idx.data(), in.data + in.tail.index_off, in.tail.index_size, cudaMemcpyDeviceToHost));
+      blk = idx.data();
+    }
+    const std::string e = index_anchors(blk, in.tail.index_size, in.tail, 128, &anchors);
+    if (!e.empty()) return fail(B200C_ERR_CORRUPTION, e);
+  }
+  std::stable_sort(anchors.begin(), anchors.end(), [](const Anchor& a, const Anchor& b) { return anchor_cmp(a, b) < 0; });
+  // ranges of about equal input bytes, none smaller than min_range_bytes (the reference: at least one output file per range,
+  // compaction_job.cc:571-600); a boundary is the first user key of the NEXT range: [.., key) | [key, ..)
+  const uint64_t target = std::max<uint64_t>(std::max<uint64_t>(total / max_ranges, min_range_bytes), 1);
+  uint64_t acc = 0;
+  uint32_t nb = 0;
+  const Anchor* lastb = nullptr;
+  for (size_t i = 0; i < anchors.size() && nb + 1 < max_ranges; i++) {
+    acc += anchors[i].bytes;
+    if (acc < target) continue;
+    if (anchors[i].klen == 0 || (lastb && anchor_cmp(*lastb, anchors[i]) >= 0)) continue;
+    // (any user key is a valid bound of [start, end) ranges; the separator's own key, if present, opens the next range)
+    memcpy(keys + (size_t)nb * kMaxUserKey, anchors[i].key, kMaxUserKey);
+    key_lens[nb] = anchors[i].klen;
+    lastb = &anchors[i];
+    nb++;
+    acc = 0;
+  }
+  *n_boundaries = nb;
+  return B200C_OK;
+}
+
+int b200c_job_create_sub(b200c_job* parent, const b200c_params* p, b200c_job** out) {
+  if (!parent || !p || !out) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  if (p->device != parent->p.device) return fail(B200C_ERR_INVALID_ARGUMENT, "a sub-job runs on its parent's device");
+  if (parent->inputs.empty()) return fail(B200C_ERR_STATE, "parent job has no inputs");
+  CU(cudaSetDevice(parent->p.device));
+  // the device copies of the parent's host inputs: made once, here at the latest
+  for (Input& in : parent->inputs) {
+    if (in.mem_kind != B200C_MEM_HOST) continue;
+    if (in.uploaded) {
+      CU(cudaEventSynchronize(in.up_ev));
+    } else if (!in.shared_copy) {
+      CU(in.staged.reserve(in.len + 64));
+      CU(cudaMemcpy(in.staged.p, in.data, in.len, cudaMemcpyHostToDevice));
+    }
+    in.shared_copy = true;  // (a later run of the parent itself would still copy again: see run_job)
+  }
+  b200c_job* j = nullptr;
+  if (int rc = b200c_job_create(p, &j)) return rc;
+  for (const Input& in : parent->inputs) {
+    j->inputs.emplace_back();
+    Input& s = j->inputs.back();
+    s.level = in.level;
+    s.file_number = in.file_number;
+    s.len = in.len;
+    s.mem_kind = B200C_MEM_DEVICE;
+    s.data = in.mem_kind == B200C_MEM_HOST ? in.staged.as<uint8_t>() : in.data;
+  }
+  *out = j;
   return B200C_OK;
 }
 

@@ -66,7 +66,8 @@ EXPORTS = ["b200c_last_error", "b200c_abi_version", "b200c_device_count", "b200c
            "b200c_job_add_input", "b200c_job_run", "b200c_job_output_count", "b200c_job_output_meta",
            "b200c_job_output_data", "b200c_job_output_read", "b200c_job_get_stats", "b200c_job_destroy",
            "b200c_job_run_until", "b200c_job_debug_read", "b200c_block_checksums", "b200c_job_kernel_time_count",
-           "b200c_job_kernel_time", "b200c_job_encode_columns", "b200c_host_alloc", "b200c_host_free", "b200c_job_encode_kv"]
+           "b200c_job_kernel_time", "b200c_job_encode_columns", "b200c_host_alloc", "b200c_host_free", "b200c_job_encode_kv",
+           "b200c_job_plan_ranges", "b200c_job_create_sub"]
 
 
 def load_library(build_if_missing=True):
@@ -102,6 +103,8 @@ def load_library(build_if_missing=True):
     L.b200c_job_encode_kv.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200c_params_init.argtypes = [C.POINTER(Params)]
     L.b200c_params_init.restype = None
+    L.b200c_job_plan_ranges.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.b200c_job_create_sub.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(C.c_void_p)]
     _lib = L
     return L
 
@@ -136,11 +139,12 @@ class CompactionJob:
 
     Keyword arguments are the b200c_params fields; `checksum` takes "xxh3" / "crc32c" / "none"."""
 
-    def __init__(self, **kw):
+    def __init__(self, parent=None, **kw):
         L = lib()
         p = Params()
         L.b200c_params_init(C.byref(p))
         self._keep = []
+        self._kw = dict(kw)
         for k, v in kw.items():
             if k == "checksum":
                 p.checksum = CKSUM[v]
@@ -187,9 +191,30 @@ class CompactionJob:
                 setattr(p, k, v)
         self.params = p
         self._h = C.c_void_p()
-        _check(L.b200c_job_create(C.byref(p), C.byref(self._h)))
-        self.ninputs = 0
+        self._parent = parent  # a sub-job keeps its parent (and with it the shared input images) alive
+        if parent is not None:
+            parent._wait_for_torch()
+            _check(L.b200c_job_create_sub(parent._h, C.byref(p), C.byref(self._h)))
+        else:
+            _check(L.b200c_job_create(C.byref(p), C.byref(self._h)))
+        self.ninputs = parent.ninputs if parent is not None else 0
         self._torch_device_inputs = False
+
+    def plan_ranges(self, max_ranges, min_range_bytes=0):
+        """boundary user keys of up to max_ranges key ranges of about equal input bytes (GenSubcompactionBoundaries' job)"""
+        n = max(1, max_ranges)
+        keys = C.create_string_buffer(16 * n)
+        lens = (C.c_uint32 * n)()
+        nb = C.c_uint32()
+        self._wait_for_torch()
+        _check(lib().b200c_job_plan_ranges(self._h, max_ranges, min_range_bytes, keys, lens, C.byref(nb)))
+        return [keys.raw[16 * i:16 * i + lens[i]] for i in range(nb.value)]
+
+    def sub_job(self, range_start=None, range_end=None, **kw):
+        """a job over this job's inputs (shared device copies) restricted to range_start <= user key < range_end"""
+        merged = {k: v for k, v in self._kw.items() if k not in ("range_start", "range_end")}
+        merged.update(kw)
+        return CompactionJob(parent=self, range_start=range_start, range_end=range_end, **merged)
 
     def _wait_for_torch(self):
         """The library works on its own non-blocking streams: device tensors handed to it must be complete.  torch kernels that are

@@ -373,7 +373,70 @@ class B200CompactionExecutor : public CompactionExecutor {
     }
     auto shutting_down = [&]() { return p.shutting_down && p.shutting_down->load(std::memory_order_acquire); };
     if (s.ok() && shutting_down()) s = Status::ShutdownInProgress();
-    if (s.ok()) s = FromB200(b200c_job_run(job));
+    // ---- sub-compactions (CompactionJob::Prepare / GenSubcompactionBoundaries, compaction_job.cc:264-281,465-640): when the DB
+    // would split this job over threads, the executor splits it into key ranges that run concurrently -- on the streams of one
+    // device, or spread over the devices listed in B200CompactOptions::devices.  RunRemote accepts any number of result groups
+    // (compaction_job.cc:986-1000).  The ranges share the uploaded input images (b200c_job_create_sub).
+    std::vector<b200c_job*> parents{job};  // one holder of the inputs per device in use
+    std::vector<b200c_job*> units;         // what actually runs: the job itself, or its sub-jobs in key order
+    std::vector<std::string> bounds;       // owns the boundary user keys
+    uint32_t want_subs = opt_.max_subcompactions > 0 ? (uint32_t)opt_.max_subcompactions : p.max_subcompactions;
+    if (want_subs > 64) want_subs = 64;
+    if (s.ok() && want_subs > 1 && c_->ShouldFormSubcompactions()) {
+      std::vector<uint8_t> keys((size_t)want_subs * 16);
+      std::vector<uint32_t> lens(want_subs);
+      uint32_t nb = 0;
+      s = FromB200(b200c_job_plan_ranges(job, want_subs, c_->max_output_file_size(), keys.data(), lens.data(), &nb));
+      for (uint32_t i = 0; i < nb && s.ok(); i++) bounds.emplace_back(reinterpret_cast<const char*>(keys.data()) + 16 * (size_t)i, lens[i]);
+    }
+    if (s.ok() && !bounds.empty()) {
+      const size_t nsub = bounds.size() + 1;
+      std::vector<int> devs = opt_.devices.empty() ? std::vector<int>{opt_.device} : opt_.devices;
+      if (devs.size() > nsub) devs.resize(nsub);
+      if (getenv("B200C_PLUGIN_TRACE") != nullptr)
+        fprintf(stderr, "B200Compact: job %d split into %zu key ranges over %zu device(s)\n", p.job_id, nsub, devs.size());
+      for (size_t d = 1; d < devs.size() && s.ok(); d++) {  // the other devices get their own copy of the inputs (their own PCIe link)
+        b200c_params dp = bp;
+        dp.device = devs[d];
+        b200c_job* pj = nullptr;
+        s = FromB200(b200c_job_create(&dp, &pj));
+        if (!s.ok()) break;
+        parents.push_back(pj);
+        for (size_t i = 0; i < in_files.size() && s.ok(); i++)
+          s = FromB200(b200c_job_add_input(pj, in_files[i].level, in_files[i].fm->fd.GetNumber(), images[i]->p, in_files[i].fm->fd.GetFileSize(),
+                                           B200C_MEM_HOST));
+      }
+      for (size_t i = 0; i < nsub && s.ok(); i++) {
+        b200c_params sp = bp;
+        sp.device = devs[i % devs.size()];
+        sp.first_file_number = bp.first_file_number + ((uint64_t)i << 14);  // (job << 20 | sub << 14 | file): unique per session
+        if (i > 0) {
+          sp.range_start_user_key = bounds[i - 1].data();
+          sp.range_start_len = (uint32_t)bounds[i - 1].size();
+          sp.has_range_start = 1;
+        }
+        if (i + 1 < nsub) {
+          sp.range_end_user_key = bounds[i].data();
+          sp.range_end_len = (uint32_t)bounds[i].size();
+          sp.has_range_end = 1;
+        }
+        b200c_job* sj = nullptr;
+        s = FromB200(b200c_job_create_sub(parents[i % devs.size()], &sp, &sj));
+        if (s.ok()) units.push_back(sj);
+      }
+      if (s.ok()) {
+        std::vector<Status> rstat(units.size());
+        std::vector<std::thread> pool;
+        for (size_t i = 1; i < units.size(); i++)
+          pool.emplace_back([&, i]() { rstat[i] = shutting_down() ? Status::ShutdownInProgress() : FromB200(b200c_job_run(units[i])); });
+        rstat[0] = FromB200(b200c_job_run(units[0]));
+        for (auto& th : pool) th.join();
+        for (size_t i = 0; i < units.size() && s.ok(); i++) s = rstat[i];
+      }
+    } else if (s.ok()) {
+      units.push_back(job);
+      s = FromB200(b200c_job_run(job));
+    }
     if (s.ok() && shutting_down()) s = Status::ShutdownInProgress();  // do not materialise files for a DB that is closing
     std::vector<std::string> written;
     if (s.ok()) {
@@ -382,20 +445,27 @@ class B200CompactionExecutor : public CompactionExecutor {
       r->output_dir = root + "/job-" + (p.db_session_id.empty() ? std::string("s") : p.db_session_id) + "-" + std::to_string(p.job_id);
       fs->CreateDirIfMissing(root, IOOptions(), nullptr).PermitUncheckedError();
       s = fs->CreateDirIfMissing(r->output_dir, IOOptions(), nullptr);
-      r->output_files.resize(1);  // one sub-compaction: the device splits the job internally (merge-path tiles)
-      const int n = b200c_job_output_count(job);
+      r->output_files.resize(units.size());  // one result group per sub-compaction, in key order
       struct OutFile {
         b200c_file_meta m;
         const void* data;
         uint64_t len;
         std::string fname;
+        size_t unit;
       };
-      std::vector<OutFile> outs((size_t)std::max(0, n));
-      for (int i = 0; i < n && s.ok(); i++) {
-        s = FromB200(b200c_job_output_meta(job, i, &outs[i].m));
-        if (s.ok()) s = FromB200(b200c_job_output_data(job, i, &outs[i].data, &outs[i].len));
-        if (s.ok()) outs[i].fname = MakeTableFileName(r->output_dir, outs[i].m.file_number);
+      std::vector<OutFile> outs;
+      for (size_t u = 0; u < units.size() && s.ok(); u++) {
+        const int nu = b200c_job_output_count(units[u]);
+        for (int i = 0; i < nu && s.ok(); i++) {
+          OutFile o;
+          o.unit = u;
+          s = FromB200(b200c_job_output_meta(units[u], i, &o.m));
+          if (s.ok()) s = FromB200(b200c_job_output_data(units[u], i, &o.data, &o.len));
+          if (s.ok()) o.fname = MakeTableFileName(r->output_dir, o.m.file_number);
+          if (s.ok()) outs.push_back(std::move(o));
+        }
       }
+      const int n = (int)outs.size();
       if (s.ok() && n > 0) {  // write + sync the files, up to io_threads at a time
         for (auto& o : outs) written.push_back(o.fname);
         std::vector<Status> wstat((size_t)n);
@@ -421,7 +491,7 @@ class B200CompactionExecutor : public CompactionExecutor {
         fm.smallest_ikey.DecodeFrom(Slice((const char*)m.smallest_ikey, m.smallest_ikey_len));
         fm.largest_ikey.DecodeFrom(Slice((const char*)m.largest_ikey, m.largest_ikey_len));
         fm.marked_for_compaction = false;
-        r->output_files[0].push_back(std::move(fm));
+        r->output_files[outs[i].unit].push_back(std::move(fm));
       }
       if (s.ok()) s = SyncDirFS(fs, r->output_dir);  // the new names are durable too
       if (!s.ok()) {  // nothing of a failed job stays behind
@@ -432,7 +502,22 @@ class B200CompactionExecutor : public CompactionExecutor {
     }
     if (s.ok()) {
       b200c_stats st;
-      b200c_job_get_stats(job, &st);
+      memset(&st, 0, sizeof st);
+      for (b200c_job* u : units) {  // the ranges partition the job: their counters add up (AggregateStatistics on the local path)
+        b200c_stats us;
+        b200c_job_get_stats(u, &us);
+        st.num_input_records += us.num_input_records;
+        st.num_output_records += us.num_output_records;
+        st.num_input_deletion_records += us.num_input_deletion_records;
+        st.num_records_replaced += us.num_records_replaced;
+        st.num_expired_deletion_records += us.num_expired_deletion_records;
+        st.total_input_raw_key_bytes += us.total_input_raw_key_bytes;
+        st.total_input_raw_value_bytes += us.total_input_raw_value_bytes;
+        st.total_output_bytes += us.total_output_bytes;
+        st.num_output_files += us.num_output_files;
+        st.num_input_files = us.num_input_files;      // every range reads the same files
+        st.total_input_bytes = us.total_input_bytes;
+      }
       auto& js = r->job_stats;
       js.Reset();
       js.num_input_records = st.num_input_records;
@@ -475,7 +560,9 @@ class B200CompactionExecutor : public CompactionExecutor {
       r->curl_time_usec = r->mount_time_usec = r->prepare_time_usec = r->waiting_time_usec = 0;
       r->status = Status::OK();
     }
-    b200c_job_destroy(job);
+    for (b200c_job* u : units)
+      if (u != job) b200c_job_destroy(u);  // sub-jobs first: they borrow their parents' input images
+    for (b200c_job* pj : parents) b200c_job_destroy(pj);
     return s.ok() ? s : Fail(r, s);
   }
 
@@ -607,6 +694,8 @@ static std::shared_ptr<CompactionExecutorFactory> JS_NewB200Compact(const json& 
   ROCKSDB_JSON_OPT_PROP_3(js, o.verify_input_checksums, "verify_input_checksums");
   ROCKSDB_JSON_OPT_PROP_3(js, o.scratch_dir, "scratch_dir");
   ROCKSDB_JSON_OPT_PROP_3(js, o.io_threads, "io_threads");
+  ROCKSDB_JSON_OPT_PROP_3(js, o.max_subcompactions, "max_subcompactions");
+  ROCKSDB_JSON_OPT_PROP_3(js, o.devices, "devices");
   return std::make_shared<B200CompactionExecutorFactory>(o);
 }
 ROCKSDB_FACTORY_REG("B200Compact", JS_NewB200Compact);

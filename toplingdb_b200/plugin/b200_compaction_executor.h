@@ -14,6 +14,7 @@
 #pragma once
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "db/compaction/compaction_executor.h"
 
@@ -25,6 +26,11 @@ struct B200CompactOptions {
   bool verify_input_checksums = true;   // ReadOptions::verify_checksums of the compaction read
   std::string scratch_dir;              // where output files are materialised before RenameFile(); default: <dbname>/b200c-tmp
   int io_threads = 8;                   // input files are read and output files written + synced by up to this many threads per job
+  // Sub-compactions: a job the DB would split over threads (Compaction::ShouldFormSubcompactions, max_subcompactions > 1) is split
+  // into that many key ranges of about equal input bytes (0: CompactionParams::max_subcompactions; 1: never split); the ranges run
+  // concurrently and are dealt round-robin to `devices` (empty: {device}) -- one job over several GPUs.
+  int max_subcompactions = 0;
+  std::vector<int> devices;
 };
 
 class B200CompactionExecutorFactory : public CompactionExecutorFactory {
