@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <zlib.h>
 
 static __thread char g_err[256];
 const char* orc_last_error(void) { return g_err; }
@@ -270,13 +271,47 @@ typedef struct sst {
   size_t nblocks;
 } sst;
 #define SST_MAGIC 0x88e241b785f4cff7ull
-static int sst_check_block(const sst* s, uint64_t off, uint64_t size) {
+/* BlockFetcher::ReadBlockContents + UncompressBlockData (table/block_fetcher.cc:211, table/format.cc:511): the checksum covers the stored
+ * bytes and the type byte; a kZlibCompression block (type 2) is  varint32 uncompressed size | raw deflate stream  (Zlib_Uncompress,
+ * util/compression.h:834-924, window_bits -14, compress_format_version 2) and is inflated with zlib itself -- the oracle is test
+ * infrastructure.  *payload / *psize: the uncompressed block; *owned: malloc'ed copy the caller frees (NULL for a stored block). */
+static int sst_read_block(const sst* s, uint64_t off, uint64_t size, const uint8_t** payload, uint64_t* psize, uint8_t** owned) {
+  *owned = NULL;
   if (off + size + 5 > s->len) FAIL(-2, "block handle out of range");
   uint8_t ctype = s->d[off + size];
-  if (ctype != 0) FAIL(-3, "compressed block (type %u) not supported", ctype);
   uint32_t want = rd32(s->d + off + size + 1);
   uint32_t got = orc_block_checksum(s->cksum_type, s->d + off, size, ctype);
   if (s->cksum_type != ORC_CKSUM_NONE && want != got) FAIL(-4, "block checksum mismatch at %llu", (unsigned long long)off);
+  if (ctype == 0) {
+    *payload = s->d + off;
+    *psize = size;
+    return 0;
+  }
+  if (ctype != 2) FAIL(-3, "compressed block (type %u) not supported", ctype);
+  uint64_t u = 0;
+  const uint8_t* p = get_varint(s->d + off, s->d + off + size, &u);
+  if (!p || u > (1ull << 31)) FAIL(-5, "bad uncompressed size of a zlib block");
+  uint8_t* out = (uint8_t*)malloc(u ? u : 1);
+  z_stream z;
+  memset(&z, 0, sizeof z);
+  if (inflateInit2(&z, -14) != Z_OK) {
+    free(out);
+    FAIL(-5, "inflateInit2 failed");
+  }
+  z.next_in = (Bytef*)p;
+  z.avail_in = (uInt)(s->d + off + size - p);
+  z.next_out = out;
+  z.avail_out = (uInt)u;
+  int st = inflate(&z, Z_FINISH);
+  uint64_t produced = (uint64_t)z.total_out;
+  inflateEnd(&z);
+  if (st != Z_STREAM_END || produced != u) {
+    free(out);
+    FAIL(-5, "zlib block does not inflate to its announced size");
+  }
+  *payload = out;
+  *psize = u;
+  *owned = out;
   return 0;
 }
 /* iterate entries of one block payload; cb gets the fully rebuilt key. value_delta: index blocks (fv>=4). */
@@ -381,10 +416,14 @@ static int sst_open(sst* s, const uint8_t* d, size_t len) {
   if (!(p = get_varint(p, e, &s->meta_off)) || !(p = get_varint(p, e, &s->meta_size)) ||
       !(p = get_varint(p, e, &s->index_off)) || !(p = get_varint(p, e, &s->index_size)))
     FAIL(-1, "bad footer handles");
-  int rc = sst_check_block(s, s->index_off, s->index_size);
+  const uint8_t* ib;
+  uint64_t isz;
+  uint8_t* iown;
+  int rc = sst_read_block(s, s->index_off, s->index_size, &ib, &isz, &iown);
   if (rc) return rc;
   idx_ctx c = {s, 0, 0, 0};
-  rc = block_foreach(d + s->index_off, s->index_size, s->fv >= 4, index_cb, &c);
+  rc = block_foreach(ib, isz, s->fv >= 4, index_cb, &c);
+  free(iown);
   if (rc) sst_close(s);
   return rc;
 }
@@ -398,6 +437,7 @@ typedef struct sst_iter {
   size_t vlen;
   int valid, err;
   uint64_t yielded; /* entries produced so far */
+  uint8_t* ublock;  /* the current block's inflated bytes (kZlibCompression), NULL for a stored block */
 } sst_iter;
 static void sst_iter_next(sst_iter* it) {
   for (;;) {
@@ -426,11 +466,18 @@ static void sst_iter_next(sst_iter* it) {
     }
     uint64_t off = it->s.boff[it->blk], size = it->s.bsize[it->blk];
     it->blk++;
-    if ((it->err = sst_check_block(&it->s, off, size)) != 0) {
+    free(it->ublock);
+    it->ublock = NULL;
+    const uint8_t* b;
+    if ((it->err = sst_read_block(&it->s, off, size, &b, &size, &it->ublock)) != 0) {
       it->valid = 0;
       return;
     }
-    const uint8_t* b = it->s.d + off;
+    if (size < 4) {
+      it->err = -5;
+      it->valid = 0;
+      return;
+    }
     uint32_t nr = rd32(b + size - 4) & 0x7fffffffu;
     it->p = b;
     it->end = b + size - 4 - 4 * (size_t)nr;
@@ -445,6 +492,8 @@ static int sst_iter_open(sst_iter* it, const uint8_t* d, size_t len) {
   return it->err;
 }
 static void sst_iter_close(sst_iter* it) {
+  free(it->ublock);
+  it->ublock = NULL;
   sst_close(&it->s);
   buf_free(&it->key);
 }

@@ -37,6 +37,7 @@
 #include "rocksdb/system_clock.h"
 #include "rocksdb/utilities/db_ttl.h"
 #include "rocksdb/write_batch.h"
+#include "util/compression.h"
 #include "utilities/compaction_filters/remove_emptyvalue_compactionfilter.h"
 #ifdef WITH_B200_PLUGIN
 #include "rocksdb/statistics.h"
@@ -70,6 +71,8 @@ struct Opts {
   int barrier_n = 0;        // concurrent timing runs compact at the same time
   int warm = 0;             // run script + job once through a throw-away DB first (timing runs: steady state of a long-lived process)
   std::string table_factory;  // "b200" / "b200+nofallback": flushes and (local) compactions write their tables through B200TableFactory
+  std::string input_compression = "none";  // "zlib": the job's INPUT files (flushes, set-up compactions) are written with kZlibCompression
+  int index_compression = 1;               // BlockBasedTableOptions::enable_index_compression
   int b200_subs = 0;          // B200CompactOptions::max_subcompactions
   std::string b200_devices;   // B200CompactOptions::devices, comma separated
   std::string executor;  // "b200": route the job through the B200 CompactionExecutor plugin (ref_compact_b200 build only)
@@ -216,6 +219,8 @@ int main(int argc, char** argv) {
     else if (k == "partition_filters") o.partition_filters = atoi(v.c_str());
     else if (k == "executor") o.executor = v;
     else if (k == "b200_subs") o.b200_subs = atoi(v.c_str());
+    else if (k == "input_compression") o.input_compression = v;
+    else if (k == "index_compression") o.index_compression = atoi(v.c_str());
     else if (k == "b200_devices") o.b200_devices = v;
     else if (k == "table_factory") o.table_factory = v;
     else if (k == "copy") o.copy = atoi(v.c_str());
@@ -240,7 +245,16 @@ int main(int argc, char** argv) {
   Options opt;
   opt.create_if_missing = true;
   opt.disable_auto_compactions = true;
-  opt.compression = kNoCompression;
+  const CompressionType in_comp = o.input_compression == "zlib" ? kZlibCompression : kNoCompression;
+  if (o.input_compression != "zlib" && o.input_compression != "none") {
+    fprintf(stderr, "ref_compact: unknown input_compression %s\n", o.input_compression.c_str());
+    return 1;
+  }
+  if (in_comp != kNoCompression && !CompressionTypeSupported(in_comp)) {
+    fprintf(stderr, "ref_compact: this build of the reference has no zlib (-DZLIB)\n");
+    return 1;
+  }
+  opt.compression = in_comp;  // flushes write the job's L0 inputs; the measured job itself writes uncompressed (co.compression below)
   opt.bottommost_compression = kDisableCompressionOption;
   opt.compression_per_level.clear();
   opt.num_levels = 7;
@@ -266,6 +280,7 @@ int main(int argc, char** argv) {
   t.format_version = o.format_version;
   t.checksum = o.checksum == "crc32c" ? kCRC32c : kXXH3;
   t.no_block_cache = true;
+  t.enable_index_compression = o.index_compression != 0;
   if (o.bloom_bits > 0) t.filter_policy.reset(NewBloomFilterPolicy(o.bloom_bits, false));
   if (o.ribbon) t.filter_policy.reset(NewRibbonFilterPolicy(10));
   if (o.partition_filters) {
@@ -409,7 +424,7 @@ int main(int argc, char** argv) {
         for (auto& m : live) names.push_back(m.name);
         if (!names.empty()) {
           CompactionOptions co;
-          co.compression = kNoCompression;
+          co.compression = in_comp;  // set-up compactions write inputs of the measured job
           co.output_file_size_limit = o.setup_file_size;
           s = db->CompactFiles(co, names, lvl);
           if (!s.ok()) Die("setup compaction", s);

@@ -22,13 +22,13 @@ SMALL = dict(  # keep committed fixtures small (tens of KB each)
     snapshots_nonbottom=dict(n=150), varlen_keys=dict(n=200), long_keys=dict(n=100), crc32c_small_blocks=dict(n=300),
     same_user_key_across_blocks={}, tiny={}, all_deleted={}, cfg2_mini=dict(per_run=250), cfg3_mini=dict(per_run=60),
     output_level0={}, filter_empty_value=dict(n=150), filter_empty_value_nonbottom=dict(n=150),
-    ttl_filter=dict(n=150), ttl_filter_nonbottom=dict(n=150))
+    ttl_filter=dict(n=150), ttl_filter_nonbottom=dict(n=150), zlib_inputs=dict(n=400, nruns=3), zlib_inputs_nonbottom=dict(n=300, nruns=3))
 
 
 def main():
     assert H.have_ref(), "oracle/_ref/ref_compact missing: run `make -C oracle ref` where /root/reference exists"
     only = set(sys.argv[1:])  # optional: regenerate just the named cases (the others keep their committed bytes)
-    for name, fn in S.ALL.items():
+    for name, fn in list(S.ALL.items()) + list(S.ZLIB.items()):
         if only and name not in only:
             continue
         ops, opts = fn(**SMALL[name])

@@ -291,3 +291,49 @@ def single_deletes(n=400, nruns=5, seed=19, nonbottom=False, with_snapshots=True
 
 ORACLE_ONLY["single_deletes"] = single_deletes
 ORACLE_ONLY["single_deletes_nonbottom"] = lambda **kw: single_deletes(nonbottom=True, **kw)
+
+
+_WORDS = [b"compaction", b"level", b"block", b"table", b"restart", b"varint", b"checksum", b"footer", b"index", b"merge", b"snapshot", b"tombstone"]
+
+
+def _texty(rnd, n):
+    out = bytearray()
+    while len(out) < n:
+        out += rnd.choice(_WORDS) + b" "
+    return bytes(out[:n])
+
+
+def zlib_inputs(n=1500, nruns=4, seed=21, nonbottom=False):
+    """Inputs written with kZlibCompression (flush compression), outputs uncompressed: what a job reads when the upper levels are
+    compressed and its output level is not.  Values are mostly word soup (blocks compress and are stored as varint32 size + raw
+    deflate), some runs of random bytes (blocks that do not shrink by 12.5 % stay uncompressed: block_based_table_builder.cc:1150-1275),
+    some empty; the index blocks are compressed too (enable_index_compression).  Registered apart from ALL: the generic per-scenario
+    tests rebuild inputs with the uncompressed table builder."""
+    rnd = random.Random(seed)
+    ops = Ops()
+    if nonbottom:
+        for k in [key16(0), key16(1 << 40)]:
+            ops.put(k, b"base")
+        ops.flush()
+        ops.compact_all_to(6)
+    for r in range(nruns):
+        keys = sorted(rnd.sample(range(1, n * 3), n))
+        noisy = None
+        for i, k in enumerate(keys):
+            if i % 200 == 0:
+                noisy = rnd.random() < 0.3  # a stretch of incompressible values now and then
+            if rnd.random() < 0.1:
+                ops.delete(key16(k))
+            elif rnd.random() < 0.05:
+                ops.put(key16(k), b"")
+            elif noisy:
+                ops.put(key16(k), rnd.randbytes(rnd.randint(20, 120)))
+            else:
+                ops.put(key16(k), _texty(rnd, rnd.randint(1, 400)))
+        ops.flush()
+        if r == 1:
+            ops.snapshot()
+    return ops, dict(target_file_size=96 << 10, input_compression="zlib")
+
+
+ZLIB = dict(zlib_inputs=zlib_inputs, zlib_inputs_nonbottom=lambda **kw: zlib_inputs(nonbottom=True, **kw))

@@ -66,8 +66,18 @@ def block_entries(block, value_delta=False):
 
 
 def read_block(data, handle):
+    """payload (inflated when the block is stored with kZlibCompression: varint32 size + raw deflate, util/compression.h:834-924),
+    compression type byte, stored checksum"""
     off, sz = handle
-    return data[off:off + sz], data[off + sz], struct.unpack_from("<I", data, off + sz + 1)[0]
+    payload, ctype = data[off:off + sz], data[off + sz]
+    if ctype == 2:
+        import zlib
+        usize, p = varint(payload, 0)
+        payload = zlib.decompress(payload[p:], -14)
+        assert len(payload) == usize
+    else:
+        assert ctype == 0, f"block compression type {ctype}"
+    return payload, ctype, struct.unpack_from("<I", data, off + sz + 1)[0]
 
 
 def parse_sst(data):
@@ -105,7 +115,7 @@ def parse_sst(data):
     entries = []
     for _, h in index:
         blk, ctype, _ = read_block(data, h)
-        assert ctype == 0
+        assert ctype in (0, 2)  # (read_block inflates kZlibCompression)
         for k, v, _ in block_entries(blk):
             entries.append((k, v))
     return dict(footer=ft, metaindex=meta, properties=props, index=index, entries=entries)

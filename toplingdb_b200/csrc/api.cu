@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/b200c.h"
+#include "inflate_rules.h"
 #include "kernels.h"
 #include "scan.cuh"
 #include "sst_host.h"
@@ -182,6 +183,8 @@ struct Input {
   cudaEvent_t up_ev = nullptr;  // eager upload (started by b200c_job_add_input on the copy stream) has finished
   bool uploaded = false;        // the staged copy is current for the NEXT run (consumed by it)
   bool shared_copy = false;     // the staged copy is complete and in use by sub-jobs (b200c_job_create_sub)
+  DevBuf index_inflated;        // device copy of an index block that was stored compressed
+  std::vector<uint8_t> index_host;  // ... and its host bytes (source of the upload; kept until the run ends)
   const uint8_t* dev = nullptr;
   InputTail tail;
 };
@@ -253,6 +256,7 @@ struct b200c_job {
   DevBuf gp_keys_d, gp_ranks_d, gp_size_d, gp_same_d, gp_cuts_d;
   BoundKey range_lo{}, range_hi{};  // sub-compaction key range in column form (has_range_start / has_range_end in p)
   DevBuf clip_d;                    // clipped run bounds: begin[k] | end[k]
+  DevBuf cslot, cslot_off, arena;   // compressed inputs: arena slot size / offset per data block, the inflated blocks
   DevBuf vfiles_d, vrun_start;      // paranoid_file_checks: descriptors / run table of the outputs being read back
   HostBuf pin_small, pin_tails, pin_rd, pin_up;
   size_t pin_up_used = 0;  // pinned staging: input tails / tail-copy records, output tails
@@ -281,7 +285,7 @@ struct b200c_job {
 namespace {
 
 // layout of the `small` buffer (u64 slots)
-enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotDecTicket = 6, kSlotGpCuts = 7, kSlotCounters = 8 /* 8 */, kSlotClip = 16 /* 2: entries, value bytes in range */, kSlotStitchDone = 18, kSmallSlots = 32 };
+enum { kSlotErr = 0, kSlotTicket = 1, kSlotTotalIn = 2, kSlotMinS1 = 3, kSlotTotals = 4 /* 2 */, kSlotDecTicket = 6, kSlotGpCuts = 7, kSlotCounters = 8 /* 8 */, kSlotClip = 16 /* 2: entries, value bytes in range */, kSlotStitchDone = 18, kSlotArena = 19 /* bytes of the inflated-block arena */, kSmallSlots = 32 };
 
 int map_dev_err(uint32_t e) {
   e &= ~(uint32_t)kFlagHasSingleDelete;  // a note of the decoder, not an error
@@ -386,6 +390,45 @@ int fetch_tail(b200c_job* j, Input& in, const uint8_t* prefetched = nullptr) {
   if (!in.tail.comparator_name.empty() && in.tail.comparator_name != "leveldb.BytewiseComparator")
     return fail(B200C_ERR_NOT_SUPPORTED, "comparator " + in.tail.comparator_name + " (only leveldb.BytewiseComparator runs on the device)");
   if (in.tail.num_data_blocks > 0xffffffffull) return fail(B200C_ERR_NOT_SUPPORTED, "too many data blocks");
+  return B200C_OK;
+}
+
+bool input_is_compressed(const Input& in) { return !in.tail.compression_name.empty() && in.tail.compression_name != "NoCompression"; }
+// The index block of a file written with block compression goes through the same WriteBlock as data blocks (enable_index_compression,
+// block_based_table_builder.cc:1566-1573).  It is O(blocks) metadata that the host reads anyway (tail, ranges): a compressed one is
+// inflated here, with the product's own decoder (inflate_rules.h compiled for the host), after its checksum is verified.
+// *out is left empty when the block is stored uncompressed.
+int host_inflated_index(b200c_job* j, const Input& in, std::vector<uint8_t>* out) {
+  out->clear();
+  const uint64_t off = in.tail.index_off, size = in.tail.index_size;
+  if (off + size + 5 > in.len) return fail(B200C_ERR_CORRUPTION, "index handle out of range");
+  uint8_t trailer[5];
+  if (in.mem_kind == B200C_MEM_HOST) memcpy(trailer, in.data + off + size, 5);
+  else CU(cudaMemcpy(trailer, in.data + off + size, 5, cudaMemcpyDeviceToHost));
+  if (trailer[0] == 0) return B200C_OK;
+  if (trailer[0] != 2) return fail(B200C_ERR_NOT_SUPPORTED, "index block compressed with a codec the device path does not decode");
+  std::vector<uint8_t> comp;
+  const uint8_t* cp = in.data + off;
+  if (in.mem_kind != B200C_MEM_HOST) {
+    comp.resize(size);
+    CU(cudaMemcpy(comp.data(), in.data + off, size, cudaMemcpyDeviceToHost));
+    cp = comp.data();
+  }
+  (void)j;
+  if (in.tail.checksum_type && host_block_checksum(in.tail.checksum_type, cp, size, trailer[0]) !=
+                                   ((uint32_t)trailer[1] | (uint32_t)trailer[2] << 8 | (uint32_t)trailer[3] << 16 | (uint32_t)trailer[4] << 24))
+    return fail(B200C_ERR_CORRUPTION, "index block checksum mismatch");
+  uint64_t u = 0;
+  uint32_t h = 0;
+  for (int sft = 0; h < 5 && h < size; sft += 7) {
+    const uint8_t c = cp[h++];
+    u |= (uint64_t)(c & 127) << sft;
+    if (c < 128) break;
+  }
+  if (u < 8 || u > (1ull << 31)) return fail(B200C_ERR_CORRUPTION, "compressed index block announces a bad size");
+  out->resize(u);
+  if (b200c::inflate_raw(cp + h, (uint32_t)(size - h), out->data(), (uint32_t)u) != (long)u)
+    return fail(B200C_ERR_CORRUPTION, "compressed index block does not inflate to its announced size");
   return B200C_OK;
 }
 
@@ -837,6 +880,7 @@ int run_job(b200c_job* j, int until) {
   // ---------------- inputs: resident image + tail
   CU(cudaEventRecord(j->ev[0], st));
   uint64_t nblk = 0, n_props = 0, in_bytes = 0;
+  bool any_compressed = false;
   std::vector<FileDesc> fds(k);
   {  // tails of device-resident inputs: one batch of small D2H copies and a single synchronisation
     bool any_dev = false;
@@ -879,6 +923,17 @@ int run_job(b200c_job* j, int until) {
     fd.gblk_first = (uint32_t)nblk;
     fd.nblocks = (uint32_t)in.tail.num_data_blocks;
     fd.index_user_key = in.tail.index_key_is_user_key ? 1u : 0u;
+    fd.index_ptr = nullptr;
+    if (input_is_compressed(in)) {  // kZlibCompression inputs: data blocks are inflated on the device, the index block here
+      any_compressed = true;
+      if (int rc2 = host_inflated_index(j, in, &in.index_host)) return rc2;
+      if (!in.index_host.empty()) {
+        CU(in.index_inflated.reserve(in.index_host.size() + 64));
+        CU(cudaMemcpyAsync(in.index_inflated.p, in.index_host.data(), in.index_host.size(), cudaMemcpyHostToDevice, st));
+        fd.index_ptr = in.index_inflated.as<uint8_t>();
+        fd.index_size = (uint32_t)in.index_host.size();
+      }
+    }
     nblk += in.tail.num_data_blocks;
     n_props += in.tail.num_entries;
     in_bytes += in.len;
@@ -924,6 +979,26 @@ int run_job(b200c_job* j, int until) {
     j->kt_end();
     launches++;
   }
+  const uint8_t* arena = nullptr;
+  if (nblk && any_compressed) {
+    // compressed data blocks -> the arena of inflated blocks; their handles are redirected there (decode.cu)
+    CU(j->cslot.reserve(4 * (nblk + 1)));
+    CU(j->cslot_off.reserve(8 * (nblk + 1)));
+    j->kt_begin("decode.inflate");
+    launch_block_usize(files_d, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), (uint32_t)nblk, j->cslot.as<uint32_t>(), err, st);
+    exclusive_scan<uint32_t>(j->cslot.as<uint32_t>(), j->cslot_off.as<uint64_t>(), nblk, j->scan_tmp.as<uint64_t>(), small + kSlotArena, st, &launches);
+    uint64_t hc[kSmallSlots];
+    int rc = read_small(j, small, hc, nullptr, nullptr);  // sync: the arena is sized by what the blocks announce
+    if (rc) return rc;
+    rc = map_dev_err((uint32_t)hc[kSlotErr]);
+    if (rc) return rc;
+    CU(j->arena.reserve(hc[kSlotArena] + 256));
+    arena = j->arena.as<uint8_t>();
+    launch_inflate_blocks(files_d, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), j->cslot.as<uint32_t>(), j->cslot_off.as<uint64_t>(),
+                          (uint32_t)nblk, j->arena.as<uint8_t>(), P.verify_input_checksums, err, st);
+    j->kt_end();
+    launches += 3;
+  }
   KeyColsMut dec{j->dec[0].as<ulonglong2>(), j->dec[1].as<uint64_t>(), j->dec[2].as<uint64_t>(), j->dec[3].as<uint32_t>()};
   CU(cudaMemsetAsync(j->run_start.p, 0, 8 * (k + 1), st));  // stays zero when there is no data block at all
   if (nblk) {
@@ -931,7 +1006,7 @@ int run_job(b200c_job* j, int until) {
     j->kt_begin("decode.blocks");
     launch_block_decode_fused(files_d, k, j->blk_off.as<uint64_t>(), j->blk_size.as<uint32_t>(), (uint32_t)nblk, P.verify_input_checksums, N,
                               dec, j->blk_state.as<unsigned long long>(), reinterpret_cast<uint32_t*>(small + kSlotDecTicket),
-                              j->run_start.as<uint64_t>(), small + kSlotTotalIn, err, j->sms, st);
+                              j->run_start.as<uint64_t>(), small + kSlotTotalIn, err, j->sms, st, arena);
     j->kt_end();
     launches++;
   }
@@ -1419,12 +1494,21 @@ int b200c_job_plan_ranges(b200c_job* j, uint32_t max_ranges, uint64_t min_range_
     if (in.tail.num_data_blocks < 2) continue;
     if (in.tail.index_off + in.tail.index_size > in.len) return fail(B200C_ERR_CORRUPTION, "index handle out of range");
     const uint8_t* blk = in.data + in.tail.index_off;
-    if (in.mem_kind != B200C_MEM_HOST) {
+    uint64_t blk_len = in.tail.index_size;
+    if (input_is_compressed(in)) {
+      if (int rc = host_inflated_index(j, in, &idx)) return rc;
+    } else {
+      idx.clear();
+    }
+    if (!idx.empty()) {
+      blk = idx.data();
+      blk_len = idx.size();
+    } else if (in.mem_kind != B200C_MEM_HOST) {
       idx.resize(in.tail.index_size);
       CU(cudaMemcpy(idx.data(), in.data + in.tail.index_off, in.tail.index_size, cudaMemcpyDeviceToHost));
       blk = idx.data();
     }
-    const std::string e = index_anchors(blk, in.tail.index_size, in.tail, 128, &anchors);
+    const std::string e = index_anchors(blk, blk_len, in.tail, 128, &anchors);
     if (!e.empty()) return fail(B200C_ERR_CORRUPTION, e);
   }
   std::stable_sort(anchors.begin(), anchors.end(), [](const Anchor& a, const Anchor& b) { return anchor_cmp(a, b) < 0; });
@@ -1563,8 +1647,12 @@ void b200c_job_destroy(b200c_job* j) {
   j->clip_d.release();
   j->vfiles_d.release();
   j->vrun_start.release();
+  j->cslot.release();
+  j->cslot_off.release();
+  j->arena.release();
   for (auto& in : j->inputs) {
     in.staged.release();
+    in.index_inflated.release();
     if (in.up_ev) cudaEventDestroy(in.up_ev);
   }
   if (j->st_up) cudaStreamDestroy(j->st_up);

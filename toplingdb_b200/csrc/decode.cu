@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "inflate_rules.h"
 #include "range_rules.h"
 
 namespace b200c {
@@ -36,6 +37,8 @@ __device__ __forceinline__ int file_of_block(const FileDesc* files, int nfiles, 
 // blk_off[b] = offset of the block inside its file | file index << kBlkFileShift (the block decoder gets both with one load)
 constexpr int kBlkFileShift = 48;
 constexpr uint64_t kBlkOffMask = (1ull << kBlkFileShift) - 1;
+// a block that was stored compressed: the offset (bit 47 set) counts from the job's arena of inflated blocks, not from the file image
+constexpr uint64_t kBlkArenaBit = 1ull << 47;
 __device__ void index_decode_sequential(const FileDesc& fd, uint32_t file_idx, const uint8_t* blk, uint32_t nr, uint64_t* blk_off,
                                         uint32_t* blk_size, uint32_t* err) {
   const uint8_t* end = blk + fd.index_size - 4 - 4ull * nr;
@@ -72,7 +75,7 @@ __device__ void index_decode_sequential(const FileDesc& fd, uint32_t file_idx, c
       n++;
       break;
     }
-    if (off + size + 5 > fd.len || size < 4 || size > 0xffffffffull || off > kBlkOffMask) {
+    if (off + size + 5 > fd.len || size < 4 || size > 0xffffffffull || off >= kBlkArenaBit) {
       atomicOr(err, kErrCorruptBlock);
       off = 0;
       size = 4;
@@ -118,11 +121,11 @@ __global__ void index_decode_kernel(const FileDesc* __restrict__ files, int nfil
   const int f = blockIdx.y;
   if (f >= nfiles) return;
   const FileDesc fd = files[f];
-  if (fd.index_size < 8 || fd.index_off + fd.index_size + 5 > fd.len) {
+  if (fd.index_size < 8 || (fd.index_ptr == nullptr && fd.index_off + fd.index_size + 5 > fd.len)) {
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(err, kErrCorruptBlock);
     return;
   }
-  const uint8_t* blk = fd.base + fd.index_off;
+  const uint8_t* blk = fd.index_ptr ? fd.index_ptr : fd.base + fd.index_off;
   const uint32_t nr = ld_u32(blk + fd.index_size - 4) & 0x7fffffffu;
   if (4ull * nr + 4 > fd.index_size) {
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(err, kErrCorruptBlock);
@@ -151,7 +154,7 @@ __global__ void index_decode_kernel(const FileDesc* __restrict__ files, int nfil
     ok = ok && p < rs && (c = get_varint(p, rs, &off));
     if (ok) p += c;
     ok = ok && (c = get_varint(p, rs, &size));
-    if (!ok || off + size + 5 > fd.len || size < 4 || size > 0xffffffffull || off > kBlkOffMask) {
+    if (!ok || off + size + 5 > fd.len || size < 4 || size > 0xffffffffull || off >= kBlkArenaBit) {
       atomicOr(err, kErrCorruptBlock);
       off = 0;
       size = 4;
@@ -739,7 +742,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, kMinCtas)
 block_decode_fused_kernel(const FileDesc* __restrict__ files, int nfiles, const uint64_t* __restrict__ blk_off,
                           const uint32_t* __restrict__ blk_size, uint32_t nblk, uint32_t verify, uint64_t n_total, KeyColsMut out,
                           unsigned long long* blk_state, uint32_t* ticket, uint64_t* __restrict__ run_start,
-                          uint64_t* __restrict__ total_out, uint32_t* __restrict__ err) {
+                          uint64_t* __restrict__ total_out, uint32_t* __restrict__ err, const uint8_t* __restrict__ arena) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t s_mask[25 * 3];
   __shared__ XxhLaneTab s_xtab;
@@ -765,8 +768,10 @@ block_decode_fused_kernel(const FileDesc* __restrict__ files, int nfiles, const 
     if (b >= nblk) break;
     const uint64_t bo = blk_off[b];
     const int f = (int)(bo >> kBlkFileShift);
-    const uint8_t* src = files[f].base + (bo & kBlkOffMask);
-    const uint32_t size = blk_size[b], cksum = files[f].cksum;
+    // (an inflated block sits in the arena; its checksum was verified over the stored bytes by verify_compressed_kernel)
+    const bool inflated = (bo & kBlkArenaBit) != 0;
+    const uint8_t* src = inflated ? arena + (bo & (kBlkArenaBit - 1)) : files[f].base + (bo & kBlkOffMask);
+    const uint32_t size = blk_size[b], cksum = inflated ? 0u : files[f].cksum;
     if (size == 0) {  // outside the sub-compaction's key range (index_decode_kernel): an empty block, nothing is read
       publish_block_count(blk_state, b, 0, lane);
       // its position only matters where a run starts / the stream ends; every 32nd skipped block still resolves its prefix so that
@@ -847,6 +852,96 @@ __global__ void meta_vlen_kernel(const uint32_t* __restrict__ meta, uint64_t n, 
     vlen[i] = meta_vlen(meta[i]);
 }
 
+// ---------------------------------------------------------------------------------------------- compressed data blocks
+// UncompressBlockData (table/format.cc:511) for kZlibCompression, the codec this image can pin against (zlib is the only compression
+// library here; the reference is built with -DZLIB for the oracle).  Three small passes in front of the block decoder:
+//   block_usize_kernel        thread per block: compression type byte; for a compressed block the announced uncompressed size
+//                             (varint32 prefix, compress_format_version 2) -> its slot size in the arena
+//   (exclusive scan)          arena offsets
+//   verify_compressed_kernel  warp per compressed block: the block checksum covers the STORED bytes (block_fetcher.cc:32-40)
+//   inflate_blocks_kernel     thread per compressed block: raw deflate (inflate_rules.h) into its arena slot + an uncompressed trailer,
+//                             then the block's handle is redirected to the arena.  32 blocks per warp run the same decoder loops.
+constexpr uint8_t kZlibCompressionType = 2;  // CompressionType::kZlibCompression (include/rocksdb/compression_type.h)
+__device__ __forceinline__ bool compressed_prefix(const uint8_t* p, uint32_t size, uint32_t* usize, uint32_t* hdr) {
+  uint64_t u = 0;
+  const int c = get_varint(p, p + (size < 5 ? size : 5), &u);
+  if (c == 0 || u > 0x7fffffffull) return false;
+  *usize = (uint32_t)u;
+  *hdr = (uint32_t)c;
+  return true;
+}
+__global__ void block_usize_kernel(const FileDesc* __restrict__ files, const uint64_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_size,
+                                   uint32_t nblk, uint32_t* __restrict__ slot, uint32_t* __restrict__ err) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblk) return;
+  uint32_t s = 0;
+  const uint32_t size = blk_size[b];
+  if (size != 0) {
+    const uint64_t bo = blk_off[b];
+    const uint8_t* p = files[bo >> kBlkFileShift].base + (bo & kBlkOffMask);
+    const uint8_t ctype = p[size];
+    if (ctype == kZlibCompressionType) {
+      uint32_t u, h;
+      if (compressed_prefix(p, size, &u, &h) && u >= 4) s = (u + 5 + 15) & ~15u;
+      else atomicOr(err, kErrCorruptBlock);
+    } else if (ctype != 0) {
+      atomicOr(err, kErrCompressed);  // a codec the device does not decode
+    }
+  }
+  slot[b] = s;
+}
+__global__ void verify_compressed_kernel(const FileDesc* __restrict__ files, const uint64_t* __restrict__ blk_off, const uint32_t* __restrict__ blk_size,
+                                         const uint32_t* __restrict__ slot, uint32_t nblk, uint32_t* __restrict__ err) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nblk; b += (gridDim.x * blockDim.x) >> 5) {
+    if (slot[b] == 0) continue;
+    const uint64_t bo = blk_off[b];
+    const FileDesc& fd = files[bo >> kBlkFileShift];
+    if (fd.cksum == 0) continue;
+    const uint8_t* p = fd.base + (bo & kBlkOffMask);
+    const uint32_t size = blk_size[b];
+    const uint32_t got = block_checksum_warp(fd.cksum, p, size, p[size]);
+    if (lane == 0 && got != ld_u32(p + size + 1)) atomicOr(err, kErrChecksum);
+  }
+}
+__global__ void __launch_bounds__(128)
+inflate_blocks_kernel(const FileDesc* __restrict__ files, uint64_t* __restrict__ blk_off, uint32_t* __restrict__ blk_size,
+                      const uint32_t* __restrict__ slot, const uint64_t* __restrict__ slot_off, uint32_t nblk, uint8_t* __restrict__ arena,
+                      uint32_t* __restrict__ err) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblk || slot[b] == 0) return;
+  const uint64_t bo = blk_off[b];
+  const uint8_t* p = files[bo >> kBlkFileShift].base + (bo & kBlkOffMask);
+  const uint32_t size = blk_size[b];
+  uint32_t u = 0, h = 0;
+  compressed_prefix(p, size, &u, &h);
+  uint8_t* dst = arena + slot_off[b];
+  const long n = inflate_raw(p + h, size - h, dst, u);
+  if (n != (long)u) {
+    atomicOr(err, kErrCorruptBlock);
+    blk_size[b] = 0;  // (an empty block: the job fails anyway)
+    return;
+  }
+  dst[u] = 0;  // trailer of an uncompressed block; the checksum bytes are never read (cksum = 0 for arena blocks)
+  dst[u + 1] = dst[u + 2] = dst[u + 3] = dst[u + 4] = 0;
+  blk_off[b] = (bo & ~kBlkOffMask) | kBlkArenaBit | slot_off[b];
+  blk_size[b] = u;
+}
+void launch_block_usize(const FileDesc* files_dev, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk, uint32_t* slot, uint32_t* err,
+                        cudaStream_t st) {
+  if (nblk) block_usize_kernel<<<(nblk + 255) / 256, 256, 0, st>>>(files_dev, blk_off, blk_size, nblk, slot, err);
+}
+void launch_inflate_blocks(const FileDesc* files_dev, uint64_t* blk_off, uint32_t* blk_size, const uint32_t* slot, const uint64_t* slot_off,
+                           uint32_t nblk, uint8_t* arena, uint32_t verify, uint32_t* err, cudaStream_t st) {
+  if (nblk == 0) return;
+  if (verify) {
+    unsigned g = (nblk + 7) / 8;
+    if (g > 148 * 8) g = 148 * 8;
+    verify_compressed_kernel<<<g, 256, 0, st>>>(files_dev, blk_off, blk_size, slot, nblk, err);
+  }
+  inflate_blocks_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(files_dev, blk_off, blk_size, slot, slot_off, nblk, arena, err);
+}
+
 // ---------------------------------------------------------------------------------------------- host launchers
 void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blocks_per_file, uint64_t* blk_off,
                          uint32_t* blk_size, BoundKey start, uint32_t has_start, BoundKey end, uint32_t has_end, uint32_t* err, cudaStream_t st) {
@@ -856,7 +951,7 @@ void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blo
 }
 void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk,
                                uint32_t verify, uint64_t n_total, KeyColsMut out, unsigned long long* blk_state, uint32_t* ticket,
-                               uint64_t* run_start, uint64_t* total_out, uint32_t* err, int sms, cudaStream_t st) {
+                               uint64_t* run_start, uint64_t* total_out, uint32_t* err, int sms, cudaStream_t st, const uint8_t* arena) {
   constexpr int kCtasPerSm = 4;  // 64 registers (a small spill), but 32 independent warps per SM
   const int smem = kDecWarps * (int)sizeof(DecWarpSmem);
   static_assert(kCtasPerSm * (kDecWarps * sizeof(DecWarpSmem) + 4096) <= 227 * 1024, "four decode CTAs must fit one SM");
@@ -870,7 +965,7 @@ void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint
   unsigned want = (nblk + per - 1) / per, cap = (unsigned)sms * (unsigned)kCtasPerSm;
   const unsigned grid = want < cap ? (want ? want : 1) : cap;
   block_decode_fused_kernel<kCtasPerSm><<<grid, kDecWarps * 32, smem, st>>>(files_dev, nfiles, blk_off, blk_size, nblk, verify, n_total, out,
-                                                                             blk_state, ticket, run_start, total_out, err);
+                                                                             blk_state, ticket, run_start, total_out, err, arena);
 }
 void launch_gather_values(KeyCols in, const uint64_t* dst_off, uint8_t* dst, cudaStream_t st) {
   if (in.n == 0) return;

@@ -1,0 +1,202 @@
+// toplingdb_b200/csrc/inflate_rules.h — raw DEFLATE (RFC 1951) decoder for one data block, host + device.
+//
+// The reference stores a kZlibCompression block as  varint32 uncompressed_size ‖ raw deflate stream  (Zlib_Compress,
+// util/compression.h:746-826: compress_format_version 2, window_bits -14 = no zlib header / Adler-32) and reads it back with
+// Zlib_Uncompress (:834-924) from UncompressBlockData (table/format.cc:511).  On the device every compressed block is inflated by
+// ONE THREAD (decode.cu inflate_blocks_kernel): the 32 lanes of a warp run the same loops over 32 different blocks, so the decoder
+// is written as plain sequential code without tables larger than a thread's local memory: canonical Huffman decoding by code
+// length (count[] / symbol[] per code, one bit per step).  tests/test_inflate_rules_host.py compiles this header for the host and
+// checks it against zlib on reference-written blocks and on random streams of all three block types.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B200C_INF_HD __host__ __device__
+#else
+#define B200C_INF_HD
+#endif
+
+namespace b200c {
+
+constexpr int kInfMaxBits = 15, kInfMaxLCodes = 286, kInfMaxDCodes = 30, kInfFixLCodes = 288;
+
+struct InfBits {  // LSB-first bit reader over [p, end)
+  const uint8_t* p;
+  const uint8_t* end;
+  uint64_t buf;
+  int cnt;
+  int err;
+};
+B200C_INF_HD inline void inf_refill(InfBits& b) {
+  while (b.cnt <= 56 && b.p < b.end) {
+    b.buf |= (uint64_t)(*b.p++) << b.cnt;
+    b.cnt += 8;
+  }
+}
+B200C_INF_HD inline uint32_t inf_bits(InfBits& b, int n) {  // n <= 16
+  if (b.cnt < n) {
+    inf_refill(b);
+    if (b.cnt < n) {
+      b.err = 1;
+      return 0;
+    }
+  }
+  const uint32_t v = (uint32_t)(b.buf & ((1ull << n) - 1));
+  b.buf >>= n;
+  b.cnt -= n;
+  return v;
+}
+
+struct InfHuff {  // canonical code: count[len] codes of each length, symbols ordered by (length, value)
+  uint16_t count[kInfMaxBits + 1];
+  uint16_t* symbol;
+};
+// lengths[n] -> code; returns 0 for a complete code, > 0 incomplete, < 0 over-subscribed (as zlib's inflate_table reports them)
+B200C_INF_HD inline int inf_build(InfHuff& h, const uint8_t* lengths, int n) {
+  for (int l = 0; l <= kInfMaxBits; l++) h.count[l] = 0;
+  for (int s = 0; s < n; s++) h.count[lengths[s]]++;
+  if (h.count[0] == n) return 0;  // no codes: legal for the distance code of a block without matches
+  int left = 1;
+  for (int l = 1; l <= kInfMaxBits; l++) {
+    left <<= 1;
+    left -= h.count[l];
+    if (left < 0) return left;
+  }
+  uint16_t offs[kInfMaxBits + 1];
+  offs[1] = 0;
+  for (int l = 1; l < kInfMaxBits; l++) offs[l + 1] = (uint16_t)(offs[l] + h.count[l]);
+  for (int s = 0; s < n; s++)
+    if (lengths[s] != 0) h.symbol[offs[lengths[s]]++] = (uint16_t)s;
+  return left;
+}
+B200C_INF_HD inline int inf_decode(InfBits& b, const InfHuff& h) {
+  if (b.cnt < kInfMaxBits) inf_refill(b);
+  int code = 0, first = 0, index = 0;
+  uint64_t buf = b.buf;
+  const int avail = b.cnt;
+  for (int len = 1; len <= kInfMaxBits; len++) {
+    if (len > avail) break;
+    code |= (int)(buf & 1);
+    buf >>= 1;
+    const int count = h.count[len];
+    if (code - count < first) {
+      b.buf = buf;
+      b.cnt = avail - len;
+      return h.symbol[index + (code - first)];
+    }
+    index += count;
+    first += count;
+    first <<= 1;
+    code <<= 1;
+  }
+  b.err = 1;
+  return -1;
+}
+
+// Inflates the raw deflate stream src[0, n) into dst[0, cap); returns the number of bytes written or -1 (malformed stream, output
+// larger than cap, input exhausted).  dst may be global or local memory: back references are read from dst itself.
+B200C_INF_HD inline long inflate_raw(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap) {
+  const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+  const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+  const uint16_t dbase[30] = {1,   2,   3,   4,   5,   7,    9,    13,   17,   25,   33,   49,   65,    97,    129,
+                              193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+  const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+  const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  InfBits b{src, src + n, 0, 0, 0};
+  uint16_t lsym[kInfFixLCodes], dsym[kInfMaxDCodes];
+  uint8_t lengths[kInfFixLCodes + kInfMaxDCodes + 2];
+  InfHuff lc, dc;
+  lc.symbol = lsym;
+  dc.symbol = dsym;
+  uint32_t out = 0;
+  for (;;) {
+    const uint32_t last = inf_bits(b, 1), type = inf_bits(b, 2);
+    if (b.err) return -1;
+    if (type == 0) {  // stored: skip to the byte boundary, LEN, NLEN, bytes
+      b.buf >>= b.cnt & 7;
+      b.cnt -= b.cnt & 7;
+      const uint32_t len = inf_bits(b, 16), nlen = inf_bits(b, 16);
+      if (b.err || len != (~nlen & 0xffffu)) return -1;
+      for (uint32_t i = 0; i < len; i++) {
+        const uint32_t c = inf_bits(b, 8);
+        if (b.err || out >= cap) return -1;
+        dst[out++] = (uint8_t)c;
+      }
+    } else if (type == 1 || type == 2) {
+      if (type == 1) {  // fixed code (RFC 1951 3.2.6)
+        int s = 0;
+        for (; s < 144; s++) lengths[s] = 8;
+        for (; s < 256; s++) lengths[s] = 9;
+        for (; s < 280; s++) lengths[s] = 7;
+        for (; s < kInfFixLCodes; s++) lengths[s] = 8;
+        inf_build(lc, lengths, kInfFixLCodes);
+        for (s = 0; s < kInfMaxDCodes; s++) lengths[s] = 5;
+        inf_build(dc, lengths, kInfMaxDCodes);
+      } else {  // dynamic code: code-length code, then the literal/length and distance code lengths (3.2.7)
+        const int nlen = (int)inf_bits(b, 5) + 257, ndist = (int)inf_bits(b, 5) + 1, ncode = (int)inf_bits(b, 4) + 4;
+        if (b.err || nlen > kInfMaxLCodes || ndist > kInfMaxDCodes) return -1;
+        int i = 0;
+        for (; i < ncode; i++) lengths[order[i]] = (uint8_t)inf_bits(b, 3);
+        for (; i < 19; i++) lengths[order[i]] = 0;
+        if (b.err) return -1;
+        if (inf_build(lc, lengths, 19) != 0) return -1;  // the code-length code must be complete
+        i = 0;
+        while (i < nlen + ndist) {
+          int sym = inf_decode(b, lc);
+          if (sym < 0) return -1;
+          if (sym < 16) {
+            lengths[i++] = (uint8_t)sym;
+          } else {
+            int prev = 0, rep;
+            if (sym == 16) {
+              if (i == 0) return -1;
+              prev = lengths[i - 1];
+              rep = 3 + (int)inf_bits(b, 2);
+            } else if (sym == 17) {
+              rep = 3 + (int)inf_bits(b, 3);
+            } else {
+              rep = 11 + (int)inf_bits(b, 7);
+            }
+            if (b.err || i + rep > nlen + ndist) return -1;
+            while (rep--) lengths[i++] = (uint8_t)prev;
+          }
+        }
+        if (lengths[256] == 0) return -1;  // no end-of-block code
+        // an incomplete code is only legal when it has a single code word (zlib's inflate_table, puff.c)
+        int e = inf_build(lc, lengths, nlen);
+        if (e < 0 || (e > 0 && nlen - lc.count[0] != 1)) return -1;
+        uint8_t* dl = lengths + nlen;
+        e = inf_build(dc, dl, ndist);
+        if (e < 0 || (e > 0 && ndist - dc.count[0] != 1)) return -1;
+      }
+      for (;;) {  // literals and matches until end-of-block
+        int sym = inf_decode(b, lc);
+        if (sym < 0) return -1;
+        if (sym < 256) {
+          if (out >= cap) return -1;
+          dst[out++] = (uint8_t)sym;
+        } else if (sym == 256) {
+          break;
+        } else {
+          sym -= 257;
+          if (sym >= 29) return -1;
+          uint32_t len = lbase[sym] + inf_bits(b, lext[sym]);
+          const int ds = inf_decode(b, dc);
+          if (ds < 0 || ds >= 30) return -1;
+          const uint32_t dist = dbase[ds] + inf_bits(b, dext[ds]);
+          if (b.err || dist > out || out + len > cap) return -1;
+          while (len--) {
+            dst[out] = dst[out - dist];
+            out++;
+          }
+        }
+      }
+    } else {
+      return -1;
+    }
+    if (last) break;
+  }
+  return (long)out;
+}
+
+}  // namespace b200c

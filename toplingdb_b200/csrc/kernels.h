@@ -33,6 +33,7 @@ struct FileDesc {          // one input BlockBasedTable image resident in HBM
   uint32_t gblk_first;     // first global data-block number of this file
   uint32_t nblocks;        // rocksdb.num.data.blocks
   uint32_t index_user_key; // rocksdb.index.key.is.user.key: index separators are user keys (no trailer)
+  const uint8_t* index_ptr; // nullptr: the index block lies at base + index_off; else its inflated copy (index_size = inflated size)
 };
 
 struct BoundKey {              // a user key in column form (grandparent boundary, sub-compaction range bound)
@@ -47,7 +48,15 @@ void launch_index_decode(const FileDesc* files_dev, int nfiles, uint32_t max_blo
                          uint32_t* blk_size, BoundKey start, uint32_t has_start, BoundKey end, uint32_t has_end, uint32_t* err, cudaStream_t st);
 void launch_block_decode_fused(const FileDesc* files_dev, int nfiles, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk,
                                uint32_t verify, uint64_t n_total, KeyColsMut out, unsigned long long* blk_state, uint32_t* ticket,
-                               uint64_t* run_start, uint64_t* total_out, uint32_t* err, int sms, cudaStream_t st);
+                               uint64_t* run_start, uint64_t* total_out, uint32_t* err, int sms, cudaStream_t st,
+                               const uint8_t* arena = nullptr);
+// Inputs with kZlibCompression data blocks (UncompressBlockData, table/format.cc:511): slot[b] = bytes block b needs in the arena of
+// inflated blocks (0: stored uncompressed / outside the key range); after an exclusive scan of the slots, launch_inflate_blocks verifies
+// the stored bytes' checksums, inflates every compressed block into its slot and redirects its handle (blk_off / blk_size) there.
+void launch_block_usize(const FileDesc* files_dev, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk, uint32_t* slot, uint32_t* err,
+                        cudaStream_t st);
+void launch_inflate_blocks(const FileDesc* files_dev, uint64_t* blk_off, uint32_t* blk_size, const uint32_t* slot, const uint64_t* slot_off,
+                           uint32_t nblk, uint8_t* arena, uint32_t verify, uint32_t* err, cudaStream_t st);
 // paranoid_file_checks: entry i of `written` (what the encoder consumed) and of `reread` (the output images decoded again) must be
 // the same key, the same trailer and the same value bytes; a difference sets kErrParanoid
 void launch_flip_byte(uint8_t* p, cudaStream_t st);  // test hook of paranoid_file_checks
