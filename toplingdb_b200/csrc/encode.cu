@@ -727,6 +727,7 @@ __device__ __forceinline__ bool chase_tile(const uint16_t* nxt, const uint32_t* 
 struct StitchSmem {
   uint16_t nxt[kTT];
   uint32_t disk[kTT];
+  uint64_t nd[kTT];       // (nxt << 32) | disk of the tile being chased: one shared-memory load per block link
   WalkState st;
   GpState gp;             // grandparent boundary state of the reference's CompactionOutputs (rules off: untouched)
   uint64_t g, t, tend;    // cursor: next group; next tile / end tile of the group being walked tile by tile
@@ -949,11 +950,56 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
       coop_copy_cg<uint16_t, 16>(s.nxt, wk.nxt + tstart, tl);
       coop_copy_cg<uint32_t, 16>(s.disk, wk.disk + tstart, tl);
       __syncthreads();
+      if (ep.gp.n == 0) {
+        for (uint32_t i = threadIdx.x; i < tl; i += blockDim.x) s.nd[i] = ((uint64_t)s.nxt[i] << 32) | s.disk[i];
+        __syncthreads();
+      }
       if (threadIdx.x == 0) {
         WalkState st = s.st;
         GpState g = s.gp;
-        const bool chased = ep.gp.n ? chase_tile<1>(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, wk.files, nullptr, 0, err, &g)
-                                    : chase_tile<0>(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, wk.files, nullptr, 0, err);
+        bool chased = true;
+        if (ep.gp.n) {
+          chased = chase_tile<1>(s.nxt, s.disk, tstart, tl, n, ep, m, wk, st, wk.files, nullptr, 0, err, &g);
+        } else {
+          // Without grandparents the only events on the chain are the size rule and the end of the stream.  The walk is one thread
+          // chasing dependent loads, so the common link is kept to a single 8-byte shared-memory load and a dozen 32-bit instructions
+          // (the general loop costs ~320 cycles per link, measured with clock64: 58 links per file cut); the block in which an event
+          // happens goes through the exact rule (chase_tile over that one block).
+          const uint32_t nd_base = (uint32_t)__cvta_generic_to_shared(s.nd);
+          const uint64_t left = n - tstart;
+          const uint32_t nlocal = left < 0xffffull ? (uint32_t)left : 0xffffu;  // y >= n  <=>  yr >= nlocal  (0xffff: no block end tabulated)
+          const bool cut_files = ep.output_level != 0;
+          const uint64_t fmax = ep.max_output_file_size;
+          uint32_t x = (uint32_t)(st.a - tstart);
+          uint64_t foff = st.foff, blk = st.blk;
+          while (x < tl) {
+            for (;;) {
+              uint64_t v;
+              asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(nd_base + 8u * x));
+              const uint32_t yr = (uint32_t)(v >> 32), d = (uint32_t)v;
+              const uint64_t nf = foff + d;
+              if (yr <= x || yr >= nlocal || (cut_files && nf >= fmax)) break;  // an event (or a broken link): exact rule below
+              foff = nf;
+              blk++;
+              x = yr;
+              if (x >= tl) break;
+            }
+            if (x >= tl) break;
+            st.a = tstart + x;
+            st.foff = foff;
+            st.blk = blk;
+            chased = chase_tile<0>(s.nxt, s.disk, tstart, x + 1, n, ep, m, wk, st, wk.files, nullptr, 0, err);
+            if (!chased || st.a >= n) break;
+            x = (uint32_t)(st.a - tstart);  // (behind the tile when the block ended there: the loop ends)
+            foff = st.foff;
+            blk = st.blk;
+          }
+          if (chased && st.a < n && x >= tl && st.a < tstart + x) {
+            st.a = tstart + x;
+            st.foff = foff;
+            st.blk = blk;
+          }
+        }
         s.gp = g;
         if (!chased) {
           atomicOr(err, kErrBlockTooLong);
@@ -2301,7 +2347,12 @@ void launch_encode_emit(KeyCols m, EncodeParams ep, EncodeWork w, uint64_t nbloc
   if (per_sm < 1) per_sm = 1;
   if (per_sm > (unsigned)occ) per_sm = (unsigned)occ;
   const uint64_t want = (nblocks + kEmitWarps - 1) / kEmitWarps;
-  const uint64_t cap = (uint64_t)sms * per_sm;
+  // The persistent CTAs own every register of the SMs they sit on, so the side stream's kernels (per-file statistics, index blocks:
+  // ~0.17 ms on an idle device) queue behind the last emit CTA.  Leaving CTA slots free for them (B200C_EMIT_RESERVE = n slots) was
+  // measured and does not pay: 8 slots cost the emit kernel 0.12 ms, 16 / 32 slots changed nothing (profiles/README.md).
+  static const int reserve = getenv("B200C_EMIT_RESERVE") ? atoi(getenv("B200C_EMIT_RESERVE")) : 0;
+  uint64_t cap = (uint64_t)sms * per_sm;
+  if (reserve > 0 && cap > 4 * (uint64_t)reserve) cap -= (uint64_t)reserve;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   if (occ == 4) encode_emit_kernel<4><<<grid, kEmitWarps * 32, smem, st>>>(m, ep, w, nblocks, out_base, slot, err);
   else if (occ == 5) encode_emit_kernel<5><<<grid, kEmitWarps * 32, smem, st>>>(m, ep, w, nblocks, out_base, slot, err);

@@ -213,8 +213,8 @@ __device__ __forceinline__ void msel_grouped(const KeyCols& in, const GroupLanes
 // One warp resolves `chunk` CONSECUTIVE boundaries: the first one with the two-level search, every further one starting from
 // its predecessor's split -- between rank d and rank d' >= d every run advances by at most d' - d entries, so the brackets are
 // kMergeTile wide and lie in cache lines the previous search just touched.  The kernel is one chain of dependent loads per warp
-// (about 135 for the two-level search, 55 for every further boundary): the chunk is the smallest one that still keeps all warps
-// of the grid resident at once (32 warps per SM at 64 registers).
+// (about 135 for the two-level search, 55 for every further boundary), so the chunk is small: measured on the cfg2 job (18.7 k
+// boundaries) 433 us with 4 boundaries per warp, 379 us with 3, 428 us with 2 (profiles/README.md).
 __global__ void __launch_bounds__(128)
 merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint32_t gshift, uint64_t n_total,
                                uint64_t ntiles, uint64_t* __restrict__ splits, uint32_t* __restrict__ err, uint32_t chunk) {
@@ -320,14 +320,12 @@ merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint3
 constexpr uint32_t kSnapCache = 16;
 struct TileSmem {
   uint64_t hi[kMT], lo[kMT], tr[kMT];
-  uint32_t lw[kMT + kMT / 32];     // merge order as one sortable word per entry: (key proxy << kIdxBits) | load position; PH() pads
+  uint16_t idx[kMT];               // merge order: idx[o] = load position of the o-th smallest key
   uint8_t ulen[kMT];
   uint8_t verd[kMT];               // per merged position: verdict of the serial SingleDelete walk (bit 7: walked)
   uint32_t seg[kMaxRuns + 1];      // segment starts in load order
   uint32_t lst[2][kMaxRuns + 2];   // list bounds per merge round (ping-pong)
   uint64_t sbeg[kMaxRuns];         // absolute index of each segment's first element
-  ulonglong2 kfirst[kMaxRuns], klast[kMaxRuns];  // first / last key prefix of each segment (range of the tile's keys)
-  uint32_t cp;                     // leading bits of the 128-bit key prefix that all keys of the tile share
   uint64_t snaps[kSnapCache];      // cached snapshots (the first kSnapCache)
   unsigned long long red[8];       // per-CTA counter staging
   unsigned long long stat[5];      // statistics of the tile's output entries (TileStat)
@@ -347,21 +345,9 @@ __device__ __forceinline__ Key skey(const TileSmem& s, uint32_t id) {
   k.ulen = s.ulen[id] & 0x3fu;
   return k;
 }
-// The merge rounds permute one 32-bit word per entry: the kProxyBits key bits behind the tile's common key prefix (a monotone map
-// of the 128-bit prefix inside the tile's key range) above the entry's load position.  Two words with different proxies order their
-// keys without touching the key arrays; equal proxies (same user key in two runs, or a rare collision) fall back to the full compare.
-// List position e lives in word e + e / 32: a thread owns kMV = 8 consecutive positions, and the padding puts the 32 lanes of one
-// store on 32 different banks.
-constexpr uint32_t kIdxBits = 11, kIdxMask = (1u << kIdxBits) - 1, kProxyBits = 32 - kIdxBits;
-static_assert(kMT <= (1 << kIdxBits), "load position must fit the word");
-__device__ __forceinline__ uint32_t PH(uint32_t e) { return e + (e >> 5); }
-// bits [cp, cp + kProxyBits) of the 128-bit value hi:lo
-__device__ __forceinline__ uint32_t key_proxy(uint64_t hi, uint64_t lo, uint32_t cp) {
-  uint64_t v;
-  if (cp >= 64) v = cp >= 128 ? 0ull : lo << (cp - 64);
-  else v = cp ? (hi << cp) | (lo >> (64 - cp)) : hi;
-  return (uint32_t)(v >> (64 - kProxyBits));
-}
+// List positions are XOR-swizzled inside 16-element groups: a thread owns kMV = 8 consecutive list positions, and with
+// the plain layout the 32 lanes of one store to idx[] would fall on only eight banks (4-way conflict).
+__device__ __forceinline__ uint32_t PH(uint32_t e) { return e ^ ((e >> 4) & 15u); }
 // keys with equal high words: is the key at load position ib strictly before the one at ia?
 __device__ __forceinline__ bool tie_less(const TileSmem& s, uint32_t ib, uint32_t ia) {
   const uint64_t lb = s.lo[ib], la = s.lo[ia];
@@ -374,14 +360,6 @@ __device__ __forceinline__ bool tie_less(const TileSmem& s, uint32_t ib, uint32_
 __device__ __forceinline__ bool id_less(const TileSmem& s, uint32_t ib, uint64_t hb, uint32_t ia, uint64_t ha) {
   if (hb != ha) return hb < ha;
   return tie_less(s, ib, ia);
-}
-
-// is the entry of word wb strictly before the entry of word wa?
-__device__ __forceinline__ bool word_less(const TileSmem& s, uint32_t wb, uint32_t wa) {
-  const uint32_t pb = wb >> kIdxBits, pa = wa >> kIdxBits;
-  if (pb != pa) return pb < pa;
-  const uint32_t ib = wb & kIdxMask, ia = wa & kIdxMask;
-  return id_less(s, ib, s.hi[ib], ia, s.hi[ia]);
 }
 
 struct PairState {
@@ -411,8 +389,8 @@ __device__ __noinline__ void init_pair(const TileSmem& s, const uint32_t* lst, u
   uint32_t lo = diag > bn ? diag - bn : 0, hi = diag < an ? diag : an;
   while (lo < hi) {
     uint32_t mid = (lo + hi) >> 1;
-    const uint32_t wa = s.lw[PH(a0 + mid)], wb = s.lw[PH(a1 + diag - 1 - mid)];
-    if (!word_less(s, wb, wa)) lo = mid + 1;  // a <= b: a goes first (stable, lower run index wins ties)
+    const uint32_t ia = s.idx[PH(a0 + mid)], ib = s.idx[PH(a1 + diag - 1 - mid)];
+    if (!id_less(s, ib, s.hi[ib], ia, s.hi[ia])) lo = mid + 1;  // a <= b: a goes first (stable, lower run index wins ties)
     else hi = mid;
   }
   ps->ai = a0 + lo;
@@ -515,11 +493,11 @@ __device__ __noinline__ void sd_walk_tile(TileSmem& s, const KeyCols& in, const 
   for (int x = 0; x < kMV; x++) {
     const uint32_t o = t * kMV + x;
     if (o >= cnt) break;
-    const uint32_t id0 = (s.lw[PH(o)] & kIdxMask);
+    const uint32_t id0 = s.idx[PH(o)];
     const Key k0 = skey(s, id0);
     bool head = true;
     if (o > 0) {
-      const Key p = skey(s, (s.lw[PH(o - 1)] & kIdxMask));
+      const Key p = skey(s, s.idx[PH(o - 1)]);
       head = !(p.hi == k0.hi && p.lo == k0.lo && p.ulen == k0.ulen);
     } else if (s.has_pred && s.pred.hi == k0.hi && s.pred.lo == k0.lo && s.pred.ulen == k0.ulen) {
       atomicOr(err, (uint32_t)kErrInternal);  // the partition keeps keys inside one tile in this mode
@@ -529,7 +507,7 @@ __device__ __noinline__ void sd_walk_tile(TileSmem& s, const KeyCols& in, const 
     uint32_t n = 0;
     bool has_sd = false;
     for (uint32_t q = o; q < cnt; q++) {
-      const uint32_t id = (s.lw[PH(q)] & kIdxMask);
+      const uint32_t id = s.idx[PH(q)];
       if (q != o && !(s.hi[id] == k0.hi && s.lo[id] == k0.lo && (s.ulen[id] & 0x3fu) == k0.ulen)) break;
       const uint64_t tr = s.tr[id];
       has_sd = has_sd || (tr & 0xff) == kTypeSingleDeletion;
@@ -597,7 +575,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   if (tile >= ntiles) return;
   // last element before the split, per run: staged in arrays the load phase overwrites later (keeps 3 CTAs per SM)
   Key* cand = reinterpret_cast<Key*>(s.hi);
-  uint32_t* cand_ok = s.lw;
+  uint32_t* cand_ok = reinterpret_cast<uint32_t*>(s.idx);
   // ---- segment table; the tile's predecessor in merged order (= largest element before the split) is fetched here
   // too, one lane per run, so its DRAM round trip overlaps the split loads
   if (t < k) {
@@ -607,10 +585,6 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     s.lst[1][t] = (uint32_t)(s1 - s0);  // lengths, scanned below
     cand_ok[t] = s0 != 0;
     if (s0 != 0) cand[t] = load_key(in, b0 - 1);
-    if (s1 > s0) {
-      s.kfirst[t] = in.pfx[b0];
-      s.klast[t] = in.pfx[b0 + (s1 - s0) - 1];
-    }
   }
   __syncthreads();
   if (t == 0) {
@@ -626,17 +600,6 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
       atomicOr(err, kErrKeyOrder);
       s.seg[k] = 0;
     }
-    {  // key range of the tile -> number of leading key bits every entry shares (the proxies start behind them)
-      uint64_t nhi = ~0ull, nlo = ~0ull, xhi = 0, xlo = 0;
-      for (uint32_t r = 0; r < k; r++) {
-        if (s.lst[1][r] == 0) continue;
-        const ulonglong2 a = s.kfirst[r], b = s.klast[r];
-        if (a.x < nhi || (a.x == nhi && a.y < nlo)) nhi = a.x, nlo = a.y;
-        if (b.x > xhi || (b.x == xhi && b.y > xlo)) xhi = b.x, xlo = b.y;
-      }
-      const uint64_t dh = nhi ^ xhi, dl = nlo ^ xlo;
-      s.cp = acc == 0 ? 0u : dh ? (uint32_t)__clzll((long long)dh) : dl ? 64u + (uint32_t)__clzll((long long)dl) : 128u;
-    }
     s.has_pred = 0;
     for (uint32_t r = 0; r < k; r++) {
       if (!cand_ok[r]) continue;
@@ -649,7 +612,6 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   }
   __syncthreads();
   const uint32_t cnt = s.seg[k];
-  const uint32_t cp = s.cp;
   bool tile_sd = false;  // some entry of the tile is a kTypeSingleDeletion
   // ---- coalesced load of the k segments.  All of a thread's loads are issued before the first one is consumed: a
   // warp issues in order, so a load-then-store loop body would pay one DRAM round trip per iteration.
@@ -682,7 +644,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         s.tr[i] = ltr[j];
         if (kSD) my_sd = my_sd || (ltr[j] & 0xff) == kTypeSingleDeletion;
         s.ulen[i] = (uint8_t)(meta_ulen(lmt[j]) | (meta_vlen(lmt[j]) == 0 ? 0x80u : 0u));  // bit 7: empty value (compaction filter); bit 6 is set later: value removed by the filter
-        s.lw[PH(i)] = (key_proxy(lp[j].x, lp[j].y, cp) << kIdxBits) | i;
+        s.idx[PH(i)] = (uint16_t)i;
       }
     }
     if (kSD) tile_sd = __syncthreads_or(my_sd) != 0;  // (also the barrier behind the load phase)
@@ -693,12 +655,13 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
   int cur = 0;
   while (nlists > 1) {
     const uint32_t* lst = s.lst[cur];
-    uint32_t rid[kMV];
+    uint16_t rid[kMV];
     const uint32_t o0 = t * kMV;
     PairState ps;
     ps.pend = 0;
     ps.ai = ps.a1 = ps.bi = ps.b1 = 0;
-    uint32_t wa = 0, wb = 0;
+    uint32_t ia = 0, ib = 0;
+    uint64_t ha = 0, hb = 0;
     bool va = false, vb = false;
 #pragma unroll
     for (int x = 0; x < kMV; x++) {
@@ -709,19 +672,31 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
           init_pair(s, lst, nlists, o, &ps);
           va = ps.ai < ps.a1;
           vb = ps.bi < ps.b1;
-          if (va) wa = s.lw[PH(ps.ai)];
-          if (vb) wb = s.lw[PH(ps.bi)];
+          if (va) {
+            ia = s.idx[PH(ps.ai)];
+            ha = s.hi[ia];
+          }
+          if (vb) {
+            ib = s.idx[PH(ps.bi)];
+            hb = s.hi[ib];
+          }
         }
-        const bool take_a = !vb || (va && !word_less(s, wb, wa));
-        rid[x] = take_a ? wa : wb;
+        const bool take_a = !vb || (va && !id_less(s, ib, hb, ia, ha));
+        rid[x] = (uint16_t)(take_a ? ia : ib);
         if (take_a) {
           ps.ai++;
           va = ps.ai < ps.a1;
-          if (va) wa = s.lw[PH(ps.ai)];
+          if (va) {
+            ia = s.idx[PH(ps.ai)];
+            ha = s.hi[ia];
+          }
         } else {
           ps.bi++;
           vb = ps.bi < ps.b1;
-          if (vb) wb = s.lw[PH(ps.bi)];
+          if (vb) {
+            ib = s.idx[PH(ps.bi)];
+            hb = s.hi[ib];
+          }
         }
       }
     }
@@ -729,7 +704,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
 #pragma unroll
     for (int x = 0; x < kMV; x++) {
       uint32_t o = o0 + x;
-      if (o < cnt) s.lw[PH(o)] = rid[x];
+      if (o < cnt) s.idx[PH(o)] = rid[x];
     }
     // next round's list bounds
     uint32_t nn = (nlists + 1) >> 1;
@@ -765,7 +740,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     otr[x] = 0;
     oid[x] = 0;
     if (o >= cnt) continue;
-    const uint32_t id = (s.lw[PH(o)] & kIdxMask);
+    const uint32_t id = s.idx[PH(o)];
     oid[x] = (uint16_t)id;
     Key c = skey(s, id);
     if (kSD && tile_sd && (s.verd[o] & 0x80u)) {  // a version of a key with a SingleDelete: the serial walk decided
@@ -788,7 +763,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
     }
     Key p;
     bool has_prev = true;
-    if (o > 0) p = skey(s, (s.lw[PH(o - 1)] & kIdxMask));
+    if (o > 0) p = skey(s, s.idx[PH(o - 1)]);
     else {
       p = s.pred;
       has_prev = s.has_pred != 0;
@@ -820,7 +795,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         uint32_t head_id = 0;
         bool have = false;
         while (q >= 0) {
-          const uint32_t hid = (s.lw[PH(q)] & kIdxMask);
+          const uint32_t hid = s.idx[PH(q)];
           Key h = skey(s, hid);
           uint64_t d2;
           bool same_grp = h.hi == c.hi && h.lo == c.lo && h.ulen == c.ulen &&
@@ -836,7 +811,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
           // the head is filtered if it is the first version of its user key: look at the entry in front of it
           bool first_occ;
           if (q >= 0) {
-            const Key b = skey(s, (s.lw[PH(q)] & kIdxMask));
+            const Key b = skey(s, s.idx[PH(q)]);
             first_occ = !(b.hi == c.hi && b.lo == c.lo && b.ulen == c.ulen);
           } else {
             first_occ = !(s.has_pred && s.pred.hi == c.hi && s.pred.lo == c.lo && s.pred.ulen == c.ulen);
@@ -858,7 +833,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
       // :947-990 keep the tombstone only if an older stripe still holds a version of this user key
       bool resolved = false;
       for (uint32_t q = o + 1; q < cnt; q++) {
-        Key nx = skey(s, (s.lw[PH(q)] & kIdxMask));
+        Key nx = skey(s, s.idx[PH(q)]);
         if (!(nx.hi == c.hi && nx.lo == c.lo && nx.ulen == c.ulen)) {
           resolved = true;
           break;
@@ -919,7 +894,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
 #pragma unroll
   for (int x = 0; x < kMV; x++) {
     if ((keep_mask >> x) & 1) {
-      s.lw[PH(rank)] = oid[x];
+      s.idx[PH(rank)] = oid[x];
       s.tr[oid[x]] = otr[x];  // each load position is owned by exactly one merged position
       if ((keep_mask >> (24 + x)) & 1) s.ulen[oid[x]] |= 0x40u;
       rank++;
@@ -939,7 +914,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
       gm[j] = 0;
       gp[j] = 0;
       if (i < kept_total) {
-        const uint32_t pos = (s.lw[PH(i)] & kIdxMask);
+        const uint32_t pos = s.idx[PH(i)];
         const uint64_t src = col_of(pos);
         gp[j] = (uint16_t)pos;
         gv[j] = in.vref[src];
@@ -995,7 +970,7 @@ merge_tiles_kernel(KeyCols in, RunBounds runs, MergeParams mp, uint64_t n_total,
         // encoded size against the previous OUTPUT entry (BlockBuilder::AddWithLastKey); the tile's first entry is left to
         // merge_sizes_fix_kernel: its predecessor is the last survivor of an earlier tile
         if (fold && i > 0) {
-          const uint32_t pp = (s.lw[PH(i - 1)] & kIdxMask);
+          const uint32_t pp = s.idx[PH(i - 1)];
           const uint32_t sh = shared_prefix(chi, clo, cul, ctr, s.hi[pp], s.lo[pp], s.ulen[pp] & 0x3fu, s.tr[pp]);
           const uint32_t s1 = entry_size(sh, cul + 8, vlen);
           ms.esz[dst] = s1;
@@ -1171,8 +1146,8 @@ void launch_merge_partition(KeyCols in, RunBounds runs, uint32_t nruns, uint64_t
     while ((kp2 << (gshift + 1)) <= 32) gshift++;  // lanes per run = 32 / pow2(nruns)
     static const uint32_t chunk_env = getenv("B200C_PART_CHUNK") ? (uint32_t)atoi(getenv("B200C_PART_CHUNK")) : 0;  // tuning knob
     uint32_t chunk = chunk_env;
-    if (chunk == 0) {  // all warps resident at once: 148 SMs x 32 warps (64 registers per thread)
-      chunk = (uint32_t)((warps + 148u * 32u - 1) / (148u * 32u));
+    if (chunk == 0) {  // about one and a half waves of warps (32 resident per SM at 64 registers)
+      chunk = (uint32_t)((warps + 148u * 48u - 1) / (148u * 48u));
       if (chunk > 4) chunk = 4;
     }
     if (chunk < 1) chunk = 1;
