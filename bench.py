@@ -45,48 +45,71 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of one GPU, sampled every ~2 ms from a thread.  NVML is initialised by the constructor (it takes
+    longer than a whole timed region), sampling starts with start(), and summary() only counts the samples taken between
+    mark_begin() and mark_end() -- the timed region(s)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
-
-    def run(self):
-        # NVML in-process (a sample every ~2 ms, so that even a 50 ms timed region is covered); nvidia-smi as a fallback
+        self.windows = []  # [begin, end] of the timed regions (perf_counter)
+        self.nvml = None
         try:
             import pynvml as N
             N.nvmlInit()
-            h = N.nvmlDeviceGetHandleByIndex(self.index)
-            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
-            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
-            bits = [(0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6)]  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap -> row columns
-            while not self.stop_flag:
-                r = int(get_reasons(h))
-                row = [str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx), "0", "", "", "", ""]
-                for bit, col in bits:
-                    row[col] = "Active" if r & bit else "Not Active"
-                self.rows.append(row)
-                time.sleep(0.002)
-            return
+            self.handle = N.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = N.nvmlDeviceGetMaxClockInfo(self.handle, N.NVML_CLOCK_SM)
+            self.get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nvml = N
         except Exception:
-            pass
+            self.nvml = None
+
+    def mark_begin(self):
+        self.windows.append([time.perf_counter(), float("inf")])
+
+    def mark_end(self):
+        self.windows[-1][1] = time.perf_counter()
+
+    def sample_nvml(self):
+        N = self.nvml
+        bits = [(0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6)]  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap -> row columns
+        r = int(self.get_reasons(self.handle))
+        row = [str(N.nvmlDeviceGetClockInfo(self.handle, N.NVML_CLOCK_SM)), str(self.max_mhz), "0", "", "", "", ""]
+        for bit, col in bits:
+            row[col] = "Active" if r & bit else "Not Active"
+        return row
+
+    def run(self):
+        if self.nvml is not None:
+            while not self.stop_flag:
+                try:
+                    self.rows.append((time.perf_counter(), self.sample_nvml()))
+                except Exception:
+                    break
+                time.sleep(0.002)
+            if self.rows:
+                return
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                    self.rows.append((time.perf_counter(), [x.strip() for x in out.split(",")]))
             except Exception:
                 pass
             time.sleep(0.05)
 
     def summary(self):
-        if not self.rows:
+        wins = self.windows or [[0.0, float("inf")]]
+        rows = [r for t, r in self.rows if any(lo <= t <= hi for lo, hi in wins)]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows if len(r) > 3 + i)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "sm_min_mhz": min(sm) if sm else None, "timed_regions": len(self.windows)}
 
 
 def reference_arm(args, rank, world):
@@ -188,22 +211,23 @@ def concurrent_jobs_arm(args, w, rank, world, local, numa_info):
         if errs:
             raise errs[0]
 
+    sampler = ClockSampler(local)
+    sampler.start()  # (samples outside the timed regions are dropped by summary())
     for _ in range(args.warmup):
         run_all(jobs)
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         run_all(jobs)
     torch.cuda.synchronize()
     ev1.record()
     barrier()
+    sampler.mark_end()
     wall_s = (time.perf_counter() - t0) / args.steps
     step_s = ev0.elapsed_time(ev1) / 1e3 / args.steps
-    sampler.stop_flag = True
     out_bytes = sum(j.output_meta(i).file_size for j in jobs for i in range(j.output_count()))
     nout = sum(j.output_count() for j in jobs)
     launches = sum(j.stats().kernel_launches for j in jobs)
@@ -233,11 +257,13 @@ def concurrent_jobs_arm(args, w, rank, world, local, numa_info):
             ejs.append(ej)
         run_all(ejs)
         barrier()
+        sampler.mark_begin()
         t0 = time.perf_counter()
         reps = max(2, min(args.steps, 4))
         for _ in range(reps):
             run_all(ejs)
         barrier()
+        sampler.mark_end()
         es = (time.perf_counter() - t0) / reps
         if world > 1:
             tt = torch.tensor([es], dtype=torch.float64, device="cuda")
@@ -247,6 +273,7 @@ def concurrent_jobs_arm(args, w, rank, world, local, numa_info):
                "ms_per_step": round(es * 1e3, 2), "steps": reps, "jobs_in_flight": J}
         for ej in ejs:
             ej.close()
+    sampler.stop_flag = True
     if rank == 0:
         line = {"metric": "compaction_input_kv_MB_per_s", "value": round(value, 1), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(step_s * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -325,13 +352,14 @@ def main():
         if world > 1:
             sharding.exchange_boundaries(sharding.job_boundary(job), device=torch.device("cuda", local))
 
+    sampler = ClockSampler(local)
+    sampler.start()  # (samples outside the timed regions are dropped by summary())
     for _ in range(args.warmup):
         job.run()
         boundary_exchange()
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     dev_us, ktimes = [], {}
+    sampler.mark_begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         job.run()
@@ -341,8 +369,8 @@ def main():
         for name, us in job.kernel_times():
             ktimes.setdefault(name, []).append(us)
     barrier()
+    sampler.mark_end()
     wall = time.perf_counter() - t0
-    sampler.stop_flag = True
     st = job.stats()
     nout = job.output_count()
     out_bytes = sum(job.output_meta(i).file_size for i in range(nout))
@@ -468,6 +496,7 @@ def main():
                 errs.append(e)
 
         barrier()
+        sampler.mark_begin()
         t0 = time.perf_counter()
         ths = [threading.Thread(target=worker, args=(ej,)) for ej in ejs]
         for th in ths:
@@ -475,6 +504,7 @@ def main():
         for th in ths:
             th.join()
         barrier()
+        sampler.mark_end()
         es = (time.perf_counter() - t0) / esteps
         if errs:
             raise errs[0]
@@ -488,6 +518,7 @@ def main():
         for ej in ejs:
             ej.close()
 
+    sampler.stop_flag = True
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -8,9 +8,11 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <unordered_map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200c.h"
@@ -427,7 +429,8 @@ int host_inflated_index(b200c_job* j, const Input& in, std::vector<uint8_t>* out
   }
   if (u < 8 || u > (1ull << 31)) return fail(B200C_ERR_CORRUPTION, "compressed index block announces a bad size");
   out->resize(u);
-  if (b200c::inflate_raw(cp + h, (uint32_t)(size - h), out->data(), (uint32_t)u) != (long)u)
+  std::unique_ptr<b200c::InfWork> iw(new b200c::InfWork);
+  if (b200c::inflate_raw(cp + h, (uint32_t)(size - h), out->data(), (uint32_t)u, iw.get()) != (long)u)
     return fail(B200C_ERR_CORRUPTION, "compressed index block does not inflate to its announced size");
   return B200C_OK;
 }
@@ -924,20 +927,35 @@ int run_job(b200c_job* j, int until) {
     fd.nblocks = (uint32_t)in.tail.num_data_blocks;
     fd.index_user_key = in.tail.index_key_is_user_key ? 1u : 0u;
     fd.index_ptr = nullptr;
-    if (input_is_compressed(in)) {  // kZlibCompression inputs: data blocks are inflated on the device, the index block here
-      any_compressed = true;
-      if (int rc2 = host_inflated_index(j, in, &in.index_host)) return rc2;
-      if (!in.index_host.empty()) {
-        CU(in.index_inflated.reserve(in.index_host.size() + 64));
-        CU(cudaMemcpyAsync(in.index_inflated.p, in.index_host.data(), in.index_host.size(), cudaMemcpyHostToDevice, st));
-        fd.index_ptr = in.index_inflated.as<uint8_t>();
-        fd.index_size = (uint32_t)in.index_host.size();
-      }
-    }
+    if (input_is_compressed(in)) any_compressed = true;  // kZlibCompression: data blocks are inflated on the device, the index block below
     nblk += in.tail.num_data_blocks;
     n_props += in.tail.num_entries;
     in_bytes += in.len;
     if (in.tail.index_size > 0xffffffffull) return fail(B200C_ERR_NOT_SUPPORTED, "index block >= 4 GiB");
+  }
+  if (any_compressed) {
+    // compressed index blocks: inflated on the host, one thread per file (a 256 MiB file has ~3.5 MB of index: ~17 ms on one core)
+    std::vector<int> rcs(k, B200C_OK);
+    std::vector<std::string> msgs(k);
+    std::vector<std::thread> pool;
+    for (int i = 0; i < k; i++) {
+      if (!input_is_compressed(j->inputs[i])) continue;
+      pool.emplace_back([&, i]() {
+        cudaSetDevice(P.device);
+        rcs[i] = host_inflated_index(j, j->inputs[i], &j->inputs[i].index_host);
+        if (rcs[i]) msgs[i] = g_err;  // (the message is per thread)
+      });
+    }
+    for (auto& th : pool) th.join();
+    for (int i = 0; i < k; i++) {
+      if (rcs[i]) return fail(rcs[i], msgs[i]);
+      Input& in = j->inputs[i];
+      if (!input_is_compressed(in) || in.index_host.empty()) continue;
+      CU(in.index_inflated.reserve(in.index_host.size() + 64));
+      CU(cudaMemcpyAsync(in.index_inflated.p, in.index_host.data(), in.index_host.size(), cudaMemcpyHostToDevice, st));
+      fds[i].index_ptr = in.index_inflated.as<uint8_t>();
+      fds[i].index_size = (uint32_t)in.index_host.size();
+    }
   }
   if (nblk > 0xfffffff0ull) return fail(B200C_ERR_NOT_SUPPORTED, "too many data blocks");
   j->nblk_in = nblk;

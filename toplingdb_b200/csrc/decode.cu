@@ -904,28 +904,68 @@ __global__ void verify_compressed_kernel(const FileDesc* __restrict__ files, con
     if (lane == 0 && got != ld_u32(p + size + 1)) atomicOr(err, kErrChecksum);
   }
 }
-__global__ void __launch_bounds__(128)
+// One WARP per compressed block.  Inflating is control flow all the way down (a different path per symbol), so 32 blocks in the 32
+// lanes of a warp serialise on each other -- measured: 20 ms per warp whatever the tables cost, because the lanes' byte-by-byte
+// match copies through global memory (a dependent L2 round trip per byte) take turns.  Here lane 0 runs the decoder with its tables
+// AND its output window in shared memory (a match copy is a shared-memory load + store), and the whole warp then moves the inflated
+// block to the arena with coalesced stores; other warps of the SM hide the single lane's latency.  Blocks larger than the window
+// are inflated straight into the arena.
+constexpr int kInflateWarps = 8;
+constexpr uint32_t kInflateWindow = 8192;  // bytes of inflated block a warp keeps in shared memory
+struct InflateWarpSmem {
+  InfWork wk;
+  uint8_t pad[12];  // keeps the window 16-byte aligned
+  uint8_t out[kInflateWindow + 16];
+};
+static_assert(sizeof(InflateWarpSmem) % 16 == 0, "warp slices stay 16-byte aligned");
+__global__ void __launch_bounds__(kInflateWarps * 32)
 inflate_blocks_kernel(const FileDesc* __restrict__ files, uint64_t* __restrict__ blk_off, uint32_t* __restrict__ blk_size,
                       const uint32_t* __restrict__ slot, const uint64_t* __restrict__ slot_off, uint32_t nblk, uint8_t* __restrict__ arena,
                       uint32_t* __restrict__ err) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nblk || slot[b] == 0) return;
-  const uint64_t bo = blk_off[b];
-  const uint8_t* p = files[bo >> kBlkFileShift].base + (bo & kBlkOffMask);
-  const uint32_t size = blk_size[b];
-  uint32_t u = 0, h = 0;
-  compressed_prefix(p, size, &u, &h);
-  uint8_t* dst = arena + slot_off[b];
-  const long n = inflate_raw(p + h, size - h, dst, u);
-  if (n != (long)u) {
-    atomicOr(err, kErrCorruptBlock);
-    blk_size[b] = 0;  // (an empty block: the job fails anyway)
-    return;
+  extern __shared__ __align__(16) uint8_t inflate_smem[];
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  InflateWarpSmem& ws = reinterpret_cast<InflateWarpSmem*>(inflate_smem)[w];
+  for (uint32_t b = blockIdx.x * kInflateWarps + w; b < nblk; b += gridDim.x * kInflateWarps) {
+    if (slot[b] == 0) continue;
+    const uint64_t bo = blk_off[b];
+    const uint8_t* p = files[bo >> kBlkFileShift].base + (bo & kBlkOffMask);
+    const uint32_t size = blk_size[b];
+    uint32_t u = 0, h = 0;
+    compressed_prefix(p, size, &u, &h);
+    uint8_t* dst = arena + slot_off[b];
+    const bool windowed = u <= kInflateWindow;
+    long n = 0;
+    if (lane == 0) n = inflate_raw(p + h, size - h, windowed ? ws.out : dst, u, &ws.wk);
+    n = __shfl_sync(0xffffffffu, n, 0);
+    if (n != (long)u) {
+      if (lane == 0) {
+        atomicOr(err, kErrCorruptBlock);
+        blk_size[b] = 0;  // (an empty block: the job fails anyway)
+      }
+      __syncwarp();
+      continue;
+    }
+    __syncwarp();
+    if (windowed) {  // slots are 16-byte aligned and hold u + 5 bytes rounded up to 16
+      if (lane == 0) {
+        ws.out[u] = 0;  // trailer of an uncompressed block; the checksum bytes are never read (cksum = 0 for arena blocks)
+        ws.out[u + 1] = ws.out[u + 2] = ws.out[u + 3] = ws.out[u + 4] = 0;
+      }
+      __syncwarp();
+      const uint32_t nvec = (u + 5 + 15) >> 4;
+      const uint4* src4 = reinterpret_cast<const uint4*>(ws.out);
+      uint4* dst4 = reinterpret_cast<uint4*>(dst);
+      for (uint32_t i = lane; i < nvec; i += 32) dst4[i] = src4[i];
+    } else if (lane == 0) {
+      dst[u] = 0;
+      dst[u + 1] = dst[u + 2] = dst[u + 3] = dst[u + 4] = 0;
+    }
+    if (lane == 0) {
+      blk_off[b] = (bo & ~kBlkOffMask) | kBlkArenaBit | slot_off[b];
+      blk_size[b] = u;
+    }
+    __syncwarp();  // the window is free for the next block
   }
-  dst[u] = 0;  // trailer of an uncompressed block; the checksum bytes are never read (cksum = 0 for arena blocks)
-  dst[u + 1] = dst[u + 2] = dst[u + 3] = dst[u + 4] = 0;
-  blk_off[b] = (bo & ~kBlkOffMask) | kBlkArenaBit | slot_off[b];
-  blk_size[b] = u;
 }
 void launch_block_usize(const FileDesc* files_dev, const uint64_t* blk_off, const uint32_t* blk_size, uint32_t nblk, uint32_t* slot, uint32_t* err,
                         cudaStream_t st) {
@@ -939,7 +979,16 @@ void launch_inflate_blocks(const FileDesc* files_dev, uint64_t* blk_off, uint32_
     if (g > 148 * 8) g = 148 * 8;
     verify_compressed_kernel<<<g, 256, 0, st>>>(files_dev, blk_off, blk_size, slot, nblk, err);
   }
-  inflate_blocks_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(files_dev, blk_off, blk_size, slot, slot_off, nblk, arena, err);
+  static PerDeviceFlag attr;
+  const uint64_t dev_bit = attr.bit_of_current_device();
+  const size_t smem = sizeof(InflateWarpSmem) * kInflateWarps;
+  if (!attr.is_set(dev_bit)) {
+    cudaFuncSetAttribute(inflate_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr.set(dev_bit);
+  }
+  unsigned grid = (nblk + kInflateWarps - 1) / kInflateWarps;
+  if (grid > 148u * 3u) grid = 148u * 3u;  // three CTAs (24 warps) per SM, each warp walks its share of the blocks
+  inflate_blocks_kernel<<<grid, kInflateWarps * 32, smem, st>>>(files_dev, blk_off, blk_size, slot, slot_off, nblk, arena, err);
 }
 
 // ---------------------------------------------------------------------------------------------- host launchers

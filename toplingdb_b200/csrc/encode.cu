@@ -947,11 +947,15 @@ encode_stitch_kernel(KeyCols m, EncodeParams ep, EncodeWork wk, uint64_t n, uint
       const uint64_t tstart = ridx * (uint64_t)kTT;
       const uint32_t tl = (uint32_t)(((tstart + kTT) < n ? (tstart + kTT) : n) - tstart);
       TR_BEGIN();
-      coop_copy_cg<uint16_t, 16>(s.nxt, wk.nxt + tstart, tl);
-      coop_copy_cg<uint32_t, 16>(s.disk, wk.disk + tstart, tl);
+      // only the part of the tile the chain can still touch: from the walk's position on (16-byte vectors: the tile starts are
+      // multiples of kTT, so element c0 = position rounded down to 8 is 16-byte aligned in both arrays)
+      const uint32_t c0 = (uint32_t)(s.st.a > tstart ? (s.st.a - tstart) & ~7ull : 0);
+      const uint32_t c1 = (tl + 7u) & ~7u;  // (the arrays are allocated past n: reading up to 7 elements behind the end is harmless)
+      coop_copy_cg<uint4, 4>(reinterpret_cast<uint4*>(s.nxt + c0), reinterpret_cast<const uint4*>(wk.nxt + tstart + c0), (c1 - c0) / 8);
+      coop_copy_cg<uint4, 8>(reinterpret_cast<uint4*>(s.disk + c0), reinterpret_cast<const uint4*>(wk.disk + tstart + c0), (c1 - c0) / 4);
       __syncthreads();
       if (ep.gp.n == 0) {
-        for (uint32_t i = threadIdx.x; i < tl; i += blockDim.x) s.nd[i] = ((uint64_t)s.nxt[i] << 32) | s.disk[i];
+        for (uint32_t i = c0 + threadIdx.x; i < tl; i += blockDim.x) s.nd[i] = ((uint64_t)s.nxt[i] << 32) | s.disk[i];
         __syncthreads();
       }
       if (threadIdx.x == 0) {

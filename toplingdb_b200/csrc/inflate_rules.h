@@ -48,9 +48,19 @@ B200C_INF_HD inline uint32_t inf_bits(InfBits& b, int n) {  // n <= 16
 }
 
 struct InfHuff {  // canonical code: count[len] codes of each length, symbols ordered by (length, value)
-  uint16_t count[kInfMaxBits + 1];
+  uint16_t* count;   // [kInfMaxBits + 1]
   uint16_t* symbol;
 };
+// The decoder's tables.  On the device they live in SHARED memory, one slice per thread (as thread-local arrays they go to local
+// memory, and with tens of thousands of blocks in flight every count[] / symbol[] probe of the bit-by-bit decode was an L2 round
+// trip: 22.9 ms for 86 MB of compressed blocks, profiles/README.md).  257 words: consecutive threads' slices start in different banks.
+struct InfWork {
+  uint16_t lcount[kInfMaxBits + 1], dcount[kInfMaxBits + 1];
+  uint16_t lsym[kInfFixLCodes], dsym[kInfMaxDCodes];
+  uint8_t lengths[kInfFixLCodes + kInfMaxDCodes + 2];
+  uint8_t pad[1028 - 2 * 2 * (kInfMaxBits + 1) - 2 * kInfFixLCodes - 2 * kInfMaxDCodes - (kInfFixLCodes + kInfMaxDCodes + 2)];
+};
+static_assert(sizeof(InfWork) == 1028, "one odd number of 32-bit words per thread");
 // lengths[n] -> code; returns 0 for a complete code, > 0 incomplete, < 0 over-subscribed (as zlib's inflate_table reports them)
 B200C_INF_HD inline int inf_build(InfHuff& h, const uint8_t* lengths, int n) {
   for (int l = 0; l <= kInfMaxBits; l++) h.count[l] = 0;
@@ -95,19 +105,19 @@ B200C_INF_HD inline int inf_decode(InfBits& b, const InfHuff& h) {
 
 // Inflates the raw deflate stream src[0, n) into dst[0, cap); returns the number of bytes written or -1 (malformed stream, output
 // larger than cap, input exhausted).  dst may be global or local memory: back references are read from dst itself.
-B200C_INF_HD inline long inflate_raw(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap) {
-  const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-  const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-  const uint16_t dbase[30] = {1,   2,   3,   4,   5,   7,    9,    13,   17,   25,   33,   49,   65,    97,    129,
-                              193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-  const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-  const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+B200C_INF_HD inline long inflate_raw(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, InfWork* wk) {
+  // (the length / distance base tables of RFC 1951 3.2.5 and the code-length order of 3.2.7 are computed, not stored: a thread's
+  //  constant arrays would live in local memory on the device)
+  const uint64_t order_lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 | 10ull << 40 |
+                            5ull << 45 | 11ull << 50 | 4ull << 55;
+  const uint64_t order_hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
   InfBits b{src, src + n, 0, 0, 0};
-  uint16_t lsym[kInfFixLCodes], dsym[kInfMaxDCodes];
-  uint8_t lengths[kInfFixLCodes + kInfMaxDCodes + 2];
+  uint8_t* lengths = wk->lengths;
   InfHuff lc, dc;
-  lc.symbol = lsym;
-  dc.symbol = dsym;
+  lc.count = wk->lcount;
+  lc.symbol = wk->lsym;
+  dc.count = wk->dcount;
+  dc.symbol = wk->dsym;
   uint32_t out = 0;
   for (;;) {
     const uint32_t last = inf_bits(b, 1), type = inf_bits(b, 2);
@@ -136,8 +146,10 @@ B200C_INF_HD inline long inflate_raw(const uint8_t* src, uint32_t n, uint8_t* ds
         const int nlen = (int)inf_bits(b, 5) + 257, ndist = (int)inf_bits(b, 5) + 1, ncode = (int)inf_bits(b, 4) + 4;
         if (b.err || nlen > kInfMaxLCodes || ndist > kInfMaxDCodes) return -1;
         int i = 0;
-        for (; i < ncode; i++) lengths[order[i]] = (uint8_t)inf_bits(b, 3);
-        for (; i < 19; i++) lengths[order[i]] = 0;
+        for (; i < 19; i++) {
+          const uint32_t o = (uint32_t)((i < 12 ? order_lo >> (5 * i) : order_hi >> (5 * (i - 12))) & 31);
+          lengths[o] = i < ncode ? (uint8_t)inf_bits(b, 3) : (uint8_t)0;
+        }
         if (b.err) return -1;
         if (inf_build(lc, lengths, 19) != 0) return -1;  // the code-length code must be complete
         i = 0;
@@ -180,10 +192,12 @@ B200C_INF_HD inline long inflate_raw(const uint8_t* src, uint32_t n, uint8_t* ds
         } else {
           sym -= 257;
           if (sym >= 29) return -1;
-          uint32_t len = lbase[sym] + inf_bits(b, lext[sym]);
+          const int le = sym < 8 || sym == 28 ? 0 : (sym >> 2) - 1;
+          uint32_t len = (sym < 8 ? 3u + (uint32_t)sym : sym == 28 ? 258u : (((4u + ((uint32_t)sym & 3u)) << le) + 3u)) + inf_bits(b, le);
           const int ds = inf_decode(b, dc);
           if (ds < 0 || ds >= 30) return -1;
-          const uint32_t dist = dbase[ds] + inf_bits(b, dext[ds]);
+          const int de = ds < 4 ? 0 : (ds >> 1) - 1;
+          const uint32_t dist = (ds < 4 ? 1u + (uint32_t)ds : (((2u + ((uint32_t)ds & 1u)) << de) + 1u)) + inf_bits(b, de);
           if (b.err || dist > out || out + len > cap) return -1;
           while (len--) {
             dst[out] = dst[out - dist];
