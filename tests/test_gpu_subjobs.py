@@ -96,9 +96,15 @@ def test_sub_jobs_share_inputs_and_match_the_oracle(device_inputs):
     parent.close()
 
 
-def test_reference_db_splits_a_job_over_ranges_through_the_b200_executor():
+@pytest.mark.parametrize("devices", ["0", "0,1"])
+def test_reference_db_splits_a_job_over_ranges_through_the_b200_executor(devices):
+    """devices "0,1": the ranges of ONE job are dealt to two GPUs (B200CompactOptions::devices); needs a box with two of them"""
     if not (os.path.exists(H.REF_BIN) and os.path.exists(H.REF_B200_BIN)):
         pytest.fail("oracle/_ref/ref_compact(_b200) missing: run __graft_entry__.build() where /root/reference exists")
+    import toplingdb_b200 as T
+    ndev = len(devices.split(","))
+    if T.device_count() < ndev:
+        pytest.skip(f"needs {ndev} CUDA devices")
     ops, opts = S.ALL["cfg2_mini"]()
     opts = dict(opts, max_subcompactions=4)
     want = H.run_reference(ops, **opts)
@@ -106,13 +112,14 @@ def test_reference_db_splits_a_job_over_ranges_through_the_b200_executor():
         with open(os.path.join(w, "ops.bin"), "wb") as f:
             f.write(ops.bytes())
         env = dict(os.environ, B200C_PLUGIN_TRACE="1")
-        args = [H.REF_B200_BIN, os.path.join(w, "ops.bin"), os.path.join(w, "w"), "executor=b200"] + [f"{k}={v}" for k, v in opts.items()]
+        args = [H.REF_B200_BIN, os.path.join(w, "ops.bin"), os.path.join(w, "w"), "executor=b200", f"b200_devices={devices}"] + \
+               [f"{k}={v}" for k, v in opts.items()]
         r = subprocess.run(args, capture_output=True, text=True, env=env)
         assert r.returncode == 0, r.stderr[-3000:]
         gm = json.load(open(os.path.join(w, "w", "manifest.json")))
         got = [open(os.path.join(w, "w", "outputs" + m["name"]), "rb").read() for m in gm["outputs"]]
     wm = want["manifest"]
-    assert "split into" in r.stderr and "key ranges" in r.stderr, r.stderr[-2000:]
+    assert "split into" in r.stderr and f"key ranges over {ndev} device(s)" in r.stderr, r.stderr[-2000:]
     assert gm["executor"] == "B200Compact" and gm["remote_compact_read_bytes"] > 0
     assert (gm["scan_count"], gm["scan_digest"]) == (wm["scan_count"], wm["scan_digest"])
     # same entries, in order, whatever the file cuts of the ranges are

@@ -911,13 +911,14 @@ __global__ void verify_compressed_kernel(const FileDesc* __restrict__ files, con
 // block to the arena with coalesced stores; other warps of the SM hide the single lane's latency.  Blocks larger than the window
 // are inflated straight into the arena.
 constexpr int kInflateWarps = 8;
-constexpr uint32_t kInflateWindow = 8192;  // bytes of inflated block a warp keeps in shared memory
+constexpr uint32_t kInflateWindow = 6144;  // bytes of inflated block a warp keeps in shared memory (block_size 4096 + one entry fits)
 struct InflateWarpSmem {
   InfWork wk;
-  uint8_t pad[12];  // keeps the window 16-byte aligned
+  uint8_t pad[4];  // keeps the window 16-byte aligned
   uint8_t out[kInflateWindow + 16];
 };
-static_assert(sizeof(InflateWarpSmem) % 16 == 0, "warp slices stay 16-byte aligned");
+static_assert(sizeof(InflateWarpSmem) % 16 == 0 && (sizeof(InfWork) + 4) % 16 == 0, "warp slices and windows stay 16-byte aligned");
+static_assert(3 * (sizeof(InflateWarpSmem) * kInflateWarps + 1024) <= 227 * 1024, "three inflate CTAs per SM");
 __global__ void __launch_bounds__(kInflateWarps * 32)
 inflate_blocks_kernel(const FileDesc* __restrict__ files, uint64_t* __restrict__ blk_off, uint32_t* __restrict__ blk_size,
                       const uint32_t* __restrict__ slot, const uint64_t* __restrict__ slot_off, uint32_t nblk, uint8_t* __restrict__ arena,

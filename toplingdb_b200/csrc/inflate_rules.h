@@ -54,13 +54,14 @@ struct InfHuff {  // canonical code: count[len] codes of each length, symbols or
 // The decoder's tables.  On the device they live in SHARED memory, one slice per thread (as thread-local arrays they go to local
 // memory, and with tens of thousands of blocks in flight every count[] / symbol[] probe of the bit-by-bit decode was an L2 round
 // trip: 22.9 ms for 86 MB of compressed blocks, profiles/README.md).  257 words: consecutive threads' slices start in different banks.
+constexpr int kInfLBits = 9, kInfDBits = 6;  // first-level lookup: codes of up to this many bits decode with one table probe
 struct InfWork {
   uint16_t lcount[kInfMaxBits + 1], dcount[kInfMaxBits + 1];
   uint16_t lsym[kInfFixLCodes], dsym[kInfMaxDCodes];
   uint8_t lengths[kInfFixLCodes + kInfMaxDCodes + 2];
-  uint8_t pad[1028 - 2 * 2 * (kInfMaxBits + 1) - 2 * kInfFixLCodes - 2 * kInfMaxDCodes - (kInfFixLCodes + kInfMaxDCodes + 2)];
+  uint16_t ltab[1 << kInfLBits], dtab[1 << kInfDBits];  // (symbol << 4) | code length, indexed by the next bits of the stream; 0: longer code
 };
-static_assert(sizeof(InfWork) == 1028, "one odd number of 32-bit words per thread");
+static_assert(sizeof(InfWork) == 2172 && (sizeof(InfWork) / 4) % 2 == 1, "an odd number of 32-bit words per thread / warp slice");
 // lengths[n] -> code; returns 0 for a complete code, > 0 incomplete, < 0 over-subscribed (as zlib's inflate_table reports them)
 B200C_INF_HD inline int inf_build(InfHuff& h, const uint8_t* lengths, int n) {
   for (int l = 0; l <= kInfMaxBits; l++) h.count[l] = 0;
@@ -103,6 +104,40 @@ B200C_INF_HD inline int inf_decode(InfBits& b, const InfHuff& h) {
   return -1;
 }
 
+// First-level table of a canonical code: entry[next kbits of the stream] = (symbol << 4) | length for every code of at most kbits
+// bits (the stream delivers a code's first bit in the lowest position, so the table is indexed by the bit-reversed code).
+B200C_INF_HD inline void inf_build_table(const InfHuff& h, const uint8_t* lengths, int n, uint16_t* tab, int kbits) {
+  for (int i = 0; i < (1 << kbits); i++) tab[i] = 0;
+  uint32_t next[kInfMaxBits + 2];
+  uint32_t code = 0;
+  next[0] = 0;
+  for (int l = 1; l <= kInfMaxBits; l++) {
+    code = (code + (l > 1 ? h.count[l - 1] : 0)) << 1;
+    next[l] = code;
+  }
+  for (int s = 0; s < n; s++) {
+    const int l = lengths[s];
+    if (l == 0) continue;
+    const uint32_t c = next[l]++;
+    if (l > kbits) continue;
+    uint32_t r = 0;
+    for (int i = 0; i < l; i++) r |= ((c >> i) & 1u) << (l - 1 - i);
+    const uint16_t e = (uint16_t)((s << 4) | l);
+    for (uint32_t f = r; f < (1u << kbits); f += 1u << l) tab[f] = e;
+  }
+}
+B200C_INF_HD inline int inf_decode_fast(InfBits& b, const InfHuff& h, const uint16_t* tab, int kbits) {
+  if (b.cnt < kInfMaxBits) inf_refill(b);
+  const uint32_t e = tab[(uint32_t)b.buf & ((1u << kbits) - 1)];
+  const int l = (int)(e & 15u);
+  if (l != 0 && l <= b.cnt) {
+    b.buf >>= l;
+    b.cnt -= l;
+    return (int)(e >> 4);
+  }
+  return inf_decode(b, h);  // a code longer than the table's reach (or the tail of the stream)
+}
+
 // Inflates the raw deflate stream src[0, n) into dst[0, cap); returns the number of bytes written or -1 (malformed stream, output
 // larger than cap, input exhausted).  dst may be global or local memory: back references are read from dst itself.
 B200C_INF_HD inline long inflate_raw(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, InfWork* wk) {
@@ -140,8 +175,10 @@ B200C_INF_HD inline long inflate_raw(const uint8_t* src, uint32_t n, uint8_t* ds
         for (; s < 280; s++) lengths[s] = 7;
         for (; s < kInfFixLCodes; s++) lengths[s] = 8;
         inf_build(lc, lengths, kInfFixLCodes);
+        inf_build_table(lc, lengths, kInfFixLCodes, wk->ltab, kInfLBits);
         for (s = 0; s < kInfMaxDCodes; s++) lengths[s] = 5;
         inf_build(dc, lengths, kInfMaxDCodes);
+        inf_build_table(dc, lengths, kInfMaxDCodes, wk->dtab, kInfDBits);
       } else {  // dynamic code: code-length code, then the literal/length and distance code lengths (3.2.7)
         const int nlen = (int)inf_bits(b, 5) + 257, ndist = (int)inf_bits(b, 5) + 1, ncode = (int)inf_bits(b, 4) + 4;
         if (b.err || nlen > kInfMaxLCodes || ndist > kInfMaxDCodes) return -1;
@@ -177,12 +214,14 @@ B200C_INF_HD inline long inflate_raw(const uint8_t* src, uint32_t n, uint8_t* ds
         // an incomplete code is only legal when it has a single code word (zlib's inflate_table, puff.c)
         int e = inf_build(lc, lengths, nlen);
         if (e < 0 || (e > 0 && nlen - lc.count[0] != 1)) return -1;
+        inf_build_table(lc, lengths, nlen, wk->ltab, kInfLBits);
         uint8_t* dl = lengths + nlen;
         e = inf_build(dc, dl, ndist);
         if (e < 0 || (e > 0 && ndist - dc.count[0] != 1)) return -1;
+        inf_build_table(dc, dl, ndist, wk->dtab, kInfDBits);
       }
       for (;;) {  // literals and matches until end-of-block
-        int sym = inf_decode(b, lc);
+        int sym = inf_decode_fast(b, lc, wk->ltab, kInfLBits);
         if (sym < 0) return -1;
         if (sym < 256) {
           if (out >= cap) return -1;
@@ -194,7 +233,7 @@ B200C_INF_HD inline long inflate_raw(const uint8_t* src, uint32_t n, uint8_t* ds
           if (sym >= 29) return -1;
           const int le = sym < 8 || sym == 28 ? 0 : (sym >> 2) - 1;
           uint32_t len = (sym < 8 ? 3u + (uint32_t)sym : sym == 28 ? 258u : (((4u + ((uint32_t)sym & 3u)) << le) + 3u)) + inf_bits(b, le);
-          const int ds = inf_decode(b, dc);
+          const int ds = inf_decode_fast(b, dc, wk->dtab, kInfDBits);
           if (ds < 0 || ds >= 30) return -1;
           const int de = ds < 4 ? 0 : (ds >> 1) - 1;
           const uint32_t dist = (ds < 4 ? 1u + (uint32_t)ds : (((2u + ((uint32_t)ds & 1u)) << de) + 1u)) + inf_bits(b, de);
