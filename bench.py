@@ -160,6 +160,7 @@ def plugin_arm(args, rank):
             "config": {"workload": w["desc"], "sample": r["sample"]},
             "executor": r["plugin"]["executor"], "remote_compact_read_bytes": r["plugin"]["remote_compact_read_bytes"],
             "local_cpu_compaction": {"value": round(r["local"]["mbps"], 1), "unit": "MB/s", "ms": round(r["local"]["seconds"] * 1e3, 2)},
+            "plugin_4_ranges": {"value": round(r["plugin_4_ranges"]["mbps"], 1), "unit": "MB/s", "ms": round(r["plugin_4_ranges"]["seconds"] * 1e3, 2)},
             "speedup_vs_local": round(r["plugin"]["mbps"] / r["local"]["mbps"], 2)}
     print(json.dumps(line))
 

@@ -169,11 +169,13 @@ def run_plugin_sample(w, sample_bytes):
     try:
         _ops_file(os.path.join(d, "ops.bin"), w, n_total, seed=2)
         # warm=1: script + job once through a throw-away DB of the same process first -- a DB's second and later compactions
-        for name, binary, extra in (("plugin", b200_bin, ["executor=b200", "warm=1"]), ("local", REF_BIN, ["warm=1"])):
+        # plugin_4_ranges: the same job with max_subcompactions=4 -- the plugin splits it into key ranges that share the uploaded inputs
+        for name, binary, extra, subs in (("plugin", b200_bin, ["executor=b200", "warm=1"], 1), ("plugin_4_ranges", b200_bin, ["executor=b200", "warm=1"], 4),
+                                          ("local", REF_BIN, ["warm=1"], 1)):
             best = None
             for rep in range(1):
                 wd = os.path.join(d, f"{name}{rep}")
-                subprocess.check_call([binary, os.path.join(d, "ops.bin"), wd, "output_level=1", "max_subcompactions=1",
+                subprocess.check_call([binary, os.path.join(d, "ops.bin"), wd, "output_level=1", f"max_subcompactions={subs}",
                                        "target_file_size=67108864", "copy=0"] + extra, stdout=subprocess.DEVNULL)
                 man = json.load(open(os.path.join(wd, "manifest.json")))
                 stt = man["stats"]
