@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-(time timeout 900 python -m pytest tests/test_gpu_zlib.py -x -q) > gpurun_out/gputest.log 2>&1; tail -4 gpurun_out/gputest.log
-python tools/zlib_cost.py > gpurun_out/zlib_cost4.json 2> gpurun_out/zlib_cost4.err; cut -c1-700 gpurun_out/zlib_cost4.json
+timeout 400 python tools/fuzz_gpu_vs_reference.py 240 4711 > gpurun_out/fuzz_gpu.log 2>&1; tail -5 gpurun_out/fuzz_gpu.log | cut -c1-600
+python bench.py --impl plugin > gpurun_out/plugin2.json 2> gpurun_out/plugin2.err; cut -c1-900 gpurun_out/plugin2.json
