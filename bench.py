@@ -303,6 +303,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-depth", type=int, default=4, help="compaction jobs in flight in the end-to-end measurement")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--pipeline-ranges", type=int, default=8, help="key ranges of the pipelined single-job measurement (e2e.single_job_pipelined)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -518,6 +519,50 @@ def main():
                "single_job_ms": round(single_s * 1e3, 2)}
         for ej in ejs:
             ej.close()
+        del ejs
+        # ONE job alone, pipelined over its own PCIe link: the inputs go up in key order and the job runs as key-range sub-jobs
+        # (b200c_job_plan_ranges / b200c_job_upload_by_ranges / b200c_job_create_sub), each of which starts -- and downloads its
+        # outputs -- as soon as its own blocks have arrived.  Its outputs are those of the ranges (what the reference writes with
+        # max_subcompactions > 1), checked per range in tests/test_gpu_subjobs.py; here: entry conservation.
+        try:
+            def pipelined_once():
+                parent = T.CompactionJob(output_mem="host", **common)
+                for i, img in enumerate(host_imgs):
+                    parent.add_input(img, level=0, file_number=100 + i, deferred=True)
+                bounds = parent.plan_ranges(args.pipeline_ranges, min_range_bytes=BENCH_JOB["max_output_file_size"])
+                parent.upload_by_ranges(bounds)
+                rng = list(zip([None] + bounds, bounds + [None]))
+                subs = [parent.sub_job(range_start=a, range_end=b, first_file_number=1000 * (x + 1)) for x, (a, b) in enumerate(rng)]
+                perr = []
+
+                def go(sj):
+                    try:
+                        sj.run()
+                    except Exception as e:  # noqa: BLE001
+                        perr.append(e)
+                pth = [threading.Thread(target=go, args=(sj,)) for sj in subs]
+                for th in pth:
+                    th.start()
+                for th in pth:
+                    th.join()
+                if perr:
+                    raise perr[0]
+                n_in = sum(sj.stats().num_input_records for sj in subs)
+                n_files = sum(sj.output_count() for sj in subs)
+                for sj in subs:
+                    sj.close()
+                parent.close()
+                return len(rng), n_in, n_files
+            pipelined_once()  # buffers of the sub-jobs come from the library's cache afterwards, as for the other numbers
+            barrier()
+            t0 = time.perf_counter()
+            nr, n_in_p, nf_p = pipelined_once()
+            barrier()
+            e2e["single_job_pipelined"] = {"ms": round((time.perf_counter() - t0) * 1e3, 2), "key_ranges": nr, "output_files": nf_p,
+                                           "input_records": n_in_p}
+            assert n_in_p == st.num_input_records, (n_in_p, st.num_input_records)
+        except Exception as e:  # noqa: BLE001
+            e2e["single_job_pipelined"] = {"error": repr(e)[:200]}
 
     sampler.stop_flag = True
     cpu = None

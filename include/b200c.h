@@ -51,7 +51,11 @@ enum b200c_status {
   B200C_ERR_STATE = 7            /* call order violated (e.g. output queried before run) */
 };
 
-enum b200c_mem_kind { B200C_MEM_HOST = 0, B200C_MEM_DEVICE = 1 };
+enum b200c_mem_kind {
+  B200C_MEM_HOST = 0,
+  B200C_MEM_DEVICE = 1,
+  B200C_MEM_HOST_DEFERRED = 2 /* b200c_job_add_input only: a host image whose upload waits for b200c_job_upload_by_ranges / the run */
+};
 /* CompactionFilter applied inside the merge kernel (compaction_iterator.cc:231-473, :579-584): only built-in filters whose
  * decision is a function of the entry itself can run on the device */
 enum b200c_compaction_filter {
@@ -212,6 +216,14 @@ B200C_API void b200c_job_destroy(b200c_job* j);
 B200C_API int b200c_job_plan_ranges(b200c_job* j, uint32_t max_ranges, uint64_t min_range_bytes, uint8_t* keys, uint32_t* key_lens,
                                     uint32_t* n_boundaries);
 B200C_API int b200c_job_create_sub(b200c_job* parent, const b200c_params* p, b200c_job** out);
+/* Pipelines ONE job over its own PCIe link: the parent's host inputs (added with B200C_MEM_HOST_DEFERRED) are uploaded in KEY order --
+ * first the index / metadata tail of every file, then, range after range, the data blocks that range can touch (cut at the first block
+ * whose index separator reaches the boundary) -- and an event is recorded behind every range.  A sub-job created afterwards for
+ * [boundary r-1, boundary r) only waits for ITS event: it decodes, merges, encodes and downloads its outputs while the later ranges
+ * are still going up, so host -> device, compute and device -> host of one job overlap (a job that is uploaded whole, compacted and
+ * downloaded is two PCIe copies long: 78 of 83 ms on the bench job).  keys / key_lens / n_boundaries as b200c_job_plan_ranges fills
+ * them.  The reference has no counterpart (its sub-compactions share the block cache); results are per range, as for any sub-job. */
+B200C_API int b200c_job_upload_by_ranges(b200c_job* parent, const uint8_t* keys, const uint32_t* key_lens, uint32_t n_boundaries);
 
 /* ---- stage-level entry points (used by the parity tests and by bench.py's per-kernel roofline) ---- */
 enum b200c_debug_array {

@@ -140,6 +140,10 @@ int b200c_job_plan_ranges(b200c_job* j, uint32_t max_ranges, uint64_t min_range_
   }
   return B200C_OK;
 }
+int b200c_job_upload_by_ranges(b200c_job* j, const uint8_t* keys, const uint32_t* key_lens, uint32_t n) {
+  (void)j; (void)keys; (void)key_lens; (void)n;
+  return B200C_OK;
+}
 int b200c_job_create_sub(b200c_job* parent, const b200c_params* p, b200c_job** out) {
   int rc = b200c_job_create(p, out);
   if (rc == B200C_OK) (*out)->sub_index = parent->n_subs++;

@@ -42,23 +42,27 @@ def _seeded(seed, nruns=6, n=30000, vlen=40):
     return [H.oracle_build_sst(H.Params(), H.kvstream(r)) for r in reversed(runs)]
 
 
-@pytest.mark.parametrize("device_inputs", [False, True])
-def test_sub_jobs_share_inputs_and_match_the_oracle(device_inputs):
+@pytest.mark.parametrize("mode", ["host", "device", "pipelined"])
+def test_sub_jobs_share_inputs_and_match_the_oracle(mode):
+    """pipelined: the host inputs are uploaded in key order (b200c_job_upload_by_ranges) and every sub-job starts when the blocks of its
+    own range have arrived -- the device may still be receiving the later ranges while the first ones are compacted"""
     from gpu_harness import job_from_params
     inputs = _seeded(5)
     p = H.Params(output_level=1, bottommost_level=True, max_output_file_size=256 << 10, file_creation_times=[3])
     parent = job_from_params(p)
     keep = []
     for i, data in enumerate(inputs):
-        if device_inputs:
+        if mode == "device":
             t = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
             keep.append(t)
             parent.add_input(t, level=0, file_number=i)
         else:
-            parent.add_input(data, level=0, file_number=i)
+            parent.add_input(data, level=0, file_number=i, deferred=mode == "pipelined")
     bounds = parent.plan_ranges(4, min_range_bytes=64 << 10)
     assert len(bounds) == 3 and bounds == sorted(bounds) and len(set(bounds)) == 3
     assert parent.plan_ranges(1) == [] and len(parent.plan_ranges(64, min_range_bytes=1 << 40)) == 0  # never smaller than min_range_bytes
+    if mode == "pipelined":
+        parent.upload_by_ranges(bounds)
     ranges = list(zip([None] + bounds, bounds + [None]))
     subs = [parent.sub_job(range_start=a, range_end=b, first_file_number=1000 * (i + 1)) for i, (a, b) in enumerate(ranges)]
     errs = []

@@ -1,4 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 400 python tools/fuzz_gpu_vs_reference.py 240 4711 > gpurun_out/fuzz_gpu.log 2>&1; tail -5 gpurun_out/fuzz_gpu.log | cut -c1-600
-python bench.py --impl plugin > gpurun_out/plugin2.json 2> gpurun_out/plugin2.err; cut -c1-900 gpurun_out/plugin2.json
+for n in 16 4 32; do
+python bench.py --no-cpu-baseline --steps 3 --pipeline-ranges $n > gpurun_out/bench_p$n.json 2> gpurun_out/bench_p$n.err; python - <<P
+import json
+d = json.load(open("gpurun_out/bench_p$n.json"))
+print($n, d["ms_per_step"], d["e2e"]["single_job_ms"], d["e2e"]["single_job_pipelined"], d["roofline"]["traffic"])
+P
+done

@@ -259,6 +259,9 @@ struct b200c_job {
   BoundKey range_lo{}, range_hi{};  // sub-compaction key range in column form (has_range_start / has_range_end in p)
   DevBuf clip_d;                    // clipped run bounds: begin[k] | end[k]
   DevBuf cslot, cslot_off, arena;   // compressed inputs: arena slot size / offset per data block, the inflated blocks
+  std::vector<cudaEvent_t> range_events;   // b200c_job_upload_by_ranges: event r = the blocks of ranges 0..r (and every file's tail) are on the device
+  std::vector<std::string> range_bounds;   // ... the boundary user keys it was called with
+  cudaEvent_t wait_ev = nullptr;           // sub-job of such a parent: what its streams wait for before they touch the inputs (owned by the parent)
   DevBuf vfiles_d, vrun_start;      // paranoid_file_checks: descriptors / run table of the outputs being read back
   HostBuf pin_small, pin_tails, pin_rd, pin_up;
   size_t pin_up_used = 0;  // pinned staging: input tails / tail-copy records, output tails
@@ -870,6 +873,7 @@ int run_job(b200c_job* j, int until) {
     j->sms = prop.multiProcessorCount;
   }
   cudaStream_t st = j->st;
+  if (j->wait_ev) CU(cudaStreamWaitEvent(st, j->wait_ev, 0));  // sub-job of a range-pipelined parent: its part of the inputs is on its way
   uint64_t launches = 0;
   j->outputs.clear();
   j->ran = false;
@@ -1397,7 +1401,10 @@ int b200c_job_create(const b200c_params* p, b200c_job** out) {
 
 int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const void* data, uint64_t len, int mem_kind) {
   if (!j || !data) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
-  if (mem_kind != B200C_MEM_HOST && mem_kind != B200C_MEM_DEVICE) return fail(B200C_ERR_INVALID_ARGUMENT, "bad mem_kind");
+  if (mem_kind != B200C_MEM_HOST && mem_kind != B200C_MEM_DEVICE && mem_kind != B200C_MEM_HOST_DEFERRED)
+    return fail(B200C_ERR_INVALID_ARGUMENT, "bad mem_kind");
+  const bool deferred = mem_kind == B200C_MEM_HOST_DEFERRED;
+  if (deferred) mem_kind = B200C_MEM_HOST;
   j->inputs.emplace_back();
   Input& in = j->inputs.back();
   in.level = level;
@@ -1405,7 +1412,7 @@ int b200c_job_add_input(b200c_job* j, int level, uint64_t file_number, const voi
   in.data = static_cast<const uint8_t*>(data);
   in.len = len;
   in.mem_kind = mem_kind;
-  if (mem_kind == B200C_MEM_HOST && len >= (1u << 20) && !getenv("B200C_NO_EAGER_UPLOAD")) {
+  if (mem_kind == B200C_MEM_HOST && !deferred && len >= (1u << 20) && !getenv("B200C_NO_EAGER_UPLOAD")) {
     // Start the host -> device copy now, on the job's copy stream: a caller that reads its input files one after the other (the
     // executor plugin) gets the PCIe transfer of file i overlapped with the read of file i + 1.  Failures here are not errors: the
     // run copies the file itself when no eager copy is pending.
@@ -1440,11 +1447,71 @@ bool host_varint(const uint8_t*& p, const uint8_t* end, uint64_t* v) {
   }
   return false;
 }
+// Entry i of an index block whose every entry is a restart point (index_block_restart_interval == 1, the default and the only value
+// the device's index builder writes): the restart array addresses it directly, the key is stored whole and the handle in full.
+struct IndexView {
+  const uint8_t* blk;
+  const uint8_t* end;      // end of the entries
+  const uint8_t* restarts;
+  uint32_t nr;
+  bool value_delta, user_key;
+  bool entry(uint32_t i, const uint8_t** key, size_t* ulen, uint64_t* off, uint64_t* size) const {
+    const uint8_t* r = restarts + 4ull * i;
+    const uint32_t ro = (uint32_t)r[0] | (uint32_t)r[1] << 8 | (uint32_t)r[2] << 16 | (uint32_t)r[3] << 24;
+    const uint8_t* p = blk + ro;
+    if (p >= end) return false;
+    uint64_t shared, non_shared, vl = 0;
+    if (!host_varint(p, end, &shared) || shared != 0 || !host_varint(p, end, &non_shared)) return false;
+    if (!value_delta && !host_varint(p, end, &vl)) return false;
+    if (non_shared > (uint64_t)(end - p)) return false;
+    *key = p;
+    size_t u = (size_t)non_shared;
+    if (!user_key) {
+      if (u < 8) return false;
+      u -= 8;
+    }
+    *ulen = u;
+    p += non_shared;
+    return host_varint(p, end, off) && host_varint(p, end, size);
+  }
+};
+bool index_view(const uint8_t* blk, uint64_t size, const InputTail& t, IndexView* v) {
+  if (size < 8) return false;
+  const uint32_t nr = ((uint32_t)blk[size - 4] | (uint32_t)blk[size - 3] << 8 | (uint32_t)blk[size - 2] << 16 | (uint32_t)blk[size - 1] << 24) & 0x7fffffffu;
+  if (4ull * nr + 4 > size || nr != t.num_data_blocks || nr == 0) return false;  // (other restart intervals: the sequential walk)
+  v->blk = blk;
+  v->restarts = blk + size - 4 - 4ull * nr;
+  v->end = v->restarts;
+  v->nr = nr;
+  v->value_delta = t.format_version >= 4;
+  v->user_key = t.index_key_is_user_key != 0;
+  return true;
+}
 // Walks one index block on the host (entry layout: table/block_based/block_builder.cc:21-32, values: table/format.cc:102-140) and
 // appends about `per_file` anchors: the separator of every (nblocks / per_file)-th data block as a user key with the data bytes
 // since the previous anchor -- what TableReader::ApproximateKeyAnchors gives GenSubcompactionBoundaries (compaction_job.cc:520-560).
 std::string index_anchors(const uint8_t* blk, uint64_t size, const InputTail& t, uint32_t per_file, std::vector<Anchor>* out) {
   if (size < 8) return "index block too short";
+  IndexView iv;
+  if (index_view(blk, size, t, &iv)) {  // restart interval 1: read the ~per_file sampled entries directly
+    const uint64_t stepf = std::max<uint64_t>(1, t.num_data_blocks / std::max<uint32_t>(per_file, 1));
+    uint64_t last = 0;
+    for (uint64_t n = stepf; n < t.num_data_blocks; n += stepf) {
+      const uint8_t* kp;
+      size_t ulen;
+      uint64_t off, bsize;
+      if (!iv.entry((uint32_t)(n - 1), &kp, &ulen, &off, &bsize)) return "malformed index entry";
+      if (ulen > (size_t)kMaxUserKey) continue;
+      Anchor a;
+      memset(&a, 0, sizeof a);
+      memcpy(a.key, kp, ulen);
+      a.klen = (uint32_t)ulen;
+      a.bytes = off + bsize + 5 - last;
+      last = off + bsize + 5;
+      out->push_back(a);
+    }
+    return "";
+  }
   const uint32_t nr = ((uint32_t)blk[size - 4] | (uint32_t)blk[size - 3] << 8 | (uint32_t)blk[size - 2] << 16 | (uint32_t)blk[size - 1] << 24) & 0x7fffffffu;
   if (4ull * nr + 4 > size) return "index block restart array out of range";
   const uint8_t* p = blk;
@@ -1558,7 +1625,7 @@ int b200c_job_create_sub(b200c_job* parent, const b200c_params* p, b200c_job** o
   CU(cudaSetDevice(parent->p.device));
   // the device copies of the parent's host inputs: made once, here at the latest
   for (Input& in : parent->inputs) {
-    if (in.mem_kind != B200C_MEM_HOST) continue;
+    if (in.mem_kind != B200C_MEM_HOST || !parent->range_events.empty()) continue;  // (range-pipelined: the sub-job waits for its event)
     if (in.uploaded) {
       CU(cudaEventSynchronize(in.up_ev));
     } else if (!in.shared_copy) {
@@ -1578,7 +1645,154 @@ int b200c_job_create_sub(b200c_job* parent, const b200c_params* p, b200c_job** o
     s.mem_kind = B200C_MEM_DEVICE;
     s.data = in.mem_kind == B200C_MEM_HOST ? in.staged.as<uint8_t>() : in.data;
   }
+  if (!parent->range_events.empty()) {
+    // the range that ends at boundary r needs the uploads up to event r; an open end (or a bound that is not one of the boundaries)
+    // needs everything
+    size_t r = parent->range_events.size() - 1;
+    if (p->has_range_end) {
+      const std::string end(static_cast<const char*>(p->range_end_user_key ? p->range_end_user_key : ""), p->range_end_len);
+      for (size_t i = 0; i < parent->range_bounds.size(); i++)
+        if (parent->range_bounds[i] == end) {
+          r = i;
+          break;
+        }
+    }
+    j->wait_ev = parent->range_events[r];
+  }
   *out = j;
+  return B200C_OK;
+}
+
+int b200c_job_upload_by_ranges(b200c_job* j, const uint8_t* keys, const uint32_t* key_lens, uint32_t nb) {
+  if (!j || (nb && (!keys || !key_lens))) return fail(B200C_ERR_INVALID_ARGUMENT, "null argument");
+  if (j->inputs.empty()) return fail(B200C_ERR_STATE, "job has no inputs");
+  if (!j->range_events.empty()) return fail(B200C_ERR_STATE, "the inputs of this job are already uploaded by ranges");
+  if (b200c_device_count() <= 0) return fail(B200C_ERR_NO_DEVICE, "no CUDA device");
+  CU(cudaSetDevice(j->p.device));
+  if (!j->st_up) CU(cudaStreamCreateWithFlags(&j->st_up, cudaStreamNonBlocking));
+  std::vector<Anchor> bounds(nb);
+  for (uint32_t r = 0; r < nb; r++) {
+    if (key_lens[r] > (uint32_t)kMaxUserKey) return fail(B200C_ERR_NOT_SUPPORTED, "range boundary longer than 16 bytes");
+    memset(&bounds[r], 0, sizeof(Anchor));
+    memcpy(bounds[r].key, keys + (size_t)r * kMaxUserKey, key_lens[r]);
+    bounds[r].klen = key_lens[r];
+    if (r && anchor_cmp(bounds[r - 1], bounds[r]) >= 0) return fail(B200C_ERR_INVALID_ARGUMENT, "range boundaries must be strictly ascending");
+  }
+  const size_t k = j->inputs.size();
+  std::vector<std::vector<uint64_t>> cuts(k, std::vector<uint64_t>(nb, 0));  // end of chunk r inside file f's data region
+  std::vector<uint64_t> data_end(k, 0);
+  std::vector<uint8_t> idx;
+  for (size_t f = 0; f < k; f++) {
+    Input& in = j->inputs[f];
+    if (in.mem_kind != B200C_MEM_HOST || in.uploaded)
+      return fail(B200C_ERR_STATE, "upload by ranges needs host inputs added with B200C_MEM_HOST_DEFERRED");
+    if (int rc = fetch_tail(j, in)) return rc;
+    if (in.tail.index_off + in.tail.index_size + 5 > in.len) return fail(B200C_ERR_CORRUPTION, "index handle out of range");
+    const uint8_t* blk = in.data + in.tail.index_off;
+    uint64_t blk_len = in.tail.index_size;
+    idx.clear();
+    if (input_is_compressed(in))
+      if (int rc = host_inflated_index(j, in, &idx)) return rc;
+    if (!idx.empty()) {
+      blk = idx.data();
+      blk_len = idx.size();
+    }
+    // chunk r of this file ends behind the first block whose separator reaches boundary r (range_rules.h: that block is the last
+    // one the range [.., boundary r) can touch)
+    IndexView iv;
+    if (index_view(blk, blk_len, in.tail, &iv)) {  // restart interval 1: binary search per boundary
+      const uint8_t* kp;
+      size_t ul;
+      uint64_t off, bsize;
+      if (!iv.entry(iv.nr - 1, &kp, &ul, &off, &bsize) || off + bsize + 5 > in.len) return fail(B200C_ERR_CORRUPTION, "malformed index entry");
+      data_end[f] = off + bsize + 5;
+      for (uint32_t r = 0; r < nb; r++) {
+        uint32_t lo = 0, hi = iv.nr;  // first entry with separator >= boundary r
+        while (lo < hi) {
+          const uint32_t mid = lo + ((hi - lo) >> 1);
+          if (!iv.entry(mid, &kp, &ul, &off, &bsize)) return fail(B200C_ERR_CORRUPTION, "malformed index entry");
+          const size_t m = std::min<size_t>(ul, bounds[r].klen);
+          int c = memcmp(kp, bounds[r].key, m);
+          if (c == 0) c = ul < bounds[r].klen ? -1 : (ul > bounds[r].klen ? 1 : 0);
+          if (c < 0) lo = mid + 1;
+          else hi = mid;
+        }
+        if (lo == iv.nr) {
+          cuts[f][r] = data_end[f];
+        } else {
+          if (!iv.entry(lo, &kp, &ul, &off, &bsize) || off + bsize + 5 > in.len) return fail(B200C_ERR_CORRUPTION, "block handle out of range");
+          cuts[f][r] = off + bsize + 5;
+        }
+      }
+      CU(in.staged.reserve(in.len + 64));
+      continue;
+    }
+    if (blk_len < 8) return fail(B200C_ERR_CORRUPTION, "index block too short");
+    const uint32_t nr = ((uint32_t)blk[blk_len - 4] | (uint32_t)blk[blk_len - 3] << 8 | (uint32_t)blk[blk_len - 2] << 16 | (uint32_t)blk[blk_len - 1] << 24) & 0x7fffffffu;
+    if (4ull * nr + 4 > blk_len) return fail(B200C_ERR_CORRUPTION, "index block restart array out of range");
+    const uint8_t* p = blk;
+    const uint8_t* end = blk + blk_len - 4 - 4ull * nr;
+    const bool value_delta = in.tail.format_version >= 4;
+    std::string key;
+    uint64_t poff = 0, psize = 0, last_end = 0;
+    uint32_t ri = 0;
+    while (p < end) {
+      uint64_t shared, non_shared, vl = 0, off, bsize;
+      if (!host_varint(p, end, &shared) || !host_varint(p, end, &non_shared)) return fail(B200C_ERR_CORRUPTION, "malformed index entry");
+      if (!value_delta && !host_varint(p, end, &vl)) return fail(B200C_ERR_CORRUPTION, "malformed index entry");
+      if (shared > key.size() || non_shared > (uint64_t)(end - p)) return fail(B200C_ERR_CORRUPTION, "malformed index entry");
+      key.resize(shared);
+      key.append(reinterpret_cast<const char*>(p), non_shared);
+      p += non_shared;
+      if (shared == 0 || !value_delta) {
+        if (!host_varint(p, end, &off) || !host_varint(p, end, &bsize)) return fail(B200C_ERR_CORRUPTION, "malformed index value");
+      } else {
+        uint64_t d;
+        if (!host_varint(p, end, &d)) return fail(B200C_ERR_CORRUPTION, "malformed index value");
+        bsize = psize + (uint64_t)((int64_t)(d >> 1) ^ -(int64_t)(d & 1));
+        off = poff + psize + 5;
+      }
+      poff = off;
+      psize = bsize;
+      if (off + bsize + 5 > in.len) return fail(B200C_ERR_CORRUPTION, "block handle out of range");
+      last_end = off + bsize + 5;
+      size_t ulen = key.size();
+      if (!in.tail.index_key_is_user_key) {
+        if (ulen < 8) return fail(B200C_ERR_CORRUPTION, "index separator shorter than a trailer");
+        ulen -= 8;
+      }
+      while (ri < nb) {  // separator >= boundary ri (user-key order; a longer separator compares by its bytes)
+        const size_t m = std::min<size_t>(ulen, bounds[ri].klen);
+        int c = memcmp(key.data(), bounds[ri].key, m);
+        if (c == 0) c = ulen < bounds[ri].klen ? -1 : (ulen > bounds[ri].klen ? 1 : 0);
+        if (c < 0) break;
+        cuts[f][ri++] = last_end;
+      }
+    }
+    data_end[f] = last_end;
+    for (; ri < nb; ri++) cuts[f][ri] = last_end;  // every block of the file lies in front of these boundaries
+    CU(in.staged.reserve(in.len + 64));
+  }
+  // 1. what every range needs of every file: everything behind the data blocks (filter, index, properties, metaindex, footer)
+  for (size_t f = 0; f < k; f++) {
+    Input& in = j->inputs[f];
+    if (in.len > data_end[f])
+      CU(cudaMemcpyAsync(in.staged.as<uint8_t>() + data_end[f], in.data + data_end[f], in.len - data_end[f], cudaMemcpyHostToDevice, j->st_up));
+  }
+  // 2. the data blocks, range after range
+  j->range_events.resize((size_t)nb + 1, nullptr);
+  for (uint32_t r = 0; r <= nb; r++) {
+    for (size_t f = 0; f < k; f++) {
+      Input& in = j->inputs[f];
+      const uint64_t lo = r == 0 ? 0 : cuts[f][r - 1], hi = r == nb ? data_end[f] : cuts[f][r];
+      if (hi > lo) CU(cudaMemcpyAsync(in.staged.as<uint8_t>() + lo, in.data + lo, hi - lo, cudaMemcpyHostToDevice, j->st_up));
+    }
+    CU(cudaEventCreateWithFlags(&j->range_events[r], cudaEventDisableTiming));
+    CU(cudaEventRecord(j->range_events[r], j->st_up));
+  }
+  j->range_bounds.clear();
+  for (uint32_t r = 0; r < nb; r++) j->range_bounds.emplace_back(reinterpret_cast<const char*>(bounds[r].key), bounds[r].klen);
+  for (Input& in : j->inputs) in.shared_copy = true;
   return B200C_OK;
 }
 
@@ -1668,6 +1882,8 @@ void b200c_job_destroy(b200c_job* j) {
   j->cslot.release();
   j->cslot_off.release();
   j->arena.release();
+  for (cudaEvent_t e : j->range_events)
+    if (e) cudaEventDestroy(e);
   for (auto& in : j->inputs) {
     in.staged.release();
     in.index_inflated.release();

@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200C_LIB") or os.path.join(HERE, "libb200c.so")  # B200C_LIB: debugging override
 
 OK, ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_CORRUPTION, ERR_NOT_SUPPORTED, ERR_OOM, ERR_STATE = range(8)
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_DEFERRED = 0, 1, 2
 CKSUM = {"none": 0, "crc32c": 1, "xxh3": 4}
 DBG_DECODED_KEYS, DBG_DECODED_VALUES, DBG_MERGED_KEYS, DBG_MERGED_VALUES, DBG_BLOCK_LIST = 1, 2, 3, 4, 5
 
@@ -67,7 +67,7 @@ EXPORTS = ["b200c_last_error", "b200c_abi_version", "b200c_device_count", "b200c
            "b200c_job_output_data", "b200c_job_output_read", "b200c_job_get_stats", "b200c_job_destroy",
            "b200c_job_run_until", "b200c_job_debug_read", "b200c_block_checksums", "b200c_job_kernel_time_count",
            "b200c_job_kernel_time", "b200c_job_encode_columns", "b200c_host_alloc", "b200c_host_free", "b200c_job_encode_kv",
-           "b200c_job_plan_ranges", "b200c_job_create_sub"]
+           "b200c_job_plan_ranges", "b200c_job_create_sub", "b200c_job_upload_by_ranges"]
 
 
 def load_library(build_if_missing=True):
@@ -105,6 +105,7 @@ def load_library(build_if_missing=True):
     L.b200c_params_init.restype = None
     L.b200c_job_plan_ranges.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.b200c_job_create_sub.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(C.c_void_p)]
+    L.b200c_job_upload_by_ranges.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32]
     _lib = L
     return L
 
@@ -210,6 +211,17 @@ class CompactionJob:
         _check(lib().b200c_job_plan_ranges(self._h, max_ranges, min_range_bytes, keys, lens, C.byref(nb)))
         return [keys.raw[16 * i:16 * i + lens[i]] for i in range(nb.value)]
 
+    def upload_by_ranges(self, boundaries):
+        """uploads the (deferred) host inputs in key order, range after range; sub-jobs created afterwards start as soon as the blocks
+        of their own range are on the device"""
+        n = len(boundaries)
+        keys = C.create_string_buffer(16 * max(1, n))
+        lens = (C.c_uint32 * max(1, n))()
+        for i, b in enumerate(boundaries):
+            keys[16 * i:16 * i + len(b)] = b
+            lens[i] = len(b)
+        _check(lib().b200c_job_upload_by_ranges(self._h, keys, lens, n))
+
     def sub_job(self, range_start=None, range_end=None, **kw):
         """a job over this job's inputs (shared device copies) restricted to range_start <= user key < range_end"""
         merged = {k: v for k, v in self._kw.items() if k not in ("range_start", "range_end")}
@@ -223,16 +235,18 @@ class CompactionJob:
             import torch
             torch.cuda.synchronize(self.params.device)
 
-    def add_input(self, data, level=0, file_number=0):
-        """data: bytes (host image) or a CUDA uint8 torch tensor (device-resident image)."""
+    def add_input(self, data, level=0, file_number=0, deferred=False):
+        """data: bytes (host image) or a CUDA uint8 torch tensor (device-resident image).  deferred: a host image whose upload waits
+        for upload_by_ranges() (or the run)."""
         L = lib()
+        host_kind = MEM_HOST_DEFERRED if deferred else MEM_HOST
         if isinstance(data, (bytes, bytearray)):
             buf = C.create_string_buffer(bytes(data), len(data))
             self._keep.append(buf)
-            _check(L.b200c_job_add_input(self._h, level, file_number, C.cast(buf, C.c_void_p), len(data), MEM_HOST))
+            _check(L.b200c_job_add_input(self._h, level, file_number, C.cast(buf, C.c_void_p), len(data), host_kind))
         elif hasattr(data, "data_ptr"):
             self._keep.append(data)
-            kind = MEM_DEVICE if data.is_cuda else MEM_HOST
+            kind = MEM_DEVICE if data.is_cuda else host_kind
             self._torch_device_inputs = self._torch_device_inputs or bool(data.is_cuda)
             _check(L.b200c_job_add_input(self._h, level, file_number, C.c_void_p(data.data_ptr()), data.numel() * data.element_size(), kind))
         else:
