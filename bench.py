@@ -10,6 +10,8 @@ the (smallest, largest) internal keys of their outputs over NCCL to stitch / ass
 metric  : compaction MB/s of input KV bytes (sum over input entries of internal-key + value bytes), MB = 1e6 bytes
 value   : device-resident inputs, CUDA-event time on the job stream, max over ranks
 e2e     : same job through the C ABI with HOST (pinned) input images and host outputs, H2D + D2H inside the timed region
+          (several jobs in flight, as concurrent background compactions are); e2e.single_job_ms: one job alone, uploaded whole;
+          e2e.single_job_pipelined: one job alone as key-range sub-jobs whose inputs are uploaded in key order
 """
 import argparse
 import json

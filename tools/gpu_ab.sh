@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for n in 16 4 32; do
-python bench.py --no-cpu-baseline --steps 3 --pipeline-ranges $n > gpurun_out/bench_p$n.json 2> gpurun_out/bench_p$n.err; python - <<P
+(time timeout 1200 python -m pytest tests -m gpu -x -q) > gpurun_out/final_gputest.log 2>&1; tail -3 gpurun_out/final_gputest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; python - <<P
 import json
-d = json.load(open("gpurun_out/bench_p$n.json"))
-print($n, d["ms_per_step"], d["e2e"]["single_job_ms"], d["e2e"]["single_job_pipelined"], d["roofline"]["traffic"])
+d = json.load(open("gpurun_out/final_bench.json"))
+print(d["ms_per_step"], d["value"], d["e2e"], d["roofline"]["frac"], d["roofline"]["traffic"], d["clocks"], d["cpu_baseline"]["value"], d["output_digest"]["matches_oracle"])
 P
-done
