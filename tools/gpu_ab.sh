@@ -1,9 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
 (time timeout 1200 python -m pytest tests -m gpu -x -q) > gpurun_out/final_gputest.log 2>&1; tail -3 gpurun_out/final_gputest.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; python - <<P
 import json
 d = json.load(open("gpurun_out/final_bench.json"))
-print(d["ms_per_step"], d["value"], d["e2e"], d["roofline"]["frac"], d["roofline"]["traffic"], d["clocks"], d["cpu_baseline"]["value"], d["output_digest"]["matches_oracle"])
+print(d["ms_per_step"], d["value"], d["e2e"], d["roofline"]["frac"], d["roofline"]["traffic"], d["clocks"], d["output_digest"]["matches_oracle"])
 P
+bash tools/prof_launches.sh final
+python tools/feature_cost.py > gpurun_out/feature_cost.json 2> gpurun_out/feature_cost.err

@@ -215,7 +215,13 @@ __device__ __forceinline__ void msel_grouped(const KeyCols& in, const GroupLanes
 // kMergeTile wide and lie in cache lines the previous search just touched.  The kernel is one chain of dependent loads per warp
 // (about 135 for the two-level search, 55 for every further boundary), so the chunk is small: measured on the cfg2 job (18.7 k
 // boundaries) 433 us with 4 boundaries per warp, 379 us with 3, 428 us with 2 (profiles/README.md).
-__global__ void __launch_bounds__(128)
+// 12 CTAs (48 warps) per SM: 42 registers with a small spill, but all of a job's warps are resident at once -- the kernel is one
+// chain of dependent loads per warp, so residency is what counts (cfg2: 288 us against 375 us with the 64 registers ptxas takes
+// unasked; 10 CTAs: 394 us).
+#ifndef B200C_PART_MIN_CTAS
+#define B200C_PART_MIN_CTAS 12
+#endif
+__global__ void __launch_bounds__(128, B200C_PART_MIN_CTAS)
 merge_partition_grouped_kernel(KeyCols in, RunBounds runs, uint32_t nruns, uint32_t gshift, uint64_t n_total,
                                uint64_t ntiles, uint64_t* __restrict__ splits, uint32_t* __restrict__ err, uint32_t chunk) {
   const unsigned lane = threadIdx.x & 31;
