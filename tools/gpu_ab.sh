@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; python - <<P
 import json
 d = json.load(open("gpurun_out/final_bench.json"))
-print(d["ms_per_step"], d["value"], d["e2e"], d["roofline"]["frac"], d["roofline"]["traffic"], d["clocks"], d["output_digest"]["matches_oracle"])
+k = {x["name"]: x["us"] for x in d["kernels"]}
+print(d["ms_per_step"], d["value"], d["stage_us"], "stitch", k.get("~encode.stitch"), "tables", k.get("encode.tables"), d["e2e"], d["roofline"]["frac"], d["clocks"], d["output_digest"]["matches_oracle"])
 P
 bash tools/prof_launches.sh final
-python tools/feature_cost.py > gpurun_out/feature_cost.json 2> gpurun_out/feature_cost.err
