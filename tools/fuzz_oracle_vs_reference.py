@@ -1,6 +1,6 @@
 """Random cross-check of the CPU oracle against the compiled reference (oracle/_ref): scenarios of tests/scenarios.py re-seeded at random,
 with random table options (block size, restart interval, format_version 3-5, checksum), a Bloom filter policy at random bits per key,
-random target file sizes, SingleDelete scenarios included.  Every run compares all output files byte for byte and the job statistics.
+random target file sizes, SingleDelete scenarios and zlib-compressed inputs included.  Every run compares all output files byte for byte and the job statistics.
 `python tools/fuzz_oracle_vs_reference.py [seconds] [seed]`; the run recorded in DESIGN.md: 1500 s, seed 777 -> 16 244 jobs, 0 mismatches.
 `python tools/fuzz_oracle_vs_reference.py [seconds] [seed] picker`: jobs the DB's own picker builds (DB::CompactRange: grandparents
 attached) with 1-8 sub-compactions and a random filter policy, every sub-compaction range checked on its own (files + statistics);
@@ -54,12 +54,12 @@ def main():
     rnd = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 777)
     if len(sys.argv) > 3 and sys.argv[3] == "picker":
         return picker_jobs(budget, rnd)
-    names = [n for n in S.ALL if n != "long_keys"] + ["single_deletes", "single_deletes_nonbottom"]
+    names = [n for n in S.ALL if n != "long_keys"] + ["single_deletes", "single_deletes_nonbottom"] + list(S.ZLIB)
     runs = bad = 0
     t0 = time.time()
     while time.time() - t0 < budget:
         name, seed = rnd.choice(names), rnd.randrange(1000, 100000)
-        fn = S.ALL.get(name) or S.ORACLE_ONLY[name]
+        fn = S.ALL.get(name) or S.ORACLE_ONLY.get(name) or S.ZLIB[name]
         try:
             ops, opts = fn(seed=seed)
         except TypeError:
@@ -71,6 +71,8 @@ def main():
             table["bloom_bits"] = rnd.choice([1, 4.5, 10, 12.5, 20, 33])
         if "target_file_size" in opts and rnd.random() < 0.5:
             opts["target_file_size"] = rnd.choice([8 << 10, 20 << 10, 64 << 10, 300 << 10])
+        if name in S.ZLIB and rnd.random() < 0.3:
+            opts["index_compression"] = 0
         opts = dict(opts, **table)
         ref = H.run_reference(ops, **opts)
         p = H.params_from_reference(ref)
