@@ -59,6 +59,22 @@ def test_ranges_reach_the_c_abi():
             assert s[k] == parents[-1][k], k
 
 
+def test_ranges_are_dealt_to_the_listed_devices():
+    """B200CompactOptions::devices = {0, 1}: every device in use gets its own parent (= its own copy of the inputs), the ranges go to
+    the devices round-robin"""
+    ops, opts = S.ALL["cfg3_mini"]()
+    opts = dict(opts, max_subcompactions=4, b200_devices="0,1")
+    k0, k1 = b"\x00" * 7 + b"\x40", b"\x00" * 7 + b"\x80"
+    jobs, man, _, err = _run_mock(ops, opts, dict(B200C_MOCK_BOUNDARIES=f"{k0.hex()},{k1.hex()}"), "b200+fallback")
+    want_inputs = sorted(m["file_number"] for m in man["inputs"])
+    mine = [j for j in jobs if j["output_level"] == man["output_level"]]
+    parents = [j for j in mine if sorted(i["file_number"] for i in j["inputs"]) == want_inputs and not (j["has_range_start"] or j["has_range_end"])]
+    subs = [j for j in mine if not j["inputs"] and (j["has_range_start"] or j["has_range_end"])]
+    assert "split into 3 key ranges over 2 device(s)" in err
+    assert sorted(p["device"] for p in parents[-2:]) == [0, 1]
+    assert [s["device"] for s in subs] == [0, 1, 0]
+
+
 def test_a_job_that_must_not_be_split_stays_whole():
     ops, opts = S.ALL["cfg3_mini"]()
     jobs, man, _, err = _run_mock(ops, dict(opts, max_subcompactions=1), dict(B200C_MOCK_BOUNDARIES="0000000000000040"), "b200+fallback")
