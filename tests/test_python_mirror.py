@@ -57,3 +57,44 @@ def test_keyword_arguments_arrive_in_the_c_struct(tmp_path):
     assert (j["level_compaction_dynamic_file_size"], j["max_compaction_bytes"], j["target_output_file_size"]) == (0, 777, 61728)
     assert (j["has_range_start"], j["has_range_end"], j["paranoid_file_checks"], j["bloom_millibits_per_key"]) == (1, 1, 1, 9500)
     assert j["inputs"] == [{"level": 0, "file_number": 31, "len": 100, "mem_kind": 0}, {"level": 2, "file_number": 12, "len": 50, "mem_kind": 0}]
+
+
+CHILD_RANGES = textwrap.dedent("""
+    import json, os, sys
+    sys.path.insert(0, {root!r})
+    import toplingdb_b200.native as N
+    N.LIB_PATH, N._lib = {so!r}, None
+    import toplingdb_b200 as T
+    parent = T.CompactionJob(output_level=2, block_size=1024, db_session_id="S", first_file_number=5)
+    parent.add_input(b"x" * 64, level=0, file_number=1, deferred=True)
+    bounds = parent.plan_ranges(4, min_range_bytes=10)
+    print("BOUNDS", [b.hex() for b in bounds])
+    parent.upload_by_ranges(bounds)
+    subs = [parent.sub_job(range_start=a, range_end=b, first_file_number=100 * (i + 1))
+            for i, (a, b) in enumerate(zip([None] + bounds, bounds + [None]))]
+    for j in subs:
+        j.close()
+    parent.close()
+""")
+
+
+def test_sub_job_and_range_calls_marshal_their_keys(tmp_path):
+    """plan_ranges / upload_by_ranges / sub_job: boundary keys with embedded zero bytes and different lengths travel as 16-byte slots +
+    lengths; a sub-job inherits its parent's keyword arguments, takes its own range and file numbers; a deferred host input is added
+    with B200C_MEM_HOST_DEFERRED"""
+    so = str(tmp_path / "libmock.so")
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-std=c11", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "native", "mock_b200c.c"), "-o", so])
+    dump = str(tmp_path / "dump.jsonl")
+    k0, k1 = b"a\x00b", b"a\x00b\x00\x00c" + b"\xff" * 10
+    r = subprocess.run([sys.executable, "-c", CHILD_RANGES.format(root=ROOT, so=so)], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, B200C_MOCK_DUMP=dump, B200C_MOCK_BOUNDARIES=f"{k0.hex()},{k1.hex()}"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.split("BOUNDS ")[1].strip() == str([k0.hex(), k1.hex()])
+    jobs = [json.loads(line) for line in open(dump).read().splitlines()]
+    subs = [j for j in jobs if j["has_range_start"] or j["has_range_end"]]
+    parent = [j for j in jobs if j["inputs"]][0]
+    assert parent["inputs"] == [{"level": 0, "file_number": 1, "len": 64, "mem_kind": 2}]
+    assert [(s["range_start"], s["range_end"], s["first_file_number"]) for s in subs] == \
+           [("", k0.hex(), 100), (k0.hex(), k1.hex(), 200), (k1.hex(), "", 300)]
+    assert all((s["output_level"], s["block_size"], s["db_session_id"]) == (2, 1024, "S") for s in subs)
